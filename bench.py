@@ -1,0 +1,350 @@
+#!/usr/bin/env python
+"""bench.py — frames/s tracked @752x480 (kNN match + GN pose solve) on synthetic EuRoC-shaped data.
+
+Contract (driver):  python bench.py --gpus N --steps K --warmup W [--impl reference]
+  * a "step" = one pass of the frame-tracking hot path over the whole workload: BASELINE.json configs[1],
+    a 2000-frame 752x480 sequence, 1000 ORB descriptors per frame, 200 Hz gyro prior — 1999 frame pairs —
+    pyramid -> Hamming kNN-2 (both directions) -> ratio/symmetry/grid filter -> candidates -> 4-level GN.
+  * value   = frames/s with the sequence already resident in HBM (CUDA events on the launching stream).
+  * e2e     = the same pass through the host-buffer C-ABI entry (vsb_track_sequence_host): pinned host
+              frames/descriptors/key points/priors in, poses out, H2D and D2H inside the timed region.
+  * N > 1   = N independent replicas (one process per GPU, different sequence seed per rank), no
+              data-path collective ("replicas only"); torch.distributed is used only for
+              the barrier and the max-over-ranks of the timed region.
+  * --impl reference = the CPU oracle (restatement of the reference's algorithm; the reference itself
+              needs OpenCV 3.2 + ROS and cannot be built here) on all host threads, bounded sample.
+One JSON line on stdout (rank 0).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for _p in (ROOT, os.path.join(ROOT, "vi-slam_b200")):
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
+
+import numpy as np  # noqa: E402
+
+W, H, N_FEAT, N_FRAMES, N_CELLS = 752, 480, 1000, 2000, 49
+METRIC = "frames/s tracked @752x480 (kNN match + GN pose solve)"
+WORKLOAD = ("configs[1]: synthetic EuRoC MH-like sequence 752x480, 2000 frames, 1000 ORB features/frame, "
+            "200 Hz IMU prior, num_cells=49, GN levels 3->0")
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+# ----------------------------------------------------------------------------------------------- data
+def make_data(n_frames, seed, device):
+    from vislam_b200 import synth
+    import vislam_b200 as vb
+    import ctypes as C
+    t0 = time.time()
+    seq = synth.make_sequence(n_frames, w=W, h=H, n_feat=N_FEAT, seed=seed, device=device)
+    prior = np.zeros((n_frames - 1, 7), np.float32)
+    eye = (C.c_float * 9)(1, 0, 0, 0, 1, 0, 0, 0, 1)
+    out = (C.c_float * 7)()
+    for k in range(n_frames - 1):   # initial pose exactly as VISystem.cpp:1135-1168 forms it (host helper of the C ABI)
+        r = (C.c_float * 9)(*[float(x) for x in seq["R_imu_res"][k].reshape(-1)])
+        t = (C.c_float * 3)(*[float(x) for x in seq["t_res"][k]])
+        vb.lib().vsb_initial_pose(eye, r, t, out)
+        prior[k] = out[:]
+    seq["prior"] = prior
+    log(f"[bench] synthetic sequence: {n_frames} frames in {time.time() - t0:.1f}s")
+    return seq
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu, self.proc, self.lines = gpu_index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._pump, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ----------------------------------------------------------------------------------------------- CPU oracle timing
+def cpu_track_sample(seq, pair_ids, threads):
+    """Times the CPU oracle (oracle/libvso.so — test infrastructure, used here only as the measured CPU
+    baseline) on a bounded sample of frame pairs, `threads` pairs in flight."""
+    from concurrent.futures import ThreadPoolExecutor
+    from oracle import vso
+    vso.lib()
+    K = seq["K"]
+
+    def one(k):
+        r = vso.track_pair(seq["frames"][k], seq["frames"][k + 1], seq["desc"][k], seq["desc"][k + 1],
+                           seq["kp"][k], K, seq["prior"][k], n_cells=N_CELLS)
+        return r["pose"]
+
+    t0 = time.perf_counter()
+    if threads <= 1:
+        poses = [one(k) for k in pair_ids]
+    else:
+        with ThreadPoolExecutor(threads) as ex:
+            poses = list(ex.map(one, pair_ids))
+    dt = time.perf_counter() - t0
+    return len(pair_ids) / dt, dt, poses
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the reference's CPU algorithm (oracle port) on all host threads, bounded sample."""
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    n_sample = int(os.environ.get("VSB_REF_SAMPLE_PAIRS", "48"))
+    seq = make_data(n_sample + 1, 2001, None)
+    ids = list(range(n_sample))
+    for _ in range(args.warmup):
+        cpu_track_sample(seq, ids[: max(cores, 4)], cores)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        cpu_track_sample(seq, ids, cores)
+    dt = (time.perf_counter() - t0) / args.steps
+    fps = n_sample / dt
+    sample = f"{n_sample} consecutive frame pairs of the same synthetic sequence per step, {cores} pairs in flight"
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "u8/int32 Hamming + f32 GN (f64 accumulate)",
+        "data": "synthetic",
+        "config": {"workload": WORKLOAD, "sample": sample},
+        "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }), flush=True)
+
+
+# ----------------------------------------------------------------------------------------------- GPU arm
+def run_gpu(args, rank, world, local_rank):
+    import torch
+    import vislam_b200 as vb
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    n_frames = int(os.environ.get("VSB_BENCH_FRAMES", str(N_FRAMES)))
+    chunk = int(os.environ.get("VSB_BENCH_CHUNK", "500"))
+    grad_mode = int(os.environ.get("VSB_GRAD_MODE", "0"))
+    seq = make_data(n_frames, 2001 + 1000 * rank, dev)
+    n_pairs = n_frames - 1
+    ctx = vb.Context(local_rank)
+    tr = ctx.tracker(W, H, N_FEAT, seq["K"], n_cells=N_CELLS, max_pairs=chunk,
+                     gn_opts=vb.default_gn_opts(grad_mode=grad_mode))
+    # host (pinned) and device copies of the inputs
+    h = {k: torch.from_numpy(np.ascontiguousarray(seq[k])).pin_memory() for k in ("frames", "desc", "kp", "prior")}
+    d = {k: v.to(dev) for k, v in h.items()}
+    d_pose = torch.zeros((n_pairs, 7), dtype=torch.float32, device=dev)
+    d_ng = torch.zeros((n_pairs,), dtype=torch.int32, device=dev)
+    h_pose = torch.zeros((n_pairs, 7), dtype=torch.float32).pin_memory()
+    h_ng = torch.zeros((n_pairs,), dtype=torch.int32).pin_memory()
+    stream = torch.cuda.current_stream(dev)
+
+    def step_device():
+        for p0 in range(0, n_pairs, chunk):
+            p1 = min(p0 + chunk, n_pairs)
+            tr.track_sequence(d["frames"][p0:p1 + 1], d["desc"][p0:p1 + 1], d["kp"][p0:p1 + 1], d["prior"][p0:p1],
+                              pose=d_pose[p0:p1], n_good=d_ng[p0:p1], stream=stream)
+
+    def step_host():
+        tr.track_sequence_host(h["frames"], h["desc"], h["kp"], h["prior"], h_pose, h_ng)
+
+    # ---- device-resident timing ("value") ------------------------------------------------------------
+    for _ in range(args.warmup):
+        step_device()
+    barrier()
+    tr.stats()
+    ctx.profile(True)
+    launches0 = ctx.launches
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record(stream)
+    for _ in range(args.steps):
+        step_device()
+    ev1.record(stream)
+    barrier()
+    ms = ev0.elapsed_time(ev1)
+    clocks = sampler.stop()
+    launches = ctx.launches - launches0
+    prof = ctx.profile_read()
+    ctx.profile(False)
+    stats = tr.stats()
+    t_ms = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if dist is not None:
+        dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
+    ms_max = float(t_ms.item())
+    ms_per_step = ms_max / args.steps
+    value = world * n_pairs / (ms_per_step * 1e-3)
+
+    # ---- end-to-end timing through the host-buffer entry ("e2e") -------------------------------------
+    for _ in range(max(1, min(args.warmup, 2))):
+        step_host()
+    barrier()
+    t0 = time.perf_counter()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(args.steps):
+        step_host()      # synchronous: returns when the poses are in host memory
+    e1.record(stream)
+    barrier()
+    e2e_ms = (time.perf_counter() - t0) * 1e3
+    t_e = torch.tensor([e2e_ms], dtype=torch.float64, device=dev)
+    if dist is not None:
+        dist.all_reduce(t_e, op=dist.ReduceOp.MAX)
+    e2e_ms_step = float(t_e.item()) / args.steps
+    e2e_value = world * n_pairs / (e2e_ms_step * 1e-3)
+    h2d = sum(int(h[k].numel() * h[k].element_size()) for k in ("frames", "desc", "kp", "prior"))
+    n_chunks = (n_pairs + chunk - 1) // chunk
+    h2d += (n_chunks - 1) * (W * H + N_FEAT * 32 + N_FEAT * 8)    # the frame shared by two chunks is sent twice
+    d2h = int(h_pose.numel() * 4 + h_ng.numel() * 4)
+    same = bool(torch.equal(h_pose.to(dev), d_pose))
+
+    if rank != 0:
+        return
+    # ---- roofline of every kernel, the dominant one reported in "roofline" ---------------------------
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    hbm_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6.65 TB/s"
+    popc_peak = ctx.popc_peak() / 1e9     # GPOPC/s, microbenchmarked on this GPU
+    lay = vb.pyr_layout(W, H)
+    px_all = sum(lay.w[l] * lay.h[l] for l in range(lay.levels))
+    px_gn = sum(lay.w[l] * lay.h[l] for l in range(4))
+    steps = args.steps
+    pairs_total = stats["pairs"]
+    alg = {
+        # 8*N*M 32-bit POPC per frame pair, one distance matrix for both directions
+        "knn2_hamming": ("int", 8.0 * N_FEAT * N_FEAT * pairs_total, "GPOPC/s", popc_peak,
+                         "measured by vsb_popc_peak on this GPU"),
+        # 14 B per candidate point per iteration + one-time staging of cur I, prev I, gx, gy (6 B/px, levels 0-3)
+        "gn_solve": ("hbm", 14.0 * stats["point_visits"] + 6.0 * px_gn * pairs_total, "GB/s", hbm_peak, hbm_src),
+        # read w*h, write every level (level 0 is copied, as the reference's Camera::Update does)
+        "pyramid": ("hbm", (W * H + px_all) * (pairs_total + steps * n_chunks), "GB/s", hbm_peak, hbm_src),
+        # read every level once, write gx and gy (int16) for the previous frame of every pair
+        "gradient": ("hbm", 5.0 * px_all * pairs_total, "GB/s", hbm_peak, hbm_src),
+    }
+    total_prof_ms = sum(v[0] for v in prof.values()) or 1.0
+    kernels = []
+    for name, (kms, n) in sorted(prof.items(), key=lambda kv: -kv[1][0]):
+        ent = {"kernel": name, "ms_per_step": kms / steps, "launches_per_step": n / steps,
+               "share": kms / total_prof_ms}
+        if name in alg:
+            bound, work, unit, peak, src = alg[name]
+            ach = work / (kms * 1e-3) / 1e9
+            ent.update({"bound": bound, "achieved": ach, "peak": peak, "unit": unit, "frac": ach / peak,
+                        "peak_source": src, "traffic": None})
+        kernels.append(ent)
+    dom = next((k for k in kernels if "bound" in k), None)
+    roofline = None
+    if dom:
+        roofline = {"kernel": dom["kernel"], "bound": dom["bound"], "achieved": dom["achieved"], "peak": dom["peak"],
+                    "unit": dom["unit"], "frac": dom["frac"], "traffic": dom["traffic"],
+                    "peak_source": dom["peak_source"], "share_of_step": dom["share"]}
+
+    # ---- CPU baseline: the oracle on this box's host cores, bounded sample --------------------------
+    cores = os.cpu_count() or 1
+    n_sample = int(os.environ.get("VSB_CPU_SAMPLE_PAIRS", "32"))
+    ids = list(range(min(n_sample, n_pairs)))
+    cpu_fps1, cpu_dt1, cpu_poses = cpu_track_sample(seq, ids, 1)
+    dpose = np.stack(cpu_poses) - d_pose[: len(ids)].cpu().numpy()
+    parity = float(np.abs(dpose).max())
+    out = {
+        "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "u8/int32 Hamming + f32 GN (f64 accumulate)", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "frames": n_frames, "pairs_per_step": n_pairs, "chunk_pairs": chunk,
+                   "grad_mode": grad_mode, "parallelism": f"replicas x{world}" if world > 1 else "single GPU",
+                   "l2_policy": "inputs larger than L2 (722 MB of frames per step), no flush needed",
+                   "gn_iterations_per_pair": stats["iterations"] / max(1, pairs_total),
+                   "gn_points_per_pair": stats["point_visits"] / max(1, pairs_total)},
+        "e2e": {"value": e2e_value, "unit": "frames/s", "ms_per_step": e2e_ms_step, "h2d_bytes_per_step": h2d,
+                "d2h_bytes_per_step": d2h, "matches_device_path": same},
+        "gpu_launches": int(launches),
+        "clocks": clocks,
+        "roofline": roofline,
+        "kernels": kernels,
+        "cpu_baseline": {"value": cpu_fps1, "unit": "frames/s", "cores": 1, "kind": "port",
+                         "sample": f"first {len(ids)} frame pairs of the same sequence, oracle single thread "
+                                   f"({cpu_dt1:.1f}s); box has {cores} host cores",
+                         "max_abs_pose_diff_vs_gpu": parity},
+    }
+    print(json.dumps(out), flush=True)
+    tr.close()
+    ctx.close()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+    run_gpu(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,229 @@
+/*
+ * vislam_b200.h — C ABI of the B200-native frame-tracking path (libvislam_b200.so).
+ *
+ * This is the drop-in boundary for the hot path of MecatronicaUSB/vi-slam: the reference has no FFI,
+ * its "operator API" is the C++ classes Matcher / Camera / VISystem.  The class mirrors
+ * in vi-slam_b200/host/ call ONLY the functions declared here; each entry cites the reference code it
+ * replaces (file:line under the reference tree).
+ *
+ * Conventions
+ *   - every function returns an int status: 0 = VSB_OK, negative = error (vsb_error_string()).
+ *   - pointers are DEVICE pointers unless the parameter name starts with h_ (host, ideally pinned).
+ *   - `stream` is a cudaStream_t passed as void* (NULL = default stream).  Calls are asynchronous on
+ *     that stream unless documented otherwise; no hidden host synchronisation.
+ *   - batched calls process `count` independent frame pairs laid out with uniform strides; per-problem
+ *     feature counts may be given as device int32 arrays (NULL = every problem uses the max count).
+ *   - pose layout: {qx, qy, qz, qw, tx, ty, tz} float32 (Sophus::SE3f storage order).
+ *   - there is no CPU fallback: without a CUDA device every compute entry returns VSB_ERR_CUDA.
+ */
+#ifndef VISLAM_B200_H_
+#define VISLAM_B200_H_
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VSB_OK 0
+#define VSB_ERR_INVALID (-1)     /* bad argument */
+#define VSB_ERR_CUDA (-2)        /* CUDA runtime error (see vsb_last_cuda_error) */
+#define VSB_ERR_UNSUPPORTED (-3) /* mode not implemented */
+#define VSB_ERR_CAPACITY (-4)    /* a size exceeds a compiled-in or context limit */
+
+#define VSB_MAX_LEVELS 5         /* Frame keeps 5 pyramid levels, Camera.hpp:46 */
+#define VSB_MAX_GN_FEATURES 200  /* Camera.cpp:382 */
+#define VSB_MAX_TRACE 64
+
+typedef struct vsb_ctx vsb_ctx_t;
+
+/* ---- context ------------------------------------------------------------------------------------ */
+int vsb_version(void);
+const char* vsb_error_string(int status);
+int vsb_ctx_create(int device, vsb_ctx_t** ctx);
+int vsb_ctx_destroy(vsb_ctx_t* ctx);
+const char* vsb_last_cuda_error(vsb_ctx_t* ctx);
+int vsb_sm_count(vsb_ctx_t* ctx);
+/* number of kernels this context has launched so far (bench.py's gpu_launches) */
+long long vsb_launch_count(vsb_ctx_t* ctx);
+
+/* Optional per-kernel timing: CUDA events recorded on the launching stream around every kernel launch.
+ * kernel ids are 0 .. vsb_kernel_count()-1 (vsb_kernel_name).  vsb_profile_read synchronises on the events
+ * recorded so far and returns the accumulated device time and launch count of one kernel. */
+int vsb_kernel_count(void);
+const char* vsb_kernel_name(int kernel_id);
+int vsb_profile_enable(vsb_ctx_t* ctx, int on);
+int vsb_profile_reset(vsb_ctx_t* ctx);
+int vsb_profile_read(vsb_ctx_t* ctx, int kernel_id, double* total_ms, long long* launches);
+/* INT-pipe ceiling of this GPU, measured: 32-bit POPC (independent chains, all SMs) per second. */
+int vsb_popc_peak(vsb_ctx_t* ctx, double* popc_per_s, void* stream);
+
+/* ---- Matcher ------------------------------------------------------------------------------------ */
+/* Replaces Matcher::computeMatches (src/Matcher.cpp:83-94) / MatcherGPU::computeGPUMatches
+ * (src/MatcherGPU.cpp:44-66) with BFMatcher(NORM_HAMMING): both knnMatch(...,2) calls from ONE
+ * pass over the distance matrix.
+ *   d1: [count][n1_max][32] u8 (previous key-frame descriptors), d2: [count][n2_max][32] u8.
+ *   n1/n2: optional device int32[count] with the true row counts (<= max).
+ *   idx12/dist12: [count][n1_max][2] (neighbours of d1 rows in d2); idx21/dist21: [count][n2_max][2].
+ * Order: (distance asc, train index asc) — bit-exact with cv::BFMatcher incl. ties; slots without a
+ * neighbour (fewer than 2 train rows) get idx = -1, dist = 0.  dist holds the integer popcount as float. */
+int vsb_knn2_hamming(vsb_ctx_t* ctx, const uint8_t* d1, int n1_max, const int32_t* n1,
+                     const uint8_t* d2, int n2_max, const int32_t* n2, int count,
+                     int32_t* idx12, float* dist12, int32_t* idx21, float* dist21, void* stream);
+
+/* Same for float descriptors, BFMatcher(NORM_L2) (Matcher.cpp:55): dim floats per row,
+ * distance = sqrtf(sum (a-b)^2). */
+int vsb_knn2_l2(vsb_ctx_t* ctx, const float* d1, int n1_max, const int32_t* n1,
+                const float* d2, int n2_max, const int32_t* n2, int dim, int count,
+                int32_t* idx12, float* dist12, int32_t* idx21, float* dist21, void* stream);
+
+/* Replaces Matcher::computeBestMatches + getGoodMatches (Matcher.cpp:353-367, 295-303):
+ * nnFilter (ratio), symmetry test, sort by y, sqrt(n_cells) x sqrt(n_cells) grid best.
+ *   kp1_xy: [count][n1_max][2] f32 key-point coordinates of the previous key frame.
+ *   sym_mode: 0 de-facto reference behaviour (2->1 ratio test has no effect, App. B-1), 1 intended.
+ *   good_q/good_t/good_d: [count][good_cap]; n_good, n_sym: [count].  Order = reference order
+ *   (band-major, column-minor).  good_cap must be >= floor(sqrt(n_cells))^2. */
+int vsb_match_filter(vsb_ctx_t* ctx, const int32_t* idx12, const float* dist12, int n1_max, const int32_t* n1,
+                     const int32_t* idx21, const float* dist21, int n2_max, const int32_t* n2,
+                     const float* kp1_xy, int count, int w, int h, int n_cells, float ratio, int sym_mode,
+                     int32_t* good_q, int32_t* good_t, float* good_d, int good_cap,
+                     int32_t* n_good, int32_t* n_sym, void* stream);
+
+/* ---- Camera ------------------------------------------------------------------------------------- */
+typedef struct {
+    int levels;                       /* <= VSB_MAX_LEVELS */
+    int w[VSB_MAX_LEVELS], h[VSB_MAX_LEVELS];
+    int64_t offset[VSB_MAX_LEVELS];   /* pixel offset of level l inside one frame's packed pyramid (level 0 = 0) */
+    int64_t frame_stride;             /* pixels per frame in the packed pyramid (256-aligned) */
+} vsb_pyr_layout_t;
+
+/* Packed-pyramid layout for a w x h frame: level sizes follow cv::resize(0.5) (cvRound), Camera.cpp:68-70. */
+int vsb_pyr_layout(int w, int h, int levels, vsb_pyr_layout_t* out);
+
+/* Replaces Camera::Update (Camera.cpp:63-72): builds levels 0..levels-1 of `count` frames.
+ *   img: [count] frames, row pitch `pitch` bytes, frame stride `img_stride` bytes.
+ *   pyr: [count][layout.frame_stride] u8 (level 0 is copied, as the reference does). */
+int vsb_pyramid_build(vsb_ctx_t* ctx, const uint8_t* img, int64_t img_stride, int pitch, int count,
+                      const vsb_pyr_layout_t* layout, uint8_t* pyr, void* stream);
+
+/* Replaces Camera::computeGradient (Camera.cpp:167-184): Scharr x/y, scale 3, CV_16S, reflect-101, every level.
+ *   gx, gy: [count][layout.frame_stride] int16;  gmag (optional, may be NULL): |gx|/2+|gy|/2 u8 image. */
+int vsb_gradient_build(vsb_ctx_t* ctx, const uint8_t* pyr, int count, const vsb_pyr_layout_t* layout,
+                       int16_t* gx, int16_t* gy, uint8_t* gmag, void* stream);
+
+/* Replaces Camera::ObtainPatchesPointsPreviousFrame (Camera.cpp:358-409).
+ *   good_xy: [count][good_cap][2] f32 level-0 key points (prev.nextGoodMatches), n_good: [count].
+ *   lw/lh: Camera::w_size/h_size tables (w>>l, Camera.cpp:44-47).
+ *   cand: [count][levels][cand_cap][4] f32 rows (x, y, 1, 1) = Frame::candidatePoints; n_cand: [count][levels].
+ *   cand_cap >= 121 * min(max n_good, 200). */
+int vsb_candidates_build(vsb_ctx_t* ctx, const float* good_xy, int good_cap, const int32_t* n_good, int count,
+                         int levels, const int* lw, const int* lh,
+                         float* cand, int cand_cap, int32_t* n_cand, void* stream);
+
+/* Gathers key points of the good matches (Matcher::getGoodMatches, Matcher.cpp:295-303):
+ * out_xy[c][m] = kp_xy[c][good_idx[c][m]]. */
+int vsb_gather_keypoints(vsb_ctx_t* ctx, const float* kp_xy, int n_max, const int32_t* good_idx, int good_cap,
+                         const int32_t* n_good, int count, float* out_xy, void* stream);
+
+/* ---- VISystem ----------------------------------------------------------------------------------- */
+typedef struct {
+    float fx, fy, cx, cy, invfx, invfy;
+    int w, h;   /* InitializePyramid's size table (w>>l); image rows/cols come from the pyramid layout */
+} vsb_intr_t;
+
+/* Replaces VISystem::InitializePyramid (VISystem.cpp:1451-1493) — host-side, no device work. */
+int vsb_init_pyramid(int w, int h, float fx, float fy, float cx, float cy, vsb_intr_t out[VSB_MAX_LEVELS]);
+
+typedef struct {
+    int first_lvl;       /* 3      VISystem.cpp:1119 */
+    int last_lvl;        /* 0      VISystem.cpp:1120 */
+    int max_iterations;  /* 10     VISystem.cpp:1117 */
+    float epsilon;       /* 0.001  VISystem.cpp:1115 */
+    float z_factor;      /* 0.002  VISystem.cpp:1121 */
+    int weight_mode;     /* 0 identity (reference, :1343)   2 Huber (north-star extension) */
+    int sample_mode;     /* 0 nearest round() (reference, :1321)   1 bilinear (north-star extension) */
+    float huber_k;
+    int grad_mode;       /* 0 read gx/gy images   1 Scharr evaluated on the fly from the previous image */
+    int accum_mode;      /* 0 FP64 accumulation of exact FP32 products (parity default)
+                            1 FP32 per-thread partials, FP64 across threads (north-star wording) */
+} vsb_gn_opts_t;
+void vsb_gn_default_opts(vsb_gn_opts_t* o);
+
+typedef struct {
+    int lvl, iter, n_valid, updated;
+    float error;
+    float pose[7];
+    float delta[6];
+} vsb_gn_trace_t;
+
+/* Replaces VISystem::EstimatePoseFeatures (VISystem.cpp:1113-1448) incl. WarpFunctionSE3 (:1495-1558),
+ * IdentityWeights (:1561-1565) and the Sophus SE3f update (se3.hpp:723-742, 285-321), for `count`
+ * independent frame pairs, one thread block per pair, all levels and iterations inside the kernel.
+ *   prev_pyr/cur_pyr: packed pyramids of the previous / current frame of pair c at
+ *                     base + c * pair_stride_pixels (so consecutive frames of a sequence can be
+ *                     addressed with prev = pyr, cur = pyr + frame_stride, pair stride = frame_stride).
+ *   prev_gx/prev_gy : packed gradients of the previous frame (may be NULL when grad_mode == 1).
+ *   cand/n_cand     : as produced by vsb_candidates_build.
+ *   pose_in/pose_out: [count][7].   trace (optional): [count][VSB_MAX_TRACE], n_trace: [count]. */
+int vsb_gn_solve(vsb_ctx_t* ctx, const uint8_t* prev_pyr, const uint8_t* cur_pyr,
+                 const int16_t* prev_gx, const int16_t* prev_gy, int64_t pair_stride_pixels,
+                 const vsb_pyr_layout_t* layout, const float* cand, int cand_cap, const int32_t* n_cand,
+                 const vsb_intr_t K[VSB_MAX_LEVELS], const float* pose_in, const vsb_gn_opts_t* opts, int count,
+                 float* pose_out, vsb_gn_trace_t* trace, int32_t* n_trace, void* stream);
+
+/* Initial pose exactly as VISystem.cpp:1135-1168 forms it (host-side helper):
+ * pose0 = SE3(RPY2rotationMatrix(-rotationMatrix2RPY(imu2cam^T * R_imu_res * imu2cam)), -t_res). */
+int vsb_initial_pose(const float imu2cam[9], const float r_imu_res[9], const float t_res[3], float pose[7]);
+/* Sophus SE3f group product as VISystem::Track uses it (VISystem.cpp:1599; se3.hpp:285-321). Host-side. */
+int vsb_se3_mul(const float a[7], const float b[7], float out[7]);
+
+/* ---- whole tracking step ------------------------------------------------------------------------ */
+typedef struct {
+    int w, h, n_feat_max, desc_bytes;   /* desc_bytes = 32 (ORB).  float descriptors: desc_bytes = 4*dim */
+    int norm;                           /* 1 Hamming, 0 L2 */
+    int n_cells;                        /* calibration `num_cells` (49 in calibrationEUROC.xml:54) */
+    float ratio;                        /* 0.8f, Matcher.cpp:103 */
+    int sym_mode;
+    float fx, fy, cx, cy;
+    vsb_gn_opts_t gn;
+    int max_pairs;                      /* capacity of one tracker batch */
+} vsb_tracker_cfg_t;
+typedef struct vsb_tracker vsb_tracker_t;
+
+/* A tracker owns the device scratch for `max_pairs` frame pairs (pyramids, kNN results, matches,
+ * candidates) so the whole loop of VISystemGPU::AddFrameGPU (VISystemGPU.cpp:144-169) —
+ * Update -> computeGPUGoodMatches -> computeGradient -> ObtainPatchesPointsPreviousFrame ->
+ * EstimatePoseFeatures — runs without returning to the host between stages. */
+int vsb_tracker_create(vsb_ctx_t* ctx, const vsb_tracker_cfg_t* cfg, vsb_tracker_t** out);
+int vsb_tracker_destroy(vsb_tracker_t* t);
+
+/* Work counters of the solver since the last call (then reset): out[0] = frame pairs solved,
+ * out[1] = GN iterations (error evaluations), out[2] = sum over iterations of the candidate points visited
+ * (SURVEY.md §8d's  sum_l K_l * P_l), out[3] = symmetric matches found.  Synchronises the device. */
+int vsb_tracker_stats(vsb_tracker_t* t, long long out[4]);
+
+/* Tracks `n_frames - 1` consecutive pairs of a sequence resident on the DEVICE.
+ *   frames [n_frames][h][w] u8, desc [n_frames][n_feat_max][desc_bytes], kp_xy [n_frames][n_feat_max][2] f32,
+ *   n_feat (optional) int32[n_frames], pose_prior [n_frames-1][7].
+ *   Outputs: pose [n_frames-1][7] (relative pose prev->cur of every pair), n_good (optional) [n_frames-1].
+ * n_frames - 1 <= cfg.max_pairs. */
+int vsb_track_sequence(vsb_tracker_t* t, const uint8_t* frames, const uint8_t* desc, const float* kp_xy,
+                       const int32_t* n_feat, const float* pose_prior, int n_frames,
+                       float* pose, int32_t* n_good, void* stream);
+
+/* Same with HOST buffers (the end-to-end entry the class mirrors and bench.py's e2e leg use): frames,
+ * descriptors, key points and priors are copied host->device in chunks of cfg.max_pairs pairs on two
+ * streams so the copy of chunk i+1 overlaps the kernels of chunk i; poses are copied back.
+ * Synchronous: returns when h_pose is complete. */
+int vsb_track_sequence_host(vsb_tracker_t* t, const uint8_t* h_frames, const uint8_t* h_desc,
+                            const float* h_kp_xy, const int32_t* h_n_feat, const float* h_pose_prior,
+                            int n_frames, float* h_pose, int32_t* h_n_good);
+
+/* Tracks `count` independent frame pairs resident on the DEVICE (BASELINE config 5):
+ *   prev/cur [count][h][w] u8, d1/d2 [count][n_feat_max][desc_bytes], kp1 [count][n_feat_max][2]. */
+int vsb_track_pairs(vsb_tracker_t* t, const uint8_t* prev, const uint8_t* cur, const uint8_t* d1,
+                    const uint8_t* d2, const float* kp1_xy, const int32_t* n1, const int32_t* n2,
+                    const float* pose_prior, int count, float* pose, int32_t* n_good, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

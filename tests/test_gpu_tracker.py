@@ -1,0 +1,71 @@
+"""GPU parity of the whole tracking step (vsb_track_pairs / vsb_track_sequence / _host) vs the oracle's
+track_pair: match -> candidates -> GN chained on the device without host round trips."""
+import numpy as np
+import pytest
+
+from test_gpu_gn import TOL, rot_angle
+
+pytestmark = pytest.mark.gpu
+
+
+def _prior(vb_mod, R_res, t_res):
+    import ctypes as C
+    out = (C.c_float * 7)()
+    eye = (C.c_float * 9)(1, 0, 0, 0, 1, 0, 0, 0, 1)
+    r = (C.c_float * 9)(*[float(x) for x in np.asarray(R_res, np.float32).reshape(-1)])
+    t = (C.c_float * 3)(*[float(x) for x in t_res])
+    assert vb_mod.lib().vsb_initial_pose(eye, r, t, out) == 0
+    return np.array(out[:], np.float32)
+
+
+@pytest.mark.parametrize("n_cells", [49, 225])
+def test_track_pairs_vs_oracle(ctx, oracle, n_cells):
+    import torch
+    from vislam_b200 import synth
+    pairs = [synth.make_pair(n_feat=400, seed=s) for s in (1001, 1777)]
+    tr = ctx.tracker(752, 480, 400, pairs[0]["K"], n_cells=n_cells, max_pairs=4)
+    st = lambda k, dt=None: torch.from_numpy(np.stack([p[k] for p in pairs])).cuda()
+    pose, n_good = tr.track_pairs(st("prev"), st("cur"), st("d1"), st("d2"), st("kp1"), st("pose_prior"))
+    torch.cuda.synchronize()
+    pose, n_good = pose.cpu().numpy(), n_good.cpu().numpy()
+    for b, p in enumerate(pairs):
+        ref = oracle.track_pair(p["prev"], p["cur"], p["d1"], p["d2"], p["kp1"], p["K"], p["pose_prior"], n_cells=n_cells)
+        assert n_good[b] == len(ref["good_q"])
+        assert rot_angle(pose[b][:4], ref["pose"][:4]) <= TOL
+        assert np.abs(pose[b][4:] - ref["pose"][4:]).max() <= TOL
+    tr.close()
+
+
+@pytest.mark.parametrize("grad_mode", [0, 1])
+def test_track_sequence_device_and_host(ctx, oracle, grad_mode):
+    """A 6-frame synthetic sequence: device-resident entry, host entry (chunked, two streams) and the oracle agree."""
+    import torch
+    import vislam_b200 as vb
+    from vislam_b200 import synth
+    T, N = 6, 300
+    seq = synth.make_sequence(T, n_feat=N, seed=2001)
+    prior = np.stack([_prior(vb, seq["R_imu_res"][k], seq["t_res"][k]) for k in range(T - 1)])
+    for k in range(T - 1):   # the product's host helper and the oracle form the same initial pose
+        np.testing.assert_array_equal(prior[k], oracle.initial_pose(np.eye(3), seq["R_imu_res"][k], seq["t_res"][k]))
+    tr = ctx.tracker(752, 480, N, seq["K"], n_cells=49, max_pairs=2, gn_opts=vb.default_gn_opts(grad_mode=grad_mode))
+    frames, desc, kp = seq["frames"], seq["desc"], seq["kp"]
+    # host entry: 5 pairs with max_pairs = 2 -> three chunks over two slots
+    pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
+    h_pose = torch.zeros((T - 1, 7), dtype=torch.float32).pin_memory()
+    h_ng = torch.zeros((T - 1,), dtype=torch.int32).pin_memory()
+    tr.track_sequence_host(pin(frames), pin(desc), pin(kp), pin(prior), h_pose, h_ng)
+    # device entry, 2 pairs at a time
+    dev = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()
+    d_pose = []
+    for k in range(0, T - 1, 2):
+        e = min(k + 3, T)
+        pz, _ = tr.track_sequence(dev(frames[k:e]), dev(desc[k:e]), dev(kp[k:e]), dev(prior[k:e - 1]))
+        d_pose.append(pz.cpu().numpy())
+    d_pose = np.concatenate(d_pose)
+    np.testing.assert_array_equal(d_pose, h_pose.numpy())
+    for k in range(T - 1):
+        ref = oracle.track_pair(frames[k], frames[k + 1], desc[k], desc[k + 1], kp[k], seq["K"], prior[k], n_cells=49)
+        assert h_ng[k] == len(ref["good_q"])
+        assert rot_angle(h_pose[k][:4].numpy(), ref["pose"][:4]) <= TOL
+        assert np.abs(h_pose[k][4:].numpy() - ref["pose"][4:]).max() <= TOL
+    tr.close()

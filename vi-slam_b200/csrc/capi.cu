@@ -1,0 +1,213 @@
+// capi.cu — context management and the host-side helpers of the C ABI (no device work here).
+// vsb_init_pyramid restates VISystem::InitializePyramid (reference src/VISystem.cpp:1451-1493);
+// vsb_initial_pose restates VISystem.cpp:1135-1168 with Plus.cpp:56-83 (rotationMatrix2RPY) and
+// Plus.cpp:182-220 (RPY2rotationMatrix); vsb_se3_mul is Sophus SE3f::operator* (se3.hpp:285-321).
+#include "common.cuh"
+#include "se3.cuh"
+
+#define VSB_VERSION 100
+
+extern "C" int vsb_version(void) { return VSB_VERSION; }
+
+extern "C" const char* vsb_error_string(int status) {
+    switch (status) {
+        case VSB_OK: return "ok";
+        case VSB_ERR_INVALID: return "invalid argument";
+        case VSB_ERR_CUDA: return "CUDA runtime error";
+        case VSB_ERR_UNSUPPORTED: return "unsupported mode";
+        case VSB_ERR_CAPACITY: return "capacity exceeded";
+        default: return "unknown status";
+    }
+}
+
+extern "C" int vsb_ctx_create(int device, vsb_ctx_t** out) {
+    if (!out) return VSB_ERR_INVALID;
+    *out = nullptr;
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev <= 0 || device < 0 || device >= ndev) return VSB_ERR_CUDA;  // no CPU fallback
+    if (cudaSetDevice(device) != cudaSuccess) return VSB_ERR_CUDA;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return VSB_ERR_CUDA;
+    vsb_ctx* c = new vsb_ctx();
+    c->device = device;
+    c->sm_count = prop.multiProcessorCount;
+    c->launches = 0;
+    c->last_error[0] = 0;
+    c->scratch = nullptr;
+    c->scratch_bytes = 0;
+    c->prof_on = 0;
+    for (int i = 0; i < VSB_K_COUNT; i++) { c->prof_ms[i] = 0.0; c->prof_n[i] = 0; }
+    *out = c;
+    return VSB_OK;
+}
+
+extern "C" int vsb_ctx_destroy(vsb_ctx_t* ctx) {
+    if (!ctx) return VSB_ERR_INVALID;
+    if (ctx->scratch) cudaFree(ctx->scratch);
+    for (auto& r : ctx->prof_pending) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
+    for (auto e : ctx->prof_free) cudaEventDestroy(e);
+    delete ctx;
+    return VSB_OK;
+}
+
+extern "C" const char* vsb_last_cuda_error(vsb_ctx_t* ctx) { return ctx ? ctx->last_error : ""; }
+extern "C" int vsb_sm_count(vsb_ctx_t* ctx) { return ctx ? ctx->sm_count : 0; }
+extern "C" long long vsb_launch_count(vsb_ctx_t* ctx) { return ctx ? ctx->launches : 0; }
+
+int vsb_scratch_reserve(vsb_ctx* ctx, size_t bytes, void** out) {
+    if (bytes > ctx->scratch_bytes) {
+        if (ctx->scratch) VSB_CUDA(ctx, cudaFree(ctx->scratch));   // cudaFree synchronises: no kernel still uses it
+        ctx->scratch = nullptr;
+        ctx->scratch_bytes = 0;
+        size_t want = bytes + bytes / 4;
+        VSB_CUDA(ctx, cudaMalloc(&ctx->scratch, want));
+        ctx->scratch_bytes = want;
+    }
+    *out = ctx->scratch;
+    return VSB_OK;
+}
+
+extern "C" int vsb_init_pyramid(int w, int h, float fx, float fy, float cx, float cy, vsb_intr_t out[VSB_MAX_LEVELS]) {
+    if (!out || w <= 0 || h <= 0) return VSB_ERR_INVALID;
+    out[0].w = w; out[0].h = h;
+    out[0].fx = fx; out[0].fy = fy; out[0].cx = cx; out[0].cy = cy;
+    out[0].invfx = F_DIV(1.f, fx);                                           // VISystem.cpp:1463
+    out[0].invfy = F_DIV(1.f, fy);
+    for (int lvl = 1; lvl < VSB_MAX_LEVELS; lvl++) {
+        out[lvl].w = w >> lvl;                                               // :1468
+        out[lvl].h = h >> lvl;
+        out[lvl].fx = (float)((double)out[lvl - 1].fx * 0.5);                // :1470
+        out[lvl].fy = (float)((double)out[lvl - 1].fy * 0.5);
+        out[lvl].cx = (float)(((double)cx + 0.5) / (double)(1 << lvl) - 0.5);  // :1472
+        out[lvl].cy = (float)(((double)cy + 0.5) / (double)(1 << lvl) - 0.5);
+        out[lvl].invfx = F_DIV(1.f, out[lvl].fx);                            // :1481
+        out[lvl].invfy = F_DIV(1.f, out[lvl].fy);
+    }
+    return VSB_OK;
+}
+
+static void mat33_mul(const float* a, const float* b, float* c) {
+    for (int i = 0; i < 3; i++)
+        for (int j = 0; j < 3; j++)
+            c[3 * i + j] = vsb::dot3(a[3 * i], b[j], a[3 * i + 1], b[3 + j], a[3 * i + 2], b[6 + j]);
+}
+
+static void rot_to_quat(const float* m, float* q) {   // Eigen Quaternion(Matrix3)
+    float t = F_ADD(F_ADD(m[0], m[4]), m[8]);
+    if (t > 0.0f) {
+        t = F_SQRT(F_ADD(t, 1.0f));
+        q[3] = F_MUL(0.5f, t);
+        t = F_DIV(0.5f, t);
+        q[0] = F_MUL(F_SUB(m[7], m[5]), t);
+        q[1] = F_MUL(F_SUB(m[2], m[6]), t);
+        q[2] = F_MUL(F_SUB(m[3], m[1]), t);
+    } else {
+        int i = 0;
+        if (m[4] > m[0]) i = 1;
+        if (m[8] > m[4 * i]) i = 2;
+        const int j = (i + 1) % 3, k = (j + 1) % 3;
+        t = F_SQRT(F_ADD(F_SUB(F_SUB(m[4 * i], m[4 * j]), m[4 * k]), 1.0f));
+        q[i] = F_MUL(0.5f, t);
+        t = F_DIV(0.5f, t);
+        q[3] = F_MUL(F_SUB(m[3 * k + j], m[3 * j + k]), t);
+        q[j] = F_MUL(F_ADD(m[3 * j + i], m[3 * i + j]), t);
+        q[k] = F_MUL(F_ADD(m[3 * k + i], m[3 * i + k]), t);
+    }
+}
+
+extern "C" int vsb_initial_pose(const float imu2cam[9], const float r_imu_res[9], const float t_res[3], float pose[7]) {
+    if (!imu2cam || !r_imu_res || !t_res || !pose) return VSB_ERR_INVALID;
+    const float it[9] = {imu2cam[0], imu2cam[3], imu2cam[6], imu2cam[1], imu2cam[4], imu2cam[7],
+                         imu2cam[2], imu2cam[5], imu2cam[8]};
+    float tmp[9], rc[9], r0[9];
+    mat33_mul(it, r_imu_res, tmp);      // imu2camRotation.t() * residual_rotationMatrix * imu2camRotation, :1135
+    mat33_mul(tmp, imu2cam, rc);
+    // rotationMatrix2RPY (Plus.cpp:56-83), negated, RPY2rotationMatrix (Plus.cpp:182-220, VISystem.cpp:1146)
+    const double r11 = rc[0], r21 = rc[3], r31 = rc[6], r32 = rc[7], r33 = rc[8];
+    const double yaw = -atan2(r21, r11);
+    const double pitch = -atan2(-r31, sqrt(r32 * r32 + r33 * r33));
+    const double roll = -atan2(r32, r33);
+    const double c1 = cos(roll), s1 = sin(roll), c2 = cos(pitch), s2 = sin(pitch), c3 = cos(yaw), s3 = sin(yaw);
+    r0[0] = (float)(c3 * c2); r0[1] = (float)(c3 * s2 * s1 - s3 * c1); r0[2] = (float)(c3 * s2 * c1 + s3 * s1);
+    r0[3] = (float)(s3 * c2); r0[4] = (float)(s3 * s2 * s1 + c3 * c1); r0[5] = (float)(s3 * s2 * c1 - c3 * s1);
+    r0[6] = (float)(-s2);     r0[7] = (float)(c2 * s1);                r0[8] = (float)(c2 * c1);
+    rot_to_quat(r0, pose);              // SE3(rotationEigen, Point(-sx,-sy,-sz)), :1162
+    pose[4] = -t_res[0]; pose[5] = -t_res[1]; pose[6] = -t_res[2];
+    return VSB_OK;
+}
+
+extern "C" int vsb_se3_mul(const float a[7], const float b[7], float out[7]) {
+    if (!a || !b || !out) return VSB_ERR_INVALID;
+    float tmp[7];
+    vsb::se3_mul(a, b, tmp);
+    for (int i = 0; i < 7; i++) out[i] = tmp[i];
+    return VSB_OK;
+}
+
+// ---- per-kernel timing with CUDA events on the launching stream (bench.py's roofline leg) --------------
+static cudaEvent_t prof_event(vsb_ctx* ctx) {
+    if (!ctx->prof_free.empty()) {
+        cudaEvent_t e = ctx->prof_free.back();
+        ctx->prof_free.pop_back();
+        return e;
+    }
+    cudaEvent_t e = nullptr;
+    cudaEventCreate(&e);
+    return e;
+}
+
+int vsb_prof_begin(vsb_ctx* ctx, int id, cudaStream_t st) {
+    vsb_prof_rec r;
+    r.id = id;
+    r.a = prof_event(ctx);
+    r.b = prof_event(ctx);
+    cudaEventRecord(r.a, st);
+    ctx->prof_pending.push_back(r);
+    return (int)ctx->prof_pending.size() - 1;
+}
+
+void vsb_prof_end(vsb_ctx* ctx, int slot, cudaStream_t st) { cudaEventRecord(ctx->prof_pending[slot].b, st); }
+
+static const char* kKernelNames[VSB_K_COUNT] = {"knn2_hamming", "knn_unpack", "match_filter", "gather_keypoints",
+                                                "pyramid", "gradient", "candidates", "gn_solve", "knn2_l2",
+                                                "knn2_l2_prep"};
+
+extern "C" int vsb_kernel_count(void) { return VSB_K_COUNT; }
+extern "C" const char* vsb_kernel_name(int id) { return (id >= 0 && id < VSB_K_COUNT) ? kKernelNames[id] : ""; }
+
+extern "C" int vsb_profile_enable(vsb_ctx_t* ctx, int on) {
+    if (!ctx) return VSB_ERR_INVALID;
+    ctx->prof_on = on ? 1 : 0;
+    return VSB_OK;
+}
+
+// Folds every finished event pair into the per-kernel totals (synchronises on the recorded events).
+static int prof_collect(vsb_ctx* ctx) {
+    for (auto& r : ctx->prof_pending) {
+        VSB_CUDA(ctx, cudaEventSynchronize(r.b));
+        float ms = 0.f;
+        VSB_CUDA(ctx, cudaEventElapsedTime(&ms, r.a, r.b));
+        ctx->prof_ms[r.id] += ms;
+        ctx->prof_n[r.id] += 1;
+        ctx->prof_free.push_back(r.a);
+        ctx->prof_free.push_back(r.b);
+    }
+    ctx->prof_pending.clear();
+    return VSB_OK;
+}
+
+extern "C" int vsb_profile_reset(vsb_ctx_t* ctx) {
+    if (!ctx) return VSB_ERR_INVALID;
+    int rc = prof_collect(ctx);
+    for (int i = 0; i < VSB_K_COUNT; i++) { ctx->prof_ms[i] = 0.0; ctx->prof_n[i] = 0; }
+    return rc;
+}
+
+extern "C" int vsb_profile_read(vsb_ctx_t* ctx, int kernel_id, double* total_ms, long long* launches) {
+    if (!ctx || kernel_id < 0 || kernel_id >= VSB_K_COUNT) return VSB_ERR_INVALID;
+    int rc = prof_collect(ctx);
+    if (total_ms) *total_ms = ctx->prof_ms[kernel_id];
+    if (launches) *launches = ctx->prof_n[kernel_id];
+    return rc;
+}

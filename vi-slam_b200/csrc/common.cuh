@@ -1,0 +1,65 @@
+// common.cuh — shared host-side plumbing of libvislam_b200.so (context, status codes, launch accounting).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "../../include/vislam_b200.h"
+
+#include <vector>
+
+enum vsb_kernel_id {
+    VSB_K_KNN_HAMMING = 0, VSB_K_KNN_UNPACK, VSB_K_MATCH_FILTER, VSB_K_GATHER, VSB_K_PYRAMID, VSB_K_GRADIENT,
+    VSB_K_CANDIDATES, VSB_K_GN_SOLVE, VSB_K_KNN_L2, VSB_K_KNN_L2_PREP, VSB_K_COUNT
+};
+
+struct vsb_prof_rec { int id; cudaEvent_t a, b; };
+
+struct vsb_ctx {
+    int device;
+    int sm_count;
+    long long launches;
+    char last_error[256];
+    // scratch owned by the context (grown on demand, freed in vsb_ctx_destroy)
+    void* scratch;
+    size_t scratch_bytes;
+    // optional per-kernel timing with CUDA events on the launching stream (bench.py's roofline leg)
+    int prof_on;
+    std::vector<vsb_prof_rec> prof_pending;
+    std::vector<cudaEvent_t> prof_free;
+    double prof_ms[VSB_K_COUNT];
+    long long prof_n[VSB_K_COUNT];
+};
+
+int vsb_prof_begin(vsb_ctx* ctx, int id, cudaStream_t st);
+void vsb_prof_end(vsb_ctx* ctx, int slot, cudaStream_t st);
+
+struct ProfScope {
+    vsb_ctx* c; int slot; cudaStream_t st;
+    ProfScope(vsb_ctx* ctx, int id, cudaStream_t s) : c(ctx), slot(-1), st(s) { if (c && c->prof_on) slot = vsb_prof_begin(c, id, st); }
+    ~ProfScope() { if (slot >= 0) vsb_prof_end(c, slot, st); }
+};
+
+static inline int vsb_cuda_fail(vsb_ctx* ctx, cudaError_t e, const char* what) {
+    if (ctx) snprintf(ctx->last_error, sizeof(ctx->last_error), "%s: %s", what, cudaGetErrorString(e));
+    return VSB_ERR_CUDA;
+}
+
+#define VSB_CUDA(ctx, call)                                              \
+    do {                                                                 \
+        cudaError_t e__ = (call);                                        \
+        if (e__ != cudaSuccess) return vsb_cuda_fail((ctx), e__, #call); \
+    } while (0)
+
+// every kernel launch goes through this so bench.py can report gpu_launches truthfully
+#define VSB_LAUNCHED(ctx)                                                          \
+    do {                                                                           \
+        (ctx)->launches++;                                                         \
+        cudaError_t e__ = cudaGetLastError();                                      \
+        if (e__ != cudaSuccess) return vsb_cuda_fail((ctx), e__, "kernel launch"); \
+    } while (0)
+
+int vsb_scratch_reserve(vsb_ctx* ctx, size_t bytes, void** out);
+
+static inline int vsb_div_up(int a, int b) { return (a + b - 1) / b; }

@@ -1,0 +1,195 @@
+// match_filter.cu — ratio test, symmetry test, sort-by-y and grid-best selection on the device, one CTA per
+// frame pair.  Replaces Matcher::computeBestMatches + getGoodMatches (reference src/Matcher.cpp:353-367,
+// 96-169, 171-244, 295-303, 329-352) so descriptors -> GN never returns to the host.
+//
+// The reference's sequential band sweep over y-sorted matches is order-equivalent to: every symmetric match
+// falls into cell (band, column) given by the float-accumulated band/column edges, and each cell keeps the
+// match that is smallest under (distance, y, queryIdx) — strict '<' in the sweep keeps the first of equal
+// distances, the sweep order is y ascending with ties in match (= queryIdx) order.  Cells are emitted
+// band-major, column-minor.  That form needs no sort and is bit-identical to the sweep.
+#include "common.cuh"
+
+namespace {
+
+constexpr int FT = 256;
+constexpr int MAX_ROOT = 64;  // floor(sqrt(n_cells)) <= 64
+
+__device__ __forceinline__ uint32_t float_order_bits(float v) {
+    uint32_t b = __float_as_uint(v);
+    return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+
+__global__ void __launch_bounds__(FT)
+match_filter_kernel(const int32_t* __restrict__ idx12, const float* __restrict__ dist12, int n1_max,
+                    const int32_t* __restrict__ n1_arr, const int32_t* __restrict__ idx21,
+                    const float* __restrict__ dist21, int n2_max, const int32_t* __restrict__ n2_arr,
+                    const float* __restrict__ kp1_xy, int w, int h, int n_cells, float ratio_f, int sym_mode,
+                    int32_t* __restrict__ good_q, int32_t* __restrict__ good_t, float* __restrict__ good_d,
+                    int good_cap, int32_t* __restrict__ n_good, int32_t* __restrict__ n_sym) {
+    extern __shared__ unsigned char smem_raw[];
+    const int prob = blockIdx.x;
+    const int tid = threadIdx.x;
+    const int n1 = n1_arr ? min(n1_arr[prob], n1_max) : n1_max;
+    const int n2 = n2_arr ? min(n2_arr[prob], n2_max) : n2_max;
+    const int32_t* i12 = idx12 + (size_t)prob * n1_max * 2;
+    const float* d12 = dist12 + (size_t)prob * n1_max * 2;
+    const int32_t* i21 = idx21 + (size_t)prob * n2_max * 2;
+    const float* d21 = dist21 + (size_t)prob * n2_max * 2;
+    const float* kp = kp1_xy + (size_t)prob * n1_max * 2;
+
+    const int root = (int)floor(sqrt((double)n_cells));         // Matcher.cpp:191
+    const int ncell = root * root;
+    int16_t* s_cell = reinterpret_cast<int16_t*>(smem_raw);     // [n1_max] cell of row i, -1 = no symmetric match
+    uint32_t* s_best = reinterpret_cast<uint32_t*>(smem_raw + (((size_t)n1_max * 2 + 15) & ~(size_t)15)); // [ncell]
+    __shared__ float s_hf[MAX_ROOT], s_wf[MAX_ROOT];
+    __shared__ int s_nsym, s_base;
+    __shared__ int s_warp_cnt[FT / 32];
+
+    if (tid == 0) {
+        s_nsym = 0;
+        s_base = 0;
+        float winW = (float)((double)w / floor(sqrt((double)n_cells)));   // Matcher.cpp:177
+        float winH = (float)((double)h / floor(sqrt((double)n_cells)));   // Matcher.cpp:178
+        float hf = winH, wf = winW;
+        for (int k = 0; k < root; k++) {
+            s_hf[k] = hf; s_wf[k] = wf;
+            hf = __fadd_rn(hf, winH);                                     // Matcher.cpp:236
+            wf = __fadd_rn(wf, winW);                                     // Matcher.cpp:213
+        }
+    }
+    for (int c = tid; c < ncell; c += FT) s_best[c] = 0xFFFFFFFFu;
+    __syncthreads();
+
+    const double ratio = (double)ratio_f;                                  // Matcher.cpp:103
+    // ---- pass 0: ratio + symmetry, cell of every surviving row, per-cell min distance -----------------
+    int my_sym = 0;
+    for (int i = tid; i < n1; i += FT) {
+        int cell = -1;
+        const int j0 = i12[2 * i], j1 = i12[2 * i + 1];
+        const float dd0 = d12[2 * i], dd1 = d12[2 * i + 1];
+        bool keep = (j0 >= 0 && j1 >= 0) && !((double)dd0 > ratio * (double)dd1);   // Matcher.cpp:153-166
+        if (keep && j0 < n2) {
+            const int b0 = i21[2 * j0], b1 = i21[2 * j0 + 1];
+            bool ok = (b0 >= 0);
+            if (sym_mode == 1)   // intended: the 2->1 row must survive its own ratio test
+                ok = ok && (b1 >= 0) && !((double)d21[2 * j0] > ratio * (double)d21[2 * j0 + 1]);
+            if (ok && b0 == i) { // Matcher.cpp:124-125
+                my_sym++;
+                const float x = kp[2 * i], y = kp[2 * i + 1];
+                int band = -1;
+                for (int k = 0; k < root; k++) if (y <= s_hf[k]) { band = k; break; }   // Matcher.cpp:205
+                if (band >= 0) {
+                    int col = 0;
+                    while (col < root && x > s_wf[col]) col++;                          // Matcher.cpp:211-216
+                    if (col >= root) col = root - 1;                                    // App. B-13
+                    cell = band * root + col;
+                    if (dd0 < 100000.0f) atomicMin(&s_best[cell], __float_as_uint(dd0)); // Matcher.cpp:218
+                    else cell = -1;
+                }
+            }
+        }
+        s_cell[i] = (int16_t)cell;
+    }
+    if (my_sym) atomicAdd(&s_nsym, my_sym);
+    __syncthreads();
+    // ---- pass 1/2: among rows at the cell's min distance keep the smallest y, then the smallest index --
+    // (s_best is reused: distance bits -> y order bits -> row index, each pass filtering on the previous)
+    uint32_t* s_y = s_best + ncell;     // [ncell]
+    uint32_t* s_i = s_y + ncell;        // [ncell]
+    for (int c = tid; c < ncell; c += FT) { s_y[c] = 0xFFFFFFFFu; s_i[c] = 0xFFFFFFFFu; }
+    __syncthreads();
+    for (int i = tid; i < n1; i += FT) {
+        int cell = s_cell[i];
+        if (cell >= 0 && __float_as_uint(d12[2 * i]) == s_best[cell])
+            atomicMin(&s_y[cell], float_order_bits(kp[2 * i + 1]));
+    }
+    __syncthreads();
+    for (int i = tid; i < n1; i += FT) {
+        int cell = s_cell[i];
+        if (cell >= 0 && __float_as_uint(d12[2 * i]) == s_best[cell] &&
+            float_order_bits(kp[2 * i + 1]) == s_y[cell])
+            atomicMin(&s_i[cell], (uint32_t)i);
+    }
+    __syncthreads();
+    // ---- emit non-empty cells band-major / column-minor (Matcher.cpp:232-233, 318-326) ---------------
+    int32_t* gq = good_q + (size_t)prob * good_cap;
+    int32_t* gt = good_t + (size_t)prob * good_cap;
+    float* gd = good_d + (size_t)prob * good_cap;
+    for (int c0 = 0; c0 < ncell; c0 += FT) {
+        const int c = c0 + tid;
+        const bool full = (c < ncell) && (s_i[c] != 0xFFFFFFFFu);
+        const unsigned ballot = __ballot_sync(0xffffffffu, full);
+        const int lane = tid & 31, wid = tid >> 5;
+        if (lane == 0) s_warp_cnt[wid] = __popc(ballot);
+        __syncthreads();
+        int off = s_base;
+        for (int k = 0; k < wid; k++) off += s_warp_cnt[k];
+        off += __popc(ballot & ((1u << lane) - 1u));
+        if (full && off < good_cap) {
+            const int i = (int)s_i[c];
+            gq[off] = i;
+            gt[off] = i12[2 * i];
+            gd[off] = d12[2 * i];
+        }
+        __syncthreads();
+        if (tid == 0) {
+            int tot = 0;
+            for (int k = 0; k < FT / 32; k++) tot += s_warp_cnt[k];
+            s_base += tot;
+        }
+        __syncthreads();
+    }
+    if (tid == 0) {
+        n_good[prob] = min(s_base, good_cap);
+        if (n_sym) n_sym[prob] = s_nsym;
+    }
+}
+
+__global__ void gather_keypoints_kernel(const float2* __restrict__ kp, int n_max, const int32_t* __restrict__ good,
+                                        int good_cap, const int32_t* __restrict__ n_good, float2* __restrict__ out) {
+    const int prob = blockIdx.x;
+    const int m = blockIdx.y * blockDim.x + threadIdx.x;
+    if (m >= good_cap) return;
+    const int n = min(n_good[prob], good_cap);
+    float2 v = make_float2(0.f, 0.f);
+    if (m < n) v = kp[(size_t)prob * n_max + good[(size_t)prob * good_cap + m]];
+    out[(size_t)prob * good_cap + m] = v;
+}
+
+}  // namespace
+
+extern "C" int vsb_match_filter(vsb_ctx_t* ctx, const int32_t* idx12, const float* dist12, int n1_max,
+                                const int32_t* n1, const int32_t* idx21, const float* dist21, int n2_max,
+                                const int32_t* n2, const float* kp1_xy, int count, int w, int h, int n_cells,
+                                float ratio, int sym_mode, int32_t* good_q, int32_t* good_t, float* good_d,
+                                int good_cap, int32_t* n_good, int32_t* n_sym, void* stream) {
+    if (!ctx || count < 0 || n_cells < 1 || n1_max < 0 || n2_max < 0 || !n_good) return VSB_ERR_INVALID;
+    if (count == 0) return VSB_OK;
+    const int root = (int)floor(sqrt((double)n_cells));
+    if (root > MAX_ROOT || n1_max > 32767 * 2) return VSB_ERR_CAPACITY;
+    if (root * root > 32767) return VSB_ERR_CAPACITY;
+    if (good_cap < root * root) return VSB_ERR_INVALID;
+    size_t smem = (((size_t)n1_max * 2 + 15) & ~(size_t)15) + (size_t)root * root * 3 * sizeof(uint32_t);
+    if (smem > 200 * 1024) return VSB_ERR_CAPACITY;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (smem > 48 * 1024)
+        VSB_CUDA(ctx, cudaFuncSetAttribute(match_filter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    ProfScope ps(ctx, VSB_K_MATCH_FILTER, st);
+    match_filter_kernel<<<count, FT, smem, st>>>(idx12, dist12, n1_max, n1, idx21, dist21, n2_max, n2, kp1_xy, w, h,
+                                                  n_cells, ratio, sym_mode, good_q, good_t, good_d, good_cap, n_good,
+                                                  n_sym);
+    VSB_LAUNCHED(ctx);
+    return VSB_OK;
+}
+
+extern "C" int vsb_gather_keypoints(vsb_ctx_t* ctx, const float* kp_xy, int n_max, const int32_t* good_idx,
+                                    int good_cap, const int32_t* n_good, int count, float* out_xy, void* stream) {
+    if (!ctx || count < 0 || good_cap < 0) return VSB_ERR_INVALID;
+    if (count == 0 || good_cap == 0) return VSB_OK;
+    dim3 grid(count, vsb_div_up(good_cap, 128));
+    ProfScope ps(ctx, VSB_K_GATHER, (cudaStream_t)stream);
+    gather_keypoints_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(
+        reinterpret_cast<const float2*>(kp_xy), n_max, good_idx, good_cap, n_good, reinterpret_cast<float2*>(out_xy));
+    VSB_LAUNCHED(ctx);
+    return VSB_OK;
+}

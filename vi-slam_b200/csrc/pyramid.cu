@@ -1,0 +1,291 @@
+// pyramid.cu — per-frame front end on the device: image pyramid, Scharr gradients, candidate patch points.
+// Replaces Camera::Update (reference src/Camera.cpp:63-72), Camera::computeGradient (:167-184) and
+// Camera::ObtainPatchesPointsPreviousFrame (:358-409).  All integer-exact, so results are bit-identical
+// to cv::resize(0.5) / cv::Scharr(scale 3) (checked against cv2 through the oracle).
+#include "common.cuh"
+
+namespace {
+
+// ---------------------------------------------------------------------------------------------- pyramid
+// One CTA cascades a 64x64 level-0 tile through all levels in shared memory: level l+1 pixel (x,y) is
+// the rounded mean of the level-l block (2x..2x+1, 2y..2y+1) clipped to the image, which is what
+// cv::resize(src, dst, Size(), 0.5, 0.5) computes (INTER_LINEAR at scale exactly 2 takes OpenCV's
+// area fast path; clipped blocks are averaged in float and rounded half-to-even).
+constexpr int PT = 64;
+
+struct PyrParams {
+    vsb_pyr_layout_t lay;
+};
+
+__device__ __forceinline__ uint8_t mean_clipped(int sum, int count) {
+    if (count == 4) return (uint8_t)((sum + 2) >> 2);
+    if (count == 0) return 0;
+    float v = __fdiv_rn((float)sum, (float)count);
+    return (uint8_t)min(__float2int_rn(v), 255);
+}
+
+__global__ void __launch_bounds__(256)
+pyramid_kernel(const uint8_t* __restrict__ img, long long img_stride, int pitch, PyrParams P,
+               uint8_t* __restrict__ pyr) {
+    __shared__ uint8_t s[2][PT * PT];
+    const vsb_pyr_layout_t& L = P.lay;
+    const int frame = blockIdx.z;
+    const int x0 = blockIdx.x * PT, y0 = blockIdx.y * PT;
+    uint8_t* out = pyr + (size_t)frame * L.frame_stride;
+    const uint8_t* in = img ? img + (size_t)frame * img_stride : out;  // img == NULL: level 0 already in place
+    const int in_pitch = img ? pitch : L.w[0];
+    const int tid = threadIdx.x;
+    const int w0 = L.w[0], h0 = L.h[0];
+
+    // level 0: load the tile (16 bytes per thread when aligned), copy it out unless it is in place
+    {
+        const int ty = tid >> 2, tx = (tid & 3) * 16;
+        const int gy = y0 + ty, gx = x0 + tx;
+        const bool vec_ok = ((in_pitch & 15) == 0) && ((w0 & 15) == 0) && ((((size_t)in) & 15) == 0);
+        if (gy < h0 && gx + 15 < w0 && vec_ok) {
+            uint4 v = __ldg(reinterpret_cast<const uint4*>(in + (size_t)gy * in_pitch + gx));
+            *reinterpret_cast<uint4*>(&s[0][ty * PT + tx]) = v;
+            if (img) *reinterpret_cast<uint4*>(out + (size_t)gy * w0 + gx) = v;
+        } else {
+            for (int k = 0; k < 16; k++) {
+                uint8_t v = 0;
+                if (gy < h0 && gx + k < w0) {
+                    v = __ldg(in + (size_t)gy * in_pitch + gx + k);
+                    if (img) out[(size_t)gy * w0 + gx + k] = v;
+                }
+                s[0][ty * PT + tx + k] = v;
+            }
+        }
+    }
+    __syncthreads();
+    int cur = 0;
+    int tw = PT;                         // tile extent at the current level
+    int lx0 = x0, ly0 = y0;              // tile origin at the current level
+    for (int l = 1; l < L.levels; l++) {
+        const int sw = L.w[l - 1], sh = L.h[l - 1];
+        const int dw = L.w[l], dh = L.h[l];
+        const int ntw = tw >> 1;
+        const int nx0 = lx0 >> 1, ny0 = ly0 >> 1;
+        uint8_t* dst = out + L.offset[l];
+        for (int p = tid; p < ntw * ntw; p += 256) {
+            const int py = p / ntw, px = p - py * ntw;
+            const int dx = nx0 + px, dy = ny0 + py;
+            uint8_t v = 0;
+            if (dx < dw && dy < dh) {
+                int sum = 0, cnt = 0;
+#pragma unroll
+                for (int sy = 0; sy < 2; sy++) {
+                    if (2 * dy + sy >= sh) break;
+#pragma unroll
+                    for (int sx = 0; sx < 2; sx++) {
+                        if (2 * dx + sx >= sw) break;
+                        sum += s[cur][(2 * py + sy) * tw + 2 * px + sx];
+                        cnt++;
+                    }
+                }
+                v = mean_clipped(sum, cnt);
+                dst[(size_t)dy * dw + dx] = v;
+            }
+            s[cur ^ 1][py * ntw + px] = v;
+        }
+        __syncthreads();
+        cur ^= 1; tw = ntw; lx0 = nx0; ly0 = ny0;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------- Scharr
+// cv::Scharr(src, dst, CV_16S, dx, dy, scale = 3, 0, BORDER_REFLECT_101): derivative [-1 0 1], smoothing
+// [3 10 3], times 3 (Camera.cpp:171-172; the literal 3 is `scale`).  One launch covers every
+// level of every frame; a CTA stages a (GW+2) x (GH+2) tile (reflected at the borders) in shared memory.
+constexpr int GW = 64, GH = 16;
+
+struct GradParams {
+    vsb_pyr_layout_t lay;
+    int tile_begin[VSB_MAX_LEVELS + 1];   // prefix of tiles per level
+    int tiles_x[VSB_MAX_LEVELS];
+};
+
+__device__ __forceinline__ int reflect101(int p, int len) {
+    if (len == 1) return 0;
+    if (p < 0) return -p;
+    if (p >= len) return 2 * len - 2 - p;
+    return p;
+}
+
+__global__ void __launch_bounds__(256)
+gradient_kernel(const uint8_t* __restrict__ pyr, GradParams P, int16_t* __restrict__ gx, int16_t* __restrict__ gy,
+                uint8_t* __restrict__ gmag) {
+    __shared__ uint8_t s[(GH + 2)][GW + 4];
+    const vsb_pyr_layout_t& L = P.lay;
+    int lvl = 0;
+    while (lvl + 1 < L.levels && (int)blockIdx.x >= P.tile_begin[lvl + 1]) lvl++;
+    const int t = blockIdx.x - P.tile_begin[lvl];
+    const int tyi = t / P.tiles_x[lvl], txi = t - tyi * P.tiles_x[lvl];
+    const int w = L.w[lvl], h = L.h[lvl];
+    const int x0 = txi * GW, y0 = tyi * GH;
+    const size_t base = (size_t)blockIdx.y * L.frame_stride + L.offset[lvl];
+    const uint8_t* src = pyr + base;
+    for (int p = threadIdx.x; p < (GH + 2) * (GW + 2); p += 256) {
+        const int py = p / (GW + 2), px = p - py * (GW + 2);
+        const int yy = reflect101(min(y0 + py - 1, h), h);
+        const int xx = reflect101(min(x0 + px - 1, w), w);
+        s[py][px] = __ldg(src + (size_t)yy * w + xx);
+    }
+    __syncthreads();
+    for (int p = threadIdx.x; p < GH * GW; p += 256) {
+        const int py = p / GW, px = p - py * GW;
+        const int x = x0 + px, y = y0 + py;
+        if (x >= w || y >= h) continue;
+        const int a00 = s[py][px], a01 = s[py][px + 1], a02 = s[py][px + 2];
+        const int a10 = s[py + 1][px], a12 = s[py + 1][px + 2];
+        const int a20 = s[py + 2][px], a21 = s[py + 2][px + 1], a22 = s[py + 2][px + 2];
+        const int dx = 3 * (a02 - a00) + 10 * (a12 - a10) + 3 * (a22 - a20);
+        const int dy = 3 * (a20 - a00) + 10 * (a21 - a01) + 3 * (a22 - a02);
+        const size_t o = base + (size_t)y * w + x;
+        const int vx = 3 * dx, vy = 3 * dy;
+        gx[o] = (int16_t)vx;
+        gy[o] = (int16_t)vy;
+        if (gmag) {   // convertScaleAbs + addWeighted(0.5, 0.5), Camera.cpp:174-180
+            float m = __fadd_rn(__fmul_rn((float)min(abs(vx), 255), 0.5f), __fmul_rn((float)min(abs(vy), 255), 0.5f));
+            gmag[o] = (uint8_t)min(__float2int_rn(m), 255);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------- candidates
+struct CandParams {
+    int levels;
+    int lw[VSB_MAX_LEVELS], lh[VSB_MAX_LEVELS];
+};
+
+__global__ void __launch_bounds__(256)
+candidates_kernel(const float* __restrict__ good_xy, int good_cap, const int32_t* __restrict__ n_good, CandParams P,
+                  float4* __restrict__ cand, int cand_cap, int32_t* __restrict__ n_cand) {
+    const int prob = blockIdx.x;
+    const int lvl = blockIdx.y;
+    const int tid = threadIdx.x;
+    __shared__ int s_cnt[256], s_off[257];
+    __shared__ int s_ia[256], s_ja[256], s_nj[256];
+    const int patch_size[VSB_MAX_LEVELS] = {5, 3, 2, 5, 5};              // Camera.cpp:369-373
+    const int nf = min(min(n_good[prob], good_cap), VSB_MAX_GN_FEATURES);  // Camera.cpp:382
+    const float factor_lvl = (float)(1.0 / (double)(1 << lvl));           // Camera.cpp:379
+    const int sp = patch_size[lvl] - 1 / 2;                               // Camera.cpp:381 (int division)
+    const int lw = P.lw[lvl], lh = P.lh[lvl];
+    int cnt = 0;
+    if (tid < nf) {
+        const float px = good_xy[((size_t)prob * good_cap + tid) * 2];
+        const float py = good_xy[((size_t)prob * good_cap + tid) * 2 + 1];
+        const float x = (float)(((double)px + 0.5) * (double)factor_lvl - 0.5);   // Camera.cpp:384
+        const float y = (float)(((double)py + 0.5) * (double)factor_lvl - 0.5);   // Camera.cpp:385
+        // for (int i = x - sp; i <= x + sp; i++): float -> int truncation, float compare (Camera.cpp:391-392)
+        const int i0 = (int)__fsub_rn(x, (float)sp), i1 = (int)floorf(__fadd_rn(x, (float)sp));
+        const int j0 = (int)__fsub_rn(y, (float)sp), j1 = (int)floorf(__fadd_rn(y, (float)sp));
+        const int ia = max(i0, 1), ib = min(i1, lw - 1);                  // 0 < i < w (Camera.cpp:393)
+        const int ja = max(j0, 1), jb = min(j1, lh - 1);
+        const int ni = max(ib - ia + 1, 0), nj = max(jb - ja + 1, 0);
+        cnt = ni * nj;
+        s_ia[tid] = ia; s_ja[tid] = ja; s_nj[tid] = nj;
+    }
+    s_cnt[tid] = cnt;
+    __syncthreads();
+    if (tid == 0) {
+        int acc = 0;
+        for (int f = 0; f < nf; f++) { s_off[f] = acc; acc += s_cnt[f]; }
+        s_off[nf] = acc;
+        n_cand[(size_t)prob * P.levels + lvl] = min(acc, cand_cap);
+    }
+    __syncthreads();
+    float4* out = cand + ((size_t)prob * P.levels + lvl) * cand_cap;
+    const int total = min(s_off[nf], cand_cap);
+    // one warp per feature: lanes stride over the feature's points (i outer, j inner — reference row order)
+    const int warp = tid >> 5, lane = tid & 31;
+    for (int f = warp; f < nf; f += 8) {
+        const int c = s_cnt[f], off = s_off[f], nj = s_nj[f], ia = s_ia[f], ja = s_ja[f];
+        for (int p = lane; p < c; p += 32) {
+            if (off + p >= total) break;
+            const int ii = p / nj, jj = p - ii * nj;
+            out[off + p] = make_float4((float)(ia + ii), (float)(ja + jj), 1.0f, 1.0f);
+        }
+    }
+}
+
+}  // namespace
+
+static int round_half_even_half(int v) {  // cvRound(v * 0.5)
+    int k = v >> 1;
+    return (v & 1) ? k + (k & 1) : k;
+}
+
+extern "C" int vsb_pyr_layout(int w, int h, int levels, vsb_pyr_layout_t* out) {
+    if (!out || w <= 0 || h <= 0 || levels < 1 || levels > VSB_MAX_LEVELS) return VSB_ERR_INVALID;
+    memset(out, 0, sizeof(*out));
+    out->levels = levels;
+    int64_t off = 0;
+    for (int l = 0; l < levels; l++) {
+        out->w[l] = l ? round_half_even_half(out->w[l - 1]) : w;
+        out->h[l] = l ? round_half_even_half(out->h[l - 1]) : h;
+        if (out->w[l] <= 0 || out->h[l] <= 0) return VSB_ERR_INVALID;
+        out->offset[l] = off;
+        off += ((int64_t)out->w[l] * out->h[l] + 255) & ~(int64_t)255;
+    }
+    out->frame_stride = off;
+    return VSB_OK;
+}
+
+extern "C" int vsb_pyramid_build(vsb_ctx_t* ctx, const uint8_t* img, int64_t img_stride, int pitch, int count,
+                                 const vsb_pyr_layout_t* layout, uint8_t* pyr, void* stream) {
+    if (!ctx || !layout || !pyr || count < 0) return VSB_ERR_INVALID;
+    if (count == 0) return VSB_OK;
+    PyrParams P;
+    P.lay = *layout;
+    for (int z0 = 0; z0 < count; z0 += 65535) {
+        int zc = count - z0 < 65535 ? count - z0 : 65535;
+        dim3 grid(vsb_div_up(layout->w[0], PT), vsb_div_up(layout->h[0], PT), zc);
+        ProfScope ps(ctx, VSB_K_PYRAMID, (cudaStream_t)stream);
+        pyramid_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(img ? img + (size_t)z0 * img_stride : nullptr, img_stride,
+                                                                pitch, P, pyr + (size_t)z0 * layout->frame_stride);
+        VSB_LAUNCHED(ctx);
+    }
+    return VSB_OK;
+}
+
+extern "C" int vsb_gradient_build(vsb_ctx_t* ctx, const uint8_t* pyr, int count, const vsb_pyr_layout_t* layout,
+                                  int16_t* gx, int16_t* gy, uint8_t* gmag, void* stream) {
+    if (!ctx || !layout || !pyr || !gx || !gy || count < 0) return VSB_ERR_INVALID;
+    if (count == 0) return VSB_OK;
+    GradParams P;
+    P.lay = *layout;
+    int acc = 0;
+    for (int l = 0; l < layout->levels; l++) {
+        P.tile_begin[l] = acc;
+        P.tiles_x[l] = vsb_div_up(layout->w[l], GW);
+        acc += P.tiles_x[l] * vsb_div_up(layout->h[l], GH);
+    }
+    for (int l = layout->levels; l <= VSB_MAX_LEVELS; l++) P.tile_begin[l] = acc;
+    for (int z0 = 0; z0 < count; z0 += 65535) {
+        int zc = count - z0 < 65535 ? count - z0 : 65535;
+        dim3 grid(acc, zc);
+        ProfScope ps(ctx, VSB_K_GRADIENT, (cudaStream_t)stream);
+        size_t o = (size_t)z0 * layout->frame_stride;
+        gradient_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(pyr + o, P, gx + o, gy + o, gmag ? gmag + o : nullptr);
+        VSB_LAUNCHED(ctx);
+    }
+    return VSB_OK;
+}
+
+extern "C" int vsb_candidates_build(vsb_ctx_t* ctx, const float* good_xy, int good_cap, const int32_t* n_good,
+                                    int count, int levels, const int* lw, const int* lh, float* cand, int cand_cap,
+                                    int32_t* n_cand, void* stream) {
+    if (!ctx || !good_xy || !n_good || !cand || !n_cand || !lw || !lh) return VSB_ERR_INVALID;
+    if (levels < 1 || levels > VSB_MAX_LEVELS || count < 0 || cand_cap < 0) return VSB_ERR_INVALID;
+    if (count == 0) return VSB_OK;
+    CandParams P;
+    P.levels = levels;
+    for (int l = 0; l < levels; l++) { P.lw[l] = lw[l]; P.lh[l] = lh[l]; }
+    dim3 grid(count, levels);
+    ProfScope ps(ctx, VSB_K_CANDIDATES, (cudaStream_t)stream);
+    candidates_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(good_xy, good_cap, n_good, P,
+                                                              reinterpret_cast<float4*>(cand), cand_cap, n_cand);
+    VSB_LAUNCHED(ctx);
+    return VSB_OK;
+}

@@ -1,0 +1,279 @@
+// tracker.cu — the whole tracking step on the device: the stage sequence of VISystemGPU::AddFrameGPU
+// (reference src/VISystemGPU.cpp:144-169) and CameraGPU::addGPUKeyframe (src/CameraGPU.cpp:138-163) —
+// Update (pyramid) -> computeGPUGoodMatches -> computeGradient -> ObtainPatchesPointsPreviousFrame ->
+// EstimatePoseFeatures — batched over independent frame pairs, with no host round trip between stages.
+// Pairs of a sequence are independent given their priors, so a sequence is one batch.
+#include "common.cuh"
+#include "knn_keys.cuh"
+
+int vsb_knn2_hamming_keys(vsb_ctx* ctx, const uint8_t* d1, int n1_max, const int32_t* n1, const uint8_t* d2,
+                          int n2_max, const int32_t* n2, int count, uint32_t* key12, uint32_t* key21, cudaStream_t st);
+int vsb_gn_solve_stats(vsb_ctx_t* ctx, const uint8_t* prev_pyr, const uint8_t* cur_pyr, const int16_t* prev_gx,
+                       const int16_t* prev_gy, int64_t pair_stride_pixels, const vsb_pyr_layout_t* layout,
+                       const float* cand, int cand_cap, const int32_t* n_cand, const vsb_intr_t K[VSB_MAX_LEVELS],
+                       const float* pose_in, const vsb_gn_opts_t* opts, int count, float* pose_out,
+                       vsb_gn_trace_t* trace, int32_t* n_trace, unsigned long long* stats, void* stream);
+int vsb_knn_unpack(vsb_ctx* ctx, const uint32_t* keys, int n_max, const int32_t* n, int count, int32_t* idx,
+                   float* dist, cudaStream_t st);
+
+namespace {
+
+struct Slot {
+    // frames: up to max_pairs + 1 (sequence) or 2 * max_pairs (independent pairs)
+    uint8_t* pyr = nullptr;
+    int16_t* gx = nullptr;
+    int16_t* gy = nullptr;
+    uint8_t* desc = nullptr;      // staging for the host entry: [max_pairs + 1][n_feat][desc_bytes]
+    float* kp = nullptr;          // [max_pairs + 1][n_feat][2]
+    int32_t* n_feat = nullptr;    // [max_pairs + 1]
+    float* prior = nullptr;       // [max_pairs][7]
+    uint32_t* key12 = nullptr;
+    uint32_t* key21 = nullptr;
+    int32_t* idx12 = nullptr;
+    int32_t* idx21 = nullptr;
+    float* dist12 = nullptr;
+    float* dist21 = nullptr;
+    int32_t* good_q = nullptr;
+    int32_t* good_t = nullptr;
+    float* good_d = nullptr;
+    int32_t* n_good = nullptr;
+    int32_t* n_sym = nullptr;
+    float* good_xy = nullptr;
+    float* cand = nullptr;
+    int32_t* n_cand = nullptr;
+    float* pose = nullptr;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t done = nullptr;
+};
+
+}  // namespace
+
+struct vsb_tracker {
+    vsb_ctx* ctx;
+    vsb_tracker_cfg_t cfg;
+    vsb_pyr_layout_t lay;
+    vsb_intr_t K[VSB_MAX_LEVELS];
+    int lw[VSB_MAX_LEVELS], lh[VSB_MAX_LEVELS];
+    int good_cap, cand_cap;
+    Slot slot[2];
+    int n_slots;
+    unsigned long long* stats;   // device, 4 counters shared by both slots
+};
+
+namespace {
+
+template <typename T>
+int dev_alloc(vsb_ctx* ctx, T** p, size_t n) {
+    VSB_CUDA(ctx, cudaMalloc((void**)p, (n ? n : 1) * sizeof(T)));
+    return VSB_OK;
+}
+
+int slot_alloc(vsb_tracker* t, Slot& s) {
+    vsb_ctx* ctx = t->ctx;
+    const vsb_tracker_cfg_t& c = t->cfg;
+    const size_t P = (size_t)c.max_pairs, F = 2 * P, N = (size_t)c.n_feat_max;
+    int rc;
+#define A(ptr, n) if ((rc = dev_alloc(ctx, &s.ptr, (n)))) return rc
+    A(pyr, F * t->lay.frame_stride);
+    if (c.gn.grad_mode == 0) {
+        A(gx, F * t->lay.frame_stride);
+        A(gy, F * t->lay.frame_stride);
+    }
+    A(desc, (P + 1) * N * c.desc_bytes);
+    A(kp, (P + 1) * N * 2);
+    A(n_feat, P + 1);
+    A(prior, P * 7);
+    A(key12, P * N * 2); A(key21, P * N * 2);
+    A(idx12, P * N * 2); A(idx21, P * N * 2);
+    A(dist12, P * N * 2); A(dist21, P * N * 2);
+    A(good_q, P * t->good_cap); A(good_t, P * t->good_cap); A(good_d, P * t->good_cap);
+    A(n_good, P); A(n_sym, P);
+    A(good_xy, P * t->good_cap * 2);
+    A(cand, P * VSB_MAX_LEVELS * (size_t)t->cand_cap * 4);
+    A(n_cand, P * VSB_MAX_LEVELS);
+    A(pose, P * 7);
+#undef A
+    VSB_CUDA(ctx, cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
+    VSB_CUDA(ctx, cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming));
+    return VSB_OK;
+}
+
+void slot_free(Slot& s) {
+    void* ptrs[] = {s.pyr, s.gx, s.gy, s.desc, s.kp, s.n_feat, s.prior, s.key12, s.key21, s.idx12, s.idx21, s.dist12,
+                    s.dist21, s.good_q, s.good_t, s.good_d, s.n_good, s.n_sym, s.good_xy, s.cand, s.n_cand, s.pose};
+    for (void* p : ptrs) if (p) cudaFree(p);
+    if (s.stream) cudaStreamDestroy(s.stream);
+    if (s.done) cudaEventDestroy(s.done);
+    s = Slot();
+}
+
+// Stages after the pyramids exist: match -> filter -> candidates -> GN.  prev pyramid of pair c is
+// pyr_prev + c * frame_stride, current is pyr_cur + c * frame_stride.
+int run_pairs(vsb_tracker* t, Slot& s, const uint8_t* pyr_prev, const uint8_t* pyr_cur, const int16_t* gx_prev,
+              const int16_t* gy_prev, const uint8_t* d1, const uint8_t* d2, const float* kp1, const int32_t* n1,
+              const int32_t* n2, const float* prior, int count, float* pose_out, int32_t* n_good_out, cudaStream_t st) {
+    vsb_ctx* ctx = t->ctx;
+    const vsb_tracker_cfg_t& c = t->cfg;
+    const int N = c.n_feat_max;
+    int rc;
+    if (c.norm != 1 || c.desc_bytes != 32) return VSB_ERR_UNSUPPORTED;
+    if ((rc = vsb_knn2_hamming_keys(ctx, d1, N, n1, d2, N, n2, count, s.key12, s.key21, st))) return rc;
+    if ((rc = vsb_knn_unpack(ctx, s.key12, N, n1, count, s.idx12, s.dist12, st))) return rc;
+    if ((rc = vsb_knn_unpack(ctx, s.key21, N, n2, count, s.idx21, s.dist21, st))) return rc;
+    if ((rc = vsb_match_filter(ctx, s.idx12, s.dist12, N, n1, s.idx21, s.dist21, N, n2, kp1, count, c.w, c.h, c.n_cells,
+                               c.ratio, c.sym_mode, s.good_q, s.good_t, s.good_d, t->good_cap, s.n_good, s.n_sym, st)))
+        return rc;
+    if ((rc = vsb_gather_keypoints(ctx, kp1, N, s.good_q, t->good_cap, s.n_good, count, s.good_xy, st))) return rc;
+    if ((rc = vsb_candidates_build(ctx, s.good_xy, t->good_cap, s.n_good, count, t->lay.levels, t->lw, t->lh, s.cand,
+                                   t->cand_cap, s.n_cand, st)))
+        return rc;
+    if ((rc = vsb_gn_solve_stats(ctx, pyr_prev, pyr_cur, gx_prev, gy_prev, t->lay.frame_stride, &t->lay, s.cand,
+                                 t->cand_cap, s.n_cand, t->K, prior, &c.gn, count, pose_out, nullptr, nullptr, t->stats,
+                                 st)))
+        return rc;
+    if (n_good_out)
+        VSB_CUDA(ctx, cudaMemcpyAsync(n_good_out, s.n_good, sizeof(int32_t) * count, cudaMemcpyDeviceToDevice, st));
+    return VSB_OK;
+}
+
+}  // namespace
+
+extern "C" int vsb_tracker_create(vsb_ctx_t* ctx, const vsb_tracker_cfg_t* cfg, vsb_tracker_t** out) {
+    if (!ctx || !cfg || !out) return VSB_ERR_INVALID;
+    *out = nullptr;
+    if (cfg->w <= 0 || cfg->h <= 0 || cfg->n_feat_max <= 0 || cfg->max_pairs <= 0 || cfg->n_cells < 1)
+        return VSB_ERR_INVALID;
+    vsb_tracker* t = new vsb_tracker();
+    t->ctx = ctx;
+    t->cfg = *cfg;
+    int rc = vsb_pyr_layout(cfg->w, cfg->h, VSB_MAX_LEVELS, &t->lay);
+    if (rc) { delete t; return rc; }
+    vsb_init_pyramid(cfg->w, cfg->h, cfg->fx, cfg->fy, cfg->cx, cfg->cy, t->K);
+    for (int l = 0; l < VSB_MAX_LEVELS; l++) { t->lw[l] = cfg->w >> l; t->lh[l] = cfg->h >> l; }  // Camera.cpp:44-47
+    const int root = (int)floor(sqrt((double)cfg->n_cells));
+    t->good_cap = root * root;
+    const int nf = t->good_cap < VSB_MAX_GN_FEATURES ? t->good_cap : VSB_MAX_GN_FEATURES;
+    t->cand_cap = 121 * nf;
+    t->n_slots = 2;
+    t->stats = nullptr;
+    if (cudaMalloc((void**)&t->stats, 4 * sizeof(unsigned long long)) != cudaSuccess ||
+        cudaMemset(t->stats, 0, 4 * sizeof(unsigned long long)) != cudaSuccess) {
+        delete t;
+        return VSB_ERR_CUDA;
+    }
+    for (int i = 0; i < t->n_slots; i++) {
+        rc = slot_alloc(t, t->slot[i]);
+        if (rc) { vsb_tracker_destroy(t); return rc; }
+    }
+    *out = t;
+    return VSB_OK;
+}
+
+extern "C" int vsb_tracker_destroy(vsb_tracker_t* t) {
+    if (!t) return VSB_ERR_INVALID;
+    cudaDeviceSynchronize();
+    for (int i = 0; i < 2; i++) slot_free(t->slot[i]);
+    if (t->stats) cudaFree(t->stats);
+    delete t;
+    return VSB_OK;
+}
+
+static int track_sequence_slot(vsb_tracker* t, Slot& s, const uint8_t* frames, bool frames_in_place, const uint8_t* desc,
+                               const float* kp_xy, const int32_t* n_feat, const float* prior, int n_frames,
+                               float* pose, int32_t* n_good, cudaStream_t st) {
+    vsb_ctx* ctx = t->ctx;
+    const vsb_tracker_cfg_t& c = t->cfg;
+    const int pairs = n_frames - 1;
+    int rc;
+    // Camera::Update for every frame (level 0 is copied unless it was uploaded straight into the pyramid)
+    if ((rc = vsb_pyramid_build(ctx, frames_in_place ? nullptr : frames, (int64_t)c.w * c.h, c.w, n_frames, &t->lay, s.pyr, st)))
+        return rc;
+    // Camera::computeGradient — only the previous frame of each pair is read by the solver
+    if (c.gn.grad_mode == 0)
+        if ((rc = vsb_gradient_build(ctx, s.pyr, pairs, &t->lay, s.gx, s.gy, nullptr, st))) return rc;
+    const size_t dstride = (size_t)c.n_feat_max * c.desc_bytes;
+    return run_pairs(t, s, s.pyr, s.pyr + t->lay.frame_stride, s.gx, s.gy, desc, desc + dstride, kp_xy, n_feat,
+                     n_feat ? n_feat + 1 : nullptr, prior, pairs, pose, n_good, st);
+}
+
+extern "C" int vsb_track_sequence(vsb_tracker_t* t, const uint8_t* frames, const uint8_t* desc, const float* kp_xy,
+                                  const int32_t* n_feat, const float* pose_prior, int n_frames, float* pose,
+                                  int32_t* n_good, void* stream) {
+    if (!t || !frames || !desc || !kp_xy || !pose_prior || !pose) return VSB_ERR_INVALID;
+    if (n_frames < 2) return n_frames < 0 ? VSB_ERR_INVALID : VSB_OK;
+    if (n_frames - 1 > t->cfg.max_pairs) return VSB_ERR_CAPACITY;
+    return track_sequence_slot(t, t->slot[0], frames, false, desc, kp_xy, n_feat, pose_prior, n_frames, pose, n_good,
+                               (cudaStream_t)stream);
+}
+
+extern "C" int vsb_track_pairs(vsb_tracker_t* t, const uint8_t* prev, const uint8_t* cur, const uint8_t* d1,
+                               const uint8_t* d2, const float* kp1_xy, const int32_t* n1, const int32_t* n2,
+                               const float* pose_prior, int count, float* pose, int32_t* n_good, void* stream) {
+    if (!t || !prev || !cur || !d1 || !d2 || !kp1_xy || !pose_prior || !pose) return VSB_ERR_INVALID;
+    if (count < 0) return VSB_ERR_INVALID;
+    if (count == 0) return VSB_OK;
+    if (count > t->cfg.max_pairs) return VSB_ERR_CAPACITY;
+    vsb_ctx* ctx = t->ctx;
+    const vsb_tracker_cfg_t& c = t->cfg;
+    Slot& s = t->slot[0];
+    cudaStream_t st = (cudaStream_t)stream;
+    uint8_t* pyr_prev = s.pyr;
+    uint8_t* pyr_cur = s.pyr + (size_t)c.max_pairs * t->lay.frame_stride;
+    int rc;
+    if ((rc = vsb_pyramid_build(ctx, prev, (int64_t)c.w * c.h, c.w, count, &t->lay, pyr_prev, st))) return rc;
+    if ((rc = vsb_pyramid_build(ctx, cur, (int64_t)c.w * c.h, c.w, count, &t->lay, pyr_cur, st))) return rc;
+    if (c.gn.grad_mode == 0)
+        if ((rc = vsb_gradient_build(ctx, pyr_prev, count, &t->lay, s.gx, s.gy, nullptr, st))) return rc;
+    return run_pairs(t, s, pyr_prev, pyr_cur, s.gx, s.gy, d1, d2, kp1_xy, n1, n2, pose_prior, count, pose, n_good, st);
+}
+
+extern "C" int vsb_track_sequence_host(vsb_tracker_t* t, const uint8_t* h_frames, const uint8_t* h_desc,
+                                       const float* h_kp_xy, const int32_t* h_n_feat, const float* h_pose_prior,
+                                       int n_frames, float* h_pose, int32_t* h_n_good) {
+    if (!t || !h_frames || !h_desc || !h_kp_xy || !h_pose_prior || !h_pose) return VSB_ERR_INVALID;
+    if (n_frames < 2) return n_frames < 0 ? VSB_ERR_INVALID : VSB_OK;
+    vsb_ctx* ctx = t->ctx;
+    const vsb_tracker_cfg_t& c = t->cfg;
+    const size_t fbytes = (size_t)c.w * c.h;
+    const size_t dstride = (size_t)c.n_feat_max * c.desc_bytes;
+    const size_t kstride = (size_t)c.n_feat_max * 2;
+    const int total_pairs = n_frames - 1;
+    int chunk_idx = 0;
+    for (int p0 = 0; p0 < total_pairs; p0 += c.max_pairs, chunk_idx++) {
+        const int pairs = total_pairs - p0 < c.max_pairs ? total_pairs - p0 : c.max_pairs;
+        const int nf = pairs + 1;
+        Slot& s = t->slot[chunk_idx & 1];
+        cudaStream_t st = s.stream;
+        if (chunk_idx >= 2) VSB_CUDA(ctx, cudaEventSynchronize(s.done));   // slot buffers are free again
+        // frames go straight into level 0 of the packed pyramid (one strided copy, no repack kernel)
+        VSB_CUDA(ctx, cudaMemcpy2DAsync(s.pyr, (size_t)t->lay.frame_stride, h_frames + (size_t)p0 * fbytes, fbytes,
+                                        fbytes, nf, cudaMemcpyHostToDevice, st));
+        VSB_CUDA(ctx, cudaMemcpyAsync(s.desc, h_desc + (size_t)p0 * dstride, nf * dstride, cudaMemcpyHostToDevice, st));
+        VSB_CUDA(ctx, cudaMemcpyAsync(s.kp, h_kp_xy + (size_t)p0 * kstride, nf * kstride * sizeof(float),
+                                      cudaMemcpyHostToDevice, st));
+        if (h_n_feat)
+            VSB_CUDA(ctx, cudaMemcpyAsync(s.n_feat, h_n_feat + p0, nf * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+        VSB_CUDA(ctx, cudaMemcpyAsync(s.prior, h_pose_prior + (size_t)p0 * 7, (size_t)pairs * 7 * sizeof(float),
+                                      cudaMemcpyHostToDevice, st));
+        int rc = track_sequence_slot(t, s, nullptr, true, s.desc, s.kp, h_n_feat ? s.n_feat : nullptr, s.prior, nf,
+                                     s.pose, nullptr, st);
+        if (rc) return rc;
+        VSB_CUDA(ctx, cudaMemcpyAsync(h_pose + (size_t)p0 * 7, s.pose, (size_t)pairs * 7 * sizeof(float),
+                                      cudaMemcpyDeviceToHost, st));
+        if (h_n_good)
+            VSB_CUDA(ctx, cudaMemcpyAsync(h_n_good + p0, s.n_good, pairs * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+        VSB_CUDA(ctx, cudaEventRecord(s.done, st));
+    }
+    for (int i = 0; i < 2; i++) VSB_CUDA(ctx, cudaStreamSynchronize(t->slot[i].stream));
+    return VSB_OK;
+}
+
+extern "C" int vsb_tracker_stats(vsb_tracker_t* t, long long out[4]) {
+    if (!t || !out) return VSB_ERR_INVALID;
+    VSB_CUDA(t->ctx, cudaDeviceSynchronize());
+    unsigned long long h[4];
+    VSB_CUDA(t->ctx, cudaMemcpy(h, t->stats, sizeof(h), cudaMemcpyDeviceToHost));
+    VSB_CUDA(t->ctx, cudaMemset(t->stats, 0, sizeof(h)));
+    for (int i = 0; i < 4; i++) out[i] = (long long)h[i];
+    return VSB_OK;
+}
