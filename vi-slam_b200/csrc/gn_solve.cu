@@ -3,12 +3,21 @@
 // src/VISystem.cpp:1113-1448) with WarpFunctionSE3 (:1495-1558), IdentityWeights (:1561-1565) and the Sophus
 // update pose <- pose * exp(delta) (:1421).
 //
+// Data flow.  Everything a candidate point contributes that does NOT depend on the pose — its source
+// intensity I_prev(y1,x1) and the previous-frame Scharr gradient at that pixel (:1320-1325) — is gathered
+// once per level by gn_prepare_kernel into an 8-byte attribute record, so an iteration reads 24 coalesced
+// bytes per point (the reference-layout float4 candidate + the record) and does ONE scattered load, the
+// current-frame intensity at the warped position.  Points are processed in batches of GT*U so a thread has U
+// independent gathers in flight; the 28 sums are formed per batch, reduced with a warp shuffle tree and
+// accumulated per warp in shared memory, which keeps the register footprint small enough for several blocks
+// per SM (one block's serial 6x6 solve overlaps the other blocks' point loops).
+//
 // Parity design: every float operation of the reference's per-point arithmetic is issued with an explicitly
-// rounded intrinsic in the source order (no FMA contraction); cv::gemm's "float in, double accumulate"
-// is reproduced with exact float*float products summed in FP64.  The 6x6 J^T J, 6-vector J^T r and the
-// residual energy are reduced with a fixed tree (thread partials -> warp shuffle tree -> 8 warp sums added in
-// warp order), so results are run-to-run deterministic and independent of the grid.  accum_mode 1 keeps
-// FP32 per-thread partials (FMA) and only the cross-thread part in FP64, the north-star's wording.
+// rounded intrinsic in the source order (no FMA contraction); cv::gemm's "float in, double accumulate" is
+// reproduced with exact float*float products summed in FP64.  The reduction order is fixed (batch order,
+// shuffle tree, warp order), so results are run-to-run deterministic and independent of the grid.
+// accum_mode 1 sums a thread's products in FP32 (FMA) and only the cross-thread part in FP64 (north-star
+// wording).  The 6x6 system is solved by warp 0 with OpenCV's LU elimination order, one matrix column per lane.
 #include "common.cuh"
 #include "se3.cuh"
 
@@ -16,6 +25,7 @@ namespace {
 
 constexpr int GT = 256;          // threads per frame pair
 constexpr int NW = GT / 32;
+constexpr int U = 4;             // points per thread per batch
 constexpr int NRED = 28;         // 21 (upper triangle of J^T J) + 6 (J^T r) + 1 (sum w r^2)
 
 struct GnParams {
@@ -26,6 +36,7 @@ struct GnParams {
     long long pair_stride;
     vsb_pyr_layout_t lay;
     const float4* cand;
+    uint2* patt;                 // [count][levels][cand_cap] {gx | gy << 16, I_prev}
     int cand_cap;
     const int32_t* n_cand;
     vsb_intr_t K[VSB_MAX_LEVELS];
@@ -44,24 +55,145 @@ __device__ __forceinline__ int reflect101(int p, int len) {
     return p;
 }
 
+// ---- per-level, pose-independent point attributes ------------------------------------------------------
+__global__ void __launch_bounds__(256)
+gn_prepare_kernel(const GnParams P) {
+    const int prob = blockIdx.z;
+    const int lvl = P.o.first_lvl - (int)blockIdx.y;
+    const int i = blockIdx.x * 256 + threadIdx.x;
+    const int ncand = min(P.n_cand[(size_t)prob * P.lay.levels + lvl], P.cand_cap);
+    if (i >= ncand) return;
+    const int cols = P.lay.w[lvl], rows = P.lay.h[lvl];
+    const size_t off = (size_t)prob * P.pair_stride + P.lay.offset[lvl];
+    const uint8_t* __restrict__ image1 = P.prev_pyr + off;
+    const size_t slot = ((size_t)prob * P.lay.levels + lvl) * P.cand_cap + i;
+    const float4 c = __ldg(P.cand + slot);
+    int sx = (int)c.x, sy = (int)c.y;                      // image1.at<uchar>(y1, x1): float -> int truncation (:1320)
+    sx = min(max(sx, 0), cols - 1);                        // candidates from Camera.cpp:393 are always inside
+    sy = min(max(sy, 0), rows - 1);
+    const size_t src = (size_t)sy * cols + sx;
+    const uint32_t i1 = __ldg(image1 + src);
+    int gx, gy;
+    if (P.o.grad_mode == 0) {                              // Frame::gradientX/Y (Camera.cpp:171-172), :1324-1325
+        gx = __ldg(P.prev_gx + off + src);
+        gy = __ldg(P.prev_gy + off + src);
+    } else {                                               // the same Scharr x3 evaluated at the point
+        const int xm = reflect101(sx - 1, cols), xp = reflect101(sx + 1, cols);
+        const int ym = reflect101(sy - 1, rows), yp = reflect101(sy + 1, rows);
+        const uint8_t* q0 = image1 + (size_t)ym * cols;
+        const uint8_t* q1 = image1 + (size_t)sy * cols;
+        const uint8_t* q2 = image1 + (size_t)yp * cols;
+        const int a00 = __ldg(q0 + xm), a01 = __ldg(q0 + sx), a02 = __ldg(q0 + xp);
+        const int a10 = __ldg(q1 + xm), a12 = __ldg(q1 + xp);
+        const int a20 = __ldg(q2 + xm), a21 = __ldg(q2 + sx), a22 = __ldg(q2 + xp);
+        gx = 3 * (3 * (a02 - a00) + 10 * (a12 - a10) + 3 * (a22 - a20));
+        gy = 3 * (3 * (a20 - a00) + 10 * (a21 - a01) + 3 * (a22 - a02));
+    }
+    P.patt[slot] = make_uint2(((uint32_t)gx & 0xFFFFu) | ((uint32_t)gy << 16), i1);
+}
+
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
     for (int off = 16; off >= 1; off >>= 1) v += __shfl_down_sync(0xffffffffu, v, off);
     return v;
 }
 
+// exact small-integer conversions on the ALU/FP pipes (keeps the quarter-rate conversion pipe for the rest)
+__device__ __forceinline__ float u23_to_float(uint32_t v) {          // 0 <= v < 2^23
+    return __fsub_rn(__uint_as_float(0x4B000000u | v), 8388608.0f);
+}
+__device__ __forceinline__ double i32_to_double(int v) {
+    return __dsub_rn(__hiloint2double(0x43300000, (int)((uint32_t)v ^ 0x80000000u)), 4503601774854144.0);
+}
+
+// D(8x8) += A(8x4) * B(4x8) in FP64 on the tensor cores.  With a == b (lane (g,t) supplies V[g] of point t)
+// this accumulates the Gram matrix V V^T of 4 points; products of floats are exact in double.
+__device__ __forceinline__ void dmma_8x8x4(double& c0, double& c1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                 : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+
+// ---- 6x6 solve by one warp -----------------------------------------------------------------------------
+// cv::Mat::inv() (DECOMP_LU -> hal::LU32f on [A | I]) followed by delta = Ainv * b (cv::gemm), VISystem.cpp:1412.
+// Lane c < 12 owns column c of the augmented matrix; every arithmetic operation is the one LU32f performs on
+// that element, in the same order, so the result is bit-identical to the sequential code in se3.cuh / the oracle.
+// G is the 8x8 Gram matrix of V = (J0..J5, r*w, r): A = G[0..5][0..5], J^T(r w) = G[a][6], sum r (r w) = G[7][6].
+__device__ __forceinline__ void warp_solve6(const double* G, int lane, float delta[6]) {
+    const unsigned FULL = 0xffffffffu;
+    float v[6];
+#pragma unroll
+    for (int r = 0; r < 6; r++) {
+        float x = 0.f;
+        if (lane < 6) x = (float)G[r * 8 + lane];                 // A = J^T J rounded once to float (:1408)
+        else if (lane < 12) x = (lane - 6 == r) ? 1.f : 0.f;
+        v[r] = x;
+    }
+    const float eps = 1.1920929e-07f * 10;
+    bool singular = false;
+#pragma unroll
+    for (int i = 0; i < 6; i++) {
+        float col[6];
+#pragma unroll
+        for (int j = i; j < 6; j++) col[j] = __shfl_sync(FULL, v[j], i);
+        int k = i;
+        float best = fabsf(col[i]);
+#pragma unroll
+        for (int j = i + 1; j < 6; j++)
+            if (fabsf(col[j]) > best) { best = fabsf(col[j]); k = j; }
+        if (best < eps) singular = true;
+#pragma unroll
+        for (int j = i + 1; j < 6; j++)
+            if (k == j) {
+                float t = v[i]; v[i] = v[j]; v[j] = t;
+                t = col[i]; col[i] = col[j]; col[j] = t;
+            }
+        const float d = F_DIV(-1.f, col[i]);
+#pragma unroll
+        for (int j = i + 1; j < 6; j++) {
+            const float alpha = F_MUL(col[j], d);
+            v[j] = F_ADD(v[j], F_MUL(alpha, v[i]));
+        }
+    }
+    float x[6];
+#pragma unroll
+    for (int i = 5; i >= 0; i--) {
+        float s = v[i];
+#pragma unroll
+        for (int k = i + 1; k < 6; k++) {
+            const float u = __shfl_sync(FULL, v[i], k);
+            s = F_SUB(s, F_MUL(u, x[k]));
+        }
+        const float diag = __shfl_sync(FULL, v[i], i);
+        x[i] = F_DIV(s, diag);
+    }
+    const int jcol = lane - 6;
+    const float bj = (lane >= 6 && lane < 12) ? (float)(-1.0 * G[jcol * 8 + 6]) : 0.f;   // b = -J^T (r w), :1409
+#pragma unroll
+    for (int a = 0; a < 6; a++) {
+        const double p = singular ? 0.0 : (double)x[a] * (double)bj;   // singular => inverse is all zeros => delta = 0
+        double s = 0.0;
+#pragma unroll
+        for (int j = 0; j < 6; j++) s += __shfl_sync(FULL, p, 6 + j);
+        delta[a] = (float)s;
+    }
+}
+
+constexpr int VROW = 36;   // staging row stride (floats): conflict-free for the [g][4s+t] reads of the MMA feed
+
 template <bool FP32_PARTIALS>
-__global__ void __launch_bounds__(GT)
+__global__ void __launch_bounds__(GT, 3)
 gn_solve_kernel(const GnParams P) {
     const int prob = blockIdx.x;
     const int tid = threadIdx.x;
     const int lane = tid & 31, warp = tid >> 5;
+    const int g8 = lane >> 2, t4 = lane & 3;
 
     __shared__ float s_pose[7];
-    __shared__ float s_m[12];
-    __shared__ double s_red[NW][NRED];
+    __shared__ double s_md[12];
+    __shared__ float s_v[NW][8 * VROW];
+    __shared__ double s_red[NW][64];
     __shared__ int s_cnt[NW];
-    __shared__ double s_sum[NRED];
+    __shared__ double s_G[64];
     __shared__ int s_nv;
     __shared__ int s_stop;      // 1 = leave the level
     __shared__ int s_ntrace;
@@ -74,223 +206,255 @@ gn_solve_kernel(const GnParams P) {
     if (tid == 0) { s_ntrace = 0; s_pts = 0ull; s_upd = 0; }
     __syncthreads();
 
-    const uint8_t* prev_base = P.prev_pyr + (size_t)prob * P.pair_stride;
     const uint8_t* cur_base = P.cur_pyr + (size_t)prob * P.pair_stride;
-    const int16_t* gx_base = P.prev_gx ? P.prev_gx + (size_t)prob * P.pair_stride : nullptr;
-    const int16_t* gy_base = P.prev_gy ? P.prev_gy + (size_t)prob * P.pair_stride : nullptr;
     vsb_gn_trace_t* trace = P.trace ? P.trace + (size_t)prob * VSB_MAX_TRACE : nullptr;
+    float* sv = s_v[warp];
 
     for (int lvl = o.first_lvl; lvl >= o.last_lvl; lvl--) {                       // VISystem.cpp:1181
         const int cols = P.lay.w[lvl], rows = P.lay.h[lvl];
-        const uint8_t* __restrict__ image1 = prev_base + P.lay.offset[lvl];
         const uint8_t* __restrict__ image2 = cur_base + P.lay.offset[lvl];
-        const int16_t* __restrict__ gx1 = gx_base ? gx_base + P.lay.offset[lvl] : nullptr;
-        const int16_t* __restrict__ gy1 = gy_base ? gy_base + P.lay.offset[lvl] : nullptr;
-        const float4* __restrict__ cand = P.cand + ((size_t)prob * P.lay.levels + lvl) * P.cand_cap;
+        const size_t slot0 = ((size_t)prob * P.lay.levels + lvl) * P.cand_cap;
+        const float4* __restrict__ cand = P.cand + slot0;
+        const uint2* __restrict__ patt = P.patt + slot0;
         const int ncand = min(P.n_cand[(size_t)prob * P.lay.levels + lvl], P.cand_cap);
         const float fx = P.K[lvl].fx, fy = P.K[lvl].fy, cx = P.K[lvl].cx, cy = P.K[lvl].cy;
         const float invfx = P.K[lvl].invfx, invfy = P.K[lvl].invfy;
         const float zf = o.z_factor;
         const float frows = (float)rows, fcols = (float)cols;
+        const int npix = rows * cols;
         if (tid == 0) s_last_err = 50000.0f;                                      // VISystem.cpp:1185
 
         for (int k = 0; k < o.max_iterations; k++) {                              // VISystem.cpp:1214
-            if (tid == 0) vsb::se3_matrix34(s_pose, s_m);
+            if (tid == 0) {
+                float m34[12];
+                vsb::se3_matrix34(s_pose, m34);
+                for (int i = 0; i < 12; i++) s_md[i] = (double)m34[i];
+            }
             __syncthreads();
-            float m[12];
+            double md[12];
 #pragma unroll
-            for (int i = 0; i < 12; i++) m[i] = s_m[i];
-
-            double acc[NRED];
-            float accf[NRED];
-#pragma unroll
-            for (int i = 0; i < NRED; i++) { acc[i] = 0.0; accf[i] = 0.f; }
+            for (int i = 0; i < 12; i++) md[i] = s_md[i];
             int nv = 0;
+            double acc0 = 0.0, acc1 = 0.0;      // this lane's two entries of the warp's 8x8 Gram matrix
+            float accf[FP32_PARTIALS ? NRED : 1];
+            if (FP32_PARTIALS) {
+#pragma unroll
+                for (int i = 0; i < NRED; i++) accf[i] = 0.f;
+            }
 
-            for (int i = tid; i < ncand; i += GT) {                               // VISystem.cpp:1281-1338
-                const float4 c = __ldg(cand + i);
-                // WarpFunctionSE3, VISystem.cpp:1519-1553
-                const float X = F_MUL(F_MUL(F_SUB(c.x, cx), invfx), c.z);
-                const float Y = F_MUL(F_MUL(F_SUB(c.y, cy), invfy), c.z);
-                const double dX = X, dY = Y, dZ = c.z, dW = c.w;
-                double s0 = (double)m[0] * dX; s0 += (double)m[1] * dY; s0 += (double)m[2] * dZ; s0 += (double)m[3] * dW;
-                double s1 = (double)m[4] * dX; s1 += (double)m[5] * dY; s1 += (double)m[6] * dZ; s1 += (double)m[7] * dW;
-                double s2 = (double)m[8] * dX; s2 += (double)m[9] * dY; s2 += (double)m[10] * dZ; s2 += (double)m[11] * dW;
-                const float r0 = (float)s0, r1 = (float)s1, r2 = (float)s2, r3 = c.w;  // last row of T is (0,0,0,1)
-                const float x2 = F_MUL(F_ADD(F_DIV(F_MUL(r0, fx), r2), cx), r3);
-                const float y2 = F_MUL(F_ADD(F_DIV(F_MUL(r1, fy), r2), cy), r3);
-                const float z2 = r2;
-                float iz = F_DIV(1.f, z2);
-                if (!(y2 > 0.f && y2 < frows && x2 > 0.f && x2 < fcols)) continue;   // :1299
-                if (!(z2 != 0.f)) continue;                                           // :1300
-                if (iz < 0.f) iz = 0.f;                                               // :1301
-                float i2;
-                if (o.sample_mode == 0) {                                             // round(), :1321
-                    const float fxr = floorf(x2), fyr = floorf(y2);
-                    const int rx = (int)fxr + ((F_SUB(x2, fxr) >= 0.5f) ? 1 : 0);
-                    const int ry = (int)fyr + ((F_SUB(y2, fyr) >= 0.5f) ? 1 : 0);
-                    const long long lin = (long long)ry * cols + rx;
-                    if (lin >= (long long)rows * cols) continue;
-                    i2 = (float)__ldg(image2 + lin);
-                } else {                                                              // bilinear extension
-                    const float x0f = floorf(x2), y0f = floorf(y2);
-                    const int ix = (int)x0f, iy = (int)y0f;
-                    if (ix + 1 >= cols || iy + 1 >= rows) continue;
-                    const float ax = F_SUB(x2, x0f), ay = F_SUB(y2, y0f);
-                    const uint8_t* p0 = image2 + (size_t)iy * cols + ix;
-                    const float i00 = (float)__ldg(p0), i01 = (float)__ldg(p0 + 1);
-                    const float i10 = (float)__ldg(p0 + cols), i11 = (float)__ldg(p0 + cols + 1);
-                    const float top = F_ADD(i00, F_MUL(ax, F_SUB(i01, i00)));
-                    const float bot = F_ADD(i10, F_MUL(ax, F_SUB(i11, i10)));
-                    i2 = F_ADD(top, F_MUL(ay, F_SUB(bot, top)));
-                }
-                // Jw, VISystem.cpp:1304-1316 (pixel coordinates and z_factor kept as the reference has them)
-                const float iz2x = F_MUL(F_MUL(F_MUL(fx, x2), iz), iz);               // fx*x2*iz*iz
-                const float iz2y = F_MUL(F_MUL(F_MUL(fy, y2), iz), iz);               // fy*y2*iz*iz
-                float Jw0[6], Jw1[6];
-                Jw0[0] = F_MUL(fx, iz);
-                Jw0[1] = 0.f;
-                Jw0[2] = F_MUL(-iz2x, zf);
-                Jw0[3] = -F_MUL(F_MUL(F_MUL(F_MUL(fx, x2), y2), iz), iz);
-                Jw0[4] = F_MUL(fx, F_ADD(1.f, F_MUL(F_MUL(F_MUL(x2, x2), iz), iz)));
-                Jw0[5] = F_MUL(F_MUL(-fx, y2), iz);
-                Jw1[0] = 0.f;
-                Jw1[1] = F_MUL(fy, iz);
-                Jw1[2] = F_MUL(-iz2y, zf);
-                Jw1[3] = -F_MUL(fy, F_ADD(1.f, F_MUL(F_MUL(F_MUL(y2, y2), iz), iz)));
-                Jw1[4] = F_MUL(F_MUL(F_MUL(F_MUL(fy, x2), y2), iz), iz);
-                Jw1[5] = F_MUL(F_MUL(-fy, x2), iz);
-                // source pixel and image gradient of the PREVIOUS frame, :1320-1325
-                const int sx = (int)c.x, sy = (int)c.y;
-                const size_t src = (size_t)sy * cols + sx;
-                const float i1 = (float)__ldg(image1 + src);
-                float jl0, jl1;
-                if (o.grad_mode == 0) {
-                    jl0 = (float)__ldg(gx1 + src);
-                    jl1 = (float)__ldg(gy1 + src);
-                } else {                                                              // Scharr x3 on the fly
-                    const int xm = reflect101(sx - 1, cols), xp = reflect101(sx + 1, cols);
-                    const int ym = reflect101(sy - 1, rows), yp = reflect101(sy + 1, rows);
-                    const uint8_t* q0 = image1 + (size_t)ym * cols;
-                    const uint8_t* q1 = image1 + (size_t)sy * cols;
-                    const uint8_t* q2 = image1 + (size_t)yp * cols;
-                    const int a00 = __ldg(q0 + xm), a01 = __ldg(q0 + sx), a02 = __ldg(q0 + xp);
-                    const int a10 = __ldg(q1 + xm), a12 = __ldg(q1 + xp);
-                    const int a20 = __ldg(q2 + xm), a21 = __ldg(q2 + sx), a22 = __ldg(q2 + xp);
-                    jl0 = (float)(3 * (3 * (a02 - a00) + 10 * (a12 - a10) + 3 * (a22 - a20)));
-                    jl1 = (float)(3 * (3 * (a20 - a00) + 10 * (a21 - a01) + 3 * (a22 - a02)));
-                }
-                const float r = F_SUB(i2, i1);                                        // :1323
-                float wgt = 1.f;
-                if (o.weight_mode == 2) {                                             // Huber extension
-                    const float a = fabsf(r);
-                    wgt = (a <= o.huber_k) ? 1.f : F_DIV(o.huber_k, a);
-                }
-                // J = Jl * Jw (1x2 * 2x6 gemm: double accumulate, one rounding), then row *= w (:1404-1405)
-                float J[6];
+            for (int base = 0; base < ncand; base += GT * U) {                    // VISystem.cpp:1281-1338
+                // ---- phase 1: coalesced loads of U points per thread --------------------------------------
+                float4 c[U];
+                uint2 at[U];
 #pragma unroll
-                for (int q = 0; q < 6; q++) {
-                    double s = (double)jl0 * (double)Jw0[q];
-                    s += (double)jl1 * (double)Jw1[q];
-                    J[q] = F_MUL(wgt, (float)s);
+                for (int u = 0; u < U; u++) {
+                    const int i = base + u * GT + tid;
+                    if (i < ncand) { c[u] = __ldg(cand + i); at[u] = __ldg(patt + i); }
+                    else { c[u] = make_float4(0.f, 0.f, 0.f, 0.f); at[u] = make_uint2(0u, 0u); }   // z = 0 => invalid
                 }
-                const float rw = F_MUL(r, wgt);
-                nv++;
-                if (!FP32_PARTIALS) {
-                    int t = 0;
+                // ---- phase 2: warp (WarpFunctionSE3, :1519-1553), validity, address of the one gather ------
+                float x2[U], y2[U], iz[U];
+                int lin[U];
+                bool ok[U];
 #pragma unroll
-                    for (int a = 0; a < 6; a++) {
-#pragma unroll
-                        for (int b = a; b < 6; b++) acc[t++] += (double)J[a] * (double)J[b];
+                for (int u = 0; u < U; u++) {
+                    const float X = F_MUL(F_MUL(F_SUB(c[u].x, cx), invfx), c[u].z);
+                    const float Y = F_MUL(F_MUL(F_SUB(c[u].y, cy), invfy), c[u].z);
+                    const double dX = X, dY = Y, dZ = c[u].z, dW = c[u].w;
+                    double s0 = md[0] * dX; s0 += md[1] * dY; s0 += md[2] * dZ; s0 += md[3] * dW;
+                    double s1 = md[4] * dX; s1 += md[5] * dY; s1 += md[6] * dZ; s1 += md[7] * dW;
+                    double s2 = md[8] * dX; s2 += md[9] * dY; s2 += md[10] * dZ; s2 += md[11] * dW;
+                    const float r0 = (float)s0, r1 = (float)s1, r2 = (float)s2, r3 = c[u].w;  // last row of T is (0,0,0,1)
+                    x2[u] = F_MUL(F_ADD(F_DIV(F_MUL(r0, fx), r2), cx), r3);
+                    y2[u] = F_MUL(F_ADD(F_DIV(F_MUL(r1, fy), r2), cy), r3);
+                    float izz = F_DIV(1.f, r2);
+                    bool v = (y2[u] > 0.f && y2[u] < frows && x2[u] > 0.f && x2[u] < fcols) && (r2 != 0.f);  // :1299-1300
+                    if (izz < 0.f) izz = 0.f;                                                            // :1301
+                    iz[u] = izz;
+                    int l = 0;
+                    if (v) {
+                        // x2, y2 are positive here: truncation == floor, and the fraction x2 - floor(x2) is exact
+                        const int ix = __float2int_rz(x2[u]), iy = __float2int_rz(y2[u]);
+                        if (o.sample_mode == 0) {                                    // round(), :1321
+                            const int rx = ix + ((F_SUB(x2[u], u23_to_float((uint32_t)ix)) >= 0.5f) ? 1 : 0);
+                            const int ry = iy + ((F_SUB(y2[u], u23_to_float((uint32_t)iy)) >= 0.5f) ? 1 : 0);
+                            l = ry * cols + rx;
+                            if (l >= npix) v = false;
+                        } else {                                                     // bilinear extension
+                            if (ix + 1 >= cols || iy + 1 >= rows) v = false;
+                            l = iy * cols + ix;
+                        }
                     }
+                    ok[u] = v;
+                    lin[u] = v ? l : 0;
+                }
+                float i2[U];
+                if (o.sample_mode == 0) {
 #pragma unroll
-                    for (int a = 0; a < 6; a++) acc[21 + a] += (double)J[a] * (double)rw;
-                    acc[27] += (double)r * (double)rw;
+                    for (int u = 0; u < U; u++) i2[u] = u23_to_float((uint32_t)__ldg(image2 + lin[u]));
                 } else {
-                    int t = 0;
 #pragma unroll
-                    for (int a = 0; a < 6; a++) {
-#pragma unroll
-                        for (int b = a; b < 6; b++) { accf[t] = fmaf(J[a], J[b], accf[t]); t++; }
+                    for (int u = 0; u < U; u++) {
+                        float val = 0.f;
+                        if (ok[u]) {
+                            const uint8_t* p0 = image2 + lin[u];
+                            const float i00 = (float)__ldg(p0), i01 = (float)__ldg(p0 + 1);
+                            const float i10 = (float)__ldg(p0 + cols), i11 = (float)__ldg(p0 + cols + 1);
+                            const float ax = F_SUB(x2[u], floorf(x2[u])), ay = F_SUB(y2[u], floorf(y2[u]));
+                            const float top = F_ADD(i00, F_MUL(ax, F_SUB(i01, i00)));
+                            const float bot = F_ADD(i10, F_MUL(ax, F_SUB(i11, i10)));
+                            val = F_ADD(top, F_MUL(ay, F_SUB(bot, top)));
+                        }
+                        i2[u] = val;
                     }
+                }
+                // ---- phase 3+4: Jacobian row, residual, weight (:1304-1327, :1343, :1404-1405), then the Gram
+                //      matrix of V = (J0..J5, r*w, r) of 32 points at a time on the FP64 tensor cores -------------
 #pragma unroll
-                    for (int a = 0; a < 6; a++) accf[21 + a] = fmaf(J[a], rw, accf[21 + a]);
-                    accf[27] = fmaf(r, rw, accf[27]);
+                for (int u = 0; u < U; u++) {
+                    const float X2 = x2[u], Y2 = y2[u], Z = iz[u];
+                    const float fxx = F_MUL(fx, X2), fyy = F_MUL(fy, Y2);
+                    const float iz2x = F_MUL(F_MUL(fxx, Z), Z);                       // fx*x2*iz*iz
+                    const float iz2y = F_MUL(F_MUL(fyy, Z), Z);                       // fy*y2*iz*iz
+                    const float jw00 = F_MUL(fx, Z);
+                    const float jw02 = F_MUL(-iz2x, zf);
+                    const float jw03 = -F_MUL(F_MUL(F_MUL(fxx, Y2), Z), Z);
+                    const float jw04 = F_MUL(fx, F_ADD(1.f, F_MUL(F_MUL(F_MUL(X2, X2), Z), Z)));
+                    const float jw05 = F_MUL(F_MUL(-fx, Y2), Z);
+                    const float jw11 = F_MUL(fy, Z);
+                    const float jw12 = F_MUL(-iz2y, zf);
+                    const float jw13 = -F_MUL(fy, F_ADD(1.f, F_MUL(F_MUL(F_MUL(Y2, Y2), Z), Z)));
+                    const float jw14 = F_MUL(F_MUL(F_MUL(F_MUL(fy, X2), Y2), Z), Z);
+                    const float jw15 = F_MUL(F_MUL(-fy, X2), Z);
+                    const int gxi = (int)(short)(at[u].x & 0xFFFFu);                  // gradientX1.at<short>(y1,x1), :1324
+                    const int gyi = (int)(short)(at[u].x >> 16);                      // gradientY1, :1325
+                    const float res = F_SUB(i2[u], u23_to_float(at[u].y));            // :1323
+                    float wgt = 1.f;
+                    if (o.weight_mode == 2) {                                         // Huber extension
+                        const float a = fabsf(res);
+                        wgt = (a <= o.huber_k) ? 1.f : F_DIV(o.huber_k, a);
+                    }
+                    // J = Jl * Jw (1x2 * 2x6 cv::gemm: products exact in double, one rounding to float).
+                    // Columns 0 and 1 have a single non-zero product, so the float product is already that rounding.
+                    const double dgx = i32_to_double(gxi), dgy = i32_to_double(gyi);
+                    float V[8];
+                    V[0] = F_MUL((float)gxi, jw00);
+                    V[1] = F_MUL((float)gyi, jw11);
+                    { double s = dgx * (double)jw02; s += dgy * (double)jw12; V[2] = (float)s; }
+                    { double s = dgx * (double)jw03; s += dgy * (double)jw13; V[3] = (float)s; }
+                    { double s = dgx * (double)jw04; s += dgy * (double)jw14; V[4] = (float)s; }
+                    { double s = dgx * (double)jw05; s += dgy * (double)jw15; V[5] = (float)s; }
+                    const bool good = ok[u];
+#pragma unroll
+                    for (int q = 0; q < 6; q++) V[q] = good ? F_MUL(wgt, V[q]) : 0.f;  // row *= w, :1404-1405
+                    V[6] = good ? F_MUL(res, wgt) : 0.f;
+                    V[7] = good ? res : 0.f;
+                    nv += good ? 1 : 0;
+                    if (!FP32_PARTIALS) {
+                        __syncwarp();
+#pragma unroll
+                        for (int q = 0; q < 8; q++) sv[q * VROW + lane] = V[q];
+                        __syncwarp();
+#pragma unroll
+                        for (int s = 0; s < 8; s++) {
+                            const double d = (double)sv[g8 * VROW + 4 * s + t4];      // V[g] of point 4s+t
+                            dmma_8x8x4(acc0, acc1, d, d);
+                        }
+                    } else {
+                        int t = 0;
+#pragma unroll
+                        for (int a = 0; a < 6; a++) {
+#pragma unroll
+                            for (int b = a; b < 6; b++) { accf[t] = fmaf(V[a], V[b], accf[t]); t++; }
+                        }
+#pragma unroll
+                        for (int a = 0; a < 6; a++) accf[21 + a] = fmaf(V[a], V[6], accf[21 + a]);
+                        accf[27] = fmaf(V[7], V[6], accf[27]);
+                    }
                 }
             }
-            // ---- deterministic reduction: warp tree, then the 8 warp sums in warp order -----------------
+            // ---- cross-warp reduction in warp order (deterministic) --------------------------------------------
+            if (!FP32_PARTIALS) {
+                s_red[warp][g8 * 8 + 2 * t4] = acc0;
+                s_red[warp][g8 * 8 + 2 * t4 + 1] = acc1;
+            } else {
+                // FP32 thread partials -> FP64 warp tree -> the same 8x8 layout
+                int t = 0;
 #pragma unroll
-            for (int i = 0; i < NRED; i++) {
-                double v = FP32_PARTIALS ? (double)accf[i] : acc[i];
-                v = warp_sum(v);
-                if (lane == 0) s_red[warp][i] = v;
+                for (int a = 0; a < 6; a++) {
+#pragma unroll
+                    for (int b = a; b < 6; b++) {
+                        const double v = warp_sum((double)accf[t++]);
+                        if (lane == 0) { s_red[warp][a * 8 + b] = v; s_red[warp][b * 8 + a] = v; }
+                    }
+                }
+#pragma unroll
+                for (int a = 0; a < 6; a++) {
+                    const double v = warp_sum((double)accf[21 + a]);
+                    if (lane == 0) s_red[warp][a * 8 + 6] = v;
+                }
+                const double v = warp_sum((double)accf[27]);
+                if (lane == 0) s_red[warp][7 * 8 + 6] = v;
             }
             {
-                int c = nv;
+                int cnum = nv;
 #pragma unroll
-                for (int off = 16; off >= 1; off >>= 1) c += __shfl_down_sync(0xffffffffu, c, off);
-                if (lane == 0) s_cnt[warp] = c;
+                for (int off = 16; off >= 1; off >>= 1) cnum += __shfl_down_sync(0xffffffffu, cnum, off);
+                if (lane == 0) s_cnt[warp] = cnum;
             }
             __syncthreads();
-            if (tid < NRED) {
+            if (tid < 64) {
                 double v = s_red[0][tid];
 #pragma unroll
                 for (int wv = 1; wv < NW; wv++) v += s_red[wv][tid];
-                s_sum[tid] = v;
+                s_G[tid] = v;
             }
-            if (tid == 32) {
-                int c = 0;
-                for (int wv = 0; wv < NW; wv++) c += s_cnt[wv];
-                s_nv = c;
+            if (tid == 64) {
+                int cnum = 0;
+                for (int wv = 0; wv < NW; wv++) cnum += s_cnt[wv];
+                s_nv = cnum;
             }
             __syncthreads();
-            // ---- error test, normal equations, pose update (one thread; VISystem.cpp:1343-1421) ---------
-            if (tid == 0) {
-                vsb_gn_trace_t tr;
-                tr.lvl = lvl; tr.iter = k; tr.n_valid = s_nv; tr.updated = 0; tr.error = 0.f;
-                for (int i = 0; i < 6; i++) tr.delta[i] = 0.f;
-                int stop = 0;
-                if (s_nv == 0) {
+            // ---- error test, normal equations, pose update (warp 0; VISystem.cpp:1343-1421) ----------------
+            if (warp == 0) {
+                int stop = 0, updated = 0;
+                float err = 0.f;
+                float delta[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+                const int n_valid = s_nv;
+                if (n_valid == 0) {
                     stop = 1;
                 } else {
-                    const float inv_n = (float)(1.0 / (double)s_nv);                  // :1347
-                    const float err = (float)((double)inv_n * s_sum[27]);             // :1349-1350
-                    tr.error = err;
+                    const float inv_n = (float)(1.0 / (double)n_valid);               // :1347
+                    err = (float)((double)inv_n * s_G[7 * 8 + 6]);                    // :1349-1350
                     const float last = s_last_err;
                     if (err >= last || k == o.max_iterations - 1 || fabsf(F_SUB(err, last)) < o.epsilon) {  // :1357
                         stop = 1;
                     } else {
+                        warp_solve6(s_G, lane, delta);                                // :1408-1412
+                        updated = 1;
+                    }
+                }
+                __syncwarp();
+                if (lane == 0) {
+                    if (updated) {
                         s_last_err = err;                                             // :1377
-                        float A[36], b[6], Ainv[36], delta[6];
-                        int t = 0;
-                        for (int a = 0; a < 6; a++)
-                            for (int c = a; c < 6; c++) {
-                                const float v = (float)s_sum[t++];                    // A = J^T J, :1408
-                                A[6 * a + c] = v;
-                                A[6 * c + a] = v;
-                            }
-                        for (int a = 0; a < 6; a++) b[a] = (float)(-1.0 * s_sum[21 + a]);   // :1409
-                        vsb::inv6(A, Ainv);                                           // :1412
-                        for (int a = 0; a < 6; a++) {
-                            double s = 0.0;
-                            for (int c = 0; c < 6; c++) s += (double)Ainv[6 * a + c] * (double)b[c];
-                            delta[a] = (float)s;
-                        }
                         float e[7], np[7], cur[7];
                         for (int i = 0; i < 7; i++) cur[i] = s_pose[i];
                         vsb::se3_exp(delta, e);
                         vsb::se3_mul(cur, e, np);                                     // :1421
                         for (int i = 0; i < 7; i++) s_pose[i] = np[i];
-                        for (int i = 0; i < 6; i++) tr.delta[i] = delta[i];
-                        tr.updated = 1;
                     }
+                    if (trace && s_ntrace < VSB_MAX_TRACE) {
+                        vsb_gn_trace_t* tr = trace + s_ntrace;
+                        tr->lvl = lvl; tr->iter = k; tr->n_valid = n_valid; tr->updated = updated; tr->error = err;
+                        for (int i = 0; i < 7; i++) tr->pose[i] = s_pose[i];
+                        for (int i = 0; i < 6; i++) tr->delta[i] = delta[i];
+                    }
+                    s_ntrace++;
+                    s_pts += (unsigned long long)ncand;
+                    s_upd += updated;
+                    s_stop = stop;
                 }
-                for (int i = 0; i < 7; i++) tr.pose[i] = s_pose[i];
-                if (trace && s_ntrace < VSB_MAX_TRACE) trace[s_ntrace] = tr;
-                s_ntrace++;
-                s_pts += (unsigned long long)ncand;
-                s_upd += tr.updated;
-                s_stop = stop;
             }
             __syncthreads();
             if (s_stop) break;
@@ -317,11 +481,13 @@ extern "C" void vsb_gn_default_opts(vsb_gn_opts_t* o) {
     o->grad_mode = 0; o->accum_mode = 0;
 }
 
+// Internal entry (tracker): `patt` is caller-owned scratch of count * levels * cand_cap uint2 (NULL = context scratch).
 int vsb_gn_solve_stats(vsb_ctx_t* ctx, const uint8_t* prev_pyr, const uint8_t* cur_pyr, const int16_t* prev_gx,
                        const int16_t* prev_gy, int64_t pair_stride_pixels, const vsb_pyr_layout_t* layout,
                        const float* cand, int cand_cap, const int32_t* n_cand, const vsb_intr_t K[VSB_MAX_LEVELS],
                        const float* pose_in, const vsb_gn_opts_t* opts, int count, float* pose_out,
-                       vsb_gn_trace_t* trace, int32_t* n_trace, unsigned long long* stats, void* stream) {
+                       vsb_gn_trace_t* trace, int32_t* n_trace, unsigned long long* stats, void* patt_scratch,
+                       void* stream) {
     if (!ctx || !prev_pyr || !cur_pyr || !layout || !cand || !n_cand || !K || !pose_in || !opts || !pose_out)
         return VSB_ERR_INVALID;
     if (count < 0 || cand_cap < 0) return VSB_ERR_INVALID;
@@ -332,17 +498,40 @@ int vsb_gn_solve_stats(vsb_ctx_t* ctx, const uint8_t* prev_pyr, const uint8_t* c
     if (opts->grad_mode == 0 && (!prev_gx || !prev_gy)) return VSB_ERR_INVALID;
     if (trace && (opts->first_lvl - opts->last_lvl + 1) * opts->max_iterations > VSB_MAX_TRACE) return VSB_ERR_CAPACITY;
     if (count == 0) return VSB_OK;
+    if (!patt_scratch) {
+        int rc = vsb_scratch_reserve(ctx, (size_t)count * layout->levels * cand_cap * sizeof(uint2) + 256, &patt_scratch);
+        if (rc) return rc;
+    }
     GnParams P;
     P.prev_pyr = prev_pyr; P.cur_pyr = cur_pyr; P.prev_gx = prev_gx; P.prev_gy = prev_gy;
     P.pair_stride = pair_stride_pixels;
     P.lay = *layout;
     P.cand = reinterpret_cast<const float4*>(cand);
+    P.patt = reinterpret_cast<uint2*>(patt_scratch);
     P.cand_cap = cand_cap;
     P.n_cand = n_cand;
     for (int l = 0; l < VSB_MAX_LEVELS; l++) P.K[l] = K[l];
     P.pose_in = pose_in; P.o = *opts; P.pose_out = pose_out; P.trace = trace; P.n_trace = n_trace;
     P.stats = stats;
     cudaStream_t st = (cudaStream_t)stream;
+    const int nlev = opts->first_lvl - opts->last_lvl + 1;
+    if (cand_cap > 0) {
+        for (int z0 = 0; z0 < count; z0 += 65535) {
+            GnParams Q = P;
+            const int zc = count - z0 < 65535 ? count - z0 : 65535;
+            // shift every per-pair base by z0 pairs
+            Q.prev_pyr += (size_t)z0 * P.pair_stride;
+            if (Q.prev_gx) Q.prev_gx += (size_t)z0 * P.pair_stride;
+            if (Q.prev_gy) Q.prev_gy += (size_t)z0 * P.pair_stride;
+            Q.cand += (size_t)z0 * layout->levels * cand_cap;
+            Q.patt += (size_t)z0 * layout->levels * cand_cap;
+            Q.n_cand += (size_t)z0 * layout->levels;
+            dim3 grid(vsb_div_up(cand_cap, 256), nlev, zc);
+            ProfScope ps(ctx, VSB_K_GN_PREPARE, st);
+            gn_prepare_kernel<<<grid, 256, 0, st>>>(Q);
+            VSB_LAUNCHED(ctx);
+        }
+    }
     ProfScope ps(ctx, VSB_K_GN_SOLVE, st);
     if (opts->accum_mode == 1) gn_solve_kernel<true><<<count, GT, 0, st>>>(P);
     else gn_solve_kernel<false><<<count, GT, 0, st>>>(P);
@@ -356,5 +545,5 @@ extern "C" int vsb_gn_solve(vsb_ctx_t* ctx, const uint8_t* prev_pyr, const uint8
                             const float* pose_in, const vsb_gn_opts_t* opts, int count, float* pose_out,
                             vsb_gn_trace_t* trace, int32_t* n_trace, void* stream) {
     return vsb_gn_solve_stats(ctx, prev_pyr, cur_pyr, prev_gx, prev_gy, pair_stride_pixels, layout, cand, cand_cap,
-                              n_cand, K, pose_in, opts, count, pose_out, trace, n_trace, nullptr, stream);
+                              n_cand, K, pose_in, opts, count, pose_out, trace, n_trace, nullptr, nullptr, stream);
 }

@@ -12,7 +12,8 @@ int vsb_gn_solve_stats(vsb_ctx_t* ctx, const uint8_t* prev_pyr, const uint8_t* c
                        const int16_t* prev_gy, int64_t pair_stride_pixels, const vsb_pyr_layout_t* layout,
                        const float* cand, int cand_cap, const int32_t* n_cand, const vsb_intr_t K[VSB_MAX_LEVELS],
                        const float* pose_in, const vsb_gn_opts_t* opts, int count, float* pose_out,
-                       vsb_gn_trace_t* trace, int32_t* n_trace, unsigned long long* stats, void* stream);
+                       vsb_gn_trace_t* trace, int32_t* n_trace, unsigned long long* stats, void* patt_scratch,
+                       void* stream);
 int vsb_knn_unpack(vsb_ctx* ctx, const uint32_t* keys, int n_max, const int32_t* n, int count, int32_t* idx,
                    float* dist, cudaStream_t st);
 
@@ -40,6 +41,7 @@ struct Slot {
     int32_t* n_sym = nullptr;
     float* good_xy = nullptr;
     float* cand = nullptr;
+    uint2* patt = nullptr;        // per-point attributes of the solver, [max_pairs][levels][cand_cap]
     int32_t* n_cand = nullptr;
     float* pose = nullptr;
     cudaStream_t stream = nullptr;
@@ -90,6 +92,7 @@ int slot_alloc(vsb_tracker* t, Slot& s) {
     A(n_good, P); A(n_sym, P);
     A(good_xy, P * t->good_cap * 2);
     A(cand, P * VSB_MAX_LEVELS * (size_t)t->cand_cap * 4);
+    A(patt, P * VSB_MAX_LEVELS * (size_t)t->cand_cap);
     A(n_cand, P * VSB_MAX_LEVELS);
     A(pose, P * 7);
 #undef A
@@ -100,7 +103,7 @@ int slot_alloc(vsb_tracker* t, Slot& s) {
 
 void slot_free(Slot& s) {
     void* ptrs[] = {s.pyr, s.gx, s.gy, s.desc, s.kp, s.n_feat, s.prior, s.key12, s.key21, s.idx12, s.idx21, s.dist12,
-                    s.dist21, s.good_q, s.good_t, s.good_d, s.n_good, s.n_sym, s.good_xy, s.cand, s.n_cand, s.pose};
+                    s.dist21, s.good_q, s.good_t, s.good_d, s.n_good, s.n_sym, s.good_xy, s.cand, s.patt, s.n_cand, s.pose};
     for (void* p : ptrs) if (p) cudaFree(p);
     if (s.stream) cudaStreamDestroy(s.stream);
     if (s.done) cudaEventDestroy(s.done);
@@ -129,7 +132,7 @@ int run_pairs(vsb_tracker* t, Slot& s, const uint8_t* pyr_prev, const uint8_t* p
         return rc;
     if ((rc = vsb_gn_solve_stats(ctx, pyr_prev, pyr_cur, gx_prev, gy_prev, t->lay.frame_stride, &t->lay, s.cand,
                                  t->cand_cap, s.n_cand, t->K, prior, &c.gn, count, pose_out, nullptr, nullptr, t->stats,
-                                 st)))
+                                 s.patt, st)))
         return rc;
     if (n_good_out)
         VSB_CUDA(ctx, cudaMemcpyAsync(n_good_out, s.n_good, sizeof(int32_t) * count, cudaMemcpyDeviceToDevice, st));
