@@ -60,8 +60,62 @@ def make_data(n_frames, seed, device):
     return seq
 
 
+class NvmlSampler:
+    """SM clock / throttle reasons sampled every few ms DURING the timed region through NVML (the same counters
+    `nvidia-smi --query-gpu=clocks.sm,clocks_event_reasons.*` prints; nvidia-smi's own loop is too slow to see a
+    sub-second region)."""
+
+    def __init__(self, gpu_index):
+        self.gpu, self.th, self.stop_flag = gpu_index, None, False
+        self.sm, self.reasons, self.max_sm, self.power = [], 0, None, []
+
+    def start(self):
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            idx = self.gpu
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            if vis:
+                try:
+                    idx = int(vis.split(",")[self.gpu])
+                except Exception:
+                    idx = self.gpu
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(idx)
+            self.max_sm = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+        except Exception:
+            return False
+        self.th = threading.Thread(target=self._loop, daemon=True)
+        self.th.start()
+        return True
+
+    def _loop(self):
+        nv = self.nv
+        while not self.stop_flag:
+            try:
+                self.sm.append(float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+                self.reasons |= int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.h))
+                self.power.append(nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0)
+            except Exception:
+                pass
+            time.sleep(0.002)
+
+    def stop(self):
+        self.stop_flag = True
+        if self.th:
+            self.th.join(timeout=2)
+        nv = self.nv
+        names = {"hw_slowdown": getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8),
+                 "hw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40),
+                 "sw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20),
+                 "sw_power_cap": getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4)}
+        return {"sm_mhz": float(np.median(self.sm)) if self.sm else None, "sm_max_mhz": self.max_sm,
+                "samples": len(self.sm), "power_w_max": max(self.power) if self.power else None,
+                "reasons": sorted(k for k, bit in names.items() if self.reasons & bit), "source": "nvml"}
+
+
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (fallback when NVML is not importable)."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
@@ -163,6 +217,7 @@ def run_reference(args, rank, world):
 def run_gpu(args, rank, world, local_rank):
     import torch
     import vislam_b200 as vb
+    from vislam_b200 import replicas
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     dist = None
@@ -177,8 +232,8 @@ def run_gpu(args, rank, world, local_rank):
 
     n_frames = int(os.environ.get("VSB_BENCH_FRAMES", str(N_FRAMES)))
     chunk = int(os.environ.get("VSB_BENCH_CHUNK", "500"))
-    grad_mode = int(os.environ.get("VSB_GRAD_MODE", "0"))
-    seq = make_data(n_frames, 2001 + 1000 * rank, dev)
+    grad_mode = int(os.environ.get("VSB_GRAD_MODE", "1"))   # 1: Scharr evaluated at the candidate points (bit-identical)
+    seq = make_data(n_frames, replicas.replica_seed(2001, rank), dev)
     n_pairs = n_frames - 1
     ctx = vb.Context(local_rank)
     tr = ctx.tracker(W, H, N_FEAT, seq["K"], n_cells=N_CELLS, max_pairs=chunk,
@@ -208,8 +263,10 @@ def run_gpu(args, rank, world, local_rank):
     tr.stats()
     ctx.profile(True)
     launches0 = ctx.launches
-    sampler = ClockSampler(local_rank)
-    sampler.start()
+    sampler = NvmlSampler(local_rank)
+    if not sampler.start():
+        sampler = ClockSampler(local_rank)
+        sampler.start()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     ev0.record(stream)
@@ -223,12 +280,9 @@ def run_gpu(args, rank, world, local_rank):
     prof = ctx.profile_read()
     ctx.profile(False)
     stats = tr.stats()
-    t_ms = torch.tensor([ms], dtype=torch.float64, device=dev)
-    if dist is not None:
-        dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
-    ms_max = float(t_ms.item())
+    ms_max = replicas.max_over_ranks(ms, dist, dev)
     ms_per_step = ms_max / args.steps
-    value = world * n_pairs / (ms_per_step * 1e-3)
+    value = replicas.aggregate_throughput(n_pairs, ms_per_step, world)
 
     # ---- end-to-end timing through the host-buffer entry ("e2e") -------------------------------------
     for _ in range(max(1, min(args.warmup, 2))):
@@ -242,11 +296,8 @@ def run_gpu(args, rank, world, local_rank):
     e1.record(stream)
     barrier()
     e2e_ms = (time.perf_counter() - t0) * 1e3
-    t_e = torch.tensor([e2e_ms], dtype=torch.float64, device=dev)
-    if dist is not None:
-        dist.all_reduce(t_e, op=dist.ReduceOp.MAX)
-    e2e_ms_step = float(t_e.item()) / args.steps
-    e2e_value = world * n_pairs / (e2e_ms_step * 1e-3)
+    e2e_ms_step = replicas.max_over_ranks(e2e_ms, dist, dev) / args.steps
+    e2e_value = replicas.aggregate_throughput(n_pairs, e2e_ms_step, world)
     h2d = sum(int(h[k].numel() * h[k].element_size()) for k in ("frames", "desc", "kp", "prior"))
     n_chunks = (n_pairs + chunk - 1) // chunk
     h2d += (n_chunks - 1) * (W * H + N_FEAT * 32 + N_FEAT * 8)    # the frame shared by two chunks is sent twice

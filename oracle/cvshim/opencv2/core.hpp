@@ -1,0 +1,135 @@
+// oracle/cvshim/opencv2/core.hpp — MINIMAL OpenCV type shim (TEST INFRASTRUCTURE ONLY).
+// Just enough of cv:: for the reference's src/Matcher.cpp + include/Matcher.hpp to compile UNMODIFIED where
+// they lie under /root/reference, so the oracle's restatement of the Matcher filter chain (nnFilter,
+// computeSymMatches, sortMatches, bestMatchesFilter, getGoodMatches) can be checked against the
+// reference's own code.  The only arithmetic supplied here is what OpenCV itself would supply:
+// BFMatcher::knnMatch (exhaustive, sorted by distance then train index — checked against cv2 4.13 in
+// tests/test_oracle_cv2.py) and cv::sortIdx (stable ascending).  Nothing in the product links this.
+#ifndef VSO_CVSHIM_CORE_HPP
+#define VSO_CVSHIM_CORE_HPP
+#include <algorithm>
+#include <cmath>
+#include <cstdint>
+#include <cstring>
+#include <memory>
+#include <vector>
+
+#define CV_8U 0
+#define CV_32S 4
+#define CV_32F 5
+#define CV_SORT_EVERY_ROW 0
+#define CV_SORT_ASCENDING 0
+
+namespace cv {
+
+enum { NORM_L2 = 4, NORM_HAMMING = 6 };
+
+struct Point2f { float x = 0, y = 0; };
+
+struct KeyPoint {
+    Point2f pt;
+    float size = 0, angle = -1, response = 0;
+    int octave = 0, class_id = -1;
+};
+
+struct DMatch {
+    DMatch() : queryIdx(-1), trainIdx(-1), imgIdx(-1), distance(3.402823466e+38F) {}
+    DMatch(int q, int t, float d) : queryIdx(q), trainIdx(t), imgIdx(-1), distance(d) {}
+    int queryIdx, trainIdx, imgIdx;
+    float distance;
+};
+
+class Mat {
+public:
+    int rows = 0, cols = 0, type_ = CV_8U;
+    std::shared_ptr<std::vector<uint8_t>> buf;
+    Mat() {}
+    Mat(int r, int c, int t) { create(r, c, t); }
+    static int esz(int t) { return t == CV_8U ? 1 : 4; }
+    void create(int r, int c, int t) {
+        rows = r; cols = c; type_ = t;
+        buf = std::make_shared<std::vector<uint8_t>>((size_t)r * c * esz(t), 0);
+    }
+    static Mat zeros(int r, int c, int t) { return Mat(r, c, t); }
+    void release() { buf.reset(); rows = cols = 0; }
+    int type() const { return type_; }
+    bool empty() const { return !buf || rows == 0 || cols == 0; }
+    uint8_t* data() const { return buf ? buf->data() : nullptr; }
+    template <typename T> T& at(int r, int c) { return reinterpret_cast<T*>(buf->data())[(size_t)r * cols + c]; }
+    template <typename T> const T& at(int r, int c) const { return reinterpret_cast<const T*>(buf->data())[(size_t)r * cols + c]; }
+};
+
+template <typename T>
+class Ptr : public std::shared_ptr<T> {
+public:
+    Ptr() {}
+    Ptr(T* p) : std::shared_ptr<T>(p) {}
+    template <typename U> Ptr(const Ptr<U>& o) : std::shared_ptr<T>(o) {}
+    template <typename U> Ptr(const std::shared_ptr<U>& o) : std::shared_ptr<T>(o) {}
+};
+
+class DescriptorMatcher {
+public:
+    virtual ~DescriptorMatcher() {}
+    // exhaustive k-NN, rows sorted by (distance ascending, train index ascending); fewer than k train rows
+    // gives shorter lists; imgIdx = 0 — cv::BFMatcher::knnMatch semantics
+    virtual void knnMatch(const Mat& q, const Mat& t, std::vector<std::vector<DMatch>>& out, int k) {
+        out.clear();
+        out.resize(q.rows);
+        for (int i = 0; i < q.rows; i++) {
+            std::vector<std::pair<float, int>> d(t.rows);
+            for (int j = 0; j < t.rows; j++) d[j] = std::make_pair(dist(q, i, t, j), j);
+            int kk = std::min(k, t.rows);
+            std::partial_sort(d.begin(), d.begin() + kk, d.end());
+            for (int m = 0; m < kk; m++) {
+                DMatch dm(i, d[m].second, d[m].first);
+                dm.imgIdx = 0;
+                out[i].push_back(dm);
+            }
+        }
+    }
+protected:
+    int norm_ = NORM_L2;
+    float dist(const Mat& a, int i, const Mat& b, int j) const {
+        if (norm_ == NORM_HAMMING) {
+            const uint8_t* x = a.data() + (size_t)i * a.cols;
+            const uint8_t* y = b.data() + (size_t)j * b.cols;
+            int s = 0;
+            for (int c = 0; c < a.cols; c++) s += __builtin_popcount((unsigned)(x[c] ^ y[c]));
+            return (float)s;
+        }
+        const float* x = reinterpret_cast<const float*>(a.data()) + (size_t)i * a.cols;
+        const float* y = reinterpret_cast<const float*>(b.data()) + (size_t)j * b.cols;
+        double s = 0;
+        for (int c = 0; c < a.cols; c++) { float d = x[c] - y[c]; s += (double)d * (double)d; }
+        return std::sqrt((float)s);
+    }
+};
+
+class BFMatcher : public DescriptorMatcher {
+public:
+    explicit BFMatcher(int norm = NORM_L2) { norm_ = norm; }
+    static Ptr<BFMatcher> create(int norm = NORM_L2) { return Ptr<BFMatcher>(new BFMatcher(norm)); }
+};
+
+class FlannBasedMatcher : public DescriptorMatcher {   // exhaustive stand-in; the hot path never selects FLANN
+public:
+    static Ptr<FlannBasedMatcher> create() { return Ptr<FlannBasedMatcher>(new FlannBasedMatcher()); }
+};
+
+// cv::sortIdx(src, dst, CV_SORT_EVERY_ROW + CV_SORT_ASCENDING) for CV_32F rows; stable (decision for ties)
+inline void sortIdx(const Mat& src, Mat& dst, int /*flags*/) {
+    dst.create(src.rows, src.cols, CV_32S);
+    for (int r = 0; r < src.rows; r++) {
+        std::vector<int> idx(src.cols);
+        for (int c = 0; c < src.cols; c++) idx[c] = c;
+        const float* p = reinterpret_cast<const float*>(src.data()) + (size_t)r * src.cols;
+        std::stable_sort(idx.begin(), idx.end(), [p](int a, int b) { return p[a] < p[b]; });
+        for (int c = 0; c < src.cols; c++) dst.at<int>(r, c) = idx[c];
+    }
+}
+
+namespace xfeatures2d {}
+
+}  // namespace cv
+#endif
