@@ -1,0 +1,57 @@
+#!/usr/bin/env python
+"""Turns the raw ncu outputs brought back in gpurun_out/ into the small text summaries committed under profiles/.
+usage: summarize_ncu.py launches <launches.csv>   |   summarize_ncu.py full <report.ncu-rep>"""
+import collections
+import csv
+import subprocess
+import sys
+
+
+def launches(path):
+    rows = list(csv.reader(open(path)))
+    hi = [i for i, r in enumerate(rows) if "Kernel Name" in r][0]
+    hdr, data = rows[hi], rows[hi + 1:]
+    kn, mn, mv = hdr.index("Kernel Name"), hdr.index("Metric Name"), hdr.index("Metric Value")
+    agg = collections.OrderedDict()
+    for r in data:
+        if len(r) <= mv or r[mn] != "gpu__time_duration.sum":
+            continue
+        name = r[kn].split("(")[0].replace("<unnamed>::", "").replace("void ", "")
+        a = agg.setdefault(name, [0, 0.0])
+        a[0] += 1
+        a[1] += float(r[mv].replace(",", ""))
+    tot = sum(v[1] for v in agg.values())
+    print(f"# ncu launch list ({path}): per-launch gpu__time_duration.sum, cold-cache and serialised — compare SHARES")
+    print(f"{'kernel':32s} {'launches':>8s} {'total_us':>12s} {'avg_us':>10s} {'share':>7s}")
+    for k, v in sorted(agg.items(), key=lambda kv: -kv[1][1]):
+        print(f"{k:32s} {v[0]:8d} {v[1] / 1e3:12.1f} {v[1] / 1e3 / v[0]:10.1f} {v[1] / tot:7.3f}")
+
+
+WANT = ["gpu__time_duration.sum", "launch__grid_size", "launch__block_size", "launch__registers_per_thread",
+        "launch__occupancy_limit_registers", "sm__warps_active.avg.pct_of_peak_sustained_active",
+        "sm__throughput.avg.pct_of_peak_sustained_elapsed", "smsp__issue_active.avg.pct",
+        "sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active",
+        "sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active",
+        "sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active",
+        "sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active",
+        "sm__inst_executed_pipe_tensor.sum", "dram__bytes_read.sum", "dram__bytes_write.sum",
+        "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "lts__t_bytes.sum",
+        "l1tex__t_bytes.sum", "smsp__inst_executed.sum"]
+
+
+def full(path):
+    out = subprocess.check_output(["ncu", "-i", path, "--page", "raw", "--csv"], text=True, stderr=subprocess.DEVNULL)
+    rows = list(csv.reader(out.splitlines()))
+    hdr, units = rows[0], rows[1]
+    kn = hdr.index("Kernel Name")
+    print(f"# ncu --set full ({path}): selected raw metrics per captured launch")
+    for r in rows[2:]:
+        print("\n== " + r[kn].split("(")[0].replace("<unnamed>::", "").replace("void ", ""))
+        for w in WANT:
+            if w in hdr:
+                i = hdr.index(w)
+                print(f"  {w:70s} {r[i]:>16s} {units[i]}")
+
+
+if __name__ == "__main__":
+    {"launches": launches, "full": full}[sys.argv[1]](sys.argv[2])
