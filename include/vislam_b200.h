@@ -18,6 +18,7 @@
  */
 #ifndef VISLAM_B200_H_
 #define VISLAM_B200_H_
+#include <stddef.h>
 #include <stdint.h>
 #ifdef __cplusplus
 extern "C" {
@@ -56,6 +57,23 @@ int vsb_profile_read(vsb_ctx_t* ctx, int kernel_id, double* total_ms, long long*
 /* INT-pipe ceiling of this GPU, measured: 32-bit POPC (independent chains, all SMs) per second. */
 int vsb_popc_peak(vsb_ctx_t* ctx, double* popc_per_s, void* stream);
 
+/* Device / pinned-host memory, copies and streams for hosts that do not link the CUDA runtime themselves
+ * (the C++ class mirrors in vi-slam_b200/host/ are plain g++ code; they replace the cv::Mat / cuda::GpuMat
+ * upload()/download() calls of MatcherGPU.cpp:48-50 and CameraGPU.cpp).  Copies are asynchronous on `stream`. */
+int vsb_malloc(vsb_ctx_t* ctx, size_t bytes, void** dptr);
+int vsb_free(vsb_ctx_t* ctx, void* dptr);
+int vsb_host_alloc(vsb_ctx_t* ctx, size_t bytes, void** hptr);
+int vsb_host_free(vsb_ctx_t* ctx, void* hptr);
+int vsb_upload(vsb_ctx_t* ctx, void* dst, const void* h_src, size_t bytes, void* stream);
+int vsb_upload_2d(vsb_ctx_t* ctx, void* dst, size_t dst_pitch, const void* h_src, size_t src_pitch,
+                  size_t width_bytes, size_t rows, void* stream);
+int vsb_download(vsb_ctx_t* ctx, void* h_dst, const void* src, size_t bytes, void* stream);
+int vsb_copy(vsb_ctx_t* ctx, void* dst, const void* src, size_t bytes, void* stream);
+int vsb_memset(vsb_ctx_t* ctx, void* dst, int value, size_t bytes, void* stream);
+int vsb_stream_create(vsb_ctx_t* ctx, void** stream);
+int vsb_stream_destroy(vsb_ctx_t* ctx, void* stream);
+int vsb_stream_sync(vsb_ctx_t* ctx, void* stream);
+
 /* ---- Matcher ------------------------------------------------------------------------------------ */
 /* Replaces Matcher::computeMatches (src/Matcher.cpp:83-94) / MatcherGPU::computeGPUMatches
  * (src/MatcherGPU.cpp:44-66) with BFMatcher(NORM_HAMMING): both knnMatch(...,2) calls from ONE
@@ -86,6 +104,32 @@ int vsb_match_filter(vsb_ctx_t* ctx, const int32_t* idx12, const float* dist12, 
                      const float* kp1_xy, int count, int w, int h, int n_cells, float ratio, int sym_mode,
                      int32_t* good_q, int32_t* good_t, float* good_d, int good_cap,
                      int32_t* n_good, int32_t* n_sym, void* stream);
+
+/* The same chain one public Matcher method at a time (the reference exposes them separately over public
+ * vectors, Matcher.hpp:34-47); the class mirror calls these, the tracker uses the fused vsb_match_filter.
+ *
+ * Matcher::nnFilter (Matcher.cpp:148-169): keep[c][i] = 0 where the reference clears the row
+ * (fewer than 2 neighbours, or d0 > ratio * d1 evaluated in double with ratio = (double)0.8f). */
+int vsb_nn_filter(vsb_ctx_t* ctx, const int32_t* idx, const float* dist, int n_max, const int32_t* n, int count,
+                  double ratio, uint8_t* keep, void* stream);
+/* Matcher::computeSymMatches after its two nnFilter calls (Matcher.cpp:113-143).  keep12 / keep21 are the
+ * nnFilter masks; sym_mode 0 ignores keep21 (de-facto: cleared rows are still read, App. B-1), 1 requires it.
+ * sym_q / sym_t / sym_d: [count][n1_max] compacted in ascending query order = Matcher::matches; n_sym: [count]. */
+int vsb_sym_matches(vsb_ctx_t* ctx, const int32_t* idx12, const float* dist12, const uint8_t* keep12, int n1_max,
+                    const int32_t* n1, const int32_t* idx21, const uint8_t* keep21, int n2_max, const int32_t* n2,
+                    int count, int sym_mode, int32_t* sym_q, int32_t* sym_t, float* sym_d, int32_t* n_sym,
+                    void* stream);
+/* Matcher::sortMatches (Matcher.cpp:329-352): order[c][r] = position of the r-th smallest key, ties keep the
+ * input order (cv::sortIdx ascending; stable by decision).  keys/order: [count][cap]. */
+int vsb_sort_keys(vsb_ctx_t* ctx, const float* keys, int cap, const int32_t* n, int count, int32_t* order,
+                  void* stream);
+/* Matcher::bestMatchesFilter (Matcher.cpp:171-244) over a y-sorted match list (Matcher::sortedMatches):
+ * list_q/list_t/list_d [count][list_cap], n_list [count]; good_* [count][good_cap] in reference order;
+ * good_pos (optional) = position of each winner in the input list. */
+int vsb_grid_best(vsb_ctx_t* ctx, const int32_t* list_q, const int32_t* list_t, const float* list_d, int list_cap,
+                  const int32_t* n_list, const float* kp1_xy, int n1_max, int count, int w, int h, int n_cells,
+                  int32_t* good_q, int32_t* good_t, float* good_d, int32_t* good_pos, int good_cap,
+                  int32_t* n_good, void* stream);
 
 /* ---- Camera ------------------------------------------------------------------------------------- */
 typedef struct {
@@ -168,6 +212,15 @@ int vsb_gn_solve(vsb_ctx_t* ctx, const uint8_t* prev_pyr, const uint8_t* cur_pyr
                  const vsb_pyr_layout_t* layout, const float* cand, int cand_cap, const int32_t* n_cand,
                  const vsb_intr_t K[VSB_MAX_LEVELS], const float* pose_in, const vsb_gn_opts_t* opts, int count,
                  float* pose_out, vsb_gn_trace_t* trace, int32_t* n_trace, void* stream);
+
+/* VISystem::WarpFunctionSE3 (VISystem.cpp:1495-1558) on its own: pts/out are n x 4 f32 rows (x, y, z, 1). */
+int vsb_warp_se3(vsb_ctx_t* ctx, const float* pts, int n, const float pose[7], const vsb_intr_t* K, float* out,
+                 void* stream);
+/* Sophus SE3f::exp (se3.hpp:723-742) and SE3f::matrix (se3.hpp:253-268, row-major 4x4).  Host-side. */
+int vsb_se3_exp(const float delta[6], float pose[7]);
+/* Sophus SE3f(rotation matrix, translation) (so3.hpp:422-427 -> Eigen Quaternion(Matrix3)); r row-major. Host-side. */
+int vsb_se3_from_rt(const float r[9], const float t[3], float pose[7]);
+int vsb_se3_matrix(const float pose[7], float m[16]);
 
 /* Initial pose exactly as VISystem.cpp:1135-1168 forms it (host-side helper):
  * pose0 = SE3(RPY2rotationMatrix(-rotationMatrix2RPY(imu2cam^T * R_imu_res * imu2cam)), -t_res). */

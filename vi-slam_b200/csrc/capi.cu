@@ -137,6 +137,15 @@ extern "C" int vsb_initial_pose(const float imu2cam[9], const float r_imu_res[9]
     return VSB_OK;
 }
 
+extern "C" int vsb_se3_from_rt(const float r[9], const float t[3], float pose[7]) {
+    if (!r || !t || !pose) return VSB_ERR_INVALID;
+    float q[4];
+    rot_to_quat(r, q);   // SE3(Matrix3, Point): Eigen Quaternion(Matrix3), so3.hpp:422-427
+    pose[0] = q[0]; pose[1] = q[1]; pose[2] = q[2]; pose[3] = q[3];
+    pose[4] = t[0]; pose[5] = t[1]; pose[6] = t[2];
+    return VSB_OK;
+}
+
 extern "C" int vsb_se3_mul(const float a[7], const float b[7], float out[7]) {
     if (!a || !b || !out) return VSB_ERR_INVALID;
     float tmp[7];
@@ -171,7 +180,8 @@ void vsb_prof_end(vsb_ctx* ctx, int slot, cudaStream_t st) { cudaEventRecord(ctx
 
 static const char* kKernelNames[VSB_K_COUNT] = {"knn2_hamming", "knn_unpack", "match_filter", "gather_keypoints",
                                                 "pyramid", "gradient", "candidates", "gn_solve", "knn2_l2",
-                                                "knn2_l2_prep", "gn_prepare"};
+                                                "knn2_l2_prep", "gn_prepare", "match_stage", "warp_se3",
+                                                "knn2_l2_final"};
 
 extern "C" int vsb_kernel_count(void) { return VSB_K_COUNT; }
 extern "C" const char* vsb_kernel_name(int id) { return (id >= 0 && id < VSB_K_COUNT) ? kKernelNames[id] : ""; }

@@ -1,0 +1,140 @@
+// VISystem.hpp — drop-in mirror of vi::VISystem / vi::VISystemGPU for the frame-tracking path
+// (include/VISystem.hpp:40-148, include/VISystemGPU.hpp:17-30): InitializePyramid, EstimatePoseFeatures,
+// WarpFunctionSE3, IdentityWeights, Track, AddFrame / AddFrameGPU and the public pose state.
+//
+// Out of this library's scope, and therefore absent here: calibration XML / undistortion
+// (InitializeSystem, Calibration, CameraModel), the ROS/Madgwick IMU filter (imuCore), RANSAC / triangulation
+// experiments (F2FRansac, Triangulate, ...), drawing.  Their outputs that the path consumes are plain public
+// fields the caller sets: K (through InitializePyramid), imu2camRotation, RotationResidualImu (the reference's
+// imuCore.residual_rotationMatrix), TranslationResidual (setGtRes).
+#ifndef VISLAM_VISYSTEM_HPP_
+#define VISLAM_VISYSTEM_HPP_
+
+#include <string>
+#include <vector>
+
+#include "vislam/Camera.hpp"
+#include "vislam/compat.hpp"
+#include "vislam/device.hpp"
+
+#define PYRAMID_LEVELS 5
+
+// include/Plus.hpp:10-16
+struct Quaterniond {
+    double w, x, y, z;
+    Quaterniond() : w(1), x(0), y(0), z(0) {}
+};
+
+namespace vi {
+
+class VISystem {
+public:
+    VISystem();
+    VISystem(int argc, char* argv[]);
+    virtual ~VISystem();
+
+    void InitializeCamera(int _detector, int _matcher, int _w_size, int _h_size, int _num_cells, int _length_path);
+    void InitializePyramid(int _width, int _height, cv::Mat _K);
+    void EstimatePoseFeatures(Frame* _previous_frame, Frame* _current_frame);
+    bool AddFrame(cv::Mat _currentImage, std::vector<cv::Point3d> _imuAngularVelocity,
+                  std::vector<cv::Point3d> _imuAcceleration);
+    bool AddFrame(cv::Mat _currentImage, std::vector<cv::Point3d> _imuAngularVelocity,
+                  std::vector<cv::Point3d> _imuAcceleration, cv::Point3d _gtPosition);
+    void FreeLastFrame();
+    void Track();
+    cv::Mat IdentityWeights(int _num_residuals);
+    cv::Mat TukeyFunctionWeights(cv::Mat _input);
+    cv::Mat WarpFunctionSE3(cv::Mat _points2warp, SE3 _rigid_transformation, int _lvl);
+    void setGtRes(cv::Mat TranslationResGT, cv::Mat RotationGT);
+
+    bool initialized, distortion_valid, depth_available;
+    int num_keyframes;
+    int num_max_keyframes;
+    int min_features;
+    int start_index;
+
+    int h, w, h_input, w_input;
+    float fx, fy, cx, cy;
+
+    cv::Point3d positionImu, velocityImu, accImu;
+    Quaterniond qOrientationImu;
+    cv::Point3d RPYOrientationImu;
+
+    cv::Point3d positionCam, velocityCam, accCam;
+    Quaterniond qOrientationCam;
+    cv::Point3d RPYOrientationCam;
+
+    cv::Matx33f imu2camRotation;
+    cv::Point3d imu2camTranslation;
+
+    SE3 final_poseCam;
+    SE3 final_poseImu;
+    SE3 current_poseCam;
+    SE3 current_poseImu;
+    cv::Point3d prev_gtPosition, current_gtPosition, current_gtTraslation;
+
+    Camera camera;
+
+    cv::Mat currentImage, prevImage;
+    cv::Mat K;
+
+    std::vector<int> w_ = std::vector<int>(PYRAMID_LEVELS);
+    std::vector<int> h_ = std::vector<int>(PYRAMID_LEVELS);
+    std::vector<float> fx_ = std::vector<float>(PYRAMID_LEVELS);
+    std::vector<float> fy_ = std::vector<float>(PYRAMID_LEVELS);
+    std::vector<float> cx_ = std::vector<float>(PYRAMID_LEVELS);
+    std::vector<float> cy_ = std::vector<float>(PYRAMID_LEVELS);
+    std::vector<float> invfx_ = std::vector<float>(PYRAMID_LEVELS);
+    std::vector<float> invfy_ = std::vector<float>(PYRAMID_LEVELS);
+    std::vector<float> invcx_ = std::vector<float>(PYRAMID_LEVELS);
+    std::vector<float> invcy_ = std::vector<float>(PYRAMID_LEVELS);
+    std::vector<cv::Mat> K_ = std::vector<cv::Mat>(PYRAMID_LEVELS);
+
+    cv::Mat TranslationResidual;
+    cv::Matx33f RotationResidual;
+    cv::Matx33f RotationResCam;
+    cv::Matx33f init_rotationMatrix, final_rotationMatrix;
+    cv::Point3f translationResEst;
+    int nPointsLastKeyframe;
+    int nPointsCurrentImage;
+    bool lastImageWasKeyframe;
+    bool currentImageIsKeyframe;
+
+    // ---- additions (not in the reference) ----
+    cv::Matx33f RotationResidualImu;    // stands in for imuCore.residual_rotationMatrix (VISystem.cpp:1135)
+    vsb_gn_opts_t gn_options;           // the literals of VISystem.cpp:1115-1121 by default
+    bool track_from_estimate;           // Track() composes the GN estimate instead of RotationResCam / translationResEst
+                                        // (the reference ignores the GN result there); default false
+    std::vector<vsb_gn_trace_t> last_trace;   // per-iteration record of the last EstimatePoseFeatures (when keep_trace)
+    bool keep_trace;
+    bool verbose;
+
+protected:
+    void fill_intrinsics(vsb_intr_t out[VSB_MAX_LEVELS]) const;
+    virtual Camera& active_camera() { return camera; }   // the camera whose frameList Track() reads
+    DevBuf d_pose_, d_trace_, d_ntrace_, d_cand_, d_ncand_, d_pts_;
+};
+
+class VISystemGPU : public VISystem {
+public:
+    VISystemGPU();
+    VISystemGPU(int argc, char* argv[]);
+    ~VISystemGPU();
+    void InitializeCameraGPU(int _detector, int _matcher, int _w_size, int _h_size, int _num_cells, int _length_path);
+    void AddFrameGPU(cv::Mat _currentImage, std::vector<cv::Point3d> _imuAngularVelocity,
+                     std::vector<cv::Point3d> _imuAcceleration);
+    void FreeLastFrameGPU();
+
+    CameraGPU cameraGPU;
+
+protected:
+    Camera& active_camera() override { return cameraGPU; }
+};
+
+}  // namespace vi
+
+// src/Plus.cpp:3-19, 23-50 (double precision helpers used by Track)
+Quaterniond toQuaternion(double roll, double pitch, double yaw);
+cv::Point3d toRPY(const Quaterniond& q);
+
+#endif

@@ -57,6 +57,10 @@ EXPORTS = [
     "vsb_se3_mul", "vsb_tracker_create", "vsb_tracker_destroy", "vsb_track_sequence",
     "vsb_track_sequence_host", "vsb_track_pairs", "vsb_kernel_count", "vsb_kernel_name", "vsb_profile_enable",
     "vsb_profile_reset", "vsb_profile_read", "vsb_popc_peak", "vsb_tracker_stats",
+    "vsb_malloc", "vsb_free", "vsb_host_alloc", "vsb_host_free", "vsb_upload", "vsb_upload_2d", "vsb_download",
+    "vsb_copy", "vsb_memset", "vsb_stream_create", "vsb_stream_destroy", "vsb_stream_sync",
+    "vsb_nn_filter", "vsb_sym_matches", "vsb_sort_keys", "vsb_grid_best", "vsb_warp_se3", "vsb_se3_exp",
+    "vsb_se3_matrix", "vsb_se3_from_rt",
 ]
 
 _lib = None
