@@ -69,3 +69,46 @@ def test_track_sequence_device_and_host(ctx, oracle, grad_mode):
         assert rot_angle(h_pose[k][:4].numpy(), ref["pose"][:4]) <= TOL
         assert np.abs(h_pose[k][4:].numpy() - ref["pose"][4:]).max() <= TOL
     tr.close()
+
+
+def test_track_pairs_float_descriptors_tum_shaped(ctx, oracle):
+    """BASELINE configs[2]: 640x480 TUM-shaped pair, 64-d float descriptors, L2 kNN (Matcher.cpp:55)."""
+    import torch
+    from vislam_b200 import synth
+    pairs = [synth.make_pair(w=640, h=480, n_feat=500, K=synth.TUM_K, seed=s, desc="float") for s in (3001, 3055)]
+    tr = ctx.tracker(640, 480, 500, pairs[0]["K"], n_cells=49, max_pairs=2, norm=0, desc_bytes=64 * 4)
+    st = lambda k: torch.from_numpy(np.stack([p[k] for p in pairs])).cuda()
+    d1 = st("d1").view(torch.uint8).reshape(2, 500, 256)
+    d2 = st("d2").view(torch.uint8).reshape(2, 500, 256)
+    pose, n_good = tr.track_pairs(st("prev"), st("cur"), d1, d2, st("kp1"), st("pose_prior"))
+    torch.cuda.synchronize()
+    pose, n_good = pose.cpu().numpy(), n_good.cpu().numpy()
+    for b, p in enumerate(pairs):
+        ref = oracle.track_pair(p["prev"], p["cur"], p["d1"], p["d2"], p["kp1"], p["K"], p["pose_prior"], n_cells=49,
+                                norm=0)
+        assert n_good[b] == len(ref["good_q"]) and n_good[b] > 10
+        assert rot_angle(pose[b][:4], ref["pose"][:4]) <= TOL
+        assert np.abs(pose[b][4:] - ref["pose"][4:]).max() <= TOL
+    tr.close()
+
+
+@pytest.mark.parametrize("first_lvl", [3, 4])
+def test_track_pairs_kitti_shaped(ctx, oracle, first_lvl):
+    """BASELINE configs[3]: 1241x376 (odd width: clipped 2x2 blocks in the pyramid), 2000 ORB features, GN start level
+    3 (reference literal, VISystem.cpp:1119) or 4 (5-level config)."""
+    import torch
+    import vislam_b200 as vb
+    from vislam_b200 import synth
+    p = synth.make_pair(w=1241, h=376, n_feat=2000, K=synth.KITTI_K, seed=4001)
+    tr = ctx.tracker(1241, 376, 2000, p["K"], n_cells=225, max_pairs=1, gn_opts=vb.default_gn_opts(first_lvl=first_lvl))
+    dev = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()[None]
+    pose, n_good = tr.track_pairs(dev(p["prev"]), dev(p["cur"]), dev(p["d1"]), dev(p["d2"]), dev(p["kp1"]),
+                                  dev(p["pose_prior"]))
+    torch.cuda.synchronize()
+    ref = oracle.track_pair(p["prev"], p["cur"], p["d1"], p["d2"], p["kp1"], p["K"], p["pose_prior"], n_cells=225,
+                            opts=oracle.default_opts(first_lvl=first_lvl))
+    pose = pose[0].cpu().numpy()
+    assert int(n_good[0]) == len(ref["good_q"]) and int(n_good[0]) > 50
+    assert rot_angle(pose[:4], ref["pose"][:4]) <= TOL
+    assert np.abs(pose[4:] - ref["pose"][4:]).max() <= TOL
+    tr.close()

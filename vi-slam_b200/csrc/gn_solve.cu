@@ -20,11 +20,11 @@
 // wording).  The 6x6 system is solved by warp 0 with OpenCV's LU elimination order, one matrix column per lane.
 #include "common.cuh"
 #include "se3.cuh"
+#include <stdlib.h>
 
 namespace {
 
-constexpr int GT = 256;          // threads per frame pair
-constexpr int NW = GT / 32;
+constexpr int GT_DEFAULT = 128;  // threads per frame pair (template parameter GT; VSB_GN_THREADS overrides)
 constexpr int U = 4;             // points per thread per batch
 constexpr int NRED = 28;         // 21 (upper triangle of J^T J) + 6 (J^T r) + 1 (sum w r^2)
 
@@ -180,9 +180,10 @@ __device__ __forceinline__ void warp_solve6(const double* G, int lane, float del
 
 constexpr int VROW = 36;   // staging row stride (floats): conflict-free for the [g][4s+t] reads of the MMA feed
 
-template <bool FP32_PARTIALS>
-__global__ void __launch_bounds__(GT, 3)
+template <bool FP32_PARTIALS, int GT>
+__global__ void __launch_bounds__(GT, 768 / GT)
 gn_solve_kernel(const GnParams P) {
+    constexpr int NW = GT / 32;
     const int prob = blockIdx.x;
     const int tid = threadIdx.x;
     const int lane = tid & 31, warp = tid >> 5;
@@ -409,7 +410,7 @@ gn_solve_kernel(const GnParams P) {
                 for (int wv = 1; wv < NW; wv++) v += s_red[wv][tid];
                 s_G[tid] = v;
             }
-            if (tid == 64) {
+            if (tid == GT - 1) {
                 int cnum = 0;
                 for (int wv = 0; wv < NW; wv++) cnum += s_cnt[wv];
                 s_nv = cnum;
@@ -533,8 +534,19 @@ int vsb_gn_solve_stats(vsb_ctx_t* ctx, const uint8_t* prev_pyr, const uint8_t* c
         }
     }
     ProfScope ps(ctx, VSB_K_GN_SOLVE, st);
-    if (opts->accum_mode == 1) gn_solve_kernel<true><<<count, GT, 0, st>>>(P);
-    else gn_solve_kernel<false><<<count, GT, 0, st>>>(P);
+    static int gt_env = -1;
+    if (gt_env < 0) {
+        const char* e = getenv("VSB_GN_THREADS");
+        gt_env = e ? atoi(e) : GT_DEFAULT;
+        if (gt_env != 64 && gt_env != 128 && gt_env != 256) gt_env = GT_DEFAULT;
+    }
+#define GN_LAUNCH(FP, T) gn_solve_kernel<FP, T><<<count, T, 0, st>>>(P)
+    if (opts->accum_mode == 1) {
+        if (gt_env == 64) GN_LAUNCH(true, 64); else if (gt_env == 128) GN_LAUNCH(true, 128); else GN_LAUNCH(true, 256);
+    } else {
+        if (gt_env == 64) GN_LAUNCH(false, 64); else if (gt_env == 128) GN_LAUNCH(false, 128); else GN_LAUNCH(false, 256);
+    }
+#undef GN_LAUNCH
     VSB_LAUNCHED(ctx);
     return VSB_OK;
 }

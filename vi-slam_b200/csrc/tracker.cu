@@ -16,6 +16,11 @@ int vsb_gn_solve_stats(vsb_ctx_t* ctx, const uint8_t* prev_pyr, const uint8_t* c
                        void* stream);
 int vsb_knn_unpack(vsb_ctx* ctx, const uint32_t* keys, int n_max, const int32_t* n, int count, int32_t* idx,
                    float* dist, cudaStream_t st);
+int vsb_knn2_l2_keys(vsb_ctx* ctx, const float* d1, int n1_max, const int32_t* n1, const float* d2, int n2_max,
+                     const int32_t* n2, int dim, int count, unsigned long long* key12, unsigned long long* key21,
+                     cudaStream_t st);
+int vsb_knn_unpack64(vsb_ctx* ctx, const unsigned long long* keys, int n_max, const int32_t* n, int count,
+                     int32_t* idx, float* dist, cudaStream_t st);
 
 namespace {
 
@@ -85,7 +90,8 @@ int slot_alloc(vsb_tracker* t, Slot& s) {
     A(kp, (P + 1) * N * 2);
     A(n_feat, P + 1);
     A(prior, P * 7);
-    A(key12, P * N * 2); A(key21, P * N * 2);
+    const size_t kw = c.norm == 1 ? 1 : 2;   // L2 keys are 64-bit (float bits << 32 | index)
+    A(key12, P * N * 2 * kw); A(key21, P * N * 2 * kw);
     A(idx12, P * N * 2); A(idx21, P * N * 2);
     A(dist12, P * N * 2); A(dist21, P * N * 2);
     A(good_q, P * t->good_cap); A(good_t, P * t->good_cap); A(good_d, P * t->good_cap);
@@ -119,10 +125,22 @@ int run_pairs(vsb_tracker* t, Slot& s, const uint8_t* pyr_prev, const uint8_t* p
     const vsb_tracker_cfg_t& c = t->cfg;
     const int N = c.n_feat_max;
     int rc;
-    if (c.norm != 1 || c.desc_bytes != 32) return VSB_ERR_UNSUPPORTED;
-    if ((rc = vsb_knn2_hamming_keys(ctx, d1, N, n1, d2, N, n2, count, s.key12, s.key21, st))) return rc;
-    if ((rc = vsb_knn_unpack(ctx, s.key12, N, n1, count, s.idx12, s.dist12, st))) return rc;
-    if ((rc = vsb_knn_unpack(ctx, s.key21, N, n2, count, s.idx21, s.dist21, st))) return rc;
+    if (c.norm == 1) {
+        if (c.desc_bytes != 32) return VSB_ERR_UNSUPPORTED;
+        if ((rc = vsb_knn2_hamming_keys(ctx, d1, N, n1, d2, N, n2, count, s.key12, s.key21, st))) return rc;
+        if ((rc = vsb_knn_unpack(ctx, s.key12, N, n1, count, s.idx12, s.dist12, st))) return rc;
+        if ((rc = vsb_knn_unpack(ctx, s.key21, N, n2, count, s.idx21, s.dist21, st))) return rc;
+    } else {
+        if (c.desc_bytes <= 0 || (c.desc_bytes & 3)) return VSB_ERR_INVALID;
+        const int dim = c.desc_bytes / 4;
+        unsigned long long* k12 = reinterpret_cast<unsigned long long*>(s.key12);
+        unsigned long long* k21 = reinterpret_cast<unsigned long long*>(s.key21);
+        if ((rc = vsb_knn2_l2_keys(ctx, reinterpret_cast<const float*>(d1), N, n1, reinterpret_cast<const float*>(d2), N,
+                                   n2, dim, count, k12, k21, st)))
+            return rc;
+        if ((rc = vsb_knn_unpack64(ctx, k12, N, n1, count, s.idx12, s.dist12, st))) return rc;
+        if ((rc = vsb_knn_unpack64(ctx, k21, N, n2, count, s.idx21, s.dist21, st))) return rc;
+    }
     if ((rc = vsb_match_filter(ctx, s.idx12, s.dist12, N, n1, s.idx21, s.dist21, N, n2, kp1, count, c.w, c.h, c.n_cells,
                                c.ratio, c.sym_mode, s.good_q, s.good_t, s.good_d, t->good_cap, s.n_good, s.n_sym, st)))
         return rc;
