@@ -41,6 +41,11 @@ int vsb_version(void);
 const char* vsb_error_string(int status);
 int vsb_ctx_create(int device, vsb_ctx_t** ctx);
 int vsb_ctx_destroy(vsb_ctx_t* ctx);
+/* Tuning knobs (defaults in parentheses; the environment variables VSB_KNN_IMPL / VSB_GN_THREADS set the same at
+ * context creation): "knn_impl" = 0 POPC kernel on the INT pipe, 1 tcgen05 tensor-core kernel, (2) tensor-core kernel
+ * with the packed 16x2 epilogue; "gn_threads" = threads per frame pair of the GN solver, 64 / (128) / 256.
+ * Results are identical for every setting. */
+int vsb_ctx_option(vsb_ctx_t* ctx, const char* name, int value);
 const char* vsb_last_cuda_error(vsb_ctx_t* ctx);
 int vsb_sm_count(vsb_ctx_t* ctx);
 /* number of kernels this context has launched so far (bench.py's gpu_launches) */

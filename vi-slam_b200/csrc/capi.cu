@@ -4,6 +4,7 @@
 // Plus.cpp:182-220 (RPY2rotationMatrix); vsb_se3_mul is Sophus SE3f::operator* (se3.hpp:285-321).
 #include "common.cuh"
 #include "se3.cuh"
+#include <stdlib.h>
 
 #define VSB_VERSION 100
 
@@ -38,8 +39,27 @@ extern "C" int vsb_ctx_create(int device, vsb_ctx_t** out) {
     c->scratch_bytes = 0;
     c->prof_on = 0;
     for (int i = 0; i < VSB_K_COUNT; i++) { c->prof_ms[i] = 0.0; c->prof_n[i] = 0; }
+    c->knn_impl = 2;
+    c->gn_threads = 128;
+    if (const char* e = getenv("VSB_KNN_IMPL")) vsb_ctx_option(c, "knn_impl", atoi(e));
+    if (const char* e = getenv("VSB_GN_THREADS")) vsb_ctx_option(c, "gn_threads", atoi(e));
     *out = c;
     return VSB_OK;
+}
+
+extern "C" int vsb_ctx_option(vsb_ctx_t* ctx, const char* name, int value) {
+    if (!ctx || !name) return VSB_ERR_INVALID;
+    if (!strcmp(name, "knn_impl")) {
+        if (value < 0 || value > 2) return VSB_ERR_INVALID;
+        ctx->knn_impl = value;
+        return VSB_OK;
+    }
+    if (!strcmp(name, "gn_threads")) {
+        if (value != 64 && value != 128 && value != 256) return VSB_ERR_INVALID;
+        ctx->gn_threads = value;
+        return VSB_OK;
+    }
+    return VSB_ERR_INVALID;
 }
 
 extern "C" int vsb_ctx_destroy(vsb_ctx_t* ctx) {

@@ -31,6 +31,10 @@ struct vsb_ctx {
     std::vector<cudaEvent_t> prof_free;
     double prof_ms[VSB_K_COUNT];
     long long prof_n[VSB_K_COUNT];
+    // tuning knobs (vsb_ctx_option)
+    int knn_impl;     // Hamming kNN: 0 = POPC kernel (INT pipe), 1 = tcgen05 tensor-core kernel, 32-bit epilogue,
+                      //              2 = tcgen05 kernel with the packed 16x2 epilogue
+    int gn_threads;   // threads per frame pair of the GN solver: 64 / 128 / 256
 };
 
 int vsb_prof_begin(vsb_ctx* ctx, int id, cudaStream_t st);

@@ -24,7 +24,6 @@
 
 namespace {
 
-constexpr int GT_DEFAULT = 128;  // threads per frame pair (template parameter GT; VSB_GN_THREADS overrides)
 constexpr int U = 4;             // points per thread per batch
 constexpr int NRED = 28;         // 21 (upper triangle of J^T J) + 6 (J^T r) + 1 (sum w r^2)
 
@@ -534,12 +533,7 @@ int vsb_gn_solve_stats(vsb_ctx_t* ctx, const uint8_t* prev_pyr, const uint8_t* c
         }
     }
     ProfScope ps(ctx, VSB_K_GN_SOLVE, st);
-    static int gt_env = -1;
-    if (gt_env < 0) {
-        const char* e = getenv("VSB_GN_THREADS");
-        gt_env = e ? atoi(e) : GT_DEFAULT;
-        if (gt_env != 64 && gt_env != 128 && gt_env != 256) gt_env = GT_DEFAULT;
-    }
+    const int gt_env = ctx->gn_threads;
 #define GN_LAUNCH(FP, T) gn_solve_kernel<FP, T><<<count, T, 0, st>>>(P)
     if (opts->accum_mode == 1) {
         if (gt_env == 64) GN_LAUNCH(true, 64); else if (gt_env == 128) GN_LAUNCH(true, 128); else GN_LAUNCH(true, 256);

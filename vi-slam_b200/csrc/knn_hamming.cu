@@ -170,6 +170,10 @@ __global__ void knn_unpack_kernel(const uint32_t* __restrict__ keys, int n_max, 
 
 }  // namespace
 
+int vsb_knn2_hamming_tc(vsb_ctx* ctx, const uint8_t* d1, int n1_max, const int32_t* n1, const uint8_t* d2,
+                        int n2_max, const int32_t* n2, int count, uint32_t* key12, uint32_t* key21, int pack16,
+                        int32_t* dump, int dump_ld, cudaStream_t st);
+
 // Internal entry used by the tracker too: leaves packed keys (distance << 23 | index) in key12 / key21.
 int vsb_knn2_hamming_keys(vsb_ctx* ctx, const uint8_t* d1, int n1_max, const int32_t* n1, const uint8_t* d2,
                           int n2_max, const int32_t* n2, int count, uint32_t* key12, uint32_t* key21,
@@ -177,6 +181,9 @@ int vsb_knn2_hamming_keys(vsb_ctx* ctx, const uint8_t* d1, int n1_max, const int
     if (!ctx || count < 0 || n1_max < 0 || n2_max < 0) return VSB_ERR_INVALID;
     if (n1_max > (int)KEY_IDX_MASK || n2_max > (int)KEY_IDX_MASK) return VSB_ERR_CAPACITY;
     if (count == 0) return VSB_OK;
+    if (ctx->knn_impl != 0)   // tensor-core path: every valid row is written by exactly one CTA, no memset, no atomics
+        return vsb_knn2_hamming_tc(ctx, d1, n1_max, n1, d2, n2_max, n2, count, key12, key21, ctx->knn_impl == 2,
+                                   nullptr, 0, st);
     if (n2_max > 0)
         VSB_CUDA(ctx, cudaMemsetAsync(key21, 0xFF, (size_t)count * n2_max * 2 * sizeof(uint32_t), st));
     if (n1_max > 0)

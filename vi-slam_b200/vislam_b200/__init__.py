@@ -60,7 +60,7 @@ EXPORTS = [
     "vsb_malloc", "vsb_free", "vsb_host_alloc", "vsb_host_free", "vsb_upload", "vsb_upload_2d", "vsb_download",
     "vsb_copy", "vsb_memset", "vsb_stream_create", "vsb_stream_destroy", "vsb_stream_sync",
     "vsb_nn_filter", "vsb_sym_matches", "vsb_sort_keys", "vsb_grid_best", "vsb_warp_se3", "vsb_se3_exp",
-    "vsb_se3_matrix", "vsb_se3_from_rt",
+    "vsb_se3_matrix", "vsb_se3_from_rt", "vsb_ctx_option",
 ]
 
 _lib = None
@@ -85,6 +85,7 @@ def lib():
     L.vsb_error_string.argtypes = [i32]
     L.vsb_ctx_create.argtypes = [i32, C.POINTER(vp)]
     L.vsb_ctx_destroy.argtypes = [vp]
+    L.vsb_ctx_option.argtypes = [vp, C.c_char_p, i32]
     L.vsb_last_cuda_error.restype = C.c_char_p
     L.vsb_last_cuda_error.argtypes = [vp]
     L.vsb_sm_count.argtypes = [vp]
@@ -213,6 +214,10 @@ class Context:
         return v.value
 
     # ---- Matcher -------------------------------------------------------------------------------
+    def option(self, name, value):
+        """Tuning knob (vsb_ctx_option): "knn_impl" 0/1/2, "gn_threads" 64/128/256."""
+        check(lib().vsb_ctx_option(self.handle, name.encode(), int(value)), self.handle)
+
     def knn2_hamming(self, d1, d2, n1=None, n2=None, stream=None):
         """d1 [B,N1,32] u8, d2 [B,N2,32] u8 (or 2-D for a single pair). Returns idx12, dist12, idx21, dist21."""
         t = self.torch
