@@ -12,8 +12,12 @@ def _run(ctx, d1, d2, n1=None, n2=None):
     t2 = torch.from_numpy(d2).cuda()
     a1 = None if n1 is None else torch.tensor(n1, dtype=torch.int32).cuda()
     a2 = None if n2 is None else torch.tensor(n2, dtype=torch.int32).cuda()
-    out = ctx.knn2_hamming(t1, t2, a1, a2)
-    torch.cuda.synchronize()
+    ctx.option("knn_impl", 0)          # this file covers the POPC kernel; test_gpu_knn_tc.py covers the tensor-core ones
+    try:
+        out = ctx.knn2_hamming(t1, t2, a1, a2)
+        torch.cuda.synchronize()
+    finally:
+        ctx.option("knn_impl", 2)
     return [o.cpu().numpy() for o in out]
 
 

@@ -86,7 +86,12 @@ def test_se3_exp_matches_closed_form(delta):
     H[:3, 3] = d[:3]
     E = expm(H)
     np.testing.assert_allclose(_rot(pose[:4]), E[:3, :3], atol=3e-6)
-    np.testing.assert_allclose(pose[4:], E[:3, 3], atol=3e-6)
+    # Sophus evaluates (1 - cos(theta)) / theta^2 in float32 (se3.hpp:738): for small theta the subtraction cancels
+    # (cos rounds to within 1 ulp of 1), so V carries an error of up to min(theta/2, ~2 ulp / theta) per unit of
+    # upsilon.  That is reference behaviour the oracle must keep, so it is part of the tolerance.
+    theta = float(np.linalg.norm(w))
+    cancel = float(np.linalg.norm(d[:3])) * min(0.5 * theta, 2.4e-7 / max(theta, 1e-30))
+    np.testing.assert_allclose(pose[4:], E[:3, 3], atol=3e-6 + cancel)
     assert abs(np.linalg.norm(pose[:4]) - 1) < 1e-5          # SOPHUS_ENSURE in so3.hpp:562-566
 
 
