@@ -1,5 +1,7 @@
 """GPU parity: pyramid (Camera::Update), Scharr gradients (Camera::computeGradient) and candidate patch
 points (Camera::ObtainPatchesPointsPreviousFrame) through the C ABI vs the oracle — bit-exact."""
+import ctypes
+
 import numpy as np
 import pytest
 
@@ -35,6 +37,40 @@ def test_pyramid_and_gradient(ctx, oracle, w, h):
             np.testing.assert_array_equal(ggx[l], rx)
             np.testing.assert_array_equal(ggy[l], ry)
             np.testing.assert_array_equal(ggm[l], oracle.grad_mag(rx, ry))
+
+
+@pytest.mark.parametrize("w,h", [(752, 480), (640, 480), (64, 48), (16, 16), (2048, 1024)])
+@pytest.mark.parametrize("levels", [5, 3, 1])
+def test_pyramid_register_blocked_kernel(ctx, oracle, w, h, levels):
+    """The register-blocked kernel (pyr_impl 1: one thread per 16x16 block) against the shared-memory tile kernel
+    (pyr_impl 0) and the oracle, for every level count, with the frame copied in and with level 0 already in place."""
+    import torch
+    import vislam_b200 as vb
+    rng = np.random.default_rng(w + h + levels)
+    B = 2
+    img = rng.integers(0, 256, (B, h, w), dtype=np.uint8)
+    img[1, ::2] = 255                                       # rounding of (a+b+c+d+2)>>2 at the extremes
+    img[1, 1::2, ::3] = 254
+    lay = vb.pyr_layout(w, h, levels)
+    dimg = torch.from_numpy(img).cuda()
+    out = {}
+    for impl in (0, 1):
+        ctx.option("pyr_impl", impl)
+        out[impl] = ctx.pyramid_build(dimg, lay)
+        # level 0 already in place (the host-buffer tracker entry uploads frames straight into the pyramid)
+        inplace = torch.zeros_like(out[impl])
+        inplace[:, :w * h] = dimg.reshape(B, -1)
+        vb.check(vb.lib().vsb_pyramid_build(ctx.handle, None, w * h, w, B, ctypes.byref(lay), inplace.data_ptr(),
+                                            vb._stream_ptr()), ctx.handle)
+        torch.cuda.synchronize()
+        assert torch.equal(inplace, out[impl])
+    ctx.option("pyr_impl", 1)
+    assert torch.equal(out[0], out[1])
+    got = out[1].cpu().numpy()
+    for b in range(B):
+        ref = oracle.pyramid(img[b])
+        for l, g in enumerate(_levels(got[b], lay)):
+            np.testing.assert_array_equal(g, ref[l])
 
 
 def test_candidates(ctx, oracle):

@@ -41,6 +41,7 @@ extern "C" int vsb_ctx_create(int device, vsb_ctx_t** out) {
     for (int i = 0; i < VSB_K_COUNT; i++) { c->prof_ms[i] = 0.0; c->prof_n[i] = 0; }
     c->knn_impl = 2;
     c->gn_threads = 128;
+    c->pyr_impl = 1;
     if (const char* e = getenv("VSB_KNN_IMPL")) vsb_ctx_option(c, "knn_impl", atoi(e));
     if (const char* e = getenv("VSB_GN_THREADS")) vsb_ctx_option(c, "gn_threads", atoi(e));
     *out = c;
@@ -52,6 +53,11 @@ extern "C" int vsb_ctx_option(vsb_ctx_t* ctx, const char* name, int value) {
     if (!strcmp(name, "knn_impl")) {
         if (value < 0 || value > 2) return VSB_ERR_INVALID;
         ctx->knn_impl = value;
+        return VSB_OK;
+    }
+    if (!strcmp(name, "pyr_impl")) {
+        if (value < 0 || value > 1) return VSB_ERR_INVALID;
+        ctx->pyr_impl = value;
         return VSB_OK;
     }
     if (!strcmp(name, "gn_threads")) {

@@ -93,6 +93,93 @@ pyramid_kernel(const uint8_t* __restrict__ img, long long img_stride, int pitch,
     }
 }
 
+// Fast path for frames whose width and height are multiples of 16 (752x480, 640x480): every level is an exact
+// halving, so a 16x16 level-0 block maps to 8x8 / 4x4 / 2x2 / 1 pixels of levels 1..4 with no clipping.  One
+// THREAD owns one block and keeps it in registers (16 rows x uint4); the 2x2 means are formed four bytes at a time in
+// 16-bit lanes ((a+b+c+d+2)>>2, exact), so there is no shared memory, no barrier and no idle thread at the small
+// levels.  Lanes of a warp own horizontally consecutive blocks: every load/store instruction of a warp touches one
+// contiguous run per image row (512 B at level 0, 256/128/64/32 B at levels 1..4).
+constexpr int P16_THREADS = 128;
+
+__device__ __forceinline__ uint32_t hsum2(uint32_t w) {          // bytes p0..p3 -> (p0+p1) | (p2+p3) << 16
+    return (w & 0x00FF00FFu) + ((w >> 8) & 0x00FF00FFu);
+}
+__device__ __forceinline__ uint32_t mean4(uint32_t s) {          // two 16-bit sums of four pixels -> two rounded means
+    return ((s + 0x00020002u) >> 2) & 0x00FF00FFu;
+}
+__device__ __forceinline__ uint32_t pack4(uint32_t a, uint32_t b) {   // bytes a0, a2, b0, b2
+    return __byte_perm(a, b, 0x6420);
+}
+
+__global__ void __launch_bounds__(P16_THREADS)
+pyramid16_kernel(const uint8_t* __restrict__ img, long long img_stride, int pitch, PyrParams P,
+                 uint8_t* __restrict__ pyr) {
+    const vsb_pyr_layout_t& L = P.lay;
+    const int w0 = L.w[0];
+    const int bw = w0 >> 4, nb = bw * (L.h[0] >> 4);
+    const int b = blockIdx.x * P16_THREADS + threadIdx.x;
+    if (b >= nb) return;
+    const int by = b / bw, bx = b - by * bw;
+    const int frame = blockIdx.y;
+    uint8_t* out = pyr + (size_t)frame * L.frame_stride;
+    const uint8_t* in = img ? img + (size_t)frame * img_stride : out;
+    const int in_pitch = img ? pitch : w0;
+
+    uint4 r[16];
+    const uint8_t* src = in + (size_t)(by * 16) * in_pitch + bx * 16;
+#pragma unroll
+    for (int k = 0; k < 16; k++) r[k] = __ldcs(reinterpret_cast<const uint4*>(src + (size_t)k * in_pitch));
+    if (img) {                                                    // Camera::Update keeps a copy of the frame as level 0
+        uint8_t* dst = out + (size_t)(by * 16) * w0 + bx * 16;
+#pragma unroll
+        for (int k = 0; k < 16; k++) *reinterpret_cast<uint4*>(dst + (size_t)k * w0) = r[k];
+    }
+    if (L.levels < 2) return;
+    uint2 l1[8];
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+        const uint4 a = r[2 * k], c = r[2 * k + 1];
+        const uint32_t s0 = mean4(hsum2(a.x) + hsum2(c.x)), s1 = mean4(hsum2(a.y) + hsum2(c.y));
+        const uint32_t s2 = mean4(hsum2(a.z) + hsum2(c.z)), s3 = mean4(hsum2(a.w) + hsum2(c.w));
+        l1[k] = make_uint2(pack4(s0, s1), pack4(s2, s3));
+    }
+    {
+        const int w1 = L.w[1];
+        uint8_t* dst = out + L.offset[1] + (size_t)(by * 8) * w1 + bx * 8;
+#pragma unroll
+        for (int k = 0; k < 8; k++) *reinterpret_cast<uint2*>(dst + (size_t)k * w1) = l1[k];
+    }
+    if (L.levels < 3) return;
+    uint32_t l2[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        const uint2 a = l1[2 * k], c = l1[2 * k + 1];
+        l2[k] = pack4(mean4(hsum2(a.x) + hsum2(c.x)), mean4(hsum2(a.y) + hsum2(c.y)));
+    }
+    {
+        const int w2 = L.w[2];
+        uint8_t* dst = out + L.offset[2] + (size_t)(by * 4) * w2 + bx * 4;
+#pragma unroll
+        for (int k = 0; k < 4; k++) *reinterpret_cast<uint32_t*>(dst + (size_t)k * w2) = l2[k];
+    }
+    if (L.levels < 4) return;
+    uint32_t l3[2];
+#pragma unroll
+    for (int k = 0; k < 2; k++) {
+        const uint32_t s = mean4(hsum2(l2[2 * k]) + hsum2(l2[2 * k + 1]));
+        l3[k] = (s & 0xFFu) | ((s >> 8) & 0xFF00u);
+    }
+    {
+        const int w3 = L.w[3];
+        uint8_t* dst = out + L.offset[3] + (size_t)(by * 2) * w3 + bx * 2;
+        *reinterpret_cast<uint16_t*>(dst) = (uint16_t)l3[0];
+        *reinterpret_cast<uint16_t*>(dst + w3) = (uint16_t)l3[1];
+    }
+    if (L.levels < 5) return;
+    const uint32_t s4 = (l3[0] & 0xFFu) + (l3[0] >> 8) + (l3[1] & 0xFFu) + (l3[1] >> 8);
+    out[L.offset[4] + (size_t)by * L.w[4] + bx] = (uint8_t)((s4 + 2u) >> 2);
+}
+
 // ---------------------------------------------------------------------------------------------- Scharr
 // cv::Scharr(src, dst, CV_16S, dx, dy, scale = 3, 0, BORDER_REFLECT_101): derivative [-1 0 1], smoothing
 // [3 10 3], times 3 (Camera.cpp:171-172; the literal 3 is `scale`).  One launch covers every
@@ -238,6 +325,23 @@ extern "C" int vsb_pyramid_build(vsb_ctx_t* ctx, const uint8_t* img, int64_t img
     if (count == 0) return VSB_OK;
     PyrParams P;
     P.lay = *layout;
+    // register-blocked fast path: exact halving at every level and 16-byte aligned rows
+    const int in_pitch = img ? pitch : layout->w[0];
+    const bool fast = ctx->pyr_impl != 0 && (layout->w[0] % 16 == 0) && (layout->h[0] % 16 == 0) &&
+                      (in_pitch % 16 == 0) && (!img || (((uintptr_t)img | (uintptr_t)img_stride) % 16 == 0)) &&
+                      ((uintptr_t)pyr % 16 == 0);
+    if (fast) {
+        const int nb = (layout->w[0] / 16) * (layout->h[0] / 16);
+        for (int z0 = 0; z0 < count; z0 += 65535) {
+            int zc = count - z0 < 65535 ? count - z0 : 65535;
+            dim3 grid(vsb_div_up(nb, P16_THREADS), zc);
+            ProfScope ps(ctx, VSB_K_PYRAMID, (cudaStream_t)stream);
+            pyramid16_kernel<<<grid, P16_THREADS, 0, (cudaStream_t)stream>>>(
+                img ? img + (size_t)z0 * img_stride : nullptr, img_stride, pitch, P, pyr + (size_t)z0 * layout->frame_stride);
+            VSB_LAUNCHED(ctx);
+        }
+        return VSB_OK;
+    }
     for (int z0 = 0; z0 < count; z0 += 65535) {
         int zc = count - z0 < 65535 ? count - z0 : 65535;
         dim3 grid(vsb_div_up(layout->w[0], PT), vsb_div_up(layout->h[0], PT), zc);
