@@ -191,7 +191,7 @@ def run_reference(args, rank, world):
     if rank != 0:
         return
     cores = os.cpu_count() or 1
-    n_sample = int(os.environ.get("VSB_REF_SAMPLE_PAIRS", "48"))
+    n_sample = int(os.environ.get("VSB_REF_SAMPLE_PAIRS", "1024"))
     seq = make_data(n_sample + 1, 2001, None)
     ids = list(range(n_sample))
     for _ in range(args.warmup):
@@ -301,6 +301,16 @@ def run_gpu(args, rank, world, local_rank):
     e2e_ms = (time.perf_counter() - t0) * 1e3
     e2e_ms_step = replicas.max_over_ranks(e2e_ms, dist, dev) / args.steps
     e2e_value = replicas.aggregate_throughput(n_pairs, e2e_ms_step, world)
+    # what the link gives a plain pinned -> device copy of the same frame buffer (the e2e pass is bound by it)
+    barrier()
+    c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    d["frames"].copy_(h["frames"], non_blocking=True)
+    c0.record(stream)
+    for _ in range(3):
+        d["frames"].copy_(h["frames"], non_blocking=True)
+    c1.record(stream)
+    torch.cuda.synchronize(dev)
+    h2d_copy_gbs = 3 * h["frames"].numel() / (c0.elapsed_time(c1) * 1e-3) / 1e9
     h2d = sum(int(h[k].numel() * h[k].element_size()) for k in ("frames", "desc", "kp", "prior"))
     n_chunks = (n_pairs + chunk - 1) // chunk
     n_host_chunks = (n_pairs + host_chunk - 1) // host_chunk
@@ -319,6 +329,11 @@ def run_gpu(args, rank, world, local_rank):
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
     hbm_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6.65 TB/s"
     popc_peak = ctx.popc_peak() / 1e9     # GPOPC/s, microbenchmarked on this GPU
+    knn_impl = int(os.environ.get("VSB_KNN_IMPL", "2"))
+    # tcgen05 kind::i8 runs at twice the bf16 rate; MEASURED_PEAKS.json holds the measured dense bf16 figure
+    i8_peak = 2.0 * float(peaks.get("bf16_tflops", 2250.0))
+    i8_src = ("2 x measured dense bf16 (MEASURED_PEAKS.json bf16_tflops); nominal int8 dense is 4500 TOP/s"
+              if "bf16_tflops" in peaks else "fallback: nominal 4500 TOP/s dense int8")
     lay = vb.pyr_layout(W, H)
     px_all = sum(lay.w[l] * lay.h[l] for l in range(lay.levels))
     px_gn = sum(lay.w[l] * lay.h[l] for l in range(4))
@@ -326,8 +341,10 @@ def run_gpu(args, rank, world, local_rank):
     pairs_total = stats["pairs"]
     alg = {
         # 8*N*M 32-bit POPC per frame pair, one distance matrix for both directions
-        "knn2_hamming": ("int", 8.0 * N_FEAT * N_FEAT * pairs_total, "GPOPC/s", popc_peak,
-                         "measured by vsb_popc_peak on this GPU"),
+        # tensor-core form (knn_impl 1/2): one +-1 byte per descriptor bit, 2 * N * M * 256 int8 ops per distance matrix
+        "knn2_hamming": (("int", 8.0 * N_FEAT * N_FEAT * pairs_total, "GPOPC/s", popc_peak,
+                          "measured by vsb_popc_peak on this GPU") if knn_impl == 0 else
+                         ("tensor", 2.0 * 256 * N_FEAT * N_FEAT * pairs_total / 1e3, "TOP/s", i8_peak, i8_src)),
         # 14 B per candidate point per iteration + one-time staging of cur I, prev I, gx, gy (6 B/px, levels 0-3)
         "gn_solve": ("hbm", 14.0 * stats["point_visits"] + 6.0 * px_gn * pairs_total, "GB/s", hbm_peak, hbm_src),
         # read w*h, write every level (level 0 is copied, as the reference's Camera::Update does)
@@ -355,7 +372,7 @@ def run_gpu(args, rank, world, local_rank):
 
     # ---- CPU baseline: the oracle on this box's host cores, bounded sample --------------------------
     cores = os.cpu_count() or 1
-    n_sample = int(os.environ.get("VSB_CPU_SAMPLE_PAIRS", "32"))
+    n_sample = int(os.environ.get("VSB_CPU_SAMPLE_PAIRS", "512"))
     ids = list(range(min(n_sample, n_pairs)))
     cpu_fps1, cpu_dt1, cpu_poses = cpu_track_sample(seq, ids, 1)
     dpose = np.stack(cpu_poses) - d_pose[: len(ids)].cpu().numpy()
@@ -370,7 +387,8 @@ def run_gpu(args, rank, world, local_rank):
                    "gn_iterations_per_pair": stats["iterations"] / max(1, pairs_total),
                    "gn_points_per_pair": stats["point_visits"] / max(1, pairs_total)},
         "e2e": {"value": e2e_value, "unit": "frames/s", "ms_per_step": e2e_ms_step, "h2d_bytes_per_step": h2d,
-                "d2h_bytes_per_step": d2h, "matches_device_path": same},
+                "d2h_bytes_per_step": d2h, "matches_device_path": same,
+                "h2d_gbs_achieved": h2d / (e2e_ms_step * 1e-3) / 1e9, "h2d_gbs_plain_copy": h2d_copy_gbs},
         "gpu_launches": int(launches),
         "clocks": clocks,
         "roofline": roofline,

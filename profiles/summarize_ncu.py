@@ -8,23 +8,42 @@ import sys
 
 
 def launches(path):
+    """Per-kernel totals, split into the device-resident pass (the launch(es) with the largest grid of each kernel:
+    the whole workload as one batch — what bench.py's `value` and per-kernel shares time) and the host-buffer (e2e)
+    pass, whose chunked launches are smaller."""
     rows = list(csv.reader(open(path)))
     hi = [i for i, r in enumerate(rows) if "Kernel Name" in r][0]
     hdr, data = rows[hi], rows[hi + 1:]
-    kn, mn, mv = hdr.index("Kernel Name"), hdr.index("Metric Name"), hdr.index("Metric Value")
-    agg = collections.OrderedDict()
+    kn, mn, mv, idc = hdr.index("Kernel Name"), hdr.index("Metric Name"), hdr.index("Metric Value"), hdr.index("ID")
+    per = collections.OrderedDict()      # launch id -> [name, time_ns, grid]
     for r in data:
-        if len(r) <= mv or r[mn] != "gpu__time_duration.sum":
+        if len(r) <= mv:
             continue
         name = r[kn].split("(")[0].replace("<unnamed>::", "").replace("void ", "")
-        a = agg.setdefault(name, [0, 0.0])
-        a[0] += 1
-        a[1] += float(r[mv].replace(",", ""))
-    tot = sum(v[1] for v in agg.values())
-    print(f"# ncu launch list ({path}): per-launch gpu__time_duration.sum, cold-cache and serialised — compare SHARES")
-    print(f"{'kernel':32s} {'launches':>8s} {'total_us':>12s} {'avg_us':>10s} {'share':>7s}")
-    for k, v in sorted(agg.items(), key=lambda kv: -kv[1][1]):
-        print(f"{k:32s} {v[0]:8d} {v[1] / 1e3:12.1f} {v[1] / 1e3 / v[0]:10.1f} {v[1] / tot:7.3f}")
+        e = per.setdefault(r[idc], [name, 0.0, 0])
+        if r[mn] == "gpu__time_duration.sum":
+            e[1] = float(r[mv].replace(",", ""))
+        elif r[mn] == "launch__grid_size":
+            e[2] = int(float(r[mv].replace(",", "")))
+    maxgrid = collections.defaultdict(int)
+    for name, t, g in per.values():
+        maxgrid[name] = max(maxgrid[name], g)
+    print(f"# ncu launch list ({path}): per-launch gpu__time_duration.sum, cold-cache and serialised - compare SHARES")
+    for title, pick in (("device-resident pass (largest grid per kernel = the whole workload in one batch)",
+                         lambda n, g: g == maxgrid[n]),
+                        ("host-buffer (e2e) pass: chunked launches", lambda n, g: g != maxgrid[n]),
+                        ("all launches", lambda n, g: True)):
+        agg = collections.OrderedDict()
+        for name, t, g in per.values():
+            if pick(name, g):
+                a = agg.setdefault(name, [0, 0.0])
+                a[0] += 1
+                a[1] += t
+        tot = sum(v[1] for v in agg.values()) or 1.0
+        print(f"\n## {title}")
+        print(f"{'kernel':32s} {'launches':>8s} {'total_us':>12s} {'avg_us':>10s} {'share':>7s}")
+        for k, v in sorted(agg.items(), key=lambda kv: -kv[1][1]):
+            print(f"{k:32s} {v[0]:8d} {v[1] / 1e3:12.1f} {v[1] / 1e3 / v[0]:10.1f} {v[1] / tot:7.3f}")
 
 
 WANT = ["gpu__time_duration.sum", "launch__grid_size", "launch__block_size", "launch__registers_per_thread",

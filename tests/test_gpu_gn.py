@@ -84,9 +84,11 @@ def test_gn_reference_mode_per_iteration(ctx, oracle, pair_small, n_cells, grad_
     print(f"n_cells={n_cells} grad_mode={grad_mode}: {len(ref_trace)} iterations, worst rot {wr:.2e} rad, trans {wt:.2e} m")
 
 
-@pytest.mark.parametrize("weight_mode,sample_mode", [(2, 0), (0, 1), (2, 1)])
+@pytest.mark.parametrize("weight_mode,sample_mode", [(2, 0), (0, 1), (2, 1), (1, 0), (1, 1)])
 def test_gn_extension_modes(ctx, oracle, pair_small, weight_mode, sample_mode):
-    """Huber weights / bilinear sampling (north-star extensions, oracle-defined)."""
+    """Tukey weights (VISystem::TukeyFunctionWeights / MedianAbsoluteDeviation / MedianMat, VISystem.cpp:1797-1870 —
+    the mode the reference has commented out at :1344), Huber weights and bilinear sampling (north-star extensions,
+    oracle-defined)."""
     import torch
     import vislam_b200 as vb
     p = pair_small

@@ -42,6 +42,8 @@ extern "C" int vsb_ctx_create(int device, vsb_ctx_t** out) {
     c->knn_impl = 2;
     c->gn_threads = 128;
     c->pyr_impl = 1;
+    c->gn_variant = 0;
+    if (const char* e = getenv("VSB_GN_VARIANT")) c->gn_variant = atoi(e);
     if (const char* e = getenv("VSB_KNN_IMPL")) vsb_ctx_option(c, "knn_impl", atoi(e));
     if (const char* e = getenv("VSB_GN_THREADS")) vsb_ctx_option(c, "gn_threads", atoi(e));
     *out = c;
@@ -53,6 +55,11 @@ extern "C" int vsb_ctx_option(vsb_ctx_t* ctx, const char* name, int value) {
     if (!strcmp(name, "knn_impl")) {
         if (value < 0 || value > 2) return VSB_ERR_INVALID;
         ctx->knn_impl = value;
+        return VSB_OK;
+    }
+    if (!strcmp(name, "gn_variant")) {
+        if (value < 0 || value > 6) return VSB_ERR_INVALID;
+        ctx->gn_variant = value;
         return VSB_OK;
     }
     if (!strcmp(name, "pyr_impl")) {

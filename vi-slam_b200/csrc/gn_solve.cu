@@ -24,7 +24,6 @@
 
 namespace {
 
-constexpr int U = 4;             // points per thread per batch
 constexpr int NRED = 28;         // 21 (upper triangle of J^T J) + 6 (J^T r) + 1 (sum w r^2)
 
 struct GnParams {
@@ -36,6 +35,7 @@ struct GnParams {
     vsb_pyr_layout_t lay;
     const float4* cand;
     uint2* patt;                 // [count][levels][cand_cap] {gx | gy << 16, I_prev}
+    float* resid;                // [count][cand_cap] residual scratch of the Tukey pre-pass (weight_mode 1 only)
     int cand_cap;
     const int32_t* n_cand;
     vsb_intr_t K[VSB_MAX_LEVELS];
@@ -177,10 +177,106 @@ __device__ __forceinline__ void warp_solve6(const double* G, int lane, float del
     }
 }
 
+// ---- Tukey weights (optional mode; upstream it is commented out at VISystem.cpp:1344) ---------------------------
+// TukeyFunctionWeights (:1797-1826) needs the scale 1.4826 * MAD of ALL residuals of the iteration before any weight
+// exists, and MedianMat (:1846-1870) takes both medians from a 256-bin histogram of the values saturate-cast to u8.
+// So the iteration gets a pre-pass: residuals -> histogram -> median -> histogram of |r - median| -> MAD.  The residual
+// arithmetic below is the same sequence of rounded operations as the main loop's (warp :1519-1553, round() :1321).
+struct LvlConst {
+    float fx, fy, cx, cy, invfx, invfy, frows, fcols;
+    int cols, rows, npix;
+};
+
+__device__ __forceinline__ bool point_residual(const float4 c, uint32_t i_prev, const double* md, const LvlConst& L,
+                                               const uint8_t* __restrict__ image2, int sample_mode, float& res) {
+    const float X = F_MUL(F_MUL(F_SUB(c.x, L.cx), L.invfx), c.z);
+    const float Y = F_MUL(F_MUL(F_SUB(c.y, L.cy), L.invfy), c.z);
+    const double dX = X, dY = Y, dZ = c.z, dW = c.w;
+    double s0 = md[0] * dX; s0 += md[1] * dY; s0 += md[2] * dZ; s0 += md[3] * dW;
+    double s1 = md[4] * dX; s1 += md[5] * dY; s1 += md[6] * dZ; s1 += md[7] * dW;
+    double s2 = md[8] * dX; s2 += md[9] * dY; s2 += md[10] * dZ; s2 += md[11] * dW;
+    const float r0 = (float)s0, r1 = (float)s1, r2 = (float)s2, r3 = c.w;
+    const float x2 = F_MUL(F_ADD(F_DIV(F_MUL(r0, L.fx), r2), L.cx), r3);
+    const float y2 = F_MUL(F_ADD(F_DIV(F_MUL(r1, L.fy), r2), L.cy), r3);
+    if (!((y2 > 0.f && y2 < L.frows && x2 > 0.f && x2 < L.fcols) && (r2 != 0.f))) return false;
+    const int ix = __float2int_rz(x2), iy = __float2int_rz(y2);
+    float i2;
+    if (sample_mode == 0) {
+        const int rx = ix + ((F_SUB(x2, (float)ix) >= 0.5f) ? 1 : 0);
+        const int ry = iy + ((F_SUB(y2, (float)iy) >= 0.5f) ? 1 : 0);
+        const int l = ry * L.cols + rx;
+        if (l >= L.npix) return false;
+        i2 = (float)__ldg(image2 + l);
+    } else {
+        if (ix + 1 >= L.cols || iy + 1 >= L.rows) return false;
+        const uint8_t* p0 = image2 + iy * L.cols + ix;
+        const float i00 = (float)__ldg(p0), i01 = (float)__ldg(p0 + 1);
+        const float i10 = (float)__ldg(p0 + L.cols), i11 = (float)__ldg(p0 + L.cols + 1);
+        const float ax = F_SUB(x2, floorf(x2)), ay = F_SUB(y2, floorf(y2));
+        const float top = F_ADD(i00, F_MUL(ax, F_SUB(i01, i00)));
+        const float bot = F_ADD(i10, F_MUL(ax, F_SUB(i11, i10)));
+        i2 = F_ADD(top, F_MUL(ay, F_SUB(bot, top)));
+    }
+    res = F_SUB(i2, (float)i_prev);
+    return true;
+}
+
+__device__ __forceinline__ int sat_u8(float v) {              // Mat::convertTo(CV_8U): saturate_cast<uchar>(cvRound(v))
+    return min(max(__float2int_rn(v), 0), 255);
+}
+
+// MedianMat's scan (:1856-1866): first bin whose running count exceeds (float)(n / 2); -1 when there is none (n == 0).
+__device__ float hist_median(const int* hist) {
+    int n = 0;
+    for (int i = 0; i < 256; i++) n += hist[i];
+    const float m = (float)(n / 2);
+    int bin = 0;
+    for (int i = 0; i < 256; i++) {
+        bin += hist[i];
+        if ((float)bin > m) return (float)i;
+    }
+    return -1.0f;
+}
+
+// Returns 1 / (1.4826 * MAD) as TukeyFunctionWeights forms it (MAD == 0 -> 1).  Called by every thread of the block.
+__device__ __noinline__ float tukey_inv_mad(const float4* __restrict__ cand, const uint2* __restrict__ patt,
+                                            float* __restrict__ resid, int ncand, const double* s_md, LvlConst L,
+                                            const uint8_t* __restrict__ image2, int sample_mode, int* s_hist,
+                                            float* s_val) {
+    const int tid = threadIdx.x, nt = blockDim.x;
+    for (int i = tid; i < 256; i += nt) s_hist[i] = 0;
+    __syncthreads();
+    for (int i = tid; i < ncand; i += nt) {
+        float res = 0.f;
+        const bool ok = point_residual(__ldg(cand + i), __ldg(patt + i).y, s_md, L, image2, sample_mode, res);
+        resid[i] = ok ? res : __int_as_float(0x7fc00000);
+        if (ok) atomicAdd(&s_hist[sat_u8(res)], 1);
+    }
+    __syncthreads();
+    if (tid == 0) s_val[0] = hist_median(s_hist);
+    __syncthreads();
+    const float median = s_val[0];
+    for (int i = tid; i < 256; i += nt) s_hist[i] = 0;
+    __syncthreads();
+    for (int i = tid; i < ncand; i += nt) {
+        const float r = resid[i];
+        if (r == r) atomicAdd(&s_hist[sat_u8(fabsf(F_SUB(r, median)))], 1);          // abs(_input - median), :1836
+    }
+    __syncthreads();
+    if (tid == 0) {
+        float mad = F_MUL(1.4826f, hist_median(s_hist));                               // c * MAD, :1841
+        if (mad == 0.f) mad = 1.f;                                                     // :1807-1810
+        s_val[1] = (float)(1.0 / (double)mad);                                         // :1811
+    }
+    __syncthreads();
+    return s_val[1];
+}
+
 constexpr int VROW = 36;   // staging row stride (floats): conflict-free for the [g][4s+t] reads of the MMA feed
 
-template <bool FP32_PARTIALS, int GT>
-__global__ void __launch_bounds__(GT, 768 / GT)
+// U = points per thread per batch; TPS = resident threads per SM the register budget is sized for
+template <bool FP32_PARTIALS, int GT, bool TUKEY, int U = 4, int TPS = 768>
+__global__ void __launch_bounds__(GT, TPS / GT)
 gn_solve_kernel(const GnParams P) {
     constexpr int NW = GT / 32;
     const int prob = blockIdx.x;
@@ -200,6 +296,8 @@ gn_solve_kernel(const GnParams P) {
     __shared__ float s_last_err;
     __shared__ unsigned long long s_pts;
     __shared__ int s_upd;
+    __shared__ int s_hist[TUKEY ? 256 : 1];
+    __shared__ float s_tk[2];
 
     const vsb_gn_opts_t& o = P.o;
     if (tid < 7) s_pose[tid] = P.pose_in[(size_t)prob * 7 + tid];
@@ -231,6 +329,14 @@ gn_solve_kernel(const GnParams P) {
                 for (int i = 0; i < 12; i++) s_md[i] = (double)m34[i];
             }
             __syncthreads();
+            float tk_inv_mad = 1.f;
+            if (TUKEY) {
+                LvlConst L;
+                L.fx = fx; L.fy = fy; L.cx = cx; L.cy = cy; L.invfx = invfx; L.invfy = invfy;
+                L.frows = frows; L.fcols = fcols; L.cols = cols; L.rows = rows; L.npix = npix;
+                tk_inv_mad = tukey_inv_mad(cand, patt, P.resid + (size_t)prob * P.cand_cap, ncand, s_md, L, image2,
+                                           o.sample_mode, s_hist, s_tk);
+            }
             double md[12];
 #pragma unroll
             for (int i = 0; i < 12; i++) md[i] = s_md[i];
@@ -330,7 +436,17 @@ gn_solve_kernel(const GnParams P) {
                     const int gyi = (int)(short)(at[u].x >> 16);                      // gradientY1, :1325
                     const float res = F_SUB(i2[u], u23_to_float(at[u].y));            // :1323
                     float wgt = 1.f;
-                    if (o.weight_mode == 2) {                                         // Huber extension
+                    if (TUKEY) {                                                      // Tukey, :1812-1823
+                        const float tk_b = 4.6851f;
+                        const float inv_b2 = (float)(1.0 / (double)F_MUL(tk_b, tk_b));
+                        const float x = F_MUL(res, tk_inv_mad);
+                        if (fabsf(x) <= tk_b) {
+                            const float tukey = (float)(1.0 - (double)F_MUL(F_MUL(x, x), inv_b2));
+                            wgt = F_MUL(tukey, tukey);
+                        } else {
+                            wgt = 0.f;
+                        }
+                    } else if (o.weight_mode == 2) {                                  // Huber extension
                         const float a = fabsf(res);
                         wgt = (a <= o.huber_k) ? 1.f : F_DIV(o.huber_k, a);
                     }
@@ -493,16 +609,24 @@ int vsb_gn_solve_stats(vsb_ctx_t* ctx, const uint8_t* prev_pyr, const uint8_t* c
     if (count < 0 || cand_cap < 0) return VSB_ERR_INVALID;
     if (opts->first_lvl >= layout->levels || opts->last_lvl < 0 || opts->first_lvl < opts->last_lvl)
         return VSB_ERR_INVALID;
-    if (opts->weight_mode != 0 && opts->weight_mode != 2) return VSB_ERR_UNSUPPORTED;   // Tukey (:1797-1826) is dead code upstream
+    if (opts->weight_mode < 0 || opts->weight_mode > 2) return VSB_ERR_UNSUPPORTED;     // 0 identity, 1 Tukey, 2 Huber
     if (opts->sample_mode != 0 && opts->sample_mode != 1) return VSB_ERR_UNSUPPORTED;
     if (opts->grad_mode == 0 && (!prev_gx || !prev_gy)) return VSB_ERR_INVALID;
     if (trace && (opts->first_lvl - opts->last_lvl + 1) * opts->max_iterations > VSB_MAX_TRACE) return VSB_ERR_CAPACITY;
     if (count == 0) return VSB_OK;
-    if (!patt_scratch) {
-        int rc = vsb_scratch_reserve(ctx, (size_t)count * layout->levels * cand_cap * sizeof(uint2) + 256, &patt_scratch);
+    // context scratch: [point attributes unless the caller owns them][Tukey residuals when weight_mode == 1]
+    const size_t patt_bytes = patt_scratch ? 0 : ((size_t)count * layout->levels * cand_cap * sizeof(uint2) + 255) & ~(size_t)255;
+    const size_t resid_bytes = opts->weight_mode == 1 ? (size_t)count * cand_cap * sizeof(float) : 0;
+    float* resid = nullptr;
+    if (patt_bytes + resid_bytes) {
+        void* scratch = nullptr;
+        int rc = vsb_scratch_reserve(ctx, patt_bytes + resid_bytes + 256, &scratch);
         if (rc) return rc;
+        if (!patt_scratch) patt_scratch = scratch;
+        if (resid_bytes) resid = reinterpret_cast<float*>(static_cast<uint8_t*>(scratch) + patt_bytes);
     }
     GnParams P;
+    P.resid = resid;
     P.prev_pyr = prev_pyr; P.cur_pyr = cur_pyr; P.prev_gx = prev_gx; P.prev_gy = prev_gy;
     P.pair_stride = pair_stride_pixels;
     P.lay = *layout;
@@ -534,8 +658,21 @@ int vsb_gn_solve_stats(vsb_ctx_t* ctx, const uint8_t* prev_pyr, const uint8_t* c
     }
     ProfScope ps(ctx, VSB_K_GN_SOLVE, st);
     const int gt_env = ctx->gn_threads;
-#define GN_LAUNCH(FP, T) gn_solve_kernel<FP, T><<<count, T, 0, st>>>(P)
-    if (opts->accum_mode == 1) {
+#define GN_LAUNCH(FP, T)                                                                 \
+    do {                                                                                 \
+        if (opts->weight_mode == 1) gn_solve_kernel<FP, T, true><<<count, T, 0, st>>>(P); \
+        else gn_solve_kernel<FP, T, false><<<count, T, 0, st>>>(P);                      \
+    } while (0)
+    if (ctx->gn_variant > 0 && opts->accum_mode == 0 && opts->weight_mode != 1 && gt_env == 128) {   // tuning experiments
+        switch (ctx->gn_variant) {
+            case 1: gn_solve_kernel<false, 128, false, 2, 1024><<<count, 128, 0, st>>>(P); break;
+            case 2: gn_solve_kernel<false, 128, false, 2, 1280><<<count, 128, 0, st>>>(P); break;
+            case 3: gn_solve_kernel<false, 128, false, 1, 1536><<<count, 128, 0, st>>>(P); break;
+            case 4: gn_solve_kernel<false, 128, false, 2, 768><<<count, 128, 0, st>>>(P); break;
+            case 5: gn_solve_kernel<false, 128, false, 4, 640><<<count, 128, 0, st>>>(P); break;
+            default: gn_solve_kernel<false, 128, false, 4, 512><<<count, 128, 0, st>>>(P); break;
+        }
+    } else if (opts->accum_mode == 1) {
         if (gt_env == 64) GN_LAUNCH(true, 64); else if (gt_env == 128) GN_LAUNCH(true, 128); else GN_LAUNCH(true, 256);
     } else {
         if (gt_env == 64) GN_LAUNCH(false, 64); else if (gt_env == 128) GN_LAUNCH(false, 128); else GN_LAUNCH(false, 256);
