@@ -11,6 +11,23 @@ pytestmark = pytest.mark.gpu
 HERE = os.path.dirname(os.path.abspath(__file__))
 
 
+@pytest.fixture(autouse=True, params=[1, 0], ids=["tensor-core", "exact-fp64"])
+def l2_impl(request, ctx):
+    """Every case runs through both float-kNN implementations: knn_l2_impl 1 = tcgen05 TF32x3 distance GEMM + exact
+    re-check (dim <= 64, dim % 8 == 0; other dimensions dispatch to the exact kernel) and 0 = the exact FP64 kernel."""
+    ctx.option("knn_l2_impl", request.param)
+    yield request.param
+    ctx.option("knn_l2_impl", 1)
+
+
+def _fallback_rows(ctx):
+    import ctypes
+    import vislam_b200 as vb
+    v = ctypes.c_longlong()
+    vb.check(vb.lib().vsb_debug_l2_fallback_rows(ctx.handle, ctypes.byref(v)), ctx.handle)
+    return v.value
+
+
 def _run(ctx, d1, d2, n1=None, n2=None):
     import torch
     t1 = torch.from_numpy(d1).cuda()
@@ -33,7 +50,8 @@ def _check_pair(oracle, d1, d2, got):
 
 @pytest.mark.parametrize("n1,n2,dim", [(1000, 1000, 64), (64, 64, 64), (65, 129, 64), (1, 1, 64), (2, 1, 64),
                                        (1, 2, 64), (3, 500, 64), (500, 3, 64), (257, 1023, 128), (300, 200, 61),
-                                       (130, 70, 7)])
+                                       (130, 70, 7), (128, 128, 64), (129, 127, 32), (400, 300, 8), (333, 777, 40),
+                                       (5000, 5000, 64), (2, 2, 16), (3, 3, 64), (4, 2, 24)])
 def test_knn_l2_random(ctx, oracle, n1, n2, dim):
     rng = np.random.default_rng(n1 * 7919 + n2 + dim)
     d1 = rng.standard_normal((n1, dim)).astype(np.float32)
@@ -100,3 +118,37 @@ def test_knn_l2_cv2_golden(ctx):
     np.testing.assert_array_equal(got[2], g["fidx21"])
     np.testing.assert_allclose(got[1], g["fdist12"], rtol=1e-6, atol=1e-7)
     np.testing.assert_allclose(got[3], g["fdist21"], rtol=1e-6, atol=1e-7)
+
+
+def test_knn_l2_tensor_core_fallback_is_rare_and_exact(ctx, oracle, l2_impl):
+    """The tensor-core path may only SELECT: rows whose candidate set cannot be proven complete are recomputed
+    exhaustively.  On well-separated data that is (almost) never needed; on near-duplicate clusters it is, and the
+    result is still bit-exact."""
+    if l2_impl != 1:
+        pytest.skip("tensor-core path only")
+    from vislam_b200 import synth
+    d1 = synth.float_descriptors(2000, 3001)
+    d2, _ = synth.perturb_float(d1, 3002)
+    got = _run(ctx, d1, d2)
+    rows = _fallback_rows(ctx)
+    _check_pair(oracle, d1, d2, got)
+    assert rows <= 40, rows                                        # 4000 rows in total
+    # clusters of near-duplicates (differences ~1e-6): the approximate scores cannot separate them
+    rng = np.random.default_rng(21)
+    centres = rng.standard_normal((25, 64)).astype(np.float32)
+    c1 = (centres[rng.integers(0, 25, 600)] + 1e-6 * rng.standard_normal((600, 64))).astype(np.float32)
+    c2 = (centres[rng.integers(0, 25, 700)] + 1e-6 * rng.standard_normal((700, 64))).astype(np.float32)
+    got = _run(ctx, c1, c2)
+    rows = _fallback_rows(ctx)
+    _check_pair(oracle, c1, c2, got)
+    assert rows > 100, rows
+
+
+def test_knn_l2_scaled_and_offset_data(ctx, oracle):
+    """Norms far from 1 and a large common offset (cancellation in |a|^2 + |b|^2 - 2ab): the bound scales with the data."""
+    rng = np.random.default_rng(33)
+    for scale, offset in ((1e3, 0.0), (1e-3, 0.0), (1.0, 50.0), (255.0, 128.0)):
+        d1 = (rng.standard_normal((300, 64)) * scale + offset).astype(np.float32)
+        d2 = (rng.standard_normal((260, 64)) * scale + offset).astype(np.float32)
+        d2[:100] = d1[:100] + (0.01 * scale * rng.standard_normal((100, 64))).astype(np.float32)
+        _check_pair(oracle, d1, d2, _run(ctx, d1, d2))

@@ -37,12 +37,17 @@ extern "C" int vsb_ctx_create(int device, vsb_ctx_t** out) {
     c->last_error[0] = 0;
     c->scratch = nullptr;
     c->scratch_bytes = 0;
+    c->scratch2 = nullptr;
+    c->scratch2_bytes = 0;
+    c->l2_fallback_counter = nullptr;
     c->prof_on = 0;
     for (int i = 0; i < VSB_K_COUNT; i++) { c->prof_ms[i] = 0.0; c->prof_n[i] = 0; }
     c->knn_impl = 2;
     c->gn_threads = 128;
     c->pyr_impl = 1;
     c->gn_variant = 0;
+    c->knn_l2_impl = 1;
+    if (const char* e = getenv("VSB_KNN_L2_IMPL")) c->knn_l2_impl = atoi(e) ? 1 : 0;
     if (const char* e = getenv("VSB_GN_VARIANT")) c->gn_variant = atoi(e);
     if (const char* e = getenv("VSB_KNN_IMPL")) vsb_ctx_option(c, "knn_impl", atoi(e));
     if (const char* e = getenv("VSB_GN_THREADS")) vsb_ctx_option(c, "gn_threads", atoi(e));
@@ -55,6 +60,11 @@ extern "C" int vsb_ctx_option(vsb_ctx_t* ctx, const char* name, int value) {
     if (!strcmp(name, "knn_impl")) {
         if (value < 0 || value > 2) return VSB_ERR_INVALID;
         ctx->knn_impl = value;
+        return VSB_OK;
+    }
+    if (!strcmp(name, "knn_l2_impl")) {
+        if (value < 0 || value > 1) return VSB_ERR_INVALID;
+        ctx->knn_l2_impl = value;
         return VSB_OK;
     }
     if (!strcmp(name, "gn_variant")) {
@@ -78,6 +88,7 @@ extern "C" int vsb_ctx_option(vsb_ctx_t* ctx, const char* name, int value) {
 extern "C" int vsb_ctx_destroy(vsb_ctx_t* ctx) {
     if (!ctx) return VSB_ERR_INVALID;
     if (ctx->scratch) cudaFree(ctx->scratch);
+    if (ctx->scratch2) cudaFree(ctx->scratch2);
     for (auto& r : ctx->prof_pending) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
     for (auto e : ctx->prof_free) cudaEventDestroy(e);
     delete ctx;
@@ -98,6 +109,20 @@ int vsb_scratch_reserve(vsb_ctx* ctx, size_t bytes, void** out) {
         ctx->scratch_bytes = want;
     }
     *out = ctx->scratch;
+    return VSB_OK;
+}
+
+int vsb_scratch2_reserve(vsb_ctx* ctx, size_t bytes, void** out) {
+    if (bytes > ctx->scratch2_bytes) {
+        if (ctx->scratch2) VSB_CUDA(ctx, cudaFree(ctx->scratch2));
+        ctx->scratch2 = nullptr;
+        ctx->scratch2_bytes = 0;
+        ctx->l2_fallback_counter = nullptr;
+        size_t want = bytes + bytes / 4;
+        VSB_CUDA(ctx, cudaMalloc(&ctx->scratch2, want));
+        ctx->scratch2_bytes = want;
+    }
+    *out = ctx->scratch2;
     return VSB_OK;
 }
 

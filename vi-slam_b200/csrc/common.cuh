@@ -25,6 +25,9 @@ struct vsb_ctx {
     // scratch owned by the context (grown on demand, freed in vsb_ctx_destroy)
     void* scratch;
     size_t scratch_bytes;
+    void* scratch2;          // second area: internals of an entry whose caller already holds `scratch`
+    size_t scratch2_bytes;
+    unsigned long long* l2_fallback_counter;   // device counter of the last tensor-core L2 kNN call (diagnostics)
     // optional per-kernel timing with CUDA events on the launching stream (bench.py's roofline leg)
     int prof_on;
     std::vector<vsb_prof_rec> prof_pending;
@@ -35,6 +38,7 @@ struct vsb_ctx {
     int knn_impl;     // Hamming kNN: 0 = POPC kernel (INT pipe), 1 = tcgen05 tensor-core kernel, 32-bit epilogue,
                       //              2 = tcgen05 kernel with the packed 16x2 epilogue
     int gn_threads;   // threads per frame pair of the GN solver: 64 / 128 / 256
+    int knn_l2_impl;  // float kNN: 0 = exact FP64 kernel, 1 = tensor-core GEMM + exact re-check (dim <= 64, dim % 8 == 0)
     int gn_variant;   // GN solver register/unroll variant (tuning experiments; 0 = default)
     int pyr_impl;     // pyramid: 0 = generic shared-memory tile kernel, 1 = register-blocked kernel when w, h are multiples of 16
 };
@@ -68,5 +72,6 @@ static inline int vsb_cuda_fail(vsb_ctx* ctx, cudaError_t e, const char* what) {
     } while (0)
 
 int vsb_scratch_reserve(vsb_ctx* ctx, size_t bytes, void** out);
+int vsb_scratch2_reserve(vsb_ctx* ctx, size_t bytes, void** out);
 
 static inline int vsb_div_up(int a, int b) { return (a + b - 1) / b; }

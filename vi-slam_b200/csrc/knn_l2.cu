@@ -168,6 +168,10 @@ __global__ void knn_unpack64_kernel(const unsigned long long* __restrict__ keys,
 
 }  // namespace
 
+int vsb_knn2_l2_tc(vsb_ctx* ctx, const float* d1, int n1_max, const int32_t* n1, const float* d2, int n2_max,
+                   const int32_t* n2, int dim, int count, unsigned long long* key12, unsigned long long* key21,
+                   cudaStream_t st);
+
 // Internal entry (tracker too): leaves packed 64-bit keys (float bits << 32 | index) in key12 / key21.
 int vsb_knn2_l2_keys(vsb_ctx* ctx, const float* d1, int n1_max, const int32_t* n1, const float* d2, int n2_max,
                      const int32_t* n2, int dim, int count, unsigned long long* key12, unsigned long long* key21,
@@ -178,6 +182,8 @@ int vsb_knn2_l2_keys(vsb_ctx* ctx, const float* d1, int n1_max, const int32_t* n
     if (n1_max > 0) VSB_CUDA(ctx, cudaMemsetAsync(key12, 0xFF, (size_t)count * n1_max * 2 * sizeof(unsigned long long), st));
     if (n1_max == 0 || n2_max == 0) return VSB_OK;
     if (!d1 || !d2) return VSB_ERR_INVALID;
+    if (ctx->knn_l2_impl == 1 && dim <= 64 && (dim & 7) == 0 && ((((uintptr_t)d1 | (uintptr_t)d2) & 15) == 0))
+        return vsb_knn2_l2_tc(ctx, d1, n1_max, n1, d2, n2_max, n2, dim, count, key12, key21, st);
     const int row_tiles = vsb_div_up(n1_max, LQ);
     const int col_tiles = vsb_div_up(n2_max, LT);
     int chunks = 1;
