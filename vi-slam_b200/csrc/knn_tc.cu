@@ -12,12 +12,14 @@
 // (distance asc, lowest index first) order exactly.  The second direction (knnMatch(d2, d1)) is the same
 // kernel with the operands swapped (blockIdx.y): tensor work is cheap, cross-lane column reductions are not.
 //
-// Packed epilogue (PACK16).  One extra UMMA with a constant operand (a single byte -128 per row, 128 * 128 = 16384)
-// biases the accumulator to dot' = dot + 16384 = 128 * (256 - hamming) in [0, 32768]; tcgen05.ld.pack::16b then
-// delivers TWO columns per register, and  key16 = hamming << 7 | column_in_tile = 32768 + c - dot'  is one
-// subtraction for both halves.
-// Top-2 selection runs on the 16x2 SIMD min/max unit (VIMNMX.U16x2), 1.5 ALU instructions per distance
-// instead of 3, and the per-tile winners are folded into the global 32-bit keys (distance << 23 | index).
+// Packed epilogue (PACK16).  One extra UMMA with small constant operands (row: -128, 1, 1; column c of a tile:
+// -128, 127 - c, 1) adds 16384 + (128 - c) to every accumulator element, so the tensor core itself delivers the
+// selection key   key16 = 128 * (256 - hamming) + (128 - c)  in [1, 32896]:  larger key == smaller distance, ties ->
+// lower column, exactly cv::BFMatcher's order.  tcgen05.ld.pack::16b then delivers TWO columns per register and the
+// top-2 selection runs directly on the loaded registers on the 16x2 SIMD min/max unit (VIMNMX.U16x2, 2.5 ALU
+// instructions per pair of distances, no per-element key arithmetic at all).  Columns past the end of the set carry an
+// all-zero operand row and an all-zero bias column: key 0, which loses to every real column.  The per-tile winners are
+// folded into the global 32-bit keys (distance << 23 | index).
 //
 // Pipeline (warp-specialised, 288 threads, 2 CTAs per SM):
 //   warps 0-3  epilogue: wait tfull[s] -> tcgen05.ld -> top-2 -> arrive tempty[s]
@@ -41,7 +43,7 @@ constexpr int OP_BYTES = 2 * KB_BYTES;     // 256 K-bytes per row -> two K block
 constexpr int OFF_A = 0;
 constexpr int OFF_B = OFF_A + OP_BYTES;
 constexpr int OFF_BIAS = OFF_B + 2 * OP_BYTES;
-constexpr int OFF_BAR = OFF_BIAS + 4096;
+constexpr int OFF_BAR = OFF_BIAS + 3 * 4096;     // bias operands: row side, column side (full tile), column side (last tile)
 constexpr int TC_SMEM = OFF_BAR + 128;
 constexpr int TMEM_COLS = 2 * TN;
 
@@ -55,8 +57,15 @@ constexpr uint32_t IDESC_I8 = umma::idesc(/*D s32*/ 2, /*A s8*/ 1, /*B s8*/ 1, T
 //   COLS = false (row operand, once per CTA):  +1 / -1   = 0xFFFFFFFF - 254 * ((w >> m) & 0x01010101)
 //   COLS = true  (column operand, per tile):   +64 / -64 = ((w << (7 - m)) & 0x80808080) ^ 0xC0C0C0C0
 template <bool COLS>
-__device__ __forceinline__ void expand_row(uint8_t* rowp, const uint32_t (&coff)[8], const uint4& r0, const uint4& r1) {
+__device__ __forceinline__ void expand_row(uint8_t* rowp, const uint32_t (&coff)[8], const uint4& r0, const uint4& r1,
+                                           bool valid = true) {
     const uint32_t w[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+    if (COLS && !valid) {                                // column past the end of the set: all-zero operand row, dot = 0
+#pragma unroll
+        for (int c = 0; c < 16; c++)
+            *reinterpret_cast<uint4*>(rowp + (c >> 3) * KB_BYTES + coff[c & 7]) = make_uint4(0u, 0u, 0u, 0u);
+        return;
+    }
 #pragma unroll
     for (int c = 0; c < 16; c++) {                       // chunk c = slots 4 (c & 1) .. + 3 of raw word c / 2
         const uint32_t word = w[c >> 1];
@@ -71,32 +80,26 @@ __device__ __forceinline__ void expand_row(uint8_t* rowp, const uint32_t (&coff)
     }
 }
 
-__device__ __forceinline__ void top2_insert_u16x2(uint32_t& b0, uint32_t& b1, uint32_t x) {
-    const uint32_t hi = __vmaxu2(b0, x);
-    b0 = __vminu2(b0, x);
-    b1 = __vminu2(b1, hi);
+// top-2 LARGEST of packed u16x2 keys; two candidates at once: 5 instructions (the 3-input max is one VIMNMX3.U16x2)
+__device__ __forceinline__ void top2max_insert2_u16x2(uint32_t& b0, uint32_t& b1, uint32_t x, uint32_t y) {
+    const uint32_t hi = __vmaxu2(x, y), lo = __vminu2(x, y);
+    const uint32_t t = __vminu2(b0, hi);
+    b0 = __vmaxu2(b0, hi);
+    b1 = __vimax3_u16x2(b1, t, lo);
 }
-// two candidates at once: 5 instructions (the 3-input min is one VIMNMX3.U16x2)
-__device__ __forceinline__ void top2_insert2_u16x2(uint32_t& b0, uint32_t& b1, uint32_t x, uint32_t y) {
-    const uint32_t lo = __vminu2(x, y), hi = __vmaxu2(x, y);
-    const uint32_t t = __vmaxu2(b0, lo);
-    b0 = __vminu2(b0, lo);
-    b1 = __vimin3_u16x2(b1, t, hi);
-}
-__device__ __forceinline__ void top2_merge_u16x2(uint32_t& a0, uint32_t& a1, uint32_t o0, uint32_t o1) {
-    const uint32_t hi = __vmaxu2(a0, o0);
-    const uint32_t lo2 = __vminu2(a1, o1);
-    a0 = __vminu2(a0, o0);
-    a1 = __vminu2(hi, lo2);
+__device__ __forceinline__ void top2max_merge_u16x2(uint32_t& a0, uint32_t& a1, uint32_t o0, uint32_t o1) {
+    const uint32_t lo = __vminu2(a0, o0);
+    const uint32_t hi2 = __vmaxu2(a1, o1);
+    a0 = __vmaxu2(a0, o0);
+    a1 = __vmaxu2(lo, hi2);
 }
 
-// One 128-column accumulator tile, packed epilogue: two tcgen05.ld.pack::16b (64 columns each), keys for two columns per
-// IMAD, pairwise top-2 insertion on the 16x2 SIMD unit, then the tile's winners folded into the global keys.
-// MASKED is the last, partial tile (columns >= n_cols must never win); full tiles carry no per-element masking.
-template <bool MASKED>
-__device__ __forceinline__ void epilogue_tile_pack16(uint32_t taddr, uint32_t tempty_bar, int col0, int n_cols,
+// One 128-column accumulator tile, packed epilogue: two tcgen05.ld.pack::16b (64 columns each) deliver the selection keys
+// themselves (see the header); pairwise top-2 insertion on the 16x2 SIMD unit, then the tile's winners are folded into
+// the global keys.  No per-element arithmetic and no masking: out-of-range columns arrive as key 0.
+__device__ __forceinline__ void epilogue_tile_pack16(uint32_t taddr, uint32_t tempty_bar, int col0,
                                                      uint32_t& gb0, uint32_t& gb1) {
-    uint32_t pb0[2] = {0xFFFFFFFFu, 0xFFFFFFFFu}, pb1[2] = {0xFFFFFFFFu, 0xFFFFFFFFu};
+    uint32_t pb0[2] = {0u, 0u}, pb1[2] = {0u, 0u};
 #pragma unroll
     for (int half = 0; half < 2; half++) {
         uint32_t v[32];
@@ -104,24 +107,17 @@ __device__ __forceinline__ void epilogue_tile_pack16(uint32_t taddr, uint32_t te
         umma::tmem_wait_ld();
         if (half == 1) { umma::fence_before_sync(); umma::mbar_arrive(tempty_bar); }   // accumulator stage is free again
 #pragma unroll
-        for (int i = 0; i < 32; i++) {
-            const uint32_t c = half * 64 + 2 * i;
-            const uint32_t k2 = ((32768u + c + 1u) << 16) | (32768u + c);
-            v[i] = k2 - v[i];                                  // both halves: 32768 + c - dot'  (= hamming << 7 | c)
-            if (MASKED) {
-                if (col0 + (int)c >= n_cols) v[i] |= 0x0000FFFFu;
-                if (col0 + (int)c + 1 >= n_cols) v[i] |= 0xFFFF0000u;
-            }
-        }
-#pragma unroll
-        for (int i = 0; i < 32; i += 2) top2_insert2_u16x2(pb0[(i >> 1) & 1], pb1[(i >> 1) & 1], v[i], v[i + 1]);
+        for (int i = 0; i < 32; i += 2) top2max_insert2_u16x2(pb0[(i >> 1) & 1], pb1[(i >> 1) & 1], v[i], v[i + 1]);
     }
-    top2_merge_u16x2(pb0[0], pb1[0], pb0[1], pb1[1]);
+    top2max_merge_u16x2(pb0[0], pb1[0], pb0[1], pb1[1]);
+    // a register holds columns (2i, 2i+1) of its 64-column half in its (low, high) 16 bits: the column inside the half
+    // tile comes from the key itself (128 - c_tile), so halves need no bookkeeping
     const uint32_t k16[4] = {pb0[0] & 0xFFFFu, pb0[0] >> 16, pb1[0] & 0xFFFFu, pb1[0] >> 16};
 #pragma unroll
     for (int q = 0; q < 4; q++) {
-        const uint32_t g = (k16[q] == 0xFFFFu) ? KEY_INF
-                                               : (((k16[q] >> 7) << KEY_SHIFT) | (uint32_t)(col0 + (int)(k16[q] & 127u)));
+        const uint32_t t = k16[q] - 1u;                         // 128 * (256 - hamming) + (127 - c)
+        const uint32_t g = (k16[q] == 0u) ? KEY_INF
+                                          : (((256u - (t >> 7)) << KEY_SHIFT) | (uint32_t)(col0 + 127 - (int)(t & 127u)));
         top2_insert(gb0, gb1, g);
     }
 }
@@ -186,10 +182,22 @@ knn2_hamming_tc_kernel(const uint8_t* __restrict__ d1, int n1_max, const int32_t
         umma::fence_mbar_init();
     }
     if (warp == 8) umma::tmem_alloc<TMEM_COLS>(umma::smem_u32(tmem_slot));
-    // bias operand (no swizzle, K-major): 8-row core matrices of 16-byte rows, 128 bytes apart (SBO); the second
-    // 16-byte K column 2048 bytes further (LBO).  K element 0 of every row is -128, everything else 0.
-    for (int ci = tid; ci < 256; ci += TC_THREADS)
-        reinterpret_cast<uint4*>(sBias)[ci] = make_uint4(ci < 128 ? 0x80u : 0u, 0u, 0u, 0u);
+    // bias operands (no swizzle, K-major): 8-row core matrices of 16-byte rows, 128 bytes apart (SBO); the second
+    // 16-byte K column 2048 bytes further (LBO).  Row side: K elements (-128, 1, 1, 0, ...); column side, column c of a
+    // tile: (-128, 127 - c, 1, 0, ...), so the extra UMMA adds 16384 + (128 - c); columns past the end of the set are all
+    // zero (only the last tile can have them).
+    {
+        const int last_valid = n_cols - (T - 1) * TN;
+        for (int ci = tid; ci < 3 * 256; ci += TC_THREADS) {
+            const int which = ci >> 8, r = ci & 255;
+            uint32_t w0 = 0u;
+            if (r < 128) {
+                if (which == 0) w0 = 0x00010180u;
+                else if (which == 1 || r < last_valid) w0 = 0x00010080u | ((uint32_t)(127 - r) << 8);
+            }
+            reinterpret_cast<uint4*>(sBias)[ci] = make_uint4(w0, 0u, 0u, 0u);
+        }
+    }
     umma::fence_proxy_async();
     umma::fence_before_sync();
     __syncthreads();
@@ -212,8 +220,7 @@ knn2_hamming_tc_kernel(const uint8_t* __restrict__ d1, int n1_max, const int32_t
             const int col0 = j * TN;
             const bool full = col0 + TN <= n_cols;
             if (PACK16) {
-                if (full) epilogue_tile_pack16<false>(taddr, BAR(6 + s), col0, n_cols, gb0, gb1);
-                else epilogue_tile_pack16<true>(taddr, BAR(6 + s), col0, n_cols, gb0, gb1);
+                epilogue_tile_pack16(taddr, BAR(6 + s), col0, gb0, gb1);
             } else {
                 // the variant is chosen by a CTA-uniform condition: tcgen05.ld is warp-collective
                 const bool dumping = dump != nullptr && dir == 0 && prob == 0;
@@ -246,11 +253,12 @@ knn2_hamming_tc_kernel(const uint8_t* __restrict__ d1, int n1_max, const int32_t
         for (int j = 0; j < T; j++) {
             const int s = j & 1, n = j >> 1;
             const uint4 c0 = n0, c1 = n1v;
+            const bool cvalid = j * TN + p < n_cols;
             const int cn = (j + 1) * TN + p;
             if (j + 1 < T && cn < n_cols) { n0 = __ldg(g_cols + (size_t)cn * 2); n1v = __ldg(g_cols + (size_t)cn * 2 + 1); }
             else { n0 = zero; n1v = zero; }
             umma::mbar_wait(BAR(2 + s), (n & 1) ^ 1);                  // the UMMAs that read this stage have completed
-            expand_row<true>(sB + s * OP_BYTES + row_off, coff, c0, c1);
+            expand_row<true>(sB + s * OP_BYTES + row_off, coff, c0, c1, cvalid);
             umma::fence_proxy_async();
             umma::mbar_arrive(BAR(0 + s));
         }
@@ -258,7 +266,9 @@ knn2_hamming_tc_kernel(const uint8_t* __restrict__ d1, int n1_max, const int32_t
         // ===================================== UMMA issuer ==================================================
         if (lane == 0) {
             const uint32_t aA = umma::smem_u32(sA), aB = umma::smem_u32(sB), aBias = umma::smem_u32(sBias);
-            const uint64_t bias_desc = umma::smem_desc(aBias, /*LBO*/ 2048, /*SBO*/ 128, umma::LAYOUT_NONE);
+            const uint64_t abias_desc = umma::smem_desc(aBias, /*LBO*/ 2048, /*SBO*/ 128, umma::LAYOUT_NONE);
+            const uint64_t bbias_full = umma::smem_desc(aBias + 4096, 2048, 128, umma::LAYOUT_NONE);
+            const uint64_t bbias_last = umma::smem_desc(aBias + 8192, 2048, 128, umma::LAYOUT_NONE);
             for (int j = 0; j < T; j++) {
                 const int s = j & 1, n = j >> 1;
                 umma::mbar_wait(BAR(0 + s), n & 1);                    // operands of tile j are in shared memory
@@ -272,7 +282,7 @@ knn2_hamming_tc_kernel(const uint8_t* __restrict__ d1, int n1_max, const int32_t
                     const uint64_t db = umma::smem_desc(aB + s * OP_BYTES + off, 16, 1024, umma::LAYOUT_SW128);
                     umma::mma_i8(d_tmem, da, db, IDESC_I8, k > 0 ? 1u : 0u);
                 }
-                if (PACK16) umma::mma_i8(d_tmem, bias_desc, bias_desc, IDESC_I8, 1u);   // + (-128) * (-128) = 16384
+                if (PACK16) umma::mma_i8(d_tmem, abias_desc, j == T - 1 ? bbias_last : bbias_full, IDESC_I8, 1u);
                 umma::commit(BAR(2 + s));
                 umma::commit(BAR(4 + s));
             }
