@@ -352,6 +352,14 @@ def run_gpu(args, rank, world, local_rank):
         # read every level once, write gx and gy (int16) for the previous frame of every pair
         "gradient": ("hbm", 5.0 * px_all * pairs_total, "GB/s", hbm_peak, hbm_src),
     }
+    # DRAM traffic per launch of the dominant kernels, from the committed ncu --set full capture of this same workload
+    traffic = {}
+    try:
+        tj = json.load(open(os.path.join(ROOT, "profiles", "traffic_r1.json")))
+        if n_frames == N_FRAMES and chunk == n_frames - 1:      # the capture is of the full workload in one batch
+            traffic = {k: v["dram_bytes_read"] + v["dram_bytes_write"] for k, v in tj["per_launch"].items()}
+    except Exception:
+        pass
     total_prof_ms = sum(v[0] for v in prof.values()) or 1.0
     kernels = []
     for name, (kms, n) in sorted(prof.items(), key=lambda kv: -kv[1][0]):
@@ -361,7 +369,12 @@ def run_gpu(args, rank, world, local_rank):
             bound, work, unit, peak, src = alg[name]
             ach = work / (kms * 1e-3) / 1e9
             ent.update({"bound": bound, "achieved": ach, "peak": peak, "unit": unit, "frac": ach / peak,
-                        "peak_source": src, "traffic": None})
+                        "peak_source": src, "traffic": traffic.get(name),
+                        "algorithmic_per_launch": work / max(1, n)})
+            if name == "gn_solve":
+                ent["note"] = ("bound as SURVEY 8(d) defines it (algorithmic bytes over HBM peak); ncu shows the kernel "
+                               "limited by the XU pipe (FP32<->FP64 conversions, 57 %) and instruction issue (59 %), "
+                               "DRAM at 14 %: profiles/r1_full_topkernels_v3.txt")
         kernels.append(ent)
     dom = next((k for k in kernels if "bound" in k), None)
     roofline = None
