@@ -17,6 +17,10 @@
 #define CV_8U 0
 #define CV_32S 4
 #define CV_32F 5
+#define CV_64F 6
+#define CV_8UC1 CV_8U
+#define CV_32FC1 CV_32F
+#define CV_64FC1 CV_64F
 #define CV_SORT_EVERY_ROW 0
 #define CV_SORT_ASCENDING 0
 
@@ -25,6 +29,57 @@ namespace cv {
 enum { NORM_L2 = 4, NORM_HAMMING = 6 };
 
 struct Point2f { float x = 0, y = 0; };
+
+// cv::Point3_ / cv::Matx33f as the reference's Plus / DataReader / Imu sources use them (containers + the element-wise
+// operators OpenCV defines; Matx product and Matx * Point3f accumulate in float like cv::Matx does)
+template <typename T>
+struct Point3_ {
+    T x, y, z;
+    Point3_() : x(0), y(0), z(0) {}
+    Point3_(T a, T b, T c) : x(a), y(b), z(c) {}
+    template <typename U> Point3_(const Point3_<U>& o) : x((T)o.x), y((T)o.y), z((T)o.z) {}
+};
+template <typename T> Point3_<T> operator+(const Point3_<T>& a, const Point3_<T>& b) { return Point3_<T>(a.x + b.x, a.y + b.y, a.z + b.z); }
+template <typename T> Point3_<T> operator-(const Point3_<T>& a, const Point3_<T>& b) { return Point3_<T>(a.x - b.x, a.y - b.y, a.z - b.z); }
+template <typename T> Point3_<T> operator-(const Point3_<T>& a) { return Point3_<T>(-a.x, -a.y, -a.z); }
+template <typename T> Point3_<T> operator*(const Point3_<T>& a, double s) { return Point3_<T>((T)(a.x * s), (T)(a.y * s), (T)(a.z * s)); }
+template <typename T> Point3_<T> operator/(const Point3_<T>& a, int s) { return Point3_<T>((T)(a.x / s), (T)(a.y / s), (T)(a.z / s)); }
+template <typename T> Point3_<T> operator/(const Point3_<T>& a, double s) { return Point3_<T>((T)(a.x / s), (T)(a.y / s), (T)(a.z / s)); }
+typedef Point3_<float> Point3f;
+typedef Point3_<double> Point3d;
+
+struct Matx33f {
+    float val[9];
+    Matx33f() { for (int i = 0; i < 9; i++) val[i] = 0.f; }
+    float& operator()(int r, int c) { return val[3 * r + c]; }
+    const float& operator()(int r, int c) const { return val[3 * r + c]; }
+    Matx33f t() const {
+        Matx33f m;
+        for (int r = 0; r < 3; r++)
+            for (int c = 0; c < 3; c++) m(r, c) = (*this)(c, r);
+        return m;
+    }
+};
+inline Matx33f operator*(const Matx33f& a, const Matx33f& b) {   // cv::Matx product: float accumulator, k ascending
+    Matx33f m;
+    for (int r = 0; r < 3; r++)
+        for (int c = 0; c < 3; c++) {
+            float s = 0;
+            for (int k = 0; k < 3; k++) s += a(r, k) * b(k, c);
+            m(r, c) = s;
+        }
+    return m;
+}
+inline Point3f operator*(const Matx33f& a, const Point3f& p) {
+    const float v[3] = {p.x, p.y, p.z};
+    float o[3];
+    for (int r = 0; r < 3; r++) {
+        float s = 0;
+        for (int k = 0; k < 3; k++) s += a(r, k) * v[k];
+        o[r] = s;
+    }
+    return Point3f(o[0], o[1], o[2]);
+}
 
 struct KeyPoint {
     Point2f pt;
@@ -45,7 +100,7 @@ public:
     std::shared_ptr<std::vector<uint8_t>> buf;
     Mat() {}
     Mat(int r, int c, int t) { create(r, c, t); }
-    static int esz(int t) { return t == CV_8U ? 1 : 4; }
+    static int esz(int t) { return t == CV_8U ? 1 : (t == CV_64F ? 8 : 4); }
     void create(int r, int c, int t) {
         rows = r; cols = c; type_ = t;
         buf = std::make_shared<std::vector<uint8_t>>((size_t)r * c * esz(t), 0);

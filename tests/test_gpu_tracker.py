@@ -112,3 +112,35 @@ def test_track_pairs_kitti_shaped(ctx, oracle, first_lvl):
     assert rot_angle(pose[:4], ref["pose"][:4]) <= TOL
     assert np.abs(pose[4:] - ref["pose"][4:]).max() <= TOL
     tr.close()
+
+
+def test_track_pairs_batched_5000_features_config5(ctx, oracle):
+    """BASELINE configs[4] shape (independent 752x480 pairs, 5000 ORB features each, seeds 5000+i), scaled to a
+    96-pair batch: two distinct pairs are checked against the oracle, and — the size-independent property — a pair's
+    result does not depend on where it sits in the batch or on what surrounds it (bit-identical poses)."""
+    import torch
+    from vislam_b200 import synth
+    uniq = [synth.make_pair(n_feat=5000, seed=5000 + i) for i in range(3)]
+    B = 96
+    order = [i % 3 for i in range(B)]
+    order[1], order[2] = 0, 0                       # neighbours differ from the i % 3 pattern
+    tr = ctx.tracker(752, 480, 5000, uniq[0]["K"], n_cells=225, max_pairs=B)
+    st = lambda k: torch.from_numpy(np.stack([uniq[o][k] for o in order])).cuda()
+    pose, n_good = tr.track_pairs(st("prev"), st("cur"), st("d1"), st("d2"), st("kp1"), st("pose_prior"))
+    torch.cuda.synchronize()
+    pose, n_good = pose.cpu().numpy(), n_good.cpu().numpy()
+    first = {}
+    for b, o in enumerate(order):
+        if o in first:
+            np.testing.assert_array_equal(pose[b], pose[first[o]])
+            assert n_good[b] == n_good[first[o]]
+        else:
+            first[o] = b
+    for o in (0, 1):
+        p = uniq[o]
+        ref = oracle.track_pair(p["prev"], p["cur"], p["d1"], p["d2"], p["kp1"], p["K"], p["pose_prior"], n_cells=225)
+        b = first[o]
+        assert n_good[b] == len(ref["good_q"]) and n_good[b] > 100
+        assert rot_angle(pose[b][:4], ref["pose"][:4]) <= TOL
+        assert np.abs(pose[b][4:] - ref["pose"][4:]).max() <= TOL
+    tr.close()

@@ -26,7 +26,13 @@ def test_host_library_builds_and_exports_reference_methods():
                  "CameraGPU::computeGPUGoodMatches()", "CameraGPU::addGPUKeyframe()",
                  "vi::VISystem::InitializePyramid(", "vi::VISystem::EstimatePoseFeatures(Frame*, Frame*)",
                  "vi::VISystem::WarpFunctionSE3(", "vi::VISystem::IdentityWeights(int)", "vi::VISystem::Track()",
-                 "vi::VISystem::AddFrame(", "vi::VISystem::setGtRes(", "vi::VISystemGPU::AddFrameGPU("]:
+                 "vi::VISystem::AddFrame(", "vi::VISystem::setGtRes(", "vi::VISystemGPU::AddFrameGPU(",
+                 # dataset ingestion and angle helpers
+                 "ImageReader::searchImages()", "ImageReader::getImageTime(int)", "ImageReader::getImage(int)",
+                 "GroundTruth::getDataFromFile()", "GroundTruth::getGroundTruthData(int, int)",
+                 "DataReader::setProperties(", "DataReader::UpdateDataReader(int, int)", "DataReader::UpdateImu(int, int)",
+                 "rotationMatrix2RPY(", "RPY2rotationMatrix(", "toQuaternion(double, double, double)", "toRPY(Quaterniond const&)",
+                 "vi::TrajectoryWriter::write(", "vi::imread_gray("]:
         assert name in syms, name
     # the class mirrors reach the device only through the C ABI: no CUDA runtime symbols of their own
     undefined = subprocess.run(["nm", "-D", "--undefined-only", so], capture_output=True, text=True, check=True).stdout

@@ -14,16 +14,12 @@
 #include <vector>
 
 #include "vislam/Camera.hpp"
+#include "vislam/Plus.hpp"
 #include "vislam/compat.hpp"
 #include "vislam/device.hpp"
 
 #define PYRAMID_LEVELS 5
 
-// include/Plus.hpp:10-16
-struct Quaterniond {
-    double w, x, y, z;
-    Quaterniond() : w(1), x(0), y(0), z(0) {}
-};
 
 namespace vi {
 
@@ -132,9 +128,5 @@ protected:
 };
 
 }  // namespace vi
-
-// src/Plus.cpp:3-19, 23-50 (double precision helpers used by Track)
-Quaterniond toQuaternion(double roll, double pitch, double yaw);
-cv::Point3d toRPY(const Quaterniond& q);
 
 #endif

@@ -16,30 +16,6 @@ using cv::Matx33f;
 using cv::Point3d;
 using std::vector;
 
-Quaterniond toQuaternion(double roll, double pitch, double yaw) {   // Plus.cpp:3-19
-    Quaterniond q;
-    const double cy = std::cos(yaw * 0.5), sy = std::sin(yaw * 0.5);
-    const double cr = std::cos(roll * 0.5), sr = std::sin(roll * 0.5);
-    const double cp = std::cos(pitch * 0.5), sp = std::sin(pitch * 0.5);
-    q.w = cy * cr * cp + sy * sr * sp;
-    q.x = cy * sr * cp - sy * cr * sp;
-    q.y = cy * cr * sp + sy * sr * cp;
-    q.z = sy * cr * cp - cy * sr * sp;
-    return q;
-}
-
-Point3d toRPY(const Quaterniond& q) {   // Plus.cpp:23-50
-    const double sinr_cosp = +2.0 * (q.w * q.x + q.y * q.z);
-    const double cosr_cosp = +1.0 - 2.0 * (q.x * q.x + q.y * q.y);
-    const double roll = std::atan2(sinr_cosp, cosr_cosp);
-    const double sinp = +2.0 * (q.w * q.y - q.z * q.x);
-    const double pitch = std::fabs(sinp) >= 1 ? std::copysign(M_PI / 2, sinp) : std::asin(sinp);
-    const double siny_cosp = +2.0 * (q.w * q.z + q.x * q.y);
-    const double cosy_cosp = +1.0 - 2.0 * (q.y * q.y + q.z * q.z);
-    const double yaw = std::atan2(siny_cosp, cosy_cosp);
-    return Point3d(roll, pitch, yaw);
-}
-
 namespace vi {
 
 VISystem::VISystem()
