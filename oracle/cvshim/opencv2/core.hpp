@@ -12,6 +12,7 @@
 #include <cstdint>
 #include <cstring>
 #include <memory>
+#include <ostream>
 #include <vector>
 
 #define CV_8U 0
@@ -45,6 +46,7 @@ template <typename T> Point3_<T> operator-(const Point3_<T>& a) { return Point3_
 template <typename T> Point3_<T> operator*(const Point3_<T>& a, double s) { return Point3_<T>((T)(a.x * s), (T)(a.y * s), (T)(a.z * s)); }
 template <typename T> Point3_<T> operator/(const Point3_<T>& a, int s) { return Point3_<T>((T)(a.x / s), (T)(a.y / s), (T)(a.z / s)); }
 template <typename T> Point3_<T> operator/(const Point3_<T>& a, double s) { return Point3_<T>((T)(a.x / s), (T)(a.y / s), (T)(a.z / s)); }
+template <typename T> std::ostream& operator<<(std::ostream& o, const Point3_<T>& p) { return o << "[" << p.x << ", " << p.y << ", " << p.z << "]"; }
 typedef Point3_<float> Point3f;
 typedef Point3_<double> Point3d;
 

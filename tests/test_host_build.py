@@ -32,7 +32,11 @@ def test_host_library_builds_and_exports_reference_methods():
                  "GroundTruth::getDataFromFile()", "GroundTruth::getGroundTruthData(int, int)",
                  "DataReader::setProperties(", "DataReader::UpdateDataReader(int, int)", "DataReader::UpdateImu(int, int)",
                  "rotationMatrix2RPY(", "RPY2rotationMatrix(", "toQuaternion(double, double, double)", "toRPY(Quaterniond const&)",
-                 "vi::TrajectoryWriter::write(", "vi::imread_gray("]:
+                 "vi::TrajectoryWriter::write(", "vi::imread_gray(",
+                 # IMU prior
+                 "Imu::initializate(", "Imu::estimate()", "Imu::estimateOrientation()", "Imu::computeAcceleration()",
+                 "Imu::calibrateAng(int)", "ImuFilterNode::UpdatePublisher(", "ImuFilterNode::UpdateSubscriber()",
+                 "vi::MadgwickFilter::update("]:
         assert name in syms, name
     # the class mirrors reach the device only through the C ABI: no CUDA runtime symbols of their own
     undefined = subprocess.run(["nm", "-D", "--undefined-only", so], capture_output=True, text=True, check=True).stdout

@@ -54,6 +54,10 @@ struct Point3_ {
     T x, y, z;
     Point3_() : x(0), y(0), z(0) {}
     Point3_(T x_, T y_, T z_) : x(x_), y(y_), z(z_) {}
+    template <typename U> explicit Point3_(const Point3_<U>& o) : x((T)o.x), y((T)o.y), z((T)o.z) {}
+    template <typename U> Point3_& operator=(const Point3_<U>& o) { x = (T)o.x; y = (T)o.y; z = (T)o.z; return *this; }
+    Point3_ operator/(int s) const { return Point3_((T)(x / s), (T)(y / s), (T)(z / s)); }
+    Point3_ operator/(double s) const { return Point3_((T)(x / s), (T)(y / s), (T)(z / s)); }
     Point3_ operator+(const Point3_& o) const { return Point3_(x + o.x, y + o.y, z + o.z); }
     Point3_ operator-(const Point3_& o) const { return Point3_(x - o.x, y - o.y, z - o.z); }
     Point3_ operator-() const { return Point3_(-x, -y, -z); }
@@ -96,6 +100,27 @@ struct Matx33f {
     const float& operator()(int r, int c) const { return val[3 * r + c]; }
     Matx33f t() const { return Matx33f(val[0], val[3], val[6], val[1], val[4], val[7], val[2], val[5], val[8]); }
 };
+// cv::Matx products accumulate in the element type (float), k ascending from a zero accumulator
+inline Matx33f operator*(const Matx33f& a, const Matx33f& b) {
+    Matx33f m;
+    for (int r = 0; r < 3; r++)
+        for (int c = 0; c < 3; c++) {
+            float s = 0.f;
+            for (int k = 0; k < 3; k++) s += a(r, k) * b(k, c);
+            m(r, c) = s;
+        }
+    return m;
+}
+inline Point3f operator*(const Matx33f& a, const Point3f& p) {
+    const float v[3] = {p.x, p.y, p.z};
+    float o[3];
+    for (int r = 0; r < 3; r++) {
+        float s = 0.f;
+        for (int k = 0; k < 3; k++) s += a(r, k) * v[k];
+        o[r] = s;
+    }
+    return Point3f(o[0], o[1], o[2]);
+}
 
 // Reference-counted dense 2-D array, single channel (the subset of cv::Mat the path touches).
 class Mat {

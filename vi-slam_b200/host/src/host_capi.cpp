@@ -7,6 +7,7 @@
 #include <string>
 
 #include "vislam/DataReader.hpp"
+#include "vislam/Imu.hpp"
 #include "vislam/Plus.hpp"
 
 namespace {
@@ -152,6 +153,78 @@ int vih_trajectory_write(const char* file, const double* rows, int n) {
             qg.x = r[20]; qg.y = r[21]; qg.z = r[22]; qg.w = r[23];
             w.write(r[0], cv::Point3d(r[1], r[2], r[3]), cv::Point3d(r[4], r[5], r[6]), cv::Point3d(r[7], r[8], r[9]), q,
                     cv::Point3d(r[14], r[15], r[16]), cv::Point3d(r[17], r[18], r[19]), qg, cv::Point3d(r[24], r[25], r[26]));
+        }
+        return 0;
+    } catch (const std::exception& e) { return fail(e); }
+}
+
+// ---- Imu -------------------------------------------------------------------------------------------------
+// The filter alone: n samples (w, a: n x 3) -> n orientations (w, x, y, z).
+void vih_madgwick_run(double gain, double dt, const double* w, const double* a, int n, double* q_wxyz) {
+    vi::MadgwickFilter f(gain, dt);
+    for (int i = 0; i < n; i++) {
+        f.update(w[3 * i], w[3 * i + 1], w[3 * i + 2], a[3 * i], a[3 * i + 1], a[3 * i + 2]);
+        f.getOrientation(q_wxyz[4 * i], q_wxyz[4 * i + 1], q_wxyz[4 * i + 2], q_wxyz[4 * i + 3]);
+    }
+}
+
+namespace {
+struct ImuTable { const double* in; double* out; int n, next; vi::MadgwickFilter filter; };
+void imu_table_source(void* user, const vi::ImuMsg& raw, vi::ImuMsg& fused) {
+    ImuTable* t = static_cast<ImuTable*>(user);
+    double q[4];
+    if (t->in) {
+        for (int k = 0; k < 4; k++) q[k] = t->next < t->n ? t->in[4 * t->next + k] : (k == 0 ? 1.0 : 0.0);
+    } else {
+        t->filter.update(raw.angular_velocity.x, raw.angular_velocity.y, raw.angular_velocity.z, raw.linear_acceleration.x,
+                         raw.linear_acceleration.y, raw.linear_acceleration.z);
+        t->filter.getOrientation(q[0], q[1], q[2], q[3]);
+    }
+    if (t->out && t->next < t->n) for (int k = 0; k < 4; k++) t->out[4 * t->next + k] = q[k];
+    t->next++;
+    fused.orientation.w = q[0]; fused.orientation.x = q[1]; fused.orientation.y = q[2]; fused.orientation.z = q[3];
+}
+}  // namespace
+
+// One Imu life: initializate(gt_yaw, gt_velocity, first n0 samples), then `steps` x { setImuData(next n_per samples);
+// estimate() }.  q_in != NULL: the orientation answered for each published sample (w, x, y, z), otherwise the built-in
+// Madgwick filter; q_out (optional) records them.  out: 60 doubles after initializate and after every step, in the
+// layout documented in oracle/cvshim/ref_imu_capi.cpp (the reference's Imu runs behind the same signature there).
+int vih_imu_run(double timestep, double gt_yaw, const double gt_vel[3], const double* w, const double* a,
+                const double* q_in, double* q_out, int n0, int n_per, int steps, double* out) {
+    try {
+        ImuTable table = {q_in, q_out, n0 + steps * n_per, 0, vi::MadgwickFilter(0.1, timestep)};
+        Imu imu(timestep);
+        imu.setOrientationSource(imu_table_source, &table);
+        auto pts = [](const double* v, int n) {
+            std::vector<cv::Point3d> o;
+            for (int i = 0; i < n; i++) o.push_back(cv::Point3d(v[3 * i], v[3 * i + 1], v[3 * i + 2]));
+            return o;
+        };
+        std::vector<cv::Point3d> wv = pts(w, n0), av = pts(a, n0);
+        imu.initializate(gt_yaw, cv::Point3d(gt_vel[0], gt_vel[1], gt_vel[2]), wv, av);
+        auto dump = [&](double* o) {
+            const cv::Point3d* p[] = {&imu.residualRPY, &imu.residualPosition, &imu.residualVelocity, &imu.velocity,
+                                      &imu.position, &imu.angBias, &imu.accBias, &imu.initialVelocity};
+            for (int k = 0; k < 8; k++) { o[3 * k] = p[k]->x; o[3 * k + 1] = p[k]->y; o[3 * k + 2] = p[k]->z; }
+            for (int i = 0; i < 9; i++) {
+                o[24 + i] = imu.init_rotationMatrix.val[i];
+                o[33 + i] = imu.final_rotationMatrix.val[i];
+                o[42 + i] = imu.residual_rotationMatrix.val[i];
+            }
+            const cv::Point3d r = imu.rpyAnglesWorld.empty() ? cv::Point3d() : imu.rpyAnglesWorld.back();
+            const cv::Point3d aw = imu.accelerationWorld.empty() ? cv::Point3d() : imu.accelerationWorld.back();
+            o[51] = r.x; o[52] = r.y; o[53] = r.z;
+            o[54] = aw.x; o[55] = aw.y; o[56] = aw.z;
+            o[57] = imu.angularVelocity.x; o[58] = imu.angularVelocity.y; o[59] = imu.angularVelocity.z;
+        };
+        dump(out);
+        for (int s = 0; s < steps; s++) {
+            wv = pts(w + 3 * (n0 + s * n_per), n_per);
+            av = pts(a + 3 * (n0 + s * n_per), n_per);
+            imu.setImuData(wv, av);
+            imu.estimate();
+            dump(out + 60 * (s + 1));
         }
         return 0;
     } catch (const std::exception& e) { return fail(e); }
