@@ -68,7 +68,7 @@ extern "C" int vsb_ctx_option(vsb_ctx_t* ctx, const char* name, int value) {
         return VSB_OK;
     }
     if (!strcmp(name, "gn_variant")) {
-        if (value < 0 || value > 6) return VSB_ERR_INVALID;
+        if (value < 0 || value > 5) return VSB_ERR_INVALID;
         ctx->gn_variant = value;
         return VSB_OK;
     }

@@ -7,15 +7,16 @@
 // intensity I_prev(y1,x1) and the previous-frame Scharr gradient at that pixel (:1320-1325) — is gathered
 // once per level by gn_prepare_kernel into an 8-byte attribute record, so an iteration reads 24 coalesced
 // bytes per point (the reference-layout float4 candidate + the record) and does ONE scattered load, the
-// current-frame intensity at the warped position.  Points are processed in batches of GT*U so a thread has U
-// independent gathers in flight; the 28 sums are formed per batch, reduced with a warp shuffle tree and
-// accumulated per warp in shared memory, which keeps the register footprint small enough for several blocks
-// per SM (one block's serial 6x6 solve overlaps the other blocks' point loops).
+// current-frame intensity at the warped position.  Points are processed in batches of GT*U (U = 2) so a thread has U
+// independent gathers in flight.  Per point the 8-vector V = (J0..J5, r*w, r) is staged through shared memory
+// (transposed: one row of V per warp lane group) and the warp accumulates the 8x8 Gram matrix V V^T of 4 points per
+// instruction on the FP64 tensor cores; A = J^T J, b = -J^T r and the error are entries of that matrix.  69 registers
+// per thread: six 128-thread blocks per SM, so one block's serial 6x6 solve overlaps the other blocks' point loops.
 //
 // Parity design: every float operation of the reference's per-point arithmetic is issued with an explicitly
 // rounded intrinsic in the source order (no FMA contraction); cv::gemm's "float in, double accumulate" is
-// reproduced with exact float*float products summed in FP64.  The reduction order is fixed (batch order,
-// shuffle tree, warp order), so results are run-to-run deterministic and independent of the grid.
+// reproduced with exact float*float products summed in FP64.  The reduction order is fixed (batch order, DMMA k
+// order, warp order), so results are run-to-run deterministic and independent of the grid.
 // accum_mode 1 sums a thread's products in FP32 (FMA) and only the cross-thread part in FP64 (north-star
 // wording).  The 6x6 system is solved by warp 0 with OpenCV's LU elimination order, one matrix column per lane.
 #include "common.cuh"
@@ -275,7 +276,7 @@ __device__ __noinline__ float tukey_inv_mad(const float4* __restrict__ cand, con
 constexpr int VROW = 36;   // staging row stride (floats): conflict-free for the [g][4s+t] reads of the MMA feed
 
 // U = points per thread per batch; TPS = resident threads per SM the register budget is sized for
-template <bool FP32_PARTIALS, int GT, bool TUKEY, int U = 4, int TPS = 768>
+template <bool FP32_PARTIALS, int GT, bool TUKEY, int U = 2, int TPS = 768>
 __global__ void __launch_bounds__(GT, TPS / GT)
 gn_solve_kernel(const GnParams P) {
     constexpr int NW = GT / 32;
@@ -286,7 +287,7 @@ gn_solve_kernel(const GnParams P) {
 
     __shared__ float s_pose[7];
     __shared__ double s_md[12];
-    __shared__ float s_v[NW][8 * VROW];
+    __shared__ float s_v[NW][(FP32_PARTIALS ? 1 : U) * 8 * VROW];   // one staging slot per point of a batch
     __shared__ double s_red[NW][64];
     __shared__ int s_cnt[NW];
     __shared__ double s_G[64];
@@ -467,15 +468,10 @@ gn_solve_kernel(const GnParams P) {
                     V[7] = good ? res : 0.f;
                     nv += good ? 1 : 0;
                     if (!FP32_PARTIALS) {
-                        __syncwarp();
+                        // stage only: no barrier between the points of a batch, so their (long, dependent) Jacobian
+                        // chains can be interleaved by the scheduler; the Gram update of the whole batch follows below
 #pragma unroll
-                        for (int q = 0; q < 8; q++) sv[q * VROW + lane] = V[q];
-                        __syncwarp();
-#pragma unroll
-                        for (int s = 0; s < 8; s++) {
-                            const double d = (double)sv[g8 * VROW + 4 * s + t4];      // V[g] of point 4s+t
-                            dmma_8x8x4(acc0, acc1, d, d);
-                        }
+                        for (int q = 0; q < 8; q++) sv[(u * 8 + q) * VROW + lane] = V[q];
                     } else {
                         int t = 0;
 #pragma unroll
@@ -487,6 +483,18 @@ gn_solve_kernel(const GnParams P) {
                         for (int a = 0; a < 6; a++) accf[21 + a] = fmaf(V[a], V[6], accf[21 + a]);
                         accf[27] = fmaf(V[7], V[6], accf[27]);
                     }
+                }
+                if (!FP32_PARTIALS) {
+                    __syncwarp();
+#pragma unroll
+                    for (int u = 0; u < U; u++) {
+#pragma unroll
+                        for (int s = 0; s < 8; s++) {
+                            const double d = (double)sv[(u * 8 + g8) * VROW + 4 * s + t4];   // V[g] of point 4s+t of slot u
+                            dmma_8x8x4(acc0, acc1, d, d);
+                        }
+                    }
+                    __syncwarp();                 // the next batch overwrites the slots
                 }
             }
             // ---- cross-warp reduction in warp order (deterministic) --------------------------------------------
@@ -664,13 +672,12 @@ int vsb_gn_solve_stats(vsb_ctx_t* ctx, const uint8_t* prev_pyr, const uint8_t* c
         else gn_solve_kernel<FP, T, false><<<count, T, 0, st>>>(P);                      \
     } while (0)
     if (ctx->gn_variant > 0 && opts->accum_mode == 0 && opts->weight_mode != 1 && gt_env == 128) {   // tuning experiments
-        switch (ctx->gn_variant) {
-            case 1: gn_solve_kernel<false, 128, false, 2, 1024><<<count, 128, 0, st>>>(P); break;
-            case 2: gn_solve_kernel<false, 128, false, 2, 1280><<<count, 128, 0, st>>>(P); break;
-            case 3: gn_solve_kernel<false, 128, false, 1, 1536><<<count, 128, 0, st>>>(P); break;
-            case 4: gn_solve_kernel<false, 128, false, 2, 768><<<count, 128, 0, st>>>(P); break;
-            case 5: gn_solve_kernel<false, 128, false, 4, 640><<<count, 128, 0, st>>>(P); break;
-            default: gn_solve_kernel<false, 128, false, 4, 512><<<count, 128, 0, st>>>(P); break;
+        switch (ctx->gn_variant) {    // (points per thread per batch, resident threads per SM the registers are sized for)
+            case 1: gn_solve_kernel<false, 128, false, 4, 768><<<count, 128, 0, st>>>(P); break;
+            case 2: gn_solve_kernel<false, 128, false, 2, 1024><<<count, 128, 0, st>>>(P); break;
+            case 3: gn_solve_kernel<false, 128, false, 3, 768><<<count, 128, 0, st>>>(P); break;
+            case 4: gn_solve_kernel<false, 128, false, 4, 640><<<count, 128, 0, st>>>(P); break;
+            default: gn_solve_kernel<false, 128, false, 1, 1024><<<count, 128, 0, st>>>(P); break;
         }
     } else if (opts->accum_mode == 1) {
         if (gt_env == 64) GN_LAUNCH(true, 64); else if (gt_env == 128) GN_LAUNCH(true, 128); else GN_LAUNCH(true, 256);
