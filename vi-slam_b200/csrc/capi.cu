@@ -43,7 +43,7 @@ extern "C" int vsb_ctx_create(int device, vsb_ctx_t** out) {
     c->prof_on = 0;
     for (int i = 0; i < VSB_K_COUNT; i++) { c->prof_ms[i] = 0.0; c->prof_n[i] = 0; }
     c->knn_impl = 2;
-    c->gn_threads = 128;
+    c->gn_threads = 0;      // auto: by batch size
     c->pyr_impl = 1;
     c->gn_variant = 0;
     c->knn_l2_impl = 1;
@@ -78,7 +78,7 @@ extern "C" int vsb_ctx_option(vsb_ctx_t* ctx, const char* name, int value) {
         return VSB_OK;
     }
     if (!strcmp(name, "gn_threads")) {
-        if (value != 64 && value != 128 && value != 256) return VSB_ERR_INVALID;
+        if (value != 0 && value != 64 && value != 128 && value != 256 && value != 512 && value != 1024) return VSB_ERR_INVALID;
         ctx->gn_threads = value;
         return VSB_OK;
     }

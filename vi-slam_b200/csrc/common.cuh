@@ -37,7 +37,7 @@ struct vsb_ctx {
     // tuning knobs (vsb_ctx_option)
     int knn_impl;     // Hamming kNN: 0 = POPC kernel (INT pipe), 1 = tcgen05 tensor-core kernel, 32-bit epilogue,
                       //              2 = tcgen05 kernel with the packed 16x2 epilogue
-    int gn_threads;   // threads per frame pair of the GN solver: 64 / 128 / 256
+    int gn_threads;   // threads per frame pair of the GN solver: 64 / 128 / 256 / 512 / 1024, 0 = chosen from the batch size
     int knn_l2_impl;  // float kNN: 0 = exact FP64 kernel, 1 = tensor-core GEMM + exact re-check (dim <= 64, dim % 8 == 0)
     int gn_variant;   // GN solver register/unroll variant (tuning experiments; 0 = default)
     int pyr_impl;     // pyramid: 0 = generic shared-memory tile kernel, 1 = register-blocked kernel when w, h are multiples of 16

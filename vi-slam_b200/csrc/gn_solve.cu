@@ -277,7 +277,7 @@ constexpr int VROW = 36;   // staging row stride (floats): conflict-free for the
 
 // U = points per thread per batch; TPS = resident threads per SM the register budget is sized for
 template <bool FP32_PARTIALS, int GT, bool TUKEY, int U = 2, int TPS = 768>
-__global__ void __launch_bounds__(GT, TPS / GT)
+__global__ void __launch_bounds__(GT, (TPS / GT) > 0 ? (TPS / GT) : 1)
 gn_solve_kernel(const GnParams P) {
     constexpr int NW = GT / 32;
     const int prob = blockIdx.x;
@@ -287,8 +287,9 @@ gn_solve_kernel(const GnParams P) {
 
     __shared__ float s_pose[7];
     __shared__ double s_md[12];
-    __shared__ float s_v[NW][(FP32_PARTIALS ? 1 : U) * 8 * VROW];   // one staging slot per point of a batch
-    __shared__ double s_red[NW][64];
+    constexpr int SV_FLOATS = (FP32_PARTIALS ? 1 : U) * 8 * VROW;     // one staging slot per point of a batch
+    __shared__ __align__(16) float s_v[NW][SV_FLOATS];
+    static_assert(SV_FLOATS * sizeof(float) >= 64 * sizeof(double), "a warp's staging area doubles as its 8x8 partial sum");
     __shared__ int s_cnt[NW];
     __shared__ double s_G[64];
     __shared__ int s_nv;
@@ -308,6 +309,7 @@ gn_solve_kernel(const GnParams P) {
     const uint8_t* cur_base = P.cur_pyr + (size_t)prob * P.pair_stride;
     vsb_gn_trace_t* trace = P.trace ? P.trace + (size_t)prob * VSB_MAX_TRACE : nullptr;
     float* sv = s_v[warp];
+    double* red = reinterpret_cast<double*>(sv);     // the warp's partial Gram matrix, written after its last staging read
 
     for (int lvl = o.first_lvl; lvl >= o.last_lvl; lvl--) {                       // VISystem.cpp:1181
         const int cols = P.lay.w[lvl], rows = P.lay.h[lvl];
@@ -499,8 +501,8 @@ gn_solve_kernel(const GnParams P) {
             }
             // ---- cross-warp reduction in warp order (deterministic) --------------------------------------------
             if (!FP32_PARTIALS) {
-                s_red[warp][g8 * 8 + 2 * t4] = acc0;
-                s_red[warp][g8 * 8 + 2 * t4 + 1] = acc1;
+                red[g8 * 8 + 2 * t4] = acc0;
+                red[g8 * 8 + 2 * t4 + 1] = acc1;
             } else {
                 // FP32 thread partials -> FP64 warp tree -> the same 8x8 layout
                 int t = 0;
@@ -509,16 +511,16 @@ gn_solve_kernel(const GnParams P) {
 #pragma unroll
                     for (int b = a; b < 6; b++) {
                         const double v = warp_sum((double)accf[t++]);
-                        if (lane == 0) { s_red[warp][a * 8 + b] = v; s_red[warp][b * 8 + a] = v; }
+                        if (lane == 0) { red[a * 8 + b] = v; red[b * 8 + a] = v; }
                     }
                 }
 #pragma unroll
                 for (int a = 0; a < 6; a++) {
                     const double v = warp_sum((double)accf[21 + a]);
-                    if (lane == 0) s_red[warp][a * 8 + 6] = v;
+                    if (lane == 0) red[a * 8 + 6] = v;
                 }
                 const double v = warp_sum((double)accf[27]);
-                if (lane == 0) s_red[warp][7 * 8 + 6] = v;
+                if (lane == 0) red[7 * 8 + 6] = v;
             }
             {
                 int cnum = nv;
@@ -528,9 +530,9 @@ gn_solve_kernel(const GnParams P) {
             }
             __syncthreads();
             if (tid < 64) {
-                double v = s_red[0][tid];
+                double v = reinterpret_cast<const double*>(s_v[0])[tid];
 #pragma unroll
-                for (int wv = 1; wv < NW; wv++) v += s_red[wv][tid];
+                for (int wv = 1; wv < NW; wv++) v += reinterpret_cast<const double*>(s_v[wv])[tid];
                 s_G[tid] = v;
             }
             if (tid == GT - 1) {
@@ -665,7 +667,15 @@ int vsb_gn_solve_stats(vsb_ctx_t* ctx, const uint8_t* prev_pyr, const uint8_t* c
         }
     }
     ProfScope ps(ctx, VSB_K_GN_SOLVE, st);
-    const int gt_env = ctx->gn_threads;
+    // Threads per frame pair.  A pair is one block, so a small batch cannot fill the machine with 128-thread blocks: the
+    // fewer pairs there are, the more threads each one gets (a lone 752x480 pair: 0.77 ms at 128 threads, see
+    // tools/latency_pairs.py).  The partition of points over warps changes with it, i.e. the order of the FP64 sums; the
+    // float results are the same unless a sum sits within 2^-29 of a rounding boundary.
+    int gt_env = ctx->gn_threads;
+    if (gt_env == 0) {
+        const int sms = ctx->sm_count > 0 ? ctx->sm_count : 148;
+        gt_env = count >= 4 * sms ? 128 : count >= 2 * sms ? 256 : count >= sms / 2 ? 512 : 1024;
+    }
 #define GN_LAUNCH(FP, T)                                                                 \
     do {                                                                                 \
         if (opts->weight_mode == 1) gn_solve_kernel<FP, T, true><<<count, T, 0, st>>>(P); \
@@ -681,6 +691,12 @@ int vsb_gn_solve_stats(vsb_ctx_t* ctx, const uint8_t* prev_pyr, const uint8_t* c
         }
     } else if (opts->accum_mode == 1) {
         if (gt_env == 64) GN_LAUNCH(true, 64); else if (gt_env == 128) GN_LAUNCH(true, 128); else GN_LAUNCH(true, 256);
+    } else if (gt_env >= 1024) {
+        if (opts->weight_mode == 1) gn_solve_kernel<false, 1024, true, 1, 1024><<<count, 1024, 0, st>>>(P);
+        else gn_solve_kernel<false, 1024, false, 1, 1024><<<count, 1024, 0, st>>>(P);
+    } else if (gt_env >= 512) {
+        if (opts->weight_mode == 1) gn_solve_kernel<false, 512, true, 2, 1024><<<count, 512, 0, st>>>(P);
+        else gn_solve_kernel<false, 512, false, 2, 1024><<<count, 512, 0, st>>>(P);
     } else {
         if (gt_env == 64) GN_LAUNCH(false, 64); else if (gt_env == 128) GN_LAUNCH(false, 128); else GN_LAUNCH(false, 256);
     }
