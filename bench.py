@@ -311,11 +311,9 @@ def run_gpu(args, rank, world, local_rank):
     c1.record(stream)
     torch.cuda.synchronize(dev)
     h2d_copy_gbs = 3 * h["frames"].numel() / (c0.elapsed_time(c1) * 1e-3) / 1e9
-    h2d = sum(int(h[k].numel() * h[k].element_size()) for k in ("frames", "desc", "kp", "prior"))
+    traffic_host = tr_host.host_traffic()      # counted by the library from the copies it issued
+    h2d, d2h, n_host_chunks = int(traffic_host["h2d"]), int(traffic_host["d2h"]), int(traffic_host["chunks"])
     n_chunks = (n_pairs + chunk - 1) // chunk
-    n_host_chunks = (n_pairs + host_chunk - 1) // host_chunk
-    h2d += (n_host_chunks - 1) * (W * H + N_FEAT * 32 + N_FEAT * 8)    # the frame shared by two chunks is sent twice
-    d2h = int(h_pose.numel() * 4 + h_ng.numel() * 4)
     same = bool(torch.equal(h_pose.to(dev), d_pose))
 
     if rank != 0:
@@ -394,7 +392,7 @@ def run_gpu(args, rank, world, local_rank):
         "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "u8/int32 Hamming + f32 GN (f64 accumulate)", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "frames": n_frames, "pairs_per_step": n_pairs, "chunk_pairs": chunk, "host_chunk_pairs": host_chunk,
+        "config": {"workload": WORKLOAD, "frames": n_frames, "pairs_per_step": n_pairs, "chunk_pairs": chunk, "host_chunk_pairs": host_chunk, "host_chunks": n_host_chunks,
                    "grad_mode": grad_mode, "parallelism": f"replicas x{world}" if world > 1 else "single GPU",
                    "l2_policy": "inputs larger than L2 (722 MB of frames per step), no flush needed",
                    "gn_iterations_per_pair": stats["iterations"] / max(1, pairs_total),

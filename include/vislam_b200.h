@@ -257,6 +257,9 @@ int vsb_tracker_destroy(vsb_tracker_t* t);
  * out[1] = GN iterations (error evaluations), out[2] = sum over iterations of the candidate points visited
  * (SURVEY.md §8d's  sum_l K_l * P_l), out[3] = symmetric matches found.  Synchronises the device. */
 int vsb_tracker_stats(vsb_tracker_t* t, long long out[4]);
+/* Bytes the last vsb_track_sequence_host call copied host->device and device->host, and its chunk count
+ * (out[0..2]); the frame shared by two consecutive chunks is uploaded with both. */
+int vsb_tracker_host_traffic(vsb_tracker_t* t, long long out[3]);
 
 /* Tracks `n_frames - 1` consecutive pairs of a sequence resident on the DEVICE.
  *   frames [n_frames][h][w] u8, desc [n_frames][n_feat_max][desc_bytes], kp_xy [n_frames][n_feat_max][2] f32,

@@ -65,6 +65,7 @@ struct vsb_tracker {
     Slot slot[2];
     int n_slots;
     unsigned long long* stats;   // device, 4 counters shared by both slots
+    long long host_h2d_bytes, host_d2h_bytes, host_chunks;   // what the last vsb_track_sequence_host call moved
 };
 
 namespace {
@@ -177,6 +178,7 @@ extern "C" int vsb_tracker_create(vsb_ctx_t* ctx, const vsb_tracker_cfg_t* cfg, 
     t->cand_cap = 121 * nf;
     t->n_slots = 2;
     t->stats = nullptr;
+    t->host_h2d_bytes = t->host_d2h_bytes = t->host_chunks = 0;
     if (cudaMalloc((void**)&t->stats, 4 * sizeof(unsigned long long)) != cudaSuccess ||
         cudaMemset(t->stats, 0, 4 * sizeof(unsigned long long)) != cudaSuccess) {
         delete t;
@@ -260,8 +262,15 @@ extern "C" int vsb_track_sequence_host(vsb_tracker_t* t, const uint8_t* h_frames
     const size_t kstride = (size_t)c.n_feat_max * 2;
     const int total_pairs = n_frames - 1;
     int chunk_idx = 0;
-    for (int p0 = 0; p0 < total_pairs; p0 += c.max_pairs, chunk_idx++) {
-        const int pairs = total_pairs - p0 < c.max_pairs ? total_pairs - p0 : c.max_pairs;
+    long long h2d = 0, d2h = 0;
+    // Chunk schedule: full chunks while plenty is left, then halving chunks (down to 32 pairs).  The pass is bound by the
+    // host link, so device work hides behind the next chunk's upload — except for the LAST chunk, whose whole compute is
+    // exposed; tapering makes that last chunk small.
+    for (int p0 = 0; p0 < total_pairs; chunk_idx++) {
+        const int remaining = total_pairs - p0;
+        int pairs = remaining < c.max_pairs ? remaining : c.max_pairs;
+        if (remaining <= 2 * c.max_pairs && remaining > 32) pairs = (remaining + 1) / 2 < c.max_pairs ? (remaining + 1) / 2 : c.max_pairs;
+        if (pairs < 32 && remaining >= 32) pairs = 32;
         const int nf = pairs + 1;
         Slot& s = t->slot[chunk_idx & 1];
         cudaStream_t st = s.stream;
@@ -276,6 +285,8 @@ extern "C" int vsb_track_sequence_host(vsb_tracker_t* t, const uint8_t* h_frames
             VSB_CUDA(ctx, cudaMemcpyAsync(s.n_feat, h_n_feat + p0, nf * sizeof(int32_t), cudaMemcpyHostToDevice, st));
         VSB_CUDA(ctx, cudaMemcpyAsync(s.prior, h_pose_prior + (size_t)p0 * 7, (size_t)pairs * 7 * sizeof(float),
                                       cudaMemcpyHostToDevice, st));
+        h2d += (long long)nf * (fbytes + dstride + kstride * sizeof(float)) + (h_n_feat ? nf * 4LL : 0) + pairs * 28LL;
+        d2h += pairs * 28LL + (h_n_good ? pairs * 4LL : 0);
         int rc = track_sequence_slot(t, s, nullptr, true, s.desc, s.kp, h_n_feat ? s.n_feat : nullptr, s.prior, nf,
                                      s.pose, nullptr, st);
         if (rc) return rc;
@@ -284,8 +295,10 @@ extern "C" int vsb_track_sequence_host(vsb_tracker_t* t, const uint8_t* h_frames
         if (h_n_good)
             VSB_CUDA(ctx, cudaMemcpyAsync(h_n_good + p0, s.n_good, pairs * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
         VSB_CUDA(ctx, cudaEventRecord(s.done, st));
+        p0 += pairs;
     }
     for (int i = 0; i < 2; i++) VSB_CUDA(ctx, cudaStreamSynchronize(t->slot[i].stream));
+    t->host_h2d_bytes = h2d; t->host_d2h_bytes = d2h; t->host_chunks = chunk_idx;
     return VSB_OK;
 }
 
@@ -296,5 +309,11 @@ extern "C" int vsb_tracker_stats(vsb_tracker_t* t, long long out[4]) {
     VSB_CUDA(t->ctx, cudaMemcpy(h, t->stats, sizeof(h), cudaMemcpyDeviceToHost));
     VSB_CUDA(t->ctx, cudaMemset(t->stats, 0, sizeof(h)));
     for (int i = 0; i < 4; i++) out[i] = (long long)h[i];
+    return VSB_OK;
+}
+
+extern "C" int vsb_tracker_host_traffic(vsb_tracker_t* t, long long out[3]) {
+    if (!t || !out) return VSB_ERR_INVALID;
+    out[0] = t->host_h2d_bytes; out[1] = t->host_d2h_bytes; out[2] = t->host_chunks;
     return VSB_OK;
 }

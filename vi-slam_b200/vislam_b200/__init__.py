@@ -56,7 +56,7 @@ EXPORTS = [
     "vsb_gather_keypoints", "vsb_init_pyramid", "vsb_gn_default_opts", "vsb_gn_solve", "vsb_initial_pose",
     "vsb_se3_mul", "vsb_tracker_create", "vsb_tracker_destroy", "vsb_track_sequence",
     "vsb_track_sequence_host", "vsb_track_pairs", "vsb_kernel_count", "vsb_kernel_name", "vsb_profile_enable",
-    "vsb_profile_reset", "vsb_profile_read", "vsb_popc_peak", "vsb_tracker_stats",
+    "vsb_profile_reset", "vsb_profile_read", "vsb_popc_peak", "vsb_tracker_stats", "vsb_tracker_host_traffic",
     "vsb_malloc", "vsb_free", "vsb_host_alloc", "vsb_host_free", "vsb_upload", "vsb_upload_2d", "vsb_download",
     "vsb_copy", "vsb_memset", "vsb_stream_create", "vsb_stream_destroy", "vsb_stream_sync",
     "vsb_nn_filter", "vsb_sym_matches", "vsb_sort_keys", "vsb_grid_best", "vsb_warp_se3", "vsb_se3_exp",
@@ -120,6 +120,7 @@ def lib():
     L.vsb_profile_read.argtypes = [vp, i32, C.POINTER(C.c_double), C.POINTER(C.c_longlong)]
     L.vsb_popc_peak.argtypes = [vp, C.POINTER(C.c_double), vp]
     L.vsb_tracker_stats.argtypes = [vp, C.POINTER(C.c_longlong)]
+    L.vsb_tracker_host_traffic.argtypes = [vp, C.POINTER(C.c_longlong)]
     _lib = L
     return L
 
@@ -382,6 +383,12 @@ class Tracker:
         out = (C.c_longlong * 4)()
         check(lib().vsb_tracker_stats(self.handle, out), self.ctx.handle)
         return dict(pairs=out[0], iterations=out[1], point_visits=out[2], updates=out[3])
+
+    def host_traffic(self):
+        """Bytes moved by the last track_sequence_host call: dict(h2d, d2h, chunks)."""
+        out = (C.c_longlong * 3)()
+        check(lib().vsb_tracker_host_traffic(self.handle, out), self.ctx.handle)
+        return dict(h2d=out[0], d2h=out[1], chunks=out[2])
 
     def track_sequence(self, frames, desc, kp_xy, prior, n_feat=None, pose=None, n_good=None, stream=None):
         """Device tensors: frames [T,h,w] u8, desc [T,N,D] u8, kp_xy [T,N,2] f32, prior [T-1,7] f32."""
