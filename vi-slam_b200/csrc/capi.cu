@@ -40,6 +40,8 @@ extern "C" int vsb_ctx_create(int device, vsb_ctx_t** out) {
     c->scratch2 = nullptr;
     c->scratch2_bytes = 0;
     c->l2_fallback_counter = nullptr;
+    c->attr_knn_tc_done = 0;
+    c->attr_l2_tc_smem = 0;
     c->prof_on = 0;
     for (int i = 0; i < VSB_K_COUNT; i++) { c->prof_ms[i] = 0.0; c->prof_n[i] = 0; }
     c->knn_impl = 2;

@@ -27,6 +27,9 @@ struct vsb_ctx {
     size_t scratch_bytes;
     void* scratch2;          // second area: internals of an entry whose caller already holds `scratch`
     size_t scratch2_bytes;
+    // kernel attributes are per device: remembered per context, not per process
+    int attr_knn_tc_done;
+    int attr_l2_tc_smem;
     unsigned long long* l2_fallback_counter;   // device counter of the last tensor-core L2 kNN call (diagnostics)
     // optional per-kernel timing with CUDA events on the launching stream (bench.py's roofline leg)
     int prof_on;

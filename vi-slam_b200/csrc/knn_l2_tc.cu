@@ -478,10 +478,9 @@ int vsb_knn2_l2_tc(vsb_ctx* ctx, const float* d1, int n1_max, const int32_t* n1,
     P.dim = dim; P.kblocks = (dim + 31) / 32;
     P.cand12 = cand12; P.cand21 = cand21;
     const int smem = 6 * P.kblocks * KB_BYTES + 3 * EXT_BYTES + 128;
-    static int attr_smem = 0;
-    if (smem > attr_smem) {
+    if (smem > ctx->attr_l2_tc_smem) {
         VSB_CUDA(ctx, cudaFuncSetAttribute(knn2_l2_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        attr_smem = smem;
+        ctx->attr_l2_tc_smem = smem;
     }
     const int n_big = n1_max > n2_max ? n1_max : n2_max;
     for (int z0 = 0; z0 < count; z0 += 65535) {

@@ -307,13 +307,12 @@ int vsb_knn2_hamming_tc(vsb_ctx* ctx, const uint8_t* d1, int n1_max, const int32
     if (!ctx || count < 0 || n1_max < 0 || n2_max < 0) return VSB_ERR_INVALID;
     if (n1_max > (int)KEY_IDX_MASK || n2_max > (int)KEY_IDX_MASK) return VSB_ERR_CAPACITY;
     if (count == 0 || (n1_max == 0 && n2_max == 0)) return VSB_OK;
-    static bool attr_done = false;
-    if (!attr_done) {
+    if (!ctx->attr_knn_tc_done) {
         VSB_CUDA(ctx, cudaFuncSetAttribute(knn2_hamming_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM));
         VSB_CUDA(ctx, cudaFuncSetAttribute(knn2_hamming_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM));
         VSB_CUDA(ctx, cudaFuncSetAttribute(knn2_hamming_tc_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
         VSB_CUDA(ctx, cudaFuncSetAttribute(knn2_hamming_tc_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-        attr_done = true;
+        ctx->attr_knn_tc_done = 1;
     }
     const int row_tiles = vsb_div_up(n1_max > n2_max ? n1_max : n2_max, TM);
     for (int z0 = 0; z0 < count; z0 += 65535) {
