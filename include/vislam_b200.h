@@ -253,6 +253,15 @@ typedef struct vsb_tracker vsb_tracker_t;
 int vsb_tracker_create(vsb_ctx_t* ctx, const vsb_tracker_cfg_t* cfg, vsb_tracker_t** out);
 int vsb_tracker_destroy(vsb_tracker_t* t);
 
+/* ---- feature detection, first stage ---------------------------------------------------------
+ * FAST-9/16 corners with non-maximum suppression, the key-point detector inside cv::ORB (src/Camera.cpp:124-129,
+ * ORB::create) and cv::cuda::ORB (src/CameraGPU.cpp:99-104): cv::FAST(img, kps, threshold, nonmax, TYPE_9_16) for `count`
+ * frames.  img: device, frames of h rows x pitch bytes, img_stride bytes apart.  Outputs (device): kp_xy
+ * [count][cap][2] int32 (x, y) and kp_score [count][cap] int32 (cv::KeyPoint::response; 0 without suppression), in
+ * cv::FAST's row-major order; n_kp [count] = number of corners FOUND (only the first cap are stored). */
+int vsb_fast_detect(vsb_ctx_t* ctx, const uint8_t* img, int64_t img_stride, int pitch, int w, int h, int count,
+                    int threshold, int nonmax, int cap, int32_t* kp_xy, int32_t* kp_score, int32_t* n_kp, void* stream);
+
 /* Work counters of the solver since the last call (then reset): out[0] = frame pairs solved,
  * out[1] = GN iterations (error evaluations), out[2] = sum over iterations of the candidate points visited
  * (SURVEY.md §8d's  sum_l K_l * P_l), out[3] = symmetric matches found.  Synchronises the device. */

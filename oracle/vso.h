@@ -155,4 +155,9 @@ typedef struct {
 #ifdef __cplusplus
 }
 #endif
+/* FAST-9/16 corners (cv::FAST as used inside cv::ORB / cv::cuda::ORB, Camera.cpp:124-129, CameraGPU.cpp:99-104):
+ * up to cap corners (x, y) + score in row-major order; returns the total found.  oracle/fast.c */
+int vso_fast9(const uint8_t* img, int w, int h, int pitch, int threshold, int nonmax, int32_t* out_xy, int32_t* out_score,
+              int cap);
+
 #endif

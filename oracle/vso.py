@@ -101,6 +101,8 @@ def lib():
     L.vso_gn_solve.argtypes = [C.POINTER(GnFrames), C.POINTER(Intr), _f32p, C.POINTER(GnOpts), _f32p,
                                C.POINTER(GnTrace), C.c_int]
     L.vso_gn_solve.restype = C.c_int
+    L.vso_fast9.argtypes = [_u8p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _i32p, _i32p, C.c_int]
+    L.vso_fast9.restype = C.c_int
     _lib = L
     return L
 
@@ -209,6 +211,18 @@ def grad_mag(gx, gy):
     lib().vso_grad_mag(np.ascontiguousarray(gx).reshape(-1), np.ascontiguousarray(gy).reshape(-1), gx.size,
                        g.reshape(-1))
     return g
+
+
+def fast9(img, threshold=20, nonmax=True, cap=None):
+    """cv::FAST(TYPE_9_16): returns (xy [n,2] int32, score [n] int32) in row-major order."""
+    img = np.ascontiguousarray(img, np.uint8)
+    h, w = img.shape
+    cap = w * h if cap is None else cap
+    xy = np.zeros((max(cap, 1), 2), np.int32)
+    sc = np.zeros((max(cap, 1),), np.int32)
+    n = lib().vso_fast9(img, w, h, w, int(threshold), int(bool(nonmax)), xy, sc, cap)
+    n = min(n, cap)
+    return xy[:n].copy(), sc[:n].copy()
 
 
 def candidates(good_xy, lvl, lw, lh):

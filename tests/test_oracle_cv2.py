@@ -59,3 +59,16 @@ def test_inv6_vs_cv2(oracle):
         ok, inv = oracle.inv6(A)
         _, ref = cv2.invert(A, flags=cv2.DECOMP_LU)
         np.testing.assert_array_equal(inv, ref)
+
+
+@pytest.mark.parametrize("shape", [(480, 752), (33, 67), (7, 7), (6, 40)])
+def test_fast9_vs_cv2(oracle, shape):
+    rng = np.random.default_rng(shape[0] * 31 + shape[1])
+    for img in (rng.integers(0, 256, shape, dtype=np.uint8),
+                cv2.GaussianBlur(rng.integers(0, 256, shape, dtype=np.uint8), (5, 5), 1.0)):
+        for thr, nm in ((20, True), (20, False), (5, True)):
+            det = cv2.FastFeatureDetector_create(threshold=thr, nonmaxSuppression=nm, type=cv2.FAST_FEATURE_DETECTOR_TYPE_9_16)
+            kps = det.detect(img)
+            xy, sc = oracle.fast9(img, thr, nm)
+            np.testing.assert_array_equal(xy, np.array([[int(k.pt[0]), int(k.pt[1])] for k in kps], np.int32).reshape(-1, 2))
+            np.testing.assert_array_equal(sc, np.array([int(k.response) for k in kps], np.int32))

@@ -115,3 +115,21 @@ def test_intrinsics_known_answer(oracle):
         assert K[l].w == 752 >> l and K[l].h == 480 >> l
         np.testing.assert_allclose([K[l].fx, K[l].fy, K[l].cx, K[l].cy], [fx[l], fy[l], cx[l], cy[l]], rtol=2e-7)
         assert K[l].invfx == np.float32(1) / np.float32(K[l].fx)
+
+
+def test_fast9_against_cv2_golden(oracle):
+    """oracle/fast.c vs cv2.FastFeatureDetector (TYPE_9_16): corners, row-major order and scores, thresholds 0 / 20 / 50,
+    with and without non-maximum suppression (tests/golden/fast_cv2.npz, make_fast_golden.py)."""
+    g = load("fast_cv2.npz")
+    names = [k[4:] for k in g.files if k.startswith("img_")]
+    assert len(names) == 5
+    total = 0
+    for name in names:
+        img = g["img_" + name]
+        for thr in (0, 20, 50):
+            for nm in (0, 1):
+                xy, sc = oracle.fast9(img, thr, bool(nm))
+                np.testing.assert_array_equal(xy, g[f"xy_{name}_{thr}_{nm}"], err_msg=f"{name} {thr} {nm}")
+                np.testing.assert_array_equal(sc, g[f"sc_{name}_{thr}_{nm}"], err_msg=f"{name} {thr} {nm}")
+                total += len(xy)
+    assert total > 10000

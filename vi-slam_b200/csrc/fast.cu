@@ -1,0 +1,394 @@
+// fast.cu — FAST-9/16 corner detection with non-maximum suppression on the device, batched over frames: the key-point
+// stage of the feature detectors the reference calls before the tracking path (cv::ORB, src/Camera.cpp:124-129, and
+// cv::cuda::ORB, src/CameraGPU.cpp:99-104, both detect with FAST-9/16, threshold 20) — SURVEY.md 8f row N-4, first stage.
+// Semantics are cv::FAST(TYPE_9_16)'s, restated in oracle/fast.c and pinned there against cv2: corner test, score
+// (largest threshold that keeps the pixel a corner, minus one), strict 3x3 suppression, row-major output order.
+//
+//   fast_score_kernel   one 64x16 tile (+halo) per CTA in shared memory, four adjacent pixels per thread; the 32 ring
+//                       comparisons and the "9 contiguous" test run on packed bytes (SWAR), corners get their score from
+//                       sliding-window minima.  Writes score + 1 per pixel (0 = no corner): one byte read, one written.
+//   fast_count4_kernel  one warp per image row, 4 pixels per lane: 3x3 suppression on packed bytes, the row's corner count
+//                       (fast_count_kernel: byte-wise variant for widths that are not a multiple of 4).
+//   fast_scan_kernel    exclusive scan of the row counts of each frame (row-major order needs the offsets).
+//   fast_write4_kernel  suppression again (cheaper than a flag image), warp scan, ordered write of (x, y, score) while the
+//                       slot is below the caller's capacity (fast_write_kernel: byte-wise variant).
+#include "common.cuh"
+
+namespace {
+
+
+// ring offsets (x, y) of the radius-3 Bresenham circle, clockwise from (0, 3) — cv::FAST's order.  Kept as local constant
+// arrays inside the kernel: after unrolling they fold into immediate shared-memory offsets.
+#define FAST_RING_X {0, 1, 2, 3, 3, 3, 2, 1, 0, -1, -2, -3, -3, -3, -2, -1}
+#define FAST_RING_Y {3, 3, 2, 1, 0, -1, -2, -3, -3, -3, -2, -1, 0, 1, 2, 3}
+
+__device__ __forceinline__ bool has_arc9(uint32_t m16) {      // 9 contiguous set bits in the circular 16-bit mask
+    const uint32_t x = m16 | (m16 << 16);
+    uint32_t t = x & (x >> 1);
+    t &= t >> 2;
+    t &= t >> 4;                                               // bit i: bits i..i+7 set
+    t &= x >> 8;                                               // ... and bit i+8
+    return (t & 0xFFFFu) != 0u;
+}
+
+// max over the 16 arcs of the minimum of a[k..k+8] (indices mod 16)
+__device__ __forceinline__ int best_arc_min(const int (&a)[16]) {
+    int m2[16], m4[16];
+#pragma unroll
+    for (int k = 0; k < 16; k++) m2[k] = min(a[k], a[(k + 1) & 15]);
+#pragma unroll
+    for (int k = 0; k < 16; k++) m4[k] = min(m2[k], m2[(k + 2) & 15]);
+    int best = -(1 << 30);
+#pragma unroll
+    for (int k = 0; k < 16; k++) {
+        const int m8 = min(m4[k], m4[(k + 4) & 15]);
+        best = max(best, min(m8, a[(k + 8) & 15]));
+    }
+    return best;
+}
+
+// Byte-wise unsigned compare of four packed pixels, result in bit 7 of every byte (the other bits are garbage):
+//   gt7(a, b):  a_j > b_j.   The carry out of bit 6 of (a & 0x7f) + (~b & 0x7f) tells a7 > b7 for the low 7 bits, and the
+//   majority-like LOP3 0xb2 folds in the top bits — the first four instructions of the compiler's own __vcmpgtu4 (which
+//   then spends one more to smear bit 7 over the byte; the arc test below only needs the bit).
+__device__ __forceinline__ uint32_t gt7(uint32_t a, uint32_t b) {
+    uint32_t r;
+    const uint32_t t = (a & 0x7f7f7f7fu) + (~b & 0x7f7f7f7fu);
+    asm("lop3.b32 %0, %1, %2, %3, 0xb2;" : "=r"(r) : "r"(a), "r"(b), "r"(t));
+    return r;
+}
+
+// One 64x16 tile per CTA, FOUR horizontally adjacent pixels per thread, all ring comparisons on packed bytes.
+// Shared tile: 22 rows x 72 bytes (x0 - 4 .. x0 + 67), so a thread's centre word is aligned and the 16 ring positions of
+// its four pixels are funnel shifts of three aligned words per row (21 LDS.32 per thread instead of 17 byte loads per
+// pixel); rows are 48 words apart so that the two tile rows a warp touches fall into disjoint banks.  (Reading the 21
+// words straight through L1 instead was measured 13 % slower.)
+// Arc test on bit masks: T3_k = B_k & B_k+1 & B_k+2, T9_k = T3_k & T3_k+3 & T3_k+6 (one LOP3 each), any = OR_k T9_k.
+// Pixels that ARE corners take the scalar score path.
+constexpr int FT_W = 64, FT_H = 16, FT_HALO = 3, FT_SH = FT_H + 2 * FT_HALO;
+constexpr int FT_WORDS = 18, FT_PITCH = 48;
+
+__global__ void __launch_bounds__(256)
+fast_score_kernel(const uint8_t* __restrict__ img, long long img_stride, int pitch, int w, int h, int threshold,
+                  uint8_t* __restrict__ score1) {
+    __shared__ uint32_t s[FT_SH][FT_PITCH];
+    const int frame = blockIdx.z;
+    const uint8_t* in = img + (size_t)frame * img_stride;
+    uint8_t* out = score1 + (size_t)frame * w * h;
+    const int x0 = blockIdx.x * FT_W, y0 = blockIdx.y * FT_H;
+    const bool aligned_in = ((reinterpret_cast<uintptr_t>(in) | (uintptr_t)pitch) & 3u) == 0;
+    for (int p = threadIdx.x; p < FT_SH * FT_WORDS; p += 256) {
+        const int py = p / FT_WORDS, pw = p - py * FT_WORDS;
+        const int gx = x0 - 4 + 4 * pw, gy = y0 + py - FT_HALO;
+        uint32_t v = 0u;
+        if (gy >= 0 && gy < h) {
+            const uint8_t* row = in + (size_t)gy * pitch;
+            if (aligned_in && gx >= 0 && gx + 3 < w) {
+                v = __ldg(reinterpret_cast<const uint32_t*>(row + gx));
+            } else {
+#pragma unroll
+                for (int j = 0; j < 4; j++)
+                    if (gx + j >= 0 && gx + j < w) v |= (uint32_t)__ldg(row + gx + j) << (8 * j);
+            }
+        }
+        s[py][pw] = v;
+    }
+    __syncthreads();
+    const int ty = threadIdx.x >> 4, wc = (threadIdx.x & 15) + 1;      // row in the tile, word column of the centre word
+    const int x = x0 + 4 * (wc - 1), y = y0 + ty;
+    if (x >= w || y >= h) return;
+    uint32_t result = 0u;
+    if (y >= 3 && y < h - 3) {
+        uint32_t W[7][3];                                              // rows y-3 .. y+3, word columns wc-1, wc, wc+1
+#pragma unroll
+        for (int r = 0; r < 7; r++)
+#pragma unroll
+            for (int c = 0; c < 3; c++) W[r][c] = s[ty + r][wc - 1 + c];
+        const uint32_t C = W[3][1];
+        const uint32_t T4 = (uint32_t)threshold * 0x01010101u;
+        const uint32_t hi = __vaddus4(C, T4), lo = __vsubus4(C, T4);   // saturating: a ring byte can never beat 255 / 0
+        const int ring_x[16] = FAST_RING_X, ring_y[16] = FAST_RING_Y;
+        uint32_t R[16], Bb[16], Bd[16];
+#pragma unroll
+        for (int k = 0; k < 16; k++) {
+            const int rx = ring_x[k], row = 3 + ring_y[k];
+            const int c0 = rx < 0 ? 0 : 1, sh = (rx + 4) & 3;          // first aligned word and byte shift of the 4-pixel window
+            R[k] = sh == 0 ? W[row][c0] : __funnelshift_r(W[row][c0], W[row][c0 + 1], 8 * sh);
+            Bb[k] = gt7(R[k], hi);                                     // ring brighter than centre + t
+            Bd[k] = gt7(lo, R[k]);                                     // ring darker than centre - t
+        }
+        uint32_t any_b = 0u, any_d = 0u;
+        {
+            uint32_t T3b[16], T3d[16];
+#pragma unroll
+            for (int k = 0; k < 16; k++) {
+                T3b[k] = Bb[k] & Bb[(k + 1) & 15] & Bb[(k + 2) & 15];
+                T3d[k] = Bd[k] & Bd[(k + 1) & 15] & Bd[(k + 2) & 15];
+            }
+#pragma unroll
+            for (int k = 0; k < 16; k++) {
+                any_b |= T3b[k] & T3b[(k + 3) & 15] & T3b[(k + 6) & 15];
+                any_d |= T3d[k] & T3d[(k + 3) & 15] & T3d[(k + 6) & 15];
+            }
+        }
+        uint32_t corner = (any_b | any_d) & 0x80808080u;
+        if (corner) {
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                if (!((corner >> (8 * j + 7)) & 1u)) continue;
+                if (x + j < 3 || x + j >= w - 3) continue;             // the 3-pixel border is never a corner
+                const int v = (int)((C >> (8 * j)) & 0xFFu);
+                int d[16], neg[16];
+#pragma unroll
+                for (int k = 0; k < 16; k++) {
+                    d[k] = v - (int)((R[k] >> (8 * j)) & 0xFFu);
+                    neg[k] = -d[k];
+                }
+                const int best = max(best_arc_min(d), best_arc_min(neg));   // > threshold for a corner; score + 1, in 1..255
+                result |= (uint32_t)best << (8 * j);
+            }
+        }
+    }
+    uint8_t* o = out + (size_t)y * w + x;
+    if ((w & 3) == 0) {
+        *reinterpret_cast<uint32_t*>(o) = result;
+    } else {
+#pragma unroll
+        for (int j = 0; j < 4; j++)
+            if (x + j < w) o[j] = (uint8_t)(result >> (8 * j));
+    }
+}
+
+__device__ __forceinline__ bool fast_keep(const uint8_t* __restrict__ sc, int w, int x, int y, int nonmax, int& score) {
+    const int s1 = sc[(size_t)y * w + x];
+    if (!s1) return false;
+    score = s1 - 1;
+    if (!nonmax) return true;
+    // interior corners only exist for 3 <= x < w-3, 3 <= y < h-3, so all 8 neighbours are inside the image
+    const uint8_t* r0 = sc + (size_t)(y - 1) * w + x;
+    const uint8_t* r1 = sc + (size_t)y * w + x;
+    const uint8_t* r2 = sc + (size_t)(y + 1) * w + x;
+    int m = max(max(r0[-1], r0[0]), r0[1]);
+    m = max(m, max(r1[-1], r1[1]));
+    m = max(m, max(max(r2[-1], r2[0]), r2[1]));
+    const int other = m ? m - 1 : 0;                                   // "no corner" counts as score 0
+    return score > other;
+}
+
+__global__ void __launch_bounds__(256)
+fast_count_kernel(const uint8_t* __restrict__ score1, int w, int h, int nonmax, int32_t* __restrict__ row_count) {
+    const int y = blockIdx.x, frame = blockIdx.y;
+    const uint8_t* sc = score1 + (size_t)frame * w * h;
+    int n = 0;
+    if (y >= 3 && y < h - 3)
+        for (int x = 3 + threadIdx.x; x < w - 3; x += 256) {
+            int sco;
+            n += fast_keep(sc, w, x, y, nonmax, sco) ? 1 : 0;
+        }
+    __shared__ int s_part[8];
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) n += __shfl_down_sync(0xffffffffu, n, off);
+    if ((threadIdx.x & 31) == 0) s_part[threadIdx.x >> 5] = n;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int t = 0;
+        for (int i = 0; i < 8; i++) t += s_part[i];
+        row_count[(size_t)frame * h + y] = t;
+    }
+}
+
+__global__ void __launch_bounds__(256)
+fast_scan_kernel(const int32_t* __restrict__ row_count, int h, int32_t* __restrict__ row_offset, int32_t* __restrict__ n_kp) {
+    const int frame = blockIdx.x;
+    const int32_t* c = row_count + (size_t)frame * h;
+    int32_t* o = row_offset + (size_t)frame * h;
+    __shared__ int s_sum[256];
+    const int per = (h + 255) / 256;
+    const int b = threadIdx.x * per, e = min(b + per, h);
+    int t = 0;
+    for (int i = b; i < e; i++) t += c[i];
+    s_sum[threadIdx.x] = t;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int acc = 0;
+        for (int i = 0; i < 256; i++) { const int v = s_sum[i]; s_sum[i] = acc; acc += v; }
+        n_kp[frame] = acc;
+    }
+    __syncthreads();
+    int acc = s_sum[threadIdx.x];
+    for (int i = b; i < e; i++) { o[i] = acc; acc += c[i]; }
+}
+
+__global__ void __launch_bounds__(256)
+fast_write_kernel(const uint8_t* __restrict__ score1, int w, int h, int nonmax, const int32_t* __restrict__ row_offset,
+                  int cap, int32_t* __restrict__ kp_xy, int32_t* __restrict__ kp_score) {
+    const int y = blockIdx.x, frame = blockIdx.y;
+    if (y < 3 || y >= h - 3) return;
+    const uint8_t* sc = score1 + (size_t)frame * w * h;
+    int base = row_offset[(size_t)frame * h + y];
+    if (base >= cap) return;
+    int32_t* oxy = kp_xy + (size_t)frame * cap * 2;
+    int32_t* osc = kp_score + (size_t)frame * cap;
+    __shared__ int s_warp[8];
+    __shared__ int s_total;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int xb = 3; xb < w - 3; xb += 256) {
+        const int x = xb + threadIdx.x;
+        int sco = 0;
+        const bool keep = x < w - 3 && fast_keep(sc, w, x, y, nonmax, sco);
+        const unsigned ballot = __ballot_sync(0xffffffffu, keep);
+        const int in_warp = __popc(ballot & ((1u << lane) - 1u));
+        if (lane == 0) s_warp[warp] = __popc(ballot);
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            int acc = 0;
+            for (int i = 0; i < 8; i++) { const int v = s_warp[i]; s_warp[i] = acc; acc += v; }
+            s_total = acc;
+        }
+        __syncthreads();
+        if (keep) {
+            const int slot = base + s_warp[warp] + in_warp;
+            if (slot < cap) {
+                oxy[2 * slot] = x; oxy[2 * slot + 1] = y;
+                osc[slot] = nonmax ? sco : 0;
+            }
+        }
+        base += s_total;
+        __syncthreads();
+        if (base >= cap) return;
+    }
+}
+
+
+// ---- compaction, 4 pixels per lane (score rows 4-byte aligned: w % 4 == 0) -----------------------------------------------
+// One warp per image row.  A lane looks at 4 consecutive pixels: their score bytes and the words left / right of them for
+// the rows y-1, y, y+1; the 3x3 neighbour maximum and the "strictly greater" test run on all four bytes at once
+// (__vmaxu4 / __vcmpgtu4).  score1 bytes are score + 1 with 0 = no corner, so "keep" is  cur > max(neighbours, 1).
+// Words that straddle the row ends only ever pick up pixels of the 3-pixel border, which are never corners (0).
+__device__ __forceinline__ uint32_t row_max3(uint32_t prev, uint32_t cur, uint32_t next, bool centre) {
+    const uint32_t L = (cur << 8) | (prev >> 24);          // byte j = pixel j - 1
+    const uint32_t R = (cur >> 8) | (next << 24);          // byte j = pixel j + 1
+    const uint32_t m = __vmaxu4(L, R);
+    return centre ? __vmaxu4(m, cur) : m;
+}
+__device__ __forceinline__ uint32_t keep_mask4(const uint32_t* __restrict__ r0, const uint32_t* __restrict__ r1,
+                                               const uint32_t* __restrict__ r2, int k, int nonmax, uint32_t& cur) {
+    cur = __ldg(r1 + k);
+    if (cur == 0u) return 0u;                              // the common case: no corner among these 4 pixels
+    if (!nonmax) return __vcmpgtu4(cur, 0u);
+    uint32_t n = row_max3(__ldg(r1 + k - 1), cur, __ldg(r1 + k + 1), false);
+    n = __vmaxu4(n, row_max3(__ldg(r0 + k - 1), __ldg(r0 + k), __ldg(r0 + k + 1), true));
+    n = __vmaxu4(n, row_max3(__ldg(r2 + k - 1), __ldg(r2 + k), __ldg(r2 + k + 1), true));
+    return __vcmpgtu4(cur, __vmaxu4(n, 0x01010101u));
+}
+
+__global__ void __launch_bounds__(256)
+fast_count4_kernel(const uint8_t* __restrict__ score1, int w, int h, int nonmax, int32_t* __restrict__ row_count) {
+    const int y = blockIdx.x * 8 + (threadIdx.x >> 5), frame = blockIdx.y, lane = threadIdx.x & 31;
+    if (y >= h) return;
+    int n = 0;
+    if (y >= 3 && y < h - 3) {
+        const uint8_t* sc = score1 + (size_t)frame * w * h;
+        const uint32_t* r0 = reinterpret_cast<const uint32_t*>(sc + (size_t)(y - 1) * w);
+        const uint32_t* r1 = reinterpret_cast<const uint32_t*>(sc + (size_t)y * w);
+        const uint32_t* r2 = reinterpret_cast<const uint32_t*>(sc + (size_t)(y + 1) * w);
+        for (int k = lane; k < (w >> 2); k += 32) {
+            uint32_t cur;
+            n += __popc(keep_mask4(r0, r1, r2, k, nonmax, cur) & 0x01010101u);
+        }
+    }
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) n += __shfl_down_sync(0xffffffffu, n, off);
+    if (lane == 0) row_count[(size_t)frame * h + y] = n;
+}
+
+__global__ void __launch_bounds__(256)
+fast_write4_kernel(const uint8_t* __restrict__ score1, int w, int h, int nonmax, const int32_t* __restrict__ row_offset,
+                   int cap, int32_t* __restrict__ kp_xy, int32_t* __restrict__ kp_score) {
+    const int y = blockIdx.x * 8 + (threadIdx.x >> 5), frame = blockIdx.y, lane = threadIdx.x & 31;
+    if (y < 3 || y >= h - 3) return;
+    int base = row_offset[(size_t)frame * h + y];
+    if (base >= cap) return;
+    const uint8_t* sc = score1 + (size_t)frame * w * h;
+    const uint32_t* r0 = reinterpret_cast<const uint32_t*>(sc + (size_t)(y - 1) * w);
+    const uint32_t* r1 = reinterpret_cast<const uint32_t*>(sc + (size_t)y * w);
+    const uint32_t* r2 = reinterpret_cast<const uint32_t*>(sc + (size_t)(y + 1) * w);
+    int32_t* oxy = kp_xy + (size_t)frame * cap * 2;
+    int32_t* osc = kp_score + (size_t)frame * cap;
+    const int words = w >> 2;
+    for (int k0 = 0; k0 < words; k0 += 32) {
+        const int k = k0 + lane;
+        uint32_t cur = 0u, keep = 0u;
+        if (k < words) keep = keep_mask4(r0, r1, r2, k, nonmax, cur);
+        if (!__any_sync(0xffffffffu, keep != 0u)) continue;
+        const int cnt = __popc(keep & 0x01010101u);
+        int incl = cnt;                                    // inclusive warp scan of the per-lane counts
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+            const int v = __shfl_up_sync(0xffffffffu, incl, off);
+            if (lane >= off) incl += v;
+        }
+        int slot = base + incl - cnt;
+#pragma unroll
+        for (int j = 0; j < 4; j++)
+            if ((keep >> (8 * j)) & 1u) {
+                if (slot < cap) {
+                    oxy[2 * slot] = 4 * k + j; oxy[2 * slot + 1] = y;
+                    osc[slot] = nonmax ? (int)((cur >> (8 * j)) & 0xFFu) - 1 : 0;
+                }
+                slot++;
+            }
+        base += __shfl_sync(0xffffffffu, incl, 31);
+        if (base >= cap) return;
+    }
+}
+
+}  // namespace
+
+// FAST-9/16 corners of `count` frames (cv::FAST, TYPE_9_16).  img: frames of h rows x pitch bytes, img_stride bytes apart.
+// kp_xy [count][cap][2] int32 (x, y) and kp_score [count][cap] int32 in row-major order; n_kp [count] = corners FOUND
+// (may exceed cap; only the first cap are stored).  Scratch comes from the context.
+extern "C" int vsb_fast_detect(vsb_ctx_t* ctx, const uint8_t* img, int64_t img_stride, int pitch, int w, int h, int count,
+                               int threshold, int nonmax, int cap, int32_t* kp_xy, int32_t* kp_score, int32_t* n_kp,
+                               void* stream) {
+    if (!ctx || !img || !kp_xy || !kp_score || !n_kp) return VSB_ERR_INVALID;
+    if (w <= 0 || h <= 0 || pitch < w || count < 0 || cap < 0 || threshold < 0 || threshold > 255) return VSB_ERR_INVALID;
+    if (count == 0) return VSB_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t img_bytes = ((size_t)count * w * h + 255) & ~(size_t)255;
+    const size_t rows_bytes = ((size_t)count * h * sizeof(int32_t) + 255) & ~(size_t)255;
+    void* scratch = nullptr;
+    int rc = vsb_scratch_reserve(ctx, img_bytes + 2 * rows_bytes + 256, &scratch);
+    if (rc) return rc;
+    uint8_t* score1 = static_cast<uint8_t*>(scratch);
+    int32_t* row_count = reinterpret_cast<int32_t*>(score1 + img_bytes);
+    int32_t* row_offset = reinterpret_cast<int32_t*>(score1 + img_bytes + rows_bytes);
+    for (int z0 = 0; z0 < count; z0 += 65535) {
+        const int zc = count - z0 < 65535 ? count - z0 : 65535;
+        const uint8_t* in = img + (size_t)z0 * img_stride;
+        uint8_t* sc = score1 + (size_t)z0 * w * h;
+        {
+            ProfScope ps(ctx, VSB_K_FAST_SCORE, st);
+            fast_score_kernel<<<dim3(vsb_div_up(w, FT_W), vsb_div_up(h, FT_H), zc), 256, 0, st>>>(in, img_stride, pitch, w, h,
+                                                                                                 threshold, sc);
+            VSB_LAUNCHED(ctx);
+        }
+        ProfScope ps(ctx, VSB_K_FAST_COMPACT, st);
+        const bool words = (w % 4) == 0;                   // 4 pixels per lane needs 4-byte aligned score rows
+        if (words) fast_count4_kernel<<<dim3(vsb_div_up(h, 8), zc), 256, 0, st>>>(sc, w, h, nonmax, row_count + (size_t)z0 * h);
+        else fast_count_kernel<<<dim3(h, zc), 256, 0, st>>>(sc, w, h, nonmax, row_count + (size_t)z0 * h);
+        VSB_LAUNCHED(ctx);
+        fast_scan_kernel<<<zc, 256, 0, st>>>(row_count + (size_t)z0 * h, h, row_offset + (size_t)z0 * h, n_kp + z0);
+        VSB_LAUNCHED(ctx);
+        if (cap > 0) {
+            if (words)
+                fast_write4_kernel<<<dim3(vsb_div_up(h, 8), zc), 256, 0, st>>>(sc, w, h, nonmax, row_offset + (size_t)z0 * h, cap,
+                                                                               kp_xy + (size_t)z0 * cap * 2, kp_score + (size_t)z0 * cap);
+            else
+                fast_write_kernel<<<dim3(h, zc), 256, 0, st>>>(sc, w, h, nonmax, row_offset + (size_t)z0 * h, cap,
+                                                                kp_xy + (size_t)z0 * cap * 2, kp_score + (size_t)z0 * cap);
+            VSB_LAUNCHED(ctx);
+        }
+    }
+    return VSB_OK;
+}

@@ -56,7 +56,7 @@ EXPORTS = [
     "vsb_gather_keypoints", "vsb_init_pyramid", "vsb_gn_default_opts", "vsb_gn_solve", "vsb_initial_pose",
     "vsb_se3_mul", "vsb_tracker_create", "vsb_tracker_destroy", "vsb_track_sequence",
     "vsb_track_sequence_host", "vsb_track_pairs", "vsb_kernel_count", "vsb_kernel_name", "vsb_profile_enable",
-    "vsb_profile_reset", "vsb_profile_read", "vsb_popc_peak", "vsb_tracker_stats", "vsb_tracker_host_traffic",
+    "vsb_profile_reset", "vsb_profile_read", "vsb_popc_peak", "vsb_tracker_stats", "vsb_tracker_host_traffic", "vsb_fast_detect",
     "vsb_malloc", "vsb_free", "vsb_host_alloc", "vsb_host_free", "vsb_upload", "vsb_upload_2d", "vsb_download",
     "vsb_copy", "vsb_memset", "vsb_stream_create", "vsb_stream_destroy", "vsb_stream_sync",
     "vsb_nn_filter", "vsb_sym_matches", "vsb_sort_keys", "vsb_grid_best", "vsb_warp_se3", "vsb_se3_exp",
@@ -121,6 +121,7 @@ def lib():
     L.vsb_popc_peak.argtypes = [vp, C.POINTER(C.c_double), vp]
     L.vsb_tracker_stats.argtypes = [vp, C.POINTER(C.c_longlong)]
     L.vsb_tracker_host_traffic.argtypes = [vp, C.POINTER(C.c_longlong)]
+    L.vsb_fast_detect.argtypes = [vp, vp, i64, i32, i32, i32, i32, i32, i32, i32, vp, vp, vp, vp]
     _lib = L
     return L
 
@@ -275,6 +276,19 @@ class Context:
                                      _ptr(kp1_xy.contiguous()), B, w, h, n_cells, ratio, sym_mode, _ptr(gq), _ptr(gt),
                                      _ptr(gd), cap, _ptr(ng), _ptr(ns), _stream_ptr(stream)), self.handle)
         return gq, gt, gd, ng, ns
+
+    # ---- feature detection (first stage) ----------------------------------------------------------
+    def fast_detect(self, img, threshold=20, nonmax=True, cap=4096, stream=None):
+        """img [B,h,w] u8 (device) -> kp_xy [B,cap,2] i32, score [B,cap] i32, n_found [B] i32 (cv::FAST TYPE_9_16)."""
+        t = self.torch
+        img = img.contiguous()
+        B, h, w = img.shape
+        xy = t.zeros((B, cap, 2), dtype=t.int32, device=self.dev)
+        sc = t.zeros((B, cap), dtype=t.int32, device=self.dev)
+        n = t.zeros((B,), dtype=t.int32, device=self.dev)
+        check(lib().vsb_fast_detect(self.handle, _ptr(img), w * h, w, w, h, B, int(threshold), int(bool(nonmax)), cap,
+                                    _ptr(xy), _ptr(sc), _ptr(n), _stream_ptr(stream)), self.handle)
+        return xy, sc, n
 
     # ---- Camera --------------------------------------------------------------------------------
     def pyramid_build(self, img, layout, stream=None):
