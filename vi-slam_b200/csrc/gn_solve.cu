@@ -613,7 +613,7 @@ int vsb_gn_solve_stats(vsb_ctx_t* ctx, const uint8_t* prev_pyr, const uint8_t* c
                        const float* cand, int cand_cap, const int32_t* n_cand, const vsb_intr_t K[VSB_MAX_LEVELS],
                        const float* pose_in, const vsb_gn_opts_t* opts, int count, float* pose_out,
                        vsb_gn_trace_t* trace, int32_t* n_trace, unsigned long long* stats, void* patt_scratch,
-                       void* stream) {
+                       int patt_ready, void* stream) {
     if (!ctx || !prev_pyr || !cur_pyr || !layout || !cand || !n_cand || !K || !pose_in || !opts || !pose_out)
         return VSB_ERR_INVALID;
     if (count < 0 || cand_cap < 0) return VSB_ERR_INVALID;
@@ -649,7 +649,7 @@ int vsb_gn_solve_stats(vsb_ctx_t* ctx, const uint8_t* prev_pyr, const uint8_t* c
     P.stats = stats;
     cudaStream_t st = (cudaStream_t)stream;
     const int nlev = opts->first_lvl - opts->last_lvl + 1;
-    if (cand_cap > 0) {
+    if (cand_cap > 0 && !(patt_ready && patt_scratch)) {     // patt_ready: the caller's fused candidate pass wrote the records
         for (int z0 = 0; z0 < count; z0 += 65535) {
             GnParams Q = P;
             const int zc = count - z0 < 65535 ? count - z0 : 65535;
@@ -711,5 +711,5 @@ extern "C" int vsb_gn_solve(vsb_ctx_t* ctx, const uint8_t* prev_pyr, const uint8
                             const float* pose_in, const vsb_gn_opts_t* opts, int count, float* pose_out,
                             vsb_gn_trace_t* trace, int32_t* n_trace, void* stream) {
     return vsb_gn_solve_stats(ctx, prev_pyr, cur_pyr, prev_gx, prev_gy, pair_stride_pixels, layout, cand, cand_cap,
-                              n_cand, K, pose_in, opts, count, pose_out, trace, n_trace, nullptr, nullptr, stream);
+                              n_cand, K, pose_in, opts, count, pose_out, trace, n_trace, nullptr, nullptr, 0, stream);
 }

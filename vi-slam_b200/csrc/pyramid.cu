@@ -243,6 +243,13 @@ gradient_kernel(const uint8_t* __restrict__ pyr, GradParams P, int16_t* __restri
 struct CandParams {
     int levels;
     int lw[VSB_MAX_LEVELS], lh[VSB_MAX_LEVELS];
+    // fused attribute pass of the solver (optional): for levels last_lvl..first_lvl also write, per point, the record
+    // {Scharr gx | gy << 16, I_prev} that gn_prepare_kernel would gather (grad_mode 1 arithmetic, bit-identical)
+    const uint8_t* prev_pyr;
+    long long pair_stride;
+    vsb_pyr_layout_t lay;
+    int first_lvl, last_lvl;
+    uint2* patt;
 };
 
 __global__ void __launch_bounds__(256)
@@ -284,6 +291,10 @@ candidates_kernel(const float* __restrict__ good_xy, int good_cap, const int32_t
     __syncthreads();
     float4* out = cand + ((size_t)prob * P.levels + lvl) * cand_cap;
     const int total = min(s_off[nf], cand_cap);
+    const bool attrs = P.patt != nullptr && lvl <= P.first_lvl && lvl >= P.last_lvl;
+    uint2* pout = attrs ? P.patt + ((size_t)prob * P.levels + lvl) * cand_cap : nullptr;
+    const uint8_t* image1 = attrs ? P.prev_pyr + (size_t)prob * P.pair_stride + P.lay.offset[lvl] : nullptr;
+    const int cols = P.lay.w[lvl], rows = P.lay.h[lvl];
     // one warp per feature: lanes stride over the feature's points (i outer, j inner — reference row order)
     const int warp = tid >> 5, lane = tid & 31;
     for (int f = warp; f < nf; f += 8) {
@@ -292,6 +303,20 @@ candidates_kernel(const float* __restrict__ good_xy, int good_cap, const int32_t
             if (off + p >= total) break;
             const int ii = p / nj, jj = p - ii * nj;
             out[off + p] = make_float4((float)(ia + ii), (float)(ja + jj), 1.0f, 1.0f);
+            if (attrs) {
+                const int sx = min(max(ia + ii, 0), cols - 1), sy = min(max(ja + jj, 0), rows - 1);
+                const int xm = reflect101(sx - 1, cols), xp = reflect101(sx + 1, cols);
+                const int ym = reflect101(sy - 1, rows), yp = reflect101(sy + 1, rows);
+                const uint8_t* q0 = image1 + (size_t)ym * cols;
+                const uint8_t* q1 = image1 + (size_t)sy * cols;
+                const uint8_t* q2 = image1 + (size_t)yp * cols;
+                const int a00 = __ldg(q0 + xm), a01 = __ldg(q0 + sx), a02 = __ldg(q0 + xp);
+                const int a10 = __ldg(q1 + xm), a11 = __ldg(q1 + sx), a12 = __ldg(q1 + xp);
+                const int a20 = __ldg(q2 + xm), a21 = __ldg(q2 + sx), a22 = __ldg(q2 + xp);
+                const int gx = 3 * (3 * (a02 - a00) + 10 * (a12 - a10) + 3 * (a22 - a20));
+                const int gy = 3 * (3 * (a20 - a00) + 10 * (a21 - a01) + 3 * (a22 - a02));
+                pout[off + p] = make_uint2(((uint32_t)gx & 0xFFFFu) | ((uint32_t)gy << 16), (uint32_t)a11);
+            }
         }
     }
 }
@@ -377,15 +402,24 @@ extern "C" int vsb_gradient_build(vsb_ctx_t* ctx, const uint8_t* pyr, int count,
     return VSB_OK;
 }
 
-extern "C" int vsb_candidates_build(vsb_ctx_t* ctx, const float* good_xy, int good_cap, const int32_t* n_good,
-                                    int count, int levels, const int* lw, const int* lh, float* cand, int cand_cap,
-                                    int32_t* n_cand, void* stream) {
+// Internal entry (tracker): candidate points AND, for the solver's levels, the per-point attribute records in one pass
+// (prev_pyr == NULL: candidates only).  The candidate level sizes lw/lh must equal the pyramid layout's (exact halving).
+int vsb_candidates_prepare(vsb_ctx_t* ctx, const float* good_xy, int good_cap, const int32_t* n_good, int count, int levels,
+                           const int* lw, const int* lh, float* cand, int cand_cap, int32_t* n_cand,
+                           const uint8_t* prev_pyr, int64_t pair_stride, const vsb_pyr_layout_t* layout, int first_lvl,
+                           int last_lvl, void* patt, void* stream) {
     if (!ctx || !good_xy || !n_good || !cand || !n_cand || !lw || !lh) return VSB_ERR_INVALID;
     if (levels < 1 || levels > VSB_MAX_LEVELS || count < 0 || cand_cap < 0) return VSB_ERR_INVALID;
     if (count == 0) return VSB_OK;
     CandParams P;
     P.levels = levels;
     for (int l = 0; l < levels; l++) { P.lw[l] = lw[l]; P.lh[l] = lh[l]; }
+    P.prev_pyr = nullptr; P.pair_stride = 0; P.first_lvl = -1; P.last_lvl = 0; P.patt = nullptr;
+    memset(&P.lay, 0, sizeof(P.lay));
+    if (prev_pyr && layout && patt) {
+        P.prev_pyr = prev_pyr; P.pair_stride = pair_stride; P.lay = *layout;
+        P.first_lvl = first_lvl; P.last_lvl = last_lvl; P.patt = reinterpret_cast<uint2*>(patt);
+    }
     dim3 grid(count, levels);
     ProfScope ps(ctx, VSB_K_CANDIDATES, (cudaStream_t)stream);
     candidates_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(good_xy, good_cap, n_good, P,
@@ -393,3 +427,11 @@ extern "C" int vsb_candidates_build(vsb_ctx_t* ctx, const float* good_xy, int go
     VSB_LAUNCHED(ctx);
     return VSB_OK;
 }
+
+extern "C" int vsb_candidates_build(vsb_ctx_t* ctx, const float* good_xy, int good_cap, const int32_t* n_good,
+                                    int count, int levels, const int* lw, const int* lh, float* cand, int cand_cap,
+                                    int32_t* n_cand, void* stream) {
+    return vsb_candidates_prepare(ctx, good_xy, good_cap, n_good, count, levels, lw, lh, cand, cand_cap, n_cand, nullptr, 0,
+                                  nullptr, 0, 0, nullptr, stream);
+}
+
