@@ -19,7 +19,8 @@ def launches(path):
     for r in data:
         if len(r) <= mv:
             continue
-        name = r[kn].split("(")[0].replace("<unnamed>::", "").replace("void ", "")
+        # base name: template arguments dropped (the GN solver is instantiated per thread count)
+        name = r[kn].split("(")[0].replace("<unnamed>::", "").replace("void ", "").split("<")[0]
         e = per.setdefault(r[idc], [name, 0.0, 0])
         if r[mn] == "gpu__time_duration.sum":
             e[1] = float(r[mv].replace(",", ""))

@@ -64,14 +64,18 @@ __device__ __forceinline__ uint32_t gt7(uint32_t a, uint32_t b) {
 // pixel); rows are 48 words apart so that the two tile rows a warp touches fall into disjoint banks.  (Reading the 21
 // words straight through L1 instead was measured 13 % slower.)
 // Arc test on bit masks: T3_k = B_k & B_k+1 & B_k+2, T9_k = T3_k & T3_k+3 & T3_k+6 (one LOP3 each), any = OR_k T9_k.
-// Pixels that ARE corners take the scalar score path.
+// Pixels that ARE corners (a percent or so) are queued in shared memory and scored densely, one thread per corner, after
+// the tile's flag pass — inside the flag pass the scalar score would run for whole warps whenever one lane has a corner.
 constexpr int FT_W = 64, FT_H = 16, FT_HALO = 3, FT_SH = FT_H + 2 * FT_HALO;
 constexpr int FT_WORDS = 18, FT_PITCH = 48;
 
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 4)
 fast_score_kernel(const uint8_t* __restrict__ img, long long img_stride, int pitch, int w, int h, int threshold,
                   uint8_t* __restrict__ score1) {
     __shared__ uint32_t s[FT_SH][FT_PITCH];
+    __shared__ uint16_t s_list[FT_W * FT_H];                            // tile-local (y << 6 | x) of the corners found
+    __shared__ int s_count;
+    if (threadIdx.x == 0) s_count = 0;
     const int frame = blockIdx.z;
     const uint8_t* in = img + (size_t)frame * img_stride;
     uint8_t* out = score1 + (size_t)frame * w * h;
@@ -96,9 +100,9 @@ fast_score_kernel(const uint8_t* __restrict__ img, long long img_stride, int pit
     __syncthreads();
     const int ty = threadIdx.x >> 4, wc = (threadIdx.x & 15) + 1;      // row in the tile, word column of the centre word
     const int x = x0 + 4 * (wc - 1), y = y0 + ty;
-    if (x >= w || y >= h) return;
-    uint32_t result = 0u;
-    if (y >= 3 && y < h - 3) {
+    const bool in_image = x < w && y < h;
+    uint32_t corner = 0u;
+    if (in_image && y >= 3 && y < h - 3) {
         uint32_t W[7][3];                                              // rows y-3 .. y+3, word columns wc-1, wc, wc+1
 #pragma unroll
         for (int r = 0; r < 7; r++)
@@ -108,16 +112,16 @@ fast_score_kernel(const uint8_t* __restrict__ img, long long img_stride, int pit
         const uint32_t T4 = (uint32_t)threshold * 0x01010101u;
         const uint32_t hi = __vaddus4(C, T4), lo = __vsubus4(C, T4);   // saturating: a ring byte can never beat 255 / 0
         const int ring_x[16] = FAST_RING_X, ring_y[16] = FAST_RING_Y;
-        uint32_t R[16], Bb[16], Bd[16];
+        uint32_t Bb[16], Bd[16];
 #pragma unroll
         for (int k = 0; k < 16; k++) {
             const int rx = ring_x[k], row = 3 + ring_y[k];
             const int c0 = rx < 0 ? 0 : 1, sh = (rx + 4) & 3;          // first aligned word and byte shift of the 4-pixel window
-            R[k] = sh == 0 ? W[row][c0] : __funnelshift_r(W[row][c0], W[row][c0 + 1], 8 * sh);
-            Bb[k] = gt7(R[k], hi);                                     // ring brighter than centre + t
-            Bd[k] = gt7(lo, R[k]);                                     // ring darker than centre - t
+            const uint32_t R = sh == 0 ? W[row][c0] : __funnelshift_r(W[row][c0], W[row][c0 + 1], 8 * sh);
+            Bb[k] = gt7(R, hi);                                        // ring brighter than centre + t
+            Bd[k] = gt7(lo, R);                                        // ring darker than centre - t
         }
-        uint32_t any_b = 0u, any_d = 0u;
+        uint32_t T9[32];                                               // 9-arc masks, both polarities
         {
             uint32_t T3b[16], T3d[16];
 #pragma unroll
@@ -127,35 +131,51 @@ fast_score_kernel(const uint8_t* __restrict__ img, long long img_stride, int pit
             }
 #pragma unroll
             for (int k = 0; k < 16; k++) {
-                any_b |= T3b[k] & T3b[(k + 3) & 15] & T3b[(k + 6) & 15];
-                any_d |= T3d[k] & T3d[(k + 3) & 15] & T3d[(k + 6) & 15];
+                T9[k] = T3b[k] & T3b[(k + 3) & 15] & T3b[(k + 6) & 15];
+                T9[16 + k] = T3d[k] & T3d[(k + 3) & 15] & T3d[(k + 6) & 15];
             }
         }
-        uint32_t corner = (any_b | any_d) & 0x80808080u;
-        if (corner) {
+        // OR of the 32 masks as a tree of 3-input LOP3s: 32 -> 11 -> 4 -> 2 -> 1
+        uint32_t a[11];
 #pragma unroll
-            for (int j = 0; j < 4; j++) {
-                if (!((corner >> (8 * j + 7)) & 1u)) continue;
-                if (x + j < 3 || x + j >= w - 3) continue;             // the 3-pixel border is never a corner
-                const int v = (int)((C >> (8 * j)) & 0xFFu);
-                int d[16], neg[16];
+        for (int k = 0; k < 10; k++) a[k] = T9[3 * k] | T9[3 * k + 1] | T9[3 * k + 2];
+        a[10] = T9[30] | T9[31];
+        const uint32_t b0 = a[0] | a[1] | a[2], b1 = a[3] | a[4] | a[5], b2 = a[6] | a[7] | a[8], b3 = a[9] | a[10];
+        corner = ((b0 | b1 | b2) | b3) & 0x80808080u;
+    }
+    // every pixel gets its byte now (0 = no corner); the few that are corners are queued for the score pass below
+    uint8_t* o = out + (size_t)y * w + x;
+    if (in_image) {
+        if ((w & 3) == 0) {
+            *reinterpret_cast<uint32_t*>(o) = 0u;
+        } else {
 #pragma unroll
-                for (int k = 0; k < 16; k++) {
-                    d[k] = v - (int)((R[k] >> (8 * j)) & 0xFFu);
-                    neg[k] = -d[k];
-                }
-                const int best = max(best_arc_min(d), best_arc_min(neg));   // > threshold for a corner; score + 1, in 1..255
-                result |= (uint32_t)best << (8 * j);
-            }
+            for (int j = 0; j < 4; j++)
+                if (x + j < w) o[j] = 0;
         }
     }
-    uint8_t* o = out + (size_t)y * w + x;
-    if ((w & 3) == 0) {
-        *reinterpret_cast<uint32_t*>(o) = result;
-    } else {
+    if (corner) {
 #pragma unroll
         for (int j = 0; j < 4; j++)
-            if (x + j < w) o[j] = (uint8_t)(result >> (8 * j));
+            if (((corner >> (8 * j + 7)) & 1u) && x + j >= 3 && x + j < w - 3)      // the 3-pixel border is never a corner
+                s_list[atomicAdd(&s_count, 1)] = (uint16_t)((ty << 6) | (4 * (wc - 1) + j));
+    }
+    __syncthreads();
+    // ---- score pass: one thread per queued corner (dense), ring bytes from the shared tile ---------------------------------
+    const uint8_t* sb = reinterpret_cast<const uint8_t*>(&s[0][0]);
+    const int ring_x[16] = FAST_RING_X, ring_y[16] = FAST_RING_Y;
+    for (int e = threadIdx.x; e < s_count; e += 256) {
+        const int ly = s_list[e] >> 6, lx = s_list[e] & 63;
+        const uint8_t* c = sb + (size_t)(ly + FT_HALO) * (FT_PITCH * 4) + lx + 4;
+        const int v = c[0];
+        int d[16], neg[16];
+#pragma unroll
+        for (int k = 0; k < 16; k++) {
+            d[k] = v - (int)c[ring_y[k] * (FT_PITCH * 4) + ring_x[k]];
+            neg[k] = -d[k];
+        }
+        const int best = max(best_arc_min(d), best_arc_min(neg));       // > threshold for a corner; score + 1, in 1..255
+        out[(size_t)(y0 + ly) * w + x0 + lx] = (uint8_t)best;
     }
 }
 
