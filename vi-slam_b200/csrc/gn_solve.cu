@@ -276,7 +276,9 @@ __device__ __noinline__ float tukey_inv_mad(const float4* __restrict__ cand, con
 constexpr int VROW = 36;   // staging row stride (floats): conflict-free for the [g][4s+t] reads of the MMA feed
 
 // U = points per thread per batch; TPS = resident threads per SM the register budget is sized for
-template <bool FP32_PARTIALS, int GT, bool TUKEY, int U = 2, int TPS = 768>
+// WM = weight mode (0 identity: the reference default, 1 Tukey, 2 Huber) at compile time: identity drops the seven
+// multiplications by w = 1 per point
+template <bool FP32_PARTIALS, int GT, int WM, int U = 2, int TPS = 768>
 __global__ void __launch_bounds__(GT, (TPS / GT) > 0 ? (TPS / GT) : 1)
 gn_solve_kernel(const GnParams P) {
     constexpr int NW = GT / 32;
@@ -298,6 +300,7 @@ gn_solve_kernel(const GnParams P) {
     __shared__ float s_last_err;
     __shared__ unsigned long long s_pts;
     __shared__ int s_upd;
+    constexpr bool TUKEY = WM == 1;
     __shared__ int s_hist[TUKEY ? 256 : 1];
     __shared__ float s_tk[2];
 
@@ -449,7 +452,7 @@ gn_solve_kernel(const GnParams P) {
                         } else {
                             wgt = 0.f;
                         }
-                    } else if (o.weight_mode == 2) {                                  // Huber extension
+                    } else if (WM == 2) {                                             // Huber extension
                         const float a = fabsf(res);
                         wgt = (a <= o.huber_k) ? 1.f : F_DIV(o.huber_k, a);
                     }
@@ -465,8 +468,8 @@ gn_solve_kernel(const GnParams P) {
                     { double s = dgx * (double)jw05; s += dgy * (double)jw15; V[5] = (float)s; }
                     const bool good = ok[u];
 #pragma unroll
-                    for (int q = 0; q < 6; q++) V[q] = good ? F_MUL(wgt, V[q]) : 0.f;  // row *= w, :1404-1405
-                    V[6] = good ? F_MUL(res, wgt) : 0.f;
+                    for (int q = 0; q < 6; q++) V[q] = good ? (WM == 0 ? V[q] : F_MUL(wgt, V[q])) : 0.f;  // row *= w, :1404-1405
+                    V[6] = good ? (WM == 0 ? res : F_MUL(res, wgt)) : 0.f;
                     V[7] = good ? res : 0.f;
                     nv += good ? 1 : 0;
                     if (!FP32_PARTIALS) {
@@ -678,25 +681,28 @@ int vsb_gn_solve_stats(vsb_ctx_t* ctx, const uint8_t* prev_pyr, const uint8_t* c
     }
 #define GN_LAUNCH(FP, T)                                                                 \
     do {                                                                                 \
-        if (opts->weight_mode == 1) gn_solve_kernel<FP, T, true><<<count, T, 0, st>>>(P); \
-        else gn_solve_kernel<FP, T, false><<<count, T, 0, st>>>(P);                      \
+        if (opts->weight_mode == 1) gn_solve_kernel<FP, T, 1><<<count, T, 0, st>>>(P);      \
+        else if (opts->weight_mode == 2) gn_solve_kernel<FP, T, 2><<<count, T, 0, st>>>(P); \
+        else gn_solve_kernel<FP, T, 0><<<count, T, 0, st>>>(P);                          \
     } while (0)
-    if (ctx->gn_variant > 0 && opts->accum_mode == 0 && opts->weight_mode != 1 && gt_env == 128) {   // tuning experiments
+    if (ctx->gn_variant > 0 && opts->accum_mode == 0 && opts->weight_mode == 0 && gt_env == 128) {   // tuning experiments
         switch (ctx->gn_variant) {    // (points per thread per batch, resident threads per SM the registers are sized for)
-            case 1: gn_solve_kernel<false, 128, false, 4, 768><<<count, 128, 0, st>>>(P); break;
-            case 2: gn_solve_kernel<false, 128, false, 2, 1024><<<count, 128, 0, st>>>(P); break;
-            case 3: gn_solve_kernel<false, 128, false, 3, 768><<<count, 128, 0, st>>>(P); break;
-            case 4: gn_solve_kernel<false, 128, false, 4, 640><<<count, 128, 0, st>>>(P); break;
-            default: gn_solve_kernel<false, 128, false, 1, 1024><<<count, 128, 0, st>>>(P); break;
+            case 1: gn_solve_kernel<false, 128, 0, 4, 768><<<count, 128, 0, st>>>(P); break;
+            case 2: gn_solve_kernel<false, 128, 0, 2, 1024><<<count, 128, 0, st>>>(P); break;
+            case 3: gn_solve_kernel<false, 128, 0, 3, 768><<<count, 128, 0, st>>>(P); break;
+            case 4: gn_solve_kernel<false, 128, 0, 4, 640><<<count, 128, 0, st>>>(P); break;
+            default: gn_solve_kernel<false, 128, 0, 1, 1024><<<count, 128, 0, st>>>(P); break;
         }
     } else if (opts->accum_mode == 1) {
         if (gt_env == 64) GN_LAUNCH(true, 64); else if (gt_env == 128) GN_LAUNCH(true, 128); else GN_LAUNCH(true, 256);
     } else if (gt_env >= 1024) {
-        if (opts->weight_mode == 1) gn_solve_kernel<false, 1024, true, 1, 1024><<<count, 1024, 0, st>>>(P);
-        else gn_solve_kernel<false, 1024, false, 1, 1024><<<count, 1024, 0, st>>>(P);
+        if (opts->weight_mode == 1) gn_solve_kernel<false, 1024, 1, 1, 1024><<<count, 1024, 0, st>>>(P);
+        else if (opts->weight_mode == 2) gn_solve_kernel<false, 1024, 2, 1, 1024><<<count, 1024, 0, st>>>(P);
+        else gn_solve_kernel<false, 1024, 0, 1, 1024><<<count, 1024, 0, st>>>(P);
     } else if (gt_env >= 512) {
-        if (opts->weight_mode == 1) gn_solve_kernel<false, 512, true, 2, 1024><<<count, 512, 0, st>>>(P);
-        else gn_solve_kernel<false, 512, false, 2, 1024><<<count, 512, 0, st>>>(P);
+        if (opts->weight_mode == 1) gn_solve_kernel<false, 512, 1, 2, 1024><<<count, 512, 0, st>>>(P);
+        else if (opts->weight_mode == 2) gn_solve_kernel<false, 512, 2, 2, 1024><<<count, 512, 0, st>>>(P);
+        else gn_solve_kernel<false, 512, 0, 2, 1024><<<count, 512, 0, st>>>(P);
     } else {
         if (gt_env == 64) GN_LAUNCH(false, 64); else if (gt_env == 128) GN_LAUNCH(false, 128); else GN_LAUNCH(false, 256);
     }
