@@ -8,6 +8,7 @@
 // distances, the sweep order is y ascending with ties in match (= queryIdx) order.  Cells are emitted
 // band-major, column-minor.  That form needs no sort and is bit-identical to the sweep.
 #include "common.cuh"
+#include "knn_keys.cuh"
 
 namespace {
 
@@ -19,22 +20,47 @@ __device__ __forceinline__ uint32_t float_order_bits(float v) {
     return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
 }
 
+// kNN results as the filter reads them.  KEYS == 0: the public form, idx / dist arrays (-1 = missing neighbour).
+// KEYS == 1 / 2: the kNN kernels' packed keys read in place — 32-bit (hamming << 23 | index) or 64-bit
+// (float bits << 32 | index), all-ones = missing — which is what knn_unpack would have expanded (tracker path).
+template <int KEYS>
+struct KnnView {
+    const int32_t* idx; const float* dist; const void* keys;
+    __device__ __forceinline__ int index(int e) const {
+        if (KEYS == 0) return idx[e];
+        if (KEYS == 1) { const uint32_t k = reinterpret_cast<const uint32_t*>(keys)[e]; return k == KEY_INF ? -1 : (int)(k & KEY_IDX_MASK); }
+        const unsigned long long k = reinterpret_cast<const unsigned long long*>(keys)[e];
+        return k == KEY64_INF ? -1 : (int)(uint32_t)(k & 0xFFFFFFFFull);
+    }
+    __device__ __forceinline__ float distance(int e) const {
+        if (KEYS == 0) return dist[e];
+        if (KEYS == 1) { const uint32_t k = reinterpret_cast<const uint32_t*>(keys)[e]; return k == KEY_INF ? 0.f : (float)(k >> KEY_SHIFT); }
+        const unsigned long long k = reinterpret_cast<const unsigned long long*>(keys)[e];
+        return k == KEY64_INF ? 0.f : __uint_as_float((uint32_t)(k >> 32));
+    }
+};
+
+template <int KEYS>
 __global__ void __launch_bounds__(FT)
-match_filter_kernel(const int32_t* __restrict__ idx12, const float* __restrict__ dist12, int n1_max,
-                    const int32_t* __restrict__ n1_arr, const int32_t* __restrict__ idx21,
-                    const float* __restrict__ dist21, int n2_max, const int32_t* __restrict__ n2_arr,
+match_filter_kernel(const int32_t* __restrict__ idx12, const float* __restrict__ dist12, const void* __restrict__ keys12,
+                    int n1_max, const int32_t* __restrict__ n1_arr, const int32_t* __restrict__ idx21,
+                    const float* __restrict__ dist21, const void* __restrict__ keys21, int n2_max,
+                    const int32_t* __restrict__ n2_arr,
                     const float* __restrict__ kp1_xy, int w, int h, int n_cells, float ratio_f, int sym_mode,
                     int32_t* __restrict__ good_q, int32_t* __restrict__ good_t, float* __restrict__ good_d,
-                    int good_cap, int32_t* __restrict__ n_good, int32_t* __restrict__ n_sym) {
+                    int good_cap, int32_t* __restrict__ n_good, int32_t* __restrict__ n_sym,
+                    float* __restrict__ good_xy) {
     extern __shared__ unsigned char smem_raw[];
     const int prob = blockIdx.x;
     const int tid = threadIdx.x;
     const int n1 = n1_arr ? min(n1_arr[prob], n1_max) : n1_max;
     const int n2 = n2_arr ? min(n2_arr[prob], n2_max) : n2_max;
-    const int32_t* i12 = idx12 + (size_t)prob * n1_max * 2;
-    const float* d12 = dist12 + (size_t)prob * n1_max * 2;
-    const int32_t* i21 = idx21 + (size_t)prob * n2_max * 2;
-    const float* d21 = dist21 + (size_t)prob * n2_max * 2;
+    const size_t o12 = (size_t)prob * n1_max * 2, o21 = (size_t)prob * n2_max * 2;
+    const size_t kb = KEYS == 2 ? 8 : 4;
+    const KnnView<KEYS> v12 = {KEYS == 0 ? idx12 + o12 : nullptr, KEYS == 0 ? dist12 + o12 : nullptr,
+                               KEYS ? static_cast<const unsigned char*>(keys12) + o12 * kb : nullptr};
+    const KnnView<KEYS> v21 = {KEYS == 0 ? idx21 + o21 : nullptr, KEYS == 0 ? dist21 + o21 : nullptr,
+                               KEYS ? static_cast<const unsigned char*>(keys21) + o21 * kb : nullptr};
     const float* kp = kp1_xy + (size_t)prob * n1_max * 2;
 
     const int root = (int)floor(sqrt((double)n_cells));         // Matcher.cpp:191
@@ -65,14 +91,15 @@ match_filter_kernel(const int32_t* __restrict__ idx12, const float* __restrict__
     int my_sym = 0;
     for (int i = tid; i < n1; i += FT) {
         int cell = -1;
-        const int j0 = i12[2 * i], j1 = i12[2 * i + 1];
-        const float dd0 = d12[2 * i], dd1 = d12[2 * i + 1];
+        // rows past the set's true size are "missing" in either form (knn_unpack wrote -1 there)
+        const int j0 = v12.index(2 * i), j1 = v12.index(2 * i + 1);
+        const float dd0 = v12.distance(2 * i), dd1 = v12.distance(2 * i + 1);
         bool keep = (j0 >= 0 && j1 >= 0) && !((double)dd0 > ratio * (double)dd1);   // Matcher.cpp:153-166
         if (keep && j0 < n2) {
-            const int b0 = i21[2 * j0], b1 = i21[2 * j0 + 1];
+            const int b0 = v21.index(2 * j0), b1 = v21.index(2 * j0 + 1);
             bool ok = (b0 >= 0);
             if (sym_mode == 1)   // intended: the 2->1 row must survive its own ratio test
-                ok = ok && (b1 >= 0) && !((double)d21[2 * j0] > ratio * (double)d21[2 * j0 + 1]);
+                ok = ok && (b1 >= 0) && !((double)v21.distance(2 * j0) > ratio * (double)v21.distance(2 * j0 + 1));
             if (ok && b0 == i) { // Matcher.cpp:124-125
                 my_sym++;
                 const float x = kp[2 * i], y = kp[2 * i + 1];
@@ -100,13 +127,13 @@ match_filter_kernel(const int32_t* __restrict__ idx12, const float* __restrict__
     __syncthreads();
     for (int i = tid; i < n1; i += FT) {
         int cell = s_cell[i];
-        if (cell >= 0 && __float_as_uint(d12[2 * i]) == s_best[cell])
+        if (cell >= 0 && __float_as_uint(v12.distance(2 * i)) == s_best[cell])
             atomicMin(&s_y[cell], float_order_bits(kp[2 * i + 1]));
     }
     __syncthreads();
     for (int i = tid; i < n1; i += FT) {
         int cell = s_cell[i];
-        if (cell >= 0 && __float_as_uint(d12[2 * i]) == s_best[cell] &&
+        if (cell >= 0 && __float_as_uint(v12.distance(2 * i)) == s_best[cell] &&
             float_order_bits(kp[2 * i + 1]) == s_y[cell])
             atomicMin(&s_i[cell], (uint32_t)i);
     }
@@ -128,8 +155,12 @@ match_filter_kernel(const int32_t* __restrict__ idx12, const float* __restrict__
         if (full && off < good_cap) {
             const int i = (int)s_i[c];
             gq[off] = i;
-            gt[off] = i12[2 * i];
-            gd[off] = d12[2 * i];
+            gt[off] = v12.index(2 * i);
+            gd[off] = v12.distance(2 * i);
+            if (good_xy) {                                   // Matcher::getGoodMatches for the previous frame (:295-303)
+                good_xy[((size_t)prob * good_cap + off) * 2] = kp[2 * i];
+                good_xy[((size_t)prob * good_cap + off) * 2 + 1] = kp[2 * i + 1];
+            }
         }
         __syncthreads();
         if (tid == 0) {
@@ -158,11 +189,11 @@ __global__ void gather_keypoints_kernel(const float2* __restrict__ kp, int n_max
 
 }  // namespace
 
-extern "C" int vsb_match_filter(vsb_ctx_t* ctx, const int32_t* idx12, const float* dist12, int n1_max,
-                                const int32_t* n1, const int32_t* idx21, const float* dist21, int n2_max,
-                                const int32_t* n2, const float* kp1_xy, int count, int w, int h, int n_cells,
-                                float ratio, int sym_mode, int32_t* good_q, int32_t* good_t, float* good_d,
-                                int good_cap, int32_t* n_good, int32_t* n_sym, void* stream) {
+static int match_filter_launch(vsb_ctx_t* ctx, int key_mode, const int32_t* idx12, const float* dist12, const void* keys12,
+                               int n1_max, const int32_t* n1, const int32_t* idx21, const float* dist21,
+                               const void* keys21, int n2_max, const int32_t* n2, const float* kp1_xy, int count, int w,
+                               int h, int n_cells, float ratio, int sym_mode, int32_t* good_q, int32_t* good_t,
+                               float* good_d, int good_cap, int32_t* n_good, int32_t* n_sym, float* good_xy, void* stream) {
     if (!ctx || count < 0 || n_cells < 1 || n1_max < 0 || n2_max < 0 || !n_good) return VSB_ERR_INVALID;
     if (count == 0) return VSB_OK;
     const int root = (int)floor(sqrt((double)n_cells));
@@ -172,14 +203,42 @@ extern "C" int vsb_match_filter(vsb_ctx_t* ctx, const int32_t* idx12, const floa
     size_t smem = (((size_t)n1_max * 2 + 15) & ~(size_t)15) + (size_t)root * root * 3 * sizeof(uint32_t);
     if (smem > 200 * 1024) return VSB_ERR_CAPACITY;
     cudaStream_t st = (cudaStream_t)stream;
-    if (smem > 48 * 1024)
-        VSB_CUDA(ctx, cudaFuncSetAttribute(match_filter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (smem > 48 * 1024) {
+        VSB_CUDA(ctx, cudaFuncSetAttribute(match_filter_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        VSB_CUDA(ctx, cudaFuncSetAttribute(match_filter_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        VSB_CUDA(ctx, cudaFuncSetAttribute(match_filter_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    }
     ProfScope ps(ctx, VSB_K_MATCH_FILTER, st);
-    match_filter_kernel<<<count, FT, smem, st>>>(idx12, dist12, n1_max, n1, idx21, dist21, n2_max, n2, kp1_xy, w, h,
-                                                  n_cells, ratio, sym_mode, good_q, good_t, good_d, good_cap, n_good,
-                                                  n_sym);
+#define MF_ARGS idx12, dist12, keys12, n1_max, n1, idx21, dist21, keys21, n2_max, n2, kp1_xy, w, h, n_cells, ratio, sym_mode, \
+                good_q, good_t, good_d, good_cap, n_good, n_sym, good_xy
+    if (key_mode == 1) match_filter_kernel<1><<<count, FT, smem, st>>>(MF_ARGS);
+    else if (key_mode == 2) match_filter_kernel<2><<<count, FT, smem, st>>>(MF_ARGS);
+    else match_filter_kernel<0><<<count, FT, smem, st>>>(MF_ARGS);
+#undef MF_ARGS
     VSB_LAUNCHED(ctx);
     return VSB_OK;
+}
+
+extern "C" int vsb_match_filter(vsb_ctx_t* ctx, const int32_t* idx12, const float* dist12, int n1_max,
+                                const int32_t* n1, const int32_t* idx21, const float* dist21, int n2_max,
+                                const int32_t* n2, const float* kp1_xy, int count, int w, int h, int n_cells,
+                                float ratio, int sym_mode, int32_t* good_q, int32_t* good_t, float* good_d,
+                                int good_cap, int32_t* n_good, int32_t* n_sym, void* stream) {
+    return match_filter_launch(ctx, 0, idx12, dist12, nullptr, n1_max, n1, idx21, dist21, nullptr, n2_max, n2, kp1_xy, count,
+                               w, h, n_cells, ratio, sym_mode, good_q, good_t, good_d, good_cap, n_good, n_sym, nullptr,
+                               stream);
+}
+
+// Internal entry (tracker): reads the kNN kernels' packed keys in place (key_bytes 4: Hamming, 8: float) and also
+// gathers the key points of the good matches (Matcher::getGoodMatches), so neither knn_unpack nor the gather runs.
+int vsb_match_filter_keys(vsb_ctx_t* ctx, const void* keys12, const void* keys21, int key_bytes, int n1_max,
+                          const int32_t* n1, int n2_max, const int32_t* n2, const float* kp1_xy, int count, int w, int h,
+                          int n_cells, float ratio, int sym_mode, int32_t* good_q, int32_t* good_t, float* good_d,
+                          int good_cap, int32_t* n_good, int32_t* n_sym, float* good_xy, void* stream) {
+    if (!keys12 || !keys21 || (key_bytes != 4 && key_bytes != 8)) return VSB_ERR_INVALID;
+    return match_filter_launch(ctx, key_bytes == 4 ? 1 : 2, nullptr, nullptr, keys12, n1_max, n1, nullptr, nullptr, keys21,
+                               n2_max, n2, kp1_xy, count, w, h, n_cells, ratio, sym_mode, good_q, good_t, good_d, good_cap,
+                               n_good, n_sym, good_xy, stream);
 }
 
 extern "C" int vsb_gather_keypoints(vsb_ctx_t* ctx, const float* kp_xy, int n_max, const int32_t* good_idx,

@@ -14,6 +14,10 @@ int vsb_gn_solve_stats(vsb_ctx_t* ctx, const uint8_t* prev_pyr, const uint8_t* c
                        const float* pose_in, const vsb_gn_opts_t* opts, int count, float* pose_out,
                        vsb_gn_trace_t* trace, int32_t* n_trace, unsigned long long* stats, void* patt_scratch,
                        int patt_ready, void* stream);
+int vsb_match_filter_keys(vsb_ctx_t* ctx, const void* keys12, const void* keys21, int key_bytes, int n1_max,
+                          const int32_t* n1, int n2_max, const int32_t* n2, const float* kp1_xy, int count, int w, int h,
+                          int n_cells, float ratio, int sym_mode, int32_t* good_q, int32_t* good_t, float* good_d,
+                          int good_cap, int32_t* n_good, int32_t* n_sym, float* good_xy, void* stream);
 int vsb_candidates_prepare(vsb_ctx_t* ctx, const float* good_xy, int good_cap, const int32_t* n_good, int count, int levels,
                            const int* lw, const int* lh, float* cand, int cand_cap, int32_t* n_cand,
                            const uint8_t* prev_pyr, int64_t pair_stride, const vsb_pyr_layout_t* layout, int first_lvl,
@@ -39,10 +43,6 @@ struct Slot {
     float* prior = nullptr;       // [max_pairs][7]
     uint32_t* key12 = nullptr;
     uint32_t* key21 = nullptr;
-    int32_t* idx12 = nullptr;
-    int32_t* idx21 = nullptr;
-    float* dist12 = nullptr;
-    float* dist21 = nullptr;
     int32_t* good_q = nullptr;
     int32_t* good_t = nullptr;
     float* good_d = nullptr;
@@ -97,8 +97,6 @@ int slot_alloc(vsb_tracker* t, Slot& s) {
     A(prior, P * 7);
     const size_t kw = c.norm == 1 ? 1 : 2;   // L2 keys are 64-bit (float bits << 32 | index)
     A(key12, P * N * 2 * kw); A(key21, P * N * 2 * kw);
-    A(idx12, P * N * 2); A(idx21, P * N * 2);
-    A(dist12, P * N * 2); A(dist21, P * N * 2);
     A(good_q, P * t->good_cap); A(good_t, P * t->good_cap); A(good_d, P * t->good_cap);
     A(n_good, P); A(n_sym, P);
     A(good_xy, P * t->good_cap * 2);
@@ -113,8 +111,7 @@ int slot_alloc(vsb_tracker* t, Slot& s) {
 }
 
 void slot_free(Slot& s) {
-    void* ptrs[] = {s.pyr, s.gx, s.gy, s.desc, s.kp, s.n_feat, s.prior, s.key12, s.key21, s.idx12, s.idx21, s.dist12,
-                    s.dist21, s.good_q, s.good_t, s.good_d, s.n_good, s.n_sym, s.good_xy, s.cand, s.patt, s.n_cand, s.pose};
+    void* ptrs[] = {s.pyr, s.gx, s.gy, s.desc, s.kp, s.n_feat, s.prior, s.key12, s.key21, s.good_q, s.good_t, s.good_d, s.n_good, s.n_sym, s.good_xy, s.cand, s.patt, s.n_cand, s.pose};
     for (void* p : ptrs) if (p) cudaFree(p);
     if (s.stream) cudaStreamDestroy(s.stream);
     if (s.done) cudaEventDestroy(s.done);
@@ -130,11 +127,12 @@ int run_pairs(vsb_tracker* t, Slot& s, const uint8_t* pyr_prev, const uint8_t* p
     const vsb_tracker_cfg_t& c = t->cfg;
     const int N = c.n_feat_max;
     int rc;
+    // kNN (both directions) -> packed keys; the filter reads them in place and gathers the good key points itself
+    int key_bytes;
     if (c.norm == 1) {
         if (c.desc_bytes != 32) return VSB_ERR_UNSUPPORTED;
         if ((rc = vsb_knn2_hamming_keys(ctx, d1, N, n1, d2, N, n2, count, s.key12, s.key21, st))) return rc;
-        if ((rc = vsb_knn_unpack(ctx, s.key12, N, n1, count, s.idx12, s.dist12, st))) return rc;
-        if ((rc = vsb_knn_unpack(ctx, s.key21, N, n2, count, s.idx21, s.dist21, st))) return rc;
+        key_bytes = 4;
     } else {
         if (c.desc_bytes <= 0 || (c.desc_bytes & 3)) return VSB_ERR_INVALID;
         const int dim = c.desc_bytes / 4;
@@ -143,13 +141,11 @@ int run_pairs(vsb_tracker* t, Slot& s, const uint8_t* pyr_prev, const uint8_t* p
         if ((rc = vsb_knn2_l2_keys(ctx, reinterpret_cast<const float*>(d1), N, n1, reinterpret_cast<const float*>(d2), N,
                                    n2, dim, count, k12, k21, st)))
             return rc;
-        if ((rc = vsb_knn_unpack64(ctx, k12, N, n1, count, s.idx12, s.dist12, st))) return rc;
-        if ((rc = vsb_knn_unpack64(ctx, k21, N, n2, count, s.idx21, s.dist21, st))) return rc;
+        key_bytes = 8;
     }
-    if ((rc = vsb_match_filter(ctx, s.idx12, s.dist12, N, n1, s.idx21, s.dist21, N, n2, kp1, count, c.w, c.h, c.n_cells,
-                               c.ratio, c.sym_mode, s.good_q, s.good_t, s.good_d, t->good_cap, s.n_good, s.n_sym, st)))
+    if ((rc = vsb_match_filter_keys(ctx, s.key12, s.key21, key_bytes, N, n1, N, n2, kp1, count, c.w, c.h, c.n_cells, c.ratio,
+                                    c.sym_mode, s.good_q, s.good_t, s.good_d, t->good_cap, s.n_good, s.n_sym, s.good_xy, st)))
         return rc;
-    if ((rc = vsb_gather_keypoints(ctx, kp1, N, s.good_q, t->good_cap, s.n_good, count, s.good_xy, st))) return rc;
     // candidate points and — when the gradients are evaluated at the points (grad_mode 1) — the solver's per-point
     // attribute records in the same pass
     const int fused = c.gn.grad_mode == 1 ? 1 : 0;
