@@ -258,6 +258,10 @@ candidates_kernel(const float* __restrict__ good_xy, int good_cap, const int32_t
     const int prob = blockIdx.x;
     const int lvl = blockIdx.y;
     const int tid = threadIdx.x;
+    if (P.patt != nullptr && lvl > P.first_lvl) {           // fused (tracker) form: levels the solver never visits stay empty
+        if (tid == 0) n_cand[(size_t)prob * P.levels + lvl] = 0;
+        return;
+    }
     __shared__ int s_cnt[256], s_off[257];
     __shared__ int s_ia[256], s_ja[256], s_nj[256];
     const int patch_size[VSB_MAX_LEVELS] = {5, 3, 2, 5, 5};              // Camera.cpp:369-373
