@@ -35,6 +35,7 @@ struct GnParams {
     long long pair_stride;
     vsb_pyr_layout_t lay;
     const float4* cand;
+    const double2* xy;           // tracker form (optional): back-projected (X, Y) of unit-depth points, replaces cand (z = w = 1)
     uint2* patt;                 // [count][levels][cand_cap] {gx | gy << 16, I_prev}
     float* resid;                // [count][cand_cap] residual scratch of the Tukey pre-pass (weight_mode 1 only)
     int cand_cap;
@@ -278,7 +279,9 @@ constexpr int VROW = 36;   // staging row stride (floats): conflict-free for the
 // U = points per thread per batch; TPS = resident threads per SM the register budget is sized for
 // WM = weight mode (0 identity: the reference default, 1 Tukey, 2 Huber) at compile time: identity drops the seven
 // multiplications by w = 1 per point
-template <bool FP32_PARTIALS, int GT, int WM, int U = 2, int TPS = 768>
+// UNITZW: the points come as pre-back-projected doubles (X, Y) with z = w = 1 (the tracker's fused candidate pass): the
+// per-iteration back-projection, four conversions and the two multiplications by w vanish; same bits.
+template <bool FP32_PARTIALS, int GT, int WM, int U = 2, int TPS = 768, bool UNITZW = false>
 __global__ void __launch_bounds__(GT, (TPS / GT) > 0 ? (TPS / GT) : 1)
 gn_solve_kernel(const GnParams P) {
     constexpr int NW = GT / 32;
@@ -318,7 +321,8 @@ gn_solve_kernel(const GnParams P) {
         const int cols = P.lay.w[lvl], rows = P.lay.h[lvl];
         const uint8_t* __restrict__ image2 = cur_base + P.lay.offset[lvl];
         const size_t slot0 = ((size_t)prob * P.lay.levels + lvl) * P.cand_cap;
-        const float4* __restrict__ cand = P.cand + slot0;
+        const float4* __restrict__ cand = UNITZW ? nullptr : P.cand + slot0;
+        const double2* __restrict__ xyp = UNITZW ? P.xy + slot0 : nullptr;
         const uint2* __restrict__ patt = P.patt + slot0;
         const int ncand = min(P.n_cand[(size_t)prob * P.lay.levels + lvl], P.cand_cap);
         const float fx = P.K[lvl].fx, fy = P.K[lvl].fy, cx = P.K[lvl].cx, cy = P.K[lvl].cy;
@@ -357,12 +361,20 @@ gn_solve_kernel(const GnParams P) {
             for (int base = 0; base < ncand; base += GT * U) {                    // VISystem.cpp:1281-1338
                 // ---- phase 1: coalesced loads of U points per thread --------------------------------------
                 float4 c[U];
+                double2 pxy[U];
+                bool live[U];
                 uint2 at[U];
 #pragma unroll
                 for (int u = 0; u < U; u++) {
                     const int i = base + u * GT + tid;
-                    if (i < ncand) { c[u] = __ldg(cand + i); at[u] = __ldg(patt + i); }
-                    else { c[u] = make_float4(0.f, 0.f, 0.f, 0.f); at[u] = make_uint2(0u, 0u); }   // z = 0 => invalid
+                    live[u] = i < ncand;
+                    c[u] = make_float4(0.f, 0.f, 0.f, 0.f);                                        // z = 0 => invalid
+                    pxy[u] = make_double2(0.0, 0.0);
+                    at[u] = make_uint2(0u, 0u);
+                    if (live[u]) {
+                        if (UNITZW) pxy[u] = __ldg(xyp + i); else c[u] = __ldg(cand + i);
+                        at[u] = __ldg(patt + i);
+                    }
                 }
                 // ---- phase 2: warp (WarpFunctionSE3, :1519-1553), validity, address of the one gather ------
                 float x2[U], y2[U], iz[U];
@@ -370,17 +382,35 @@ gn_solve_kernel(const GnParams P) {
                 bool ok[U];
 #pragma unroll
                 for (int u = 0; u < U; u++) {
-                    const float X = F_MUL(F_MUL(F_SUB(c[u].x, cx), invfx), c[u].z);
-                    const float Y = F_MUL(F_MUL(F_SUB(c[u].y, cy), invfy), c[u].z);
-                    const double dX = X, dY = Y, dZ = c[u].z, dW = c[u].w;
-                    double s0 = md[0] * dX; s0 += md[1] * dY; s0 += md[2] * dZ; s0 += md[3] * dW;
-                    double s1 = md[4] * dX; s1 += md[5] * dY; s1 += md[6] * dZ; s1 += md[7] * dW;
-                    double s2 = md[8] * dX; s2 += md[9] * dY; s2 += md[10] * dZ; s2 += md[11] * dW;
-                    const float r0 = (float)s0, r1 = (float)s1, r2 = (float)s2, r3 = c[u].w;  // last row of T is (0,0,0,1)
-                    x2[u] = F_MUL(F_ADD(F_DIV(F_MUL(r0, fx), r2), cx), r3);
-                    y2[u] = F_MUL(F_ADD(F_DIV(F_MUL(r1, fy), r2), cy), r3);
+                    double s0, s1, s2;
+                    float r3;
+                    if (UNITZW) {
+                        // z = w = 1: m * 1.0 is m exactly, so the two last terms are plain additions; (...) * w is the identity
+                        const double dX = pxy[u].x, dY = pxy[u].y;
+                        s0 = md[0] * dX; s0 += md[1] * dY; s0 += md[2]; s0 += md[3];
+                        s1 = md[4] * dX; s1 += md[5] * dY; s1 += md[6]; s1 += md[7];
+                        s2 = md[8] * dX; s2 += md[9] * dY; s2 += md[10]; s2 += md[11];
+                        r3 = 1.f;
+                    } else {
+                        const float X = F_MUL(F_MUL(F_SUB(c[u].x, cx), invfx), c[u].z);
+                        const float Y = F_MUL(F_MUL(F_SUB(c[u].y, cy), invfy), c[u].z);
+                        const double dX = X, dY = Y, dZ = c[u].z, dW = c[u].w;
+                        s0 = md[0] * dX; s0 += md[1] * dY; s0 += md[2] * dZ; s0 += md[3] * dW;
+                        s1 = md[4] * dX; s1 += md[5] * dY; s1 += md[6] * dZ; s1 += md[7] * dW;
+                        s2 = md[8] * dX; s2 += md[9] * dY; s2 += md[10] * dZ; s2 += md[11] * dW;
+                        r3 = c[u].w;                                                               // last row of T is (0,0,0,1)
+                    }
+                    const float r0 = (float)s0, r1 = (float)s1, r2 = (float)s2;
+                    if (UNITZW) {
+                        x2[u] = F_ADD(F_DIV(F_MUL(r0, fx), r2), cx);
+                        y2[u] = F_ADD(F_DIV(F_MUL(r1, fy), r2), cy);
+                    } else {
+                        x2[u] = F_MUL(F_ADD(F_DIV(F_MUL(r0, fx), r2), cx), r3);
+                        y2[u] = F_MUL(F_ADD(F_DIV(F_MUL(r1, fy), r2), cy), r3);
+                    }
                     float izz = F_DIV(1.f, r2);
                     bool v = (y2[u] > 0.f && y2[u] < frows && x2[u] > 0.f && x2[u] < fcols) && (r2 != 0.f);  // :1299-1300
+                    if (UNITZW) v = v && live[u];
                     if (izz < 0.f) izz = 0.f;                                                            // :1301
                     iz[u] = izz;
                     int l = 0;
@@ -616,9 +646,12 @@ int vsb_gn_solve_stats(vsb_ctx_t* ctx, const uint8_t* prev_pyr, const uint8_t* c
                        const float* cand, int cand_cap, const int32_t* n_cand, const vsb_intr_t K[VSB_MAX_LEVELS],
                        const float* pose_in, const vsb_gn_opts_t* opts, int count, float* pose_out,
                        vsb_gn_trace_t* trace, int32_t* n_trace, unsigned long long* stats, void* patt_scratch,
-                       int patt_ready, void* stream) {
-    if (!ctx || !prev_pyr || !cur_pyr || !layout || !cand || !n_cand || !K || !pose_in || !opts || !pose_out)
+                       int patt_ready, const void* xy_ready, void* stream) {
+    // xy_ready (tracker): [count][levels][cand_cap] double2 (X, Y) of unit-depth points, written together with the
+    // attribute records by the fused candidate pass; `cand` may then be NULL
+    if (!ctx || !prev_pyr || !cur_pyr || !layout || (!cand && !xy_ready) || !n_cand || !K || !pose_in || !opts || !pose_out)
         return VSB_ERR_INVALID;
+    if (xy_ready && !(patt_ready && patt_scratch && opts->accum_mode == 0 && opts->weight_mode == 0)) return VSB_ERR_INVALID;
     if (count < 0 || cand_cap < 0) return VSB_ERR_INVALID;
     if (opts->first_lvl >= layout->levels || opts->last_lvl < 0 || opts->first_lvl < opts->last_lvl)
         return VSB_ERR_INVALID;
@@ -644,6 +677,7 @@ int vsb_gn_solve_stats(vsb_ctx_t* ctx, const uint8_t* prev_pyr, const uint8_t* c
     P.pair_stride = pair_stride_pixels;
     P.lay = *layout;
     P.cand = reinterpret_cast<const float4*>(cand);
+    P.xy = reinterpret_cast<const double2*>(xy_ready);
     P.patt = reinterpret_cast<uint2*>(patt_scratch);
     P.cand_cap = cand_cap;
     P.n_cand = n_cand;
@@ -685,7 +719,12 @@ int vsb_gn_solve_stats(vsb_ctx_t* ctx, const uint8_t* prev_pyr, const uint8_t* c
         else if (opts->weight_mode == 2) gn_solve_kernel<FP, T, 2><<<count, T, 0, st>>>(P); \
         else gn_solve_kernel<FP, T, 0><<<count, T, 0, st>>>(P);                          \
     } while (0)
-    if (ctx->gn_variant > 0 && opts->accum_mode == 0 && opts->weight_mode == 0 && gt_env == 128) {   // tuning experiments
+    if (xy_ready) {
+        if (gt_env >= 1024) gn_solve_kernel<false, 1024, 0, 1, 1024, true><<<count, 1024, 0, st>>>(P);
+        else if (gt_env >= 512) gn_solve_kernel<false, 512, 0, 2, 1024, true><<<count, 512, 0, st>>>(P);
+        else if (gt_env >= 256) gn_solve_kernel<false, 256, 0, 2, 768, true><<<count, 256, 0, st>>>(P);
+        else gn_solve_kernel<false, 128, 0, 2, 768, true><<<count, 128, 0, st>>>(P);
+    } else if (ctx->gn_variant > 0 && opts->accum_mode == 0 && opts->weight_mode == 0 && gt_env == 128) {   // tuning experiments
         switch (ctx->gn_variant) {    // (points per thread per batch, resident threads per SM the registers are sized for)
             case 1: gn_solve_kernel<false, 128, 0, 4, 768><<<count, 128, 0, st>>>(P); break;
             case 2: gn_solve_kernel<false, 128, 0, 2, 1024><<<count, 128, 0, st>>>(P); break;
@@ -717,5 +756,5 @@ extern "C" int vsb_gn_solve(vsb_ctx_t* ctx, const uint8_t* prev_pyr, const uint8
                             const float* pose_in, const vsb_gn_opts_t* opts, int count, float* pose_out,
                             vsb_gn_trace_t* trace, int32_t* n_trace, void* stream) {
     return vsb_gn_solve_stats(ctx, prev_pyr, cur_pyr, prev_gx, prev_gy, pair_stride_pixels, layout, cand, cand_cap,
-                              n_cand, K, pose_in, opts, count, pose_out, trace, n_trace, nullptr, nullptr, 0, stream);
+                              n_cand, K, pose_in, opts, count, pose_out, trace, n_trace, nullptr, nullptr, 0, nullptr, stream);
 }

@@ -250,6 +250,10 @@ struct CandParams {
     vsb_pyr_layout_t lay;
     int first_lvl, last_lvl;
     uint2* patt;
+    // ... and, instead of the float4 rows, the back-projected (X, Y) = ((x - cx) * invfx, (y - cy) * invfy) of the
+    // unit-depth points as doubles (VISystem.cpp:1519-1524 with z = 1), which is all the solver needs of a point
+    double2* xy;
+    float cx[VSB_MAX_LEVELS], cy[VSB_MAX_LEVELS], invfx[VSB_MAX_LEVELS], invfy[VSB_MAX_LEVELS];
 };
 
 __global__ void __launch_bounds__(256)
@@ -306,7 +310,13 @@ candidates_kernel(const float* __restrict__ good_xy, int good_cap, const int32_t
         for (int p = lane; p < c; p += 32) {
             if (off + p >= total) break;
             const int ii = p / nj, jj = p - ii * nj;
-            out[off + p] = make_float4((float)(ia + ii), (float)(ja + jj), 1.0f, 1.0f);
+            if (attrs && P.xy) {
+                const float X = __fmul_rn(__fsub_rn((float)(ia + ii), P.cx[lvl]), P.invfx[lvl]);   // * z (= 1) is the identity
+                const float Y = __fmul_rn(__fsub_rn((float)(ja + jj), P.cy[lvl]), P.invfy[lvl]);
+                P.xy[((size_t)prob * P.levels + lvl) * cand_cap + off + p] = make_double2((double)X, (double)Y);
+            } else {
+                out[off + p] = make_float4((float)(ia + ii), (float)(ja + jj), 1.0f, 1.0f);
+            }
             if (attrs) {
                 const int sx = min(max(ia + ii, 0), cols - 1), sy = min(max(ja + jj, 0), rows - 1);
                 const int xm = reflect101(sx - 1, cols), xp = reflect101(sx + 1, cols);
@@ -411,18 +421,23 @@ extern "C" int vsb_gradient_build(vsb_ctx_t* ctx, const uint8_t* pyr, int count,
 int vsb_candidates_prepare(vsb_ctx_t* ctx, const float* good_xy, int good_cap, const int32_t* n_good, int count, int levels,
                            const int* lw, const int* lh, float* cand, int cand_cap, int32_t* n_cand,
                            const uint8_t* prev_pyr, int64_t pair_stride, const vsb_pyr_layout_t* layout, int first_lvl,
-                           int last_lvl, void* patt, void* stream) {
+                           int last_lvl, void* patt, void* xy, const vsb_intr_t* K, void* stream) {
     if (!ctx || !good_xy || !n_good || !cand || !n_cand || !lw || !lh) return VSB_ERR_INVALID;
     if (levels < 1 || levels > VSB_MAX_LEVELS || count < 0 || cand_cap < 0) return VSB_ERR_INVALID;
     if (count == 0) return VSB_OK;
     CandParams P;
     P.levels = levels;
     for (int l = 0; l < levels; l++) { P.lw[l] = lw[l]; P.lh[l] = lh[l]; }
-    P.prev_pyr = nullptr; P.pair_stride = 0; P.first_lvl = -1; P.last_lvl = 0; P.patt = nullptr;
+    P.prev_pyr = nullptr; P.pair_stride = 0; P.first_lvl = -1; P.last_lvl = 0; P.patt = nullptr; P.xy = nullptr;
+    for (int l = 0; l < VSB_MAX_LEVELS; l++) { P.cx[l] = P.cy[l] = 0.f; P.invfx[l] = P.invfy[l] = 0.f; }
     memset(&P.lay, 0, sizeof(P.lay));
     if (prev_pyr && layout && patt) {
         P.prev_pyr = prev_pyr; P.pair_stride = pair_stride; P.lay = *layout;
         P.first_lvl = first_lvl; P.last_lvl = last_lvl; P.patt = reinterpret_cast<uint2*>(patt);
+        if (xy && K) {
+            P.xy = reinterpret_cast<double2*>(xy);
+            for (int l = 0; l < VSB_MAX_LEVELS; l++) { P.cx[l] = K[l].cx; P.cy[l] = K[l].cy; P.invfx[l] = K[l].invfx; P.invfy[l] = K[l].invfy; }
+        }
     }
     dim3 grid(count, levels);
     ProfScope ps(ctx, VSB_K_CANDIDATES, (cudaStream_t)stream);
@@ -436,6 +451,6 @@ extern "C" int vsb_candidates_build(vsb_ctx_t* ctx, const float* good_xy, int go
                                     int count, int levels, const int* lw, const int* lh, float* cand, int cand_cap,
                                     int32_t* n_cand, void* stream) {
     return vsb_candidates_prepare(ctx, good_xy, good_cap, n_good, count, levels, lw, lh, cand, cand_cap, n_cand, nullptr, 0,
-                                  nullptr, 0, 0, nullptr, stream);
+                                  nullptr, 0, 0, nullptr, nullptr, nullptr, stream);
 }
 

@@ -13,7 +13,7 @@ int vsb_gn_solve_stats(vsb_ctx_t* ctx, const uint8_t* prev_pyr, const uint8_t* c
                        const float* cand, int cand_cap, const int32_t* n_cand, const vsb_intr_t K[VSB_MAX_LEVELS],
                        const float* pose_in, const vsb_gn_opts_t* opts, int count, float* pose_out,
                        vsb_gn_trace_t* trace, int32_t* n_trace, unsigned long long* stats, void* patt_scratch,
-                       int patt_ready, void* stream);
+                       int patt_ready, const void* xy_ready, void* stream);
 int vsb_match_filter_keys(vsb_ctx_t* ctx, const void* keys12, const void* keys21, int key_bytes, int n1_max,
                           const int32_t* n1, int n2_max, const int32_t* n2, const float* kp1_xy, int count, int w, int h,
                           int n_cells, float ratio, int sym_mode, int32_t* good_q, int32_t* good_t, float* good_d,
@@ -21,7 +21,7 @@ int vsb_match_filter_keys(vsb_ctx_t* ctx, const void* keys12, const void* keys21
 int vsb_candidates_prepare(vsb_ctx_t* ctx, const float* good_xy, int good_cap, const int32_t* n_good, int count, int levels,
                            const int* lw, const int* lh, float* cand, int cand_cap, int32_t* n_cand,
                            const uint8_t* prev_pyr, int64_t pair_stride, const vsb_pyr_layout_t* layout, int first_lvl,
-                           int last_lvl, void* patt, void* stream);
+                           int last_lvl, void* patt, void* xy, const vsb_intr_t* K, void* stream);
 int vsb_knn_unpack(vsb_ctx* ctx, const uint32_t* keys, int n_max, const int32_t* n, int count, int32_t* idx,
                    float* dist, cudaStream_t st);
 int vsb_knn2_l2_keys(vsb_ctx* ctx, const float* d1, int n1_max, const int32_t* n1, const float* d2, int n2_max,
@@ -149,13 +149,17 @@ int run_pairs(vsb_tracker* t, Slot& s, const uint8_t* pyr_prev, const uint8_t* p
     // candidate points and — when the gradients are evaluated at the points (grad_mode 1) — the solver's per-point
     // attribute records in the same pass
     const int fused = c.gn.grad_mode == 1 ? 1 : 0;
+    // reference defaults (identity weights, FP64 Gram): the points are handed over already back-projected, as doubles,
+    // in the candidate buffer itself (a double2 is as wide as the float4 row it replaces)
+    const int unit = fused && c.gn.accum_mode == 0 && c.gn.weight_mode == 0;
     if ((rc = vsb_candidates_prepare(ctx, s.good_xy, t->good_cap, s.n_good, count, t->lay.levels, t->lw, t->lh, s.cand,
                                      t->cand_cap, s.n_cand, fused ? pyr_prev : nullptr, t->lay.frame_stride, &t->lay,
-                                     c.gn.first_lvl, c.gn.last_lvl, fused ? s.patt : nullptr, st)))
+                                     c.gn.first_lvl, c.gn.last_lvl, fused ? s.patt : nullptr, unit ? (void*)s.cand : nullptr,
+                                     t->K, st)))
         return rc;
-    if ((rc = vsb_gn_solve_stats(ctx, pyr_prev, pyr_cur, gx_prev, gy_prev, t->lay.frame_stride, &t->lay, s.cand,
-                                 t->cand_cap, s.n_cand, t->K, prior, &c.gn, count, pose_out, nullptr, nullptr, t->stats,
-                                 s.patt, fused, st)))
+    if ((rc = vsb_gn_solve_stats(ctx, pyr_prev, pyr_cur, gx_prev, gy_prev, t->lay.frame_stride, &t->lay,
+                                 unit ? nullptr : s.cand, t->cand_cap, s.n_cand, t->K, prior, &c.gn, count, pose_out, nullptr,
+                                 nullptr, t->stats, s.patt, fused, unit ? (const void*)s.cand : nullptr, st)))
         return rc;
     if (n_good_out)
         VSB_CUDA(ctx, cudaMemcpyAsync(n_good_out, s.n_good, sizeof(int32_t) * count, cudaMemcpyDeviceToDevice, st));
