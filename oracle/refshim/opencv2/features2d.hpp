@@ -1,0 +1,2 @@
+// oracle/refshim — see opencv2/core.hpp (TEST INFRASTRUCTURE ONLY)
+#include "core.hpp"

@@ -46,6 +46,7 @@ inline Bus& bus() { static Bus b; return b; }
 
 namespace ros {
 inline bool ok() { return true; }
+inline void init(int&, char**, const std::string&) {}   // VISystem(int, char**) (VISystem.cpp:15-17)
 struct WallDuration { explicit WallDuration(double) {} };
 struct Rate { explicit Rate(double) {} void sleep() {} };
 namespace names { inline std::string resolve(const std::string& n) { return "/" + n; } }
@@ -80,6 +81,12 @@ inline CallbackQueue* getGlobalCallbackQueue() { static CallbackQueue q; return 
 }  // namespace ros
 
 #define ROS_WARN_ONCE(...) do {} while (0)
+
+namespace std_msgs { struct Int32 { int data = 0; }; }
+namespace geometry_msgs {
+struct Vector3 { double x = 0, y = 0, z = 0; };
+struct Quaternion { double x = 0, y = 0, z = 0, w = 1; };
+}
 
 namespace message_filters {
 template <typename M>

@@ -195,9 +195,14 @@ void vso_initial_pose(const float imu2cam[9], const float r_imu_res[9], const fl
 
 /* ---------------------------------------------------------------- warp ---- */
 static inline void warp_point(const float* p, const float m[16], const vso_intr_t* K, float* o) {
-    /* VISystem.cpp:1519-1524: X = ((x - cx) * invfx) * z */
-    float X = ((p[0] - K->cx) * K->invfx) * p[2];
-    float Y = ((p[1] - K->cy) * K->invfy) * p[2];
+    /* VISystem.cpp:1519-1524: col = (col - cx) * invfx; col = col.mul(z).  cv::MatExpr folds "(A - s) * k" into ONE
+     * scaled conversion (matop.cpp MatOp_AddEx::multiply + assign -> A.convertTo(dst, type, alpha = k, beta = -s*k)),
+     * beta formed in double and rounded to float, the conversion evaluated in float as a*alpha + beta (cvtScale32f,
+     * multiply then add, not fused) — i.e. x*invfx - cx*invfx, NOT (x - cx)*invfx. */
+    float bx = (float)(-(double)K->cx * (double)K->invfx);
+    float by = (float)(-(double)K->cy * (double)K->invfy);
+    float X = (p[0] * K->invfx + bx) * p[2];
+    float Y = (p[1] * K->invfy + by) * p[2];
     float Z = p[2], W = p[3];
     /* :1536 rigid * pts.t()  — cv::gemm, double accumulation, one rounding to float */
     float r[4];
@@ -225,39 +230,57 @@ void vso_warp(const float* pts, int n, const float pose[7], const vso_intr_t* K,
 }
 
 /* ---------------------------------------------------------------- 6x6 inverse ---- */
-int vso_inv6(const float a[36], float out[36]) {
-    /* cv::invert(DECOMP_LU) n>3: copy, identity RHS, hal::LU32f; failure => zeros.  (VISystem.cpp:1412)
-     * Back-substitution divides by the pivot (s / A[ii]): bit-exact with cv2 4.13 (the only OpenCV that
-     * can be executed here); OpenCV 2.4-era sources multiplied by a stored reciprocal instead, which
-     * differs by <= 1 ulp per element — far inside the 1e-5 pose tolerance. */
+/* hal::LU32f (modules/core/src/lapack.cpp, LUImpl<float>): in-place LU with partial pivoting on [A | b], b has n columns.
+ * Back-substitution divides by the pivot (s / A[ii]): bit-exact with cv2 4.13 (the only OpenCV that can be executed
+ * here; tests/golden/inv6_cv2.npz, solve6_cv2.npz); OpenCV 3.2 multiplied by a stored reciprocal instead, which differs
+ * by <= 1 ulp per element — far inside the 1e-5 pose tolerance. */
+static int lu32f_6(float A[36], float* b, int n) {
     const int m = 6;
     const float eps = FLT_EPSILON * 10;
-    float A[36], b[36];
-    memcpy(A, a, sizeof(A));
-    for (int i = 0; i < 36; i++) b[i] = 0.f;
-    for (int i = 0; i < m; i++) b[i * m + i] = 1.f;
     for (int i = 0; i < m; i++) {
         int k = i;
         for (int j = i + 1; j < m; j++)
             if (fabsf(A[j * m + i]) > fabsf(A[k * m + i])) k = j;
-        if (fabsf(A[k * m + i]) < eps) { memset(out, 0, sizeof(float) * 36); return 0; }
+        if (fabsf(A[k * m + i]) < eps) return 0;
         if (k != i) {
             for (int j = i; j < m; j++) { float t = A[i * m + j]; A[i * m + j] = A[k * m + j]; A[k * m + j] = t; }
-            for (int j = 0; j < m; j++) { float t = b[i * m + j]; b[i * m + j] = b[k * m + j]; b[k * m + j] = t; }
+            for (int j = 0; j < n; j++) { float t = b[i * n + j]; b[i * n + j] = b[k * n + j]; b[k * n + j] = t; }
         }
         float d = -1 / A[i * m + i];
         for (int j = i + 1; j < m; j++) {
             float alpha = A[j * m + i] * d;
             for (k = i + 1; k < m; k++) A[j * m + k] += alpha * A[i * m + k];
-            for (k = 0; k < m; k++) b[j * m + k] += alpha * b[i * m + k];
+            for (k = 0; k < n; k++) b[j * n + k] += alpha * b[i * n + k];
         }
     }
     for (int i = m - 1; i >= 0; i--)
-        for (int j = 0; j < m; j++) {
-            float s = b[i * m + j];
-            for (int k = i + 1; k < m; k++) s -= A[i * m + k] * b[k * m + j];
-            b[i * m + j] = s / A[i * m + i];
+        for (int j = 0; j < n; j++) {
+            float s = b[i * n + j];
+            for (int k = i + 1; k < m; k++) s -= A[i * m + k] * b[k * n + j];
+            b[i * n + j] = s / A[i * m + i];
         }
+    return 1;
+}
+
+int vso_inv6(const float a[36], float out[36]) {
+    /* cv::invert(DECOMP_LU) n>3: copy, identity RHS, hal::LU32f; failure => zeros. */
+    float A[36], b[36];
+    memcpy(A, a, sizeof(A));
+    for (int i = 0; i < 36; i++) b[i] = 0.f;
+    for (int i = 0; i < 6; i++) b[i * 6 + i] = 1.f;
+    if (!lu32f_6(A, b, 6)) { memset(out, 0, sizeof(float) * 36); return 0; }
+    memcpy(out, b, sizeof(b));
+    return 1;
+}
+
+int vso_solve6(const float a[36], const float rhs[6], float out[6]) {
+    /* cv::solve(A, b, x, DECOMP_LU) n>3: copy A, x = b, hal::LU32f on [A | x]; failure => zeros.
+     * This is what `A.inv() * b` evaluates to (VISystem.cpp:1412): cv::MatExpr turns inverse-times-matrix into a solve
+     * (matop.cpp MatOp_Invert::matmul -> MatOp_Solve), it never forms the inverse. */
+    float A[36], b[6];
+    memcpy(A, a, sizeof(A));
+    memcpy(b, rhs, sizeof(b));
+    if (!lu32f_6(A, b, 1)) { memset(out, 0, sizeof(float) * 6); return 0; }
     memcpy(out, b, sizeof(b));
     return 1;
 }
@@ -304,6 +327,8 @@ static void tukey_weights(const float* r, int n, float* w) {
         }
     }
 }
+
+void vso_tukey_weights(const float* r, int n, float* w) { tukey_weights(r, n, w); }
 
 /* ---------------------------------------------------------------- GN ---- */
 static inline int round_half_away_pos(float v) {
@@ -434,15 +459,10 @@ int vso_gn_solve(const vso_gn_frames_t* f, const vso_intr_t K[VSO_MAX_LEVELS], c
                     bd[a] += (double)jw[a] * (double)rw;
                 }
             }
-            float A[36], b[6], Ainv[36], delta[6];
+            float A[36], b[6], delta[6];
             for (int i = 0; i < 36; i++) A[i] = (float)Ad[i];
             for (int i = 0; i < 6; i++) b[i] = (float)(-1.0 * bd[i]);
-            vso_inv6(A, Ainv);                                              /* :1412 */
-            for (int a = 0; a < 6; a++) {
-                double s = 0.0;
-                for (int c = 0; c < 6; c++) s += (double)Ainv[6 * a + c] * (double)b[c];
-                delta[a] = (float)s;
-            }
+            vso_solve6(A, b, delta);                                        /* :1412  A.inv() * b == cv::solve(A, b) */
             float e[7], np[7];
             vso_se3_exp(delta, e);
             vso_se3_mul(pose, e, np);                                       /* :1421 */

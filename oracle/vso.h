@@ -110,6 +110,8 @@ void vso_warp(const float* pts, int n, const float pose[7], const vso_intr_t* K,
 
 /* 6x6 float inverse as cv::Mat::inv() (DECOMP_LU) does it: returns 0 and zeros when singular. */
 int vso_inv6(const float a[36], float out[36]);
+void vso_tukey_weights(const float* r, int n, float* w);         /* VISystem.cpp:1797-1870 */
+int vso_solve6(const float a[36], const float rhs[6], float out[6]); /* cv::solve(DECOMP_LU): what A.inv() * b evaluates to */
 
 typedef struct {
     int first_lvl;      /* 3   VISystem.cpp:1119 */

@@ -98,6 +98,9 @@ def lib():
     L.vso_warp.argtypes = [_f32p, C.c_int, _f32p, C.POINTER(Intr), _f32p]
     L.vso_inv6.argtypes = [_f32p, _f32p]
     L.vso_inv6.restype = C.c_int
+    L.vso_solve6.argtypes = [_f32p, _f32p, _f32p]
+    L.vso_solve6.restype = C.c_int
+    L.vso_tukey_weights.argtypes = [_f32p, C.c_int, _f32p]
     L.vso_gn_solve.argtypes = [C.POINTER(GnFrames), C.POINTER(Intr), _f32p, C.POINTER(GnOpts), _f32p,
                                C.POINTER(GnTrace), C.c_int]
     L.vso_gn_solve.restype = C.c_int
@@ -278,6 +281,20 @@ def inv6(a):
     out = np.zeros(36, np.float32)
     ok = lib().vso_inv6(np.ascontiguousarray(a, np.float32).reshape(-1), out)
     return ok, out.reshape(6, 6)
+
+
+def solve6(a, b):
+    """cv::solve(A, b, DECOMP_LU) — what `A.inv() * b` evaluates to (VISystem.cpp:1412)."""
+    out = np.zeros(6, np.float32)
+    ok = lib().vso_solve6(np.ascontiguousarray(a, np.float32).reshape(-1), np.ascontiguousarray(b, np.float32).reshape(-1), out)
+    return ok, out
+
+
+def tukey_weights(r):
+    r = np.ascontiguousarray(r, np.float32).reshape(-1)
+    out = np.zeros_like(r)
+    lib().vso_tukey_weights(r, r.size, out)
+    return out
 
 
 def gn_solve(prev_pyr, cur_pyr, prev_gx, prev_gy, cands, K, pose_in, opts=None):

@@ -18,7 +18,7 @@
 // reproduced with exact float*float products summed in FP64.  The reduction order is fixed (batch order, DMMA k
 // order, warp order), so results are run-to-run deterministic and independent of the grid.
 // accum_mode 1 sums a thread's products in FP32 (FMA) and only the cross-thread part in FP64 (north-star
-// wording).  The 6x6 system is solved by warp 0 with OpenCV's LU elimination order, one matrix column per lane.
+// wording).  The 6x6 system is solved by warp 0 with OpenCV's LU elimination order (cv::solve), one column of [A | b] per lane.
 #include "common.cuh"
 #include "se3.cuh"
 #include <stdlib.h>
@@ -115,9 +115,10 @@ __device__ __forceinline__ void dmma_8x8x4(double& c0, double& c1, double a, dou
 }
 
 // ---- 6x6 solve by one warp -----------------------------------------------------------------------------
-// cv::Mat::inv() (DECOMP_LU -> hal::LU32f on [A | I]) followed by delta = Ainv * b (cv::gemm), VISystem.cpp:1412.
-// Lane c < 12 owns column c of the augmented matrix; every arithmetic operation is the one LU32f performs on
-// that element, in the same order, so the result is bit-identical to the sequential code in se3.cuh / the oracle.
+// deltaMat = A.inv() * b (VISystem.cpp:1412).  cv::MatExpr never forms the inverse here: inverse-times-matrix is turned
+// into cv::solve(A, b, DECOMP_LU) (matop.cpp MatOp_Invert::matmul -> MatOp_Solve), i.e. hal::LU32f on [A | b] with ONE
+// right-hand column.  Lane c < 6 owns column c of A, lane 6 owns b; every arithmetic operation is the one LU32f performs
+// on that element, in the same order, so the result is bit-identical to the sequential code in the oracle (vso_solve6).
 // G is the 8x8 Gram matrix of V = (J0..J5, r*w, r): A = G[0..5][0..5], J^T(r w) = G[a][6], sum r (r w) = G[7][6].
 __device__ __forceinline__ void warp_solve6(const double* G, int lane, float delta[6]) {
     const unsigned FULL = 0xffffffffu;
@@ -126,7 +127,7 @@ __device__ __forceinline__ void warp_solve6(const double* G, int lane, float del
     for (int r = 0; r < 6; r++) {
         float x = 0.f;
         if (lane < 6) x = (float)G[r * 8 + lane];                 // A = J^T J rounded once to float (:1408)
-        else if (lane < 12) x = (lane - 6 == r) ? 1.f : 0.f;
+        else if (lane == 6) x = (float)(-1.0 * G[r * 8 + 6]);     // b = -J^T (r w): gemm alpha = -1, rounded once (:1409)
         v[r] = x;
     }
     const float eps = 1.1920929e-07f * 10;
@@ -167,15 +168,10 @@ __device__ __forceinline__ void warp_solve6(const double* G, int lane, float del
         const float diag = __shfl_sync(FULL, v[i], i);
         x[i] = F_DIV(s, diag);
     }
-    const int jcol = lane - 6;
-    const float bj = (lane >= 6 && lane < 12) ? (float)(-1.0 * G[jcol * 8 + 6]) : 0.f;   // b = -J^T (r w), :1409
 #pragma unroll
     for (int a = 0; a < 6; a++) {
-        const double p = singular ? 0.0 : (double)x[a] * (double)bj;   // singular => inverse is all zeros => delta = 0
-        double s = 0.0;
-#pragma unroll
-        for (int j = 0; j < 6; j++) s += __shfl_sync(FULL, p, 6 + j);
-        delta[a] = (float)s;
+        const float xa = __shfl_sync(FULL, x[a], 6);               // the solution is lane 6's column
+        delta[a] = singular ? 0.f : xa;                            // singular => cv::solve zeroes the result => delta = 0
     }
 }
 
@@ -185,14 +181,14 @@ __device__ __forceinline__ void warp_solve6(const double* G, int lane, float del
 // So the iteration gets a pre-pass: residuals -> histogram -> median -> histogram of |r - median| -> MAD.  The residual
 // arithmetic below is the same sequence of rounded operations as the main loop's (warp :1519-1553, round() :1321).
 struct LvlConst {
-    float fx, fy, cx, cy, invfx, invfy, frows, fcols;
+    float fx, fy, cx, cy, invfx, invfy, bx, by, frows, fcols;
     int cols, rows, npix;
 };
 
 __device__ __forceinline__ bool point_residual(const float4 c, uint32_t i_prev, const double* md, const LvlConst& L,
                                                const uint8_t* __restrict__ image2, int sample_mode, float& res) {
-    const float X = F_MUL(F_MUL(F_SUB(c.x, L.cx), L.invfx), c.z);
-    const float Y = F_MUL(F_MUL(F_SUB(c.y, L.cy), L.invfy), c.z);
+    const float X = F_MUL(F_ADD(F_MUL(c.x, L.invfx), L.bx), c.z);      // folded conversion, see se3.cuh backproj_offset
+    const float Y = F_MUL(F_ADD(F_MUL(c.y, L.invfy), L.by), c.z);
     const double dX = X, dY = Y, dZ = c.z, dW = c.w;
     double s0 = md[0] * dX; s0 += md[1] * dY; s0 += md[2] * dZ; s0 += md[3] * dW;
     double s1 = md[4] * dX; s1 += md[5] * dY; s1 += md[6] * dZ; s1 += md[7] * dW;
@@ -327,6 +323,7 @@ gn_solve_kernel(const GnParams P) {
         const int ncand = min(P.n_cand[(size_t)prob * P.lay.levels + lvl], P.cand_cap);
         const float fx = P.K[lvl].fx, fy = P.K[lvl].fy, cx = P.K[lvl].cx, cy = P.K[lvl].cy;
         const float invfx = P.K[lvl].invfx, invfy = P.K[lvl].invfy;
+        const float bpx = vsb::backproj_offset(cx, invfx), bpy = vsb::backproj_offset(cy, invfy);
         const float zf = o.z_factor;
         const float frows = (float)rows, fcols = (float)cols;
         const int npix = rows * cols;
@@ -342,7 +339,7 @@ gn_solve_kernel(const GnParams P) {
             float tk_inv_mad = 1.f;
             if (TUKEY) {
                 LvlConst L;
-                L.fx = fx; L.fy = fy; L.cx = cx; L.cy = cy; L.invfx = invfx; L.invfy = invfy;
+                L.fx = fx; L.fy = fy; L.cx = cx; L.cy = cy; L.invfx = invfx; L.invfy = invfy; L.bx = bpx; L.by = bpy;
                 L.frows = frows; L.fcols = fcols; L.cols = cols; L.rows = rows; L.npix = npix;
                 tk_inv_mad = tukey_inv_mad(cand, patt, P.resid + (size_t)prob * P.cand_cap, ncand, s_md, L, image2,
                                            o.sample_mode, s_hist, s_tk);
@@ -392,8 +389,8 @@ gn_solve_kernel(const GnParams P) {
                         s2 = md[8] * dX; s2 += md[9] * dY; s2 += md[10]; s2 += md[11];
                         r3 = 1.f;
                     } else {
-                        const float X = F_MUL(F_MUL(F_SUB(c[u].x, cx), invfx), c[u].z);
-                        const float Y = F_MUL(F_MUL(F_SUB(c[u].y, cy), invfy), c[u].z);
+                        const float X = F_MUL(F_ADD(F_MUL(c[u].x, invfx), bpx), c[u].z);
+                        const float Y = F_MUL(F_ADD(F_MUL(c[u].y, invfy), bpy), c[u].z);
                         const double dX = X, dY = Y, dZ = c[u].z, dW = c[u].w;
                         s0 = md[0] * dX; s0 += md[1] * dY; s0 += md[2] * dZ; s0 += md[3] * dW;
                         s1 = md[4] * dX; s1 += md[5] * dY; s1 += md[6] * dZ; s1 += md[7] * dW;

@@ -109,7 +109,7 @@ extern "C" int vsb_se3_matrix(const float pose[7], float m[16]) {
 namespace {
 struct WarpParams {
     double m[16];
-    float fx, fy, cx, cy, invfx, invfy;
+    float fx, fy, cx, cy, invfx, invfy, bx, by;
 };
 
 __global__ void __launch_bounds__(256) warp_se3_kernel(const float4* __restrict__ pts, int n, WarpParams P,
@@ -117,8 +117,8 @@ __global__ void __launch_bounds__(256) warp_se3_kernel(const float4* __restrict_
     const int i = blockIdx.x * 256 + threadIdx.x;
     if (i >= n) return;
     const float4 p = pts[i];
-    const float X = F_MUL(F_MUL(F_SUB(p.x, P.cx), P.invfx), p.z);               // VISystem.cpp:1519-1524
-    const float Y = F_MUL(F_MUL(F_SUB(p.y, P.cy), P.invfy), p.z);
+    const float X = F_MUL(F_ADD(F_MUL(p.x, P.invfx), P.bx), p.z);               // VISystem.cpp:1519-1524 (folded, se3.cuh)
+    const float Y = F_MUL(F_ADD(F_MUL(p.y, P.invfy), P.by), p.z);
     float r[4];
 #pragma unroll
     for (int k = 0; k < 4; k++) {                                               // :1536 cv::gemm, double accumulate
@@ -144,6 +144,7 @@ extern "C" int vsb_warp_se3(vsb_ctx_t* ctx, const float* pts, int n, const float
     for (int i = 0; i < 12; i++) P.m[i] = (double)m34[i];
     P.m[12] = 0.0; P.m[13] = 0.0; P.m[14] = 0.0; P.m[15] = 1.0;
     P.fx = K->fx; P.fy = K->fy; P.cx = K->cx; P.cy = K->cy; P.invfx = K->invfx; P.invfy = K->invfy;
+    P.bx = vsb::backproj_offset(K->cx, K->invfx); P.by = vsb::backproj_offset(K->cy, K->invfy);
     ProfScope ps(ctx, VSB_K_WARP, (cudaStream_t)stream);
     warp_se3_kernel<<<vsb_div_up(n, 256), 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const float4*>(pts), n, P,
                                                                            reinterpret_cast<float4*>(out));

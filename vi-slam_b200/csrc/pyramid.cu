@@ -3,6 +3,7 @@
 // Camera::ObtainPatchesPointsPreviousFrame (:358-409).  All integer-exact, so results are bit-identical
 // to cv::resize(0.5) / cv::Scharr(scale 3) (checked against cv2 through the oracle).
 #include "common.cuh"
+#include "se3.cuh"
 
 namespace {
 
@@ -250,10 +251,11 @@ struct CandParams {
     vsb_pyr_layout_t lay;
     int first_lvl, last_lvl;
     uint2* patt;
-    // ... and, instead of the float4 rows, the back-projected (X, Y) = ((x - cx) * invfx, (y - cy) * invfy) of the
-    // unit-depth points as doubles (VISystem.cpp:1519-1524 with z = 1), which is all the solver needs of a point
+    // ... and, instead of the float4 rows, the back-projected (X, Y) = (x * invfx + bx, y * invfy + by) of the unit-depth
+    // points as doubles (VISystem.cpp:1519-1524 with z = 1; bx = backproj_offset(cx, invfx), see se3.cuh), which is all the
+    // solver needs of a point
     double2* xy;
-    float cx[VSB_MAX_LEVELS], cy[VSB_MAX_LEVELS], invfx[VSB_MAX_LEVELS], invfy[VSB_MAX_LEVELS];
+    float bx[VSB_MAX_LEVELS], by[VSB_MAX_LEVELS], invfx[VSB_MAX_LEVELS], invfy[VSB_MAX_LEVELS];
 };
 
 __global__ void __launch_bounds__(256)
@@ -311,8 +313,8 @@ candidates_kernel(const float* __restrict__ good_xy, int good_cap, const int32_t
             if (off + p >= total) break;
             const int ii = p / nj, jj = p - ii * nj;
             if (attrs && P.xy) {
-                const float X = __fmul_rn(__fsub_rn((float)(ia + ii), P.cx[lvl]), P.invfx[lvl]);   // * z (= 1) is the identity
-                const float Y = __fmul_rn(__fsub_rn((float)(ja + jj), P.cy[lvl]), P.invfy[lvl]);
+                const float X = __fadd_rn(__fmul_rn((float)(ia + ii), P.invfx[lvl]), P.bx[lvl]);   // * z (= 1) is the identity
+                const float Y = __fadd_rn(__fmul_rn((float)(ja + jj), P.invfy[lvl]), P.by[lvl]);
                 P.xy[((size_t)prob * P.levels + lvl) * cand_cap + off + p] = make_double2((double)X, (double)Y);
             } else {
                 out[off + p] = make_float4((float)(ia + ii), (float)(ja + jj), 1.0f, 1.0f);
@@ -429,14 +431,17 @@ int vsb_candidates_prepare(vsb_ctx_t* ctx, const float* good_xy, int good_cap, c
     P.levels = levels;
     for (int l = 0; l < levels; l++) { P.lw[l] = lw[l]; P.lh[l] = lh[l]; }
     P.prev_pyr = nullptr; P.pair_stride = 0; P.first_lvl = -1; P.last_lvl = 0; P.patt = nullptr; P.xy = nullptr;
-    for (int l = 0; l < VSB_MAX_LEVELS; l++) { P.cx[l] = P.cy[l] = 0.f; P.invfx[l] = P.invfy[l] = 0.f; }
+    for (int l = 0; l < VSB_MAX_LEVELS; l++) { P.bx[l] = P.by[l] = 0.f; P.invfx[l] = P.invfy[l] = 0.f; }
     memset(&P.lay, 0, sizeof(P.lay));
     if (prev_pyr && layout && patt) {
         P.prev_pyr = prev_pyr; P.pair_stride = pair_stride; P.lay = *layout;
         P.first_lvl = first_lvl; P.last_lvl = last_lvl; P.patt = reinterpret_cast<uint2*>(patt);
         if (xy && K) {
             P.xy = reinterpret_cast<double2*>(xy);
-            for (int l = 0; l < VSB_MAX_LEVELS; l++) { P.cx[l] = K[l].cx; P.cy[l] = K[l].cy; P.invfx[l] = K[l].invfx; P.invfy[l] = K[l].invfy; }
+            for (int l = 0; l < VSB_MAX_LEVELS; l++) {
+                P.bx[l] = vsb::backproj_offset(K[l].cx, K[l].invfx); P.by[l] = vsb::backproj_offset(K[l].cy, K[l].invfy);
+                P.invfx[l] = K[l].invfx; P.invfy[l] = K[l].invfy;
+            }
         }
     }
     dim3 grid(count, levels);

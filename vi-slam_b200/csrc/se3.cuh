@@ -131,6 +131,11 @@ VSB_HD void se3_mul(const float* a, const float* b, float* out) {
     out[4] = tx; out[5] = ty; out[6] = tz;
 }
 
+// VISystem.cpp:1519-1524 writes col = (col - c) * invf; cv::MatExpr folds "(A - s) * k" into ONE scaled conversion
+// A.convertTo(dst, type, alpha = k, beta = -s*k): beta is formed in double and rounded to float, the conversion is
+// a*alpha + beta in float (multiply, then add; not fused).  So X = x*invf + backproj_offset(c, invf), not (x - c)*invf.
+VSB_HD float backproj_offset(float c, float invf) { return (float)(-(double)c * (double)invf); }
+
 // 6x6 float inverse, OpenCV hal::LU32f semantics (partial pivoting, eps = 10*FLT_EPSILON, zeros when singular)
 VSB_HD int inv6(const float* a, float* out) {
     const int m = 6;
