@@ -7,16 +7,21 @@
  * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may
  * load it.  The product (libvislam_b200.so) never links, loads or calls anything in oracle/.
  *
- * PARITY STATUS: **parity unpinned by the reference** — MecatronicaUSB/vi-slam ships no tests,
- * golden vectors or fixtures, and its sources need OpenCV 3.2 + contrib, ROS Kinetic, Eigen and
- * ceres, none of which exist here.  What IS pinned:
- *   - the third-party primitives the reference calls (BFMatcher::knnMatch, resize(0.5), Scharr
- *     scale 3, addWeighted, invert) are checked against Python cv2 4.13 (tests/test_oracle_cv2.py,
- *     fixtures in tests/golden/ made by tests/golden/make_golden.py);
- *   - the Matcher filter chain (nnFilter / computeSymMatches / sortMatches / bestMatchesFilter /
- *     getGoodMatches) is checked against the reference's OWN src/Matcher.cpp compiled unmodified
- *     against a minimal OpenCV type shim (oracle/_ref, recipe oracle/Makefile target `ref`).
- * The GN solver (VISystem.cpp) cannot be compiled and is restated from the source text.
+ * PARITY STATUS: **pinned by the reference's own sources run here** (oracle/_ref, recipe: oracle/Makefile target `ref`).
+ * MecatronicaUSB/vi-slam ships no tests, golden vectors or fixtures, and its build needs OpenCV 3.2 + contrib, ROS
+ * Kinetic, Eigen and ceres, none of which exist here.  Its translation units for this path are therefore
+ * compiled UNMODIFIED, in place, against stand-in headers written for the purpose:
+ *   - src/Matcher.cpp against the type shim oracle/cvshim -> nnFilter / computeSymMatches / sortMatches /
+ *     bestMatchesFilter / getGoodMatches (tests/golden/matcher_ref.npz);
+ *   - src/VISystem.cpp + Camera.cpp (+ CameraModel, Matcher, Plus, Imu) against the functional OpenCV stand-in
+ *     oracle/refshim -> Camera::Update / computeGradient / computeGoodMatches / ObtainPatchesPointsPreviousFrame,
+ *     VISystem::InitializePyramid / WarpFunctionSE3 / EstimatePoseFeatures / TukeyFunctionWeights
+ *     (tests/golden/visystem_ref.npz, tests/test_ref_visystem.py: bit for bit, also live on full-size pairs);
+ *   - the third-party primitives the stand-ins restate (BFMatcher::knnMatch, resize(0.5), Scharr scale 3, addWeighted,
+ *     invert, solve) are checked against Python cv2 4.13 (tests/test_oracle_cv2.py, tests/golden/*_cv2.npz).
+ * NOT pinned by the reference: the Sophus SE3 exp / compose arithmetic (vendored Sophus needs Eigen; restated here from
+ * se3.hpp / so3.hpp and checked against scipy) and OpenCV's float convertTo / MatExpr folding rules (restated from
+ * OpenCV 3.2's matop.cpp / convert.cpp; cv2's Python API does not expose them).
  *
  * All citations are file:line under /root/reference.
  */
