@@ -18,7 +18,7 @@
  *     VISystem::InitializePyramid / WarpFunctionSE3 / EstimatePoseFeatures / TukeyFunctionWeights
  *     (tests/golden/visystem_ref.npz, tests/test_ref_visystem.py: bit for bit, also live on full-size pairs);
  *   - the third-party primitives the stand-ins restate (BFMatcher::knnMatch, resize(0.5), Scharr scale 3, addWeighted,
- *     invert, solve) are checked against Python cv2 4.13 (tests/test_oracle_cv2.py, tests/golden/*_cv2.npz).
+ *     invert, solve) are checked against Python cv2 4.13 (tests/test_oracle_cv2.py, the _cv2.npz fixtures in tests/golden).
  * NOT pinned by the reference: the Sophus SE3 exp / compose arithmetic (vendored Sophus needs Eigen; restated here from
  * se3.hpp / so3.hpp and checked against scipy) and OpenCV's float convertTo / MatExpr folding rules (restated from
  * OpenCV 3.2's matop.cpp / convert.cpp; cv2's Python API does not expose them).
