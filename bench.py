@@ -369,6 +369,13 @@ def run_gpu(args, rank, world, local_rank):
             ent.update({"bound": bound, "achieved": ach, "peak": peak, "unit": unit, "frac": ach / peak,
                         "peak_source": src, "traffic": traffic.get(name),
                         "algorithmic_per_launch": work / max(1, n)})
+            if name == "knn2_hamming" and knn_impl != 0:
+                # SURVEY 8(d) bounds the Hamming kNN by the INT pipe: 8*N*M 32-bit POPC per frame pair (one distance
+                # matrix).  The tcgen05 kernel does no POPC at all; this is the same work expressed against that ceiling.
+                popc_equiv = 8.0 * N_FEAT * N_FEAT * pairs_total / (kms * 1e-3) / 1e9
+                ent["survey_8d_int_pipe"] = {"bound": "int", "achieved": popc_equiv, "peak": popc_peak, "unit": "GPOPC/s",
+                                             "frac": popc_equiv / popc_peak,
+                                             "peak_source": "measured by vsb_popc_peak on this GPU"}
             if name == "gn_solve":
                 ent["note"] = ("bound as SURVEY 8(d) defines it (algorithmic bytes over HBM peak); ncu shows the kernel "
                                "limited by the XU pipe (FP32<->FP64 conversions, 57 %) and instruction issue (59 %), "
