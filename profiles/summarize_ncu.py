@@ -67,9 +67,20 @@ def full(path):
     print(f"# ncu --set full ({path}): selected raw metrics per captured launch")
     for r in rows[2:]:
         print("\n== " + r[kn].split("(")[0].replace("<unnamed>::", "").replace("void ", ""))
-        for w in WANT:
+        extra = [h for h in hdr if h not in WANT and (h.startswith("smsp__average_warps_issue_stalled") and h.endswith("per_issue_active.ratio")
+                                                     or h.startswith("sm__pipe_tensor") and h.endswith("pct_of_peak_sustained_active")
+                                                     or h in ("smsp__issue_active.avg.pct_of_peak_sustained_active",
+                                                              "sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active",
+                                                              "sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active",
+                                                              "sm__mem_tensor_cycles_active.avg.pct_of_peak_sustained_active",
+                                                              "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed",
+                                                              "l1tex__data_pipe_tc_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed",
+                                                              "lts__t_sector_hit_rate.pct"))]
+        for w in WANT + extra:
             if w in hdr:
                 i = hdr.index(w)
+                if w in extra and r[i] in ("", "0", "0.0"):
+                    continue
                 print(f"  {w:70s} {r[i]:>16s} {units[i]}")
 
 
