@@ -167,4 +167,14 @@ typedef struct {
 int vso_fast9(const uint8_t* img, int w, int h, int pitch, int threshold, int nonmax, int32_t* out_xy, int32_t* out_score,
               int cap);
 
+/* cv::ORB, one pyramid level (oracle/orb.c; pinned against cv2 4.13): the stages and the whole detectAndCompute */
+void vso_orb_harris(const uint8_t* img, int w, int h, int pitch, const int32_t* xy, int n, float* resp);
+void vso_orb_ic_angle(const uint8_t* img, int w, int h, int pitch, const int32_t* xy, int n, float* angle_deg);
+void vso_orb_gauss_kernel(float k[7]);
+void vso_orb_blur(const uint8_t* img, int w, int h, int pitch, uint8_t* out);
+void vso_orb_describe(const uint8_t* blurred, int w, int h, int pitch, const int32_t* xy, const float* angle_deg, int n,
+                      uint8_t* desc);
+int vso_orb_detect_compute(const uint8_t* img, int w, int h, int pitch, int nfeatures, int fast_threshold, int32_t* out_xy,
+                           float* out_resp, float* out_angle, uint8_t* out_desc, int cap);
+
 #endif

@@ -106,6 +106,13 @@ def lib():
     L.vso_gn_solve.restype = C.c_int
     L.vso_fast9.argtypes = [_u8p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _i32p, _i32p, C.c_int]
     L.vso_fast9.restype = C.c_int
+    L.vso_orb_harris.argtypes = [_u8p, C.c_int, C.c_int, C.c_int, _i32p, C.c_int, _f32p]
+    L.vso_orb_ic_angle.argtypes = [_u8p, C.c_int, C.c_int, C.c_int, _i32p, C.c_int, _f32p]
+    L.vso_orb_gauss_kernel.argtypes = [_f32p]
+    L.vso_orb_blur.argtypes = [_u8p, C.c_int, C.c_int, C.c_int, _u8p]
+    L.vso_orb_describe.argtypes = [_u8p, C.c_int, C.c_int, C.c_int, _i32p, _f32p, C.c_int, _u8p]
+    L.vso_orb_detect_compute.argtypes = [_u8p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _i32p, _f32p, _f32p, _u8p, C.c_int]
+    L.vso_orb_detect_compute.restype = C.c_int
     _lib = L
     return L
 
@@ -226,6 +233,58 @@ def fast9(img, threshold=20, nonmax=True, cap=None):
     n = lib().vso_fast9(img, w, h, w, int(threshold), int(bool(nonmax)), xy, sc, cap)
     n = min(n, cap)
     return xy[:n].copy(), sc[:n].copy()
+
+
+def orb_harris(img, xy):
+    img = np.ascontiguousarray(img, np.uint8)
+    xy = np.ascontiguousarray(xy, np.int32).reshape(-1, 2)
+    out = np.zeros(xy.shape[0], np.float32)
+    lib().vso_orb_harris(img, img.shape[1], img.shape[0], img.shape[1], xy, xy.shape[0], out)
+    return out
+
+
+def orb_ic_angle(img, xy):
+    img = np.ascontiguousarray(img, np.uint8)
+    xy = np.ascontiguousarray(xy, np.int32).reshape(-1, 2)
+    out = np.zeros(xy.shape[0], np.float32)
+    lib().vso_orb_ic_angle(img, img.shape[1], img.shape[0], img.shape[1], xy, xy.shape[0], out)
+    return out
+
+
+def orb_gauss_kernel():
+    k = np.zeros(7, np.float32)
+    lib().vso_orb_gauss_kernel(k)
+    return k
+
+
+def orb_blur(img):
+    img = np.ascontiguousarray(img, np.uint8)
+    out = np.zeros_like(img)
+    lib().vso_orb_blur(img, img.shape[1], img.shape[0], img.shape[1], out)
+    return out
+
+
+def orb_describe(blurred, xy, angle_deg):
+    blurred = np.ascontiguousarray(blurred, np.uint8)
+    xy = np.ascontiguousarray(xy, np.int32).reshape(-1, 2)
+    ang = np.ascontiguousarray(angle_deg, np.float32)
+    out = np.zeros((xy.shape[0], 32), np.uint8)
+    lib().vso_orb_describe(blurred, blurred.shape[1], blurred.shape[0], blurred.shape[1], xy, ang, xy.shape[0], out)
+    return out
+
+
+def orb_detect_compute(img, nfeatures=500, fast_threshold=20, cap=None):
+    """cv::ORB (nlevels = 1) detectAndCompute: (xy [n,2] int32, response, angle_deg, desc [n,32]) in row-major order."""
+    img = np.ascontiguousarray(img, np.uint8)
+    h, w = img.shape
+    cap = cap or (w * h // 4 + 16)
+    xy = np.zeros((cap, 2), np.int32)
+    resp = np.zeros(cap, np.float32)
+    ang = np.zeros(cap, np.float32)
+    desc = np.zeros((cap, 32), np.uint8)
+    n = lib().vso_orb_detect_compute(img, w, h, w, int(nfeatures), int(fast_threshold), xy, resp, ang, desc, cap)
+    n = min(n, cap)
+    return xy[:n].copy(), resp[:n].copy(), ang[:n].copy(), desc[:n].copy()
 
 
 def candidates(good_xy, lvl, lw, lh):
