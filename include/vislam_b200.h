@@ -262,6 +262,21 @@ int vsb_tracker_destroy(vsb_tracker_t* t);
 int vsb_fast_detect(vsb_ctx_t* ctx, const uint8_t* img, int64_t img_stride, int pitch, int w, int h, int count,
                     int threshold, int nonmax, int cap, int32_t* kp_xy, int32_t* kp_score, int32_t* n_kp, void* stream);
 
+/* ---- feature detection + description: cv::ORB, one pyramid level --------------------------------
+ * What cv::ORB::create(nfeatures, 1.2f, 1, 31, 0, 2, ORB::HARRIS_SCORE, 31, fast_threshold)->detectAndCompute(img, noArray(),
+ * keypoints, descriptors) computes — the detector of Camera::detectAndComputeFeatures (src/Camera.cpp:79-86, setDetector
+ * :124-129) and CameraGPU (src/CameraGPU.cpp:99-104) restricted to nlevels = 1 — for `count` frames: FAST-9/16 with
+ * suppression, border filter (31), retainBest(2 n) on the FAST score, Harris response (7x7, k 0.04), retainBest(n),
+ * intensity-centroid angle, 7x7 sigma-2 blur, steered rBRIEF.  img as in vsb_fast_detect.  Outputs (device), per frame up to
+ * cap entries in row-major (y, x) order: kp_xy [count][cap][2] int32, kp_resp [count][cap] (Harris response =
+ * cv::KeyPoint::response), kp_angle [count][cap] degrees (cv::KeyPoint::angle), desc [count][cap][32] (may be NULL: detect
+ * only); n_kp [count] = key points selected (ties at the two thresholds are kept as OpenCV keeps them, so it can exceed
+ * nfeatures; only the first cap are stored).  Bit-identical to cv2 4.13 through the oracle (oracle/orb.c).
+ * w, h must exceed 62 (the border filter leaves nothing otherwise: VSB_ERR_INVALID). */
+int vsb_orb_detect_compute(vsb_ctx_t* ctx, const uint8_t* img, int64_t img_stride, int pitch, int w, int h, int count,
+                           int nfeatures, int fast_threshold, int cap, int32_t* kp_xy, float* kp_resp, float* kp_angle,
+                           uint8_t* desc, int32_t* n_kp, void* stream);
+
 /* Work counters of the solver since the last call (then reset): out[0] = frame pairs solved,
  * out[1] = GN iterations (error evaluations), out[2] = sum over iterations of the candidate points visited
  * (SURVEY.md §8d's  sum_l K_l * P_l), out[3] = symmetric matches found.  Synchronises the device. */

@@ -241,7 +241,7 @@ void vsb_prof_end(vsb_ctx* ctx, int slot, cudaStream_t st) { cudaEventRecord(ctx
 static const char* kKernelNames[VSB_K_COUNT] = {"knn2_hamming", "knn_unpack", "match_filter", "gather_keypoints",
                                                 "pyramid", "gradient", "candidates", "gn_solve", "knn2_l2",
                                                 "knn2_l2_prep", "gn_prepare", "match_stage", "warp_se3",
-                                                "knn2_l2_final", "fast_score", "fast_compact"};
+                                                "knn2_l2_final", "fast_score", "fast_compact", "orb"};
 
 extern "C" int vsb_kernel_count(void) { return VSB_K_COUNT; }
 extern "C" const char* vsb_kernel_name(int id) { return (id >= 0 && id < VSB_K_COUNT) ? kKernelNames[id] : ""; }

@@ -12,7 +12,7 @@
 enum vsb_kernel_id {
     VSB_K_KNN_HAMMING = 0, VSB_K_KNN_UNPACK, VSB_K_MATCH_FILTER, VSB_K_GATHER, VSB_K_PYRAMID, VSB_K_GRADIENT,
     VSB_K_CANDIDATES, VSB_K_GN_SOLVE, VSB_K_KNN_L2, VSB_K_KNN_L2_PREP, VSB_K_GN_PREPARE,
-    VSB_K_MATCH_STAGE, VSB_K_WARP, VSB_K_KNN_L2_FINAL, VSB_K_FAST_SCORE, VSB_K_FAST_COMPACT, VSB_K_COUNT
+    VSB_K_MATCH_STAGE, VSB_K_WARP, VSB_K_KNN_L2_FINAL, VSB_K_FAST_SCORE, VSB_K_FAST_COMPACT, VSB_K_ORB, VSB_K_COUNT
 };
 
 struct vsb_prof_rec { int id; cudaEvent_t a, b; };

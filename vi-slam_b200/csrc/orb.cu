@@ -1,0 +1,375 @@
+// orb.cu — ORB key points and descriptors on the device: what cv::ORB::detectAndCompute does for ONE
+// pyramid level (cv::ORB::create(n, 1.2f, 1)), the detector the reference runs in Camera::detectAndComputeFeatures
+// (src/Camera.cpp:79-86, 124-129) / cv::cuda::ORB in CameraGPU (src/CameraGPU.cpp:99-104) before the tracked path:
+//   FAST-9/16 (fast.cu) -> border filter (edgeThreshold 31) -> retainBest(2n) on the FAST score -> Harris response (7x7,
+//   k = 0.04) -> retainBest(n) -> intensity-centroid angle (31-pixel circular patch, cv::fastAtan2) -> 7x7 sigma-2 blur ->
+//   steered rBRIEF (256 tests).
+// Results are bit-identical to oracle/orb.c, which is pinned bit for bit against cv2 4.13: same key-point set (ties at the
+// two selection thresholds are kept, as cv::KeyPointsFilter::retainBest keeps them), same responses, angles, descriptors;
+// key points come out in row-major (y, x) order (OpenCV's own order is whatever std::nth_element leaves).
+// All float arithmetic that OpenCV evaluates without fused multiply-add uses explicitly rounded intrinsics; the blur is the
+// float separable filter with the fused steps the oracle documents.
+#include "common.cuh"
+
+namespace {
+
+constexpr int ORB_EDGE = 31;
+constexpr int ORB_HALF = 15;
+
+__device__ const signed char c_pattern[256 * 4] = {
+#include "orb_pattern.inc"
+};
+// end of each row of the circular patch of radius 15 (orb.cpp: umax)
+__constant__ int c_umax[16] = {15, 15, 15, 15, 14, 14, 14, 13, 13, 12, 11, 10, 9, 8, 6, 3};
+// cv::getGaussianKernel(7, 2, CV_32F), bit patterns
+__constant__ uint32_t c_gauss[4] = {1032826801u, 1040595070u, 1044597305u, 1046301408u};
+
+__device__ __forceinline__ int block_exclusive_scan(int v, int* s_warp, int& total) {
+    // 256 threads; returns the exclusive prefix of v over the block, total = block sum
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { int t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
+    if (lane == 31) s_warp[warp] = inc;
+    __syncthreads();
+    if (warp == 0) {
+        int w = lane < 8 ? s_warp[lane] : 0;
+#pragma unroll
+        for (int o = 1; o < 8; o <<= 1) { int t = __shfl_up_sync(0xffffffffu, w, o); if (lane >= o) w += t; }
+        if (lane < 8) s_warp[lane] = w;
+    }
+    __syncthreads();
+    total = s_warp[7];
+    const int base = warp ? s_warp[warp - 1] : 0;
+    __syncthreads();
+    return base + inc - v;
+}
+
+// ---- stage 1: border filter + retainBest(2n) on the integer FAST score, order preserved --------------------------------
+// One block per frame.  Scores are integers 1..255, so the n-th best is found on a 256-bin histogram.
+__global__ void __launch_bounds__(256)
+orb_select_fast_kernel(const int32_t* __restrict__ fxy, const int32_t* __restrict__ fscore, const int32_t* __restrict__ nfast,
+                       int fcap, int w, int h, int keep_n, int32_t* __restrict__ sel_xy, int32_t* __restrict__ n_sel) {
+    __shared__ int s_hist[256];
+    __shared__ int s_warp[8];
+    __shared__ int s_thr;
+    const int f = blockIdx.x, tid = threadIdx.x;
+    const int n = min(nfast[f], fcap);
+    const int32_t* xy = fxy + (size_t)f * fcap * 2;
+    const int32_t* sc = fscore + (size_t)f * fcap;
+    int32_t* out = sel_xy + (size_t)f * fcap * 2;
+    s_hist[tid] = 0;
+    __syncthreads();
+    for (int i = tid; i < n; i += 256) {
+        const int x = xy[2 * i], y = xy[2 * i + 1];
+        if (x >= ORB_EDGE && x < w - ORB_EDGE && y >= ORB_EDGE && y < h - ORB_EDGE) atomicAdd(&s_hist[min(max(sc[i], 0), 255)], 1);
+    }
+    __syncthreads();
+    if (tid == 0) {
+        int total = 0;
+        for (int b = 0; b < 256; b++) total += s_hist[b];
+        int thr = 0;                                      // keep everything
+        if (keep_n >= 0 && total > keep_n) {
+            int acc = 0;
+            thr = 256;                                    // keep_n == 0: nothing
+            for (int b = 255; b >= 0 && keep_n > 0; b--) { acc += s_hist[b]; if (acc >= keep_n) { thr = b; break; } }
+        }
+        s_thr = thr;
+    }
+    __syncthreads();
+    const int thr = s_thr;
+    int base = 0;
+    for (int i0 = 0; i0 < n; i0 += 256) {
+        const int i = i0 + tid;
+        int x = 0, y = 0, flag = 0;
+        if (i < n) {
+            x = xy[2 * i]; y = xy[2 * i + 1];
+            flag = (x >= ORB_EDGE && x < w - ORB_EDGE && y >= ORB_EDGE && y < h - ORB_EDGE && sc[i] >= thr) ? 1 : 0;
+        }
+        int total;
+        const int pos = block_exclusive_scan(flag, s_warp, total);
+        if (flag) { out[2 * (base + pos)] = x; out[2 * (base + pos) + 1] = y; }
+        base += total;
+    }
+    if (tid == 0) n_sel[f] = base;
+}
+
+// ---- stage 2: Harris response of every selected corner (HarrisResponses, blockSize 7, k 0.04) --------------------------
+__global__ void __launch_bounds__(128)
+orb_harris_kernel(const uint8_t* __restrict__ img, long long img_stride, int pitch, const int32_t* __restrict__ sel_xy,
+                  const int32_t* __restrict__ n_sel, int fcap, float* __restrict__ resp) {
+    const int f = blockIdx.y;
+    const int i = blockIdx.x * 128 + threadIdx.x;
+    if (i >= n_sel[f]) return;
+    const int x0 = sel_xy[((size_t)f * fcap + i) * 2], y0 = sel_xy[((size_t)f * fcap + i) * 2 + 1];
+    const uint8_t* base = img + (size_t)f * img_stride + (size_t)(y0 - 4) * pitch + (x0 - 4);
+    // 9x9 neighbourhood, three rows at a time
+    int a = 0, b = 0, c = 0;
+    int r0[9], r1[9], r2[9];
+#pragma unroll
+    for (int j = 0; j < 9; j++) { r0[j] = __ldg(base + j); r1[j] = __ldg(base + pitch + j); }
+#pragma unroll
+    for (int row = 0; row < 7; row++) {
+        const uint8_t* p = base + (size_t)(row + 2) * pitch;
+#pragma unroll
+        for (int j = 0; j < 9; j++) r2[j] = __ldg(p + j);
+#pragma unroll
+        for (int j = 1; j < 8; j++) {
+            const int Ix = (r1[j + 1] - r1[j - 1]) * 2 + (r0[j + 1] - r0[j - 1]) + (r2[j + 1] - r2[j - 1]);
+            const int Iy = (r2[j] - r0[j]) * 2 + (r2[j - 1] - r0[j - 1]) + (r2[j + 1] - r0[j + 1]);
+            a += Ix * Ix; b += Iy * Iy; c += Ix * Iy;
+        }
+#pragma unroll
+        for (int j = 0; j < 9; j++) { r0[j] = r1[j]; r1[j] = r2[j]; }
+    }
+    const float scale = __fdiv_rn(1.f, __fmul_rn((float)((1 << 2) * 7), 255.f));
+    const float s4 = __fmul_rn(__fmul_rn(__fmul_rn(scale, scale), scale), scale);
+    const float fa = (float)a, fb = (float)b, fc = (float)c;
+    const float s = __fadd_rn(fa, fb);
+    const float t3 = __fmul_rn(__fmul_rn(0.04f, s), s);
+    const float d = __fsub_rn(__fsub_rn(__fmul_rn(fa, fb), __fmul_rn(fc, fc)), t3);
+    resp[(size_t)f * fcap + i] = __fmul_rn(d, s4);
+}
+
+// ---- stage 3: retainBest(n) on the float response (radix select of the n-th largest), order preserved -------------------
+__device__ __forceinline__ uint32_t float_key(float v) {      // unsigned order == float order
+    const uint32_t u = __float_as_uint(v);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__global__ void __launch_bounds__(256)
+orb_select_harris_kernel(const int32_t* __restrict__ sel_xy, const float* __restrict__ resp, const int32_t* __restrict__ n_sel,
+                         int fcap, int keep_n, int cap, int32_t* __restrict__ kp_xy, float* __restrict__ kp_resp,
+                         int32_t* __restrict__ n_kp) {
+    __shared__ int s_hist[256];
+    __shared__ int s_warp[8];
+    __shared__ uint32_t s_prefix;
+    __shared__ int s_want;
+    const int f = blockIdx.x, tid = threadIdx.x;
+    const int n = n_sel[f];
+    const int32_t* xy = sel_xy + (size_t)f * fcap * 2;
+    const float* r = resp + (size_t)f * fcap;
+    uint32_t thr_key = 0;                                 // keep everything
+    if (keep_n >= 0 && n > keep_n) {
+        if (keep_n == 0) thr_key = 0xffffffffu;
+        else {
+            // the keep_n-th largest key, most significant byte first
+            if (tid == 0) { s_prefix = 0; s_want = keep_n; }
+            __syncthreads();
+            for (int shift = 24; shift >= 0; shift -= 8) {
+                s_hist[tid] = 0;
+                __syncthreads();
+                const uint32_t prefix = s_prefix;
+                const uint32_t mask = shift == 24 ? 0u : (0xffffffffu << (shift + 8));
+                for (int i = tid; i < n; i += 256) {
+                    const uint32_t k = float_key(r[i]);
+                    if ((k & mask) == prefix) atomicAdd(&s_hist[(k >> shift) & 255], 1);
+                }
+                __syncthreads();
+                if (tid == 0) {
+                    int want = s_want, acc = 0, b = 255;
+                    for (; b > 0; b--) { if (acc + s_hist[b] >= want) break; acc += s_hist[b]; }
+                    s_prefix = prefix | ((uint32_t)b << shift);
+                    s_want = want - acc;
+                }
+                __syncthreads();
+            }
+            thr_key = s_prefix;
+        }
+    }
+    int base = 0;
+    for (int i0 = 0; i0 < n; i0 += 256) {
+        const int i = i0 + tid;
+        int flag = 0;
+        float v = 0.f;
+        if (i < n) { v = r[i]; flag = float_key(v) >= thr_key ? 1 : 0; }
+        if (keep_n == 0) flag = 0;
+        int total;
+        const int pos = block_exclusive_scan(flag, s_warp, total);
+        if (flag && base + pos < cap) {
+            kp_xy[((size_t)f * cap + base + pos) * 2] = xy[2 * i];
+            kp_xy[((size_t)f * cap + base + pos) * 2 + 1] = xy[2 * i + 1];
+            kp_resp[(size_t)f * cap + base + pos] = v;
+        }
+        base += total;
+    }
+    if (tid == 0) n_kp[f] = base;
+}
+
+// ---- stage 4: intensity-centroid orientation (ICAngles + cv::fastAtan2), one warp per key point -------------------------
+__device__ __forceinline__ float fast_atan2_deg(float y, float x) {
+    const float c = (float)(180 / 3.14159265358979323846);
+    const float p1 = __fmul_rn(0.9997878412794807f, c), p3 = __fmul_rn(-0.3258083974640975f, c),
+                p5 = __fmul_rn(0.1555786518463281f, c), p7 = __fmul_rn(-0.04432655554792128f, c);
+    const float eps = (float)2.2204460492503131e-16;
+    const float ax = fabsf(x), ay = fabsf(y);
+    const bool xs = ax >= ay;
+    const float q = xs ? __fdiv_rn(ay, __fadd_rn(ax, eps)) : __fdiv_rn(ax, __fadd_rn(ay, eps));
+    const float q2 = __fmul_rn(q, q);
+    float a = __fmul_rn(p7, q2);
+    a = __fadd_rn(a, p5); a = __fmul_rn(a, q2); a = __fadd_rn(a, p3); a = __fmul_rn(a, q2); a = __fadd_rn(a, p1);
+    a = __fmul_rn(a, q);
+    if (!xs) a = __fsub_rn(90.f, a);
+    if (x < 0.f) a = __fsub_rn(180.f, a);
+    if (y < 0.f) a = __fsub_rn(360.f, a);
+    return a;
+}
+__global__ void __launch_bounds__(256)
+orb_angle_kernel(const uint8_t* __restrict__ img, long long img_stride, int pitch, const int32_t* __restrict__ kp_xy,
+                 const int32_t* __restrict__ n_kp, int cap, float* __restrict__ kp_angle) {
+    const int f = blockIdx.y;
+    const int k = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (k >= min(n_kp[f], cap)) return;
+    const int x0 = kp_xy[((size_t)f * cap + k) * 2], y0 = kp_xy[((size_t)f * cap + k) * 2 + 1];
+    const uint8_t* center = img + (size_t)f * img_stride + (size_t)y0 * pitch + x0;
+    // lane u-index: u = lane - 15 for lanes 0..30 (31 columns); rows v = 0..15 handled by every lane for its column
+    int m01 = 0, m10 = 0;
+    const int u = lane - ORB_HALF;
+    if (lane < 31) {
+        m10 += u * (int)__ldg(center + u);
+        const int au = u < 0 ? -u : u;
+#pragma unroll
+        for (int v = 1; v <= ORB_HALF; v++) {
+            if (au <= c_umax[v]) {
+                const int vp = __ldg(center + u + v * pitch), vm = __ldg(center + u - v * pitch);
+                m01 += v * (vp - vm);
+                m10 += u * (vp + vm);
+            }
+        }
+    }
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) { m01 += __shfl_down_sync(0xffffffffu, m01, o); m10 += __shfl_down_sync(0xffffffffu, m10, o); }
+    if (lane == 0) kp_angle[(size_t)f * cap + k] = fast_atan2_deg((float)m01, (float)m10);
+}
+
+// ---- stage 5: the blur ORB applies before describing: 7x7 sigma 2, generic float separable filter, reflect-101 ---------
+constexpr int BT = 32;
+__device__ __forceinline__ int refl101(int p, int n) {
+    if (n == 1) return 0;
+    while (p < 0 || p >= n) { if (p < 0) p = -p; if (p >= n) p = 2 * n - 2 - p; }
+    return p;
+}
+__global__ void __launch_bounds__(256)
+orb_blur_kernel(const uint8_t* __restrict__ img, long long img_stride, int pitch, int w, int h, uint8_t* __restrict__ out) {
+    __shared__ uint8_t s_in[BT + 6][BT + 8];
+    __shared__ float s_row[BT + 6][BT + 1];
+    const int f = blockIdx.z, x0 = blockIdx.x * BT, y0 = blockIdx.y * BT, tid = threadIdx.x;
+    const uint8_t* src = img + (size_t)f * img_stride;
+    for (int i = tid; i < (BT + 6) * (BT + 6); i += 256) {
+        const int ry = i / (BT + 6), rx = i - ry * (BT + 6);
+        s_in[ry][rx] = __ldg(src + (size_t)refl101(y0 + ry - 3, h) * pitch + refl101(x0 + rx - 3, w));
+    }
+    __syncthreads();
+    float k[7];
+#pragma unroll
+    for (int i = 0; i < 4; i++) { k[i] = __uint_as_float(c_gauss[i]); k[6 - i] = k[i]; }
+    for (int i = tid; i < (BT + 6) * BT; i += 256) {
+        const int ry = i / BT, cx = i - ry * BT;
+        float acc = __fmul_rn((float)s_in[ry][cx], k[0]);
+#pragma unroll
+        for (int t = 1; t < 7; t++) acc = __fmaf_rn((float)s_in[ry][cx + t], k[t], acc);
+        s_row[ry][cx] = acc;
+    }
+    __syncthreads();
+    for (int i = tid; i < BT * BT; i += 256) {
+        const int cy = i / BT, cx = i - cy * BT;
+        const int x = x0 + cx, y = y0 + cy;
+        if (x >= w || y >= h) continue;
+        float acc = __fmul_rn(s_row[cy + 3][cx], k[3]);
+#pragma unroll
+        for (int t = 1; t <= 3; t++) acc = __fmaf_rn(__fadd_rn(s_row[cy + 3 + t][cx], s_row[cy + 3 - t][cx]), k[3 + t], acc);
+        const int v = __float2int_rn(acc);
+        out[((size_t)f * h + y) * w + x] = (uint8_t)min(max(v, 0), 255);
+    }
+}
+
+// ---- stage 6: steered rBRIEF (computeOrbDescriptors, WTA_K = 2): one warp per key point, one descriptor byte per lane -----
+__global__ void __launch_bounds__(256)
+orb_describe_kernel(const uint8_t* __restrict__ blurred, int w, int h, const int32_t* __restrict__ kp_xy,
+                    const float* __restrict__ kp_angle, const int32_t* __restrict__ n_kp, int cap, uint8_t* __restrict__ desc) {
+    __shared__ signed char s_pat[1024];
+    for (int i = threadIdx.x; i < 1024; i += 256) s_pat[i] = c_pattern[i];
+    __syncthreads();
+    const int f = blockIdx.y;
+    const int k = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (k >= min(n_kp[f], cap)) return;
+    const int x0 = kp_xy[((size_t)f * cap + k) * 2], y0 = kp_xy[((size_t)f * cap + k) * 2 + 1];
+    float angle = kp_angle[(size_t)f * cap + k];
+    angle = __fmul_rn(angle, (float)(3.14159265358979323846 / 180.f));
+    const float a = (float)cos((double)angle), b = (float)sin((double)angle);
+    const uint8_t* center = blurred + (size_t)f * w * h + (size_t)y0 * w + x0;
+    int val = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        const signed char* t = s_pat + 4 * (8 * lane + i);
+        int v[2];
+#pragma unroll
+        for (int q = 0; q < 2; q++) {
+            const float px = (float)t[2 * q], py = (float)t[2 * q + 1];
+            const float x = __fsub_rn(__fmul_rn(px, a), __fmul_rn(py, b));
+            const float y = __fadd_rn(__fmul_rn(px, b), __fmul_rn(py, a));
+            v[q] = __ldg(center + __float2int_rn(y) * w + __float2int_rn(x));
+        }
+        val |= (v[0] < v[1]) << i;
+    }
+    desc[((size_t)f * cap + k) * 32 + lane] = (uint8_t)val;
+}
+
+}  // namespace
+
+// ORB key points + descriptors of `count` frames, one pyramid level (cv::ORB::create(nfeatures, 1.2f, 1, 31, 0, 2,
+// HARRIS_SCORE, 31, fast_threshold)->detectAndCompute).  See include/vislam_b200.h.
+extern "C" int vsb_orb_detect_compute(vsb_ctx_t* ctx, const uint8_t* img, int64_t img_stride, int pitch, int w, int h, int count,
+                                      int nfeatures, int fast_threshold, int cap, int32_t* kp_xy, float* kp_resp,
+                                      float* kp_angle, uint8_t* desc, int32_t* n_kp, void* stream) {
+    if (!ctx || !img || !kp_xy || !kp_resp || !kp_angle || !n_kp) return VSB_ERR_INVALID;
+    if (w <= 2 * ORB_EDGE || h <= 2 * ORB_EDGE || pitch < w || count < 0 || cap <= 0 || nfeatures < 0) return VSB_ERR_INVALID;
+    if (fast_threshold < 0 || fast_threshold > 255) return VSB_ERR_INVALID;
+    if (count == 0) return VSB_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    // FAST corners per frame: 3x3 non-maximum suppression leaves at most one corner per 2x2 block, so w*h/4 can never
+    // overflow (dense noise does reach a quarter of that); the batch is processed in chunks that keep the scratch bounded
+    const int fcap = w * h / 4 + 16;
+    const size_t per_frame = (size_t)fcap * 24 + (desc ? (size_t)w * h : 0);
+    const int chunk = (int)max((size_t)1, min((size_t)count, ((size_t)384 << 20) / per_frame));
+    auto al = [](size_t b) { return (b + 255) & ~(size_t)255; };
+    const size_t b_fxy = al((size_t)chunk * fcap * 2 * sizeof(int32_t)), b_fsc = al((size_t)chunk * fcap * sizeof(int32_t));
+    const size_t b_sel = b_fxy, b_resp = al((size_t)chunk * fcap * sizeof(float)), b_n = al((size_t)chunk * sizeof(int32_t));
+    const size_t b_blur = desc ? al((size_t)chunk * w * h) : 0;
+    void* scratch = nullptr;
+    int rc = vsb_scratch2_reserve(ctx, b_fxy + b_fsc + b_sel + b_resp + 2 * b_n + b_blur + 256, &scratch);
+    if (rc) return rc;
+    uint8_t* p = static_cast<uint8_t*>(scratch);
+    int32_t* fxy = reinterpret_cast<int32_t*>(p); p += b_fxy;
+    int32_t* fsc = reinterpret_cast<int32_t*>(p); p += b_fsc;
+    int32_t* sel = reinterpret_cast<int32_t*>(p); p += b_sel;
+    float* resp = reinterpret_cast<float*>(p); p += b_resp;
+    int32_t* nfast = reinterpret_cast<int32_t*>(p); p += b_n;
+    int32_t* nsel = reinterpret_cast<int32_t*>(p); p += b_n;
+    uint8_t* blurred = p;
+    for (int z0 = 0; z0 < count; z0 += chunk) {
+        const int zc = min(chunk, count - z0);
+        const uint8_t* in = img + (size_t)z0 * img_stride;
+        rc = vsb_fast_detect(ctx, in, img_stride, pitch, w, h, zc, fast_threshold, 1, fcap, fxy, fsc, nfast, stream);
+        if (rc) return rc;
+        ProfScope ps(ctx, VSB_K_ORB, st);
+        orb_select_fast_kernel<<<zc, 256, 0, st>>>(fxy, fsc, nfast, fcap, w, h, 2 * nfeatures, sel, nsel);
+        VSB_LAUNCHED(ctx);
+        orb_harris_kernel<<<dim3(vsb_div_up(fcap, 128), zc), 128, 0, st>>>(in, img_stride, pitch, sel, nsel, fcap, resp);
+        VSB_LAUNCHED(ctx);
+        orb_select_harris_kernel<<<zc, 256, 0, st>>>(sel, resp, nsel, fcap, nfeatures, cap, kp_xy + (size_t)z0 * cap * 2,
+                                                      kp_resp + (size_t)z0 * cap, n_kp + z0);
+        VSB_LAUNCHED(ctx);
+        orb_angle_kernel<<<dim3(vsb_div_up(cap, 8), zc), 256, 0, st>>>(in, img_stride, pitch, kp_xy + (size_t)z0 * cap * 2,
+                                                                         n_kp + z0, cap, kp_angle + (size_t)z0 * cap);
+        VSB_LAUNCHED(ctx);
+        if (desc) {
+            orb_blur_kernel<<<dim3(vsb_div_up(w, BT), vsb_div_up(h, BT), zc), 256, 0, st>>>(in, img_stride, pitch, w, h, blurred);
+            VSB_LAUNCHED(ctx);
+            orb_describe_kernel<<<dim3(vsb_div_up(cap, 8), zc), 256, 0, st>>>(blurred, w, h, kp_xy + (size_t)z0 * cap * 2,
+                                                                              kp_angle + (size_t)z0 * cap, n_kp + z0, cap,
+                                                                              desc + (size_t)z0 * cap * 32);
+            VSB_LAUNCHED(ctx);
+        }
+    }
+    return VSB_OK;
+}
