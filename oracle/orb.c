@@ -241,3 +241,116 @@ int vso_orb_detect_compute(const uint8_t* img, int w, int h, int pitch, int nfea
     free(ang); free(keep); free(sc); free(fsc); free(fxy);
     return m3;
 }
+
+/* ---------------------------------------------------------------------------------------------- the scale pyramid ---- */
+/* cv::resize(src, dst, dsize, 0, 0, INTER_LINEAR_EXACT) for 8-bit images (imgproc/src/resize.cpp, resize_bitExact with
+ * interpolationLinear<uchar>): coefficients in 8.8 fixed point from scale = 1 / (dsize / ssize) evaluated in double,
+ * horizontal pass into 8.8 values, vertical pass into 16.16 and rounding; positions that fall before the first / after the
+ * last source sample take that sample.  Bit-exact against cv2 4.13 (tests/test_oracle_orb.py). */
+static void lin_exact_coeff(int v, int ssize, int dsize, int* ofs, int* c1, int* edge) {
+    double inv = (double)dsize / (double)ssize;
+    double scale = 1.0 / inv;
+    double fval = scale * ((double)v + 0.5) - 0.5;
+    int ival = (int)floor(fval);
+    *edge = 0; *ofs = 0; *c1 = 0;
+    if (ival >= 0 && ssize > 1) {
+        if (ival < ssize - 1) { *ofs = ival; *c1 = (int)lrint((fval - (double)ival) * 256.0); }
+        else { *ofs = ssize - 1; *edge = 1; }
+    } else {
+        *edge = -1;
+    }
+}
+void vso_resize_linear_exact(const uint8_t* src, int sw, int sh, int spitch, uint8_t* dst, int dw, int dh) {
+    int* ox = (int*)malloc(sizeof(int) * 3 * (size_t)dw);
+    int *ax = ox + dw, *ex = ox + 2 * dw;
+    for (int x = 0; x < dw; x++) lin_exact_coeff(x, sw, dw, &ox[x], &ax[x], &ex[x]);
+    uint32_t* h0 = (uint32_t*)malloc(sizeof(uint32_t) * 2 * (size_t)dw);
+    uint32_t* h1 = h0 + dw;
+    for (int y = 0; y < dh; y++) {
+        int oy, ay, ey;
+        lin_exact_coeff(y, sh, dh, &oy, &ay, &ey);
+        const uint8_t* r0 = src + (size_t)(ey < 0 ? 0 : oy) * spitch;
+        const uint8_t* r1 = src + (size_t)(ey != 0 ? (ey < 0 ? 0 : oy) : oy + 1) * spitch;
+        for (int x = 0; x < dw; x++) {
+            if (ex[x] < 0) { h0[x] = (uint32_t)r0[0] << 8; h1[x] = (uint32_t)r1[0] << 8; }
+            else if (ex[x] > 0) { h0[x] = (uint32_t)r0[sw - 1] << 8; h1[x] = (uint32_t)r1[sw - 1] << 8; }
+            else {
+                h0[x] = (uint32_t)(256 - ax[x]) * r0[ox[x]] + (uint32_t)ax[x] * r0[ox[x] + 1];
+                h1[x] = (uint32_t)(256 - ax[x]) * r1[ox[x]] + (uint32_t)ax[x] * r1[ox[x] + 1];
+            }
+        }
+        for (int x = 0; x < dw; x++) {
+            uint32_t v = ey != 0 ? h0[x] << 8 : (uint32_t)(256 - ay) * h0[x] + (uint32_t)ay * h1[x];
+            v = (v + (1u << 15)) >> 16;
+            dst[(size_t)y * dw + x] = (uint8_t)(v > 255 ? 255 : v);
+        }
+    }
+    free(h0); free(ox);
+}
+
+/* layer scale and per-level feature budget of cv::ORB (orb.cpp getScale / computeKeyPoints).  ORB::create takes the scale
+ * factor as a FLOAT and stores it in a double, so every level scale is (float)pow((double)1.2f, level). */
+float vso_orb_level_scale(float scale_factor, int level) { return (float)pow((double)scale_factor, (double)level); }
+void vso_orb_level_budget(int nfeatures, float scale_factor, int nlevels, int* per_level) {
+    float factor = (float)(1.0 / (double)scale_factor);
+    float nd = nfeatures * (1 - factor) / (1 - (float)pow((double)factor, (double)nlevels));
+    int sum = 0;
+    for (int l = 0; l < nlevels - 1; l++) {
+        per_level[l] = (int)lrintf(nd);
+        sum += per_level[l];
+        nd *= factor;
+    }
+    per_level[nlevels - 1] = nfeatures - sum > 0 ? nfeatures - sum : 0;
+}
+
+/* cv::ORB::create(nfeatures, scale_factor, nlevels, 31, 0, 2, HARRIS_SCORE, 31, fast_threshold)->detectAndCompute:
+ * every level is the one-level pipeline above on the level image (level l = INTER_LINEAR_EXACT resize of level l-1 to
+ * cvRound(size / scale_l)) with that level's budget; key points are reported level by level (row-major inside a level) with
+ * pt = level coordinates * scale_l, octave = level.  Returns the number of key points (<= cap are written). */
+int vso_orb_detect_compute_pyr(const uint8_t* img, int w, int h, int pitch, int nfeatures, float scale_factor, int nlevels,
+                               int fast_threshold, float* out_xy, int32_t* out_octave, float* out_resp, float* out_angle,
+                               uint8_t* out_desc, int cap) {
+    int budget[32];
+    if (nlevels < 1) nlevels = 1;
+    if (nlevels > 32) nlevels = 32;
+    vso_orb_level_budget(nfeatures, scale_factor, nlevels, budget);
+    uint8_t* prev = NULL;
+    int pw = w, ph = h, total = 0;
+    for (int l = 0; l < nlevels; l++) {
+        float scale = vso_orb_level_scale(scale_factor, l);
+        const uint8_t* cur = img;
+        int cw = w, ch = h, cp = pitch;
+        uint8_t* mine = NULL;
+        if (l > 0) {
+            cw = cv_round_f((float)w / scale);
+            ch = cv_round_f((float)h / scale);
+            if (cw < 1 || ch < 1) break;
+            mine = (uint8_t*)malloc((size_t)cw * ch);
+            vso_resize_linear_exact(prev ? prev : img, pw, ph, prev ? pw : pitch, mine, cw, ch);
+            cur = mine; cp = cw;
+        }
+        if (cw > 62 && ch > 62) {
+            int lcap = cw * ch / 4 + 16;
+            int32_t* xy = (int32_t*)malloc(sizeof(int32_t) * 2 * (size_t)lcap);
+            float* resp = (float*)malloc(sizeof(float) * (size_t)lcap);
+            float* ang = (float*)malloc(sizeof(float) * (size_t)lcap);
+            uint8_t* desc = out_desc ? (uint8_t*)malloc((size_t)lcap * 32) : NULL;
+            int n = vso_orb_detect_compute(cur, cw, ch, cp, budget[l], fast_threshold, xy, resp, ang, desc, lcap);
+            if (n > lcap) n = lcap;
+            for (int i = 0; i < n; i++, total++) {
+                if (total >= cap) continue;
+                if (out_xy) { out_xy[2 * total] = (float)xy[2 * i] * scale; out_xy[2 * total + 1] = (float)xy[2 * i + 1] * scale; }
+                if (out_octave) out_octave[total] = l;
+                if (out_resp) out_resp[total] = resp[i];
+                if (out_angle) out_angle[total] = ang[i];
+                if (out_desc) memcpy(out_desc + (size_t)total * 32, desc + (size_t)i * 32, 32);
+            }
+            free(desc); free(ang); free(resp); free(xy);
+        }
+        free(prev);
+        prev = mine;
+        if (l > 0) { pw = cw; ph = ch; }
+    }
+    free(prev);
+    return total;
+}

@@ -177,4 +177,12 @@ void vso_orb_describe(const uint8_t* blurred, int w, int h, int pitch, const int
 int vso_orb_detect_compute(const uint8_t* img, int w, int h, int pitch, int nfeatures, int fast_threshold, int32_t* out_xy,
                            float* out_resp, float* out_angle, uint8_t* out_desc, int cap);
 
+/* cv::resize(INTER_LINEAR_EXACT) for 8-bit images and the multi-level cv::ORB built on it (oracle/orb.c) */
+void vso_resize_linear_exact(const uint8_t* src, int sw, int sh, int spitch, uint8_t* dst, int dw, int dh);
+float vso_orb_level_scale(float scale_factor, int level);
+void vso_orb_level_budget(int nfeatures, float scale_factor, int nlevels, int* per_level);
+int vso_orb_detect_compute_pyr(const uint8_t* img, int w, int h, int pitch, int nfeatures, float scale_factor, int nlevels,
+                               int fast_threshold, float* out_xy, int32_t* out_octave, float* out_resp, float* out_angle,
+                               uint8_t* out_desc, int cap);
+
 #endif

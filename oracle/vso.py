@@ -113,6 +113,13 @@ def lib():
     L.vso_orb_describe.argtypes = [_u8p, C.c_int, C.c_int, C.c_int, _i32p, _f32p, C.c_int, _u8p]
     L.vso_orb_detect_compute.argtypes = [_u8p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _i32p, _f32p, _f32p, _u8p, C.c_int]
     L.vso_orb_detect_compute.restype = C.c_int
+    L.vso_resize_linear_exact.argtypes = [_u8p, C.c_int, C.c_int, C.c_int, _u8p, C.c_int, C.c_int]
+    L.vso_orb_level_scale.argtypes = [C.c_float, C.c_int]
+    L.vso_orb_level_scale.restype = C.c_float
+    L.vso_orb_level_budget.argtypes = [C.c_int, C.c_float, C.c_int, _i32p]
+    L.vso_orb_detect_compute_pyr.argtypes = [_u8p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_int, C.c_int, _f32p, _i32p,
+                                             _f32p, _f32p, _u8p, C.c_int]
+    L.vso_orb_detect_compute_pyr.restype = C.c_int
     _lib = L
     return L
 
@@ -285,6 +292,36 @@ def orb_detect_compute(img, nfeatures=500, fast_threshold=20, cap=None):
     n = lib().vso_orb_detect_compute(img, w, h, w, int(nfeatures), int(fast_threshold), xy, resp, ang, desc, cap)
     n = min(n, cap)
     return xy[:n].copy(), resp[:n].copy(), ang[:n].copy(), desc[:n].copy()
+
+
+def resize_linear_exact(img, dw, dh):
+    img = np.ascontiguousarray(img, np.uint8)
+    out = np.zeros((dh, dw), np.uint8)
+    lib().vso_resize_linear_exact(img, img.shape[1], img.shape[0], img.shape[1], out, dw, dh)
+    return out
+
+
+def orb_level_budget(nfeatures, scale_factor=1.2, nlevels=8):
+    out = np.zeros(nlevels, np.int32)
+    lib().vso_orb_level_budget(int(nfeatures), float(scale_factor), int(nlevels), out)
+    return out
+
+
+def orb_detect_compute_pyr(img, nfeatures=500, scale_factor=1.2, nlevels=8, fast_threshold=20, cap=None):
+    """cv::ORB detectAndCompute with its scale pyramid: (xy [n,2] f32, octave [n] i32, response, angle_deg, desc [n,32]),
+    level by level, row-major inside a level."""
+    img = np.ascontiguousarray(img, np.uint8)
+    h, w = img.shape
+    cap = cap or (2 * nfeatures + 4096)
+    xy = np.zeros((cap, 2), np.float32)
+    octv = np.zeros(cap, np.int32)
+    resp = np.zeros(cap, np.float32)
+    ang = np.zeros(cap, np.float32)
+    desc = np.zeros((cap, 32), np.uint8)
+    n = lib().vso_orb_detect_compute_pyr(img, w, h, w, int(nfeatures), float(scale_factor), int(nlevels), int(fast_threshold),
+                                         xy, octv, resp, ang, desc, cap)
+    n = min(n, cap)
+    return xy[:n].copy(), octv[:n].copy(), resp[:n].copy(), ang[:n].copy(), desc[:n].copy()
 
 
 def candidates(good_xy, lvl, lw, lh):

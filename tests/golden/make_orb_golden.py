@@ -36,6 +36,23 @@ def main():
             out[f"{name}_{n}_angle"] = np.array([kps[i].angle for i in rows], np.float32)
             out[f"{name}_{n}_desc"] = des[rows] if len(rows) else des
             print(name, n, len(kps))
+    # the full detector with its scale pyramid (the reference's ORB::create(n): 8 levels, factor 1.2), and two other settings
+    for name, img in images():
+        for tag, (n, sf, nl) in {"d": (300, 1.2, 8), "e": (150, 1.5, 4)}.items():
+            kps, des = cv2.ORB_create(nfeatures=n, scaleFactor=sf, nlevels=nl).detectAndCompute(img, None)
+            des = des if des is not None else np.zeros((0, 32), np.uint8)
+            rows = sorted(range(len(kps)), key=lambda i: (kps[i].octave, kps[i].pt[1], kps[i].pt[0]))
+            out[f"{name}_pyr{tag}_cfg"] = np.array([n, sf, nl], np.float64)
+            out[f"{name}_pyr{tag}_xy"] = np.array([kps[i].pt for i in rows], np.float32).reshape(-1, 2)
+            out[f"{name}_pyr{tag}_octave"] = np.array([kps[i].octave for i in rows], np.int32)
+            out[f"{name}_pyr{tag}_resp"] = np.array([kps[i].response for i in rows], np.float32)
+            out[f"{name}_pyr{tag}_angle"] = np.array([kps[i].angle for i in rows], np.float32)
+            out[f"{name}_pyr{tag}_size"] = np.array([kps[i].size for i in rows], np.float32)
+            out[f"{name}_pyr{tag}_desc"] = des[rows] if len(rows) else des
+            print(name, "pyramid", tag, len(kps))
+    rimg = next(images())[1]
+    for i, (dw, dh) in enumerate(((220, 167), (132, 100), (263, 199), (97, 61))):
+        out[f"resize{i}"] = cv2.resize(rimg, (dw, dh), interpolation=cv2.INTER_LINEAR_EXACT)
     np.savez_compressed(os.path.join(HERE, "orb_cv2.npz"), **out)
     print(os.path.getsize(os.path.join(HERE, "orb_cv2.npz")))
 

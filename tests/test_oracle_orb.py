@@ -33,6 +33,28 @@ def test_orb_matches_cv2_golden(oracle, name, n):
         assert len(xy) >= 60                                       # ties at the threshold are kept, as in OpenCV
 
 
+@pytest.mark.parametrize("name", ["noise", "odd", "rects"])
+@pytest.mark.parametrize("tag", ["d", "e"])
+def test_orb_pyramid_matches_cv2_golden(oracle, name, tag):
+    """The full detector (scale pyramid; 'd' = the reference's setting: 8 levels, factor 1.2)."""
+    g = np.load(os.path.join(GOLD, "orb_cv2.npz"))
+    n, sf, nl = g[f"{name}_pyr{tag}_cfg"]
+    xy, octv, resp, ang, desc = oracle.orb_detect_compute_pyr(g[f"{name}_img"], int(n), float(sf), int(nl))
+    assert np.array_equal(xy, g[f"{name}_pyr{tag}_xy"])
+    assert np.array_equal(octv, g[f"{name}_pyr{tag}_octave"])
+    assert np.array_equal(resp, g[f"{name}_pyr{tag}_resp"])
+    assert np.array_equal(ang, g[f"{name}_pyr{tag}_angle"])
+    assert np.array_equal(desc, g[f"{name}_pyr{tag}_desc"])
+    scale = np.array([oracle.lib().vso_orb_level_scale(float(sf), int(o)) for o in octv], np.float32)
+    assert np.array_equal(np.float32(31.0) * scale, g[f"{name}_pyr{tag}_size"])        # cv::KeyPoint::size = patchSize * scale
+
+
+def test_resize_linear_exact_matches_cv2_golden(oracle):
+    g = np.load(os.path.join(GOLD, "orb_cv2.npz"))
+    for i, (dw, dh) in enumerate(((220, 167), (132, 100), (263, 199), (97, 61))):
+        assert np.array_equal(oracle.resize_linear_exact(g["noise_img"], dw, dh), g[f"resize{i}"])
+
+
 def test_orb_live_vs_cv2(oracle):
     cv2 = pytest.importorskip("cv2")
     rng = np.random.default_rng(99)
@@ -49,3 +71,12 @@ def test_orb_live_vs_cv2(oracle):
         # the blur ORB applies is the generic float separable filter, not GaussianBlur's 8-bit fixed-point path
         k = cv2.getGaussianKernel(7, 2, cv2.CV_32F)
         assert np.array_equal(oracle.orb_blur(img), cv2.sepFilter2D(img, cv2.CV_8U, k, k, borderType=cv2.BORDER_REFLECT_101))
+        # with the scale pyramid (default cv::ORB)
+        kps, des = cv2.ORB_create(nfeatures=n).detectAndCompute(img, None)
+        rows = sorted(range(len(kps)), key=lambda i: (kps[i].octave, kps[i].pt[1], kps[i].pt[0]))
+        xy, octv, resp, ang, desc = oracle.orb_detect_compute_pyr(img, n)
+        assert np.array_equal(xy, np.array([kps[i].pt for i in rows], np.float32).reshape(-1, 2))
+        assert np.array_equal(octv, [kps[i].octave for i in rows])
+        assert np.array_equal(resp, np.array([kps[i].response for i in rows], np.float32))
+        assert np.array_equal(ang, np.array([kps[i].angle for i in rows], np.float32))
+        assert np.array_equal(desc, des[rows])
