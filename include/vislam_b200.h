@@ -277,6 +277,17 @@ int vsb_orb_detect_compute(vsb_ctx_t* ctx, const uint8_t* img, int64_t img_strid
                            int nfeatures, int fast_threshold, int cap, int32_t* kp_xy, float* kp_resp, float* kp_angle,
                            uint8_t* desc, int32_t* n_kp, void* stream);
 
+/* The same with the detector's scale pyramid — cv::ORB::create(nfeatures, scale_factor, nlevels, 31, 0, 2, HARRIS_SCORE, 31,
+ * fast_threshold), i.e. exactly what the reference's ORB::create(n) runs with scale_factor 1.2f, nlevels 8: level l is the
+ * INTER_LINEAR_EXACT resize of level l-1 to cvRound(size / scale_l), scale_l = (float)pow((double)scale_factor, l); every
+ * level runs the one-level pipeline with cv::ORB's per-level feature budget.  Outputs per frame, level by level (row-major
+ * inside a level): kp_xy [count][cap][2] FLOAT = level coordinates * scale_l (cv::KeyPoint::pt), kp_octave [count][cap] (may
+ * be NULL), kp_resp, kp_angle, desc (may be NULL); cv::KeyPoint::size is 31 * scale_l.  Bit-identical to cv2 4.13 through the
+ * oracle. */
+int vsb_orb_detect_compute_pyr(vsb_ctx_t* ctx, const uint8_t* img, int64_t img_stride, int pitch, int w, int h, int count,
+                               int nfeatures, float scale_factor, int nlevels, int fast_threshold, int cap, float* kp_xy,
+                               int32_t* kp_octave, float* kp_resp, float* kp_angle, uint8_t* desc, int32_t* n_kp, void* stream);
+
 /* Work counters of the solver since the last call (then reset): out[0] = frame pairs solved,
  * out[1] = GN iterations (error evaluations), out[2] = sum over iterations of the candidate points visited
  * (SURVEY.md §8d's  sum_l K_l * P_l), out[3] = symmetric matches found.  Synchronises the device. */

@@ -100,3 +100,53 @@ def test_orb_descriptors_feed_the_matcher(ctx, oracle):
     assert good.sum() > 200                                         # interior points reappear with identical descriptors
     shift = xyb[idx[good, 0]] - xya[good]
     assert np.all(shift == np.array([5, 3]))
+
+
+def run_pyr(ctx, imgs, n, sf=1.2, nl=8, cap=None):
+    import torch
+    d = torch.from_numpy(np.ascontiguousarray(imgs)).cuda()
+    xy, octv, resp, ang, desc, nk = ctx.orb_detect_compute_pyr(d, nfeatures=n, scale_factor=sf, nlevels=nl, cap=cap)
+    torch.cuda.synchronize()
+    out = []
+    for b in range(imgs.shape[0]):
+        k = int(nk[b])
+        m = min(k, xy.shape[1])
+        out.append((k, xy[b, :m].cpu().numpy(), octv[b, :m].cpu().numpy(), resp[b, :m].cpu().numpy(), ang[b, :m].cpu().numpy(),
+                    desc[b, :m].cpu().numpy()))
+    return out
+
+
+@pytest.mark.parametrize("name", ["noise", "odd", "rects"])
+@pytest.mark.parametrize("tag", ["d", "e"])
+def test_orb_pyramid_matches_cv2_golden(ctx, name, tag):
+    """The full detector with its scale pyramid ('d' = the reference's ORB::create(n): 8 levels, factor 1.2) vs cv2."""
+    g = np.load(os.path.join(GOLD, "orb_cv2.npz"))
+    n, sf, nl = g[f"{name}_pyr{tag}_cfg"]
+    (k, xy, octv, resp, ang, desc), = run_pyr(ctx, g[f"{name}_img"][None], int(n), float(sf), int(nl), cap=2000)
+    assert k == len(g[f"{name}_pyr{tag}_xy"])
+    assert np.array_equal(xy, g[f"{name}_pyr{tag}_xy"])
+    assert np.array_equal(octv, g[f"{name}_pyr{tag}_octave"])
+    assert np.array_equal(resp, g[f"{name}_pyr{tag}_resp"])
+    assert np.array_equal(ang, g[f"{name}_pyr{tag}_angle"])
+    assert np.array_equal(desc, g[f"{name}_pyr{tag}_desc"])
+
+
+def test_orb_pyramid_batch_vs_oracle(ctx, oracle):
+    """A batch of EuRoC- and KITTI-shaped frames through the default detector, plus a capacity smaller than the result."""
+    rng = np.random.default_rng(8)
+    for (w, h, n) in ((752, 480, 1000), (1241, 376, 2000)):
+        frames = []
+        for s in range(3):
+            f = (rng.random((h, w)) * 255).astype(np.float32)
+            f = (f + np.roll(f, 1, 0) + np.roll(f, 1, 1) + np.roll(f, (1, 1), (0, 1))) / 4
+            frames.append(f.astype(np.uint8))
+        imgs = np.stack(frames)
+        for cap in (4 * n, n // 2):
+            res = run_pyr(ctx, imgs, n, cap=cap)
+            for b, (k, xy, octv, resp, ang, desc) in enumerate(res):
+                oxy, ooct, oresp, oang, odesc = oracle.orb_detect_compute_pyr(imgs[b], n)
+                assert k == len(oxy), (b, k, len(oxy))
+                m = min(k, cap)
+                assert np.array_equal(xy, oxy[:m]) and np.array_equal(octv, ooct[:m])
+                assert np.array_equal(resp, oresp[:m]) and np.array_equal(ang, oang[:m])
+                assert np.array_equal(desc, odesc[:m])

@@ -314,6 +314,124 @@ orb_describe_kernel(const uint8_t* __restrict__ blurred, int w, int h, const int
     desc[((size_t)f * cap + k) * 32 + lane] = (uint8_t)val;
 }
 
+// ---- the scale pyramid: cv::resize(.., INTER_LINEAR_EXACT) for 8-bit images (resize_bitExact, 8.8 fixed point) -----------
+__device__ __forceinline__ void lin_exact_coeff(int v, int ssize, int dsize, int& ofs, int& c1, int& edge) {
+    const double inv = __ddiv_rn((double)dsize, (double)ssize);
+    const double scale = __ddiv_rn(1.0, inv);
+    const double fval = __dsub_rn(__dmul_rn(scale, __dadd_rn((double)v, 0.5)), 0.5);
+    const int ival = (int)floor(fval);
+    edge = 0; ofs = 0; c1 = 0;
+    if (ival >= 0 && ssize > 1) {
+        if (ival < ssize - 1) { ofs = ival; c1 = __double2int_rn(__dmul_rn(__dsub_rn(fval, (double)ival), 256.0)); }
+        else { ofs = ssize - 1; edge = 1; }
+    } else {
+        edge = -1;
+    }
+}
+__global__ void __launch_bounds__(256)
+orb_resize_kernel(const uint8_t* __restrict__ src, long long src_stride, int spitch, int sw, int sh, uint8_t* __restrict__ dst,
+                  int dw, int dh) {
+    const int x = blockIdx.x * 32 + (threadIdx.x & 31), y = blockIdx.y * 8 + (threadIdx.x >> 5), f = blockIdx.z;
+    if (x >= dw || y >= dh) return;
+    int ox, ax, ex, oy, ay, ey;
+    lin_exact_coeff(x, sw, dw, ox, ax, ex);
+    lin_exact_coeff(y, sh, dh, oy, ay, ey);
+    const uint8_t* img = src + (size_t)f * src_stride;
+    const int y0 = ey < 0 ? 0 : oy, y1 = ey != 0 ? y0 : oy + 1;
+    const uint8_t* r0 = img + (size_t)y0 * spitch;
+    const uint8_t* r1 = img + (size_t)y1 * spitch;
+    uint32_t h0, h1;
+    if (ex < 0) { h0 = (uint32_t)__ldg(r0) << 8; h1 = (uint32_t)__ldg(r1) << 8; }
+    else if (ex > 0) { h0 = (uint32_t)__ldg(r0 + sw - 1) << 8; h1 = (uint32_t)__ldg(r1 + sw - 1) << 8; }
+    else {
+        h0 = (uint32_t)(256 - ax) * __ldg(r0 + ox) + (uint32_t)ax * __ldg(r0 + ox + 1);
+        h1 = (uint32_t)(256 - ax) * __ldg(r1 + ox) + (uint32_t)ax * __ldg(r1 + ox + 1);
+    }
+    uint32_t v = ey != 0 ? h0 << 8 : (uint32_t)(256 - ay) * h0 + (uint32_t)ay * h1;
+    v = (v + (1u << 15)) >> 16;
+    dst[((size_t)f * dh + y) * dw + x] = (uint8_t)min(v, 255u);
+}
+
+// appends one level's key points to the frame's list: pt = level coordinates * scale (float), octave = level
+__global__ void __launch_bounds__(256)
+orb_append_kernel(const int32_t* __restrict__ lxy, const float* __restrict__ lresp, const float* __restrict__ langle,
+                  const uint8_t* __restrict__ ldesc, const int32_t* __restrict__ ln, int cap, float scale, int level,
+                  float* __restrict__ kp_xy, int32_t* __restrict__ kp_octave, float* __restrict__ kp_resp,
+                  float* __restrict__ kp_angle, uint8_t* __restrict__ desc, const int32_t* __restrict__ n_total) {
+    const int f = blockIdx.y, i = blockIdx.x * 256 + threadIdx.x;
+    const int n = min(ln[f], cap);
+    if (i >= n) return;
+    const int o = n_total[f] + i;
+    if (o >= cap) return;
+    const size_t src = (size_t)f * cap + i, dst = (size_t)f * cap + o;
+    kp_xy[2 * dst] = __fmul_rn((float)lxy[2 * src], scale);
+    kp_xy[2 * dst + 1] = __fmul_rn((float)lxy[2 * src + 1], scale);
+    if (kp_octave) kp_octave[dst] = level;
+    kp_resp[dst] = lresp[src];
+    kp_angle[dst] = langle[src];
+    if (desc) {
+        const uint4* s4 = reinterpret_cast<const uint4*>(ldesc + src * 32);
+        uint4* d4 = reinterpret_cast<uint4*>(desc + dst * 32);
+        d4[0] = s4[0]; d4[1] = s4[1];
+    }
+}
+__global__ void orb_advance_kernel(int32_t* __restrict__ n_total, const int32_t* __restrict__ ln, int count) {
+    const int f = blockIdx.x * 256 + threadIdx.x;
+    if (f < count) n_total[f] += ln[f];
+}
+
+struct OrbScratch {
+    int32_t *fxy, *fsc, *sel, *nfast, *nsel;
+    float* resp;
+    uint8_t* blurred;
+    int fcap;
+};
+inline size_t orb_al(size_t b) { return (b + 255) & ~(size_t)255; }
+inline size_t orb_scratch_bytes(int chunk, int w, int h, bool describe) {
+    const size_t fcap = (size_t)w * h / 4 + 16;
+    return 2 * orb_al(chunk * fcap * 8) + orb_al(chunk * fcap * 4) + orb_al(chunk * fcap * 4) + 2 * orb_al((size_t)chunk * 4) +
+           (describe ? orb_al((size_t)chunk * w * h) : 0);
+}
+inline OrbScratch orb_scratch_carve(uint8_t*& p, int chunk, int w, int h, bool describe) {
+    OrbScratch s;
+    s.fcap = w * h / 4 + 16;
+    const size_t fcap = (size_t)s.fcap;
+    s.fxy = reinterpret_cast<int32_t*>(p); p += orb_al(chunk * fcap * 8);
+    s.sel = reinterpret_cast<int32_t*>(p); p += orb_al(chunk * fcap * 8);
+    s.fsc = reinterpret_cast<int32_t*>(p); p += orb_al(chunk * fcap * 4);
+    s.resp = reinterpret_cast<float*>(p); p += orb_al(chunk * fcap * 4);
+    s.nfast = reinterpret_cast<int32_t*>(p); p += orb_al((size_t)chunk * 4);
+    s.nsel = reinterpret_cast<int32_t*>(p); p += orb_al((size_t)chunk * 4);
+    s.blurred = describe ? p : nullptr;
+    if (describe) p += orb_al((size_t)chunk * w * h);
+    return s;
+}
+
+// the one-level pipeline on zc frames of w x h (fcap is taken from the scratch, sized for the largest level)
+int orb_one_level(vsb_ctx_t* ctx, const OrbScratch& S, const uint8_t* in, int64_t img_stride, int pitch, int w, int h, int zc,
+                  int nfeatures, int fast_threshold, int cap, int32_t* kp_xy, float* kp_resp, float* kp_angle, uint8_t* desc,
+                  int32_t* n_kp, cudaStream_t st) {
+    const int fcap = S.fcap;
+    int rc = vsb_fast_detect(ctx, in, img_stride, pitch, w, h, zc, fast_threshold, 1, fcap, S.fxy, S.fsc, S.nfast, (void*)st);
+    if (rc) return rc;
+    ProfScope ps(ctx, VSB_K_ORB, st);
+    orb_select_fast_kernel<<<zc, 256, 0, st>>>(S.fxy, S.fsc, S.nfast, fcap, w, h, 2 * nfeatures, S.sel, S.nsel);
+    VSB_LAUNCHED(ctx);
+    orb_harris_kernel<<<dim3(vsb_div_up(w * h / 4 + 16, 128), zc), 128, 0, st>>>(in, img_stride, pitch, S.sel, S.nsel, fcap, S.resp);
+    VSB_LAUNCHED(ctx);
+    orb_select_harris_kernel<<<zc, 256, 0, st>>>(S.sel, S.resp, S.nsel, fcap, nfeatures, cap, kp_xy, kp_resp, n_kp);
+    VSB_LAUNCHED(ctx);
+    orb_angle_kernel<<<dim3(vsb_div_up(cap, 8), zc), 256, 0, st>>>(in, img_stride, pitch, kp_xy, n_kp, cap, kp_angle);
+    VSB_LAUNCHED(ctx);
+    if (desc) {
+        orb_blur_kernel<<<dim3(vsb_div_up(w, BT), vsb_div_up(h, BT), zc), 256, 0, st>>>(in, img_stride, pitch, w, h, S.blurred);
+        VSB_LAUNCHED(ctx);
+        orb_describe_kernel<<<dim3(vsb_div_up(cap, 8), zc), 256, 0, st>>>(S.blurred, w, h, kp_xy, kp_angle, n_kp, cap, desc);
+        VSB_LAUNCHED(ctx);
+    }
+    return VSB_OK;
+}
+
 }  // namespace
 
 // ORB key points + descriptors of `count` frames, one pyramid level (cv::ORB::create(nfeatures, 1.2f, 1, 31, 0, 2,
@@ -328,46 +446,87 @@ extern "C" int vsb_orb_detect_compute(vsb_ctx_t* ctx, const uint8_t* img, int64_
     cudaStream_t st = (cudaStream_t)stream;
     // FAST corners per frame: 3x3 non-maximum suppression leaves at most one corner per 2x2 block, so w*h/4 can never
     // overflow (dense noise does reach a quarter of that); the batch is processed in chunks that keep the scratch bounded
-    const int fcap = w * h / 4 + 16;
-    const size_t per_frame = (size_t)fcap * 24 + (desc ? (size_t)w * h : 0);
+    const size_t per_frame = orb_scratch_bytes(1, w, h, desc != nullptr);
     const int chunk = (int)max((size_t)1, min((size_t)count, ((size_t)384 << 20) / per_frame));
-    auto al = [](size_t b) { return (b + 255) & ~(size_t)255; };
-    const size_t b_fxy = al((size_t)chunk * fcap * 2 * sizeof(int32_t)), b_fsc = al((size_t)chunk * fcap * sizeof(int32_t));
-    const size_t b_sel = b_fxy, b_resp = al((size_t)chunk * fcap * sizeof(float)), b_n = al((size_t)chunk * sizeof(int32_t));
-    const size_t b_blur = desc ? al((size_t)chunk * w * h) : 0;
     void* scratch = nullptr;
-    int rc = vsb_scratch2_reserve(ctx, b_fxy + b_fsc + b_sel + b_resp + 2 * b_n + b_blur + 256, &scratch);
+    int rc = vsb_scratch2_reserve(ctx, orb_scratch_bytes(chunk, w, h, desc != nullptr) + 256, &scratch);
     if (rc) return rc;
     uint8_t* p = static_cast<uint8_t*>(scratch);
-    int32_t* fxy = reinterpret_cast<int32_t*>(p); p += b_fxy;
-    int32_t* fsc = reinterpret_cast<int32_t*>(p); p += b_fsc;
-    int32_t* sel = reinterpret_cast<int32_t*>(p); p += b_sel;
-    float* resp = reinterpret_cast<float*>(p); p += b_resp;
-    int32_t* nfast = reinterpret_cast<int32_t*>(p); p += b_n;
-    int32_t* nsel = reinterpret_cast<int32_t*>(p); p += b_n;
-    uint8_t* blurred = p;
+    const OrbScratch S = orb_scratch_carve(p, chunk, w, h, desc != nullptr);
     for (int z0 = 0; z0 < count; z0 += chunk) {
         const int zc = min(chunk, count - z0);
-        const uint8_t* in = img + (size_t)z0 * img_stride;
-        rc = vsb_fast_detect(ctx, in, img_stride, pitch, w, h, zc, fast_threshold, 1, fcap, fxy, fsc, nfast, stream);
+        rc = orb_one_level(ctx, S, img + (size_t)z0 * img_stride, img_stride, pitch, w, h, zc, nfeatures, fast_threshold, cap,
+                           kp_xy + (size_t)z0 * cap * 2, kp_resp + (size_t)z0 * cap, kp_angle + (size_t)z0 * cap,
+                           desc ? desc + (size_t)z0 * cap * 32 : nullptr, n_kp + z0, st);
         if (rc) return rc;
-        ProfScope ps(ctx, VSB_K_ORB, st);
-        orb_select_fast_kernel<<<zc, 256, 0, st>>>(fxy, fsc, nfast, fcap, w, h, 2 * nfeatures, sel, nsel);
-        VSB_LAUNCHED(ctx);
-        orb_harris_kernel<<<dim3(vsb_div_up(fcap, 128), zc), 128, 0, st>>>(in, img_stride, pitch, sel, nsel, fcap, resp);
-        VSB_LAUNCHED(ctx);
-        orb_select_harris_kernel<<<zc, 256, 0, st>>>(sel, resp, nsel, fcap, nfeatures, cap, kp_xy + (size_t)z0 * cap * 2,
-                                                      kp_resp + (size_t)z0 * cap, n_kp + z0);
-        VSB_LAUNCHED(ctx);
-        orb_angle_kernel<<<dim3(vsb_div_up(cap, 8), zc), 256, 0, st>>>(in, img_stride, pitch, kp_xy + (size_t)z0 * cap * 2,
-                                                                         n_kp + z0, cap, kp_angle + (size_t)z0 * cap);
-        VSB_LAUNCHED(ctx);
-        if (desc) {
-            orb_blur_kernel<<<dim3(vsb_div_up(w, BT), vsb_div_up(h, BT), zc), 256, 0, st>>>(in, img_stride, pitch, w, h, blurred);
+    }
+    return VSB_OK;
+}
+
+// cv::ORB with its scale pyramid (the reference's ORB::create(n): nlevels 8, scale factor 1.2).  See include/vislam_b200.h.
+extern "C" int vsb_orb_detect_compute_pyr(vsb_ctx_t* ctx, const uint8_t* img, int64_t img_stride, int pitch, int w, int h,
+                                          int count, int nfeatures, float scale_factor, int nlevels, int fast_threshold, int cap,
+                                          float* kp_xy, int32_t* kp_octave, float* kp_resp, float* kp_angle, uint8_t* desc,
+                                          int32_t* n_kp, void* stream) {
+    if (!ctx || !img || !kp_xy || !kp_resp || !kp_angle || !n_kp) return VSB_ERR_INVALID;
+    if (w <= 2 * ORB_EDGE || h <= 2 * ORB_EDGE || pitch < w || count < 0 || cap <= 0 || nfeatures < 0) return VSB_ERR_INVALID;
+    if (fast_threshold < 0 || fast_threshold > 255 || nlevels < 1 || nlevels > 32 || !(scale_factor > 1.f)) return VSB_ERR_INVALID;
+    if (count == 0) return VSB_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    // per-level budget and scale exactly as cv::ORB computes them (orb.cpp); the factor is a float stored in a double
+    int budget[32];
+    {
+        const float factor = (float)(1.0 / (double)scale_factor);
+        float nd = nfeatures * (1 - factor) / (1 - (float)pow((double)factor, (double)nlevels));
+        int sum = 0;
+        for (int l = 0; l < nlevels - 1; l++) { budget[l] = (int)lrintf(nd); sum += budget[l]; nd *= factor; }
+        budget[nlevels - 1] = nfeatures - sum > 0 ? nfeatures - sum : 0;
+    }
+    const bool describe = desc != nullptr;
+    const size_t tmp_frame = orb_al((size_t)cap * 8) + 2 * orb_al((size_t)cap * 4) + (describe ? orb_al((size_t)cap * 32) : 0);
+    const size_t per_frame = orb_scratch_bytes(1, w, h, describe) + 2 * orb_al((size_t)w * h) + tmp_frame + 256;
+    const int chunk = (int)max((size_t)1, min((size_t)count, ((size_t)384 << 20) / per_frame));
+    const size_t b_img = orb_al((size_t)chunk * w * h);
+    void* scratch = nullptr;
+    int rc = vsb_scratch2_reserve(ctx, orb_scratch_bytes(chunk, w, h, describe) + 2 * b_img + chunk * tmp_frame + orb_al((size_t)chunk * 4) + 1024,
+                                  &scratch);
+    if (rc) return rc;
+    uint8_t* p = static_cast<uint8_t*>(scratch);
+    const OrbScratch S = orb_scratch_carve(p, chunk, w, h, describe);
+    uint8_t* lvl_img[2];
+    lvl_img[0] = p; p += b_img;
+    lvl_img[1] = p; p += b_img;
+    int32_t* lxy = reinterpret_cast<int32_t*>(p); p += orb_al((size_t)chunk * cap * 8);
+    float* lresp = reinterpret_cast<float*>(p); p += orb_al((size_t)chunk * cap * 4);
+    float* langle = reinterpret_cast<float*>(p); p += orb_al((size_t)chunk * cap * 4);
+    uint8_t* ldesc = nullptr;
+    if (describe) { ldesc = p; p += orb_al((size_t)chunk * cap * 32); }
+    int32_t* ln = reinterpret_cast<int32_t*>(p);
+    for (int z0 = 0; z0 < count; z0 += chunk) {
+        const int zc = min(chunk, count - z0);
+        VSB_CUDA(ctx, cudaMemsetAsync(n_kp + z0, 0, (size_t)zc * sizeof(int32_t), st));
+        const uint8_t* cur = img + (size_t)z0 * img_stride;
+        int64_t cur_stride = img_stride;
+        int cw = w, ch = h, cp = pitch;
+        for (int l = 0; l < nlevels; l++) {
+            const float scale = (float)pow((double)scale_factor, (double)l);
+            if (l > 0) {
+                const int nw = (int)lrintf((float)w / scale), nh = (int)lrintf((float)h / scale);
+                if (nw <= 2 * ORB_EDGE || nh <= 2 * ORB_EDGE) break;       // the border filter leaves nothing from here on
+                uint8_t* dst = lvl_img[l & 1];
+                ProfScope ps(ctx, VSB_K_ORB, st);
+                orb_resize_kernel<<<dim3(vsb_div_up(nw, 32), vsb_div_up(nh, 8), zc), 256, 0, st>>>(cur, cur_stride, cp, cw, ch, dst, nw, nh);
+                VSB_LAUNCHED(ctx);
+                cur = dst; cur_stride = (int64_t)nw * nh; cw = nw; ch = nh; cp = nw;
+            }
+            rc = orb_one_level(ctx, S, cur, cur_stride, cp, cw, ch, zc, budget[l], fast_threshold, cap, lxy, lresp, langle, ldesc, ln, st);
+            if (rc) return rc;
+            ProfScope ps(ctx, VSB_K_ORB, st);
+            orb_append_kernel<<<dim3(vsb_div_up(cap, 256), zc), 256, 0, st>>>(
+                lxy, lresp, langle, ldesc, ln, cap, scale, l, kp_xy + (size_t)z0 * cap * 2, kp_octave ? kp_octave + (size_t)z0 * cap : nullptr,
+                kp_resp + (size_t)z0 * cap, kp_angle + (size_t)z0 * cap, desc ? desc + (size_t)z0 * cap * 32 : nullptr, n_kp + z0);
             VSB_LAUNCHED(ctx);
-            orb_describe_kernel<<<dim3(vsb_div_up(cap, 8), zc), 256, 0, st>>>(blurred, w, h, kp_xy + (size_t)z0 * cap * 2,
-                                                                              kp_angle + (size_t)z0 * cap, n_kp + z0, cap,
-                                                                              desc + (size_t)z0 * cap * 32);
+            orb_advance_kernel<<<vsb_div_up(zc, 256), 256, 0, st>>>(n_kp + z0, ln, zc);
             VSB_LAUNCHED(ctx);
         }
     }

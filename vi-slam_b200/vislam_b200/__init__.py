@@ -56,7 +56,7 @@ EXPORTS = [
     "vsb_gather_keypoints", "vsb_init_pyramid", "vsb_gn_default_opts", "vsb_gn_solve", "vsb_initial_pose",
     "vsb_se3_mul", "vsb_tracker_create", "vsb_tracker_destroy", "vsb_track_sequence",
     "vsb_track_sequence_host", "vsb_track_pairs", "vsb_kernel_count", "vsb_kernel_name", "vsb_profile_enable",
-    "vsb_profile_reset", "vsb_profile_read", "vsb_popc_peak", "vsb_tracker_stats", "vsb_tracker_host_traffic", "vsb_fast_detect", "vsb_orb_detect_compute",
+    "vsb_profile_reset", "vsb_profile_read", "vsb_popc_peak", "vsb_tracker_stats", "vsb_tracker_host_traffic", "vsb_fast_detect", "vsb_orb_detect_compute", "vsb_orb_detect_compute_pyr",
     "vsb_malloc", "vsb_free", "vsb_host_alloc", "vsb_host_free", "vsb_upload", "vsb_upload_2d", "vsb_download",
     "vsb_copy", "vsb_memset", "vsb_stream_create", "vsb_stream_destroy", "vsb_stream_sync",
     "vsb_nn_filter", "vsb_sym_matches", "vsb_sort_keys", "vsb_grid_best", "vsb_warp_se3", "vsb_se3_exp",
@@ -123,6 +123,7 @@ def lib():
     L.vsb_tracker_host_traffic.argtypes = [vp, C.POINTER(C.c_longlong)]
     L.vsb_fast_detect.argtypes = [vp, vp, i64, i32, i32, i32, i32, i32, i32, i32, vp, vp, vp, vp]
     L.vsb_orb_detect_compute.argtypes = [vp, vp, i64, i32, i32, i32, i32, i32, i32, i32, vp, vp, vp, vp, vp, vp]
+    L.vsb_orb_detect_compute_pyr.argtypes = [vp, vp, i64, i32, i32, i32, i32, i32, C.c_float, i32, i32, i32, vp, vp, vp, vp, vp, vp, vp]
     _lib = L
     return L
 
@@ -307,6 +308,24 @@ class Context:
                                            _ptr(xy), _ptr(resp), _ptr(ang), _ptr(desc) if describe else None, _ptr(n),
                                            _stream_ptr(stream)), self.handle)
         return xy, resp, ang, desc, n
+
+    def orb_detect_compute_pyr(self, img, nfeatures=1000, scale_factor=1.2, nlevels=8, fast_threshold=20, cap=None,
+                               describe=True, stream=None):
+        """cv::ORB with its scale pyramid: kp_xy [B,cap,2] f32, octave [B,cap] i32, response, angle_deg, desc, n_kp."""
+        t = self.torch
+        img = img.contiguous()
+        B, h, w = img.shape
+        cap = cap or 2 * nfeatures
+        xy = t.zeros((B, cap, 2), dtype=t.float32, device=self.dev)
+        octv = t.zeros((B, cap), dtype=t.int32, device=self.dev)
+        resp = t.zeros((B, cap), dtype=t.float32, device=self.dev)
+        ang = t.zeros((B, cap), dtype=t.float32, device=self.dev)
+        desc = t.zeros((B, cap, 32), dtype=t.uint8, device=self.dev) if describe else None
+        n = t.zeros((B,), dtype=t.int32, device=self.dev)
+        check(lib().vsb_orb_detect_compute_pyr(self.handle, _ptr(img), w * h, w, w, h, B, int(nfeatures), float(scale_factor),
+                                               int(nlevels), int(fast_threshold), cap, _ptr(xy), _ptr(octv), _ptr(resp), _ptr(ang),
+                                               _ptr(desc) if describe else None, _ptr(n), _stream_ptr(stream)), self.handle)
+        return xy, octv, resp, ang, desc, n
 
     # ---- Camera --------------------------------------------------------------------------------
     def pyramid_build(self, img, layout, stream=None):
