@@ -8,10 +8,10 @@
 //                       comparisons and the "9 contiguous" test run on packed bytes (SWAR), corners get their score from
 //                       sliding-window minima.  Writes score + 1 per pixel (0 = no corner): one byte read, one written.
 //   fast_count4_kernel  one warp per image row, 4 pixels per lane: 3x3 suppression on packed bytes, the row's corner count
-//                       (fast_count_kernel: byte-wise variant for widths that are not a multiple of 4).
+//                       (score rows are padded to a multiple of 4 bytes, so every width takes this path).
 //   fast_scan_kernel    exclusive scan of the row counts of each frame (row-major order needs the offsets).
 //   fast_write4_kernel  suppression again (cheaper than a flag image), warp scan, ordered write of (x, y, score) while the
-//                       slot is below the caller's capacity (fast_write_kernel: byte-wise variant).
+//                       slot is below the caller's capacity.
 #include "common.cuh"
 
 namespace {
@@ -71,14 +71,14 @@ constexpr int FT_WORDS = 18, FT_PITCH = 48;
 
 __global__ void __launch_bounds__(256, 4)
 fast_score_kernel(const uint8_t* __restrict__ img, long long img_stride, int pitch, int w, int h, int threshold,
-                  uint8_t* __restrict__ score1) {
+                  uint8_t* __restrict__ score1, int sw) {
     __shared__ uint32_t s[FT_SH][FT_PITCH];
     __shared__ uint16_t s_list[FT_W * FT_H];                            // tile-local (y << 6 | x) of the corners found
     __shared__ int s_count;
     if (threadIdx.x == 0) s_count = 0;
     const int frame = blockIdx.z;
     const uint8_t* in = img + (size_t)frame * img_stride;
-    uint8_t* out = score1 + (size_t)frame * w * h;
+    uint8_t* out = score1 + (size_t)frame * sw * h;      // score rows are sw = round_up(w, 4) bytes apart; the pad stays 0
     const int x0 = blockIdx.x * FT_W, y0 = blockIdx.y * FT_H;
     const bool aligned_in = ((reinterpret_cast<uintptr_t>(in) | (uintptr_t)pitch) & 3u) == 0;
     for (int p = threadIdx.x; p < FT_SH * FT_WORDS; p += 256) {
@@ -144,16 +144,8 @@ fast_score_kernel(const uint8_t* __restrict__ img, long long img_stride, int pit
         corner = ((b0 | b1 | b2) | b3) & 0x80808080u;
     }
     // every pixel gets its byte now (0 = no corner); the few that are corners are queued for the score pass below
-    uint8_t* o = out + (size_t)y * w + x;
-    if (in_image) {
-        if ((w & 3) == 0) {
-            *reinterpret_cast<uint32_t*>(o) = 0u;
-        } else {
-#pragma unroll
-            for (int j = 0; j < 4; j++)
-                if (x + j < w) o[j] = 0;
-        }
-    }
+    uint8_t* o = out + (size_t)y * sw + x;
+    if (in_image) *reinterpret_cast<uint32_t*>(o) = 0u;                 // x is a multiple of 4 and x + 3 < sw
     if (corner) {
 #pragma unroll
         for (int j = 0; j < 4; j++)
@@ -175,45 +167,7 @@ fast_score_kernel(const uint8_t* __restrict__ img, long long img_stride, int pit
             neg[k] = -d[k];
         }
         const int best = max(best_arc_min(d), best_arc_min(neg));       // > threshold for a corner; score + 1, in 1..255
-        out[(size_t)(y0 + ly) * w + x0 + lx] = (uint8_t)best;
-    }
-}
-
-__device__ __forceinline__ bool fast_keep(const uint8_t* __restrict__ sc, int w, int x, int y, int nonmax, int& score) {
-    const int s1 = sc[(size_t)y * w + x];
-    if (!s1) return false;
-    score = s1 - 1;
-    if (!nonmax) return true;
-    // interior corners only exist for 3 <= x < w-3, 3 <= y < h-3, so all 8 neighbours are inside the image
-    const uint8_t* r0 = sc + (size_t)(y - 1) * w + x;
-    const uint8_t* r1 = sc + (size_t)y * w + x;
-    const uint8_t* r2 = sc + (size_t)(y + 1) * w + x;
-    int m = max(max(r0[-1], r0[0]), r0[1]);
-    m = max(m, max(r1[-1], r1[1]));
-    m = max(m, max(max(r2[-1], r2[0]), r2[1]));
-    const int other = m ? m - 1 : 0;                                   // "no corner" counts as score 0
-    return score > other;
-}
-
-__global__ void __launch_bounds__(256)
-fast_count_kernel(const uint8_t* __restrict__ score1, int w, int h, int nonmax, int32_t* __restrict__ row_count) {
-    const int y = blockIdx.x, frame = blockIdx.y;
-    const uint8_t* sc = score1 + (size_t)frame * w * h;
-    int n = 0;
-    if (y >= 3 && y < h - 3)
-        for (int x = 3 + threadIdx.x; x < w - 3; x += 256) {
-            int sco;
-            n += fast_keep(sc, w, x, y, nonmax, sco) ? 1 : 0;
-        }
-    __shared__ int s_part[8];
-#pragma unroll
-    for (int off = 16; off >= 1; off >>= 1) n += __shfl_down_sync(0xffffffffu, n, off);
-    if ((threadIdx.x & 31) == 0) s_part[threadIdx.x >> 5] = n;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        int t = 0;
-        for (int i = 0; i < 8; i++) t += s_part[i];
-        row_count[(size_t)frame * h + y] = t;
+        out[(size_t)(y0 + ly) * sw + x0 + lx] = (uint8_t)best;
     }
 }
 
@@ -239,48 +193,7 @@ fast_scan_kernel(const int32_t* __restrict__ row_count, int h, int32_t* __restri
     for (int i = b; i < e; i++) { o[i] = acc; acc += c[i]; }
 }
 
-__global__ void __launch_bounds__(256)
-fast_write_kernel(const uint8_t* __restrict__ score1, int w, int h, int nonmax, const int32_t* __restrict__ row_offset,
-                  int cap, int32_t* __restrict__ kp_xy, int32_t* __restrict__ kp_score) {
-    const int y = blockIdx.x, frame = blockIdx.y;
-    if (y < 3 || y >= h - 3) return;
-    const uint8_t* sc = score1 + (size_t)frame * w * h;
-    int base = row_offset[(size_t)frame * h + y];
-    if (base >= cap) return;
-    int32_t* oxy = kp_xy + (size_t)frame * cap * 2;
-    int32_t* osc = kp_score + (size_t)frame * cap;
-    __shared__ int s_warp[8];
-    __shared__ int s_total;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    for (int xb = 3; xb < w - 3; xb += 256) {
-        const int x = xb + threadIdx.x;
-        int sco = 0;
-        const bool keep = x < w - 3 && fast_keep(sc, w, x, y, nonmax, sco);
-        const unsigned ballot = __ballot_sync(0xffffffffu, keep);
-        const int in_warp = __popc(ballot & ((1u << lane) - 1u));
-        if (lane == 0) s_warp[warp] = __popc(ballot);
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            int acc = 0;
-            for (int i = 0; i < 8; i++) { const int v = s_warp[i]; s_warp[i] = acc; acc += v; }
-            s_total = acc;
-        }
-        __syncthreads();
-        if (keep) {
-            const int slot = base + s_warp[warp] + in_warp;
-            if (slot < cap) {
-                oxy[2 * slot] = x; oxy[2 * slot + 1] = y;
-                osc[slot] = nonmax ? sco : 0;
-            }
-        }
-        base += s_total;
-        __syncthreads();
-        if (base >= cap) return;
-    }
-}
-
-
-// ---- compaction, 4 pixels per lane (score rows 4-byte aligned: w % 4 == 0) -----------------------------------------------
+// ---- compaction, 4 pixels per lane (score rows are 4-byte aligned: their stride is round_up(w, 4)) -----------------------------------------------
 // One warp per image row.  A lane looks at 4 consecutive pixels: their score bytes and the words left / right of them for
 // the rows y-1, y, y+1; the 3x3 neighbour maximum and the "strictly greater" test run on all four bytes at once
 // (__vmaxu4 / __vcmpgtu4).  score1 bytes are score + 1 with 0 = no corner, so "keep" is  cur > max(neighbours, 1).
@@ -375,7 +288,10 @@ extern "C" int vsb_fast_detect(vsb_ctx_t* ctx, const uint8_t* img, int64_t img_s
     if (w <= 0 || h <= 0 || pitch < w || count < 0 || cap < 0 || threshold < 0 || threshold > 255) return VSB_ERR_INVALID;
     if (count == 0) return VSB_OK;
     cudaStream_t st = (cudaStream_t)stream;
-    const size_t img_bytes = ((size_t)count * w * h + 255) & ~(size_t)255;
+    // score rows are padded to a multiple of 4 bytes (zero pad = "no corner"), so the 4-pixels-per-lane compaction kernels
+    // serve every width; words that straddle a row end only ever see border / pad zeros
+    const int sw = (w + 3) & ~3;
+    const size_t img_bytes = ((size_t)count * sw * h + 255) & ~(size_t)255;
     const size_t rows_bytes = ((size_t)count * h * sizeof(int32_t) + 255) & ~(size_t)255;
     void* scratch = nullptr;
     int rc = vsb_scratch_reserve(ctx, img_bytes + 2 * rows_bytes + 256, &scratch);
@@ -386,27 +302,21 @@ extern "C" int vsb_fast_detect(vsb_ctx_t* ctx, const uint8_t* img, int64_t img_s
     for (int z0 = 0; z0 < count; z0 += 65535) {
         const int zc = count - z0 < 65535 ? count - z0 : 65535;
         const uint8_t* in = img + (size_t)z0 * img_stride;
-        uint8_t* sc = score1 + (size_t)z0 * w * h;
+        uint8_t* sc = score1 + (size_t)z0 * sw * h;
         {
             ProfScope ps(ctx, VSB_K_FAST_SCORE, st);
             fast_score_kernel<<<dim3(vsb_div_up(w, FT_W), vsb_div_up(h, FT_H), zc), 256, 0, st>>>(in, img_stride, pitch, w, h,
-                                                                                                 threshold, sc);
+                                                                                                 threshold, sc, sw);
             VSB_LAUNCHED(ctx);
         }
         ProfScope ps(ctx, VSB_K_FAST_COMPACT, st);
-        const bool words = (w % 4) == 0;                   // 4 pixels per lane needs 4-byte aligned score rows
-        if (words) fast_count4_kernel<<<dim3(vsb_div_up(h, 8), zc), 256, 0, st>>>(sc, w, h, nonmax, row_count + (size_t)z0 * h);
-        else fast_count_kernel<<<dim3(h, zc), 256, 0, st>>>(sc, w, h, nonmax, row_count + (size_t)z0 * h);
+        fast_count4_kernel<<<dim3(vsb_div_up(h, 8), zc), 256, 0, st>>>(sc, sw, h, nonmax, row_count + (size_t)z0 * h);
         VSB_LAUNCHED(ctx);
         fast_scan_kernel<<<zc, 256, 0, st>>>(row_count + (size_t)z0 * h, h, row_offset + (size_t)z0 * h, n_kp + z0);
         VSB_LAUNCHED(ctx);
         if (cap > 0) {
-            if (words)
-                fast_write4_kernel<<<dim3(vsb_div_up(h, 8), zc), 256, 0, st>>>(sc, w, h, nonmax, row_offset + (size_t)z0 * h, cap,
-                                                                               kp_xy + (size_t)z0 * cap * 2, kp_score + (size_t)z0 * cap);
-            else
-                fast_write_kernel<<<dim3(h, zc), 256, 0, st>>>(sc, w, h, nonmax, row_offset + (size_t)z0 * h, cap,
-                                                                kp_xy + (size_t)z0 * cap * 2, kp_score + (size_t)z0 * cap);
+            fast_write4_kernel<<<dim3(vsb_div_up(h, 8), zc), 256, 0, st>>>(sc, sw, h, nonmax, row_offset + (size_t)z0 * h, cap,
+                                                                           kp_xy + (size_t)z0 * cap * 2, kp_score + (size_t)z0 * cap);
             VSB_LAUNCHED(ctx);
         }
     }

@@ -99,8 +99,8 @@ __global__ void __launch_bounds__(128)
 orb_harris_kernel(const uint8_t* __restrict__ img, long long img_stride, int pitch, const int32_t* __restrict__ sel_xy,
                   const int32_t* __restrict__ n_sel, int fcap, float* __restrict__ resp) {
     const int f = blockIdx.y;
-    const int i = blockIdx.x * 128 + threadIdx.x;
-    if (i >= n_sel[f]) return;
+    const int n = n_sel[f];
+    for (int i = blockIdx.x * 128 + threadIdx.x; i < n; i += gridDim.x * 128) {
     const int x0 = sel_xy[((size_t)f * fcap + i) * 2], y0 = sel_xy[((size_t)f * fcap + i) * 2 + 1];
     const uint8_t* base = img + (size_t)f * img_stride + (size_t)(y0 - 4) * pitch + (x0 - 4);
     // 9x9 neighbourhood, three rows at a time
@@ -129,6 +129,7 @@ orb_harris_kernel(const uint8_t* __restrict__ img, long long img_stride, int pit
     const float t3 = __fmul_rn(__fmul_rn(0.04f, s), s);
     const float d = __fsub_rn(__fsub_rn(__fmul_rn(fa, fb), __fmul_rn(fc, fc)), t3);
     resp[(size_t)f * fcap + i] = __fmul_rn(d, s4);
+    }
 }
 
 // ---- stage 3: retainBest(n) on the float response (radix select of the n-th largest), order preserved -------------------
@@ -216,9 +217,9 @@ __device__ __forceinline__ float fast_atan2_deg(float y, float x) {
 __global__ void __launch_bounds__(256)
 orb_angle_kernel(const uint8_t* __restrict__ img, long long img_stride, int pitch, const int32_t* __restrict__ kp_xy,
                  const int32_t* __restrict__ n_kp, int cap, float* __restrict__ kp_angle) {
-    const int f = blockIdx.y;
-    const int k = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
-    if (k >= min(n_kp[f], cap)) return;
+    const int f = blockIdx.y, lane = threadIdx.x & 31;
+    const int nk = min(n_kp[f], cap);
+    for (int k = blockIdx.x * 8 + (threadIdx.x >> 5); k < nk; k += gridDim.x * 8) {
     const int x0 = kp_xy[((size_t)f * cap + k) * 2], y0 = kp_xy[((size_t)f * cap + k) * 2 + 1];
     const uint8_t* center = img + (size_t)f * img_stride + (size_t)y0 * pitch + x0;
     // lane u-index: u = lane - 15 for lanes 0..30 (31 columns); rows v = 0..15 handled by every lane for its column
@@ -239,6 +240,7 @@ orb_angle_kernel(const uint8_t* __restrict__ img, long long img_stride, int pitc
 #pragma unroll
     for (int o = 16; o >= 1; o >>= 1) { m01 += __shfl_down_sync(0xffffffffu, m01, o); m10 += __shfl_down_sync(0xffffffffu, m10, o); }
     if (lane == 0) kp_angle[(size_t)f * cap + k] = fast_atan2_deg((float)m01, (float)m10);
+    }
 }
 
 // ---- stage 5: the blur ORB applies before describing: 7x7 sigma 2, generic float separable filter, reflect-101 ---------
@@ -289,9 +291,9 @@ orb_describe_kernel(const uint8_t* __restrict__ blurred, int w, int h, const int
     __shared__ signed char s_pat[1024];
     for (int i = threadIdx.x; i < 1024; i += 256) s_pat[i] = c_pattern[i];
     __syncthreads();
-    const int f = blockIdx.y;
-    const int k = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
-    if (k >= min(n_kp[f], cap)) return;
+    const int f = blockIdx.y, lane = threadIdx.x & 31;
+    const int nk = min(n_kp[f], cap);
+    for (int k = blockIdx.x * 8 + (threadIdx.x >> 5); k < nk; k += gridDim.x * 8) {
     const int x0 = kp_xy[((size_t)f * cap + k) * 2], y0 = kp_xy[((size_t)f * cap + k) * 2 + 1];
     float angle = kp_angle[(size_t)f * cap + k];
     angle = __fmul_rn(angle, (float)(3.14159265358979323846 / 180.f));
@@ -312,6 +314,7 @@ orb_describe_kernel(const uint8_t* __restrict__ blurred, int w, int h, const int
         val |= (v[0] < v[1]) << i;
     }
     desc[((size_t)f * cap + k) * 32 + lane] = (uint8_t)val;
+    }
 }
 
 // ---- the scale pyramid: cv::resize(.., INTER_LINEAR_EXACT) for 8-bit images (resize_bitExact, 8.8 fixed point) -----------
@@ -328,14 +331,21 @@ __device__ __forceinline__ void lin_exact_coeff(int v, int ssize, int dsize, int
         edge = -1;
     }
 }
+// coefficient table of one axis: (offset, 8.8 weight of the second sample, edge flag) per destination index
+__global__ void orb_resize_coeff_kernel(int sw, int sh, int dw, int dh, int4* __restrict__ tab) {
+    const int i = blockIdx.x * 256 + threadIdx.x;
+    if (i >= dw + dh) return;
+    int ofs, c1, edge;
+    if (i < dw) lin_exact_coeff(i, sw, dw, ofs, c1, edge); else lin_exact_coeff(i - dw, sh, dh, ofs, c1, edge);
+    tab[i] = make_int4(ofs, c1, edge, 0);
+}
 __global__ void __launch_bounds__(256)
 orb_resize_kernel(const uint8_t* __restrict__ src, long long src_stride, int spitch, int sw, int sh, uint8_t* __restrict__ dst,
-                  int dw, int dh) {
+                  int dw, int dh, const int4* __restrict__ tab) {
     const int x = blockIdx.x * 32 + (threadIdx.x & 31), y = blockIdx.y * 8 + (threadIdx.x >> 5), f = blockIdx.z;
     if (x >= dw || y >= dh) return;
-    int ox, ax, ex, oy, ay, ey;
-    lin_exact_coeff(x, sw, dw, ox, ax, ex);
-    lin_exact_coeff(y, sh, dh, oy, ay, ey);
+    const int4 tx = __ldg(tab + x), ty = __ldg(tab + dw + y);
+    const int ox = tx.x, ax = tx.y, ex = tx.z, oy = ty.x, ay = ty.y, ey = ty.z;
     const uint8_t* img = src + (size_t)f * src_stride;
     const int y0 = ey < 0 ? 0 : oy, y1 = ey != 0 ? y0 : oy + 1;
     const uint8_t* r0 = img + (size_t)y0 * spitch;
@@ -417,16 +427,16 @@ int orb_one_level(vsb_ctx_t* ctx, const OrbScratch& S, const uint8_t* in, int64_
     ProfScope ps(ctx, VSB_K_ORB, st);
     orb_select_fast_kernel<<<zc, 256, 0, st>>>(S.fxy, S.fsc, S.nfast, fcap, w, h, 2 * nfeatures, S.sel, S.nsel);
     VSB_LAUNCHED(ctx);
-    orb_harris_kernel<<<dim3(vsb_div_up(w * h / 4 + 16, 128), zc), 128, 0, st>>>(in, img_stride, pitch, S.sel, S.nsel, fcap, S.resp);
+    orb_harris_kernel<<<dim3(min(vsb_div_up(w * h / 4 + 16, 128), max(8, vsb_div_up(4 * nfeatures, 128))), zc), 128, 0, st>>>(in, img_stride, pitch, S.sel, S.nsel, fcap, S.resp);
     VSB_LAUNCHED(ctx);
     orb_select_harris_kernel<<<zc, 256, 0, st>>>(S.sel, S.resp, S.nsel, fcap, nfeatures, cap, kp_xy, kp_resp, n_kp);
     VSB_LAUNCHED(ctx);
-    orb_angle_kernel<<<dim3(vsb_div_up(cap, 8), zc), 256, 0, st>>>(in, img_stride, pitch, kp_xy, n_kp, cap, kp_angle);
+    orb_angle_kernel<<<dim3(min(vsb_div_up(cap, 8), max(4, vsb_div_up(nfeatures + 64, 8))), zc), 256, 0, st>>>(in, img_stride, pitch, kp_xy, n_kp, cap, kp_angle);
     VSB_LAUNCHED(ctx);
     if (desc) {
         orb_blur_kernel<<<dim3(vsb_div_up(w, BT), vsb_div_up(h, BT), zc), 256, 0, st>>>(in, img_stride, pitch, w, h, S.blurred);
         VSB_LAUNCHED(ctx);
-        orb_describe_kernel<<<dim3(vsb_div_up(cap, 8), zc), 256, 0, st>>>(S.blurred, w, h, kp_xy, kp_angle, n_kp, cap, desc);
+        orb_describe_kernel<<<dim3(min(vsb_div_up(cap, 8), max(4, vsb_div_up(nfeatures + 64, 8))), zc), 256, 0, st>>>(S.blurred, w, h, kp_xy, kp_angle, n_kp, cap, desc);
         VSB_LAUNCHED(ctx);
     }
     return VSB_OK;
@@ -488,7 +498,8 @@ extern "C" int vsb_orb_detect_compute_pyr(vsb_ctx_t* ctx, const uint8_t* img, in
     const int chunk = (int)max((size_t)1, min((size_t)count, ((size_t)384 << 20) / per_frame));
     const size_t b_img = orb_al((size_t)chunk * w * h);
     void* scratch = nullptr;
-    int rc = vsb_scratch2_reserve(ctx, orb_scratch_bytes(chunk, w, h, describe) + 2 * b_img + chunk * tmp_frame + orb_al((size_t)chunk * 4) + 1024,
+    int rc = vsb_scratch2_reserve(ctx, orb_scratch_bytes(chunk, w, h, describe) + 2 * b_img + chunk * tmp_frame + orb_al((size_t)chunk * 4) +
+                                       orb_al((size_t)(w + h) * sizeof(int4)) + 1024,
                                   &scratch);
     if (rc) return rc;
     uint8_t* p = static_cast<uint8_t*>(scratch);
@@ -501,7 +512,8 @@ extern "C" int vsb_orb_detect_compute_pyr(vsb_ctx_t* ctx, const uint8_t* img, in
     float* langle = reinterpret_cast<float*>(p); p += orb_al((size_t)chunk * cap * 4);
     uint8_t* ldesc = nullptr;
     if (describe) { ldesc = p; p += orb_al((size_t)chunk * cap * 32); }
-    int32_t* ln = reinterpret_cast<int32_t*>(p);
+    int32_t* ln = reinterpret_cast<int32_t*>(p); p += orb_al((size_t)chunk * 4);
+    int4* rz_tab = reinterpret_cast<int4*>(p);
     for (int z0 = 0; z0 < count; z0 += chunk) {
         const int zc = min(chunk, count - z0);
         VSB_CUDA(ctx, cudaMemsetAsync(n_kp + z0, 0, (size_t)zc * sizeof(int32_t), st));
@@ -515,7 +527,9 @@ extern "C" int vsb_orb_detect_compute_pyr(vsb_ctx_t* ctx, const uint8_t* img, in
                 if (nw <= 2 * ORB_EDGE || nh <= 2 * ORB_EDGE) break;       // the border filter leaves nothing from here on
                 uint8_t* dst = lvl_img[l & 1];
                 ProfScope ps(ctx, VSB_K_ORB, st);
-                orb_resize_kernel<<<dim3(vsb_div_up(nw, 32), vsb_div_up(nh, 8), zc), 256, 0, st>>>(cur, cur_stride, cp, cw, ch, dst, nw, nh);
+                orb_resize_coeff_kernel<<<vsb_div_up(nw + nh, 256), 256, 0, st>>>(cw, ch, nw, nh, rz_tab);
+                VSB_LAUNCHED(ctx);
+                orb_resize_kernel<<<dim3(vsb_div_up(nw, 32), vsb_div_up(nh, 8), zc), 256, 0, st>>>(cur, cur_stride, cp, cw, ch, dst, nw, nh, rz_tab);
                 VSB_LAUNCHED(ctx);
                 cur = dst; cur_stride = (int64_t)nw * nh; cw = nw; ch = nh; cp = nw;
             }
