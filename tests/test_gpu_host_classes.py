@@ -151,3 +151,35 @@ def test_visystem_gpu_sequence_vs_oracle(tmp_path, oracle, mirror_host, grad_ima
         np.testing.assert_array_equal(pts, ref["cands"][2])
         Kl = oracle.init_pyramid(w, h, *K)
         np.testing.assert_array_equal(_rd(d, "warp2.bin").reshape(-1, 4), oracle.warp(pts, poses[T - 2], Kl[2]))
+
+
+@pytest.mark.parametrize("gpu", [0, 1])
+def test_camera_orb_detector_vs_oracle(tmp_path, oracle, gpu):
+    """Camera / CameraGPU::detectAndComputeFeatures with the ORB detector = cv::ORB::create(200) / cuda::ORB::create(1000)
+    (src/Camera.cpp:127, src/CameraGPU.cpp:99) on the device: cv::KeyPoint fields and descriptors against the oracle."""
+    rng = np.random.default_rng(21)
+    w, h, T = 376, 240, 3
+    frames = []
+    for _ in range(T):
+        f = (rng.random((h, w)) * 255).astype(np.float32)
+        f = (f + np.roll(f, 1, 0) + np.roll(f, 1, 1) + np.roll(f, (1, 1), (0, 1))) / 4
+        frames.append(f.astype(np.uint8))
+    frames = np.stack(frames)
+    d = str(tmp_path)
+    frames.tofile(os.path.join(d, "frames.bin"))
+    _write_meta(d, frames=T, w=w, h=h, gpu=gpu)
+    out = subprocess.run([_runner(), "orb", d], capture_output=True, text=True)
+    assert out.returncode == 0, out.stdout + out.stderr
+    n = 1000 if gpu else 200
+    for i in range(T):
+        kp = _rd(d, f"orb_kp{i}.bin").reshape(-1, 6)
+        desc = _rd(d, f"orb_desc{i}.bin", np.uint8).reshape(-1, 32)
+        xy, octv, resp, ang, odesc = oracle.orb_detect_compute_pyr(frames[i], n)
+        assert len(kp) == len(xy) >= n // 2
+        np.testing.assert_array_equal(kp[:, :2], xy)
+        np.testing.assert_array_equal(kp[:, 5].astype(np.int32), octv)
+        np.testing.assert_array_equal(kp[:, 4], resp)
+        np.testing.assert_array_equal(kp[:, 3], ang)
+        size = np.array([np.float32(31.0) * np.float32(oracle.lib().vso_orb_level_scale(1.2, int(o))) for o in octv], np.float32)
+        np.testing.assert_array_equal(kp[:, 2], size)
+        np.testing.assert_array_equal(desc, odesc)

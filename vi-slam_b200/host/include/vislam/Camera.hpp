@@ -3,9 +3,13 @@
 // (packed-pyramid layout of include/vislam_b200.h); the reference's public cv::Mat vectors are filled from the
 // device when Camera::mirror_host is set (default on: a caller that reads frame->grayImage[l] keeps working).
 //
-// Feature detection / description (Camera::detectFeatures, detectAndComputeFeatures — OpenCV ORB/SURF/KAZE) is
-// upstream of the hot path and not part of this library: features enter through
-// Camera::setFeatures or a Camera::featureProvider callback, and the detect* methods report what was provided.
+// Feature detection / description (Camera::detectFeatures, detectAndComputeFeatures): with the ORB
+// detector (USE_ORB, what the reference's CPU and GPU front ends select for binary descriptors) the frame's level-0 image,
+// already on the device, goes through vsb_orb_detect_compute_pyr — cv::ORB::create(orb_nfeatures) exactly (8 levels, factor
+// 1.2; 200 features in Camera as src/Camera.cpp:127, 1000 in CameraGPU as src/CameraGPU.cpp:99), key points level by level in
+// row-major order.  The other detectors (KAZE/AKAZE/SIFT/SURF) are not part of this library: their features enter through
+// Camera::setFeatures or a Camera::featureProvider callback (either also overrides ORB), and the detect* methods report what
+// was provided.
 #ifndef VISLAM_CAMERA_HPP_
 #define VISLAM_CAMERA_HPP_
 
@@ -128,6 +132,8 @@ public:
     void setFeatures(const std::vector<cv::KeyPoint>& keypoints, const cv::Mat& descriptors);
     std::function<void(const cv::Mat& image, std::vector<cv::KeyPoint>& keypoints, cv::Mat& descriptors)> featureProvider;
     bool mirror_host;   // fill the public cv::Mat members of Frame from the device (default true)
+    int orb_nfeatures;  // cv::ORB::create(n): 200 in Camera (src/Camera.cpp:127), 1000 in CameraGPU (src/CameraGPU.cpp:99)
+    int detectOrbOnDevice(bool describe);   // fills currentFrame->keypoints (and descriptors); returns the key-point count
     bool verbose;
 
 protected:

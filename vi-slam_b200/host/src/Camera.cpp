@@ -9,6 +9,7 @@
 #include "vislam/Camera.hpp"
 
 #include <chrono>
+#include <cmath>
 #include <iomanip>
 #include <iostream>
 
@@ -43,7 +44,7 @@ Camera::Camera()
       elapsed_descriptors_mean(0), elapsed_computeGoodMatches_mean(0), elapsed_computeGradient_mean(0),
       elapsed_computePatches_mean(0), nPointsDetect_mean(0), nBestMatches_mean(0), num_images(0), elapsed_detect_sum(0),
       elapsed_descriptors_sum(0), elapsed_computeGoodMatches_sum(0), elapsed_computeGradient_sum(0),
-      elapsed_computePatches_sum(0), nPointsDetect_sum(0), nBestMatches_sum(0), mirror_host(true), verbose(false) {}
+      elapsed_computePatches_sum(0), nPointsDetect_sum(0), nBestMatches_sum(0), mirror_host(true), orb_nfeatures(200), verbose(false) {}
 
 Camera::Camera(int _detector, int _matcher, int _w_size, int _h_size, int _num_cells, int _length_path) : Camera() {
     initializate(_detector, _matcher, _w_size, _h_size, _num_cells, _length_path);
@@ -100,11 +101,65 @@ void Camera::setFeatures(const vector<KeyPoint>& keypoints, const Mat& descripto
     currentFrame->descriptors = descriptors;
 }
 
+// cv::ORB::create(orb_nfeatures)->detect / detectAndCompute on the device (vsb_orb_detect_compute_pyr): the level-0 image is
+// already in the frame's packed pyramid; results come back as cv::KeyPoint (pt, size = 31 * scale, angle, response, octave)
+// and a CV_8U n x 32 descriptor matrix, level by level in row-major order
+int Camera::detectOrbOnDevice(bool describe) {
+    Frame* f = currentFrame;
+    if (!f || !f->pyr_on_device) throw std::logic_error("Camera::detectOrbOnDevice: call Update first");
+    vi::Device& dev = vi::Device::get();
+    void* st = dev.stream();
+    const int w = f->layout.w[0], h = f->layout.h[0];
+    f->keypoints.clear();
+    f->descriptors = Mat();
+    if (w <= 62 || h <= 62 || orb_nfeatures <= 0) return 0;        // the 31-pixel border filter leaves nothing
+    const int cap = 2 * orb_nfeatures + 256;                         // ties at the selection thresholds can exceed n
+    vi::DevBuf d_xy, d_oct, d_resp, d_ang, d_desc, d_n;
+    float* xy = static_cast<float*>(d_xy.reserve((size_t)cap * 8));
+    int32_t* oct = static_cast<int32_t*>(d_oct.reserve((size_t)cap * 4));
+    float* resp = static_cast<float*>(d_resp.reserve((size_t)cap * 4));
+    float* ang = static_cast<float*>(d_ang.reserve((size_t)cap * 4));
+    uint8_t* desc = describe ? static_cast<uint8_t*>(d_desc.reserve((size_t)cap * 32)) : nullptr;
+    int32_t* n = static_cast<int32_t*>(d_n.reserve(4));
+    const uint8_t* img = f->d_pyr.as<uint8_t>() + f->layout.offset[0];
+    dev.check(vsb_orb_detect_compute_pyr(dev.ctx(), img, (int64_t)w * h, w, w, h, 1, orb_nfeatures, 1.2f, 8, 20, cap, xy, oct, resp,
+                                         ang, desc, n, st), "vsb_orb_detect_compute_pyr");
+    int32_t found = 0;
+    dev.check(vsb_download(dev.ctx(), &found, n, 4, st), "key-point count download");
+    dev.sync();
+    const int m = found < cap ? found : cap;
+    if (m <= 0) return 0;
+    std::vector<float> hxy(2 * (size_t)m), hresp(m), hang(m);
+    std::vector<int32_t> hoct(m);
+    dev.check(vsb_download(dev.ctx(), hxy.data(), xy, (size_t)m * 8, st), "key points download");
+    dev.check(vsb_download(dev.ctx(), hoct.data(), oct, (size_t)m * 4, st), "octaves download");
+    dev.check(vsb_download(dev.ctx(), hresp.data(), resp, (size_t)m * 4, st), "responses download");
+    dev.check(vsb_download(dev.ctx(), hang.data(), ang, (size_t)m * 4, st), "angles download");
+    if (describe) {
+        f->descriptors.create(m, 32, CV_8U);
+        dev.check(vsb_download(dev.ctx(), f->descriptors.data, desc, (size_t)m * 32, st), "descriptors download");
+    }
+    dev.sync();
+    f->keypoints.resize(m);
+    for (int i = 0; i < m; i++) {
+        KeyPoint& k = f->keypoints[i];
+        k.pt.x = hxy[2 * i]; k.pt.y = hxy[2 * i + 1];
+        k.octave = hoct[i];
+        k.size = 31.f * (float)std::pow((double)1.2f, (double)hoct[i]);     // patchSize * layer scale (orb.cpp)
+        k.angle = hang[i];
+        k.response = hresp[i];
+        k.class_id = -1;
+    }
+    return m;
+}
+
 int Camera::detectFeatures() {   // Camera.cpp:74-82
     const Clock::time_point t0 = Clock::now();
     if (featureProvider && currentFrame && currentFrame->keypoints.empty()) {
         Mat unused;
         featureProvider(currentFrame->grayImage[0], currentFrame->keypoints, unused);
+    } else if (detectorType == USE_ORB && currentFrame && currentFrame->keypoints.empty()) {
+        detectOrbOnDevice(false);
     }
     elapsed_detect = secs(t0, Clock::now());
     return currentFrame ? (int)currentFrame->keypoints.size() : 0;
@@ -114,6 +169,8 @@ int Camera::detectAndComputeFeatures() {   // Camera.cpp:84-93
     const Clock::time_point t0 = Clock::now();
     if (featureProvider && currentFrame && currentFrame->keypoints.empty())
         featureProvider(currentFrame->grayImage[0], currentFrame->keypoints, currentFrame->descriptors);
+    else if (detectorType == USE_ORB && currentFrame && currentFrame->keypoints.empty())
+        detectOrbOnDevice(true);
     elapsed_detect = secs(t0, Clock::now());
     return currentFrame ? (int)currentFrame->keypoints.size() : 0;
 }
@@ -278,7 +335,7 @@ void CameraGPU::initializateCameraGPU(int _detector, int _matcher, int _w_size, 
     setGPUMatcher(_matcher);
 }
 
-void CameraGPU::setGPUDetector(int _detector) { detectorType = _detector; }
+void CameraGPU::setGPUDetector(int _detector) { detectorType = _detector; orb_nfeatures = 1000; }   // CameraGPU.cpp:99 cuda::ORB::create(1000)
 void CameraGPU::detectGPUFeatures() { nPointsDetect = detectFeatures(); }
 int CameraGPU::detectAndComputeGPUFeatures() { return detectAndComputeFeatures(); }
 

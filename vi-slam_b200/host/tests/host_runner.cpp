@@ -3,9 +3,12 @@
 // lives in pytest next to the other GPU tests.  Usage: host_runner <mode> <dir>
 //   mode matcher : d1.bin d2.bin kp1.bin kp2.bin + meta.txt  ->  aux1/aux2/matches/sorted/good dumps
 //   mode sequence: frames.bin desc.bin kp.bin rimu.bin tres.bin + meta.txt  ->  poses.bin, ngood.bin, ncand.bin, final.bin
+//   mode orb     : frames.bin + meta.txt (frames, w, h, gpu)  ->  per frame orb_kp<i>.bin (x, y, size, angle, response, octave)
+//                  and orb_desc<i>.bin, from Camera / CameraGPU::detectAndComputeFeatures with the ORB detector
 //   mode nodevice: expects every compute entry to throw vi::DeviceError (run with CUDA_VISIBLE_DEVICES="")
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
 #include <fstream>
 #include <iostream>
 #include <map>
@@ -217,14 +220,48 @@ static int run_nodevice() {
     return thrown == 2 ? 0 : 4;
 }
 
+static int run_orb(const string& dir) {
+    map<string, double> meta = read_meta(dir);
+    const int T = (int)meta["frames"], w = (int)meta["w"], h = (int)meta["h"];
+    const bool gpu = meta["gpu"] != 0;
+    vector<uint8_t> frames = read_bin<uint8_t>(dir + "/frames.bin");
+    Camera cam;
+    CameraGPU camg;
+    if (gpu) camg.initializateCameraGPU(USE_ORB, USE_BRUTE_FORCE_HAMMING, w, h, 49, 5);
+    else cam.initializate(USE_ORB, USE_BRUTE_FORCE_HAMMING, w, h, 49, 5);
+    Camera& c = gpu ? static_cast<Camera&>(camg) : cam;
+    for (int i = 0; i < T; i++) {
+        Mat img(h, w, CV_8U);
+        memcpy(img.data, frames.data() + (size_t)i * w * h, (size_t)w * h);
+        c.Update(img);
+        const int n = gpu ? camg.detectAndComputeGPUFeatures() : c.detectAndComputeFeatures();
+        vector<float> kp;
+        for (int k = 0; k < n; k++) {
+            const KeyPoint& q = c.currentFrame->keypoints[k];
+            kp.push_back(q.pt.x); kp.push_back(q.pt.y); kp.push_back(q.size); kp.push_back(q.angle); kp.push_back(q.response);
+            kp.push_back((float)q.octave);
+        }
+        ostringstream a, b;
+        a << dir << "/orb_kp" << i << ".bin";
+        b << dir << "/orb_desc" << i << ".bin";
+        write_bin(a.str(), kp);
+        vector<uint8_t> d((size_t)n * 32);
+        if (n) memcpy(d.data(), c.currentFrame->descriptors.data, d.size());
+        write_bin(b.str(), d);
+        if (c.currentFrame->descriptors.rows != n || (n && c.currentFrame->descriptors.cols != 32)) return 3;
+    }
+    return 0;
+}
+
 int main(int argc, char** argv) {
-    if (argc < 2) { cerr << "usage: host_runner <matcher|sequence|nodevice> [dir]" << endl; return 1; }
+    if (argc < 2) { cerr << "usage: host_runner <matcher|sequence|orb|nodevice> [dir]" << endl; return 1; }
     const string mode = argv[1];
     try {
         if (mode == "nodevice") return run_nodevice();
         if (argc < 3) return 1;
         if (mode == "matcher") return run_matcher(argv[2]);
         if (mode == "sequence") return run_sequence(argv[2]);
+        if (mode == "orb") return run_orb(argv[2]);
     } catch (const std::exception& e) {
         cerr << "host_runner: exception: " << e.what() << endl;
         return 5;
