@@ -183,3 +183,30 @@ def test_camera_orb_detector_vs_oracle(tmp_path, oracle, gpu):
         size = np.array([np.float32(31.0) * np.float32(oracle.lib().vso_orb_level_scale(1.2, int(o))) for o in octv], np.float32)
         np.testing.assert_array_equal(kp[:, 2], size)
         np.testing.assert_array_equal(desc, odesc)
+
+
+def test_visystem_gpu_from_raw_frames_vs_oracle(tmp_path, oracle):
+    """The whole loop from images alone: VISystemGPU::AddFrameGPU with the ORB detector — device ORB (cuda::ORB::create(1000)
+    as CameraGPU.cpp:99), Hamming kNN + filters, pyramid, candidates, GN — against the oracle's chain on the same frames."""
+    from vislam_b200 import synth
+    T, n_cells = 4, 49
+    seq = synth.make_sequence(T, n_feat=10, seed=2001)
+    w, h, K = seq["w"], seq["h"], seq["K"]
+    d = str(tmp_path)
+    np.ascontiguousarray(seq["frames"], np.uint8).tofile(os.path.join(d, "frames.bin"))
+    np.ascontiguousarray(seq["R_imu_res"], np.float32).tofile(os.path.join(d, "rimu.bin"))
+    np.ascontiguousarray(seq["t_res"], np.float32).tofile(os.path.join(d, "tres.bin"))
+    _write_meta(d, frames=T, n_feat=0, w=w, h=h, n_cells=n_cells, mirror_host=0, grad_images=1, orb=1,
+                fx=K[0], fy=K[1], cx=K[2], cy=K[3])
+    out = subprocess.run([_runner(), "sequence", d], capture_output=True, text=True)
+    assert out.returncode == 0, out.stdout + out.stderr
+    poses = _rd(d, "poses.bin").reshape(T - 1, 7)
+    ngood = _rd(d, "ngood.bin")
+    feats = [oracle.orb_detect_compute_pyr(seq["frames"][t], 1000) for t in range(T)]
+    assert min(len(f[0]) for f in feats) > 100
+    for k in range(T - 1):
+        prior = oracle.initial_pose(np.eye(3), seq["R_imu_res"][k], seq["t_res"][k])
+        r = oracle.track_pair(seq["frames"][k], seq["frames"][k + 1], feats[k][4], feats[k + 1][4], feats[k][0], K, prior,
+                              n_cells=n_cells)
+        assert int(ngood[k]) == len(r["good_q"]) > 10
+        np.testing.assert_array_equal(poses[k], r["pose"])

@@ -124,8 +124,10 @@ static int run_sequence(const string& dir) {
     map<string, double> meta = read_meta(dir);
     const int T = (int)meta["frames"], N = (int)meta["n_feat"], w = (int)meta["w"], h = (int)meta["h"];
     const int n_cells = (int)meta["n_cells"], mirror = (int)meta["mirror_host"], grad_images = (int)meta["grad_images"];
-    vector<uint8_t> frames = read_bin<uint8_t>(dir + "/frames.bin"), desc = read_bin<uint8_t>(dir + "/desc.bin");
-    vector<float> kp = read_bin<float>(dir + "/kp.bin"), rimu = read_bin<float>(dir + "/rimu.bin"), tres = read_bin<float>(dir + "/tres.bin");
+    const bool orb = meta.count("orb") && meta["orb"] != 0;      // features from the device ORB detector instead of files
+    vector<uint8_t> frames = read_bin<uint8_t>(dir + "/frames.bin"), desc;
+    vector<float> kp, rimu = read_bin<float>(dir + "/rimu.bin"), tres = read_bin<float>(dir + "/tres.bin");
+    if (!orb) { desc = read_bin<uint8_t>(dir + "/desc.bin"); kp = read_bin<float>(dir + "/kp.bin"); }
     vi::VISystemGPU sys;
     Mat Kmat = Mat::zeros(3, 3, CV_32F);
     Kmat.at<float>(0, 0) = (float)meta["fx"]; Kmat.at<float>(1, 1) = (float)meta["fy"];
@@ -138,12 +140,13 @@ static int run_sequence(const string& dir) {
     vector<float> poses, finals, ngood, ncand, niter;
     for (int t = 0; t < T; t++) {
         Mat img(h, w, CV_8U, frames.data() + (size_t)t * w * h);
-        const float* kxy = kp.data() + (size_t)t * N * 2;
-        uint8_t* dd = desc.data() + (size_t)t * N * 32;
-        sys.cameraGPU.featureProvider = [&](const Mat&, vector<KeyPoint>& k, Mat& d) {
-            k = to_keypoints(kxy, N);
-            d = Mat(N, 32, CV_8U, dd);
-        };
+        const float* kxy = orb ? nullptr : kp.data() + (size_t)t * N * 2;
+        uint8_t* dd = orb ? nullptr : desc.data() + (size_t)t * N * 32;
+        if (!orb)
+            sys.cameraGPU.featureProvider = [&](const Mat&, vector<KeyPoint>& k, Mat& d) {
+                k = to_keypoints(kxy, N);
+                d = Mat(N, 32, CV_8U, dd);
+            };
         if (t > 0) {
             const float* r = rimu.data() + (size_t)(t - 1) * 9;
             sys.RotationResidualImu = Matx33f(r[0], r[1], r[2], r[3], r[4], r[5], r[6], r[7], r[8]);
