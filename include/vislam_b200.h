@@ -305,6 +305,14 @@ int vsb_track_sequence(vsb_tracker_t* t, const uint8_t* frames, const uint8_t* d
                        const int32_t* n_feat, const float* pose_prior, int n_frames,
                        float* pose, int32_t* n_good, void* stream);
 
+/* The same from images alone: every frame first goes through cv::ORB::create(nfeatures) on the device
+ * (vsb_orb_detect_compute_pyr: 8 levels, factor 1.2) — Camera::detectAndComputeFeatures (src/Camera.cpp:84-93) — and its key
+ * points and descriptors feed the matcher without leaving the device.  The tracker must be configured for ORB descriptors
+ * (norm 1, desc_bytes 32); a frame with more key points than cfg.n_feat_max keeps the first n_feat_max.  n_feat_out
+ * (optional, device) [n_frames] = key points used per frame. */
+int vsb_track_sequence_orb(vsb_tracker_t* t, const uint8_t* frames, const float* pose_prior, int n_frames, int nfeatures,
+                           float* pose, int32_t* n_good, int32_t* n_feat_out, void* stream);
+
 /* Same with HOST buffers (the end-to-end entry the class mirrors and bench.py's e2e leg use): frames,
  * descriptors, key points and priors are copied host->device in chunks of cfg.max_pairs pairs on two
  * streams so the copy of chunk i+1 overlaps the kernels of chunk i; poses are copied back.

@@ -171,3 +171,31 @@ def test_track_pairs_solver_modes(ctx, oracle, kw):
     assert rot_angle(pose[:4], ref["pose"][:4]) <= tol
     assert np.abs(pose[4:] - ref["pose"][4:]).max() <= tol
     tr.close()
+
+
+@pytest.mark.parametrize("n_feat_max", [1500, 300])
+def test_track_sequence_from_raw_frames(ctx, oracle, n_feat_max):
+    """vsb_track_sequence_orb: frames only.  cv::ORB::create(1000) on the device feeds the matcher and the solver; poses are
+    bit-identical to the oracle chain (oracle ORB -> oracle matcher -> oracle GN) on the same frames, also when the key-point
+    capacity truncates a frame's list."""
+    import torch
+    import vislam_b200 as vb
+    from vislam_b200 import synth
+    T = 5
+    seq = synth.make_sequence(T, n_feat=10, seed=2001)
+    prior = np.stack([_prior(vb, seq["R_imu_res"][k], seq["t_res"][k]) for k in range(T - 1)])
+    tr = ctx.tracker(752, 480, n_feat_max, seq["K"], n_cells=49, max_pairs=T - 1)
+    dev = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()
+    pose, n_good, n_feat = tr.track_sequence_orb(dev(seq["frames"]), dev(prior), nfeatures=1000)
+    torch.cuda.synchronize()
+    pose, n_good, n_feat = pose.cpu().numpy(), n_good.cpu().numpy(), n_feat.cpu().numpy()
+    feats = [oracle.orb_detect_compute_pyr(seq["frames"][t], 1000) for t in range(T)]
+    for t in range(T):
+        assert n_feat[t] == min(len(feats[t][0]), n_feat_max)
+    for k in range(T - 1):
+        a, b = feats[k], feats[k + 1]
+        ref = oracle.track_pair(seq["frames"][k], seq["frames"][k + 1], a[4][:n_feat_max], b[4][:n_feat_max], a[0][:n_feat_max],
+                                seq["K"], prior[k], n_cells=49)
+        assert n_good[k] == len(ref["good_q"]) > 10
+        np.testing.assert_array_equal(pose[k], ref["pose"])
+    tr.close()

@@ -53,6 +53,8 @@ struct Slot {
     uint2* patt = nullptr;        // per-point attributes of the solver, [max_pairs][levels][cand_cap]
     int32_t* n_cand = nullptr;
     float* pose = nullptr;
+    float* orb_resp = nullptr;    // [max_pairs + 1][n_feat] each, allocated on the first vsb_track_sequence_orb call
+    float* orb_angle = nullptr;
     cudaStream_t stream = nullptr;
     cudaEvent_t done = nullptr;
 };
@@ -111,7 +113,7 @@ int slot_alloc(vsb_tracker* t, Slot& s) {
 }
 
 void slot_free(Slot& s) {
-    void* ptrs[] = {s.pyr, s.gx, s.gy, s.desc, s.kp, s.n_feat, s.prior, s.key12, s.key21, s.good_q, s.good_t, s.good_d, s.n_good, s.n_sym, s.good_xy, s.cand, s.patt, s.n_cand, s.pose};
+    void* ptrs[] = {s.pyr, s.gx, s.gy, s.desc, s.kp, s.n_feat, s.prior, s.key12, s.key21, s.good_q, s.good_t, s.good_d, s.n_good, s.n_sym, s.good_xy, s.cand, s.patt, s.n_cand, s.pose, s.orb_resp, s.orb_angle};
     for (void* p : ptrs) if (p) cudaFree(p);
     if (s.stream) cudaStreamDestroy(s.stream);
     if (s.done) cudaEventDestroy(s.done);
@@ -235,6 +237,39 @@ extern "C" int vsb_track_sequence(vsb_tracker_t* t, const uint8_t* frames, const
     if (n_frames - 1 > t->cfg.max_pairs) return VSB_ERR_CAPACITY;
     return track_sequence_slot(t, t->slot[0], frames, false, desc, kp_xy, n_feat, pose_prior, n_frames, pose, n_good,
                                (cudaStream_t)stream);
+}
+
+namespace {
+__global__ void clamp_counts_kernel(int32_t* n, int count, int cap) {
+    const int i = blockIdx.x * 256 + threadIdx.x;
+    if (i < count) n[i] = min(n[i], cap);
+}
+}  // namespace
+
+// The loop from images alone: every frame goes through cv::ORB::create(nfeatures) on the device (orb.cu), the key points and
+// descriptors stay on the device and feed the matcher (Camera::detectAndComputeFeatures -> computeGoodMatches ->
+// EstimatePoseFeatures, VISystemGPU.cpp:144-169).  Frames with more key points than cfg.n_feat_max keep the first n_feat_max.
+extern "C" int vsb_track_sequence_orb(vsb_tracker_t* t, const uint8_t* frames, const float* pose_prior, int n_frames,
+                                      int nfeatures, float* pose, int32_t* n_good, int32_t* n_feat_out, void* stream) {
+    if (!t || !frames || !pose_prior || !pose || nfeatures < 0) return VSB_ERR_INVALID;
+    if (t->cfg.norm != 1 || t->cfg.desc_bytes != 32) return VSB_ERR_INVALID;        // ORB descriptors: 32 bytes, Hamming
+    if (n_frames < 2) return n_frames < 0 ? VSB_ERR_INVALID : VSB_OK;
+    if (n_frames - 1 > t->cfg.max_pairs) return VSB_ERR_CAPACITY;
+    vsb_ctx* ctx = t->ctx;
+    const vsb_tracker_cfg_t& c = t->cfg;
+    Slot& s = t->slot[0];
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc;
+    const size_t per = (size_t)(c.max_pairs + 1) * c.n_feat_max;
+    if (!s.orb_resp && (rc = dev_alloc(ctx, &s.orb_resp, per))) return rc;
+    if (!s.orb_angle && (rc = dev_alloc(ctx, &s.orb_angle, per))) return rc;
+    if ((rc = vsb_orb_detect_compute_pyr(ctx, frames, (int64_t)c.w * c.h, c.w, c.w, c.h, n_frames, nfeatures, 1.2f, 8, 20,
+                                         c.n_feat_max, s.kp, nullptr, s.orb_resp, s.orb_angle, s.desc, s.n_feat, stream)))
+        return rc;
+    clamp_counts_kernel<<<vsb_div_up(n_frames, 256), 256, 0, st>>>(s.n_feat, n_frames, c.n_feat_max);
+    VSB_LAUNCHED(ctx);
+    if (n_feat_out) VSB_CUDA(ctx, cudaMemcpyAsync(n_feat_out, s.n_feat, (size_t)n_frames * sizeof(int32_t), cudaMemcpyDeviceToDevice, st));
+    return track_sequence_slot(t, s, frames, false, s.desc, s.kp, s.n_feat, pose_prior, n_frames, pose, n_good, st);
 }
 
 extern "C" int vsb_track_pairs(vsb_tracker_t* t, const uint8_t* prev, const uint8_t* cur, const uint8_t* d1,

@@ -55,7 +55,7 @@ EXPORTS = [
     "vsb_pyr_layout", "vsb_pyramid_build", "vsb_gradient_build", "vsb_candidates_build",
     "vsb_gather_keypoints", "vsb_init_pyramid", "vsb_gn_default_opts", "vsb_gn_solve", "vsb_initial_pose",
     "vsb_se3_mul", "vsb_tracker_create", "vsb_tracker_destroy", "vsb_track_sequence",
-    "vsb_track_sequence_host", "vsb_track_pairs", "vsb_kernel_count", "vsb_kernel_name", "vsb_profile_enable",
+    "vsb_track_sequence_host", "vsb_track_sequence_orb", "vsb_track_pairs", "vsb_kernel_count", "vsb_kernel_name", "vsb_profile_enable",
     "vsb_profile_reset", "vsb_profile_read", "vsb_popc_peak", "vsb_tracker_stats", "vsb_tracker_host_traffic", "vsb_fast_detect", "vsb_orb_detect_compute", "vsb_orb_detect_compute_pyr",
     "vsb_malloc", "vsb_free", "vsb_host_alloc", "vsb_host_free", "vsb_upload", "vsb_upload_2d", "vsb_download",
     "vsb_copy", "vsb_memset", "vsb_stream_create", "vsb_stream_destroy", "vsb_stream_sync",
@@ -110,6 +110,7 @@ def lib():
     L.vsb_tracker_create.argtypes = [vp, C.POINTER(TrackerCfg), C.POINTER(vp)]
     L.vsb_tracker_destroy.argtypes = [vp]
     L.vsb_track_sequence.argtypes = [vp, vp, vp, vp, vp, vp, i32, vp, vp, vp]
+    L.vsb_track_sequence_orb.argtypes = [vp, vp, vp, i32, i32, vp, vp, vp, vp]
     L.vsb_track_sequence_host.argtypes = [vp, vp, vp, vp, vp, vp, i32, vp, vp]
     L.vsb_track_pairs.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, vp, vp, vp]
     L.vsb_kernel_count.restype = i32
@@ -452,6 +453,18 @@ class Tracker:
         check(lib().vsb_track_sequence(self.handle, _ptr(frames), _ptr(desc), _ptr(kp_xy), _ptr(n_feat), _ptr(prior), T,
                                        _ptr(pose), _ptr(n_good), _stream_ptr(stream)), self.ctx.handle)
         return pose, n_good
+
+    def track_sequence_orb(self, frames, prior, nfeatures=1000, stream=None):
+        """From images alone: frames [T,h,w] u8 (device), prior [T-1,7] -> pose [T-1,7], n_good [T-1], n_feat [T] (ORB key
+        points used per frame); cv::ORB::create(nfeatures) on the device feeds the matcher."""
+        t = self.ctx.torch
+        T = frames.shape[0]
+        pose = t.zeros((T - 1, 7), dtype=t.float32, device=self.ctx.dev)
+        n_good = t.zeros((T - 1,), dtype=t.int32, device=self.ctx.dev)
+        n_feat = t.zeros((T,), dtype=t.int32, device=self.ctx.dev)
+        check(lib().vsb_track_sequence_orb(self.handle, _ptr(frames), _ptr(prior), T, int(nfeatures), _ptr(pose), _ptr(n_good),
+                                           _ptr(n_feat), _stream_ptr(stream)), self.ctx.handle)
+        return pose, n_good, n_feat
 
     def track_sequence_host(self, frames, desc, kp_xy, prior, pose, n_good=None, n_feat=None):
         """HOST (pinned) tensors in, host tensors out; synchronous."""
