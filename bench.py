@@ -316,6 +316,30 @@ def run_gpu(args, rank, world, local_rank):
     n_chunks = (n_pairs + chunk - 1) // chunk
     same = bool(torch.equal(h_pose.to(dev), d_pose))
 
+    # ---- the same sequence from images alone (informational): device ORB feeds the matcher, SURVEY 8f N-4 ---------
+    raw = None
+    if rank == 0 and os.environ.get("VSB_BENCH_RAW_FRAMES", "1") != "0":
+        try:
+            tr.track_sequence_orb(d["frames"], d["prior"], nfeatures=N_FEAT, stream=stream)      # warm-up (allocations)
+            torch.cuda.synchronize(dev)
+            ctx.profile(True)
+            r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            r0.record(stream)
+            for _ in range(2):
+                _, _, r_nf = tr.track_sequence_orb(d["frames"], d["prior"], nfeatures=N_FEAT, stream=stream)
+            r1.record(stream)
+            torch.cuda.synchronize(dev)
+            r_ms = r0.elapsed_time(r1) / 2
+            r_prof = {k: round(v[0] / 2, 3) for k, v in ctx.profile_read().items()}
+            ctx.profile(False)
+            raw = {"value": n_pairs / (r_ms * 1e-3), "unit": "frames/s", "ms_per_step": r_ms,
+                   "orb_keypoints_per_frame": float(r_nf.float().mean()),
+                   "what": "vsb_track_sequence_orb: cv::ORB::create(%d) (8 levels, factor 1.2) on the device for every frame, then the "
+                           "same match + GN path; frames resident in HBM; the rendered frames carry far fewer corners than the "
+                           "%d random descriptors of configs[1]" % (N_FEAT, N_FEAT),
+                   "kernels_ms": r_prof}
+        except Exception as e:      # informational leg: never fails the bench
+            raw = {"error": str(e)}
     if rank != 0:
         return
     # ---- roofline of every kernel, the dominant one reported in "roofline" ---------------------------
@@ -407,6 +431,7 @@ def run_gpu(args, rank, world, local_rank):
         "e2e": {"value": e2e_value, "unit": "frames/s", "ms_per_step": e2e_ms_step, "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": d2h, "matches_device_path": same,
                 "h2d_gbs_achieved": h2d / (e2e_ms_step * 1e-3) / 1e9, "h2d_gbs_plain_copy": h2d_copy_gbs},
+        "from_raw_frames": raw,
         "gpu_launches": int(launches),
         "clocks": clocks,
         "roofline": roofline,

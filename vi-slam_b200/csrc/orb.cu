@@ -244,7 +244,11 @@ orb_angle_kernel(const uint8_t* __restrict__ img, long long img_stride, int pitc
 }
 
 // ---- stage 5: the blur ORB applies before describing: 7x7 sigma 2, generic float separable filter, reflect-101 ---------
-constexpr int BT = 32;
+// One 64x32 output tile per block.  The input tile (+3 halo, 72 bytes per row so rows start on the word before the tile) is
+// loaded as aligned 32-bit words where the image allows it; the row pass produces four adjacent outputs per thread, the column
+// pass four adjacent outputs packed into one 32-bit store.  Every output is the same sequence of rounded operations as the
+// oracle's: s = x0 k0, s = fma(x_i, k_i, s) along the row; s = r3 k3, s = fma(r[3+i] + r[3-i], k[3+i], s) down the column.
+constexpr int BTW = 64, BTH = 32, BTP = 72;
 __device__ __forceinline__ int refl101(int p, int n) {
     if (n == 1) return 0;
     while (p < 0 || p >= n) { if (p < 0) p = -p; if (p >= n) p = 2 * n - 2 - p; }
@@ -252,35 +256,82 @@ __device__ __forceinline__ int refl101(int p, int n) {
 }
 __global__ void __launch_bounds__(256)
 orb_blur_kernel(const uint8_t* __restrict__ img, long long img_stride, int pitch, int w, int h, uint8_t* __restrict__ out) {
-    __shared__ uint8_t s_in[BT + 6][BT + 8];
-    __shared__ float s_row[BT + 6][BT + 1];
-    const int f = blockIdx.z, x0 = blockIdx.x * BT, y0 = blockIdx.y * BT, tid = threadIdx.x;
+    __shared__ __align__(16) uint8_t s_in[BTH + 6][BTP];          // columns x0 - 4 .. x0 + 67
+    __shared__ __align__(16) float s_row[BTH + 6][BTW];
+    const int f = blockIdx.z, x0 = blockIdx.x * BTW, y0 = blockIdx.y * BTH, tid = threadIdx.x;
     const uint8_t* src = img + (size_t)f * img_stride;
-    for (int i = tid; i < (BT + 6) * (BT + 6); i += 256) {
-        const int ry = i / (BT + 6), rx = i - ry * (BT + 6);
-        s_in[ry][rx] = __ldg(src + (size_t)refl101(y0 + ry - 3, h) * pitch + refl101(x0 + rx - 3, w));
+    const bool words_ok = ((reinterpret_cast<uintptr_t>(src) | (uintptr_t)pitch) & 3u) == 0;
+    for (int i = tid; i < (BTH + 6) * (BTP / 4); i += 256) {
+        const int ry = i / (BTP / 4), wx = i - ry * (BTP / 4);
+        const int gy = y0 + ry - 3, gx = x0 - 4 + 4 * wx;
+        uint32_t v;
+        if (words_ok && gy >= 0 && gy < h && gx >= 0 && gx + 3 < w) {
+            v = __ldg(reinterpret_cast<const uint32_t*>(src + (size_t)gy * pitch + gx));
+        } else {
+            const uint8_t* row = src + (size_t)refl101(gy, h) * pitch;
+            v = 0u;
+#pragma unroll
+            for (int j = 0; j < 4; j++) v |= (uint32_t)__ldg(row + refl101(gx + j, w)) << (8 * j);
+        }
+        *reinterpret_cast<uint32_t*>(&s_in[ry][4 * wx]) = v;
     }
     __syncthreads();
     float k[7];
 #pragma unroll
     for (int i = 0; i < 4; i++) { k[i] = __uint_as_float(c_gauss[i]); k[6 - i] = k[i]; }
-    for (int i = tid; i < (BT + 6) * BT; i += 256) {
-        const int ry = i / BT, cx = i - ry * BT;
-        float acc = __fmul_rn((float)s_in[ry][cx], k[0]);
+    // row pass: (BTH + 6) rows x 16 quads
+    for (int i = tid; i < (BTH + 6) * (BTW / 4); i += 256) {
+        const int ry = i / (BTW / 4), q = i - ry * (BTW / 4);
+        // outputs x0 + 4q .. +3 need inputs x0 + 4q - 3 .. x0 + 4q + 6 = tile bytes 4q + 1 .. 4q + 10: three aligned words
+        const uint32_t* wp = reinterpret_cast<const uint32_t*>(&s_in[ry][4 * q]);
+        const uint32_t w0 = wp[0], w1 = wp[1], w2 = wp[2];
+        float px[12];
 #pragma unroll
-        for (int t = 1; t < 7; t++) acc = __fmaf_rn((float)s_in[ry][cx + t], k[t], acc);
-        s_row[ry][cx] = acc;
+        for (int j = 0; j < 4; j++) {
+            px[j] = (float)((w0 >> (8 * j)) & 0xFFu);
+            px[4 + j] = (float)((w1 >> (8 * j)) & 0xFFu);
+            px[8 + j] = (float)((w2 >> (8 * j)) & 0xFFu);
+        }
+        float4 o;
+        float* op = reinterpret_cast<float*>(&o);
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            float acc = __fmul_rn(px[1 + j], k[0]);
+#pragma unroll
+            for (int t = 1; t < 7; t++) acc = __fmaf_rn(px[1 + j + t], k[t], acc);
+            op[j] = acc;
+        }
+        *reinterpret_cast<float4*>(&s_row[ry][4 * q]) = o;
     }
     __syncthreads();
-    for (int i = tid; i < BT * BT; i += 256) {
-        const int cy = i / BT, cx = i - cy * BT;
-        const int x = x0 + cx, y = y0 + cy;
+    // column pass: BTH rows x 16 quads, one packed store per quad
+    uint8_t* dst = out + (size_t)f * w * h;
+    const bool store_words = (w & 3) == 0;
+    for (int i = tid; i < BTH * (BTW / 4); i += 256) {
+        const int cy = i / (BTW / 4), q = i - cy * (BTW / 4);
+        const int x = x0 + 4 * q, y = y0 + cy;
         if (x >= w || y >= h) continue;
-        float acc = __fmul_rn(s_row[cy + 3][cx], k[3]);
+        float4 r[7];
 #pragma unroll
-        for (int t = 1; t <= 3; t++) acc = __fmaf_rn(__fadd_rn(s_row[cy + 3 + t][cx], s_row[cy + 3 - t][cx]), k[3 + t], acc);
-        const int v = __float2int_rn(acc);
-        out[((size_t)f * h + y) * w + x] = (uint8_t)min(max(v, 0), 255);
+        for (int t = 0; t < 7; t++) r[t] = *reinterpret_cast<const float4*>(&s_row[cy + t][4 * q]);
+        uint32_t packed = 0u;
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const float* c0 = reinterpret_cast<const float*>(&r[0]) + j;      // stride 4 floats between rows
+            float acc = __fmul_rn(c0[12], k[3]);
+#pragma unroll
+            for (int t = 1; t <= 3; t++) acc = __fmaf_rn(__fadd_rn(c0[4 * (3 + t)], c0[4 * (3 - t)]), k[3 + t], acc);
+            const int v = min(max(__float2int_rn(acc), 0), 255);
+            packed |= (uint32_t)v << (8 * j);
+        }
+        uint8_t* o = dst + (size_t)y * w + x;
+        if (store_words && x + 3 < w) {
+            *reinterpret_cast<uint32_t*>(o) = packed;
+        } else {
+#pragma unroll
+            for (int j = 0; j < 4; j++)
+                if (x + j < w) o[j] = (uint8_t)(packed >> (8 * j));
+        }
     }
 }
 
@@ -342,24 +393,41 @@ __global__ void orb_resize_coeff_kernel(int sw, int sh, int dw, int dh, int4* __
 __global__ void __launch_bounds__(256)
 orb_resize_kernel(const uint8_t* __restrict__ src, long long src_stride, int spitch, int sw, int sh, uint8_t* __restrict__ dst,
                   int dw, int dh, const int4* __restrict__ tab) {
-    const int x = blockIdx.x * 32 + (threadIdx.x & 31), y = blockIdx.y * 8 + (threadIdx.x >> 5), f = blockIdx.z;
-    if (x >= dw || y >= dh) return;
-    const int4 tx = __ldg(tab + x), ty = __ldg(tab + dw + y);
-    const int ox = tx.x, ax = tx.y, ex = tx.z, oy = ty.x, ay = ty.y, ey = ty.z;
+    // four adjacent output pixels per thread, one packed store
+    const int xq = (blockIdx.x * 32 + (threadIdx.x & 31)) * 4, y = blockIdx.y * 8 + (threadIdx.x >> 5), f = blockIdx.z;
+    if (xq >= dw || y >= dh) return;
+    const int4 ty = __ldg(tab + dw + y);
+    const int oy = ty.x, ay = ty.y, ey = ty.z;
     const uint8_t* img = src + (size_t)f * src_stride;
     const int y0 = ey < 0 ? 0 : oy, y1 = ey != 0 ? y0 : oy + 1;
     const uint8_t* r0 = img + (size_t)y0 * spitch;
     const uint8_t* r1 = img + (size_t)y1 * spitch;
-    uint32_t h0, h1;
-    if (ex < 0) { h0 = (uint32_t)__ldg(r0) << 8; h1 = (uint32_t)__ldg(r1) << 8; }
-    else if (ex > 0) { h0 = (uint32_t)__ldg(r0 + sw - 1) << 8; h1 = (uint32_t)__ldg(r1 + sw - 1) << 8; }
-    else {
-        h0 = (uint32_t)(256 - ax) * __ldg(r0 + ox) + (uint32_t)ax * __ldg(r0 + ox + 1);
-        h1 = (uint32_t)(256 - ax) * __ldg(r1 + ox) + (uint32_t)ax * __ldg(r1 + ox + 1);
+    uint32_t packed = 0u;
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        const int x = xq + j;
+        if (x >= dw) break;
+        const int4 tx = __ldg(tab + x);
+        const int ox = tx.x, ax = tx.y, ex = tx.z;
+        uint32_t h0, h1;
+        if (ex < 0) { h0 = (uint32_t)__ldg(r0) << 8; h1 = (uint32_t)__ldg(r1) << 8; }
+        else if (ex > 0) { h0 = (uint32_t)__ldg(r0 + sw - 1) << 8; h1 = (uint32_t)__ldg(r1 + sw - 1) << 8; }
+        else {
+            h0 = (uint32_t)(256 - ax) * __ldg(r0 + ox) + (uint32_t)ax * __ldg(r0 + ox + 1);
+            h1 = (uint32_t)(256 - ax) * __ldg(r1 + ox) + (uint32_t)ax * __ldg(r1 + ox + 1);
+        }
+        uint32_t v = ey != 0 ? h0 << 8 : (uint32_t)(256 - ay) * h0 + (uint32_t)ay * h1;
+        v = (v + (1u << 15)) >> 16;
+        packed |= min(v, 255u) << (8 * j);
     }
-    uint32_t v = ey != 0 ? h0 << 8 : (uint32_t)(256 - ay) * h0 + (uint32_t)ay * h1;
-    v = (v + (1u << 15)) >> 16;
-    dst[((size_t)f * dh + y) * dw + x] = (uint8_t)min(v, 255u);
+    uint8_t* o = dst + ((size_t)f * dh + y) * dw + xq;
+    if ((dw & 3) == 0) {
+        *reinterpret_cast<uint32_t*>(o) = packed;                  // dw % 4 == 0: all four pixels exist and the address is aligned
+    } else {
+#pragma unroll
+        for (int j = 0; j < 4; j++)
+            if (xq + j < dw) o[j] = (uint8_t)(packed >> (8 * j));
+    }
 }
 
 // appends one level's key points to the frame's list: pt = level coordinates * scale (float), octave = level
@@ -434,7 +502,7 @@ int orb_one_level(vsb_ctx_t* ctx, const OrbScratch& S, const uint8_t* in, int64_
     orb_angle_kernel<<<dim3(min(vsb_div_up(cap, 8), max(4, vsb_div_up(nfeatures + 64, 8))), zc), 256, 0, st>>>(in, img_stride, pitch, kp_xy, n_kp, cap, kp_angle);
     VSB_LAUNCHED(ctx);
     if (desc) {
-        orb_blur_kernel<<<dim3(vsb_div_up(w, BT), vsb_div_up(h, BT), zc), 256, 0, st>>>(in, img_stride, pitch, w, h, S.blurred);
+        orb_blur_kernel<<<dim3(vsb_div_up(w, BTW), vsb_div_up(h, BTH), zc), 256, 0, st>>>(in, img_stride, pitch, w, h, S.blurred);
         VSB_LAUNCHED(ctx);
         orb_describe_kernel<<<dim3(min(vsb_div_up(cap, 8), max(4, vsb_div_up(nfeatures + 64, 8))), zc), 256, 0, st>>>(S.blurred, w, h, kp_xy, kp_angle, n_kp, cap, desc);
         VSB_LAUNCHED(ctx);
@@ -529,7 +597,7 @@ extern "C" int vsb_orb_detect_compute_pyr(vsb_ctx_t* ctx, const uint8_t* img, in
                 ProfScope ps(ctx, VSB_K_ORB, st);
                 orb_resize_coeff_kernel<<<vsb_div_up(nw + nh, 256), 256, 0, st>>>(cw, ch, nw, nh, rz_tab);
                 VSB_LAUNCHED(ctx);
-                orb_resize_kernel<<<dim3(vsb_div_up(nw, 32), vsb_div_up(nh, 8), zc), 256, 0, st>>>(cur, cur_stride, cp, cw, ch, dst, nw, nh, rz_tab);
+                orb_resize_kernel<<<dim3(vsb_div_up(nw, 128), vsb_div_up(nh, 8), zc), 256, 0, st>>>(cur, cur_stride, cp, cw, ch, dst, nw, nh, rz_tab);
                 VSB_LAUNCHED(ctx);
                 cur = dst; cur_stride = (int64_t)nw * nh; cw = nw; ch = nh; cp = nw;
             }
