@@ -186,6 +186,29 @@ def cpu_track_sample(seq, pair_ids, threads):
     return len(pair_ids) / dt, dt, poses
 
 
+def cv2_matcher_timing(seq, cores):
+    """OpenCV's own BFMatcher (cv2 4.13 when importable) on one frame pair of the workload — knnMatch k=2 in
+    both directions, wall clock, best of 5 — with one thread and with all host threads.  Informational: the library the
+    reference calls for the matching stage, next to the oracle port that is timed for the whole path."""
+    try:
+        import cv2
+    except Exception:
+        return None
+    d1, d2 = np.ascontiguousarray(seq["desc"][0]), np.ascontiguousarray(seq["desc"][1])
+    bf = cv2.BFMatcher(cv2.NORM_HAMMING)
+    out = {"version": cv2.__version__, "unit": "ms per frame pair (2 x knnMatch k=2, %d x %d ORB descriptors)" % (len(d1), len(d2))}
+    for name, nt in (("threads_1", 1), ("threads_%d" % cores, cores)):
+        cv2.setNumThreads(nt)
+        best = 1e9
+        for _ in range(5):
+            t0 = time.perf_counter()
+            bf.knnMatch(d1, d2, k=2)
+            bf.knnMatch(d2, d1, k=2)
+            best = min(best, time.perf_counter() - t0)
+        out[name] = best * 1e3
+    return out
+
+
 def run_reference(args, rank, world):
     """--impl reference: the reference's CPU algorithm (oracle port) on all host threads, bounded sample."""
     if rank != 0:
@@ -439,7 +462,8 @@ def run_gpu(args, rank, world, local_rank):
         "cpu_baseline": {"value": cpu_fps1, "unit": "frames/s", "cores": 1, "kind": "port",
                          "sample": f"first {len(ids)} frame pairs of the same sequence, oracle single thread "
                                    f"({cpu_dt1:.1f}s); box has {cores} host cores",
-                         "max_abs_pose_diff_vs_gpu": parity},
+                         "max_abs_pose_diff_vs_gpu": parity,
+                         "cv2_bfmatcher": cv2_matcher_timing(seq, cores)},
     }
     print(json.dumps(out), flush=True)
     tr.close()
