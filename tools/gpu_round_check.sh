@@ -10,6 +10,7 @@ python bench.py > $OUT/bench.json 2> $OUT/bench.err; echo "bench rc=$?"
 python bench.py --impl reference --steps 3 --warmup 1 > $OUT/bench_ref.json 2> $OUT/bench_ref.err
 # profiled command = the bench on the full workload, one timed step, small CPU sample
 export VSB_CPU_SAMPLE_PAIRS=4
+export VSB_BENCH_RAW_FRAMES=0     # the profiled command is the headline workload only (no from-raw-frames leg)
 python bench.py --steps 1 --warmup 1 > $OUT/plain.log 2>&1 && \
 ncu --metrics gpu__time_duration.sum,launch__grid_size --clock-control none -k "$KREGEX" -c 200 --csv --log-file $OUT/launches.csv \
     python bench.py --steps 1 --warmup 1 > $OUT/ncu_l.log 2>&1
