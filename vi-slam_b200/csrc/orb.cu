@@ -348,7 +348,10 @@ orb_describe_kernel(const uint8_t* __restrict__ blurred, int w, int h, const int
     const int x0 = kp_xy[((size_t)f * cap + k) * 2], y0 = kp_xy[((size_t)f * cap + k) * 2 + 1];
     float angle = kp_angle[(size_t)f * cap + k];
     angle = __fmul_rn(angle, (float)(3.14159265358979323846 / 180.f));
-    const float a = (float)cos((double)angle), b = (float)sin((double)angle);
+    float a = 0.f, b = 0.f;
+    if (lane == 0) { a = (float)cos((double)angle); b = (float)sin((double)angle); }      // one double-precision pair per key point
+    a = __shfl_sync(0xffffffffu, a, 0);
+    b = __shfl_sync(0xffffffffu, b, 0);
     const uint8_t* center = blurred + (size_t)f * w * h + (size_t)y0 * w + x0;
     int val = 0;
 #pragma unroll
