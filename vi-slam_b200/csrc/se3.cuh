@@ -136,40 +136,4 @@ VSB_HD void se3_mul(const float* a, const float* b, float* out) {
 // a*alpha + beta in float (multiply, then add; not fused).  So X = x*invf + backproj_offset(c, invf), not (x - c)*invf.
 VSB_HD float backproj_offset(float c, float invf) { return (float)(-(double)c * (double)invf); }
 
-// 6x6 float inverse, OpenCV hal::LU32f semantics (partial pivoting, eps = 10*FLT_EPSILON, zeros when singular)
-VSB_HD int inv6(const float* a, float* out) {
-    const int m = 6;
-    const float eps = 1.1920929e-07f * 10;
-    float A[36], b[36];
-    for (int i = 0; i < 36; i++) { A[i] = a[i]; b[i] = 0.f; }
-    for (int i = 0; i < m; i++) b[i * m + i] = 1.f;
-    for (int i = 0; i < m; i++) {
-        int k = i;
-        for (int j = i + 1; j < m; j++)
-            if (fabsf(A[j * m + i]) > fabsf(A[k * m + i])) k = j;
-        if (fabsf(A[k * m + i]) < eps) {
-            for (int t = 0; t < 36; t++) out[t] = 0.f;
-            return 0;
-        }
-        if (k != i) {
-            for (int j = i; j < m; j++) { float t = A[i * m + j]; A[i * m + j] = A[k * m + j]; A[k * m + j] = t; }
-            for (int j = 0; j < m; j++) { float t = b[i * m + j]; b[i * m + j] = b[k * m + j]; b[k * m + j] = t; }
-        }
-        const float d = F_DIV(-1.f, A[i * m + i]);
-        for (int j = i + 1; j < m; j++) {
-            const float alpha = F_MUL(A[j * m + i], d);
-            for (int c = i + 1; c < m; c++) A[j * m + c] = F_ADD(A[j * m + c], F_MUL(alpha, A[i * m + c]));
-            for (int c = 0; c < m; c++) b[j * m + c] = F_ADD(b[j * m + c], F_MUL(alpha, b[i * m + c]));
-        }
-    }
-    for (int i = m - 1; i >= 0; i--)
-        for (int j = 0; j < m; j++) {
-            float s = b[i * m + j];
-            for (int c = i + 1; c < m; c++) s = F_SUB(s, F_MUL(A[i * m + c], b[c * m + j]));
-            b[i * m + j] = F_DIV(s, A[i * m + i]);
-        }
-    for (int t = 0; t < 36; t++) out[t] = b[t];
-    return 1;
-}
-
 }  // namespace vsb
