@@ -4,9 +4,11 @@
 // Semantics are cv::FAST(TYPE_9_16)'s, restated in oracle/fast.c and pinned there against cv2: corner test, score
 // (largest threshold that keeps the pixel a corner, minus one), strict 3x3 suppression, row-major output order.
 //
-//   fast_score_kernel   one 64x16 tile (+halo) per CTA in shared memory, four adjacent pixels per thread; the 32 ring
-//                       comparisons and the "9 contiguous" test run on packed bytes (SWAR), corners get their score from
-//                       sliding-window minima.  Writes score + 1 per pixel (0 = no corner): one byte read, one written.
+//   fast_score_kernel   one 64x16 tile (+halo) per CTA in shared memory, four adjacent pixels per thread.  The flag pass is
+//                       the NECESSARY condition only — two neighbouring compass points of the ring both brighter or both
+//                       darker, 8 comparisons on packed bytes (SWAR) — and the few percent of pixels that pass get the full
+//                       arc test from their score (sliding-window minima; corner iff score + 1 > threshold), one thread per
+//                       candidate.  Writes score + 1 per pixel (0 = no corner): one byte read, one written.
 //   fast_count4_kernel  one warp per image row, 4 pixels per lane: 3x3 suppression on packed bytes, the row's corner count
 //                       (score rows are padded to a multiple of 4 bytes, so every width takes this path).
 //   fast_scan_kernel    exclusive scan of the row counts of each frame (row-major order needs the offsets).
@@ -101,49 +103,25 @@ fast_score_kernel(const uint8_t* __restrict__ img, long long img_stride, int pit
     const int ty = threadIdx.x >> 4, wc = (threadIdx.x & 15) + 1;      // row in the tile, word column of the centre word
     const int x = x0 + 4 * (wc - 1), y = y0 + ty;
     const bool in_image = x < w && y < h;
+    // Flag pass = the necessary condition only.  Any 9 contiguous ring positions contain two NEIGHBOURING compass points
+    // (ring positions 0, 4, 8, 12), so a corner needs two neighbouring compass pixels that are both brighter than centre + t or
+    // both darker than centre - t.  That test needs 4 of the 16 ring positions (rows y-3, y, y+3 only) and passes for a few
+    // percent of the pixels of a natural image; the pixels that pass are queued and get the full arc test from their score.
     uint32_t corner = 0u;
     if (in_image && y >= 3 && y < h - 3) {
-        uint32_t W[7][3];                                              // rows y-3 .. y+3, word columns wc-1, wc, wc+1
-#pragma unroll
-        for (int r = 0; r < 7; r++)
-#pragma unroll
-            for (int c = 0; c < 3; c++) W[r][c] = s[ty + r][wc - 1 + c];
-        const uint32_t C = W[3][1];
+        const uint32_t C = s[ty + 3][wc];
         const uint32_t T4 = (uint32_t)threshold * 0x01010101u;
         const uint32_t hi = __vaddus4(C, T4), lo = __vsubus4(C, T4);   // saturating: a ring byte can never beat 255 / 0
-        const int ring_x[16] = FAST_RING_X, ring_y[16] = FAST_RING_Y;
-        uint32_t Bb[16], Bd[16];
-#pragma unroll
-        for (int k = 0; k < 16; k++) {
-            const int rx = ring_x[k], row = 3 + ring_y[k];
-            const int c0 = rx < 0 ? 0 : 1, sh = (rx + 4) & 3;          // first aligned word and byte shift of the 4-pixel window
-            const uint32_t R = sh == 0 ? W[row][c0] : __funnelshift_r(W[row][c0], W[row][c0 + 1], 8 * sh);
-            Bb[k] = gt7(R, hi);                                        // ring brighter than centre + t
-            Bd[k] = gt7(lo, R);                                        // ring darker than centre - t
-        }
-        uint32_t T9[32];                                               // 9-arc masks, both polarities
-        {
-            uint32_t T3b[16], T3d[16];
-#pragma unroll
-            for (int k = 0; k < 16; k++) {
-                T3b[k] = Bb[k] & Bb[(k + 1) & 15] & Bb[(k + 2) & 15];
-                T3d[k] = Bd[k] & Bd[(k + 1) & 15] & Bd[(k + 2) & 15];
-            }
-#pragma unroll
-            for (int k = 0; k < 16; k++) {
-                T9[k] = T3b[k] & T3b[(k + 3) & 15] & T3b[(k + 6) & 15];
-                T9[16 + k] = T3d[k] & T3d[(k + 3) & 15] & T3d[(k + 6) & 15];
-            }
-        }
-        // OR of the 32 masks as a tree of 3-input LOP3s: 32 -> 11 -> 4 -> 2 -> 1
-        uint32_t a[11];
-#pragma unroll
-        for (int k = 0; k < 10; k++) a[k] = T9[3 * k] | T9[3 * k + 1] | T9[3 * k + 2];
-        a[10] = T9[30] | T9[31];
-        const uint32_t b0 = a[0] | a[1] | a[2], b1 = a[3] | a[4] | a[5], b2 = a[6] | a[7] | a[8], b3 = a[9] | a[10];
-        corner = ((b0 | b1 | b2) | b3) & 0x80808080u;
+        const uint32_t up = s[ty + 6][wc], dn = s[ty][wc];            // ring positions 0 (0, +3) and 8 (0, -3)
+        const uint32_t rt = __funnelshift_r(s[ty + 3][wc], s[ty + 3][wc + 1], 24);      // position 4 (+3, 0)
+        const uint32_t lf = __funnelshift_r(s[ty + 3][wc - 1], s[ty + 3][wc], 8);       // position 12 (-3, 0)
+        const uint32_t b0 = gt7(up, hi), b4 = gt7(rt, hi), b8 = gt7(dn, hi), b12 = gt7(lf, hi);
+        const uint32_t d0 = gt7(lo, up), d4 = gt7(lo, rt), d8 = gt7(lo, dn), d12 = gt7(lo, lf);
+        const uint32_t bb = ((b0 | b8) & (b4 | b12));                  // (b0&b4)|(b4&b8)|(b8&b12)|(b12&b0)
+        const uint32_t dd = ((d0 | d8) & (d4 | d12));
+        corner = (bb | dd) & 0x80808080u;
     }
-    // every pixel gets its byte now (0 = no corner); the few that are corners are queued for the score pass below
+    // every pixel gets its byte now (0 = no corner); the candidates are queued for the arc test / score pass below
     uint8_t* o = out + (size_t)y * sw + x;
     if (in_image) *reinterpret_cast<uint32_t*>(o) = 0u;                 // x is a multiple of 4 and x + 3 < sw
     if (corner) {
@@ -166,8 +144,10 @@ fast_score_kernel(const uint8_t* __restrict__ img, long long img_stride, int pit
             d[k] = v - (int)c[ring_y[k] * (FT_PITCH * 4) + ring_x[k]];
             neg[k] = -d[k];
         }
-        const int best = max(best_arc_min(d), best_arc_min(neg));       // > threshold for a corner; score + 1, in 1..255
-        out[(size_t)(y0 + ly) * sw + x0 + lx] = (uint8_t)best;
+        // largest threshold for which the pixel still has a 9-arc, plus one: the pixel is a corner iff that exceeds the
+        // threshold (cv::FAST's corner test and cornerScore agree by construction); stored as score + 1, in 1..255
+        const int best = max(best_arc_min(d), best_arc_min(neg));
+        if (best > threshold) out[(size_t)(y0 + ly) * sw + x0 + lx] = (uint8_t)best;
     }
 }
 
