@@ -257,14 +257,15 @@ def run_gpu(args, rank, world, local_rank):
     chunk = int(os.environ.get("VSB_BENCH_CHUNK", str(n_frames - 1)))       # device-resident pass: one batch per kernel
     host_chunk = int(os.environ.get("VSB_BENCH_HOST_CHUNK", "250"))          # host-buffer pass: H2D/compute pipeline depth
     grad_mode = int(os.environ.get("VSB_GRAD_MODE", "1"))   # 1: Scharr evaluated at the candidate points (bit-identical)
+    accum_mode = int(os.environ.get("VSB_GN_ACCUM", "0"))   # 0: FP64 accumulation of exact products (bit-faithful, default); 1: FP32 partials + FP64 final
     seq = make_data(n_frames, replicas.replica_seed(2001, rank), dev)
     n_pairs = n_frames - 1
     ctx = vb.Context(local_rank)
     tr = ctx.tracker(W, H, N_FEAT, seq["K"], n_cells=N_CELLS, max_pairs=chunk,
-                     gn_opts=vb.default_gn_opts(grad_mode=grad_mode))
+                     gn_opts=vb.default_gn_opts(grad_mode=grad_mode, accum_mode=accum_mode))
     # host (pinned) and device copies of the inputs
     tr_host = ctx.tracker(W, H, N_FEAT, seq["K"], n_cells=N_CELLS, max_pairs=host_chunk,
-                          gn_opts=vb.default_gn_opts(grad_mode=grad_mode))
+                          gn_opts=vb.default_gn_opts(grad_mode=grad_mode, accum_mode=accum_mode))
     h = {k: torch.from_numpy(np.ascontiguousarray(seq[k])).pin_memory() for k in ("frames", "desc", "kp", "prior")}
     d = {k: v.to(dev) for k, v in h.items()}
     d_pose = torch.zeros((n_pairs, 7), dtype=torch.float32, device=dev)
@@ -447,7 +448,7 @@ def run_gpu(args, rank, world, local_rank):
         "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "u8/int32 Hamming + f32 GN (f64 accumulate)", "data": "synthetic",
         "config": {"workload": WORKLOAD, "frames": n_frames, "pairs_per_step": n_pairs, "chunk_pairs": chunk, "host_chunk_pairs": host_chunk, "host_chunks": n_host_chunks,
-                   "grad_mode": grad_mode, "parallelism": f"replicas x{world}" if world > 1 else "single GPU",
+                   "grad_mode": grad_mode, "gn_accum_mode": accum_mode, "parallelism": f"replicas x{world}" if world > 1 else "single GPU",
                    "l2_policy": "inputs larger than L2 (722 MB of frames per step), no flush needed",
                    "gn_iterations_per_pair": stats["iterations"] / max(1, pairs_total),
                    "gn_points_per_pair": stats["point_visits"] / max(1, pairs_total)},
