@@ -41,6 +41,7 @@ extern "C" int vsb_ctx_create(int device, vsb_ctx_t** out) {
     c->scratch2_bytes = 0;
     c->l2_fallback_counter = nullptr;
     c->attr_knn_tc_done = 0;
+    c->attr_knn_mx_done = 0;
     c->attr_l2_tc_smem = 0;
     c->prof_on = 0;
     for (int i = 0; i < VSB_K_COUNT; i++) { c->prof_ms[i] = 0.0; c->prof_n[i] = 0; }
@@ -60,7 +61,7 @@ extern "C" int vsb_ctx_create(int device, vsb_ctx_t** out) {
 extern "C" int vsb_ctx_option(vsb_ctx_t* ctx, const char* name, int value) {
     if (!ctx || !name) return VSB_ERR_INVALID;
     if (!strcmp(name, "knn_impl")) {
-        if (value < 0 || value > 2) return VSB_ERR_INVALID;
+        if (value < 0 || value > 3) return VSB_ERR_INVALID;
         ctx->knn_impl = value;
         return VSB_OK;
     }

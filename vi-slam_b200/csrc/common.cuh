@@ -29,6 +29,7 @@ struct vsb_ctx {
     size_t scratch2_bytes;
     // kernel attributes are per device: remembered per context, not per process
     int attr_knn_tc_done;
+    int attr_knn_mx_done;
     int attr_l2_tc_smem;
     unsigned long long* l2_fallback_counter;   // device counter of the last tensor-core L2 kNN call (diagnostics)
     // optional per-kernel timing with CUDA events on the launching stream (bench.py's roofline leg)
@@ -39,7 +40,7 @@ struct vsb_ctx {
     long long prof_n[VSB_K_COUNT];
     // tuning knobs (vsb_ctx_option)
     int knn_impl;     // Hamming kNN: 0 = POPC kernel (INT pipe), 1 = tcgen05 tensor-core kernel, 32-bit epilogue,
-                      //              2 = tcgen05 kernel with the packed 16x2 epilogue
+                      //              2 = tcgen05 kernel with the packed 16x2 epilogue, 3 = 4-bit operands (kind::mxf4, knn_mx.cu)
     int gn_threads;   // threads per frame pair of the GN solver: 64 / 128 / 256 / 512 / 1024, 0 = chosen from the batch size
     int knn_l2_impl;  // float kNN: 0 = exact FP64 kernel, 1 = tensor-core GEMM + exact re-check (dim <= 64, dim % 8 == 0)
     int gn_variant;   // GN solver register/unroll variant (tuning experiments; 0 = default)

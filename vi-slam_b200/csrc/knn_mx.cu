@@ -1,0 +1,338 @@
+// knn_mx.cu — Hamming kNN (k = 2) on the tensor cores with 4-bit operands: tcgen05.mma kind::mxf4.block_scale
+// (knn_impl 3).  Same problem, pipeline and result as knn_tc.cu (Matcher::computeMatches, src/Matcher.cpp:83-94 /
+// MatcherGPU::computeGPUMatches, src/MatcherGPU.cpp:44-66), with half the operand bytes and twice the tensor rate.
+//
+// Arithmetic.  Every descriptor bit becomes one e2m1 nibble, +1 (0x2) or -1 (0xA), in BOTH operands; a descriptor is then
+// exactly one 128-byte row of the 128-byte-swizzled K-major operand tile, and four UMMAs of K = 64 cover its 256 bits.
+// Block scaling is mandatory for this kind, but the scales are constants: the scale-factor columns in tensor memory are
+// filled once per CTA with tcgen05.st (every byte the same, so their layout never matters) — 1 (0x7F, ue8m0) for the rows,
+// 64 (0x85) for the columns — and the FP32 accumulator receives 64 * (256 - 2 * hamming), an exact integer.
+// Two more UMMAs with constant operands add 2^23 + 2^14 (as 2^14 x 513: fourteen products 6 x 6 and one 3 x 3, row scale
+// 2^14 = 0x8D) and 128 - c for column c of the tile (binary digits of 128 - c as products 1, 2, 4, 8, 16 and repeated 16s).
+// The accumulator then holds 2^23 + key with  key = 128 * (256 - hamming) + (128 - c)  in [1, 32896] — the same selection key
+// as knn_tc.cu's packed epilogue — and because 2^23 + key has the key as its low mantissa bits, the low 16 bits of the FP32
+// bit pattern ARE the key: tcgen05.ld.pack::16b and the VIMNMX.U16x2 top-2 stay exactly as they were.  Columns past the end
+// of the set carry all-zero operand and bias rows: accumulator 0.0, key 0, which loses to every real column.
+//
+// Tensor memory: two accumulator stages of 96 columns (tiles are 128 rows x 96 columns) + three 8-column regions of scale
+// factors = 216 of the 256 columns allocated, so two CTAs still share an SM.
+#include "common.cuh"
+#include "knn_keys.cuh"
+#include "umma.cuh"
+
+namespace {
+
+constexpr int TM = 128;                    // rows per CTA  (UMMA M)
+constexpr int TN = 96;                     // columns per tile (UMMA N)
+constexpr int MX_THREADS = 288;
+constexpr int OP_BYTES = 128 * 128;        // an operand tile: 128 rows x 128 bytes (256 nibbles), one swizzle atom per 8 rows
+constexpr int OFF_A = 0;
+constexpr int OFF_B = OFF_A + OP_BYTES;            // two stages
+constexpr int OFF_BIAS = OFF_B + 2 * OP_BYTES;     // row side, column side (full tile), column side (last tile)
+constexpr int OFF_BAR = OFF_BIAS + 3 * OP_BYTES;
+constexpr int MX_SMEM = OFF_BAR + 128;
+constexpr int TMEM_COLS = 256;
+constexpr int SF_ONE = 192, SF_64 = 200, SF_2P14 = 208;      // TMEM columns of the constant scale factors
+
+// block-scaled instruction descriptor: A/B format e2m1 (1) at [7,10) / [10,13), N >> 3 at [17,23), scale format ue8m0 at bit 23,
+// M >> 4 at [24,29), K = 64 (bit 31 clear); both operands K-major
+constexpr uint32_t IDESC_MX = (1u << 7) | (1u << 10) | ((uint32_t)(TN >> 3) << 17) | (1u << 23) | ((uint32_t)(TM >> 4) << 24);
+
+__device__ __forceinline__ void mma_mxf4(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t accumulate, uint32_t sfa,
+                                         uint32_t sfb) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::mxf4.block_scale.block32 [%0], %1, %2, %3, [%5], [%6], p;\n\t"
+        "}\n" ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(IDESC_MX), "r"(accumulate), "r"(sfa), "r"(sfb) : "memory");
+}
+__device__ __forceinline__ void tmem_st4(uint32_t taddr, uint32_t v) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %1, %1, %1};" ::"r"(taddr), "r"(v) : "memory");
+}
+__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+// packed read of 32 columns: the low 16 bits of columns (2i, 2i+1) land in the (low, high) halves of v[i]
+__device__ __forceinline__ void tmem_ld16_pack16(uint32_t taddr, uint32_t (&v)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.pack::16b.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+          "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+        : "r"(taddr)
+        : "memory");
+}
+
+// 8 descriptor bits -> 8 e2m1 nibbles, element i of the byte in nibble i: two shift-or-mask steps spread the four 2-bit
+// fields to nibble positions, one PRMT picks {0x22, 0x2A, 0xA2, 0xAA} for (bit 2i+1, bit 2i)
+__device__ __forceinline__ uint32_t expand8(uint32_t v) {
+    uint32_t x = (v | (v << 4)) & 0x0F0Fu;
+    x = (x | (x << 2)) & 0x3333u;
+    return __byte_perm(0xAAA22A22u, 0u, x);
+}
+// raw 32-byte descriptor of tile row p -> 128 bytes of nibbles at rowp = tile + (p / 8) * 1024 + (p % 8) * 128, 16-byte chunk c
+// at ((c ^ (p % 8)) * 16); chunk c holds descriptor bytes 4c .. 4c + 3
+__device__ __forceinline__ void expand_row(uint8_t* rowp, int p7, const uint4& r0, const uint4& r1, bool valid) {
+    const uint32_t w[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+#pragma unroll
+    for (int c = 0; c < 8; c++) {
+        uint4 o = make_uint4(0u, 0u, 0u, 0u);                 // a row past the end of the set: all-zero operand, dot = 0
+        if (valid) {
+            const uint32_t word = w[c];
+            o.x = expand8(word & 0xFFu);
+            o.y = expand8((word >> 8) & 0xFFu);
+            o.z = expand8((word >> 16) & 0xFFu);
+            o.w = expand8(word >> 24);
+        }
+        *reinterpret_cast<uint4*>(rowp + ((c ^ p7) << 4)) = o;
+    }
+}
+
+// top-2 LARGEST of packed u16x2 keys; two candidates at once (the 3-input max is one VIMNMX3.U16x2)
+__device__ __forceinline__ void top2max_insert2_u16x2(uint32_t& b0, uint32_t& b1, uint32_t x, uint32_t y) {
+    const uint32_t hi = __vmaxu2(x, y), lo = __vminu2(x, y);
+    const uint32_t t = __vminu2(b0, hi);
+    b0 = __vmaxu2(b0, hi);
+    b1 = __vimax3_u16x2(b1, t, lo);
+}
+__device__ __forceinline__ void top2max_merge_u16x2(uint32_t& a0, uint32_t& a1, uint32_t o0, uint32_t o1) {
+    const uint32_t lo = __vminu2(a0, o0);
+    const uint32_t hi2 = __vmaxu2(a1, o1);
+    a0 = __vmaxu2(a0, o0);
+    a1 = __vmaxu2(lo, hi2);
+}
+
+// one 96-column accumulator tile: 64 + 32 columns of packed keys, pairwise top-2 on the 16x2 unit, fold into the global keys
+__device__ __forceinline__ void epilogue_tile(uint32_t taddr, uint32_t tempty_bar, int col0, uint32_t& gb0, uint32_t& gb1) {
+    uint32_t pb0[2] = {0u, 0u}, pb1[2] = {0u, 0u};
+    uint32_t v[32], u[16];
+    umma::tmem_ld32_pack16(taddr, v);
+    tmem_ld16_pack16(taddr + 64, u);
+    umma::tmem_wait_ld();
+    umma::fence_before_sync();
+    umma::mbar_arrive(tempty_bar);                                 // accumulator stage is free again
+#pragma unroll
+    for (int i = 0; i < 32; i += 2) top2max_insert2_u16x2(pb0[(i >> 1) & 1], pb1[(i >> 1) & 1], v[i], v[i + 1]);
+#pragma unroll
+    for (int i = 0; i < 16; i += 2) top2max_insert2_u16x2(pb0[(i >> 1) & 1], pb1[(i >> 1) & 1], u[i], u[i + 1]);
+    top2max_merge_u16x2(pb0[0], pb1[0], pb0[1], pb1[1]);
+    const uint32_t k16[4] = {pb0[0] & 0xFFFFu, pb0[0] >> 16, pb1[0] & 0xFFFFu, pb1[0] >> 16};
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+        const uint32_t t = k16[q] - 1u;                             // 128 * (256 - hamming) + (127 - c)
+        const uint32_t g = (k16[q] == 0u) ? KEY_INF
+                                          : (((256u - (t >> 7)) << KEY_SHIFT) | (uint32_t)(col0 + 127 - (int)(t & 127u)));
+        top2_insert(gb0, gb1, g);
+    }
+}
+
+// bias operand rows (K slice 0 = bytes 0..31: the 2^14 x 513 term; K slice 1 = bytes 32..63: the 128 - c term)
+__device__ __forceinline__ uint32_t bias_byte(int which, int r, int b, int last_valid) {
+    // which 0: row side (every row the same); 1: column side, full tile; 2: column side, last tile (columns >= last_valid are zero)
+    if (r >= (which == 0 ? TM : TN)) return 0u;
+    if (which == 2 && r >= last_valid) return 0u;
+    if (b < 32) {                                                   // elements 0..13 = 6 (0x7), element 14 = 3 (0x5): sum of squares 513
+        return b < 7 ? 0x77u : (b == 7 ? 0x05u : 0u);
+    }
+    const int e0 = 2 * (b - 32), e1 = e0 + 1;                       // the two elements of this byte
+    auto row_elem = [](int e) -> uint32_t { return e == 0 ? 0x2u : e == 1 ? 0x4u : e <= 18 ? 0x6u : 0u; };     // 1, 2, 4, 4, 4, ...
+    auto col_elem = [](int e, int v) -> uint32_t {                  // digits of v = 128 - c against the row constants
+        if (e == 0) return (v & 1) ? 0x2u : 0u;                     // 1 x 1
+        if (e == 1) return (v & 2) ? 0x2u : 0u;                     // 2 x 1
+        if (e == 2) return (v & 4) ? 0x2u : 0u;                     // 4 x 1
+        if (e == 3) return (v & 8) ? 0x4u : 0u;                     // 4 x 2
+        if (e == 4) return (v & 16) ? 0x6u : 0u;                    // 4 x 4
+        if (e <= 6) return (v & 32) ? 0x6u : 0u;                    // 2 x (4 x 4)
+        if (e <= 10) return (v & 64) ? 0x6u : 0u;                   // 4 x (4 x 4)
+        if (e <= 18) return (v & 128) ? 0x6u : 0u;                  // 8 x (4 x 4)
+        return 0u;
+    };
+    if (which == 0) return row_elem(e0) | (row_elem(e1) << 4);
+    const int v = 128 - r;
+    return col_elem(e0, v) | (col_elem(e1, v) << 4);
+}
+
+// the bias operand rows do not depend on the problem: built once (mx_bias_init_kernel) and copied into every CTA's tiles
+__device__ uint4 g_mx_bias[2 * 128 * 4];                            // [row side, column side][row][16-byte chunk 0..3]
+__global__ void mx_bias_init_kernel() {
+    const int i = blockIdx.x * 256 + threadIdx.x;
+    if (i >= 2 * 128 * 4) return;
+    const int which = i >> 9, r = (i >> 2) & 127, c = i & 3;
+    uint32_t w[4];
+    for (int q = 0; q < 4; q++) {
+        uint32_t v = 0u;
+        for (int j = 0; j < 4; j++) v |= bias_byte(which, r, 16 * c + 4 * q + j, TN) << (8 * j);
+        w[q] = v;
+    }
+    g_mx_bias[i] = make_uint4(w[0], w[1], w[2], w[3]);
+}
+
+__global__ void __launch_bounds__(MX_THREADS, 2)
+knn2_hamming_mx_kernel(const uint8_t* __restrict__ d1, int n1_max, const int32_t* __restrict__ n1_arr,
+                       const uint8_t* __restrict__ d2, int n2_max, const int32_t* __restrict__ n2_arr,
+                       uint32_t* __restrict__ key12, uint32_t* __restrict__ key21) {
+    const int prob = blockIdx.z, dir = blockIdx.y;
+    const int n1 = n1_arr ? min(n1_arr[prob], n1_max) : n1_max;
+    const int n2 = n2_arr ? min(n2_arr[prob], n2_max) : n2_max;
+    const int n_rows = dir ? n2 : n1, n_cols = dir ? n1 : n2;
+    const int row0 = blockIdx.x * TM;
+    if (row0 >= n_rows) return;                                   // uniform per CTA, before any allocation
+    const uint4* __restrict__ g_rows = reinterpret_cast<const uint4*>(dir ? d2 + (size_t)prob * n2_max * 32
+                                                                          : d1 + (size_t)prob * n1_max * 32);
+    const uint4* __restrict__ g_cols = reinterpret_cast<const uint4*>(dir ? d1 + (size_t)prob * n1_max * 32
+                                                                          : d2 + (size_t)prob * n2_max * 32);
+    uint32_t* keys_out = dir ? key21 + (size_t)prob * n2_max * 2 : key12 + (size_t)prob * n1_max * 2;
+    const int T = (n_cols + TN - 1) / TN;
+
+    extern __shared__ __align__(1024) uint8_t smem[];    // 128-byte swizzle atoms need a 1024-byte aligned base
+    uint8_t* sA = smem + OFF_A;
+    uint8_t* sB = smem + OFF_B;
+    uint8_t* sBias = smem + OFF_BIAS;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + OFF_BAR + 64);
+    const uint32_t bar0 = umma::smem_u32(bars);
+    // barrier ids: bfull[s] = s, bempty[s] = 2 + s, tfull[s] = 4 + s, tempty[s] = 6 + s
+    auto BAR = [&](int id) { return bar0 + 8u * (uint32_t)id; };
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+    if (tid == 0) {
+        umma::mbar_init(BAR(0), 128); umma::mbar_init(BAR(1), 128);     // bfull: the 128 producer threads
+        umma::mbar_init(BAR(2), 1);   umma::mbar_init(BAR(3), 1);       // bempty: tcgen05.commit
+        umma::mbar_init(BAR(4), 1);   umma::mbar_init(BAR(5), 1);       // tfull: tcgen05.commit
+        umma::mbar_init(BAR(6), 128); umma::mbar_init(BAR(7), 128);     // tempty: the 128 epilogue threads
+        umma::fence_mbar_init();
+    }
+    if (warp == 8) umma::tmem_alloc<TMEM_COLS>(umma::smem_u32(tmem_slot));
+    // the three bias operand tiles (K slices 0 and 1 of each row; the rest of the row is never read)
+    {
+        const int last_valid = n_cols - (T - 1) * TN;
+        for (int i = tid; i < 3 * 128 * 4; i += MX_THREADS) {       // (tile, row, 16-byte chunk 0..3)
+            const int which = i >> 9, r = (i >> 2) & 127, c = i & 3;
+            uint4 w = g_mx_bias[((which ? 1 : 0) << 9) | (i & 511)];
+            if (which == 2 && r >= last_valid) w = make_uint4(0u, 0u, 0u, 0u);     // columns past the end of the set
+            uint8_t* rowp = sBias + which * OP_BYTES + (r >> 3) * 1024 + (r & 7) * 128;
+            *reinterpret_cast<uint4*>(rowp + ((c ^ (r & 7)) << 4)) = w;
+        }
+    }
+    umma::fence_proxy_async();
+    umma::fence_before_sync();
+    __syncthreads();
+    umma::fence_after_sync();
+    const uint32_t tmem_base = *tmem_slot;
+    if ((bar0 - OFF_BAR) & 1023u) __trap();                        // operand tiles must sit on a 1024-byte boundary
+    if (warp < 4) {
+        // constant block scales, every byte of the region the same: 1, 64, 2^14 (ue8m0: 127 + log2)
+        const uint32_t lane_base = tmem_base + ((uint32_t)(warp * 32) << 16);
+#pragma unroll
+        for (int c = 0; c < 8; c += 4) {
+            tmem_st4(lane_base + SF_ONE + c, 0x7F7F7F7Fu);
+            tmem_st4(lane_base + SF_64 + c, 0x85858585u);
+            tmem_st4(lane_base + SF_2P14 + c, 0x8D8D8D8Du);
+        }
+        tmem_wait_st();
+    }
+    umma::fence_before_sync();
+    __syncthreads();
+    umma::fence_after_sync();
+
+    if (warp < 4) {
+        // ===================================== epilogue =====================================================
+        const int row = row0 + warp * 32 + lane;
+        uint32_t gb0 = KEY_INF, gb1 = KEY_INF;
+        for (int j = 0; j < T; j++) {
+            const int s = j & 1, n = j >> 1;
+            umma::mbar_wait(BAR(4 + s), n & 1);
+            umma::fence_after_sync();
+            const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(s * TN);
+            epilogue_tile(taddr, BAR(6 + s), j * TN, gb0, gb1);
+        }
+        if (row < n_rows) *reinterpret_cast<uint2*>(keys_out + (size_t)row * 2) = make_uint2(gb0, gb1);
+    } else if (warp < 8) {
+        // ===================================== producers ====================================================
+        const int p = tid - 128;
+        const uint4 zero = make_uint4(0u, 0u, 0u, 0u);
+        const uint32_t row_off = (uint32_t)((p >> 3) * 1024 + (p & 7) * 128);
+        {
+            const int r = row0 + p;
+            const bool valid = r < n_rows;
+            const uint4 a0 = valid ? __ldg(g_rows + (size_t)r * 2) : zero;
+            const uint4 a1 = valid ? __ldg(g_rows + (size_t)r * 2 + 1) : zero;
+            expand_row(sA + row_off, p & 7, a0, a1, valid);
+        }
+        uint4 n0 = zero, n1v = zero;
+        if (T > 0 && p < TN && p < n_cols) { n0 = __ldg(g_cols + (size_t)p * 2); n1v = __ldg(g_cols + (size_t)p * 2 + 1); }
+        for (int j = 0; j < T; j++) {
+            const int s = j & 1, n = j >> 1;
+            const uint4 c0 = n0, c1 = n1v;
+            const bool cvalid = p < TN && j * TN + p < n_cols;
+            const int cn = (j + 1) * TN + p;
+            if (j + 1 < T && p < TN && cn < n_cols) { n0 = __ldg(g_cols + (size_t)cn * 2); n1v = __ldg(g_cols + (size_t)cn * 2 + 1); }
+            else { n0 = zero; n1v = zero; }
+            umma::mbar_wait(BAR(2 + s), (n & 1) ^ 1);                  // the UMMAs that read this stage have completed
+            if (p < TN) expand_row(sB + s * OP_BYTES + row_off, p & 7, c0, c1, cvalid);
+            umma::fence_proxy_async();
+            umma::mbar_arrive(BAR(0 + s));
+        }
+    } else {
+        // ===================================== UMMA issuer ==================================================
+        if (lane == 0) {
+            const uint32_t aA = umma::smem_u32(sA), aB = umma::smem_u32(sB), aBias = umma::smem_u32(sBias);
+            const uint32_t sf1 = tmem_base + SF_ONE, sf64 = tmem_base + SF_64, sf2p14 = tmem_base + SF_2P14;
+            for (int j = 0; j < T; j++) {
+                const int s = j & 1, n = j >> 1;
+                umma::mbar_wait(BAR(0 + s), n & 1);                    // operands of tile j are in shared memory
+                umma::mbar_wait(BAR(6 + s), (n & 1) ^ 1);              // the epilogue has drained this accumulator stage
+                umma::fence_after_sync();
+                const uint32_t d_tmem = tmem_base + (uint32_t)(s * TN);
+#pragma unroll
+                for (int k = 0; k < 4; k++) {                          // K = 64 nibbles = 32 bytes per instruction
+                    const uint64_t da = umma::smem_desc(aA + k * 32, 16, 1024, umma::LAYOUT_SW128);
+                    const uint64_t db = umma::smem_desc(aB + s * OP_BYTES + k * 32, 16, 1024, umma::LAYOUT_SW128);
+                    mma_mxf4(d_tmem, da, db, k > 0 ? 1u : 0u, sf1, sf64);
+                }
+                const uint32_t bcol = aBias + (j == T - 1 ? 2 : 1) * OP_BYTES;
+                mma_mxf4(d_tmem, umma::smem_desc(aBias, 16, 1024, umma::LAYOUT_SW128),
+                         umma::smem_desc(bcol, 16, 1024, umma::LAYOUT_SW128), 1u, sf2p14, sf1);          // + 2^23 + 2^14
+                mma_mxf4(d_tmem, umma::smem_desc(aBias + 32, 16, 1024, umma::LAYOUT_SW128),
+                         umma::smem_desc(bcol + 32, 16, 1024, umma::LAYOUT_SW128), 1u, sf1, sf1);        // + 128 - c
+                umma::commit(BAR(2 + s));
+                umma::commit(BAR(4 + s));
+            }
+        }
+        __syncwarp();
+    }
+    umma::fence_before_sync();
+    __syncthreads();
+    if (warp == 8) {
+        umma::fence_after_sync();
+        umma::tmem_dealloc<TMEM_COLS>(tmem_base);
+    }
+}
+
+}  // namespace
+
+// 4-bit tensor-core implementation behind vsb_knn2_hamming_keys (csrc/knn_hamming.cu dispatches on ctx->knn_impl == 3)
+int vsb_knn2_hamming_mx(vsb_ctx* ctx, const uint8_t* d1, int n1_max, const int32_t* n1, const uint8_t* d2, int n2_max,
+                        const int32_t* n2, int count, uint32_t* key12, uint32_t* key21, cudaStream_t st) {
+    if (!ctx || count < 0 || n1_max < 0 || n2_max < 0) return VSB_ERR_INVALID;
+    if (n1_max > (int)KEY_IDX_MASK || n2_max > (int)KEY_IDX_MASK) return VSB_ERR_CAPACITY;
+    if (count == 0 || (n1_max == 0 && n2_max == 0)) return VSB_OK;
+    if (!ctx->attr_knn_mx_done) {
+        VSB_CUDA(ctx, cudaFuncSetAttribute(knn2_hamming_mx_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, MX_SMEM));
+        VSB_CUDA(ctx, cudaFuncSetAttribute(knn2_hamming_mx_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+        mx_bias_init_kernel<<<4, 256, 0, st>>>();
+        VSB_LAUNCHED(ctx);
+        ctx->attr_knn_mx_done = 1;
+    }
+    const int row_tiles = vsb_div_up(n1_max > n2_max ? n1_max : n2_max, TM);
+    for (int z0 = 0; z0 < count; z0 += 65535) {
+        const int zc = count - z0 < 65535 ? count - z0 : 65535;
+        dim3 grid(row_tiles, 2, zc);
+        ProfScope ps(ctx, VSB_K_KNN_HAMMING, st);
+        knn2_hamming_mx_kernel<<<grid, MX_THREADS, MX_SMEM, st>>>(d1 + (size_t)z0 * n1_max * 32, n1_max, n1 ? n1 + z0 : nullptr,
+                                                                   d2 + (size_t)z0 * n2_max * 32, n2_max, n2 ? n2 + z0 : nullptr,
+                                                                   key12 + (size_t)z0 * n1_max * 2, key21 + (size_t)z0 * n2_max * 2);
+        VSB_LAUNCHED(ctx);
+    }
+    return VSB_OK;
+}
