@@ -20,7 +20,7 @@ for n, b in cfgs:
     d1 = torch.randint(0, 256, (b, n, 32), dtype=torch.uint8, device="cuda", generator=g)
     d2 = torch.randint(0, 256, (b, n, 32), dtype=torch.uint8, device="cuda", generator=g)
     ref = None
-    for impl in (0, 1, 2, 3):
+    for impl in (0, 1, 2, 3, 4, 5):
         ctx.option("knn_impl", impl)
         for _ in range(3):
             out = ctx.knn2_hamming(d1, d2)

@@ -61,7 +61,7 @@ extern "C" int vsb_ctx_create(int device, vsb_ctx_t** out) {
 extern "C" int vsb_ctx_option(vsb_ctx_t* ctx, const char* name, int value) {
     if (!ctx || !name) return VSB_ERR_INVALID;
     if (!strcmp(name, "knn_impl")) {
-        if (value < 0 || value > 3) return VSB_ERR_INVALID;
+        if (value < 0 || value > 5) return VSB_ERR_INVALID;
         ctx->knn_impl = value;
         return VSB_OK;
     }

@@ -40,7 +40,7 @@ struct vsb_ctx {
     long long prof_n[VSB_K_COUNT];
     // tuning knobs (vsb_ctx_option)
     int knn_impl;     // Hamming kNN: 0 = POPC kernel (INT pipe), 1 = tcgen05 tensor-core kernel, 32-bit epilogue,
-                      //              2 = tcgen05 kernel with the packed 16x2 epilogue, 3 = 4-bit operands (kind::mxf4, knn_mx.cu)
+                      //              2 = tcgen05 kernel with the packed 16x2 epilogue, 3 = 4-bit operands (kind::mxf4, knn_mx.cu), 4 = the same with descriptors pre-expanded once per call
     int gn_threads;   // threads per frame pair of the GN solver: 64 / 128 / 256 / 512 / 1024, 0 = chosen from the batch size
     int knn_l2_impl;  // float kNN: 0 = exact FP64 kernel, 1 = tensor-core GEMM + exact re-check (dim <= 64, dim % 8 == 0)
     int gn_variant;   // GN solver register/unroll variant (tuning experiments; 0 = default)

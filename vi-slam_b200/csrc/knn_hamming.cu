@@ -175,7 +175,7 @@ int vsb_knn2_hamming_tc(vsb_ctx* ctx, const uint8_t* d1, int n1_max, const int32
                         int32_t* dump, int dump_ld, cudaStream_t st);
 
 int vsb_knn2_hamming_mx(vsb_ctx* ctx, const uint8_t* d1, int n1_max, const int32_t* n1, const uint8_t* d2, int n2_max,
-                        const int32_t* n2, int count, uint32_t* key12, uint32_t* key21, cudaStream_t st);
+                        const int32_t* n2, int count, uint32_t* key12, uint32_t* key21, int pre, cudaStream_t st);
 
 // Internal entry used by the tracker too: leaves packed keys (distance << 23 | index) in key12 / key21.
 int vsb_knn2_hamming_keys(vsb_ctx* ctx, const uint8_t* d1, int n1_max, const int32_t* n1, const uint8_t* d2,
@@ -184,7 +184,7 @@ int vsb_knn2_hamming_keys(vsb_ctx* ctx, const uint8_t* d1, int n1_max, const int
     if (!ctx || count < 0 || n1_max < 0 || n2_max < 0) return VSB_ERR_INVALID;
     if (n1_max > (int)KEY_IDX_MASK || n2_max > (int)KEY_IDX_MASK) return VSB_ERR_CAPACITY;
     if (count == 0) return VSB_OK;
-    if (ctx->knn_impl == 3) return vsb_knn2_hamming_mx(ctx, d1, n1_max, n1, d2, n2_max, n2, count, key12, key21, st);
+    if (ctx->knn_impl >= 3) return vsb_knn2_hamming_mx(ctx, d1, n1_max, n1, d2, n2_max, n2, count, key12, key21, ctx->knn_impl - 3, st);
     if (ctx->knn_impl != 0)   // tensor-core path: every valid row is written by exactly one CTA, no memset, no atomics
         return vsb_knn2_hamming_tc(ctx, d1, n1_max, n1, d2, n2_max, n2, count, key12, key21, ctx->knn_impl == 2,
                                    nullptr, 0, st);

@@ -151,6 +151,44 @@ __device__ __forceinline__ uint32_t bias_byte(int which, int r, int b, int last_
     return col_elem(e0, v) | (col_elem(e1, v) << 4);
 }
 
+// pre-expansion (PRE): every descriptor is turned into its 128 bytes of nibbles ONCE per call (both directions and all the
+// CTAs that sweep it read the expanded form), so the producers of the matching kernel only copy: 8 x (LDG.128 + STS.128) per
+// row instead of ~200 integer instructions
+__global__ void __launch_bounds__(256) mx_expand_kernel(const uint8_t* __restrict__ d, long long n_chunks, uint4* __restrict__ out) {
+    const long long i = (long long)blockIdx.x * 256 + threadIdx.x;          // (row, 16-byte output chunk) = 4 descriptor bytes
+    if (i >= n_chunks) return;
+    const uint32_t word = __ldg(reinterpret_cast<const uint32_t*>(d) + i);
+    out[i] = make_uint4(expand8(word & 0xFFu), expand8((word >> 8) & 0xFFu), expand8((word >> 16) & 0xFFu), expand8(word >> 24));
+}
+
+// BULK: the expanded rows are additionally stored in the SWIZZLED order of the operand tile (chunk c of row r at slot
+// c ^ (r % 8); tiles start at multiples of 8 rows) and every problem is padded with zero rows to a multiple of 384 rows, so an
+// operand tile is one contiguous block of global memory with exactly the shared-memory image the UMMA wants: ONE
+// cp.async.bulk per tile, issued by one thread and completing on the tile's mbarrier, replaces the producer warps.
+__global__ void __launch_bounds__(256)
+mx_expand_swizzled_kernel(const uint8_t* __restrict__ d, int n_max, const int32_t* __restrict__ n_arr, int rows_pad, int count,
+                          uint4* __restrict__ out) {
+    const long long i = (long long)blockIdx.x * 256 + threadIdx.x;
+    if (i >= (long long)count * rows_pad * 8) return;
+    const int c = (int)(i & 7);
+    const long long rr = i >> 3;
+    const int prob = (int)(rr / rows_pad), r = (int)(rr - (long long)prob * rows_pad);
+    const int n = n_arr ? min(n_arr[prob], n_max) : n_max;
+    uint4 o = make_uint4(0u, 0u, 0u, 0u);
+    if (r < n) {
+        const uint32_t word = __ldg(reinterpret_cast<const uint32_t*>(d + ((size_t)prob * n_max + r) * 32) + c);
+        o = make_uint4(expand8(word & 0xFFu), expand8((word >> 8) & 0xFFu), expand8((word >> 16) & 0xFFu), expand8(word >> 24));
+    }
+    out[((size_t)prob * rows_pad + r) * 8 + (c ^ (r & 7))] = o;
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+
 // the bias operand rows do not depend on the problem: built once (mx_bias_init_kernel) and copied into every CTA's tiles
 __device__ uint4 g_mx_bias[2 * 128 * 4];                            // [row side, column side][row][16-byte chunk 0..3]
 __global__ void mx_bias_init_kernel() {
@@ -166,20 +204,25 @@ __global__ void mx_bias_init_kernel() {
     g_mx_bias[i] = make_uint4(w[0], w[1], w[2], w[3]);
 }
 
+template <int MODE>        // 0: expand in the kernel; 1: copy pre-expanded rows; 2: one bulk copy per pre-swizzled tile
 __global__ void __launch_bounds__(MX_THREADS, 2)
 knn2_hamming_mx_kernel(const uint8_t* __restrict__ d1, int n1_max, const int32_t* __restrict__ n1_arr,
                        const uint8_t* __restrict__ d2, int n2_max, const int32_t* __restrict__ n2_arr,
-                       uint32_t* __restrict__ key12, uint32_t* __restrict__ key21) {
+                       uint32_t* __restrict__ key12, uint32_t* __restrict__ key21, int rows_pad) {
+    // MODE 1, 2: d1 / d2 point at the EXPANDED descriptors (128 bytes per row; MODE 2: rows_pad rows per problem)
+    constexpr bool PRE = MODE != 0;
     const int prob = blockIdx.z, dir = blockIdx.y;
     const int n1 = n1_arr ? min(n1_arr[prob], n1_max) : n1_max;
     const int n2 = n2_arr ? min(n2_arr[prob], n2_max) : n2_max;
     const int n_rows = dir ? n2 : n1, n_cols = dir ? n1 : n2;
     const int row0 = blockIdx.x * TM;
     if (row0 >= n_rows) return;                                   // uniform per CTA, before any allocation
-    const uint4* __restrict__ g_rows = reinterpret_cast<const uint4*>(dir ? d2 + (size_t)prob * n2_max * 32
-                                                                          : d1 + (size_t)prob * n1_max * 32);
-    const uint4* __restrict__ g_cols = reinterpret_cast<const uint4*>(dir ? d1 + (size_t)prob * n1_max * 32
-                                                                          : d2 + (size_t)prob * n2_max * 32);
+    constexpr int ROWB = PRE ? 128 : 32;                          // bytes per descriptor row as stored
+    const size_t rows1 = MODE == 2 ? (size_t)rows_pad : (size_t)n1_max, rows2 = MODE == 2 ? (size_t)rows_pad : (size_t)n2_max;
+    const uint4* __restrict__ g_rows = reinterpret_cast<const uint4*>(dir ? d2 + (size_t)prob * rows2 * ROWB
+                                                                          : d1 + (size_t)prob * rows1 * ROWB);
+    const uint4* __restrict__ g_cols = reinterpret_cast<const uint4*>(dir ? d1 + (size_t)prob * rows1 * ROWB
+                                                                          : d2 + (size_t)prob * rows2 * ROWB);
     uint32_t* keys_out = dir ? key21 + (size_t)prob * n2_max * 2 : key12 + (size_t)prob * n1_max * 2;
     const int T = (n_cols + TN - 1) / TN;
 
@@ -188,7 +231,7 @@ knn2_hamming_mx_kernel(const uint8_t* __restrict__ d1, int n1_max, const int32_t
     uint8_t* sB = smem + OFF_B;
     uint8_t* sBias = smem + OFF_BIAS;
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + OFF_BAR + 64);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + OFF_BAR + 96);     // after the 9 barriers
     const uint32_t bar0 = umma::smem_u32(bars);
     // barrier ids: bfull[s] = s, bempty[s] = 2 + s, tfull[s] = 4 + s, tempty[s] = 6 + s
     auto BAR = [&](int id) { return bar0 + 8u * (uint32_t)id; };
@@ -196,7 +239,8 @@ knn2_hamming_mx_kernel(const uint8_t* __restrict__ d1, int n1_max, const int32_t
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
     if (tid == 0) {
-        umma::mbar_init(BAR(0), 128); umma::mbar_init(BAR(1), 128);     // bfull: the 128 producer threads
+        umma::mbar_init(BAR(0), MODE == 2 ? 1 : 128); umma::mbar_init(BAR(1), MODE == 2 ? 1 : 128);   // bfull: producers / the bulk copy
+        umma::mbar_init(BAR(8), 1);                                     // afull (MODE 2): the row tile has landed
         umma::mbar_init(BAR(2), 1);   umma::mbar_init(BAR(3), 1);       // bempty: tcgen05.commit
         umma::mbar_init(BAR(4), 1);   umma::mbar_init(BAR(5), 1);       // tfull: tcgen05.commit
         umma::mbar_init(BAR(6), 128); umma::mbar_init(BAR(7), 128);     // tempty: the 128 epilogue threads
@@ -252,6 +296,48 @@ knn2_hamming_mx_kernel(const uint8_t* __restrict__ d1, int n1_max, const int32_t
         const int p = tid - 128;
         const uint4 zero = make_uint4(0u, 0u, 0u, 0u);
         const uint32_t row_off = (uint32_t)((p >> 3) * 1024 + (p & 7) * 128);
+        if (MODE == 2) {
+            if (p == 0) {                                              // the loader: one thread, one bulk copy per tile
+                mbar_expect_tx(BAR(8), TM * 128);
+                bulk_g2s(umma::smem_u32(sA), g_rows + (size_t)row0 * 8, TM * 128, BAR(8));
+                for (int j = 0; j < T; j++) {
+                    const int s = j & 1, n = j >> 1;
+                    umma::mbar_wait(BAR(2 + s), (n & 1) ^ 1);          // the UMMAs that read this stage have completed
+                    mbar_expect_tx(BAR(0 + s), TN * 128);
+                    bulk_g2s(umma::smem_u32(sB + s * OP_BYTES), g_cols + (size_t)j * TN * 8, TN * 128, BAR(0 + s));
+                }
+            }
+        } else if (PRE) {
+            // copy of pre-expanded rows: chunk c of the row goes to the swizzled slot (c ^ (p % 8))
+            {
+                const int r = row0 + p;
+                uint8_t* rowp = sA + row_off;
+#pragma unroll
+                for (int c = 0; c < 8; c++)
+                    *reinterpret_cast<uint4*>(rowp + ((c ^ (p & 7)) << 4)) = r < n_rows ? __ldg(g_rows + (size_t)r * 8 + c) : zero;
+            }
+            uint4 nx[8];
+#pragma unroll
+            for (int c = 0; c < 8; c++) nx[c] = (T > 0 && p < TN && p < n_cols) ? __ldg(g_cols + (size_t)p * 8 + c) : zero;
+            for (int j = 0; j < T; j++) {
+                const int s = j & 1, n = j >> 1;
+                uint4 cur[8];
+#pragma unroll
+                for (int c = 0; c < 8; c++) cur[c] = nx[c];
+                const int cn = (j + 1) * TN + p;
+                const bool more = j + 1 < T && p < TN && cn < n_cols;
+#pragma unroll
+                for (int c = 0; c < 8; c++) nx[c] = more ? __ldg(g_cols + (size_t)cn * 8 + c) : zero;
+                umma::mbar_wait(BAR(2 + s), (n & 1) ^ 1);              // the UMMAs that read this stage have completed
+                if (p < TN) {
+                    uint8_t* rowp = sB + s * OP_BYTES + row_off;
+#pragma unroll
+                    for (int c = 0; c < 8; c++) *reinterpret_cast<uint4*>(rowp + ((c ^ (p & 7)) << 4)) = cur[c];
+                }
+                umma::fence_proxy_async();
+                umma::mbar_arrive(BAR(0 + s));
+            }
+        } else {
         {
             const int r = row0 + p;
             const bool valid = r < n_rows;
@@ -273,11 +359,13 @@ knn2_hamming_mx_kernel(const uint8_t* __restrict__ d1, int n1_max, const int32_t
             umma::fence_proxy_async();
             umma::mbar_arrive(BAR(0 + s));
         }
+        }
     } else {
         // ===================================== UMMA issuer ==================================================
         if (lane == 0) {
             const uint32_t aA = umma::smem_u32(sA), aB = umma::smem_u32(sB), aBias = umma::smem_u32(sBias);
             const uint32_t sf1 = tmem_base + SF_ONE, sf64 = tmem_base + SF_64, sf2p14 = tmem_base + SF_2P14;
+            if (MODE == 2) umma::mbar_wait(BAR(8), 0);                 // the row tile
             for (int j = 0; j < T; j++) {
                 const int s = j & 1, n = j >> 1;
                 umma::mbar_wait(BAR(0 + s), n & 1);                    // operands of tile j are in shared memory
@@ -313,13 +401,17 @@ knn2_hamming_mx_kernel(const uint8_t* __restrict__ d1, int n1_max, const int32_t
 
 // 4-bit tensor-core implementation behind vsb_knn2_hamming_keys (csrc/knn_hamming.cu dispatches on ctx->knn_impl == 3)
 int vsb_knn2_hamming_mx(vsb_ctx* ctx, const uint8_t* d1, int n1_max, const int32_t* n1, const uint8_t* d2, int n2_max,
-                        const int32_t* n2, int count, uint32_t* key12, uint32_t* key21, cudaStream_t st) {
+                        const int32_t* n2, int count, uint32_t* key12, uint32_t* key21, int pre, cudaStream_t st) {
     if (!ctx || count < 0 || n1_max < 0 || n2_max < 0) return VSB_ERR_INVALID;
     if (n1_max > (int)KEY_IDX_MASK || n2_max > (int)KEY_IDX_MASK) return VSB_ERR_CAPACITY;
     if (count == 0 || (n1_max == 0 && n2_max == 0)) return VSB_OK;
     if (!ctx->attr_knn_mx_done) {
-        VSB_CUDA(ctx, cudaFuncSetAttribute(knn2_hamming_mx_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, MX_SMEM));
-        VSB_CUDA(ctx, cudaFuncSetAttribute(knn2_hamming_mx_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+        VSB_CUDA(ctx, cudaFuncSetAttribute(knn2_hamming_mx_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, MX_SMEM));
+        VSB_CUDA(ctx, cudaFuncSetAttribute(knn2_hamming_mx_kernel<0>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+        VSB_CUDA(ctx, cudaFuncSetAttribute(knn2_hamming_mx_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, MX_SMEM));
+        VSB_CUDA(ctx, cudaFuncSetAttribute(knn2_hamming_mx_kernel<1>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+        VSB_CUDA(ctx, cudaFuncSetAttribute(knn2_hamming_mx_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, MX_SMEM));
+        VSB_CUDA(ctx, cudaFuncSetAttribute(knn2_hamming_mx_kernel<2>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
         mx_bias_init_kernel<<<4, 256, 0, st>>>();
         VSB_LAUNCHED(ctx);
         ctx->attr_knn_mx_done = 1;
@@ -328,10 +420,44 @@ int vsb_knn2_hamming_mx(vsb_ctx* ctx, const uint8_t* d1, int n1_max, const int32
     for (int z0 = 0; z0 < count; z0 += 65535) {
         const int zc = count - z0 < 65535 ? count - z0 : 65535;
         dim3 grid(row_tiles, 2, zc);
+        const uint8_t* a = d1 + (size_t)z0 * n1_max * 32;
+        const uint8_t* b = d2 + (size_t)z0 * n2_max * 32;
+        uint32_t* k12 = key12 + (size_t)z0 * n1_max * 2;
+        uint32_t* k21 = key21 + (size_t)z0 * n2_max * 2;
         ProfScope ps(ctx, VSB_K_KNN_HAMMING, st);
-        knn2_hamming_mx_kernel<<<grid, MX_THREADS, MX_SMEM, st>>>(d1 + (size_t)z0 * n1_max * 32, n1_max, n1 ? n1 + z0 : nullptr,
-                                                                   d2 + (size_t)z0 * n2_max * 32, n2_max, n2 ? n2 + z0 : nullptr,
-                                                                   key12 + (size_t)z0 * n1_max * 2, key21 + (size_t)z0 * n2_max * 2);
+        if (pre == 2) {
+            const int rows_pad = ((n1_max > n2_max ? n1_max : n2_max) + 383) / 384 * 384;
+            const size_t bb = (size_t)zc * rows_pad * 128;
+            void* scratch = nullptr;
+            int rc = vsb_scratch2_reserve(ctx, 2 * bb + 256, &scratch);
+            if (rc) return rc;
+            uint8_t* e1 = static_cast<uint8_t*>(scratch);
+            uint8_t* e2 = e1 + bb;
+            const long long chunks = (long long)zc * rows_pad * 8;
+            mx_expand_swizzled_kernel<<<(unsigned)((chunks + 255) / 256), 256, 0, st>>>(a, n1_max, n1 ? n1 + z0 : nullptr, rows_pad, zc,
+                                                                                         reinterpret_cast<uint4*>(e1));
+            VSB_LAUNCHED(ctx);
+            mx_expand_swizzled_kernel<<<(unsigned)((chunks + 255) / 256), 256, 0, st>>>(b, n2_max, n2 ? n2 + z0 : nullptr, rows_pad, zc,
+                                                                                         reinterpret_cast<uint4*>(e2));
+            VSB_LAUNCHED(ctx);
+            knn2_hamming_mx_kernel<2><<<grid, MX_THREADS, MX_SMEM, st>>>(e1, n1_max, n1 ? n1 + z0 : nullptr, e2, n2_max,
+                                                                         n2 ? n2 + z0 : nullptr, k12, k21, rows_pad);
+        } else if (pre) {
+            const size_t b1 = ((size_t)zc * n1_max * 128 + 255) & ~(size_t)255, b2 = ((size_t)zc * n2_max * 128 + 255) & ~(size_t)255;
+            void* scratch = nullptr;
+            int rc = vsb_scratch2_reserve(ctx, b1 + b2 + 256, &scratch);
+            if (rc) return rc;
+            uint8_t* e1 = static_cast<uint8_t*>(scratch);
+            uint8_t* e2 = e1 + b1;
+            const long long c1 = (long long)zc * n1_max * 8, c2 = (long long)zc * n2_max * 8;
+            if (c1) { mx_expand_kernel<<<(unsigned)((c1 + 255) / 256), 256, 0, st>>>(a, c1, reinterpret_cast<uint4*>(e1)); VSB_LAUNCHED(ctx); }
+            if (c2) { mx_expand_kernel<<<(unsigned)((c2 + 255) / 256), 256, 0, st>>>(b, c2, reinterpret_cast<uint4*>(e2)); VSB_LAUNCHED(ctx); }
+            knn2_hamming_mx_kernel<1><<<grid, MX_THREADS, MX_SMEM, st>>>(e1, n1_max, n1 ? n1 + z0 : nullptr, e2, n2_max,
+                                                                         n2 ? n2 + z0 : nullptr, k12, k21, 0);
+        } else {
+            knn2_hamming_mx_kernel<0><<<grid, MX_THREADS, MX_SMEM, st>>>(a, n1_max, n1 ? n1 + z0 : nullptr, b, n2_max,
+                                                                         n2 ? n2 + z0 : nullptr, k12, k21, 0);
+        }
         VSB_LAUNCHED(ctx);
     }
     return VSB_OK;
