@@ -2,6 +2,7 @@
 kNN-2 results of both epilogues (32-bit keys, packed 16x2 keys) bit-exact against the CPU oracle — indices and
 distances, ties to the lowest index, ragged and degenerate sizes, the extremes 0 and 256."""
 import ctypes as C
+import os
 
 import numpy as np
 import pytest
