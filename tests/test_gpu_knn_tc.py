@@ -8,9 +8,9 @@ import numpy as np
 import pytest
 
 pytestmark = pytest.mark.gpu
-# 1, 2: int8 tensor-core kernel (32-bit / packed epilogue); 3: 4-bit operands (kind::mxf4); extra variants under test can be
-# added from the environment (VSB_TEST_KNN_IMPLS=4,5)
-IMPLS = [1, 2, 3] + [int(v) for v in os.environ.get("VSB_TEST_KNN_IMPLS", "").split(",") if v]
+# 1, 2: int8 tensor-core kernel (32-bit / packed epilogue, 2 = the default); 3, 4, 5: 4-bit operands (kind::mxf4): expanded in
+# the kernel / pre-expanded rows copied by the producers / persistent CTAs fetching pre-swizzled tiles with cp.async.bulk
+IMPLS = [1, 2, 3, 4, 5] + [int(v) for v in os.environ.get("VSB_TEST_KNN_IMPLS", "").split(",") if v]
 
 
 def _hamming_matrix(d1, d2):

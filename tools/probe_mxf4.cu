@@ -36,14 +36,14 @@ __device__ __forceinline__ uint32_t expand8(uint32_t v) {
 
 __global__ void __launch_bounds__(160) probe_kernel(const uint8_t* __restrict__ a_bits, const uint8_t* __restrict__ b_bits,
                                                     float* __restrict__ out, uint32_t sfa_byte, uint32_t sfb_byte,
-                                                    uint32_t idesc_v) {
+                                                    uint32_t idesc_v, long long* __restrict__ clocks, int rep) {
     extern __shared__ __align__(1024) uint8_t smem[];
     uint8_t* sA = smem;
     uint8_t* sB = smem + 16384;
     uint64_t* bar = reinterpret_cast<uint64_t*>(smem + 32768);
     uint32_t* slot = reinterpret_cast<uint32_t*>(smem + 32768 + 64);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    if (tid == 0) { umma::mbar_init(umma::smem_u32(bar), 1); umma::fence_mbar_init(); }
+    if (tid == 0) { umma::mbar_init(umma::smem_u32(bar), 1); umma::mbar_init(umma::smem_u32(bar + 1), 1); umma::fence_mbar_init(); }
     if (warp == 4) umma::tmem_alloc<512>(umma::smem_u32(slot));
     if (tid < ROWS) {
         const int p = tid;
@@ -82,6 +82,22 @@ __global__ void __launch_bounds__(160) probe_kernel(const uint8_t* __restrict__ 
             mma_mxf4(tmem_base, da, db, idesc_v, k > 0 ? 1u : 0u, tmem_base + 256, tmem_base + 288);
         }
         umma::commit(umma::smem_u32(bar));
+        if (clocks && rep > 0) {
+            // issue cost vs execution time of back-to-back UMMAs (alternating between two accumulator regions)
+            umma::mbar_wait(umma::smem_u32(bar), 0);
+            const long long t0 = clock64();
+            for (int r = 0; r < rep; r++)
+                for (int k = 0; k < 4; k++) {
+                    const uint64_t da = umma::smem_desc(aA + k * 32, 16, 1024, umma::LAYOUT_SW128);
+                    const uint64_t db = umma::smem_desc(aB + k * 32, 16, 1024, umma::LAYOUT_SW128);
+                    mma_mxf4(tmem_base + 128 * (r & 1), da, db, idesc_v, 1u, tmem_base + 256, tmem_base + 288);
+                }
+            const long long t1 = clock64();
+            umma::commit(umma::smem_u32(bar + 1));
+            umma::mbar_wait(umma::smem_u32(bar + 1), 0);
+            const long long t2 = clock64();
+            clocks[0] = t1 - t0; clocks[1] = t2 - t0;
+        }
     }
     if (warp < 4) {
         umma::mbar_wait(umma::smem_u32(bar), 0);
@@ -111,6 +127,8 @@ int main() {
     cudaMalloc(&da, a.size()); cudaMalloc(&db, b.size()); cudaMalloc(&dout, ROWS * 128 * 4);
     cudaMemcpy(da, a.data(), a.size(), cudaMemcpyHostToDevice);
     cudaMemcpy(db, b.data(), b.size(), cudaMemcpyHostToDevice);
+    long long* dclk;
+    cudaMalloc(&dclk, 16);
     cudaFuncSetAttribute(probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 34000);
     // instruction descriptor (block scaled): a/b format E2M1 = 1 at [7,10) / [10,13), N >> 3 at [17,23), scale format UE8M0 = 1
     // at bit 23, M >> 4 at [24,29), K64 (bit 31 = 0)
@@ -118,7 +136,7 @@ int main() {
     for (int trial = 0; trial < 2; trial++) {
         const uint32_t sfa = 0x7F, sfb = trial ? 0x85 : 0x7F;       // 1 x 1, then 1 x 64
         cudaMemset(dout, 0, ROWS * 128 * 4);
-        probe_kernel<<<1, 160, 34000>>>(da, db, dout, sfa, sfb, idesc);
+        probe_kernel<<<1, 160, 34000>>>(da, db, dout, sfa, sfb, idesc, trial ? dclk : nullptr, 256);
         cudaError_t e = cudaDeviceSynchronize();
         if (e != cudaSuccess) { printf("CUDA error: %s\n", cudaGetErrorString(e)); return 1; }
         std::vector<float> out(ROWS * 128);
@@ -134,5 +152,9 @@ int main() {
         printf("trial %d (scale %g): %d / %d accumulators exact; out[0][0..3] = %g %g %g %g (expect %g ...), out[1][1] = %g (expect %g)\n",
                trial, s, ok, ROWS * 128, out[0], out[1], out[2], out[3], s * 256, out[129], -s * 256);
     }
+    long long clk[2];
+    cudaMemcpy(clk, dclk, 16, cudaMemcpyDeviceToHost);
+    printf("1024 back-to-back UMMAs (M128 N128 K64 mxf4) from one thread: issue %.1f cycles each, issue + execution %.1f cycles each\n",
+           clk[0] / 1024.0, clk[1] / 1024.0);
     return 0;
 }

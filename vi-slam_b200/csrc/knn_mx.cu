@@ -397,6 +397,252 @@ knn2_hamming_mx_kernel(const uint8_t* __restrict__ d1, int n1_max, const int32_t
     }
 }
 
+
+// ===== knn_impl 5: persistent CTAs, bulk-copy pipeline ==========================================================================
+// Measured on the per-row-tile kernels above: a CTA costs about 5 us before and after its tiles (launch, barrier and TMEM set-up,
+// first operand latencies, tear-down) and only ~0.5 us per tile, so at 1000 x 1000 (11 tiles per CTA) the fixed part is half of
+// the run time.  Here two CTAs per SM stay resident and walk over the work items (problem, direction, row tile): barriers,
+// tensor memory, scale factors and the bias tile are set up once; the row tile is double-buffered, so the next item's rows are
+// in flight while the current item is multiplied; the column tiles run through a ring of BS stages.  Operand tiles are fetched
+// by ONE thread with one cp.async.bulk each from descriptors that were expanded, swizzled and zero-padded once per call
+// (mx_expand_swizzled_kernel).  One constant tile (g_mx_bias_tile, also a bulk copy) carries the four bias operand slices:
+// K slices 0, 1 = row side, 2, 3 = column side.  Columns past the end of the set are masked in the epilogue of an item's
+// last tile (their operand rows are zero, so the accumulator holds the bias alone).  Two groups of four epilogue warps
+// alternate over the tiles (accumulator stage = tile parity); a row's two partial results meet in shared memory per item.
+constexpr int BS = 5;                                   // column-tile stages
+constexpr int B_STAGE = TN * 128;                       // 12 KB
+constexpr int BK_OFF_A = 0;                             // two row-tile stages
+constexpr int BK_OFF_BIAS = 2 * OP_BYTES;
+constexpr int BK_OFF_B = 3 * OP_BYTES;
+constexpr int BK_OFF_BAR = BK_OFF_B + BS * B_STAGE;
+constexpr int BK_OFF_PART = BK_OFF_BAR + 256;           // [2][128] partial top-2 of the odd-tile group
+constexpr int BK_SMEM = BK_OFF_PART + 2 * 1024;
+constexpr int BK_THREADS = 320;                         // 8 epilogue warps, the loader warp, the UMMA issuer warp
+__device__ uint4 g_mx_bias_tile[128 * 8];               // the swizzled shared-memory image of the bias tile
+__global__ void mx_bias_tile_init_kernel() {
+    const int i = blockIdx.x * 256 + threadIdx.x;       // (row, 16-byte chunk of the 128-byte row)
+    if (i >= 128 * 8) return;
+    const int r = i >> 3, c = i & 7;
+    uint32_t w[4];
+    for (int q = 0; q < 4; q++) {
+        uint32_t v = 0u;
+        for (int j = 0; j < 4; j++) {
+            const int b = 16 * c + 4 * q + j;           // byte of the row: 0..63 row-side slices, 64..127 column-side slices
+            v |= (b < 64 ? bias_byte(0, r, b, TN) : bias_byte(1, r, b - 64, TN)) << (8 * j);
+        }
+        w[q] = v;
+    }
+    g_mx_bias_tile[r * 8 + (c ^ (r & 7))] = make_uint4(w[0], w[1], w[2], w[3]);
+}
+
+struct MxItem { int prob, dir, row0, n_rows, n_cols, T; };
+__device__ __forceinline__ bool mx_item(long long it, int row_tiles, int n1_max, const int32_t* n1_arr, int n2_max,
+                                        const int32_t* n2_arr, MxItem& w) {
+    w.prob = (int)(it / (2 * row_tiles));
+    const int rem = (int)(it - (long long)w.prob * 2 * row_tiles);
+    w.dir = rem / row_tiles;
+    w.row0 = (rem - w.dir * row_tiles) * TM;
+    const int n1 = n1_arr ? min(n1_arr[w.prob], n1_max) : n1_max;
+    const int n2 = n2_arr ? min(n2_arr[w.prob], n2_max) : n2_max;
+    w.n_rows = w.dir ? n2 : n1;
+    w.n_cols = w.dir ? n1 : n2;
+    w.T = (w.n_cols + TN - 1) / TN;
+    return w.row0 < w.n_rows;                                     // false: nothing to do for this item (every role agrees)
+}
+
+__global__ void __launch_bounds__(BK_THREADS, 2)
+knn2_hamming_mx_bulk_kernel(const uint8_t* __restrict__ e1, int n1_max, const int32_t* __restrict__ n1_arr,
+                            const uint8_t* __restrict__ e2, int n2_max, const int32_t* __restrict__ n2_arr,
+                            uint32_t* __restrict__ key12, uint32_t* __restrict__ key21, int rows_pad, int row_tiles,
+                            long long n_items) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    uint8_t* sA = smem + BK_OFF_A;
+    uint8_t* sBias = smem + BK_OFF_BIAS;
+    uint8_t* sB = smem + BK_OFF_B;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + BK_OFF_BAR);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + BK_OFF_BAR + 224);
+    uint2* s_part = reinterpret_cast<uint2*>(smem + BK_OFF_PART);
+    const uint32_t bar0 = umma::smem_u32(bars);
+    // barrier ids: bfull[s] = s, bempty[s] = BS + s, tfull[t] = 2 BS + t, tempty[t] = 2 BS + 2 + t, afull[a] = 2 BS + 4 + a,
+    // aempty[a] = 2 BS + 6 + a, biasfull = 2 BS + 8
+    auto BAR = [&](int id) { return bar0 + 8u * (uint32_t)id; };
+    constexpr int TFULL = 2 * BS, TEMPTY = 2 * BS + 2, AFULL = 2 * BS + 4, AEMPTY = 2 * BS + 6, BIASFULL = 2 * BS + 8;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+    if (tid == 0) {
+        for (int s = 0; s < BS; s++) { umma::mbar_init(BAR(s), 1); umma::mbar_init(BAR(BS + s), 1); }
+        umma::mbar_init(BAR(TFULL), 1); umma::mbar_init(BAR(TFULL + 1), 1);                 // tcgen05.commit
+        umma::mbar_init(BAR(TEMPTY), 128); umma::mbar_init(BAR(TEMPTY + 1), 128);           // one epilogue group each
+        umma::mbar_init(BAR(AFULL), 1); umma::mbar_init(BAR(AFULL + 1), 1);
+        umma::mbar_init(BAR(AEMPTY), 1); umma::mbar_init(BAR(AEMPTY + 1), 1);
+        umma::mbar_init(BAR(BIASFULL), 1);
+        umma::fence_mbar_init();
+    }
+    if (warp == 9) umma::tmem_alloc<TMEM_COLS>(umma::smem_u32(tmem_slot));
+    umma::fence_before_sync();
+    __syncthreads();
+    umma::fence_after_sync();
+    const uint32_t tmem_base = *tmem_slot;
+    if ((bar0 - BK_OFF_BAR) & 1023u) __trap();
+
+    if (warp < 8) {
+        // ===================================== epilogue =====================================================
+        const int grp = warp >> 2, wq = warp & 3;
+        if (grp == 0) {   // constant block scales (see knn2_hamming_mx_kernel)
+            const uint32_t lane_base = tmem_base + ((uint32_t)(wq * 32) << 16);
+#pragma unroll
+            for (int c = 0; c < 8; c += 4) {
+                tmem_st4(lane_base + SF_ONE + c, 0x7F7F7F7Fu);
+                tmem_st4(lane_base + SF_64 + c, 0x85858585u);
+                tmem_st4(lane_base + SF_2P14 + c, 0x8D8D8D8Du);
+            }
+            tmem_wait_st();
+            umma::fence_before_sync();
+            asm volatile("bar.sync 1, 160;" ::: "memory");                // group 0 + the UMMA issuer warp
+        }
+        long long tc = 0;                                                 // tiles issued so far by this CTA (all items)
+        int ic = 0;
+        for (long long it = blockIdx.x; it < n_items; it += gridDim.x) {
+            MxItem w;
+            if (!mx_item(it, row_tiles, n1_max, n1_arr, n2_max, n2_arr, w)) continue;
+            const int last_valid = w.n_cols - (w.T - 1) * TN;
+            const int row = w.row0 + wq * 32 + lane;
+            uint32_t gb0 = KEY_INF, gb1 = KEY_INF;
+            for (int j = 0; j < w.T; j++) {
+                const long long g = tc + j;
+                if ((int)(g & 1) != grp) continue;
+                const int t = grp;
+                umma::mbar_wait(BAR(TFULL + t), (uint32_t)((g >> 1) & 1));
+                umma::fence_after_sync();
+                const uint32_t taddr = tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(t * TN);
+                uint32_t pb0[2] = {0u, 0u}, pb1[2] = {0u, 0u};
+                uint32_t v[32], u[16];
+                umma::tmem_ld32_pack16(taddr, v);
+                tmem_ld16_pack16(taddr + 64, u);
+                umma::tmem_wait_ld();
+                umma::fence_before_sync();
+                umma::mbar_arrive(BAR(TEMPTY + t));                       // accumulator stage is free again
+                if (j == w.T - 1 && last_valid < TN) {                    // columns past the end of the set: key 0
+#pragma unroll
+                    for (int i = 0; i < 32; i++) {
+                        const int c = 2 * i;
+                        v[i] = c + 1 < last_valid ? v[i] : (c < last_valid ? (v[i] & 0xFFFFu) : 0u);
+                    }
+#pragma unroll
+                    for (int i = 0; i < 16; i++) {
+                        const int c = 64 + 2 * i;
+                        u[i] = c + 1 < last_valid ? u[i] : (c < last_valid ? (u[i] & 0xFFFFu) : 0u);
+                    }
+                }
+#pragma unroll
+                for (int i = 0; i < 32; i += 2) top2max_insert2_u16x2(pb0[(i >> 1) & 1], pb1[(i >> 1) & 1], v[i], v[i + 1]);
+#pragma unroll
+                for (int i = 0; i < 16; i += 2) top2max_insert2_u16x2(pb0[(i >> 1) & 1], pb1[(i >> 1) & 1], u[i], u[i + 1]);
+                top2max_merge_u16x2(pb0[0], pb1[0], pb0[1], pb1[1]);
+                const uint32_t k16[4] = {pb0[0] & 0xFFFFu, pb0[0] >> 16, pb1[0] & 0xFFFFu, pb1[0] >> 16};
+                const int col0 = j * TN;
+#pragma unroll
+                for (int q = 0; q < 4; q++) {
+                    const uint32_t tt = k16[q] - 1u;                    // 128 * (256 - hamming) + (127 - c)
+                    const uint32_t gk = (k16[q] == 0u) ? KEY_INF
+                                                       : (((256u - (tt >> 7)) << KEY_SHIFT) | (uint32_t)(col0 + 127 - (int)(tt & 127u)));
+                    top2_insert(gb0, gb1, gk);
+                }
+            }
+            tc += w.T;
+            // the two groups' partial results of this item (double-buffered by item parity: the barrier of item ic + 1 orders the
+            // next write of a buffer after this read)
+            uint2* part = s_part + (ic & 1) * 128;
+            if (grp == 1) part[wq * 32 + lane] = make_uint2(gb0, gb1);
+            asm volatile("bar.sync 2, 256;" ::: "memory");                // the eight epilogue warps
+            if (grp == 0) {
+                const uint2 o = part[wq * 32 + lane];
+                top2_merge(gb0, gb1, o.x, o.y);
+                uint32_t* keys_out = w.dir ? key21 + (size_t)w.prob * n2_max * 2 : key12 + (size_t)w.prob * n1_max * 2;
+                if (row < w.n_rows) *reinterpret_cast<uint2*>(keys_out + (size_t)row * 2) = make_uint2(gb0, gb1);
+            }
+            ic++;
+        }
+    } else if (warp == 8) {
+        // ===================================== loader: one thread ============================================
+        if (lane == 0) {
+            mbar_expect_tx(BAR(BIASFULL), OP_BYTES);
+            bulk_g2s(umma::smem_u32(sBias), g_mx_bias_tile, OP_BYTES, BAR(BIASFULL));
+            long long tc = 0;
+            int ic = 0;
+            for (long long it = blockIdx.x; it < n_items; it += gridDim.x) {
+                MxItem w;
+                if (!mx_item(it, row_tiles, n1_max, n1_arr, n2_max, n2_arr, w)) continue;
+                const uint8_t* g_rows = (w.dir ? e2 : e1) + (size_t)w.prob * rows_pad * 128;
+                const uint8_t* g_cols = (w.dir ? e1 : e2) + (size_t)w.prob * rows_pad * 128;
+                const int a = ic & 1;
+                umma::mbar_wait(BAR(AEMPTY + a), (uint32_t)(((ic >> 1) & 1) ^ 1));       // the item two back has been multiplied
+                mbar_expect_tx(BAR(AFULL + a), OP_BYTES);
+                bulk_g2s(umma::smem_u32(sA + a * OP_BYTES), g_rows + (size_t)w.row0 * 128, OP_BYTES, BAR(AFULL + a));
+                for (int j = 0; j < w.T; j++) {
+                    const long long g = tc + j;
+                    const int s = (int)(g % BS);
+                    umma::mbar_wait(BAR(BS + s), (uint32_t)(((g / BS) & 1) ^ 1));        // the UMMAs that read this stage have completed
+                    mbar_expect_tx(BAR(s), B_STAGE);
+                    bulk_g2s(umma::smem_u32(sB + s * B_STAGE), g_cols + (size_t)j * B_STAGE, B_STAGE, BAR(s));
+                }
+                tc += w.T;
+                ic++;
+            }
+        }
+        __syncwarp();
+    } else {
+        // ===================================== UMMA issuer ==================================================
+        asm volatile("bar.sync 1, 160;" ::: "memory");                    // the scale factors are in tensor memory
+        umma::fence_after_sync();
+        if (lane == 0) {
+            const uint32_t aA = umma::smem_u32(sA), aB = umma::smem_u32(sB), aBias = umma::smem_u32(sBias);
+            const uint32_t sf1 = tmem_base + SF_ONE, sf64 = tmem_base + SF_64, sf2p14 = tmem_base + SF_2P14;
+            const uint64_t da_b1 = umma::smem_desc(aBias, 16, 1024, umma::LAYOUT_SW128);
+            const uint64_t da_b2 = umma::smem_desc(aBias + 32, 16, 1024, umma::LAYOUT_SW128);
+            const uint64_t db_b1 = umma::smem_desc(aBias + 64, 16, 1024, umma::LAYOUT_SW128);
+            const uint64_t db_b2 = umma::smem_desc(aBias + 96, 16, 1024, umma::LAYOUT_SW128);
+            umma::mbar_wait(BAR(BIASFULL), 0);
+            long long tc = 0;
+            int ic = 0;
+            for (long long it = blockIdx.x; it < n_items; it += gridDim.x) {
+                MxItem w;
+                if (!mx_item(it, row_tiles, n1_max, n1_arr, n2_max, n2_arr, w)) continue;
+                const int a = ic & 1;
+                umma::mbar_wait(BAR(AFULL + a), (uint32_t)((ic >> 1) & 1));              // this item's row tile
+                for (int j = 0; j < w.T; j++) {
+                    const long long g = tc + j;
+                    const int s = (int)(g % BS), t = (int)(g & 1);
+                    umma::mbar_wait(BAR(s), (uint32_t)((g / BS) & 1));                   // operands of the tile are in shared memory
+                    umma::mbar_wait(BAR(TEMPTY + t), (uint32_t)(((g >> 1) & 1) ^ 1));    // the epilogue has drained this stage
+                    umma::fence_after_sync();
+                    const uint32_t d_tmem = tmem_base + (uint32_t)(t * TN);
+#pragma unroll
+                    for (int k = 0; k < 4; k++) {
+                        const uint64_t da = umma::smem_desc(aA + a * OP_BYTES + k * 32, 16, 1024, umma::LAYOUT_SW128);
+                        const uint64_t db = umma::smem_desc(aB + s * B_STAGE + k * 32, 16, 1024, umma::LAYOUT_SW128);
+                        mma_mxf4(d_tmem, da, db, k > 0 ? 1u : 0u, sf1, sf64);
+                    }
+                    mma_mxf4(d_tmem, da_b1, db_b1, 1u, sf2p14, sf1);      // + 2^23 + 2^14
+                    mma_mxf4(d_tmem, da_b2, db_b2, 1u, sf1, sf1);         // + 128 - c
+                    umma::commit(BAR(BS + s));
+                    umma::commit(BAR(TFULL + t));
+                }
+                umma::commit(BAR(AEMPTY + a));                             // the row tile may be overwritten
+                tc += w.T;
+                ic++;
+            }
+        }
+        __syncwarp();
+    }
+    umma::fence_before_sync();
+    __syncthreads();
+    if (warp == 9) {
+        umma::fence_after_sync();
+        umma::tmem_dealloc<TMEM_COLS>(tmem_base);
+    }
+}
+
 }  // namespace
 
 // 4-bit tensor-core implementation behind vsb_knn2_hamming_keys (csrc/knn_hamming.cu dispatches on ctx->knn_impl == 3)
@@ -410,8 +656,10 @@ int vsb_knn2_hamming_mx(vsb_ctx* ctx, const uint8_t* d1, int n1_max, const int32
         VSB_CUDA(ctx, cudaFuncSetAttribute(knn2_hamming_mx_kernel<0>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
         VSB_CUDA(ctx, cudaFuncSetAttribute(knn2_hamming_mx_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, MX_SMEM));
         VSB_CUDA(ctx, cudaFuncSetAttribute(knn2_hamming_mx_kernel<1>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-        VSB_CUDA(ctx, cudaFuncSetAttribute(knn2_hamming_mx_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, MX_SMEM));
-        VSB_CUDA(ctx, cudaFuncSetAttribute(knn2_hamming_mx_kernel<2>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+        VSB_CUDA(ctx, cudaFuncSetAttribute(knn2_hamming_mx_bulk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, BK_SMEM));
+        VSB_CUDA(ctx, cudaFuncSetAttribute(knn2_hamming_mx_bulk_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+        mx_bias_tile_init_kernel<<<4, 256, 0, st>>>();
+        VSB_LAUNCHED(ctx);
         mx_bias_init_kernel<<<4, 256, 0, st>>>();
         VSB_LAUNCHED(ctx);
         ctx->attr_knn_mx_done = 1;
@@ -440,8 +688,11 @@ int vsb_knn2_hamming_mx(vsb_ctx* ctx, const uint8_t* d1, int n1_max, const int32
             mx_expand_swizzled_kernel<<<(unsigned)((chunks + 255) / 256), 256, 0, st>>>(b, n2_max, n2 ? n2 + z0 : nullptr, rows_pad, zc,
                                                                                          reinterpret_cast<uint4*>(e2));
             VSB_LAUNCHED(ctx);
-            knn2_hamming_mx_kernel<2><<<grid, MX_THREADS, MX_SMEM, st>>>(e1, n1_max, n1 ? n1 + z0 : nullptr, e2, n2_max,
-                                                                         n2 ? n2 + z0 : nullptr, k12, k21, rows_pad);
+            const long long n_items = (long long)zc * 2 * row_tiles;
+            const int resident = 2 * (ctx->sm_count > 0 ? ctx->sm_count : 148);
+            const int ctas = (int)(n_items < resident ? n_items : resident);
+            knn2_hamming_mx_bulk_kernel<<<ctas, BK_THREADS, BK_SMEM, st>>>(e1, n1_max, n1 ? n1 + z0 : nullptr, e2, n2_max,
+                                                                           n2 ? n2 + z0 : nullptr, k12, k21, rows_pad, row_tiles, n_items);
         } else if (pre) {
             const size_t b1 = ((size_t)zc * n1_max * 128 + 255) & ~(size_t)255, b2 = ((size_t)zc * n2_max * 128 + 255) & ~(size_t)255;
             void* scratch = nullptr;
