@@ -417,7 +417,7 @@ constexpr int BK_OFF_B = 3 * OP_BYTES;
 constexpr int BK_OFF_BAR = BK_OFF_B + BS * B_STAGE;
 constexpr int BK_OFF_PART = BK_OFF_BAR + 256;           // [2][128] partial top-2 of the odd-tile group
 constexpr int BK_SMEM = BK_OFF_PART + 2 * 1024;
-constexpr int BK_THREADS = 320;                         // 8 epilogue warps, the loader warp, the UMMA issuer warp
+constexpr int BK_THREADS = 352;                         // 8 epilogue warps, the loader warp, two UMMA issuer warps (even / odd tiles)
 __device__ uint4 g_mx_bias_tile[128 * 8];               // the swizzled shared-memory image of the bias tile
 __global__ void mx_bias_tile_init_kernel() {
     const int i = blockIdx.x * 256 + threadIdx.x;       // (row, 16-byte chunk of the 128-byte row)
@@ -474,7 +474,7 @@ knn2_hamming_mx_bulk_kernel(const uint8_t* __restrict__ e1, int n1_max, const in
         umma::mbar_init(BAR(TFULL), 1); umma::mbar_init(BAR(TFULL + 1), 1);                 // tcgen05.commit
         umma::mbar_init(BAR(TEMPTY), 128); umma::mbar_init(BAR(TEMPTY + 1), 128);           // one epilogue group each
         umma::mbar_init(BAR(AFULL), 1); umma::mbar_init(BAR(AFULL + 1), 1);
-        umma::mbar_init(BAR(AEMPTY), 1); umma::mbar_init(BAR(AEMPTY + 1), 1);
+        umma::mbar_init(BAR(AEMPTY), 2); umma::mbar_init(BAR(AEMPTY + 1), 2);               // both issuers
         umma::mbar_init(BAR(BIASFULL), 1);
         umma::fence_mbar_init();
     }
@@ -498,9 +498,9 @@ knn2_hamming_mx_bulk_kernel(const uint8_t* __restrict__ e1, int n1_max, const in
             }
             tmem_wait_st();
             umma::fence_before_sync();
-            asm volatile("bar.sync 1, 160;" ::: "memory");                // group 0 + the UMMA issuer warp
+            asm volatile("bar.sync 1, 192;" ::: "memory");                // group 0 + the two UMMA issuer warps
         }
-        long long tc = 0;                                                 // tiles issued so far by this CTA (all items)
+        uint32_t tc = 0;                                                  // tiles issued so far by this CTA (all items)
         int ic = 0;
         for (long long it = blockIdx.x; it < n_items; it += gridDim.x) {
             MxItem w;
@@ -508,11 +508,10 @@ knn2_hamming_mx_bulk_kernel(const uint8_t* __restrict__ e1, int n1_max, const in
             const int last_valid = w.n_cols - (w.T - 1) * TN;
             const int row = w.row0 + wq * 32 + lane;
             uint32_t gb0 = KEY_INF, gb1 = KEY_INF;
-            for (int j = 0; j < w.T; j++) {
-                const long long g = tc + j;
-                if ((int)(g & 1) != grp) continue;
+            for (int j = (int)((tc ^ (uint32_t)grp) & 1u); j < w.T; j += 2) {      // this group's tiles of the item
+                const uint32_t g = tc + (uint32_t)j;
                 const int t = grp;
-                umma::mbar_wait(BAR(TFULL + t), (uint32_t)((g >> 1) & 1));
+                umma::mbar_wait(BAR(TFULL + t), (g >> 1) & 1u);
                 umma::fence_after_sync();
                 const uint32_t taddr = tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(t * TN);
                 uint32_t pb0[2] = {0u, 0u}, pb1[2] = {0u, 0u};
@@ -549,7 +548,7 @@ knn2_hamming_mx_bulk_kernel(const uint8_t* __restrict__ e1, int n1_max, const in
                     top2_insert(gb0, gb1, gk);
                 }
             }
-            tc += w.T;
+            tc += (uint32_t)w.T;
             // the two groups' partial results of this item (double-buffered by item parity: the barrier of item ic + 1 orders the
             // next write of a buffer after this read)
             uint2* part = s_part + (ic & 1) * 128;
@@ -568,7 +567,8 @@ knn2_hamming_mx_bulk_kernel(const uint8_t* __restrict__ e1, int n1_max, const in
         if (lane == 0) {
             mbar_expect_tx(BAR(BIASFULL), OP_BYTES);
             bulk_g2s(umma::smem_u32(sBias), g_mx_bias_tile, OP_BYTES, BAR(BIASFULL));
-            long long tc = 0;
+            int s = 0;
+            uint32_t sphase = 0;                                          // completed passes over the ring, mod 2
             int ic = 0;
             for (long long it = blockIdx.x; it < n_items; it += gridDim.x) {
                 MxItem w;
@@ -579,21 +579,24 @@ knn2_hamming_mx_bulk_kernel(const uint8_t* __restrict__ e1, int n1_max, const in
                 umma::mbar_wait(BAR(AEMPTY + a), (uint32_t)(((ic >> 1) & 1) ^ 1));       // the item two back has been multiplied
                 mbar_expect_tx(BAR(AFULL + a), OP_BYTES);
                 bulk_g2s(umma::smem_u32(sA + a * OP_BYTES), g_rows + (size_t)w.row0 * 128, OP_BYTES, BAR(AFULL + a));
+                const uint32_t sB0 = umma::smem_u32(sB);
                 for (int j = 0; j < w.T; j++) {
-                    const long long g = tc + j;
-                    const int s = (int)(g % BS);
-                    umma::mbar_wait(BAR(BS + s), (uint32_t)(((g / BS) & 1) ^ 1));        // the UMMAs that read this stage have completed
+                    umma::mbar_wait(BAR(BS + s), sphase ^ 1u);                           // the UMMAs that read this stage have completed
                     mbar_expect_tx(BAR(s), B_STAGE);
-                    bulk_g2s(umma::smem_u32(sB + s * B_STAGE), g_cols + (size_t)j * B_STAGE, B_STAGE, BAR(s));
+                    bulk_g2s(sB0 + s * B_STAGE, g_cols + (size_t)j * B_STAGE, B_STAGE, BAR(s));
+                    if (++s == BS) { s = 0; sphase ^= 1u; }
                 }
-                tc += w.T;
                 ic++;
             }
         }
         __syncwarp();
     } else {
-        // ===================================== UMMA issuer ==================================================
-        asm volatile("bar.sync 1, 160;" ::: "memory");                    // the scale factors are in tensor memory
+        // ===================================== UMMA issuers ================================================
+        // One thread issuing every tile's six UMMAs, two waits and two commits was what paced a tile (measured: trimming its
+        // address arithmetic alone gained 9 %), so two threads share the tiles: issuer i takes the tiles of parity i, i.e. the
+        // accumulator stage i; the tensor pipe serialises their UMMAs anyway and the accumulators are independent.
+        const int iss = warp - 9;
+        asm volatile("bar.sync 1, 192;" ::: "memory");                    // the scale factors are in tensor memory
         umma::fence_after_sync();
         if (lane == 0) {
             const uint32_t aA = umma::smem_u32(sA), aB = umma::smem_u32(sB), aBias = umma::smem_u32(sBias);
@@ -602,34 +605,35 @@ knn2_hamming_mx_bulk_kernel(const uint8_t* __restrict__ e1, int n1_max, const in
             const uint64_t da_b2 = umma::smem_desc(aBias + 32, 16, 1024, umma::LAYOUT_SW128);
             const uint64_t db_b1 = umma::smem_desc(aBias + 64, 16, 1024, umma::LAYOUT_SW128);
             const uint64_t db_b2 = umma::smem_desc(aBias + 96, 16, 1024, umma::LAYOUT_SW128);
+            // descriptors differ only in their 14-bit start-address field (bytes >> 4): add the offset to a base descriptor
+            const uint64_t dA0 = umma::smem_desc(aA, 16, 1024, umma::LAYOUT_SW128);
+            const uint64_t dB0 = umma::smem_desc(aB, 16, 1024, umma::LAYOUT_SW128);
             umma::mbar_wait(BAR(BIASFULL), 0);
-            long long tc = 0;
+            uint32_t tc = 0;
             int ic = 0;
             for (long long it = blockIdx.x; it < n_items; it += gridDim.x) {
                 MxItem w;
                 if (!mx_item(it, row_tiles, n1_max, n1_arr, n2_max, n2_arr, w)) continue;
                 const int a = ic & 1;
                 umma::mbar_wait(BAR(AFULL + a), (uint32_t)((ic >> 1) & 1));              // this item's row tile
-                for (int j = 0; j < w.T; j++) {
-                    const long long g = tc + j;
-                    const int s = (int)(g % BS), t = (int)(g & 1);
-                    umma::mbar_wait(BAR(s), (uint32_t)((g / BS) & 1));                   // operands of the tile are in shared memory
-                    umma::mbar_wait(BAR(TEMPTY + t), (uint32_t)(((g >> 1) & 1) ^ 1));    // the epilogue has drained this stage
+                const uint64_t dA = dA0 + (uint64_t)((a * OP_BYTES) >> 4);
+                for (int j = (int)((tc ^ (uint32_t)iss) & 1u); j < w.T; j += 2) {          // this issuer's tiles of the item
+                    const uint32_t g = tc + (uint32_t)j;
+                    const int s = (int)(g % BS), t = iss;
+                    umma::mbar_wait(BAR(s), (g / BS) & 1u);                               // operands of the tile are in shared memory
+                    umma::mbar_wait(BAR(TEMPTY + t), ((g >> 1) & 1u) ^ 1u);               // the epilogue has drained this stage
                     umma::fence_after_sync();
                     const uint32_t d_tmem = tmem_base + (uint32_t)(t * TN);
+                    const uint64_t dB = dB0 + (uint64_t)((s * B_STAGE) >> 4);
 #pragma unroll
-                    for (int k = 0; k < 4; k++) {
-                        const uint64_t da = umma::smem_desc(aA + a * OP_BYTES + k * 32, 16, 1024, umma::LAYOUT_SW128);
-                        const uint64_t db = umma::smem_desc(aB + s * B_STAGE + k * 32, 16, 1024, umma::LAYOUT_SW128);
-                        mma_mxf4(d_tmem, da, db, k > 0 ? 1u : 0u, sf1, sf64);
-                    }
+                    for (int k = 0; k < 4; k++) mma_mxf4(d_tmem, dA + 2 * k, dB + 2 * k, k > 0 ? 1u : 0u, sf1, sf64);   // + 32 bytes per K step
                     mma_mxf4(d_tmem, da_b1, db_b1, 1u, sf2p14, sf1);      // + 2^23 + 2^14
                     mma_mxf4(d_tmem, da_b2, db_b2, 1u, sf1, sf1);         // + 128 - c
                     umma::commit(BAR(BS + s));
                     umma::commit(BAR(TFULL + t));
                 }
-                umma::commit(BAR(AEMPTY + a));                             // the row tile may be overwritten
-                tc += w.T;
+                umma::commit(BAR(AEMPTY + a));                             // this issuer is done with the row tile
+                tc += (uint32_t)w.T;
                 ic++;
             }
         }
