@@ -364,6 +364,28 @@ def run_gpu(args, rank, world, local_rank):
                    "kernels_ms": r_prof}
         except Exception as e:      # informational leg: never fails the bench
             raw = {"error": str(e)}
+    # ---- the matcher alone, default int8 kernel against the opt-in 4-bit persistent kernel (informational) ----------
+    knn_variants = None
+    if rank == 0 and os.environ.get("VSB_BENCH_KNN_VARIANTS", "1") != "0":
+        try:
+            knn_variants = {}
+            q, t_ = d["desc"][:-1].contiguous(), d["desc"][1:].contiguous()
+            for name, impl in (("int8_packed_default", 2), ("mxf4_persistent_opt_in", 5)):
+                ctx.option("knn_impl", impl)
+                for _ in range(2):
+                    ctx.knn2_hamming(q, t_)
+                k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                k0.record(stream)
+                for _ in range(5):
+                    ctx.knn2_hamming(q, t_)
+                k1.record(stream)
+                torch.cuda.synchronize(dev)
+                knn_variants[name] = k0.elapsed_time(k1) / 5
+            knn_variants["unit"] = "ms per %d pairs of %d x %d descriptors, vsb_knn2_hamming incl. unpacking" % (n_pairs, N_FEAT, N_FEAT)
+        except Exception as e:
+            knn_variants = {"error": str(e)}
+        finally:
+            ctx.option("knn_impl", int(os.environ.get("VSB_KNN_IMPL", "2")))
     if rank != 0:
         return
     # ---- roofline of every kernel, the dominant one reported in "roofline" ---------------------------
@@ -456,6 +478,7 @@ def run_gpu(args, rank, world, local_rank):
                 "d2h_bytes_per_step": d2h, "matches_device_path": same,
                 "h2d_gbs_achieved": h2d / (e2e_ms_step * 1e-3) / 1e9, "h2d_gbs_plain_copy": h2d_copy_gbs},
         "from_raw_frames": raw,
+        "knn_variants_ms": knn_variants,
         "gpu_launches": int(launches),
         "clocks": clocks,
         "roofline": roofline,
