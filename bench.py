@@ -370,7 +370,7 @@ def run_gpu(args, rank, world, local_rank):
         try:
             knn_variants = {}
             q, t_ = d["desc"][:-1].contiguous(), d["desc"][1:].contiguous()
-            for name, impl in (("int8_packed_default", 2), ("mxf4_persistent_opt_in", 5)):
+            for name, impl in (("int8_packed", 2), ("mxf4_persistent", 5)):
                 ctx.option("knn_impl", impl)
                 for _ in range(2):
                     ctx.knn2_hamming(q, t_)
@@ -385,7 +385,7 @@ def run_gpu(args, rank, world, local_rank):
         except Exception as e:
             knn_variants = {"error": str(e)}
         finally:
-            ctx.option("knn_impl", int(os.environ.get("VSB_KNN_IMPL", "2")))
+            ctx.option("knn_impl", int(os.environ.get("VSB_KNN_IMPL", "6")))
     if rank != 0:
         return
     # ---- roofline of every kernel, the dominant one reported in "roofline" ---------------------------
@@ -397,7 +397,8 @@ def run_gpu(args, rank, world, local_rank):
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
     hbm_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6.65 TB/s"
     popc_peak = ctx.popc_peak() / 1e9     # GPOPC/s, microbenchmarked on this GPU
-    knn_impl = int(os.environ.get("VSB_KNN_IMPL", "2"))
+    knn_impl = int(os.environ.get("VSB_KNN_IMPL", "6"))
+    knn_fp4 = knn_impl in (3, 4, 5) or (knn_impl == 6 and N_FEAT >= 768)      # which tensor-core kernel the matcher ran
     # tcgen05 kind::i8 runs at twice the bf16 rate; MEASURED_PEAKS.json holds the measured dense bf16 figure
     i8_peak = 2.0 * float(peaks.get("bf16_tflops", 2250.0))
     i8_src = ("2 x measured dense bf16 (MEASURED_PEAKS.json bf16_tflops); nominal int8 dense is 4500 TOP/s"
@@ -412,7 +413,8 @@ def run_gpu(args, rank, world, local_rank):
         # tensor-core form (knn_impl 1/2): one +-1 byte per descriptor bit, 2 * N * M * 256 int8 ops per distance matrix
         "knn2_hamming": (("int", 8.0 * N_FEAT * N_FEAT * pairs_total, "GPOPC/s", popc_peak,
                           "measured by vsb_popc_peak on this GPU") if knn_impl == 0 else
-                         ("tensor", 2.0 * 256 * N_FEAT * N_FEAT * pairs_total / 1e3, "TOP/s", i8_peak, i8_src)),
+                         ("tensor", 2.0 * 256 * N_FEAT * N_FEAT * pairs_total / 1e3, "TOP/s", 2.0 * i8_peak if knn_fp4 else i8_peak,
+                          ("4-bit kernel (kind::mxf4): 4 x measured dense bf16; " if knn_fp4 else "") + i8_src)),
         # 14 B per candidate point per iteration + one-time staging of cur I, prev I, gx, gy (6 B/px, levels 0-3)
         "gn_solve": ("hbm", 14.0 * stats["point_visits"] + 6.0 * px_gn * pairs_total, "GB/s", hbm_peak, hbm_src),
         # read w*h, write every level (level 0 is copied, as the reference's Camera::Update does)

@@ -17,7 +17,7 @@ def _run(ctx, d1, d2, n1=None, n2=None):
         out = ctx.knn2_hamming(t1, t2, a1, a2)
         torch.cuda.synchronize()
     finally:
-        ctx.option("knn_impl", 2)
+        ctx.option("knn_impl", 6)      # back to the default (auto)
     return [o.cpu().numpy() for o in out]
 
 

@@ -9,8 +9,9 @@ import pytest
 
 pytestmark = pytest.mark.gpu
 # 1, 2: int8 tensor-core kernel (32-bit / packed epilogue, 2 = the default); 3, 4, 5: 4-bit operands (kind::mxf4): expanded in
-# the kernel / pre-expanded rows copied by the producers / persistent CTAs fetching pre-swizzled tiles with cp.async.bulk
-IMPLS = [1, 2, 3, 4, 5] + [int(v) for v in os.environ.get("VSB_TEST_KNN_IMPLS", "").split(",") if v]
+# the kernel / pre-expanded rows copied by the producers / persistent CTAs fetching pre-swizzled tiles with cp.async.bulk;
+# 6 = the default: 5 from 768 descriptors per set up, else 2
+IMPLS = [1, 2, 3, 4, 5, 6] + [int(v) for v in os.environ.get("VSB_TEST_KNN_IMPLS", "").split(",") if v]
 
 
 def _hamming_matrix(d1, d2):
@@ -50,7 +51,7 @@ def _run(ctx, impl, d1, d2, n1=None, n2=None):
         out = ctx.knn2_hamming(t1, t2, a1, a2)
         torch.cuda.synchronize()
     finally:
-        ctx.option("knn_impl", 2)
+        ctx.option("knn_impl", 6)      # back to the default (auto)
     return [o.cpu().numpy() for o in out]
 
 
@@ -129,7 +130,7 @@ def test_tracker_with_tensor_core_matcher(ctx, oracle, impl):
         pose, n_good = tr.track_pairs(st("prev"), st("cur"), st("d1"), st("d2"), st("kp1"), st("pose_prior"))
         torch.cuda.synchronize()
     finally:
-        ctx.option("knn_impl", 2)
+        ctx.option("knn_impl", 6)      # back to the default (auto)
     pose, n_good = pose.cpu().numpy(), n_good.cpu().numpy()
     for b, p in enumerate(pairs):
         ref = oracle.track_pair(p["prev"], p["cur"], p["d1"], p["d2"], p["kp1"], p["K"], p["pose_prior"], n_cells=49)

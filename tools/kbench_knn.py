@@ -39,4 +39,4 @@ for n, b in cfgs:
         pairs = b * n * n
         print(f"N={n} batch={b} impl={impl}: {ms:.3f} ms  {pairs/ms/1e6:.1f} Gdist/s  "
               f"({8*pairs/ms/1e3/peak*1e0:.3f} of POPC roofline)  {ms*1e3/b:.2f} us/pair  same_as_impl0={same}")
-ctx.option("knn_impl", 2)
+ctx.option("knn_impl", 6)

@@ -39,13 +39,14 @@ extern "C" int vsb_ctx_create(int device, vsb_ctx_t** out) {
     c->scratch_bytes = 0;
     c->scratch2 = nullptr;
     c->scratch2_bytes = 0;
+    c->ws_n = 0;
     c->l2_fallback_counter = nullptr;
     c->attr_knn_tc_done = 0;
     c->attr_knn_mx_done = 0;
     c->attr_l2_tc_smem = 0;
     c->prof_on = 0;
     for (int i = 0; i < VSB_K_COUNT; i++) { c->prof_ms[i] = 0.0; c->prof_n[i] = 0; }
-    c->knn_impl = 2;
+    c->knn_impl = 6;     // auto: 4-bit persistent kernel from 768 descriptors per set up, int8 kernel below
     c->gn_threads = 0;      // auto: by batch size
     c->pyr_impl = 1;
     c->gn_variant = 0;
@@ -61,7 +62,7 @@ extern "C" int vsb_ctx_create(int device, vsb_ctx_t** out) {
 extern "C" int vsb_ctx_option(vsb_ctx_t* ctx, const char* name, int value) {
     if (!ctx || !name) return VSB_ERR_INVALID;
     if (!strcmp(name, "knn_impl")) {
-        if (value < 0 || value > 5) return VSB_ERR_INVALID;
+        if (value < 0 || value > 6) return VSB_ERR_INVALID;
         ctx->knn_impl = value;
         return VSB_OK;
     }
@@ -92,6 +93,7 @@ extern "C" int vsb_ctx_destroy(vsb_ctx_t* ctx) {
     if (!ctx) return VSB_ERR_INVALID;
     if (ctx->scratch) cudaFree(ctx->scratch);
     if (ctx->scratch2) cudaFree(ctx->scratch2);
+    for (int i = 0; i < ctx->ws_n; i++) if (ctx->ws_ptr[i]) cudaFree(ctx->ws_ptr[i]);
     for (auto& r : ctx->prof_pending) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
     for (auto e : ctx->prof_free) cudaEventDestroy(e);
     delete ctx;
@@ -126,6 +128,29 @@ int vsb_scratch2_reserve(vsb_ctx* ctx, size_t bytes, void** out) {
         ctx->scratch2_bytes = want;
     }
     *out = ctx->scratch2;
+    return VSB_OK;
+}
+
+int vsb_stream_ws_reserve(vsb_ctx* ctx, cudaStream_t st, size_t bytes, void** out) {
+    int slot = -1;
+    for (int i = 0; i < ctx->ws_n; i++) if (ctx->ws_stream[i] == st) slot = i;
+    if (slot < 0) {
+        if (ctx->ws_n == 8) {                              // more streams than slots: recycle the oldest (cudaFree synchronises)
+            if (ctx->ws_ptr[0]) VSB_CUDA(ctx, cudaFree(ctx->ws_ptr[0]));
+            for (int i = 1; i < 8; i++) { ctx->ws_ptr[i - 1] = ctx->ws_ptr[i]; ctx->ws_bytes[i - 1] = ctx->ws_bytes[i]; ctx->ws_stream[i - 1] = ctx->ws_stream[i]; }
+            ctx->ws_n = 7;
+        }
+        slot = ctx->ws_n++;
+        ctx->ws_ptr[slot] = nullptr; ctx->ws_bytes[slot] = 0; ctx->ws_stream[slot] = st;
+    }
+    if (bytes > ctx->ws_bytes[slot]) {
+        if (ctx->ws_ptr[slot]) VSB_CUDA(ctx, cudaFree(ctx->ws_ptr[slot]));   // cudaFree synchronises: no kernel still uses it
+        ctx->ws_ptr[slot] = nullptr; ctx->ws_bytes[slot] = 0;
+        const size_t want = bytes + bytes / 8;
+        VSB_CUDA(ctx, cudaMalloc(&ctx->ws_ptr[slot], want));
+        ctx->ws_bytes[slot] = want;
+    }
+    *out = ctx->ws_ptr[slot];
     return VSB_OK;
 }
 

@@ -27,6 +27,12 @@ struct vsb_ctx {
     size_t scratch_bytes;
     void* scratch2;          // second area: internals of an entry whose caller already holds `scratch`
     size_t scratch2_bytes;
+    // per-STREAM workspaces (the 4-bit kNN's expanded descriptors): the tracker's host entry runs two streams at once, so a
+    // workspace that two in-flight launches could share is keyed by the stream it is used on
+    void* ws_ptr[8];
+    size_t ws_bytes[8];
+    cudaStream_t ws_stream[8];
+    int ws_n;
     // kernel attributes are per device: remembered per context, not per process
     int attr_knn_tc_done;
     int attr_knn_mx_done;
@@ -40,7 +46,8 @@ struct vsb_ctx {
     long long prof_n[VSB_K_COUNT];
     // tuning knobs (vsb_ctx_option)
     int knn_impl;     // Hamming kNN: 0 = POPC kernel (INT pipe), 1 = tcgen05 tensor-core kernel, 32-bit epilogue,
-                      //              2 = tcgen05 kernel with the packed 16x2 epilogue, 3 = 4-bit operands (kind::mxf4, knn_mx.cu), 4 = the same with descriptors pre-expanded once per call
+                      //              2 = tcgen05 kernel with the packed 16x2 epilogue, 3 = 4-bit operands (kind::mxf4, knn_mx.cu), 4 = the same with descriptors pre-expanded once per call,
+                      //              5 = persistent 4-bit kernel with bulk-copied tiles, 6 (default) = 5 from 768 descriptors per set up, else 2
     int gn_threads;   // threads per frame pair of the GN solver: 64 / 128 / 256 / 512 / 1024, 0 = chosen from the batch size
     int knn_l2_impl;  // float kNN: 0 = exact FP64 kernel, 1 = tensor-core GEMM + exact re-check (dim <= 64, dim % 8 == 0)
     int gn_variant;   // GN solver register/unroll variant (tuning experiments; 0 = default)
@@ -77,5 +84,6 @@ static inline int vsb_cuda_fail(vsb_ctx* ctx, cudaError_t e, const char* what) {
 
 int vsb_scratch_reserve(vsb_ctx* ctx, size_t bytes, void** out);
 int vsb_scratch2_reserve(vsb_ctx* ctx, size_t bytes, void** out);
+int vsb_stream_ws_reserve(vsb_ctx* ctx, cudaStream_t st, size_t bytes, void** out);
 
 static inline int vsb_div_up(int a, int b) { return (a + b - 1) / b; }

@@ -184,9 +184,11 @@ int vsb_knn2_hamming_keys(vsb_ctx* ctx, const uint8_t* d1, int n1_max, const int
     if (!ctx || count < 0 || n1_max < 0 || n2_max < 0) return VSB_ERR_INVALID;
     if (n1_max > (int)KEY_IDX_MASK || n2_max > (int)KEY_IDX_MASK) return VSB_ERR_CAPACITY;
     if (count == 0) return VSB_OK;
-    if (ctx->knn_impl >= 3) return vsb_knn2_hamming_mx(ctx, d1, n1_max, n1, d2, n2_max, n2, count, key12, key21, ctx->knn_impl - 3, st);
-    if (ctx->knn_impl != 0)   // tensor-core path: every valid row is written by exactly one CTA, no memset, no atomics
-        return vsb_knn2_hamming_tc(ctx, d1, n1_max, n1, d2, n2_max, n2, count, key12, key21, ctx->knn_impl == 2,
+    int impl = ctx->knn_impl;
+    if (impl == 6) impl = (n1_max > n2_max ? n1_max : n2_max) >= 768 ? 5 : 2;      // auto: the 4-bit persistent kernel pays from ~768 rows
+    if (impl >= 3) return vsb_knn2_hamming_mx(ctx, d1, n1_max, n1, d2, n2_max, n2, count, key12, key21, impl - 3, st);
+    if (impl != 0)   // tensor-core path: every valid row is written by exactly one CTA, no memset, no atomics
+        return vsb_knn2_hamming_tc(ctx, d1, n1_max, n1, d2, n2_max, n2, count, key12, key21, impl == 2,
                                    nullptr, 0, st);
     if (n2_max > 0)
         VSB_CUDA(ctx, cudaMemsetAsync(key21, 0xFF, (size_t)count * n2_max * 2 * sizeof(uint32_t), st));

@@ -666,6 +666,7 @@ int vsb_knn2_hamming_mx(vsb_ctx* ctx, const uint8_t* d1, int n1_max, const int32
         VSB_LAUNCHED(ctx);
         mx_bias_init_kernel<<<4, 256, 0, st>>>();
         VSB_LAUNCHED(ctx);
+        VSB_CUDA(ctx, cudaStreamSynchronize(st));      // first use only: the constant tables must exist before ANY stream reads them
         ctx->attr_knn_mx_done = 1;
     }
     const int row_tiles = vsb_div_up(n1_max > n2_max ? n1_max : n2_max, TM);
@@ -681,7 +682,7 @@ int vsb_knn2_hamming_mx(vsb_ctx* ctx, const uint8_t* d1, int n1_max, const int32
             const int rows_pad = ((n1_max > n2_max ? n1_max : n2_max) + 383) / 384 * 384;
             const size_t bb = (size_t)zc * rows_pad * 128;
             void* scratch = nullptr;
-            int rc = vsb_scratch2_reserve(ctx, 2 * bb + 256, &scratch);
+            int rc = vsb_stream_ws_reserve(ctx, st, 2 * bb + 256, &scratch);
             if (rc) return rc;
             uint8_t* e1 = static_cast<uint8_t*>(scratch);
             uint8_t* e2 = e1 + bb;
@@ -700,7 +701,7 @@ int vsb_knn2_hamming_mx(vsb_ctx* ctx, const uint8_t* d1, int n1_max, const int32
         } else if (pre) {
             const size_t b1 = ((size_t)zc * n1_max * 128 + 255) & ~(size_t)255, b2 = ((size_t)zc * n2_max * 128 + 255) & ~(size_t)255;
             void* scratch = nullptr;
-            int rc = vsb_scratch2_reserve(ctx, b1 + b2 + 256, &scratch);
+            int rc = vsb_stream_ws_reserve(ctx, st, b1 + b2 + 256, &scratch);
             if (rc) return rc;
             uint8_t* e1 = static_cast<uint8_t*>(scratch);
             uint8_t* e2 = e1 + b1;

@@ -220,7 +220,7 @@ class Context:
 
     # ---- Matcher -------------------------------------------------------------------------------
     def option(self, name, value):
-        """Tuning knob (vsb_ctx_option): "knn_impl" 0/1/2, "knn_l2_impl" 0/1, "gn_threads" 64/128/256, "pyr_impl" 0/1."""
+        """Tuning knob (vsb_ctx_option): "knn_impl" 0..6 (6 = auto, the default), "knn_l2_impl" 0/1, "gn_threads" 64/128/256, "pyr_impl" 0/1."""
         check(lib().vsb_ctx_option(self.handle, name.encode(), int(value)), self.handle)
 
     def knn2_hamming(self, d1, d2, n1=None, n2=None, stream=None):
