@@ -451,7 +451,7 @@ def run_gpu(args, rank, world, local_rank):
             if name == "gn_solve":
                 ent["note"] = ("bound as SURVEY 8(d) defines it (algorithmic bytes over HBM peak); ncu shows the kernel "
                                "limited by the XU pipe (FP32<->FP64 conversions, 57 %) and instruction issue (59 %), "
-                               "DRAM at 14 %: profiles/r1_full_topkernels_v4.txt")
+                               "DRAM at 14 %: profiles/r1_full_topkernels_v5.txt")
         kernels.append(ent)
     dom = next((k for k in kernels if "bound" in k), None)
     roofline = None

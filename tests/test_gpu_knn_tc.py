@@ -117,6 +117,42 @@ def test_knn_tc_batched_ragged(ctx, oracle, impl):
         assert (got[0][b, n1[b]:] == -1).all() and (got[2][b, n2[b]:] == -1).all()
 
 
+@pytest.mark.parametrize("impl", [5, 6])
+@pytest.mark.parametrize("ragged", [False, True])
+def test_knn_tc_chained_sequence(ctx, oracle, impl, ragged):
+    """Set 2 of pair k IS set 1 of pair k + 1 (one [B+1,N,32] block, d2 = d1 + one set; counts likewise): the persistent 4-bit
+    kernel expands every frame once. Same answers as independent pairs."""
+    import torch
+    rng = np.random.default_rng(23)
+    B, N = 4, 800
+    frames = rng.integers(0, 256, (B + 1, N, 32), dtype=np.uint8)
+    counts = [800, 770, 1, 0, 799] if ragged else [N] * (B + 1)
+    tf = torch.from_numpy(frames).cuda()
+    tn = torch.tensor(counts, dtype=torch.int32).cuda() if ragged else None
+    ctx.option("knn_impl", impl)
+    try:
+        d1, d2 = tf[:-1], tf[1:]
+        assert d2.data_ptr() == d1.data_ptr() + N * 32 and d1.is_contiguous() and d2.is_contiguous()
+        out = ctx.knn2_hamming(d1, d2, None if tn is None else tn[:-1], None if tn is None else tn[1:])
+        torch.cuda.synchronize()
+    finally:
+        ctx.option("knn_impl", 6)
+    got = [o.cpu().numpy() for o in out]
+    for b in range(B):
+        a, c = frames[b, :counts[b]], frames[b + 1, :counts[b + 1]]
+        if len(a) and len(c):
+            i12, s12 = oracle.knn2_hamming(a, c)
+            i21, s21 = oracle.knn2_hamming(c, a)
+        else:
+            i12, s12 = np.full((len(a), 2), -1, np.int32), np.zeros((len(a), 2), np.float32)
+            i21, s21 = np.full((len(c), 2), -1, np.int32), np.zeros((len(c), 2), np.float32)
+        np.testing.assert_array_equal(got[0][b, :len(a)], i12)
+        np.testing.assert_array_equal(got[1][b, :len(a)], s12)
+        np.testing.assert_array_equal(got[2][b, :len(c)], i21)
+        np.testing.assert_array_equal(got[3][b, :len(c)], s21)
+        assert (got[0][b, len(a):] == -1).all() and (got[2][b, len(c):] == -1).all()
+
+
 @pytest.mark.parametrize("impl", IMPLS)
 def test_tracker_with_tensor_core_matcher(ctx, oracle, impl):
     import torch

@@ -681,18 +681,28 @@ int vsb_knn2_hamming_mx(vsb_ctx* ctx, const uint8_t* d1, int n1_max, const int32
         if (pre == 2) {
             const int rows_pad = ((n1_max > n2_max ? n1_max : n2_max) + 383) / 384 * 384;
             const size_t bb = (size_t)zc * rows_pad * 128;
+            // a SEQUENCE (set 2 of pair k is set 1 of pair k + 1: d2 = d1 + one set, the tracker's sequence entries) has every
+            // frame's descriptors expanded once instead of once per pair side
+            const bool chained = n1_max == n2_max && d2 == d1 + (size_t)n1_max * 32 && ((!n1 && !n2) || (n1 && n2 == n1 + 1));
             void* scratch = nullptr;
-            int rc = vsb_stream_ws_reserve(ctx, st, 2 * bb + 256, &scratch);
+            int rc = vsb_stream_ws_reserve(ctx, st, (chained ? bb + (size_t)rows_pad * 128 : 2 * bb) + 256, &scratch);
             if (rc) return rc;
             uint8_t* e1 = static_cast<uint8_t*>(scratch);
-            uint8_t* e2 = e1 + bb;
-            const long long chunks = (long long)zc * rows_pad * 8;
-            mx_expand_swizzled_kernel<<<(unsigned)((chunks + 255) / 256), 256, 0, st>>>(a, n1_max, n1 ? n1 + z0 : nullptr, rows_pad, zc,
-                                                                                         reinterpret_cast<uint4*>(e1));
-            VSB_LAUNCHED(ctx);
-            mx_expand_swizzled_kernel<<<(unsigned)((chunks + 255) / 256), 256, 0, st>>>(b, n2_max, n2 ? n2 + z0 : nullptr, rows_pad, zc,
-                                                                                         reinterpret_cast<uint4*>(e2));
-            VSB_LAUNCHED(ctx);
+            uint8_t* e2 = chained ? e1 + (size_t)rows_pad * 128 : e1 + bb;
+            if (chained) {
+                const long long chunks = (long long)(zc + 1) * rows_pad * 8;
+                mx_expand_swizzled_kernel<<<(unsigned)((chunks + 255) / 256), 256, 0, st>>>(a, n1_max, n1 ? n1 + z0 : nullptr, rows_pad, zc + 1,
+                                                                                             reinterpret_cast<uint4*>(e1));
+                VSB_LAUNCHED(ctx);
+            } else {
+                const long long chunks = (long long)zc * rows_pad * 8;
+                mx_expand_swizzled_kernel<<<(unsigned)((chunks + 255) / 256), 256, 0, st>>>(a, n1_max, n1 ? n1 + z0 : nullptr, rows_pad, zc,
+                                                                                             reinterpret_cast<uint4*>(e1));
+                VSB_LAUNCHED(ctx);
+                mx_expand_swizzled_kernel<<<(unsigned)((chunks + 255) / 256), 256, 0, st>>>(b, n2_max, n2 ? n2 + z0 : nullptr, rows_pad, zc,
+                                                                                             reinterpret_cast<uint4*>(e2));
+                VSB_LAUNCHED(ctx);
+            }
             const long long n_items = (long long)zc * 2 * row_tiles;
             const int resident = 2 * (ctx->sm_count > 0 ? ctx->sm_count : 148);
             const int ctas = (int)(n_items < resident ? n_items : resident);
