@@ -266,12 +266,19 @@ def run_gpu(args, rank, world, local_rank):
     # host (pinned) and device copies of the inputs
     tr_host = ctx.tracker(W, H, N_FEAT, seq["K"], n_cells=N_CELLS, max_pairs=host_chunk,
                           gn_opts=vb.default_gn_opts(grad_mode=grad_mode, accum_mode=accum_mode))
+    # the pinned host buffers live on the GPU's own NUMA node (replicas.gpu_local_cpus): with N replicas every rank then
+    # pulls its frames over its own root complex
+    numa = replicas.gpu_local_cpus(local_rank) if os.environ.get("VSB_BENCH_NUMA_BIND", "1") != "0" else None
+    if numa is not None:
+        numa.__enter__()
     h = {k: torch.from_numpy(np.ascontiguousarray(seq[k])).pin_memory() for k in ("frames", "desc", "kp", "prior")}
+    h_pose = torch.zeros((n_pairs, 7), dtype=torch.float32).pin_memory()
+    h_ng = torch.zeros((n_pairs,), dtype=torch.int32).pin_memory()
+    if numa is not None:
+        numa.__exit__(None, None, None)
     d = {k: v.to(dev) for k, v in h.items()}
     d_pose = torch.zeros((n_pairs, 7), dtype=torch.float32, device=dev)
     d_ng = torch.zeros((n_pairs,), dtype=torch.int32, device=dev)
-    h_pose = torch.zeros((n_pairs, 7), dtype=torch.float32).pin_memory()
-    h_ng = torch.zeros((n_pairs,), dtype=torch.int32).pin_memory()
     stream = torch.cuda.current_stream(dev)
 
     def step_device():
@@ -478,7 +485,8 @@ def run_gpu(args, rank, world, local_rank):
                    "gn_points_per_pair": stats["point_visits"] / max(1, pairs_total)},
         "e2e": {"value": e2e_value, "unit": "frames/s", "ms_per_step": e2e_ms_step, "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": d2h, "matches_device_path": same,
-                "h2d_gbs_achieved": h2d / (e2e_ms_step * 1e-3) / 1e9, "h2d_gbs_plain_copy": h2d_copy_gbs},
+                "h2d_gbs_achieved": h2d / (e2e_ms_step * 1e-3) / 1e9, "h2d_gbs_plain_copy": h2d_copy_gbs,
+                "host_buffers_numa_bound": bool(numa is not None and numa.bound)},
         "from_raw_frames": raw,
         "knn_variants_ms": knn_variants,
         "gpu_launches": int(launches),

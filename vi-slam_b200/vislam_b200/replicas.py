@@ -30,3 +30,49 @@ def max_over_ranks(value, dist=None, device=None):
 def aggregate_throughput(units_per_rank, ms_per_step_max, world):
     """Whole-job units/s: every rank processed `units_per_rank` in the (max-over-ranks) step time."""
     return world * units_per_rank / (ms_per_step_max * 1e-3)
+
+
+class gpu_local_cpus:
+    """Context manager: runs its body with the calling thread bound to the CPUs NVML reports as local to GPU
+    `gpu_index` (same socket / NUMA node), then restores the previous affinity.  Host buffers pinned inside it are
+    placed on the GPU's own node, so N replicas each pull their frames over their own root complex instead of all
+    reading one socket's memory across the inter-socket link (measured: the host-buffer pass at 4 GPUs).
+    A no-op when NVML or sched_setaffinity is unavailable; `.bound` says whether the binding took."""
+
+    def __init__(self, gpu_index):
+        self.gpu_index, self.bound, self._prev = gpu_index, False, None
+
+    def __enter__(self):
+        import os
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            idx = self.gpu_index
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            if vis:
+                try:
+                    idx = int(vis.split(",")[self.gpu_index])
+                except Exception:
+                    idx = self.gpu_index
+            h = pynvml.nvmlDeviceGetHandleByIndex(idx)
+            n_cpu = os.cpu_count() or 1
+            words = pynvml.nvmlDeviceGetCpuAffinity(h, (n_cpu + 63) // 64)
+            cpus = {64 * w + b for w, m in enumerate(words) for b in range(64) if (int(m) >> b) & 1}
+            self._prev = os.sched_getaffinity(0)
+            cpus &= self._prev
+            if cpus:
+                os.sched_setaffinity(0, cpus)
+                self.bound = True
+                self.cpus = sorted(cpus)
+        except Exception:
+            self.bound = False
+        return self
+
+    def __exit__(self, *exc):
+        import os
+        if self.bound and self._prev is not None:
+            try:
+                os.sched_setaffinity(0, self._prev)
+            except Exception:
+                pass
+        return False
