@@ -258,7 +258,7 @@ struct CandParams {
     float bx[VSB_MAX_LEVELS], by[VSB_MAX_LEVELS], invfx[VSB_MAX_LEVELS], invfy[VSB_MAX_LEVELS];
 };
 
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 5)
 candidates_kernel(const float* __restrict__ good_xy, int good_cap, const int32_t* __restrict__ n_good, CandParams P,
                   float4* __restrict__ cand, int cand_cap, int32_t* __restrict__ n_cand) {
     const int prob = blockIdx.x;
@@ -307,32 +307,68 @@ candidates_kernel(const float* __restrict__ good_xy, int good_cap, const int32_t
     const int cols = P.lay.w[lvl], rows = P.lay.h[lvl];
     // one warp per feature: lanes stride over the feature's points (i outer, j inner — reference row order)
     const int warp = tid >> 5, lane = tid & 31;
+    // the feature's patch plus its one-pixel Scharr apron (<= 13 x 13 bytes) is staged row by row (contiguous bytes per image
+    // row) — the points themselves run down the columns, so reading the nine neighbours straight from the image would touch
+    // a different row per lane
+    __shared__ uint8_t s_tile[8][13][16];
+    // ... and fetched one feature ahead into registers (two tile rows per pass, sixteen lanes a row, at most seven passes), so
+    // the image latency of feature f + 8 hides behind the arithmetic of feature f.  reflect101 is the identity inside the
+    // image, so one formula serves the apron and the interior
+    const int tu = lane & 15, tv = lane >> 4;
+    uint32_t pre[7];
+    auto fetch = [&](int f) {
+        if (!attrs || f >= nf) return;
+        const int c = s_cnt[f], nj = s_nj[f];
+        if (c <= 0 || tu >= c / nj + 2) return;
+        const uint8_t* col = image1 + reflect101(s_ia[f] - 1 + tu, cols);
+        const int ja = s_ja[f];
+#pragma unroll
+        for (int k = 0; k < 7; k++)
+            if (tv + 2 * k < nj + 2) pre[k] = __ldg(col + (size_t)reflect101(ja - 1 + tv + 2 * k, rows) * cols);
+    };
+    fetch(warp);
     for (int f = warp; f < nf; f += 8) {
         const int c = s_cnt[f], off = s_off[f], nj = s_nj[f], ia = s_ia[f], ja = s_ja[f];
+        if (attrs) {
+            __syncwarp();
+#pragma unroll
+            for (int k = 0; k < 7; k++)
+                if (tv + 2 * k < 13) s_tile[warp][tv + 2 * k][tu] = (uint8_t)pre[k];   // rows past the patch hold stale bytes nobody reads
+            __syncwarp();
+            fetch(f + 8);
+        }
+        // the lane's first point and the step of 32 points as (column, row), the row running fastest: one division per feature
+        const int njs = max(nj, 1);
+        int ii = lane / njs, jj = lane - ii * njs;
+        const int di = 32 / njs, dj = 32 - di * njs;
         for (int p = lane; p < c; p += 32) {
             if (off + p >= total) break;
-            const int ii = p / nj, jj = p - ii * nj;
+            // (float) of a small non-negative integer without the conversion pipe: 2^23 + n is exact, so is the subtraction
+            const float xf = __fsub_rn(__int_as_float(0x4B000000 | (ia + ii)), 8388608.0f);
+            const float yf = __fsub_rn(__int_as_float(0x4B000000 | (ja + jj)), 8388608.0f);
             if (attrs && P.xy) {
-                const float X = __fadd_rn(__fmul_rn((float)(ia + ii), P.invfx[lvl]), P.bx[lvl]);   // * z (= 1) is the identity
-                const float Y = __fadd_rn(__fmul_rn((float)(ja + jj), P.invfy[lvl]), P.by[lvl]);
+                const float X = __fadd_rn(__fmul_rn(xf, P.invfx[lvl]), P.bx[lvl]);   // * z (= 1) is the identity
+                const float Y = __fadd_rn(__fmul_rn(yf, P.invfy[lvl]), P.by[lvl]);
                 P.xy[((size_t)prob * P.levels + lvl) * cand_cap + off + p] = make_double2((double)X, (double)Y);
             } else {
-                out[off + p] = make_float4((float)(ia + ii), (float)(ja + jj), 1.0f, 1.0f);
+                out[off + p] = make_float4(xf, yf, 1.0f, 1.0f);
             }
             if (attrs) {
-                const int sx = min(max(ia + ii, 0), cols - 1), sy = min(max(ja + jj, 0), rows - 1);
-                const int xm = reflect101(sx - 1, cols), xp = reflect101(sx + 1, cols);
-                const int ym = reflect101(sy - 1, rows), yp = reflect101(sy + 1, rows);
-                const uint8_t* q0 = image1 + (size_t)ym * cols;
-                const uint8_t* q1 = image1 + (size_t)sy * cols;
-                const uint8_t* q2 = image1 + (size_t)yp * cols;
-                const int a00 = __ldg(q0 + xm), a01 = __ldg(q0 + sx), a02 = __ldg(q0 + xp);
-                const int a10 = __ldg(q1 + xm), a11 = __ldg(q1 + sx), a12 = __ldg(q1 + xp);
-                const int a20 = __ldg(q2 + xm), a21 = __ldg(q2 + sx), a22 = __ldg(q2 + xp);
+                // point (ia + ii, ja + jj) sits at tile[jj + 1][ii + 1]: 0 < x < lw <= cols and 0 < y < lh <= rows, so the
+                // centre needs no clamping and its neighbours are the reflect101 values staged above
+                const uint8_t* q0 = &s_tile[warp][jj][ii];
+                const uint8_t* q1 = q0 + 16;
+                const uint8_t* q2 = q0 + 32;
+                const int a00 = q0[0], a01 = q0[1], a02 = q0[2];
+                const int a10 = q1[0], a11 = q1[1], a12 = q1[2];
+                const int a20 = q2[0], a21 = q2[1], a22 = q2[2];
                 const int gx = 3 * (3 * (a02 - a00) + 10 * (a12 - a10) + 3 * (a22 - a20));
                 const int gy = 3 * (3 * (a20 - a00) + 10 * (a21 - a01) + 3 * (a22 - a02));
                 pout[off + p] = make_uint2(((uint32_t)gx & 0xFFFFu) | ((uint32_t)gy << 16), (uint32_t)a11);
             }
+            ii += di;
+            jj += dj;
+            if (jj >= njs) { jj -= njs; ii++; }
         }
     }
 }
