@@ -82,3 +82,18 @@ def test_shard_range_covers_everything():
             assert max(h - l for l, h in spans) - min(h - l for l, h in spans) <= 1
     with pytest.raises(ValueError):
         replicas.shard_range(10, 2, 2)
+
+
+def test_gpu_local_cpus_restores_affinity():
+    """The NUMA binding used while pinning host buffers never leaves the process bound: affinity is restored on exit, and
+    without NVML / a GPU (this container) it is a no-op that says so."""
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(__file__), "..", "vi-slam_b200"))
+    from vislam_b200 import replicas
+    before = os.sched_getaffinity(0)
+    with replicas.gpu_local_cpus(0) as g:
+        inside = os.sched_getaffinity(0)
+        assert inside <= before and len(inside) >= 1
+        if not g.bound:
+            assert inside == before
+    assert os.sched_getaffinity(0) == before

@@ -291,12 +291,23 @@ candidates_kernel(const float* __restrict__ good_xy, int good_cap, const int32_t
         s_ia[tid] = ia; s_ja[tid] = ja; s_nj[tid] = nj;
     }
     s_cnt[tid] = cnt;
+    // exclusive prefix of the per-feature counts (cnt is 0 from feature nf on): warp scans, then the eight warp totals
+    __shared__ int s_wsum[8];
+    int incl = cnt;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const int v = __shfl_up_sync(0xFFFFFFFFu, incl, d);
+        if ((tid & 31) >= d) incl += v;
+    }
+    if ((tid & 31) == 31) s_wsum[tid >> 5] = incl;
     __syncthreads();
-    if (tid == 0) {
-        int acc = 0;
-        for (int f = 0; f < nf; f++) { s_off[f] = acc; acc += s_cnt[f]; }
-        s_off[nf] = acc;
-        n_cand[(size_t)prob * P.levels + lvl] = min(acc, cand_cap);
+    int base = 0;
+#pragma unroll
+    for (int k = 0; k < 8; k++) base += k < (tid >> 5) ? s_wsum[k] : 0;
+    s_off[tid] = base + incl - cnt;
+    if (tid == 255) {
+        s_off[256] = base + incl;
+        n_cand[(size_t)prob * P.levels + lvl] = min(base + incl, cand_cap);
     }
     __syncthreads();
     float4* out = cand + ((size_t)prob * P.levels + lvl) * cand_cap;
