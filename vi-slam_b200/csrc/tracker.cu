@@ -3,6 +3,7 @@
 // Update (pyramid) -> computeGPUGoodMatches -> computeGradient -> ObtainPatchesPointsPreviousFrame ->
 // EstimatePoseFeatures — batched over independent frame pairs, with no host round trip between stages.
 // Pairs of a sequence are independent given their priors, so a sequence is one batch.
+#include <cstdlib>
 #include "common.cuh"
 #include "knn_keys.cuh"
 
@@ -55,6 +56,7 @@ struct Slot {
     float* pose = nullptr;
     float* orb_resp = nullptr;    // [max_pairs + 1][n_feat] each, allocated on the first vsb_track_sequence_orb call
     float* orb_angle = nullptr;
+    uint8_t* stage = nullptr;     // [max_pairs + 1][w * h] contiguous frames of the host entry (VSB_HOST_STAGING=1), allocated on first use
     cudaStream_t stream = nullptr;
     cudaEvent_t done = nullptr;
 };
@@ -72,6 +74,11 @@ struct vsb_tracker {
     int n_slots;
     unsigned long long* stats;   // device, 4 counters shared by both slots
     long long host_h2d_bytes, host_d2h_bytes, host_chunks;   // what the last vsb_track_sequence_host call moved
+    // whole-sequence side inputs of the host entry (descriptors, key points, counts, priors: a tenth of the bytes), uploaded with
+    // one copy each before the first chunk instead of four small copies per chunk; grown on demand
+    uint8_t* seq_side = nullptr;
+    size_t seq_side_bytes = 0;
+    cudaEvent_t seq_side_ready = nullptr;
 };
 
 namespace {
@@ -113,7 +120,7 @@ int slot_alloc(vsb_tracker* t, Slot& s) {
 }
 
 void slot_free(Slot& s) {
-    void* ptrs[] = {s.pyr, s.gx, s.gy, s.desc, s.kp, s.n_feat, s.prior, s.key12, s.key21, s.good_q, s.good_t, s.good_d, s.n_good, s.n_sym, s.good_xy, s.cand, s.patt, s.n_cand, s.pose, s.orb_resp, s.orb_angle};
+    void* ptrs[] = {s.pyr, s.gx, s.gy, s.desc, s.kp, s.n_feat, s.prior, s.key12, s.key21, s.good_q, s.good_t, s.good_d, s.n_good, s.n_sym, s.good_xy, s.cand, s.patt, s.n_cand, s.pose, s.orb_resp, s.orb_angle, s.stage};
     for (void* p : ptrs) if (p) cudaFree(p);
     if (s.stream) cudaStreamDestroy(s.stream);
     if (s.done) cudaEventDestroy(s.done);
@@ -206,6 +213,8 @@ extern "C" int vsb_tracker_destroy(vsb_tracker_t* t) {
     if (!t) return VSB_ERR_INVALID;
     cudaDeviceSynchronize();
     for (int i = 0; i < 2; i++) slot_free(t->slot[i]);
+    if (t->seq_side) cudaFree(t->seq_side);
+    if (t->seq_side_ready) cudaEventDestroy(t->seq_side_ready);
     if (t->stats) cudaFree(t->stats);
     delete t;
     return VSB_OK;
@@ -306,9 +315,38 @@ extern "C" int vsb_track_sequence_host(vsb_tracker_t* t, const uint8_t* h_frames
     const int total_pairs = n_frames - 1;
     int chunk_idx = 0;
     long long h2d = 0, d2h = 0;
-    // Chunk schedule: full chunks while plenty is left, then halving chunks (down to 32 pairs).  The pass is bound by the
-    // host link, so device work hides behind the next chunk's upload — except for the LAST chunk, whose whole compute is
-    // exposed; tapering makes that last chunk small.
+    const char* stg = getenv("VSB_HOST_STAGING");
+    const bool staged = stg && stg[0] == '1';
+    // side inputs in one go (up to 1 GB of them; longer sequences fall back to per-chunk copies)
+    const char* upf = getenv("VSB_HOST_UPFRONT");
+    const size_t al = 256;
+    const size_t sz_desc = ((size_t)n_frames * dstride + al - 1) / al * al, sz_kp = ((size_t)n_frames * kstride * 4 + al - 1) / al * al;
+    const size_t sz_nf = ((size_t)n_frames * 4 + al - 1) / al * al, sz_pr = ((size_t)total_pairs * 28 + al - 1) / al * al;
+    const size_t side_total = sz_desc + sz_kp + sz_nf + sz_pr;
+    const bool upfront = !(upf && upf[0] == '0') && side_total <= ((size_t)1 << 30);
+    uint8_t* a_desc = nullptr; float* a_kp = nullptr; int32_t* a_nf = nullptr; float* a_pr = nullptr;
+    if (upfront) {
+        if (t->seq_side_bytes < side_total) {
+            VSB_CUDA(ctx, cudaDeviceSynchronize());
+            if (t->seq_side) cudaFree(t->seq_side);
+            t->seq_side = nullptr; t->seq_side_bytes = 0;
+            VSB_CUDA(ctx, cudaMalloc((void**)&t->seq_side, side_total));
+            t->seq_side_bytes = side_total;
+        }
+        if (!t->seq_side_ready) VSB_CUDA(ctx, cudaEventCreateWithFlags(&t->seq_side_ready, cudaEventDisableTiming));
+        a_desc = t->seq_side;
+        a_kp = reinterpret_cast<float*>(t->seq_side + sz_desc);
+        a_nf = reinterpret_cast<int32_t*>(t->seq_side + sz_desc + sz_kp);
+        a_pr = reinterpret_cast<float*>(t->seq_side + sz_desc + sz_kp + sz_nf);
+        cudaStream_t s0 = t->slot[0].stream;
+        VSB_CUDA(ctx, cudaMemcpyAsync(a_desc, h_desc, (size_t)n_frames * dstride, cudaMemcpyHostToDevice, s0));
+        VSB_CUDA(ctx, cudaMemcpyAsync(a_kp, h_kp_xy, (size_t)n_frames * kstride * 4, cudaMemcpyHostToDevice, s0));
+        if (h_n_feat) VSB_CUDA(ctx, cudaMemcpyAsync(a_nf, h_n_feat, (size_t)n_frames * 4, cudaMemcpyHostToDevice, s0));
+        VSB_CUDA(ctx, cudaMemcpyAsync(a_pr, h_pose_prior, (size_t)total_pairs * 28, cudaMemcpyHostToDevice, s0));
+        VSB_CUDA(ctx, cudaEventRecord(t->seq_side_ready, s0));
+        VSB_CUDA(ctx, cudaStreamWaitEvent(t->slot[1].stream, t->seq_side_ready, 0));
+        h2d += (long long)n_frames * (dstride + kstride * 4) + (h_n_feat ? n_frames * 4LL : 0) + total_pairs * 28LL;
+    }
     for (int p0 = 0; p0 < total_pairs; chunk_idx++) {
         const int remaining = total_pairs - p0;
         int pairs = remaining < c.max_pairs ? remaining : c.max_pairs;
@@ -318,20 +356,33 @@ extern "C" int vsb_track_sequence_host(vsb_tracker_t* t, const uint8_t* h_frames
         Slot& s = t->slot[chunk_idx & 1];
         cudaStream_t st = s.stream;
         if (chunk_idx >= 2) VSB_CUDA(ctx, cudaEventSynchronize(s.done));   // slot buffers are free again
-        // frames go straight into level 0 of the packed pyramid (one strided copy, no repack kernel)
-        VSB_CUDA(ctx, cudaMemcpy2DAsync(s.pyr, (size_t)t->lay.frame_stride, h_frames + (size_t)p0 * fbytes, fbytes,
-                                        fbytes, nf, cudaMemcpyHostToDevice, st));
-        VSB_CUDA(ctx, cudaMemcpyAsync(s.desc, h_desc + (size_t)p0 * dstride, nf * dstride, cudaMemcpyHostToDevice, st));
-        VSB_CUDA(ctx, cudaMemcpyAsync(s.kp, h_kp_xy + (size_t)p0 * kstride, nf * kstride * sizeof(float),
-                                      cudaMemcpyHostToDevice, st));
-        if (h_n_feat)
-            VSB_CUDA(ctx, cudaMemcpyAsync(s.n_feat, h_n_feat + p0, nf * sizeof(int32_t), cudaMemcpyHostToDevice, st));
-        VSB_CUDA(ctx, cudaMemcpyAsync(s.prior, h_pose_prior + (size_t)p0 * 7, (size_t)pairs * 7 * sizeof(float),
-                                      cudaMemcpyHostToDevice, st));
-        h2d += (long long)nf * (fbytes + dstride + kstride * sizeof(float)) + (h_n_feat ? nf * 4LL : 0) + pairs * 28LL;
+        if (staged) {
+            // experiment knob: one contiguous copy into a staging block, the pyramid kernel copies level 0 (one more pass over
+            // the frames on the device, hidden behind the next upload)
+            if (!s.stage) VSB_CUDA(ctx, cudaMalloc((void**)&s.stage, (size_t)(c.max_pairs + 1) * fbytes));
+            VSB_CUDA(ctx, cudaMemcpyAsync(s.stage, h_frames + (size_t)p0 * fbytes, (size_t)nf * fbytes, cudaMemcpyHostToDevice, st));
+        } else {
+            // frames go straight into level 0 of the packed pyramid (one strided copy, no repack kernel)
+            VSB_CUDA(ctx, cudaMemcpy2DAsync(s.pyr, (size_t)t->lay.frame_stride, h_frames + (size_t)p0 * fbytes, fbytes,
+                                            fbytes, nf, cudaMemcpyHostToDevice, st));
+        }
+        if (!upfront) {
+            VSB_CUDA(ctx, cudaMemcpyAsync(s.desc, h_desc + (size_t)p0 * dstride, nf * dstride, cudaMemcpyHostToDevice, st));
+            VSB_CUDA(ctx, cudaMemcpyAsync(s.kp, h_kp_xy + (size_t)p0 * kstride, nf * kstride * sizeof(float),
+                                          cudaMemcpyHostToDevice, st));
+            if (h_n_feat)
+                VSB_CUDA(ctx, cudaMemcpyAsync(s.n_feat, h_n_feat + p0, nf * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+            VSB_CUDA(ctx, cudaMemcpyAsync(s.prior, h_pose_prior + (size_t)p0 * 7, (size_t)pairs * 7 * sizeof(float),
+                                          cudaMemcpyHostToDevice, st));
+            h2d += (long long)nf * (dstride + kstride * sizeof(float)) + (h_n_feat ? nf * 4LL : 0) + pairs * 28LL;
+        }
+        h2d += (long long)nf * fbytes;
         d2h += pairs * 28LL + (h_n_good ? pairs * 4LL : 0);
-        int rc = track_sequence_slot(t, s, nullptr, true, s.desc, s.kp, h_n_feat ? s.n_feat : nullptr, s.prior, nf,
-                                     s.pose, nullptr, st);
+        int rc = upfront
+            ? track_sequence_slot(t, s, staged ? s.stage : nullptr, !staged, a_desc + (size_t)p0 * dstride, a_kp + (size_t)p0 * kstride,
+                                  h_n_feat ? a_nf + p0 : nullptr, a_pr + (size_t)p0 * 7, nf, s.pose, nullptr, st)
+            : track_sequence_slot(t, s, staged ? s.stage : nullptr, !staged, s.desc, s.kp, h_n_feat ? s.n_feat : nullptr, s.prior, nf,
+                                  s.pose, nullptr, st);
         if (rc) return rc;
         VSB_CUDA(ctx, cudaMemcpyAsync(h_pose + (size_t)p0 * 7, s.pose, (size_t)pairs * 7 * sizeof(float),
                                       cudaMemcpyDeviceToHost, st));
