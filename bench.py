@@ -518,7 +518,16 @@ def main():
     if args.impl == "reference":
         run_reference(args, rank, world)
         return
-    run_gpu(args, rank, world, local_rank)
+    try:
+        run_gpu(args, rank, world, local_rank)
+    finally:
+        if world > 1:       # leave the process group cleanly (rank 0 gets here last: it alone runs the CPU baseline)
+            try:
+                import torch.distributed as dist
+                if dist.is_initialized():
+                    dist.destroy_process_group()
+            except Exception:
+                pass
 
 
 if __name__ == "__main__":
