@@ -39,11 +39,17 @@ typedef struct vsb_ctx vsb_ctx_t;
 /* ---- context ------------------------------------------------------------------------------------ */
 int vsb_version(void);
 const char* vsb_error_string(int status);
+/* A context owns scratch memory that the stand-alone compute entries (vsb_knn2_*, vsb_match_filter, vsb_gn_solve, vsb_orb_*)
+ * use internally: calls on ONE context must not overlap in time on different streams (use one context per stream, or
+ * the tracker, whose host entry keeps per-stream workspaces for its two streams). */
 int vsb_ctx_create(int device, vsb_ctx_t** ctx);
 int vsb_ctx_destroy(vsb_ctx_t* ctx);
 /* Tuning knobs (defaults in parentheses; the environment variables VSB_KNN_IMPL / VSB_GN_THREADS set the same at
  * context creation): "knn_impl" = 0 POPC kernel on the INT pipe, 1 tcgen05 tensor-core kernel, (2) tensor-core kernel
- * with the packed 16x2 epilogue; "gn_threads" = threads per frame pair of the GN solver, 64 / (128) / 256.
+ * with the packed 16x2 epilogue; "gn_threads" = threads per frame pair of the GN solver, 64 / 128 / 256 / 512 / 1024 ((0) = chosen from the
+ * batch size); "gn_impl" = (1) the tracker solves reference-mode problems with gn_track.cu, 0 = always gn_solve.cu;
+ * "gn_stage_bytes" = shared-memory budget for the staged current-image level of gn_track.cu ((8192); 0 = none);
+ * "gn_tail" = (1) the pairs of the last partial wave of a large batch get more threads each, 0 = one launch.
  * Results are identical for every setting. */
 int vsb_ctx_option(vsb_ctx_t* ctx, const char* name, int value);
 const char* vsb_last_cuda_error(vsb_ctx_t* ctx);
@@ -290,8 +296,12 @@ int vsb_orb_detect_compute_pyr(vsb_ctx_t* ctx, const uint8_t* img, int64_t img_s
 
 /* Work counters of the solver since the last call (then reset): out[0] = frame pairs solved,
  * out[1] = GN iterations (error evaluations), out[2] = sum over iterations of the candidate points visited
- * (SURVEY.md §8d's  sum_l K_l * P_l), out[3] = symmetric matches found.  Synchronises the device. */
+ * (SURVEY.md §8d's  sum_l K_l * P_l), out[3] = accepted pose updates.  Synchronises the device. */
 int vsb_tracker_stats(vsb_tracker_t* t, long long out[4]);
+/* Per-iteration trace of the solver inside the tracker (parity tests: the north-star tolerance is stated per iteration).
+ * trace: device [cfg.max_pairs][VSB_MAX_TRACE], n_trace: device [cfg.max_pairs]; both NULL switches it off.  The
+ * device entries (vsb_track_pairs / vsb_track_sequence / _orb) called afterwards fill them for their pairs. */
+int vsb_tracker_set_trace(vsb_tracker_t* t, vsb_gn_trace_t* trace, int32_t* n_trace);
 /* Bytes the last vsb_track_sequence_host call copied host->device and device->host, and its chunk count
  * (out[0..2]); the frame shared by two consecutive chunks is uploaded with both. */
 int vsb_tracker_host_traffic(vsb_tracker_t* t, long long out[3]);

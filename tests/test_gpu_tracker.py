@@ -199,3 +199,143 @@ def test_track_sequence_from_raw_frames(ctx, oracle, n_feat_max):
         assert n_good[k] == len(ref["good_q"]) > 10
         np.testing.assert_array_equal(pose[k], ref["pose"])
     tr.close()
+
+
+@pytest.mark.parametrize("n_cells,threads,stage", [(49, 0, 8192), (49, 128, 0), (49, 256, 32768), (49, 512, 8192),
+                                                   (225, 1024, 0), (225, 128, 32768), (225, 0, 8192)])
+def test_tracker_solver_per_iteration(ctx, oracle, n_cells, threads, stage):
+    """The tracker's own Gauss-Newton kernel (gn_track.cu: table-fed points, staged coarse levels) against the oracle PER
+    ITERATION — the north-star tolerance — for every block size and with / without the shared-memory staged level."""
+    import torch
+    from vislam_b200 import synth
+    pairs = [synth.make_pair(n_feat=400, seed=s) for s in (1001, 1777, 4242)]
+    ctx.option("gn_threads", threads)
+    ctx.option("gn_stage_bytes", stage)
+    try:
+        tr = ctx.tracker(752, 480, 400, pairs[0]["K"], n_cells=n_cells, max_pairs=3)
+        tr.trace_on()
+        st = lambda k: torch.from_numpy(np.stack([p[k] for p in pairs])).cuda()
+        pose, n_good = tr.track_pairs(st("prev"), st("cur"), st("d1"), st("d2"), st("kp1"), st("pose_prior"))
+        traces = tr.traces(len(pairs))
+        pose = pose.cpu().numpy()
+        from test_gpu_gn import compare_traces
+        for b, p in enumerate(pairs):
+            ref = oracle.track_pair(p["prev"], p["cur"], p["d1"], p["d2"], p["kp1"], p["K"], p["pose_prior"], n_cells=n_cells)
+            compare_traces(traces[b], ref["trace"])
+            np.testing.assert_array_equal(pose[b], ref["pose"])      # in fact the same bits
+        tr.close()
+    finally:
+        ctx.option("gn_threads", 0)
+        ctx.option("gn_stage_bytes", 8192)
+
+
+def test_tracker_solver_matches_general_kernel(ctx):
+    """gn_track.cu and gn_solve.cu give the same bits for the same pairs (gn_impl 1 / 0)."""
+    import torch
+    from vislam_b200 import synth
+    pairs = [synth.make_pair(n_feat=400, seed=s) for s in (31, 32, 33, 34)]
+    st = lambda k: torch.from_numpy(np.stack([p[k] for p in pairs])).cuda()
+    out = []
+    for impl in (1, 0):
+        ctx.option("gn_impl", impl)
+        try:
+            tr = ctx.tracker(752, 480, 400, pairs[0]["K"], n_cells=49, max_pairs=4)
+            pose, _ = tr.track_pairs(st("prev"), st("cur"), st("d1"), st("d2"), st("kp1"), st("pose_prior"))
+            out.append(pose.cpu().numpy())
+            tr.close()
+        finally:
+            ctx.option("gn_impl", 1)
+    np.testing.assert_array_equal(out[0], out[1])
+
+
+def test_tracker_tail_launch_same_bits(ctx):
+    """A batch larger than one wave of the solver (6 blocks per SM): the pairs of the last partial wave run in a second
+    launch with more threads each — every copy of a pair still gets the same bits as its first occurrence."""
+    import torch
+    import vislam_b200 as vb
+    from vislam_b200 import synth
+    sms = vb.lib().vsb_sm_count(ctx.handle)
+    uniq = [synth.make_pair(n_feat=300, seed=900 + i) for i in range(3)]
+    B = 6 * sms + 67
+    order = [i % 3 for i in range(B)]
+    tr = ctx.tracker(752, 480, 300, uniq[0]["K"], n_cells=49, max_pairs=B)
+    dev = {k: torch.from_numpy(np.stack([u[k] for u in uniq])).cuda() for k in ("prev", "cur", "d1", "d2", "kp1", "pose_prior")}
+    idx = torch.tensor(order, device="cuda")
+    st = lambda k: dev[k][idx].contiguous()
+    n0 = ctx.launches
+    pose, n_good = tr.track_pairs(st("prev"), st("cur"), st("d1"), st("d2"), st("kp1"), st("pose_prior"))
+    torch.cuda.synchronize()
+    launches = ctx.launches - n0
+    ctx.option("gn_tail", 0)
+    try:
+        n1 = ctx.launches
+        pose1, _ = tr.track_pairs(st("prev"), st("cur"), st("d1"), st("d2"), st("kp1"), st("pose_prior"))
+        torch.cuda.synchronize()
+        assert launches == (ctx.launches - n1) + 1          # the tail was a launch of its own
+    finally:
+        ctx.option("gn_tail", 1)
+    pose, pose1 = pose.cpu().numpy(), pose1.cpu().numpy()
+    np.testing.assert_array_equal(pose, pose1)
+    for b, o in enumerate(order):
+        np.testing.assert_array_equal(pose[b], pose[o])
+    tr.close()
+
+
+def test_track_sequence_host_small_max_pairs(ctx, oracle):
+    """Host entry with max_pairs below the scheduler's 32-pair floor and more than 32 pairs left: chunks must stay inside the
+    slot buffers (they are sized for max_pairs)."""
+    import torch
+    import vislam_b200 as vb
+    from vislam_b200 import synth
+    T, N = 42, 200
+    base = synth.make_sequence(6, n_feat=N, seed=2001)
+    rep = lambda a: np.concatenate([a] * 7)[:T]
+    frames, desc, kp = rep(base["frames"]), rep(base["desc"]), rep(base["kp"])
+    prior = np.stack([_prior(vb, base["R_imu_res"][k % 5], base["t_res"][k % 5]) for k in range(T - 1)])
+    pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
+    res = []
+    for mp in (16, 64):
+        tr = ctx.tracker(752, 480, N, base["K"], n_cells=49, max_pairs=mp)
+        h_pose = torch.zeros((T - 1, 7), dtype=torch.float32).pin_memory()
+        tr.track_sequence_host(pin(frames), pin(desc), pin(kp), pin(prior), h_pose)
+        assert tr.host_traffic()["chunks"] >= (T - 1 + mp - 1) // mp
+        res.append(h_pose.numpy().copy())
+        tr.close()
+    np.testing.assert_array_equal(res[0], res[1])
+    ref = oracle.track_pair(frames[0], frames[1], desc[0], desc[1], kp[0], base["K"], prior[0], n_cells=49)
+    np.testing.assert_array_equal(res[0][0], ref["pose"])
+
+
+@pytest.mark.parametrize("weight_mode", [0, 1])
+def test_track_sequence_host_float_descriptors_three_chunks(ctx, weight_mode):
+    """Host entry (two streams, consecutive chunks in flight together) with L2 descriptors — the tensor-core L2 kNN's
+    workspace — and with Tukey weights — the residual scratch — must not be shared between the streams: same poses as the
+    device entry run chunk by chunk."""
+    import torch
+    import vislam_b200 as vb
+    from vislam_b200 import synth
+    T, N = 8, 300
+    rng = np.random.default_rng(77)
+    base = synth.make_sequence(T, n_feat=N, seed=2005)
+    d0 = rng.standard_normal((N, 64)).astype(np.float32)
+    desc = []
+    for t in range(T):
+        d = d0 + 0.05 * rng.standard_normal((N, 64)).astype(np.float32)
+        desc.append(d / np.linalg.norm(d, axis=1, keepdims=True))
+    desc = np.ascontiguousarray(np.stack(desc).astype(np.float32)).view(np.uint8).reshape(T, N, 256)
+    prior = np.stack([_prior(vb, base["R_imu_res"][k], base["t_res"][k]) for k in range(T - 1)])
+    tr = ctx.tracker(752, 480, N, base["K"], n_cells=49, max_pairs=2, norm=0, desc_bytes=256,
+                     gn_opts=vb.default_gn_opts(grad_mode=1, weight_mode=weight_mode))
+    pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
+    dev = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()
+    for rep in range(3):
+        h_pose = torch.zeros((T - 1, 7), dtype=torch.float32).pin_memory()
+        tr.track_sequence_host(pin(base["frames"]), pin(desc), pin(base["kp"]), pin(prior), h_pose)
+        d_pose = []
+        for k in range(0, T - 1, 2):
+            e = min(k + 3, T)
+            pz, _ = tr.track_sequence(dev(base["frames"][k:e]), dev(desc[k:e]), dev(base["kp"][k:e]), dev(prior[k:e - 1]))
+            torch.cuda.synchronize()
+            d_pose.append(pz.cpu().numpy())
+        np.testing.assert_array_equal(np.concatenate(d_pose), h_pose.numpy())
+    tr.close()

@@ -50,10 +50,16 @@ extern "C" int vsb_ctx_create(int device, vsb_ctx_t** out) {
     c->gn_threads = 0;      // auto: by batch size
     c->pyr_impl = 1;
     c->gn_variant = 0;
+    c->gn_impl = 1;
+    c->gn_stage_bytes = 8192;
+    c->gn_tail = 1;
     c->knn_l2_impl = 1;
     if (const char* e = getenv("VSB_KNN_L2_IMPL")) c->knn_l2_impl = atoi(e) ? 1 : 0;
     if (const char* e = getenv("VSB_GN_VARIANT")) c->gn_variant = atoi(e);
     if (const char* e = getenv("VSB_KNN_IMPL")) vsb_ctx_option(c, "knn_impl", atoi(e));
+    if (const char* e = getenv("VSB_GN_IMPL")) c->gn_impl = atoi(e) ? 1 : 0;
+    if (const char* e = getenv("VSB_GN_STAGE_BYTES")) vsb_ctx_option(c, "gn_stage_bytes", atoi(e));
+    if (const char* e = getenv("VSB_GN_TAIL")) c->gn_tail = atoi(e) ? 1 : 0;
     if (const char* e = getenv("VSB_GN_THREADS")) vsb_ctx_option(c, "gn_threads", atoi(e));
     *out = c;
     return VSB_OK;
@@ -74,6 +80,21 @@ extern "C" int vsb_ctx_option(vsb_ctx_t* ctx, const char* name, int value) {
     if (!strcmp(name, "gn_variant")) {
         if (value < 0 || value > 5) return VSB_ERR_INVALID;
         ctx->gn_variant = value;
+        return VSB_OK;
+    }
+    if (!strcmp(name, "gn_impl")) {
+        if (value < 0 || value > 1) return VSB_ERR_INVALID;
+        ctx->gn_impl = value;
+        return VSB_OK;
+    }
+    if (!strcmp(name, "gn_tail")) {
+        if (value < 0 || value > 1) return VSB_ERR_INVALID;
+        ctx->gn_tail = value;
+        return VSB_OK;
+    }
+    if (!strcmp(name, "gn_stage_bytes")) {
+        if (value < 0 || value > 128 * 1024) return VSB_ERR_INVALID;
+        ctx->gn_stage_bytes = value & ~15;
         return VSB_OK;
     }
     if (!strcmp(name, "pyr_impl")) {

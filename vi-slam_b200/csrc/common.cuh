@@ -51,6 +51,9 @@ struct vsb_ctx {
     int gn_threads;   // threads per frame pair of the GN solver: 64 / 128 / 256 / 512 / 1024, 0 = chosen from the batch size
     int knn_l2_impl;  // float kNN: 0 = exact FP64 kernel, 1 = tensor-core GEMM + exact re-check (dim <= 64, dim % 8 == 0)
     int gn_variant;   // GN solver register/unroll variant (tuning experiments; 0 = default)
+    int gn_impl;      // tracker GN kernel: 1 (default) = gn_track.cu (8-byte point records + back-projection tables, staged coarse levels) for the reference modes, 0 = always gn_solve.cu
+    int gn_stage_bytes;   // gn_track.cu: shared-memory budget for the staged current-image level (0 = gather from global memory)
+    int gn_tail;      // gn_track.cu: 1 (default) = pairs of the last partial wave run with more threads each, 0 = one launch
     int pyr_impl;     // pyramid: 0 = generic shared-memory tile kernel, 1 = register-blocked kernel when w, h are multiples of 16
 };
 

@@ -21,9 +21,12 @@
 // wording).  The 6x6 system is solved by warp 0 with OpenCV's LU elimination order (cv::solve), one column of [A | b] per lane.
 #include "common.cuh"
 #include "se3.cuh"
+#include "gn_common.cuh"
 #include <stdlib.h>
 
 namespace {
+
+using namespace gn;
 
 constexpr int NRED = 28;         // 21 (upper triangle of J^T J) + 6 (J^T r) + 1 (sum w r^2)
 
@@ -91,88 +94,6 @@ gn_prepare_kernel(const GnParams P) {
         gy = 3 * (3 * (a20 - a00) + 10 * (a21 - a01) + 3 * (a22 - a02));
     }
     P.patt[slot] = make_uint2(((uint32_t)gx & 0xFFFFu) | ((uint32_t)gy << 16), i1);
-}
-
-__device__ __forceinline__ double warp_sum(double v) {
-#pragma unroll
-    for (int off = 16; off >= 1; off >>= 1) v += __shfl_down_sync(0xffffffffu, v, off);
-    return v;
-}
-
-// exact small-integer conversions on the ALU/FP pipes (keeps the quarter-rate conversion pipe for the rest)
-__device__ __forceinline__ float u23_to_float(uint32_t v) {          // 0 <= v < 2^23
-    return __fsub_rn(__uint_as_float(0x4B000000u | v), 8388608.0f);
-}
-__device__ __forceinline__ double i32_to_double(int v) {
-    return __dsub_rn(__hiloint2double(0x43300000, (int)((uint32_t)v ^ 0x80000000u)), 4503601774854144.0);
-}
-
-// D(8x8) += A(8x4) * B(4x8) in FP64 on the tensor cores.  With a == b (lane (g,t) supplies V[g] of point t)
-// this accumulates the Gram matrix V V^T of 4 points; products of floats are exact in double.
-__device__ __forceinline__ void dmma_8x8x4(double& c0, double& c1, double a, double b) {
-    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
-                 : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
-}
-
-// ---- 6x6 solve by one warp -----------------------------------------------------------------------------
-// deltaMat = A.inv() * b (VISystem.cpp:1412).  cv::MatExpr never forms the inverse here: inverse-times-matrix is turned
-// into cv::solve(A, b, DECOMP_LU) (matop.cpp MatOp_Invert::matmul -> MatOp_Solve), i.e. hal::LU32f on [A | b] with ONE
-// right-hand column.  Lane c < 6 owns column c of A, lane 6 owns b; every arithmetic operation is the one LU32f performs
-// on that element, in the same order, so the result is bit-identical to the sequential code in the oracle (vso_solve6).
-// G is the 8x8 Gram matrix of V = (J0..J5, r*w, r): A = G[0..5][0..5], J^T(r w) = G[a][6], sum r (r w) = G[7][6].
-__device__ __forceinline__ void warp_solve6(const double* G, int lane, float delta[6]) {
-    const unsigned FULL = 0xffffffffu;
-    float v[6];
-#pragma unroll
-    for (int r = 0; r < 6; r++) {
-        float x = 0.f;
-        if (lane < 6) x = (float)G[r * 8 + lane];                 // A = J^T J rounded once to float (:1408)
-        else if (lane == 6) x = (float)(-1.0 * G[r * 8 + 6]);     // b = -J^T (r w): gemm alpha = -1, rounded once (:1409)
-        v[r] = x;
-    }
-    const float eps = 1.1920929e-07f * 10;
-    bool singular = false;
-#pragma unroll
-    for (int i = 0; i < 6; i++) {
-        float col[6];
-#pragma unroll
-        for (int j = i; j < 6; j++) col[j] = __shfl_sync(FULL, v[j], i);
-        int k = i;
-        float best = fabsf(col[i]);
-#pragma unroll
-        for (int j = i + 1; j < 6; j++)
-            if (fabsf(col[j]) > best) { best = fabsf(col[j]); k = j; }
-        if (best < eps) singular = true;
-#pragma unroll
-        for (int j = i + 1; j < 6; j++)
-            if (k == j) {
-                float t = v[i]; v[i] = v[j]; v[j] = t;
-                t = col[i]; col[i] = col[j]; col[j] = t;
-            }
-        const float d = F_DIV(-1.f, col[i]);
-#pragma unroll
-        for (int j = i + 1; j < 6; j++) {
-            const float alpha = F_MUL(col[j], d);
-            v[j] = F_ADD(v[j], F_MUL(alpha, v[i]));
-        }
-    }
-    float x[6];
-#pragma unroll
-    for (int i = 5; i >= 0; i--) {
-        float s = v[i];
-#pragma unroll
-        for (int k = i + 1; k < 6; k++) {
-            const float u = __shfl_sync(FULL, v[i], k);
-            s = F_SUB(s, F_MUL(u, x[k]));
-        }
-        const float diag = __shfl_sync(FULL, v[i], i);
-        x[i] = F_DIV(s, diag);
-    }
-#pragma unroll
-    for (int a = 0; a < 6; a++) {
-        const float xa = __shfl_sync(FULL, x[a], 6);               // the solution is lane 6's column
-        delta[a] = singular ? 0.f : xa;                            // singular => cv::solve zeroes the result => delta = 0
-    }
 }
 
 // ---- Tukey weights (optional mode; upstream it is commented out at VISystem.cpp:1344) ---------------------------
@@ -285,6 +206,9 @@ gn_solve_kernel(const GnParams P) {
     const int tid = threadIdx.x;
     const int lane = tid & 31, warp = tid >> 5;
     const int g8 = lane >> 2, t4 = lane & 3;
+    // the serial part of an iteration rotates over the warps with the block index: warp w runs on SM sub-partition w % 4,
+    // and with warp 0 of EVERY block in that role sub-partition 0 would carry all of it while the other three wait
+    const int swarp = (int)(blockIdx.x % NW);
 
     __shared__ float s_pose[7];
     __shared__ double s_md[12];
@@ -572,7 +496,7 @@ gn_solve_kernel(const GnParams P) {
             }
             __syncthreads();
             // ---- error test, normal equations, pose update (warp 0; VISystem.cpp:1343-1421) ----------------
-            if (warp == 0) {
+            if (warp == swarp) {
                 int stop = 0, updated = 0;
                 float err = 0.f;
                 float delta[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
@@ -657,16 +581,20 @@ int vsb_gn_solve_stats(vsb_ctx_t* ctx, const uint8_t* prev_pyr, const uint8_t* c
     if (opts->grad_mode == 0 && (!prev_gx || !prev_gy)) return VSB_ERR_INVALID;
     if (trace && (opts->first_lvl - opts->last_lvl + 1) * opts->max_iterations > VSB_MAX_TRACE) return VSB_ERR_CAPACITY;
     if (count == 0) return VSB_OK;
-    // context scratch: [point attributes unless the caller owns them][Tukey residuals when weight_mode == 1]
-    const size_t patt_bytes = patt_scratch ? 0 : ((size_t)count * layout->levels * cand_cap * sizeof(uint2) + 255) & ~(size_t)255;
-    const size_t resid_bytes = opts->weight_mode == 1 ? (size_t)count * cand_cap * sizeof(float) : 0;
-    float* resid = nullptr;
-    if (patt_bytes + resid_bytes) {
-        void* scratch = nullptr;
-        int rc = vsb_scratch_reserve(ctx, patt_bytes + resid_bytes + 256, &scratch);
+    // point attributes: the caller's buffer, or the context scratch (stand-alone entry; see the header on concurrent use).
+    // Tukey residuals: workspace of the launching STREAM — the tracker's host entry runs two chunks on two streams.
+    cudaStream_t st = (cudaStream_t)stream;
+    if (!patt_scratch) {
+        const size_t patt_bytes = (size_t)count * layout->levels * cand_cap * sizeof(uint2) + 256;
+        int rc = vsb_scratch_reserve(ctx, patt_bytes, &patt_scratch);
         if (rc) return rc;
-        if (!patt_scratch) patt_scratch = scratch;
-        if (resid_bytes) resid = reinterpret_cast<float*>(static_cast<uint8_t*>(scratch) + patt_bytes);
+    }
+    float* resid = nullptr;
+    if (opts->weight_mode == 1) {
+        void* ws = nullptr;
+        int rc = vsb_stream_ws_reserve(ctx, st, (size_t)count * cand_cap * sizeof(float) + 256, &ws);
+        if (rc) return rc;
+        resid = static_cast<float*>(ws);
     }
     GnParams P;
     P.resid = resid;
@@ -681,7 +609,6 @@ int vsb_gn_solve_stats(vsb_ctx_t* ctx, const uint8_t* prev_pyr, const uint8_t* c
     for (int l = 0; l < VSB_MAX_LEVELS; l++) P.K[l] = K[l];
     P.pose_in = pose_in; P.o = *opts; P.pose_out = pose_out; P.trace = trace; P.n_trace = n_trace;
     P.stats = stats;
-    cudaStream_t st = (cudaStream_t)stream;
     const int nlev = opts->first_lvl - opts->last_lvl + 1;
     if (cand_cap > 0 && !(patt_ready && patt_scratch)) {     // patt_ready: the caller's fused candidate pass wrote the records
         for (int z0 = 0; z0 < count; z0 += 65535) {

@@ -444,8 +444,6 @@ l2_fallback_kernel(const L2TcParams P, unsigned long long* __restrict__ key12, u
 
 }  // namespace
 
-int vsb_scratch2_reserve(vsb_ctx* ctx, size_t bytes, void** out);
-
 // Tensor-core implementation behind vsb_knn2_l2_keys (knn_l2.cu dispatches on ctx->knn_l2_impl and the dimension).
 int vsb_knn2_l2_tc(vsb_ctx* ctx, const float* d1, int n1_max, const int32_t* n1, const float* d2, int n2_max,
                    const int32_t* n2, int dim, int count, unsigned long long* key12, unsigned long long* key21,
@@ -454,13 +452,15 @@ int vsb_knn2_l2_tc(vsb_ctx* ctx, const float* d1, int n1_max, const int32_t* n1,
     if (dim <= 0 || dim > 64 || (dim & 7)) return VSB_ERR_UNSUPPORTED;
     if ((((uintptr_t)d1 | (uintptr_t)d2) & 15) != 0) return VSB_ERR_UNSUPPORTED;
     const size_t nd = (size_t)count * ((size_t)n1_max + n2_max);
-    // scratch: prep float4 [nd] | cand int4 [nd] | flagged rows int2 [nd] | nmax u32 [2 count] | flagged-row counter
+    // workspace of the launching STREAM (the tracker's host entry has two chunks in flight on two streams, and a
+    // context-wide area would be shared by both): prep float4 [nd] | cand int4 [nd] | flagged rows int2 [nd] |
+    // nmax u32 [2 count] | flagged-row counter
     const size_t off_cand = nd * sizeof(float4);
     const size_t off_flag = off_cand + nd * sizeof(int4);
     const size_t off_nmax = (off_flag + nd * sizeof(int2) + 255) & ~(size_t)255;
     const size_t off_cnt = (off_nmax + (size_t)count * 2 * sizeof(uint32_t) + 7) & ~(size_t)7;
     void* scratch = nullptr;
-    int rc = vsb_scratch2_reserve(ctx, off_cnt + 64, &scratch);
+    int rc = vsb_stream_ws_reserve(ctx, st, off_cnt + 64, &scratch);
     if (rc) return rc;
     uint8_t* base = static_cast<uint8_t*>(scratch);
     float4* prep1 = reinterpret_cast<float4*>(base);

@@ -255,6 +255,11 @@ struct CandParams {
     // points as doubles (VISystem.cpp:1519-1524 with z = 1; bx = backproj_offset(cx, invfx), see se3.cuh), which is all the
     // solver needs of a point
     double2* xy;
+    // ... or (gn_track.cu's form) nothing per point but the record, which then also names the point's slots in the
+    // per-feature back-projection tables: {gx | gy << 16, I_prev | (f * 11 + column) << 8 | (f * 11 + row) << 20}, and
+    // per feature the first column / row of its patch
+    short2* org;
+    int feat_cap;
     float bx[VSB_MAX_LEVELS], by[VSB_MAX_LEVELS], invfx[VSB_MAX_LEVELS], invfy[VSB_MAX_LEVELS];
 };
 
@@ -289,6 +294,8 @@ candidates_kernel(const float* __restrict__ good_xy, int good_cap, const int32_t
         const int ni = max(ib - ia + 1, 0), nj = max(jb - ja + 1, 0);
         cnt = ni * nj;
         s_ia[tid] = ia; s_ja[tid] = ja; s_nj[tid] = nj;
+        if (P.org != nullptr && lvl >= P.last_lvl && tid < P.feat_cap)
+            P.org[((size_t)prob * P.levels + lvl) * P.feat_cap + tid] = make_short2((short)ia, (short)ja);
     }
     s_cnt[tid] = cnt;
     // exclusive prefix of the per-feature counts (cnt is 0 from feature nf on): warp scans, then the eight warp totals
@@ -357,11 +364,13 @@ candidates_kernel(const float* __restrict__ good_xy, int good_cap, const int32_t
             // (float) of a small non-negative integer without the conversion pipe: 2^23 + n is exact, so is the subtraction
             const float xf = __fsub_rn(__int_as_float(0x4B000000 | (ia + ii)), 8388608.0f);
             const float yf = __fsub_rn(__int_as_float(0x4B000000 | (ja + jj)), 8388608.0f);
-            if (attrs && P.xy) {
+            if (attrs && P.org) {
+                // no per-point coordinates at all: the record carries the table slots
+            } else if (attrs && P.xy) {
                 const float X = __fadd_rn(__fmul_rn(xf, P.invfx[lvl]), P.bx[lvl]);   // * z (= 1) is the identity
                 const float Y = __fadd_rn(__fmul_rn(yf, P.invfy[lvl]), P.by[lvl]);
                 P.xy[((size_t)prob * P.levels + lvl) * cand_cap + off + p] = make_double2((double)X, (double)Y);
-            } else {
+            } else if (cand != nullptr) {
                 out[off + p] = make_float4(xf, yf, 1.0f, 1.0f);
             }
             if (attrs) {
@@ -375,7 +384,9 @@ candidates_kernel(const float* __restrict__ good_xy, int good_cap, const int32_t
                 const int a20 = q2[0], a21 = q2[1], a22 = q2[2];
                 const int gx = 3 * (3 * (a02 - a00) + 10 * (a12 - a10) + 3 * (a22 - a20));
                 const int gy = 3 * (3 * (a20 - a00) + 10 * (a21 - a01) + 3 * (a22 - a02));
-                pout[off + p] = make_uint2(((uint32_t)gx & 0xFFFFu) | ((uint32_t)gy << 16), (uint32_t)a11);
+                uint32_t tag = (uint32_t)a11;
+                if (P.org) tag |= (uint32_t)(f * 11 + ii) << 8 | (uint32_t)(f * 11 + jj) << 20;
+                pout[off + p] = make_uint2(((uint32_t)gx & 0xFFFFu) | ((uint32_t)gy << 16), tag);
             }
             ii += di;
             jj += dj;
@@ -470,20 +481,24 @@ extern "C" int vsb_gradient_build(vsb_ctx_t* ctx, const uint8_t* pyr, int count,
 int vsb_candidates_prepare(vsb_ctx_t* ctx, const float* good_xy, int good_cap, const int32_t* n_good, int count, int levels,
                            const int* lw, const int* lh, float* cand, int cand_cap, int32_t* n_cand,
                            const uint8_t* prev_pyr, int64_t pair_stride, const vsb_pyr_layout_t* layout, int first_lvl,
-                           int last_lvl, void* patt, void* xy, const vsb_intr_t* K, void* stream) {
-    if (!ctx || !good_xy || !n_good || !cand || !n_cand || !lw || !lh) return VSB_ERR_INVALID;
+                           int last_lvl, void* patt, void* xy, const vsb_intr_t* K, void* org, int feat_cap, void* stream) {
+    if (!ctx || !good_xy || !n_good || (!cand && !org) || !n_cand || !lw || !lh) return VSB_ERR_INVALID;
+    if (org && (!prev_pyr || !layout || !patt || feat_cap < 1)) return VSB_ERR_INVALID;
     if (levels < 1 || levels > VSB_MAX_LEVELS || count < 0 || cand_cap < 0) return VSB_ERR_INVALID;
     if (count == 0) return VSB_OK;
     CandParams P;
     P.levels = levels;
     for (int l = 0; l < levels; l++) { P.lw[l] = lw[l]; P.lh[l] = lh[l]; }
     P.prev_pyr = nullptr; P.pair_stride = 0; P.first_lvl = -1; P.last_lvl = 0; P.patt = nullptr; P.xy = nullptr;
+    P.org = nullptr; P.feat_cap = 0;
     for (int l = 0; l < VSB_MAX_LEVELS; l++) { P.bx[l] = P.by[l] = 0.f; P.invfx[l] = P.invfy[l] = 0.f; }
     memset(&P.lay, 0, sizeof(P.lay));
     if (prev_pyr && layout && patt) {
         P.prev_pyr = prev_pyr; P.pair_stride = pair_stride; P.lay = *layout;
         P.first_lvl = first_lvl; P.last_lvl = last_lvl; P.patt = reinterpret_cast<uint2*>(patt);
-        if (xy && K) {
+        if (org) {
+            P.org = reinterpret_cast<short2*>(org); P.feat_cap = feat_cap;
+        } else if (xy && K) {
             P.xy = reinterpret_cast<double2*>(xy);
             for (int l = 0; l < VSB_MAX_LEVELS; l++) {
                 P.bx[l] = vsb::backproj_offset(K[l].cx, K[l].invfx); P.by[l] = vsb::backproj_offset(K[l].cy, K[l].invfy);
@@ -503,6 +518,6 @@ extern "C" int vsb_candidates_build(vsb_ctx_t* ctx, const float* good_xy, int go
                                     int count, int levels, const int* lw, const int* lh, float* cand, int cand_cap,
                                     int32_t* n_cand, void* stream) {
     return vsb_candidates_prepare(ctx, good_xy, good_cap, n_good, count, levels, lw, lh, cand, cand_cap, n_cand, nullptr, 0,
-                                  nullptr, 0, 0, nullptr, nullptr, nullptr, stream);
+                                  nullptr, 0, 0, nullptr, nullptr, nullptr, nullptr, 0, stream);
 }
 

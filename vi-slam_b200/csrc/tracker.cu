@@ -22,7 +22,12 @@ int vsb_match_filter_keys(vsb_ctx_t* ctx, const void* keys12, const void* keys21
 int vsb_candidates_prepare(vsb_ctx_t* ctx, const float* good_xy, int good_cap, const int32_t* n_good, int count, int levels,
                            const int* lw, const int* lh, float* cand, int cand_cap, int32_t* n_cand,
                            const uint8_t* prev_pyr, int64_t pair_stride, const vsb_pyr_layout_t* layout, int first_lvl,
-                           int last_lvl, void* patt, void* xy, const vsb_intr_t* K, void* stream);
+                           int last_lvl, void* patt, void* xy, const vsb_intr_t* K, void* org, int feat_cap, void* stream);
+int vsb_gn_track(vsb_ctx_t* ctx, const uint8_t* cur_pyr, int64_t pair_stride_pixels, const vsb_pyr_layout_t* layout,
+                 const void* patt, const void* org, const int32_t* n_cand, const int32_t* n_good, int cand_cap, int feat_cap,
+                 const vsb_intr_t K[VSB_MAX_LEVELS], const float* pose_in, const vsb_gn_opts_t* opts, int pair0, int count,
+                 int threads, float* pose_out, vsb_gn_trace_t* trace, int32_t* n_trace, unsigned long long* stats,
+                 void* stream);
 int vsb_knn_unpack(vsb_ctx* ctx, const uint32_t* keys, int n_max, const int32_t* n, int count, int32_t* idx,
                    float* dist, cudaStream_t st);
 int vsb_knn2_l2_keys(vsb_ctx* ctx, const float* d1, int n1_max, const int32_t* n1, const float* d2, int n2_max,
@@ -53,12 +58,16 @@ struct Slot {
     float* cand = nullptr;
     uint2* patt = nullptr;        // per-point attributes of the solver, [max_pairs][levels][cand_cap]
     int32_t* n_cand = nullptr;
+    short2* org = nullptr;        // first column / row of every feature's patch, [max_pairs][levels][feat_cap] (gn_track.cu)
     float* pose = nullptr;
     float* orb_resp = nullptr;    // [max_pairs + 1][n_feat] each, allocated on the first vsb_track_sequence_orb call
     float* orb_angle = nullptr;
     uint8_t* stage = nullptr;     // [max_pairs + 1][w * h] contiguous frames of the host entry (VSB_HOST_STAGING=1), allocated on first use
     cudaStream_t stream = nullptr;
     cudaEvent_t done = nullptr;
+    // the solver's tail launch (pairs of the last partial wave, more threads each) runs beside the main one
+    cudaStream_t aux = nullptr;
+    cudaEvent_t fork = nullptr, join = nullptr;
 };
 
 }  // namespace
@@ -69,10 +78,12 @@ struct vsb_tracker {
     vsb_pyr_layout_t lay;
     vsb_intr_t K[VSB_MAX_LEVELS];
     int lw[VSB_MAX_LEVELS], lh[VSB_MAX_LEVELS];
-    int good_cap, cand_cap;
+    int good_cap, cand_cap, feat_cap;
     Slot slot[2];
     int n_slots;
     unsigned long long* stats;   // device, 4 counters shared by both slots
+    vsb_gn_trace_t* trace = nullptr;   // optional per-iteration trace of the next device-entry call (vsb_tracker_set_trace)
+    int32_t* n_trace = nullptr;
     long long host_h2d_bytes, host_d2h_bytes, host_chunks;   // what the last vsb_track_sequence_host call moved
     // whole-sequence side inputs of the host entry (descriptors, key points, counts, priors: a tenth of the bytes), uploaded with
     // one copy each before the first chunk instead of four small copies per chunk; grown on demand
@@ -112,19 +123,51 @@ int slot_alloc(vsb_tracker* t, Slot& s) {
     A(cand, P * VSB_MAX_LEVELS * (size_t)t->cand_cap * 4);
     A(patt, P * VSB_MAX_LEVELS * (size_t)t->cand_cap);
     A(n_cand, P * VSB_MAX_LEVELS);
+    A(org, P * VSB_MAX_LEVELS * (size_t)t->feat_cap);
     A(pose, P * 7);
 #undef A
     VSB_CUDA(ctx, cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
     VSB_CUDA(ctx, cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming));
+    VSB_CUDA(ctx, cudaStreamCreateWithFlags(&s.aux, cudaStreamNonBlocking));
+    VSB_CUDA(ctx, cudaEventCreateWithFlags(&s.fork, cudaEventDisableTiming));
+    VSB_CUDA(ctx, cudaEventCreateWithFlags(&s.join, cudaEventDisableTiming));
     return VSB_OK;
 }
 
 void slot_free(Slot& s) {
-    void* ptrs[] = {s.pyr, s.gx, s.gy, s.desc, s.kp, s.n_feat, s.prior, s.key12, s.key21, s.good_q, s.good_t, s.good_d, s.n_good, s.n_sym, s.good_xy, s.cand, s.patt, s.n_cand, s.pose, s.orb_resp, s.orb_angle, s.stage};
+    void* ptrs[] = {s.pyr, s.gx, s.gy, s.desc, s.kp, s.n_feat, s.prior, s.key12, s.key21, s.good_q, s.good_t, s.good_d, s.n_good, s.n_sym, s.good_xy, s.cand, s.patt, s.n_cand, s.org, s.pose, s.orb_resp, s.orb_angle, s.stage};
     for (void* p : ptrs) if (p) cudaFree(p);
     if (s.stream) cudaStreamDestroy(s.stream);
     if (s.done) cudaEventDestroy(s.done);
+    if (s.aux) cudaStreamDestroy(s.aux);
+    if (s.fork) cudaEventDestroy(s.fork);
+    if (s.join) cudaEventDestroy(s.join);
     s = Slot();
+}
+
+// Threads per frame pair of gn_track.cu.  A pair is one block, so a batch that cannot fill the machine with 128-thread
+// blocks gets more threads per pair: the largest block size whose resident blocks (6 / 3 / 2 / 1 per SM for 128 / 256 / 512 /
+// 1024 threads) still hold the whole batch.  A large batch runs in waves of 6 x SMs blocks; the pairs of the last, partial
+// wave would leave most of the machine idle while they finish, so they go to a second launch with more threads each, on
+// a second stream: its blocks fill the SMs that the main launch drains.  Measured on configs[1] (1999 pairs; tools/
+// sweep_gn_tail.sh): 1.85 ms with the tail launch, 1.89 ms without; tail sizes 100..600 pairs and 256 / 512 threads all
+// land within 2 % of each other.
+void gn_plan(const vsb_ctx* ctx, int count, int* threads, int* n_tail, int* threads_tail) {
+    const int sms = ctx->sm_count > 0 ? ctx->sm_count : 148;
+    auto fit = [&](int n) { return n <= sms ? 1024 : n <= 2 * sms ? 512 : n <= 3 * sms ? 256 : 128; };
+    *n_tail = 0; *threads_tail = 128;
+    if (ctx->gn_threads) { *threads = ctx->gn_threads < 128 ? 128 : ctx->gn_threads; return; }
+    *threads = fit(count);
+    if (const char* e = getenv("VSB_GN_TAIL_PAIRS")) {           // experiment knob: explicit tail size / threads
+        const char* tt = getenv("VSB_GN_TAIL_THREADS");
+        *n_tail = atoi(e) < count ? atoi(e) : 0; *threads_tail = tt ? atoi(tt) : 512;
+        return;
+    }
+    if (ctx->gn_tail && count > 6 * sms) {
+        const int rem = count % (6 * sms);
+        const int tt = fit(rem);
+        if (rem > 0 && tt > 128) { *n_tail = rem; *threads_tail = tt; }
+    }
 }
 
 // Stages after the pyramids exist: match -> filter -> candidates -> GN.  prev pyramid of pair c is
@@ -158,17 +201,41 @@ int run_pairs(vsb_tracker* t, Slot& s, const uint8_t* pyr_prev, const uint8_t* p
     // candidate points and — when the gradients are evaluated at the points (grad_mode 1) — the solver's per-point
     // attribute records in the same pass
     const int fused = c.gn.grad_mode == 1 ? 1 : 0;
-    // reference defaults (identity weights, FP64 Gram): the points are handed over already back-projected, as doubles,
+    // reference modes (identity weights, nearest-pixel lookup, FP64 Gram): gn_track.cu — 8-byte records that name their
+    // slots in per-feature back-projection tables, nothing else per point
+    const bool tables = fused && ctx->gn_impl == 1 && c.gn.accum_mode == 0 && c.gn.weight_mode == 0 && c.gn.sample_mode == 0 &&
+                        t->feat_cap * 11 <= 4096;
+    // ... otherwise gn_solve.cu; with identity weights the points are handed over already back-projected, as doubles,
     // in the candidate buffer itself (a double2 is as wide as the float4 row it replaces)
-    const int unit = fused && c.gn.accum_mode == 0 && c.gn.weight_mode == 0;
+    const int unit = fused && !tables && c.gn.accum_mode == 0 && c.gn.weight_mode == 0;
     if ((rc = vsb_candidates_prepare(ctx, s.good_xy, t->good_cap, s.n_good, count, t->lay.levels, t->lw, t->lh, s.cand,
                                      t->cand_cap, s.n_cand, fused ? pyr_prev : nullptr, t->lay.frame_stride, &t->lay,
                                      c.gn.first_lvl, c.gn.last_lvl, fused ? s.patt : nullptr, unit ? (void*)s.cand : nullptr,
-                                     t->K, st)))
+                                     t->K, tables ? (void*)s.org : nullptr, t->feat_cap, st)))
         return rc;
-    if ((rc = vsb_gn_solve_stats(ctx, pyr_prev, pyr_cur, gx_prev, gy_prev, t->lay.frame_stride, &t->lay,
-                                 unit ? nullptr : s.cand, t->cand_cap, s.n_cand, t->K, prior, &c.gn, count, pose_out, nullptr,
-                                 nullptr, t->stats, s.patt, fused, unit ? (const void*)s.cand : nullptr, st)))
+    if (tables) {
+        int threads, n_tail, threads_tail;
+        gn_plan(ctx, count, &threads, &n_tail, &threads_tail);
+        const int n_main = count - n_tail;
+        ProfScope ps(ctx, VSB_K_GN_SOLVE, st);
+        if (n_tail > 0) {
+            VSB_CUDA(ctx, cudaEventRecord(s.fork, st));
+            VSB_CUDA(ctx, cudaStreamWaitEvent(s.aux, s.fork, 0));
+        }
+        if ((rc = vsb_gn_track(ctx, pyr_cur, t->lay.frame_stride, &t->lay, s.patt, s.org, s.n_cand, s.n_good, t->cand_cap,
+                               t->feat_cap, t->K, prior, &c.gn, 0, n_main, threads, pose_out, t->trace, t->n_trace, t->stats, st)))
+            return rc;
+        if (n_tail > 0) {
+            if ((rc = vsb_gn_track(ctx, pyr_cur, t->lay.frame_stride, &t->lay, s.patt, s.org, s.n_cand, s.n_good, t->cand_cap,
+                                   t->feat_cap, t->K, prior, &c.gn, n_main, n_tail, threads_tail, pose_out, t->trace,
+                                   t->n_trace, t->stats, s.aux)))
+                return rc;
+            VSB_CUDA(ctx, cudaEventRecord(s.join, s.aux));
+            VSB_CUDA(ctx, cudaStreamWaitEvent(st, s.join, 0));
+        }
+    } else if ((rc = vsb_gn_solve_stats(ctx, pyr_prev, pyr_cur, gx_prev, gy_prev, t->lay.frame_stride, &t->lay,
+                                        unit ? nullptr : s.cand, t->cand_cap, s.n_cand, t->K, prior, &c.gn, count, pose_out,
+                                        t->trace, t->n_trace, t->stats, s.patt, fused, unit ? (const void*)s.cand : nullptr, st)))
         return rc;
     if (n_good_out)
         VSB_CUDA(ctx, cudaMemcpyAsync(n_good_out, s.n_good, sizeof(int32_t) * count, cudaMemcpyDeviceToDevice, st));
@@ -193,6 +260,7 @@ extern "C" int vsb_tracker_create(vsb_ctx_t* ctx, const vsb_tracker_cfg_t* cfg, 
     t->good_cap = root * root;
     const int nf = t->good_cap < VSB_MAX_GN_FEATURES ? t->good_cap : VSB_MAX_GN_FEATURES;
     t->cand_cap = 121 * nf;
+    t->feat_cap = nf;
     t->n_slots = 2;
     t->stats = nullptr;
     t->host_h2d_bytes = t->host_d2h_bytes = t->host_chunks = 0;
@@ -226,6 +294,7 @@ static int track_sequence_slot(vsb_tracker* t, Slot& s, const uint8_t* frames, b
     vsb_ctx* ctx = t->ctx;
     const vsb_tracker_cfg_t& c = t->cfg;
     const int pairs = n_frames - 1;
+    if (pairs > c.max_pairs) return VSB_ERR_CAPACITY;
     int rc;
     // Camera::Update for every frame (level 0 is copied unless it was uploaded straight into the pyramid)
     if ((rc = vsb_pyramid_build(ctx, frames_in_place ? nullptr : frames, (int64_t)c.w * c.h, c.w, n_frames, &t->lay, s.pyr, st)))
@@ -352,6 +421,7 @@ extern "C" int vsb_track_sequence_host(vsb_tracker_t* t, const uint8_t* h_frames
         int pairs = remaining < c.max_pairs ? remaining : c.max_pairs;
         if (remaining <= 2 * c.max_pairs && remaining > 32) pairs = (remaining + 1) / 2 < c.max_pairs ? (remaining + 1) / 2 : c.max_pairs;
         if (pairs < 32 && remaining >= 32) pairs = 32;
+        if (pairs > c.max_pairs) pairs = c.max_pairs;      // the slot buffers hold max_pairs pairs, whatever the schedule prefers
         const int nf = pairs + 1;
         Slot& s = t->slot[chunk_idx & 1];
         cudaStream_t st = s.stream;
@@ -383,7 +453,11 @@ extern "C" int vsb_track_sequence_host(vsb_tracker_t* t, const uint8_t* h_frames
                                   h_n_feat ? a_nf + p0 : nullptr, a_pr + (size_t)p0 * 7, nf, s.pose, nullptr, st)
             : track_sequence_slot(t, s, staged ? s.stage : nullptr, !staged, s.desc, s.kp, h_n_feat ? s.n_feat : nullptr, s.prior, nf,
                                   s.pose, nullptr, st);
-        if (rc) return rc;
+        if (rc) {
+            // copies into the caller's host buffers may still be in flight: finish them before handing the buffers back
+            for (int i = 0; i < 2; i++) cudaStreamSynchronize(t->slot[i].stream);
+            return rc;
+        }
         VSB_CUDA(ctx, cudaMemcpyAsync(h_pose + (size_t)p0 * 7, s.pose, (size_t)pairs * 7 * sizeof(float),
                                       cudaMemcpyDeviceToHost, st));
         if (h_n_good)
@@ -393,6 +467,12 @@ extern "C" int vsb_track_sequence_host(vsb_tracker_t* t, const uint8_t* h_frames
     }
     for (int i = 0; i < 2; i++) VSB_CUDA(ctx, cudaStreamSynchronize(t->slot[i].stream));
     t->host_h2d_bytes = h2d; t->host_d2h_bytes = d2h; t->host_chunks = chunk_idx;
+    return VSB_OK;
+}
+
+extern "C" int vsb_tracker_set_trace(vsb_tracker_t* t, vsb_gn_trace_t* trace, int32_t* n_trace) {
+    if (!t || ((trace == nullptr) != (n_trace == nullptr))) return VSB_ERR_INVALID;
+    t->trace = trace; t->n_trace = n_trace;
     return VSB_OK;
 }
 

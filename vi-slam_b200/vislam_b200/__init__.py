@@ -56,7 +56,7 @@ EXPORTS = [
     "vsb_gather_keypoints", "vsb_init_pyramid", "vsb_gn_default_opts", "vsb_gn_solve", "vsb_initial_pose",
     "vsb_se3_mul", "vsb_tracker_create", "vsb_tracker_destroy", "vsb_track_sequence",
     "vsb_track_sequence_host", "vsb_track_sequence_orb", "vsb_track_pairs", "vsb_kernel_count", "vsb_kernel_name", "vsb_profile_enable",
-    "vsb_profile_reset", "vsb_profile_read", "vsb_popc_peak", "vsb_tracker_stats", "vsb_tracker_host_traffic", "vsb_fast_detect", "vsb_orb_detect_compute", "vsb_orb_detect_compute_pyr",
+    "vsb_profile_reset", "vsb_profile_read", "vsb_popc_peak", "vsb_tracker_stats", "vsb_tracker_set_trace", "vsb_tracker_host_traffic", "vsb_fast_detect", "vsb_orb_detect_compute", "vsb_orb_detect_compute_pyr",
     "vsb_malloc", "vsb_free", "vsb_host_alloc", "vsb_host_free", "vsb_upload", "vsb_upload_2d", "vsb_download",
     "vsb_copy", "vsb_memset", "vsb_stream_create", "vsb_stream_destroy", "vsb_stream_sync",
     "vsb_nn_filter", "vsb_sym_matches", "vsb_sort_keys", "vsb_grid_best", "vsb_warp_se3", "vsb_se3_exp",
@@ -121,6 +121,7 @@ def lib():
     L.vsb_profile_read.argtypes = [vp, i32, C.POINTER(C.c_double), C.POINTER(C.c_longlong)]
     L.vsb_popc_peak.argtypes = [vp, C.POINTER(C.c_double), vp]
     L.vsb_tracker_stats.argtypes = [vp, C.POINTER(C.c_longlong)]
+    L.vsb_tracker_set_trace.argtypes = [vp, vp, vp]
     L.vsb_tracker_host_traffic.argtypes = [vp, C.POINTER(C.c_longlong)]
     L.vsb_fast_detect.argtypes = [vp, vp, i64, i32, i32, i32, i32, i32, i32, i32, vp, vp, vp, vp]
     L.vsb_orb_detect_compute.argtypes = [vp, vp, i64, i32, i32, i32, i32, i32, i32, i32, vp, vp, vp, vp, vp, vp]
@@ -155,6 +156,16 @@ def init_pyramid(w, h, fx, fy, cx, cy):
     K = (Intr * MAX_LEVELS)()
     check(lib().vsb_init_pyramid(w, h, fx, fy, cx, cy, K))
     return K
+
+
+def unpack_traces(raw, nt, count):
+    """[count][MAX_TRACE] vsb_gn_trace_t bytes -> per pair a list of dicts."""
+    traces = []
+    for b in range(count):
+        arr = (GnTrace * MAX_TRACE).from_buffer_copy(raw[b].tobytes())
+        traces.append([dict(lvl=e.lvl, iter=e.iter, n_valid=e.n_valid, updated=e.updated, error=e.error,
+                            pose=list(e.pose), delta=list(e.delta)) for e in arr[:nt[b]]])
+    return traces
 
 
 def _ptr(t):
@@ -389,14 +400,7 @@ class Context:
         if not want_trace:
             return pose_out, None
         self.torch.cuda.synchronize(self.dev)
-        raw = trace.cpu().numpy()
-        nt = n_trace.cpu().numpy()
-        traces = []
-        for b in range(B):
-            arr = (GnTrace * MAX_TRACE).from_buffer_copy(raw[b].tobytes())
-            traces.append([dict(lvl=e.lvl, iter=e.iter, n_valid=e.n_valid, updated=e.updated, error=e.error,
-                                pose=list(e.pose), delta=list(e.delta)) for e in arr[:nt[b]]])
-        return pose_out, traces
+        return pose_out, unpack_traces(trace.cpu().numpy(), n_trace.cpu().numpy(), B)
 
     def tracker(self, w, h, n_feat_max, K, n_cells=49, max_pairs=256, norm=1, desc_bytes=32, ratio=0.8, sym_mode=0,
                 gn_opts=None):
@@ -435,6 +439,22 @@ class Tracker:
         out = (C.c_longlong * 4)()
         check(lib().vsb_tracker_stats(self.handle, out), self.ctx.handle)
         return dict(pairs=out[0], iterations=out[1], point_visits=out[2], updates=out[3])
+
+    def trace_on(self):
+        """Record the solver's per-iteration trace of the following device-entry calls (read it with traces())."""
+        t = self.ctx.torch
+        P = self.cfg.max_pairs
+        self._trace = t.zeros((P, MAX_TRACE, C.sizeof(GnTrace)), dtype=t.uint8, device=self.ctx.dev)
+        self._n_trace = t.zeros((P,), dtype=t.int32, device=self.ctx.dev)
+        check(lib().vsb_tracker_set_trace(self.handle, _ptr(self._trace), _ptr(self._n_trace)), self.ctx.handle)
+
+    def trace_off(self):
+        check(lib().vsb_tracker_set_trace(self.handle, None, None), self.ctx.handle)
+        self._trace = self._n_trace = None
+
+    def traces(self, count):
+        self.ctx.torch.cuda.synchronize()
+        return unpack_traces(self._trace.cpu().numpy(), self._n_trace.cpu().numpy(), count)
 
     def host_traffic(self):
         """Bytes moved by the last track_sequence_host call: dict(h2d, d2h, chunks)."""
