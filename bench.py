@@ -8,11 +8,17 @@ Contract (driver):  python bench.py --gpus N --steps K --warmup W [--impl refere
   * value   = frames/s with the sequence already resident in HBM (CUDA events on the launching stream).
   * e2e     = the same pass through the host-buffer C-ABI entry (vsb_track_sequence_host): pinned host
               frames/descriptors/key points/priors in, poses out, H2D and D2H inside the timed region.
-  * N > 1   = N independent replicas (one process per GPU, different sequence seed per rank), no
-              data-path collective ("replicas only"); torch.distributed is used only for
-              the barrier and the max-over-ranks of the timed region.
-  * --impl reference = the CPU oracle (restatement of the reference's algorithm; the reference itself
-              needs OpenCV 3.2 + ROS and cannot be built here) on all host threads, bounded sample.
+  * configs = the other four BASELINE configs, each with its own device-resident figure, end-to-end figure, per-kernel
+              times, roofline entry and the CPU port beside it: configs[0] single-pair latency, configs[2] TUM float
+              descriptors (tensor-core L2 kNN), configs[3] KITTI 5000 features / 5 levels (these three at N = 1 only),
+              configs[4] 8192 independent pairs x 5000 features SHARDED over the N ranks in contiguous blocks
+              (replicas.shard_range; strong scaling, aggregate pairs/s).
+  * N > 1   = N independent replicas of configs[1] (one process per GPU, different sequence seed per rank), no
+              data-path collective ("replicas only"); torch.distributed is used only for the barrier, the
+              max-over-ranks of the timed regions and the per-rank statistics.
+  * --impl reference = the reference's CPU algorithm on all host threads over the same 2000-frame workload: the oracle
+              port (oracle/libvso.so), plus a bounded sample of the reference's own translation units compiled against
+              the OpenCV stand-in (oracle/_ref/libref_visystem.so).  Loads nothing of the product.
 One JSON line on stdout (rank 0).
 """
 import argparse
@@ -30,36 +36,26 @@ for _p in (ROOT, os.path.join(ROOT, "vi-slam_b200")):
 
 import numpy as np  # noqa: E402
 
-W, H, N_FEAT, N_FRAMES, N_CELLS = 752, 480, 1000, 2000, 49
+from vislam_b200 import workloads as wl  # noqa: E402  (input generation only; loads no native code)
+
 METRIC = "frames/s tracked @752x480 (kNN match + GN pose solve)"
-WORKLOAD = ("configs[1]: synthetic EuRoC MH-like sequence 752x480, 2000 frames, 1000 ORB features/frame, "
-            "200 Hz IMU prior, num_cells=49, GN levels 3->0")
+DTYPE = "u8/int32 Hamming + f32 GN (f64 accumulate)"
+N_FRAMES = wl.CFG1["frames"]
+
+
+def base_config(world):
+    """The `config` object — identical in both arms (the driver compares them)."""
+    return {"workload": "configs[1]: " + wl.CFG1["what"], "frames": N_FRAMES, "pairs_per_step": N_FRAMES - 1,
+            "features_per_frame": wl.CFG1["n_feat"], "num_cells": wl.CFG1["n_cells"],
+            "l2_policy": "inputs larger than L2 (722 MB of frames per step), no flush needed",
+            "parallelism": f"replicas x{world}" if world > 1 else "single GPU"}
 
 
 def log(*a):
     print(*a, file=sys.stderr, flush=True)
 
 
-# ----------------------------------------------------------------------------------------------- data
-def make_data(n_frames, seed, device):
-    from vislam_b200 import synth
-    import vislam_b200 as vb
-    import ctypes as C
-    t0 = time.time()
-    seq = synth.make_sequence(n_frames, w=W, h=H, n_feat=N_FEAT, seed=seed, device=device)
-    prior = np.zeros((n_frames - 1, 7), np.float32)
-    eye = (C.c_float * 9)(1, 0, 0, 0, 1, 0, 0, 0, 1)
-    out = (C.c_float * 7)()
-    for k in range(n_frames - 1):   # initial pose exactly as VISystem.cpp:1135-1168 forms it (host helper of the C ABI)
-        r = (C.c_float * 9)(*[float(x) for x in seq["R_imu_res"][k].reshape(-1)])
-        t = (C.c_float * 3)(*[float(x) for x in seq["t_res"][k]])
-        vb.lib().vsb_initial_pose(eye, r, t, out)
-        prior[k] = out[:]
-    seq["prior"] = prior
-    log(f"[bench] synthetic sequence: {n_frames} frames in {time.time() - t0:.1f}s")
-    return seq
-
-
+# ----------------------------------------------------------------------------------------------- clocks
 class NvmlSampler:
     """SM clock / throttle reasons sampled every few ms DURING the timed region through NVML (the same counters
     `nvidia-smi --query-gpu=clocks.sm,clocks_event_reasons.*` prints; nvidia-smi's own loop is too slow to see a
@@ -162,19 +158,18 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
-# ----------------------------------------------------------------------------------------------- CPU oracle timing
-def cpu_track_sample(seq, pair_ids, threads):
-    """Times the CPU oracle (oracle/libvso.so — test infrastructure, used here only as the measured CPU
-    baseline) on a bounded sample of frame pairs, `threads` pairs in flight."""
+# ----------------------------------------------------------------------------------------------- CPU legs (oracle = checker)
+def cpu_track(seq, cfg, pair_ids, threads, first_lvl=None):
+    """The CPU oracle (oracle/libvso.so — test infrastructure, used here only as the measured CPU baseline and as the parity
+    checker) on the given frame pairs of a sequence, `threads` pairs in flight.  Returns (pairs/s, seconds, poses)."""
     from concurrent.futures import ThreadPoolExecutor
     from oracle import vso
     vso.lib()
-    K = seq["K"]
+    opts = vso.default_opts(first_lvl=cfg["first_lvl"] if first_lvl is None else first_lvl)
 
     def one(k):
-        r = vso.track_pair(seq["frames"][k], seq["frames"][k + 1], seq["desc"][k], seq["desc"][k + 1],
-                           seq["kp"][k], K, seq["prior"][k], n_cells=N_CELLS)
-        return r["pose"]
+        return vso.track_pair(seq["frames"][k], seq["frames"][k + 1], seq["desc"][k], seq["desc"][k + 1], seq["kp"][k],
+                              cfg["K"], seq["prior"][k], n_cells=cfg["n_cells"], norm=cfg.get("norm", 1), opts=opts)["pose"]
 
     t0 = time.perf_counter()
     if threads <= 1:
@@ -183,7 +178,58 @@ def cpu_track_sample(seq, pair_ids, threads):
         with ThreadPoolExecutor(threads) as ex:
             poses = list(ex.map(one, pair_ids))
     dt = time.perf_counter() - t0
-    return len(pair_ids) / dt, dt, poses
+    return len(pair_ids) / dt, dt, np.stack(poses)
+
+
+def cpu_track_pairs(pairs, cfg, threads):
+    """The same for independent pairs given as a list of dicts (prev, cur, d1, d2, kp1, prior)."""
+    from concurrent.futures import ThreadPoolExecutor
+    from oracle import vso
+    vso.lib()
+    opts = vso.default_opts(first_lvl=cfg["first_lvl"])
+
+    def one(p):
+        return vso.track_pair(p["prev"], p["cur"], p["d1"], p["d2"], p["kp1"], cfg["K"], p["prior"], n_cells=cfg["n_cells"],
+                              norm=cfg.get("norm", 1), opts=opts)["pose"]
+
+    t0 = time.perf_counter()
+    if threads <= 1:
+        poses = [one(p) for p in pairs]
+    else:
+        with ThreadPoolExecutor(threads) as ex:
+            poses = list(ex.map(one, pairs))
+    dt = time.perf_counter() - t0
+    return len(pairs) / dt, dt, np.stack(poses)
+
+
+def ref_units_timing(seq, cfg, n_pairs):
+    """The reference's OWN translation units (src/VISystem.cpp, Camera.cpp, Matcher.cpp ... compiled unmodified by
+    oracle/Makefile into oracle/_ref/libref_visystem.so) on a bounded sample, one thread (the reference is single-threaded
+    and the library captures std::cout, so it is not re-entrant).  They run against the functional OpenCV stand-in
+    oracle/refshim, not against OpenCV: its BFMatcher and cv::Mat are plain loops, so this figure bounds the reference's
+    CPU time from above — the faster oracle port is what the ratios are taken against."""
+    try:
+        from oracle import ref_visystem as rv
+        if not rv.available(build=False):
+            return None
+        rv.lib()
+        K4 = np.asarray(cfg["K"], np.float32)
+        eye = np.eye(3, dtype=np.float32)
+        t0 = time.perf_counter()
+        poses = []
+        for k in range(n_pairs):
+            r = rv.track_pair(seq["frames"][k], seq["frames"][k + 1], K4, eye, seq["R_imu_res"][k], seq["t_res"][k],
+                              kp_prev=seq["kp"][k], desc_prev=seq["desc"][k], kp_cur=seq["kp"][k + 1],
+                              desc_cur=seq["desc"][k + 1], n_cells=cfg["n_cells"])
+            poses.append(r["pose"].copy())
+        dt = time.perf_counter() - t0
+        return {"value": n_pairs / dt, "unit": "frames/s", "cores": 1, "kind": "reference",
+                "sample": f"first {n_pairs} frame pairs of the same sequence ({dt:.1f}s): the reference's own src/*.cpp "
+                          "(oracle/_ref/libref_visystem.so) against the OpenCV stand-in oracle/refshim — an upper bound on "
+                          "its CPU time, see bench.py ref_units_timing",
+                "poses": np.stack(poses)}
+    except Exception as e:      # informational
+        return {"error": str(e), "kind": "reference"}
 
 
 def cv2_matcher_timing(seq, cores):
@@ -210,91 +256,462 @@ def cv2_matcher_timing(seq, cores):
 
 
 def run_reference(args, rank, world):
-    """--impl reference: the reference's CPU algorithm (oracle port) on all host threads, bounded sample."""
+    """--impl reference: the reference's CPU algorithm on all host threads over the same workload as the GPU arm.  Priors come
+    from the oracle's own initial_pose; nothing of the product is loaded."""
     if rank != 0:
         return
+    from oracle import vso
+    vso.build()
+    vso.lib()
     cores = os.cpu_count() or 1
-    n_sample = int(os.environ.get("VSB_REF_SAMPLE_PAIRS", "1024"))
-    seq = make_data(n_sample + 1, 2001, None)
-    ids = list(range(n_sample))
-    for _ in range(args.warmup):
-        cpu_track_sample(seq, ids[: max(cores, 4)], cores)
+    n_frames = int(os.environ.get("VSB_BENCH_FRAMES", str(N_FRAMES)))
+    seq = wl.sequence(wl.CFG1, vso.initial_pose, n_frames=n_frames, device=None, log=log)
+    n_pairs = n_frames - 1
+    ids = list(range(n_pairs))
+    for _ in range(args.warmup):       # warm-up: page the library and the frames in, a bounded slice per round
+        cpu_track(seq, wl.CFG1, ids[: 4 * cores], cores)
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        cpu_track_sample(seq, ids, cores)
+        cpu_track(seq, wl.CFG1, ids, cores)
     dt = (time.perf_counter() - t0) / args.steps
-    fps = n_sample / dt
-    sample = f"{n_sample} consecutive frame pairs of the same synthetic sequence per step, {cores} pairs in flight"
+    fps = n_pairs / dt
+    sample = f"all {n_pairs} frame pairs of the workload per step, oracle port, {cores} pairs in flight"
+    ru = ref_units_timing(seq, wl.CFG1, int(os.environ.get("VSB_REF_UNITS_PAIRS", "8")))
+    if ru and "poses" in ru:
+        _, _, port = cpu_track(seq, wl.CFG1, list(range(len(ru["poses"]))), 1)
+        ru["max_abs_pose_diff_vs_port"] = float(np.abs(ru.pop("poses") - port).max())
+    cfg = base_config(world)
+    if n_frames != N_FRAMES:
+        cfg["frames"], cfg["pairs_per_step"] = n_frames, n_pairs
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "u8/int32 Hamming + f32 GN (f64 accumulate)",
-        "data": "synthetic",
-        "config": {"workload": WORKLOAD, "sample": sample},
-        "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port", "sample": sample},
+        "scaling": "weak", "vs_baseline": None, "dtype": DTYPE, "data": "synthetic", "config": cfg,
+        "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port", "sample": sample,
+                         "reference_units": ru},
         "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }), flush=True)
 
 
 # ----------------------------------------------------------------------------------------------- GPU arm
-def run_gpu(args, rank, world, local_rank):
-    import torch
-    import vislam_b200 as vb
-    from vislam_b200 import replicas
-    torch.cuda.set_device(local_rank)
-    dev = torch.device("cuda", local_rank)
-    dist = None
-    if world > 1:
-        import torch.distributed as dist
-        dist.init_process_group("nccl", device_id=dev)
+class Gpu:
+    """What every leg needs: device, context, stream, barrier, measured peaks."""
 
-    def barrier():
-        if dist is not None:
-            dist.barrier()
-        torch.cuda.synchronize(dev)
+    def __init__(self, rank, world, local_rank):
+        import torch
+        import vislam_b200 as vb
+        self.torch, self.vb, self.rank, self.world, self.local_rank = torch, vb, rank, world, local_rank
+        torch.cuda.set_device(local_rank)
+        self.dev = torch.device("cuda", local_rank)
+        self.dist = None
+        if world > 1:
+            import torch.distributed as dist
+            dist.init_process_group("nccl", device_id=self.dev)
+            self.dist = dist
+        self.ctx = vb.Context(local_rank)
+        self.stream = torch.cuda.current_stream(self.dev)
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        self.hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+        self.hbm_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6.65 TB/s"
+        self.bf16_peak = float(peaks.get("bf16_tflops", 1590.0))
+        self.bf16_src = ("measured dense bf16 (MEASURED_PEAKS.json bf16_tflops, burst)" if "bf16_tflops" in peaks
+                         else "fallback 1.59 PFLOP/s dense bf16")
+        self.traffic = {}
+        try:
+            self.traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic_r2.json")))["per_step"]
+        except Exception:
+            pass
 
-    n_frames = int(os.environ.get("VSB_BENCH_FRAMES", str(N_FRAMES)))
-    chunk = int(os.environ.get("VSB_BENCH_CHUNK", str(n_frames - 1)))       # device-resident pass: one batch per kernel
-    host_chunk = int(os.environ.get("VSB_BENCH_HOST_CHUNK", "250"))          # host-buffer pass: H2D/compute pipeline depth
-    grad_mode = int(os.environ.get("VSB_GRAD_MODE", "1"))   # 1: Scharr evaluated at the candidate points (bit-identical)
-    accum_mode = int(os.environ.get("VSB_GN_ACCUM", "0"))   # 0: FP64 accumulation of exact products (bit-faithful, default); 1: FP32 partials + FP64 final
-    seq = make_data(n_frames, replicas.replica_seed(2001, rank), dev)
+    def barrier(self):
+        if self.dist is not None:
+            self.dist.barrier()
+        self.torch.cuda.synchronize(self.dev)
+
+    def max_ranks(self, v):
+        from vislam_b200 import replicas
+        return replicas.max_over_ranks(v, self.dist, self.dev)
+
+    def gather_ranks(self, v):
+        if self.dist is None:
+            return [float(v)]
+        t = self.torch.tensor([float(v)], dtype=self.torch.float64, device=self.dev)
+        out = [self.torch.zeros_like(t) for _ in range(self.world)]
+        self.dist.all_gather(out, t)
+        return [float(x.item()) for x in out]
+
+    def pin(self, a):
+        t = a if self.torch.is_tensor(a) else self.torch.from_numpy(np.ascontiguousarray(a))
+        return t.cpu().pin_memory()
+
+
+def product_initial_pose(vb):
+    import ctypes as C
+
+    def f(imu2cam, r_imu_res, t_res):      # the product's host helper (VISystem.cpp:1135-1168), bit-identical to the oracle's
+        out = (C.c_float * 7)()
+        a = (C.c_float * 9)(*[float(x) for x in np.asarray(imu2cam, np.float32).reshape(-1)])
+        r = (C.c_float * 9)(*[float(x) for x in np.asarray(r_imu_res, np.float32).reshape(-1)])
+        t = (C.c_float * 3)(*[float(x) for x in np.asarray(t_res, np.float32).reshape(-1)])
+        vb.lib().vsb_initial_pose(a, r, t, out)
+        return np.array(out[:], np.float32)
+    return f
+
+
+def timed(g, fn, reps, warmup):
+    """fn() reps times between CUDA events on the launching stream, after warm-up; returns ms per call."""
+    torch = g.torch
+    for _ in range(warmup):
+        fn()
+    torch.cuda.synchronize(g.dev)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(g.stream)
+    for _ in range(reps):
+        fn()
+    e1.record(g.stream)
+    torch.cuda.synchronize(g.dev)
+    return e0.elapsed_time(e1) / reps
+
+
+def timed_wall(g, fn, reps, warmup):
+    """fn() is synchronous (host-buffer entries): wall clock per call."""
+    for _ in range(warmup):
+        fn()
+    g.torch.cuda.synchronize(g.dev)
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        fn()
+    return (time.perf_counter() - t0) * 1e3 / reps
+
+
+def kernel_table(g, cfg, prof, steps, stats, n_pairs_per_step, n_frames_per_step, knn_impl_env):
+    """Per-kernel times of a leg with the roofline entry of the kernels SURVEY 8(d) bounds.  prof: {name: (ms total, launches)}
+    over `steps` steps; stats: solver counters over the same steps."""
+    vb = g.vb
+    N, w, h = cfg["n_feat"], cfg["w"], cfg["h"]
+    px_all = wl.sum_levels(w, h, 5)
+    px_gn = wl.sum_levels(w, h, cfg["first_lvl"] + 1)
+    pairs_total = max(1, stats["pairs"])
+    i8_peak = 2.0 * g.bf16_peak          # tcgen05 kind::i8 runs at twice the bf16 rate, kind::mxf4 at four times
+    knn_fp4 = knn_impl_env in (3, 4, 5) or (knn_impl_env == 6 and N >= 768)
+    total_ms = sum(v[0] for v in prof.values()) or 1.0
+    l2_ms = sum(prof.get(k, (0.0, 0))[0] for k in ("knn2_l2", "knn2_l2_prep", "knn2_l2_final"))
+    out = []
+    for name, (kms, n) in sorted(prof.items(), key=lambda kv: -kv[1][0]):
+        ent = {"kernel": name, "ms_per_step": kms / steps, "launches_per_step": n / steps, "share": kms / total_ms}
+        sec = kms * 1e-3
+        if name == "gn_solve":
+            visit_b = 14.0 * stats["point_visits"]           # x, y 8 B; I_prev 1; gx, gy 4; I_cur 1 per point visit
+            stage_b = 6.0 * px_gn * pairs_total              # one-time staging of cur I, prev I, prev gx, gy
+            ach = (visit_b + stage_b) / sec / 1e9
+            ent.update({"bound": "hbm", "achieved": ach, "peak": g.hbm_peak, "unit": "GB/s", "frac": ach / g.hbm_peak,
+                        "peak_source": g.hbm_src, "algorithmic_per_launch": (visit_b + stage_b) / max(1, n),
+                        "split": {"per_visit_term_gbs": visit_b / sec / 1e9, "frac_per_visit_term": visit_b / sec / 1e9 / g.hbm_peak,
+                                  "staging_term_gbs": stage_b / sec / 1e9,
+                                  "note": "SURVEY 8(d) counts 14 B per point visit PLUS 6 B per pyramid pixel of one-time staging; "
+                                          "the solver itself only moves the first term (8-byte records + the gathered byte), the "
+                                          "second is paid by the pyramid and candidate kernels"},
+                        "point_visits_per_s": stats["point_visits"] / sec,
+                        "note": "bound as SURVEY 8(d) defines it; ncu (profiles/r2_gn_track.txt) shows the kernel limited by the "
+                                "FP64 pipe it shares between DMMA (Gram matrix) and DADD/DFMA (warp, J = Jl Jw) and by instruction "
+                                "issue (57 % of issue slots), DRAM at 3 %"})
+        elif name == "knn2_hamming":
+            if knn_impl_env == 0:
+                work, unit, peak, src, bound = 8.0 * N * N * pairs_total, "GPOPC/s", g.ctx.popc_peak() / 1e9, "measured by vsb_popc_peak on this GPU", "int"
+            else:
+                work, unit, bound = 2.0 * 256 * N * N * pairs_total / 1e3, "TOP/s", "tensor"
+                peak = 2.0 * i8_peak if knn_fp4 else i8_peak
+                src = ("4-bit kernel (tcgen05 kind::mxf4): 4 x " if knn_fp4 else "int8 kernel (tcgen05 kind::i8): 2 x ") + g.bf16_src
+            ach = work / sec / 1e9
+            ent.update({"bound": bound, "achieved": ach, "peak": peak, "unit": unit, "frac": ach / peak, "peak_source": src,
+                        "algorithmic_per_launch": work / max(1, n),
+                        "note": "one distance matrix per pair counted once (SURVEY 8d); the kernel computes it once per direction"})
+            if knn_impl_env != 0:
+                pp = g.ctx.popc_peak() / 1e9
+                pe = 8.0 * N * N * pairs_total / sec / 1e9
+                ent["survey_8d_int_pipe"] = {"bound": "int", "achieved": pe, "peak": pp, "unit": "GPOPC/s", "frac": pe / pp,
+                                             "peak_source": "measured by vsb_popc_peak on this GPU"}
+        elif name == "knn2_l2":
+            # the whole float matcher (prep + tensor-core GEMM/top-3 + exact re-check) against the tf32 tensor peak
+            D = cfg["desc_bytes"] // 4
+            flop = 2.0 * N * N * D * pairs_total
+            ach = flop / (l2_ms * 1e-3) / 1e12
+            peak = g.bf16_peak / 2.0
+            ent.update({"bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
+                        "peak_source": "tf32 = half of " + g.bf16_src, "algorithmic_per_launch": flop / max(1, n),
+                        "ms_incl_prep_and_recheck": l2_ms / steps, "outputs_per_s": float(N) * N * pairs_total / (l2_ms * 1e-3),
+                        "note": "FLOP_alg = 2 N M D, one GEMM for both directions, the 3-product tf32 split counted once (SURVEY "
+                                "8d); with K = 64 the top-3 epilogue over N M outputs is the limiter — ncu (round 1, "
+                                "prof_l2tc): tensor pipe 49 %, ALU 65 %"})
+        elif name == "pyramid":
+            work = float(w * h + px_all) * n_frames_per_step * steps
+            ach = work / sec / 1e9
+            ent.update({"bound": "hbm", "achieved": ach, "peak": g.hbm_peak, "unit": "GB/s", "frac": ach / g.hbm_peak,
+                        "peak_source": g.hbm_src, "algorithmic_per_launch": work / max(1, n)})
+        tr = g.traffic.get(cfg["name"], {}).get(name)
+        if tr is not None and "bound" in ent:
+            ent["traffic"] = tr
+        out.append(ent)
+    return out
+
+
+def leg_sequence(g, cfg, seq, steps, warmup, host_chunk, want_host=True):
+    """One sequence config on this rank: device-resident pass (value), host-buffer pass (e2e), kernel table."""
+    torch, vb = g.torch, g.vb
+    n_frames = seq["frames"].shape[0]
     n_pairs = n_frames - 1
-    ctx = vb.Context(local_rank)
-    tr = ctx.tracker(W, H, N_FEAT, seq["K"], n_cells=N_CELLS, max_pairs=chunk,
-                     gn_opts=vb.default_gn_opts(grad_mode=grad_mode, accum_mode=accum_mode))
-    # host (pinned) and device copies of the inputs
-    tr_host = ctx.tracker(W, H, N_FEAT, seq["K"], n_cells=N_CELLS, max_pairs=host_chunk,
-                          gn_opts=vb.default_gn_opts(grad_mode=grad_mode, accum_mode=accum_mode))
-    # the pinned host buffers live on the GPU's own NUMA node (replicas.gpu_local_cpus): with N replicas every rank then
-    # pulls its frames over its own root complex
-    numa = replicas.gpu_local_cpus(local_rank) if os.environ.get("VSB_BENCH_NUMA_BIND", "1") != "0" else None
-    if numa is not None:
-        numa.__enter__()
-    h = {k: torch.from_numpy(np.ascontiguousarray(seq[k])).pin_memory() for k in ("frames", "desc", "kp", "prior")}
-    h_pose = torch.zeros((n_pairs, 7), dtype=torch.float32).pin_memory()
-    h_ng = torch.zeros((n_pairs,), dtype=torch.int32).pin_memory()
-    if numa is not None:
-        numa.__exit__(None, None, None)
-    d = {k: v.to(dev) for k, v in h.items()}
-    d_pose = torch.zeros((n_pairs, 7), dtype=torch.float32, device=dev)
-    d_ng = torch.zeros((n_pairs,), dtype=torch.int32, device=dev)
-    stream = torch.cuda.current_stream(dev)
+    opts = vb.default_gn_opts(grad_mode=1, first_lvl=cfg["first_lvl"])
+    tr = g.ctx.tracker(cfg["w"], cfg["h"], cfg["n_feat"], cfg["K"], n_cells=cfg["n_cells"], max_pairs=n_pairs,
+                       norm=cfg["norm"], desc_bytes=cfg["desc_bytes"], gn_opts=opts)
+    desc = np.ascontiguousarray(seq["desc"]).view(np.uint8).reshape(n_frames, cfg["n_feat"], cfg["desc_bytes"])
+    h = {"frames": g.pin(seq["frames"]), "desc": g.pin(desc), "kp": g.pin(seq["kp"]), "prior": g.pin(seq["prior"])}
+    d = {k: v.to(g.dev) for k, v in h.items()}
+    d_pose = torch.zeros((n_pairs, 7), dtype=torch.float32, device=g.dev)
+    d_ng = torch.zeros((n_pairs,), dtype=torch.int32, device=g.dev)
 
     def step_device():
-        for p0 in range(0, n_pairs, chunk):
-            p1 = min(p0 + chunk, n_pairs)
-            tr.track_sequence(d["frames"][p0:p1 + 1], d["desc"][p0:p1 + 1], d["kp"][p0:p1 + 1], d["prior"][p0:p1],
-                              pose=d_pose[p0:p1], n_good=d_ng[p0:p1], stream=stream)
+        tr.track_sequence(d["frames"], d["desc"], d["kp"], d["prior"], pose=d_pose, n_good=d_ng, stream=g.stream)
 
-    def step_host():
-        tr_host.track_sequence_host(h["frames"], h["desc"], h["kp"], h["prior"], h_pose, h_ng)
-
-    # ---- device-resident timing ("value") ------------------------------------------------------------
-    for _ in range(args.warmup):
+    for _ in range(warmup):
         step_device()
-    barrier()
+    g.barrier()
     tr.stats()
+    g.ctx.profile(True)
+    l0 = g.ctx.launches
+    ms = timed(g, step_device, steps, 0)
+    launches = g.ctx.launches - l0
+    prof = g.ctx.profile_read()
+    g.ctx.profile(False)
+    stats = tr.stats()
+    res = {"tracker": tr, "d": d, "h": h, "d_pose": d_pose, "d_ng": d_ng, "ms": ms, "launches": launches, "prof": prof,
+           "stats": stats, "n_pairs": n_pairs, "step_device": step_device}
+    if want_host:
+        tr_host = g.ctx.tracker(cfg["w"], cfg["h"], cfg["n_feat"], cfg["K"], n_cells=cfg["n_cells"],
+                                max_pairs=min(host_chunk, n_pairs), norm=cfg["norm"], desc_bytes=cfg["desc_bytes"], gn_opts=opts)
+        h_pose = torch.zeros((n_pairs, 7), dtype=torch.float32).pin_memory()
+        h_ng = torch.zeros((n_pairs,), dtype=torch.int32).pin_memory()
+        res.update({"tr_host": tr_host, "h_pose": h_pose, "h_ng": h_ng,
+                    "step_host": lambda: tr_host.track_sequence_host(h["frames"], h["desc"], h["kp"], h["prior"], h_pose, h_ng)})
+    return res
+
+
+def summarize_leg(g, cfg, leg, steps, e2e_ms, unit_name, cpu):
+    knn_impl = int(os.environ.get("VSB_KNN_IMPL", "6"))
+    n_pairs = leg["n_pairs"]
+    kernels = kernel_table(g, cfg, leg["prof"], steps, leg["stats"], n_pairs, n_pairs + 1, knn_impl)
+    dom = next((k for k in kernels if "bound" in k), None)
+    out = {"workload": cfg["name"] + ": " + cfg["what"], "value": n_pairs / (leg["ms"] * 1e-3), "unit": unit_name,
+           "ms_per_step": leg["ms"], "pairs_per_step": n_pairs, "gpu_launches_per_step": leg["launches"] / steps,
+           "gn_iterations_per_pair": leg["stats"]["iterations"] / max(1, leg["stats"]["pairs"]),
+           "gn_points_per_pair": leg["stats"]["point_visits"] / max(1, leg["stats"]["pairs"]),
+           "good_matches_per_pair": float(leg["d_ng"].float().mean()),
+           "kernels": kernels,
+           "roofline": None if dom is None else {k: dom[k] for k in ("kernel", "bound", "achieved", "peak", "unit", "frac", "peak_source")
+                                                 if k in dom},
+           "cpu_baseline": cpu}
+    if dom is not None:
+        out["roofline"]["traffic"] = dom.get("traffic")
+    if e2e_ms is not None:
+        tt = leg["tr_host"].host_traffic()
+        out["e2e"] = {"value": n_pairs / (e2e_ms * 1e-3), "unit": unit_name, "ms_per_step": e2e_ms,
+                      "h2d_bytes_per_step": int(tt["h2d"]), "d2h_bytes_per_step": int(tt["d2h"]),
+                      "h2d_gbs_achieved": tt["h2d"] / (e2e_ms * 1e-3) / 1e9,
+                      "matches_device_path": bool(g.torch.equal(leg["h_pose"].to(g.dev), leg["d_pose"]))}
+    return out
+
+
+def cpu_sample_for(seq, cfg, leg, n_sample, threads=1):
+    """CPU port on the first n_sample pairs of a sequence leg + parity of the GPU poses on them."""
+    ids = list(range(min(n_sample, leg["n_pairs"])))
+    fps, dt, poses = cpu_track(seq, cfg, ids, threads)
+    diff = float(np.abs(poses - leg["d_pose"][: len(ids)].cpu().numpy()).max())
+    return {"value": fps, "unit": "frames/s", "cores": threads, "kind": "port",
+            "sample": f"first {len(ids)} frame pairs of the same sequence, oracle port, {threads} thread(s) ({dt:.1f}s)",
+            "max_abs_pose_diff_vs_gpu": diff}
+
+
+def leg_single_pair(g, steps):
+    """configs[0]: one frame pair — latency, not throughput.  Device-resident (vsb_track_pairs) and host-buffer
+    (vsb_track_pairs_host) microseconds per pair; the oracle port on the same pair beside it."""
+    torch, vb = g.torch, g.vb
+    cfg = wl.CFG0
+    from vislam_b200 import synth
+    p = synth.make_pair(w=cfg["w"], h=cfg["h"], n_feat=cfg["n_feat"], K=cfg["K"], seed=cfg["seed"], device=g.dev)
+    tr = g.ctx.tracker(cfg["w"], cfg["h"], cfg["n_feat"], cfg["K"], n_cells=cfg["n_cells"], max_pairs=1)
+    keys = ("prev", "cur", "d1", "d2", "kp1", "pose_prior")
+    h = {k: g.pin(p[k][None]) for k in keys}
+    d = {k: v.to(g.dev) for k, v in h.items()}
+    d_pose = torch.zeros((1, 7), dtype=torch.float32, device=g.dev)
+    d_ng = torch.zeros((1,), dtype=torch.int32, device=g.dev)
+    h_pose = torch.zeros((1, 7), dtype=torch.float32).pin_memory()
+    fn = lambda: tr.track_pairs(d["prev"], d["cur"], d["d1"], d["d2"], d["kp1"], d["pose_prior"], pose=d_pose, n_good=d_ng, stream=g.stream)
+    reps = max(20, steps)
+    for _ in range(5):
+        fn()
+    torch.cuda.synchronize(g.dev)
+    tr.stats()
+    g.ctx.profile(True)
+    l0 = g.ctx.launches
+    ms = timed(g, fn, reps, 0)
+    launches = g.ctx.launches - l0
+    prof = g.ctx.profile_read()
+    g.ctx.profile(False)
+    stats = tr.stats()
+    fh = lambda: tr.track_pairs_host(h["prev"], h["cur"], h["d1"], h["d2"], h["kp1"], h["pose_prior"], h_pose)
+    e2e_ms = timed_wall(g, fh, reps, 5)
+    tt = tr.host_traffic()
+    # the oracle port on the same pair, best of 3
+    pr = dict(prev=p["prev"], cur=p["cur"], d1=p["d1"], d2=p["d2"], kp1=p["kp1"], prior=p["pose_prior"])
+    best = None
+    for _ in range(3):
+        fps, dt, poses = cpu_track_pairs([pr], cfg, 1)
+        best = dt if best is None else min(best, dt)
+    gn = prof.get("gn_solve", (0.0, 1))
+    gn_us = gn[0] / reps * 1e3
+    visit_b = 14.0 * stats["point_visits"] / max(1, stats["pairs"])
+    out = {"workload": cfg["name"] + ": " + cfg["what"], "value": ms * 1e3, "unit": "us per frame pair (device-resident)",
+           "higher_is_better": False, "gpu_launches_per_step": launches / reps,
+           "e2e": {"value": e2e_ms * 1e3, "unit": "us per frame pair (host buffers in, pose out)",
+                   "h2d_bytes_per_step": int(tt["h2d"]), "d2h_bytes_per_step": int(tt["d2h"]),
+                   "matches_device_path": bool(torch.equal(h_pose.to(g.dev), d_pose))},
+           "kernels_us": {k: v[0] / reps * 1e3 for k, v in sorted(prof.items(), key=lambda kv: -kv[1][0])},
+           "gn_iterations": stats["iterations"] / max(1, stats["pairs"]), "gn_points": stats["point_visits"] / max(1, stats["pairs"]),
+           "roofline": {"kernel": "gn_solve", "bound": "latency", "achieved": visit_b / (gn_us * 1e-6) / 1e9, "peak": g.hbm_peak,
+                        "unit": "GB/s", "frac": visit_b / (gn_us * 1e-6) / 1e9 / g.hbm_peak, "peak_source": g.hbm_src, "traffic": None,
+                        "note": "a single pair is one thread block (1024 threads) running ~20 serial Gauss-Newton iterations: "
+                                "latency-bound by construction (SURVEY 8d: report achieved bandwidth and wall time, claim a "
+                                "roofline fraction only for the batched configs)"},
+           "cpu_baseline": {"value": best * 1e6, "unit": "us per frame pair", "cores": 1, "kind": "port",
+                            "sample": "the same pair, oracle port, best of 3",
+                            "max_abs_pose_diff_vs_gpu": float(np.abs(poses[0] - d_pose[0].cpu().numpy()).max())}}
+    tr.close()
+    return out
+
+
+def leg_batched_pairs(g, steps, warmup):
+    """configs[4]: 8192 independent pairs x 5000 features, sharded over the ranks in contiguous blocks (no data-path
+    collective); every rank generates only its shard, on its GPU.  Aggregate pairs/s = all pairs / max-over-ranks time."""
+    torch, vb = g.torch, g.vb
+    from vislam_b200 import replicas
+    cfg = wl.CFG4
+    total = int(os.environ.get("VSB_BENCH_CFG4_PAIRS", str(cfg["pairs"])))
+    lo, hi = replicas.shard_range(total, g.rank, g.world)
+    n = hi - lo
+    chunk = min(n, int(os.environ.get("VSB_BENCH_CFG4_CHUNK", "1024")))
+    data = wl.pairs_on_device(cfg, lo, hi, g.dev, log=log if g.rank == 0 else None)
+    tr = g.ctx.tracker(cfg["w"], cfg["h"], cfg["n_feat"], cfg["K"], n_cells=cfg["n_cells"], max_pairs=chunk)
+    d_pose = torch.zeros((n, 7), dtype=torch.float32, device=g.dev)
+    d_ng = torch.zeros((n,), dtype=torch.int32, device=g.dev)
+
+    def step():
+        for p0 in range(0, n, chunk):
+            p1 = min(n, p0 + chunk)
+            tr.track_pairs(data["prev"][p0:p1], data["cur"][p0:p1], data["d1"][p0:p1], data["d2"][p0:p1], data["kp1"][p0:p1],
+                           data["prior"][p0:p1], pose=d_pose[p0:p1], n_good=d_ng[p0:p1], stream=g.stream)
+
+    reps = max(2, min(steps, 3))
+    for _ in range(max(1, min(warmup, 2))):
+        step()
+    g.barrier()
+    tr.stats()
+    g.ctx.profile(True)
+    l0 = g.ctx.launches
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    g.barrier()
+    e0.record(g.stream)
+    for _ in range(reps):
+        step()
+    e1.record(g.stream)
+    g.barrier()
+    ms = e0.elapsed_time(e1) / reps
+    launches = g.ctx.launches - l0
+    prof = g.ctx.profile_read()
+    g.ctx.profile(False)
+    stats = tr.stats()
+    ms_ranks = g.gather_ranks(ms)
+    ms_max = max(ms_ranks)
+    # end to end: the shard from pinned host buffers through vsb_track_pairs_host (a bounded part of the shard: pinning
+    # gigabytes takes longer than the pass itself)
+    n_host = max(1, min(n, int(os.environ.get("VSB_BENCH_CFG4_HOST_PAIRS", "2048")) // g.world))
+    hchunk = min(n_host, 256)
+    tr_host = g.ctx.tracker(cfg["w"], cfg["h"], cfg["n_feat"], cfg["K"], n_cells=cfg["n_cells"], max_pairs=hchunk)
+    h = {k: g.pin(data[k][:n_host]) for k in ("prev", "cur", "d1", "d2", "kp1", "prior")}
+    h_pose = torch.zeros((n_host, 7), dtype=torch.float32).pin_memory()
+    fh = lambda: tr_host.track_pairs_host(h["prev"], h["cur"], h["d1"], h["d2"], h["kp1"], h["prior"], h_pose)
+    fh()
+    g.barrier()
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        fh()
+    g.barrier()
+    e2e_ms = (time.perf_counter() - t0) * 1e3 / reps
+    e2e_ranks = g.gather_ranks(e2e_ms)
+    tt = tr_host.host_traffic()
+    same = bool(torch.equal(h_pose.to(g.dev), d_pose[:n_host]))
+    out = None
+    if g.rank == 0:
+        leg = {"prof": prof, "stats": stats, "n_pairs": n, "ms": ms}
+        knn_impl = int(os.environ.get("VSB_KNN_IMPL", "6"))
+        kernels = kernel_table(g, cfg, prof, reps, stats, n, 2 * n, knn_impl)
+        dom = next((k for k in kernels if "bound" in k), None)
+        # CPU port on a bounded sample of this rank's shard, all host threads, + parity
+        cores = os.cpu_count() or 1
+        ns = min(n, int(os.environ.get("VSB_BENCH_CFG4_CPU_PAIRS", "16")))
+        cp = {k: data[k][:ns].cpu().numpy() for k in ("prev", "cur", "d1", "d2", "kp1", "prior")}
+        plist = [dict(prev=cp["prev"][i], cur=cp["cur"][i], d1=cp["d1"][i], d2=cp["d2"][i], kp1=cp["kp1"][i], prior=cp["prior"][i])
+                 for i in range(ns)]
+        fps, dt, poses = cpu_track_pairs(plist, cfg, min(cores, ns))
+        out = {"workload": cfg["name"] + ": " + cfg["what"], "value": total / (ms_max * 1e-3), "unit": "frame pairs/s (aggregate)",
+               "scaling": "strong", "pairs_total": total, "pairs_per_rank": n, "chunk_pairs": chunk, "ms_per_step": ms_max,
+               "per_rank_ms_per_step": ms_ranks, "us_per_pair_per_gpu": ms * 1e3 / n,
+               "gpu_launches_per_step": launches / reps,
+               "gn_iterations_per_pair": stats["iterations"] / max(1, stats["pairs"]),
+               "gn_points_per_pair": stats["point_visits"] / max(1, stats["pairs"]),
+               "good_matches_per_pair": float(d_ng.float().mean()),
+               "l2_policy": "every pair distinct: %.1f GB of frames and descriptors per rank per step, far beyond L2" %
+                            (n * (2.0 * cfg["w"] * cfg["h"] + 2.0 * cfg["n_feat"] * 32) / 1e9),
+               "e2e": {"value": g.world * n_host / (max(e2e_ranks) * 1e-3), "unit": "frame pairs/s (aggregate)",
+                       "pairs_per_rank": n_host, "ms_per_step": max(e2e_ranks), "per_rank_ms_per_step": e2e_ranks,
+                       "h2d_bytes_per_step": int(tt["h2d"]), "d2h_bytes_per_step": int(tt["d2h"]),
+                       "h2d_gbs_achieved_per_gpu": tt["h2d"] / (e2e_ms * 1e-3) / 1e9, "matches_device_path": same,
+                       "what": "vsb_track_pairs_host on the first pairs of every rank's shard (pinned host buffers, chunks of "
+                               "%d pairs on two streams)" % hchunk},
+               "kernels": kernels,
+               "roofline": None if dom is None else {k: dom.get(k) for k in ("kernel", "bound", "achieved", "peak", "unit", "frac", "peak_source", "traffic")},
+               "cpu_baseline": {"value": fps, "unit": "frame pairs/s", "cores": min(cores, ns), "kind": "port",
+                                "sample": f"first {ns} pairs of rank 0's shard, oracle port, {min(cores, ns)} pairs in flight ({dt:.1f}s)",
+                                "max_abs_pose_diff_vs_gpu": float(np.abs(poses - d_pose[:ns].cpu().numpy()).max())}}
+    tr.close()
+    tr_host.close()
+    del data
+    torch.cuda.empty_cache()
+    return out
+
+
+def run_gpu(args, rank, world, local_rank):
+    g = Gpu(rank, world, local_rank)
+    torch, vb, ctx, dev = g.torch, g.vb, g.ctx, g.dev
+    from vislam_b200 import replicas
+    cfg = wl.CFG1
+    n_frames = int(os.environ.get("VSB_BENCH_FRAMES", str(N_FRAMES)))
+    host_chunk = int(os.environ.get("VSB_BENCH_HOST_CHUNK", "250"))          # host-buffer pass: H2D/compute pipeline depth
+    same_seed = os.environ.get("VSB_BENCH_SAME_SEED", "0") == "1"            # control: every replica tracks the same sequence
+    seed = cfg["seed"] if same_seed else replicas.replica_seed(cfg["seed"], rank)
+    # the pinned host buffers live on the GPU's own NUMA node (replicas.gpu_local_cpus)
+    numa = replicas.gpu_local_cpus(local_rank) if os.environ.get("VSB_BENCH_NUMA_BIND", "1") != "0" else None
+    seq = wl.sequence(cfg, product_initial_pose(vb), n_frames=n_frames, seed=seed, device=dev, log=log if rank == 0 else None)
+    if numa is not None:
+        numa.__enter__()
+    leg = leg_sequence(g, cfg, seq, args.steps, args.warmup, host_chunk)
+    if numa is not None:
+        numa.__exit__(None, None, None)
+    n_pairs = leg["n_pairs"]
+    # ---- device-resident timing ("value"): W warm-up steps were done, now exactly K steps between barriers ----------
+    g.barrier()
+    leg["tracker"].stats()
     ctx.profile(True)
     launches0 = ctx.launches
     sampler = NvmlSampler(local_rank)
@@ -302,63 +719,66 @@ def run_gpu(args, rank, world, local_rank):
         sampler = ClockSampler(local_rank)
         sampler.start()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    ev0.record(stream)
+    g.barrier()
+    ev0.record(g.stream)
     for _ in range(args.steps):
-        step_device()
-    ev1.record(stream)
-    barrier()
-    ms = ev0.elapsed_time(ev1)
+        leg["step_device"]()
+    ev1.record(g.stream)
+    g.barrier()
+    ms = ev0.elapsed_time(ev1) / args.steps
     clocks = sampler.stop()
     launches = ctx.launches - launches0
-    prof = ctx.profile_read()
+    leg["prof"] = ctx.profile_read()
     ctx.profile(False)
-    stats = tr.stats()
-    ms_max = replicas.max_over_ranks(ms, dist, dev)
-    ms_per_step = ms_max / args.steps
+    leg["stats"] = leg["tracker"].stats()
+    leg["ms"] = ms
+    ms_ranks = g.gather_ranks(ms)
+    ms_per_step = max(ms_ranks)
     value = replicas.aggregate_throughput(n_pairs, ms_per_step, world)
+    clk_ranks = g.gather_ranks(clocks.get("sm_mhz") or 0.0)
 
     # ---- end-to-end timing through the host-buffer entry ("e2e") -------------------------------------
     for _ in range(max(1, min(args.warmup, 2))):
-        step_host()
-    barrier()
+        leg["step_host"]()
+    g.barrier()
     t0 = time.perf_counter()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record(stream)
     for _ in range(args.steps):
-        step_host()      # synchronous: returns when the poses are in host memory
-    e1.record(stream)
-    barrier()
-    e2e_ms = (time.perf_counter() - t0) * 1e3
-    e2e_ms_step = replicas.max_over_ranks(e2e_ms, dist, dev) / args.steps
+        leg["step_host"]()      # synchronous: returns when the poses are in host memory
+    g.barrier()
+    e2e_ms = (time.perf_counter() - t0) * 1e3 / args.steps
+    e2e_ranks = g.gather_ranks(e2e_ms)
+    e2e_ms_step = max(e2e_ranks)
     e2e_value = replicas.aggregate_throughput(n_pairs, e2e_ms_step, world)
-    # what the link gives a plain pinned -> device copy of the same frame buffer (the e2e pass is bound by it)
-    barrier()
+    # what the link gives a plain pinned -> device copy of the same frame buffer, all ranks copying at once (the e2e pass
+    # is bound by it; tools/h2d_floor.py measures the same floor without any of this program)
+    g.barrier()
     c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    d["frames"].copy_(h["frames"], non_blocking=True)
-    c0.record(stream)
+    leg["d"]["frames"].copy_(leg["h"]["frames"], non_blocking=True)
+    c0.record(g.stream)
     for _ in range(3):
-        d["frames"].copy_(h["frames"], non_blocking=True)
-    c1.record(stream)
+        leg["d"]["frames"].copy_(leg["h"]["frames"], non_blocking=True)
+    c1.record(g.stream)
     torch.cuda.synchronize(dev)
-    h2d_copy_gbs = 3 * h["frames"].numel() / (c0.elapsed_time(c1) * 1e-3) / 1e9
-    traffic_host = tr_host.host_traffic()      # counted by the library from the copies it issued
+    h2d_copy_gbs = 3 * leg["h"]["frames"].numel() / (c0.elapsed_time(c1) * 1e-3) / 1e9
+    copy_ranks = g.gather_ranks(h2d_copy_gbs)
+    traffic_host = leg["tr_host"].host_traffic()
     h2d, d2h, n_host_chunks = int(traffic_host["h2d"]), int(traffic_host["d2h"]), int(traffic_host["chunks"])
-    n_chunks = (n_pairs + chunk - 1) // chunk
-    same = bool(torch.equal(h_pose.to(dev), d_pose))
+    same = bool(torch.equal(leg["h_pose"].to(dev), leg["d_pose"]))
 
     # ---- the same sequence from images alone (informational): device ORB feeds the matcher, SURVEY 8f N-4 ---------
     raw = None
+    d = leg["d"]
     if rank == 0 and os.environ.get("VSB_BENCH_RAW_FRAMES", "1") != "0":
         try:
-            tr.track_sequence_orb(d["frames"], d["prior"], nfeatures=N_FEAT, stream=stream)      # warm-up (allocations)
+            tr = leg["tracker"]
+            tr.track_sequence_orb(d["frames"], d["prior"], nfeatures=cfg["n_feat"], stream=g.stream)      # warm-up (allocations)
             torch.cuda.synchronize(dev)
             ctx.profile(True)
             r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            r0.record(stream)
+            r0.record(g.stream)
             for _ in range(2):
-                _, _, r_nf = tr.track_sequence_orb(d["frames"], d["prior"], nfeatures=N_FEAT, stream=stream)
-            r1.record(stream)
+                _, _, r_nf = tr.track_sequence_orb(d["frames"], d["prior"], nfeatures=cfg["n_feat"], stream=g.stream)
+            r1.record(g.stream)
             torch.cuda.synchronize(dev)
             r_ms = r0.elapsed_time(r1) / 2
             r_prof = {k: round(v[0] / 2, 3) for k, v in ctx.profile_read().items()}
@@ -367,11 +787,13 @@ def run_gpu(args, rank, world, local_rank):
                    "orb_keypoints_per_frame": float(r_nf.float().mean()),
                    "what": "vsb_track_sequence_orb: cv::ORB::create(%d) (8 levels, factor 1.2) on the device for every frame, then the "
                            "same match + GN path; frames resident in HBM; the rendered frames carry far fewer corners than the "
-                           "%d random descriptors of configs[1]" % (N_FEAT, N_FEAT),
+                           "%d random descriptors of configs[1]" % (cfg["n_feat"], cfg["n_feat"]),
                    "kernels_ms": r_prof}
+            leg["step_device"]()          # restore d_pose for the parity check below
+            torch.cuda.synchronize(dev)
         except Exception as e:      # informational leg: never fails the bench
             raw = {"error": str(e)}
-    # ---- the matcher alone, default int8 kernel against the opt-in 4-bit persistent kernel (informational) ----------
+    # ---- the matcher alone, int8 kernel against the 4-bit persistent kernel (informational) ----------
     knn_variants = None
     if rank == 0 and os.environ.get("VSB_BENCH_KNN_VARIANTS", "1") != "0":
         try:
@@ -379,113 +801,86 @@ def run_gpu(args, rank, world, local_rank):
             q, t_ = d["desc"][:-1].contiguous(), d["desc"][1:].contiguous()
             for name, impl in (("int8_packed", 2), ("mxf4_persistent", 5)):
                 ctx.option("knn_impl", impl)
-                for _ in range(2):
-                    ctx.knn2_hamming(q, t_)
-                k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                k0.record(stream)
-                for _ in range(5):
-                    ctx.knn2_hamming(q, t_)
-                k1.record(stream)
-                torch.cuda.synchronize(dev)
-                knn_variants[name] = k0.elapsed_time(k1) / 5
-            knn_variants["unit"] = "ms per %d pairs of %d x %d descriptors, vsb_knn2_hamming incl. unpacking" % (n_pairs, N_FEAT, N_FEAT)
+                knn_variants[name] = timed(g, lambda: ctx.knn2_hamming(q, t_), 5, 2)
+            knn_variants["unit"] = "ms per %d pairs of %d x %d descriptors, vsb_knn2_hamming incl. unpacking" % (n_pairs, cfg["n_feat"], cfg["n_feat"])
         except Exception as e:
             knn_variants = {"error": str(e)}
         finally:
             ctx.option("knn_impl", int(os.environ.get("VSB_KNN_IMPL", "6")))
+
+    # ---- the other BASELINE configs ----------------------------------------------------------------------------
+    configs = {}
+    want = os.environ.get("VSB_BENCH_CONFIGS", "0,2,3,4").split(",")
+    if world == 1 and rank == 0:
+        if "0" in want:
+            try:
+                configs["configs[0]"] = leg_single_pair(g, args.steps)
+            except Exception as e:
+                configs["configs[0]"] = {"error": repr(e)}
+        for key, c, nsample in (("2", wl.CFG2, 32), ("3", wl.CFG3, 6)):
+            if key not in want:
+                continue
+            try:
+                sq = wl.sequence(c, product_initial_pose(vb), device=dev, log=log)
+                lg = leg_sequence(g, c, sq, 3, 2, 128)
+                e2e = timed_wall(g, lg["step_host"], 3, 1)
+                cpu = cpu_sample_for(sq, c, lg, nsample, 1)
+                configs["configs[%s]" % key] = summarize_leg(g, c, lg, 3, e2e, "frames/s", cpu)
+                lg["tracker"].close(); lg["tr_host"].close()
+                del lg, sq
+                torch.cuda.empty_cache()
+            except Exception as e:
+                configs["configs[%s]" % key] = {"error": repr(e)}
+    if "4" in want:
+        try:
+            c4 = leg_batched_pairs(g, args.steps, args.warmup)
+        except Exception as e:
+            c4 = {"error": repr(e)}
+        if rank == 0:
+            configs["configs[4]"] = c4
     if rank != 0:
+        leg["tracker"].close(); leg["tr_host"].close(); ctx.close()
         return
+
     # ---- roofline of every kernel, the dominant one reported in "roofline" ---------------------------
-    peaks = {}
-    try:
-        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-    except Exception:
-        pass
-    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
-    hbm_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6.65 TB/s"
-    popc_peak = ctx.popc_peak() / 1e9     # GPOPC/s, microbenchmarked on this GPU
     knn_impl = int(os.environ.get("VSB_KNN_IMPL", "6"))
-    knn_fp4 = knn_impl in (3, 4, 5) or (knn_impl == 6 and N_FEAT >= 768)      # which tensor-core kernel the matcher ran
-    # tcgen05 kind::i8 runs at twice the bf16 rate; MEASURED_PEAKS.json holds the measured dense bf16 figure
-    i8_peak = 2.0 * float(peaks.get("bf16_tflops", 2250.0))
-    i8_src = ("2 x measured dense bf16 (MEASURED_PEAKS.json bf16_tflops); nominal int8 dense is 4500 TOP/s"
-              if "bf16_tflops" in peaks else "fallback: nominal 4500 TOP/s dense int8")
-    lay = vb.pyr_layout(W, H)
-    px_all = sum(lay.w[l] * lay.h[l] for l in range(lay.levels))
-    px_gn = sum(lay.w[l] * lay.h[l] for l in range(4))
-    steps = args.steps
-    pairs_total = stats["pairs"]
-    alg = {
-        # 8*N*M 32-bit POPC per frame pair, one distance matrix for both directions
-        # tensor-core form (knn_impl 1/2): one +-1 byte per descriptor bit, 2 * N * M * 256 int8 ops per distance matrix
-        "knn2_hamming": (("int", 8.0 * N_FEAT * N_FEAT * pairs_total, "GPOPC/s", popc_peak,
-                          "measured by vsb_popc_peak on this GPU") if knn_impl == 0 else
-                         ("tensor", 2.0 * 256 * N_FEAT * N_FEAT * pairs_total / 1e3, "TOP/s", 2.0 * i8_peak if knn_fp4 else i8_peak,
-                          ("4-bit kernel (kind::mxf4): 4 x measured dense bf16; " if knn_fp4 else "") + i8_src)),
-        # 14 B per candidate point per iteration + one-time staging of cur I, prev I, gx, gy (6 B/px, levels 0-3)
-        "gn_solve": ("hbm", 14.0 * stats["point_visits"] + 6.0 * px_gn * pairs_total, "GB/s", hbm_peak, hbm_src),
-        # read w*h, write every level (level 0 is copied, as the reference's Camera::Update does)
-        "pyramid": ("hbm", (W * H + px_all) * (pairs_total + steps * n_chunks), "GB/s", hbm_peak, hbm_src),
-        # read every level once, write gx and gy (int16) for the previous frame of every pair
-        "gradient": ("hbm", 5.0 * px_all * pairs_total, "GB/s", hbm_peak, hbm_src),
-    }
-    # DRAM traffic per launch of the dominant kernels, from the committed ncu --set full capture of this same workload
-    traffic = {}
-    try:
-        tj = json.load(open(os.path.join(ROOT, "profiles", "traffic_r1.json")))
-        if n_frames == N_FRAMES and chunk == n_frames - 1:      # the capture is of the full workload in one batch
-            traffic = {k: v["dram_bytes_read"] + v["dram_bytes_write"] for k, v in tj["per_launch"].items()}
-    except Exception:
-        pass
-    total_prof_ms = sum(v[0] for v in prof.values()) or 1.0
-    kernels = []
-    for name, (kms, n) in sorted(prof.items(), key=lambda kv: -kv[1][0]):
-        ent = {"kernel": name, "ms_per_step": kms / steps, "launches_per_step": n / steps,
-               "share": kms / total_prof_ms}
-        if name in alg:
-            bound, work, unit, peak, src = alg[name]
-            ach = work / (kms * 1e-3) / 1e9
-            ent.update({"bound": bound, "achieved": ach, "peak": peak, "unit": unit, "frac": ach / peak,
-                        "peak_source": src, "traffic": traffic.get(name),
-                        "algorithmic_per_launch": work / max(1, n)})
-            if name == "knn2_hamming" and knn_impl != 0:
-                # SURVEY 8(d) bounds the Hamming kNN by the INT pipe: 8*N*M 32-bit POPC per frame pair (one distance
-                # matrix).  The tcgen05 kernel does no POPC at all; this is the same work expressed against that ceiling.
-                popc_equiv = 8.0 * N_FEAT * N_FEAT * pairs_total / (kms * 1e-3) / 1e9
-                ent["survey_8d_int_pipe"] = {"bound": "int", "achieved": popc_equiv, "peak": popc_peak, "unit": "GPOPC/s",
-                                             "frac": popc_equiv / popc_peak,
-                                             "peak_source": "measured by vsb_popc_peak on this GPU"}
-            if name == "gn_solve":
-                ent["note"] = ("bound as SURVEY 8(d) defines it (algorithmic bytes over HBM peak); ncu shows the kernel "
-                               "limited by the XU pipe (FP32<->FP64 conversions, 57 %) and instruction issue (59 %), "
-                               "DRAM at 14 %: profiles/r1_full_topkernels_v5.txt")
-        kernels.append(ent)
+    kernels = kernel_table(g, cfg, leg["prof"], args.steps, leg["stats"], n_pairs, n_frames, knn_impl)
     dom = next((k for k in kernels if "bound" in k), None)
     roofline = None
     if dom:
-        roofline = {"kernel": dom["kernel"], "bound": dom["bound"], "achieved": dom["achieved"], "peak": dom["peak"],
-                    "unit": dom["unit"], "frac": dom["frac"], "traffic": dom["traffic"],
-                    "peak_source": dom["peak_source"], "share_of_step": dom["share"]}
+        roofline = {k: dom.get(k) for k in ("kernel", "bound", "achieved", "peak", "unit", "frac", "traffic", "peak_source", "split")}
+        roofline["share_of_step"] = dom["share"]
 
-    # ---- CPU baseline: the oracle on this box's host cores, bounded sample --------------------------
+    # ---- CPU baseline and parity: the oracle port on this box's host cores ---------------------------------------------
+    # (1) every pair of the workload on all host threads: the parity check of ALL GPU poses; (2) a bounded single-thread
+    # sample: the reference is single-threaded, this is the figure `cpu_baseline.value` reports; (3) the reference's own
+    # translation units on a few pairs.
     cores = os.cpu_count() or 1
-    n_sample = int(os.environ.get("VSB_CPU_SAMPLE_PAIRS", "512"))
-    ids = list(range(min(n_sample, n_pairs)))
-    cpu_fps1, cpu_dt1, cpu_poses = cpu_track_sample(seq, ids, 1)
-    dpose = np.stack(cpu_poses) - d_pose[: len(ids)].cpu().numpy()
-    parity = float(np.abs(dpose).max())
+    fps_all, dt_all, poses_all = cpu_track(seq, cfg, list(range(n_pairs)), cores)
+    gpu_poses = leg["d_pose"].cpu().numpy()
+    parity = float(np.abs(poses_all - gpu_poses).max())
+    n_bad = int((np.abs(poses_all - gpu_poses).max(axis=1) > 0).sum())
+    n_sample = min(n_pairs, int(os.environ.get("VSB_CPU_SAMPLE_PAIRS", "256")))
+    fps1, dt1, _ = cpu_track(seq, cfg, list(range(n_sample)), 1)
+    ru = ref_units_timing(seq, cfg, int(os.environ.get("VSB_REF_UNITS_PAIRS", "8")))
+    if ru and "poses" in ru:
+        rp = ru.pop("poses")
+        ru["max_abs_pose_diff_vs_gpu"] = float(np.abs(rp - gpu_poses[: len(rp)]).max())
     out = {
         "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "u8/int32 Hamming + f32 GN (f64 accumulate)", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "frames": n_frames, "pairs_per_step": n_pairs, "chunk_pairs": chunk, "host_chunk_pairs": host_chunk, "host_chunks": n_host_chunks,
-                   "grad_mode": grad_mode, "gn_accum_mode": accum_mode, "parallelism": f"replicas x{world}" if world > 1 else "single GPU",
-                   "l2_policy": "inputs larger than L2 (722 MB of frames per step), no flush needed",
-                   "gn_iterations_per_pair": stats["iterations"] / max(1, pairs_total),
-                   "gn_points_per_pair": stats["point_visits"] / max(1, pairs_total)},
+        "vs_baseline": None, "dtype": DTYPE, "data": "synthetic", "config": base_config(world),
+        "details": {"frames": n_frames, "pairs_per_step": n_pairs, "host_chunk_pairs": host_chunk, "host_chunks": n_host_chunks,
+                    "grad_mode": 1, "same_seed_on_all_ranks": same_seed,
+                    "gn_iterations_per_pair": leg["stats"]["iterations"] / max(1, leg["stats"]["pairs"]),
+                    "gn_points_per_pair": leg["stats"]["point_visits"] / max(1, leg["stats"]["pairs"]),
+                    "per_rank": {"ms_per_step": ms_ranks, "ms_min": min(ms_ranks), "ms_mean": float(np.mean(ms_ranks)),
+                                 "ms_max": max(ms_ranks), "sm_mhz": clk_ranks, "e2e_ms_per_step": e2e_ranks,
+                                 "h2d_gbs_plain_copy": copy_ranks}},
         "e2e": {"value": e2e_value, "unit": "frames/s", "ms_per_step": e2e_ms_step, "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": d2h, "matches_device_path": same,
-                "h2d_gbs_achieved": h2d / (e2e_ms_step * 1e-3) / 1e9, "h2d_gbs_plain_copy": h2d_copy_gbs,
+                "h2d_gbs_achieved": h2d / (e2e_ms_step * 1e-3) / 1e9, "h2d_gbs_plain_copy": min(copy_ranks),
+                "fraction_of_plain_copy": (h2d / (e2e_ms_step * 1e-3) / 1e9) / min(copy_ranks),
                 "host_buffers_numa_bound": bool(numa is not None and numa.bound)},
         "from_raw_frames": raw,
         "knn_variants_ms": knn_variants,
@@ -493,15 +888,19 @@ def run_gpu(args, rank, world, local_rank):
         "clocks": clocks,
         "roofline": roofline,
         "kernels": kernels,
-        "cpu_baseline": {"value": cpu_fps1, "unit": "frames/s", "cores": 1, "kind": "port",
-                         "sample": f"first {len(ids)} frame pairs of the same sequence, oracle single thread "
-                                   f"({cpu_dt1:.1f}s); box has {cores} host cores",
-                         "max_abs_pose_diff_vs_gpu": parity,
+        "cpu_baseline": {"value": fps1, "unit": "frames/s", "cores": 1, "kind": "port",
+                         "sample": f"first {n_sample} frame pairs of the same sequence, oracle port, single thread ({dt1:.1f}s); "
+                                   f"box has {cores} host cores",
+                         "all_threads": {"value": fps_all, "unit": "frames/s", "cores": cores,
+                                         "sample": f"all {n_pairs} frame pairs, {cores} pairs in flight ({dt_all:.1f}s)"},
+                         "max_abs_pose_diff_vs_gpu": parity, "pairs_checked": n_pairs, "pairs_with_any_different_bit": n_bad,
+                         "reference_units": ru,
                          "cv2_bfmatcher": cv2_matcher_timing(seq, cores)},
+        "configs": configs,
     }
     print(json.dumps(out), flush=True)
-    tr.close()
-    tr_host.close()
+    leg["tracker"].close()
+    leg["tr_host"].close()
     ctx.close()
 
 

@@ -197,8 +197,8 @@ typedef struct {
     int sample_mode;     /* 0 nearest round() (reference, :1321)   1 bilinear (north-star extension) */
     float huber_k;
     int grad_mode;       /* 0 read gx/gy images   1 Scharr evaluated on the fly from the previous image */
-    int accum_mode;      /* 0 FP64 accumulation of exact FP32 products (parity default)
-                            1 FP32 per-thread partials, FP64 across threads (north-star wording) */
+    int accum_mode;      /* must be 0: exact FP32 products accumulated in FP64, as cv::gemm does (round 1's mode 1, FP32
+                            per-thread partials, missed the 1e-5 tolerance and was removed; VSB_ERR_UNSUPPORTED) */
 } vsb_gn_opts_t;
 void vsb_gn_default_opts(vsb_gn_opts_t* o);
 
@@ -336,6 +336,13 @@ int vsb_track_sequence_host(vsb_tracker_t* t, const uint8_t* h_frames, const uin
 int vsb_track_pairs(vsb_tracker_t* t, const uint8_t* prev, const uint8_t* cur, const uint8_t* d1,
                     const uint8_t* d2, const float* kp1_xy, const int32_t* n1, const int32_t* n2,
                     const float* pose_prior, int count, float* pose, int32_t* n_good, void* stream);
+
+/* The same with HOST buffers (end-to-end form of BASELINE config 5): chunks of cfg.max_pairs pairs alternate between two
+ * streams, so the upload of chunk i + 1 overlaps the kernels of chunk i; poses (and n_good, optional) are copied back.
+ * h_n1 / h_n2: both NULL (every set holds n_feat_max descriptors) or both given.  Synchronous. */
+int vsb_track_pairs_host(vsb_tracker_t* t, const uint8_t* h_prev, const uint8_t* h_cur, const uint8_t* h_d1,
+                         const uint8_t* h_d2, const float* h_kp1_xy, const int32_t* h_n1, const int32_t* h_n2,
+                         const float* h_pose_prior, int count, float* h_pose, int32_t* h_n_good);
 
 #ifdef __cplusplus
 }

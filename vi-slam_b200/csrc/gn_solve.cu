@@ -17,8 +17,8 @@
 // rounded intrinsic in the source order (no FMA contraction); cv::gemm's "float in, double accumulate" is
 // reproduced with exact float*float products summed in FP64.  The reduction order is fixed (batch order, DMMA k
 // order, warp order), so results are run-to-run deterministic and independent of the grid.
-// accum_mode 1 sums a thread's products in FP32 (FMA) and only the cross-thread part in FP64 (north-star
-// wording).  The 6x6 system is solved by warp 0 with OpenCV's LU elimination order (cv::solve), one column of [A | b] per lane.
+// (An FP32-partials variant — per-thread FMA sums, FP64 only across threads — was built in round 1 and removed: it was
+// slower and ended 1.4e-5 from the reference pose, outside the 1e-5 tolerance.)  The 6x6 system is solved by warp 0 with OpenCV's LU elimination order (cv::solve), one column of [A | b] per lane.
 #include "common.cuh"
 #include "se3.cuh"
 #include "gn_common.cuh"
@@ -28,7 +28,6 @@ namespace {
 
 using namespace gn;
 
-constexpr int NRED = 28;         // 21 (upper triangle of J^T J) + 6 (J^T r) + 1 (sum w r^2)
 
 struct GnParams {
     const uint8_t* prev_pyr;
@@ -198,7 +197,7 @@ constexpr int VROW = 36;   // staging row stride (floats): conflict-free for the
 // multiplications by w = 1 per point
 // UNITZW: the points come as pre-back-projected doubles (X, Y) with z = w = 1 (the tracker's fused candidate pass): the
 // per-iteration back-projection, four conversions and the two multiplications by w vanish; same bits.
-template <bool FP32_PARTIALS, int GT, int WM, int U = 2, int TPS = 768, bool UNITZW = false>
+template <int GT, int WM, int U = 2, int TPS = 768, bool UNITZW = false>
 __global__ void __launch_bounds__(GT, (TPS / GT) > 0 ? (TPS / GT) : 1)
 gn_solve_kernel(const GnParams P) {
     constexpr int NW = GT / 32;
@@ -212,7 +211,7 @@ gn_solve_kernel(const GnParams P) {
 
     __shared__ float s_pose[7];
     __shared__ double s_md[12];
-    constexpr int SV_FLOATS = (FP32_PARTIALS ? 1 : U) * 8 * VROW;     // one staging slot per point of a batch
+    constexpr int SV_FLOATS = U * 8 * VROW;     // one staging slot per point of a batch
     __shared__ __align__(16) float s_v[NW][SV_FLOATS];
     static_assert(SV_FLOATS * sizeof(float) >= 64 * sizeof(double), "a warp's staging area doubles as its 8x8 partial sum");
     __shared__ int s_cnt[NW];
@@ -273,11 +272,6 @@ gn_solve_kernel(const GnParams P) {
             for (int i = 0; i < 12; i++) md[i] = s_md[i];
             int nv = 0;
             double acc0 = 0.0, acc1 = 0.0;      // this lane's two entries of the warp's 8x8 Gram matrix
-            float accf[FP32_PARTIALS ? NRED : 1];
-            if (FP32_PARTIALS) {
-#pragma unroll
-                for (int i = 0; i < NRED; i++) accf[i] = 0.f;
-            }
 
             for (int base = 0; base < ncand; base += GT * U) {                    // VISystem.cpp:1281-1338
                 // ---- phase 1: coalesced loads of U points per thread --------------------------------------
@@ -423,59 +417,25 @@ gn_solve_kernel(const GnParams P) {
                     V[6] = good ? (WM == 0 ? res : F_MUL(res, wgt)) : 0.f;
                     V[7] = good ? res : 0.f;
                     nv += good ? 1 : 0;
-                    if (!FP32_PARTIALS) {
-                        // stage only: no barrier between the points of a batch, so their (long, dependent) Jacobian
-                        // chains can be interleaved by the scheduler; the Gram update of the whole batch follows below
+                    // stage only: no barrier between the points of a batch, so their (long, dependent) Jacobian
+                    // chains can be interleaved by the scheduler; the Gram update of the whole batch follows below
 #pragma unroll
-                        for (int q = 0; q < 8; q++) sv[(u * 8 + q) * VROW + lane] = V[q];
-                    } else {
-                        int t = 0;
+                    for (int q = 0; q < 8; q++) sv[(u * 8 + q) * VROW + lane] = V[q];
+                }
+                __syncwarp();
 #pragma unroll
-                        for (int a = 0; a < 6; a++) {
+                for (int u = 0; u < U; u++) {
 #pragma unroll
-                            for (int b = a; b < 6; b++) { accf[t] = fmaf(V[a], V[b], accf[t]); t++; }
-                        }
-#pragma unroll
-                        for (int a = 0; a < 6; a++) accf[21 + a] = fmaf(V[a], V[6], accf[21 + a]);
-                        accf[27] = fmaf(V[7], V[6], accf[27]);
+                    for (int s = 0; s < 8; s++) {
+                        const double d = (double)sv[(u * 8 + g8) * VROW + 4 * s + t4];   // V[g] of point 4s+t of slot u
+                        dmma_8x8x4(acc0, acc1, d, d);
                     }
                 }
-                if (!FP32_PARTIALS) {
-                    __syncwarp();
-#pragma unroll
-                    for (int u = 0; u < U; u++) {
-#pragma unroll
-                        for (int s = 0; s < 8; s++) {
-                            const double d = (double)sv[(u * 8 + g8) * VROW + 4 * s + t4];   // V[g] of point 4s+t of slot u
-                            dmma_8x8x4(acc0, acc1, d, d);
-                        }
-                    }
-                    __syncwarp();                 // the next batch overwrites the slots
-                }
+                __syncwarp();                 // the next batch overwrites the slots
             }
             // ---- cross-warp reduction in warp order (deterministic) --------------------------------------------
-            if (!FP32_PARTIALS) {
-                red[g8 * 8 + 2 * t4] = acc0;
-                red[g8 * 8 + 2 * t4 + 1] = acc1;
-            } else {
-                // FP32 thread partials -> FP64 warp tree -> the same 8x8 layout
-                int t = 0;
-#pragma unroll
-                for (int a = 0; a < 6; a++) {
-#pragma unroll
-                    for (int b = a; b < 6; b++) {
-                        const double v = warp_sum((double)accf[t++]);
-                        if (lane == 0) { red[a * 8 + b] = v; red[b * 8 + a] = v; }
-                    }
-                }
-#pragma unroll
-                for (int a = 0; a < 6; a++) {
-                    const double v = warp_sum((double)accf[21 + a]);
-                    if (lane == 0) red[a * 8 + 6] = v;
-                }
-                const double v = warp_sum((double)accf[27]);
-                if (lane == 0) red[7 * 8 + 6] = v;
-            }
+            red[g8 * 8 + 2 * t4] = acc0;
+            red[g8 * 8 + 2 * t4 + 1] = acc1;
             {
                 int cnum = nv;
 #pragma unroll
@@ -572,7 +532,8 @@ int vsb_gn_solve_stats(vsb_ctx_t* ctx, const uint8_t* prev_pyr, const uint8_t* c
     // attribute records by the fused candidate pass; `cand` may then be NULL
     if (!ctx || !prev_pyr || !cur_pyr || !layout || (!cand && !xy_ready) || !n_cand || !K || !pose_in || !opts || !pose_out)
         return VSB_ERR_INVALID;
-    if (xy_ready && !(patt_ready && patt_scratch && opts->accum_mode == 0 && opts->weight_mode == 0)) return VSB_ERR_INVALID;
+    if (opts->accum_mode != 0) return VSB_ERR_UNSUPPORTED;     // the FP32-partials variant of round 1 is gone (see the header)
+    if (xy_ready && !(patt_ready && patt_scratch && opts->weight_mode == 0)) return VSB_ERR_INVALID;
     if (count < 0 || cand_cap < 0) return VSB_ERR_INVALID;
     if (opts->first_lvl >= layout->levels || opts->last_lvl < 0 || opts->first_lvl < opts->last_lvl)
         return VSB_ERR_INVALID;
@@ -637,38 +598,18 @@ int vsb_gn_solve_stats(vsb_ctx_t* ctx, const uint8_t* prev_pyr, const uint8_t* c
         const int sms = ctx->sm_count > 0 ? ctx->sm_count : 148;
         gt_env = count >= 4 * sms ? 128 : count >= 2 * sms ? 256 : count >= sms / 2 ? 512 : 1024;
     }
-#define GN_LAUNCH(FP, T)                                                                 \
-    do {                                                                                 \
-        if (opts->weight_mode == 1) gn_solve_kernel<FP, T, 1><<<count, T, 0, st>>>(P);      \
-        else if (opts->weight_mode == 2) gn_solve_kernel<FP, T, 2><<<count, T, 0, st>>>(P); \
-        else gn_solve_kernel<FP, T, 0><<<count, T, 0, st>>>(P);                          \
+#define GN_LAUNCH(T, U, TPS)                                                                          \
+    do {                                                                                              \
+        if (opts->weight_mode == 1) gn_solve_kernel<T, 1, U, TPS><<<count, T, 0, st>>>(P);            \
+        else if (opts->weight_mode == 2) gn_solve_kernel<T, 2, U, TPS><<<count, T, 0, st>>>(P);       \
+        else if (xy_ready) gn_solve_kernel<T, 0, U, TPS, true><<<count, T, 0, st>>>(P);               \
+        else gn_solve_kernel<T, 0, U, TPS><<<count, T, 0, st>>>(P);                                   \
     } while (0)
-    if (xy_ready) {
-        if (gt_env >= 1024) gn_solve_kernel<false, 1024, 0, 1, 1024, true><<<count, 1024, 0, st>>>(P);
-        else if (gt_env >= 512) gn_solve_kernel<false, 512, 0, 2, 1024, true><<<count, 512, 0, st>>>(P);
-        else if (gt_env >= 256) gn_solve_kernel<false, 256, 0, 2, 768, true><<<count, 256, 0, st>>>(P);
-        else gn_solve_kernel<false, 128, 0, 2, 768, true><<<count, 128, 0, st>>>(P);
-    } else if (ctx->gn_variant > 0 && opts->accum_mode == 0 && opts->weight_mode == 0 && gt_env == 128) {   // tuning experiments
-        switch (ctx->gn_variant) {    // (points per thread per batch, resident threads per SM the registers are sized for)
-            case 1: gn_solve_kernel<false, 128, 0, 4, 768><<<count, 128, 0, st>>>(P); break;
-            case 2: gn_solve_kernel<false, 128, 0, 2, 1024><<<count, 128, 0, st>>>(P); break;
-            case 3: gn_solve_kernel<false, 128, 0, 3, 768><<<count, 128, 0, st>>>(P); break;
-            case 4: gn_solve_kernel<false, 128, 0, 4, 640><<<count, 128, 0, st>>>(P); break;
-            default: gn_solve_kernel<false, 128, 0, 1, 1024><<<count, 128, 0, st>>>(P); break;
-        }
-    } else if (opts->accum_mode == 1) {
-        if (gt_env == 64) GN_LAUNCH(true, 64); else if (gt_env == 128) GN_LAUNCH(true, 128); else GN_LAUNCH(true, 256);
-    } else if (gt_env >= 1024) {
-        if (opts->weight_mode == 1) gn_solve_kernel<false, 1024, 1, 1, 1024><<<count, 1024, 0, st>>>(P);
-        else if (opts->weight_mode == 2) gn_solve_kernel<false, 1024, 2, 1, 1024><<<count, 1024, 0, st>>>(P);
-        else gn_solve_kernel<false, 1024, 0, 1, 1024><<<count, 1024, 0, st>>>(P);
-    } else if (gt_env >= 512) {
-        if (opts->weight_mode == 1) gn_solve_kernel<false, 512, 1, 2, 1024><<<count, 512, 0, st>>>(P);
-        else if (opts->weight_mode == 2) gn_solve_kernel<false, 512, 2, 2, 1024><<<count, 512, 0, st>>>(P);
-        else gn_solve_kernel<false, 512, 0, 2, 1024><<<count, 512, 0, st>>>(P);
-    } else {
-        if (gt_env == 64) GN_LAUNCH(false, 64); else if (gt_env == 128) GN_LAUNCH(false, 128); else GN_LAUNCH(false, 256);
-    }
+    if (gt_env >= 1024) GN_LAUNCH(1024, 1, 1024);
+    else if (gt_env >= 512) GN_LAUNCH(512, 2, 1024);
+    else if (gt_env >= 256) GN_LAUNCH(256, 2, 768);
+    else if (gt_env >= 128) GN_LAUNCH(128, 2, 768);
+    else GN_LAUNCH(64, 2, 768);
 #undef GN_LAUNCH
     VSB_LAUNCHED(ctx);
     return VSB_OK;

@@ -62,6 +62,8 @@ struct Slot {
     float* pose = nullptr;
     float* orb_resp = nullptr;    // [max_pairs + 1][n_feat] each, allocated on the first vsb_track_sequence_orb call
     float* orb_angle = nullptr;
+    uint8_t* desc2 = nullptr;     // second descriptor set of the pairs host entry, [max_pairs][n_feat][desc_bytes], allocated on first use
+    int32_t* n_feat2 = nullptr;   // its counts, [max_pairs]
     uint8_t* stage = nullptr;     // [max_pairs + 1][w * h] contiguous frames of the host entry (VSB_HOST_STAGING=1), allocated on first use
     cudaStream_t stream = nullptr;
     cudaEvent_t done = nullptr;
@@ -135,7 +137,7 @@ int slot_alloc(vsb_tracker* t, Slot& s) {
 }
 
 void slot_free(Slot& s) {
-    void* ptrs[] = {s.pyr, s.gx, s.gy, s.desc, s.kp, s.n_feat, s.prior, s.key12, s.key21, s.good_q, s.good_t, s.good_d, s.n_good, s.n_sym, s.good_xy, s.cand, s.patt, s.n_cand, s.org, s.pose, s.orb_resp, s.orb_angle, s.stage};
+    void* ptrs[] = {s.pyr, s.gx, s.gy, s.desc, s.kp, s.n_feat, s.prior, s.key12, s.key21, s.good_q, s.good_t, s.good_d, s.n_good, s.n_sym, s.good_xy, s.cand, s.patt, s.n_cand, s.org, s.pose, s.orb_resp, s.orb_angle, s.stage, s.desc2, s.n_feat2};
     for (void* p : ptrs) if (p) cudaFree(p);
     if (s.stream) cudaStreamDestroy(s.stream);
     if (s.done) cudaEventDestroy(s.done);
@@ -203,11 +205,11 @@ int run_pairs(vsb_tracker* t, Slot& s, const uint8_t* pyr_prev, const uint8_t* p
     const int fused = c.gn.grad_mode == 1 ? 1 : 0;
     // reference modes (identity weights, nearest-pixel lookup, FP64 Gram): gn_track.cu — 8-byte records that name their
     // slots in per-feature back-projection tables, nothing else per point
-    const bool tables = fused && ctx->gn_impl == 1 && c.gn.accum_mode == 0 && c.gn.weight_mode == 0 && c.gn.sample_mode == 0 &&
+    const bool tables = fused && ctx->gn_impl == 1 && c.gn.weight_mode == 0 && c.gn.sample_mode == 0 &&
                         t->feat_cap * 11 <= 4096;
     // ... otherwise gn_solve.cu; with identity weights the points are handed over already back-projected, as doubles,
     // in the candidate buffer itself (a double2 is as wide as the float4 row it replaces)
-    const int unit = fused && !tables && c.gn.accum_mode == 0 && c.gn.weight_mode == 0;
+    const int unit = fused && !tables && c.gn.weight_mode == 0;
     if ((rc = vsb_candidates_prepare(ctx, s.good_xy, t->good_cap, s.n_good, count, t->lay.levels, t->lw, t->lh, s.cand,
                                      t->cand_cap, s.n_cand, fused ? pyr_prev : nullptr, t->lay.frame_stride, &t->lay,
                                      c.gn.first_lvl, c.gn.last_lvl, fused ? s.patt : nullptr, unit ? (void*)s.cand : nullptr,
@@ -466,6 +468,64 @@ extern "C" int vsb_track_sequence_host(vsb_tracker_t* t, const uint8_t* h_frames
         p0 += pairs;
     }
     for (int i = 0; i < 2; i++) VSB_CUDA(ctx, cudaStreamSynchronize(t->slot[i].stream));
+    t->host_h2d_bytes = h2d; t->host_d2h_bytes = d2h; t->host_chunks = chunk_idx;
+    return VSB_OK;
+}
+
+// Independent pairs from HOST buffers (BASELINE configs[4] end to end): chunks of cfg.max_pairs pairs alternate between the
+// two slots / streams, so the upload of chunk i + 1 overlaps the kernels of chunk i.  Frames go straight into level 0 of the
+// packed pyramids (one strided copy per frame set).
+extern "C" int vsb_track_pairs_host(vsb_tracker_t* t, const uint8_t* h_prev, const uint8_t* h_cur, const uint8_t* h_d1,
+                                    const uint8_t* h_d2, const float* h_kp1_xy, const int32_t* h_n1, const int32_t* h_n2,
+                                    const float* h_pose_prior, int count, float* h_pose, int32_t* h_n_good) {
+    if (!t || !h_prev || !h_cur || !h_d1 || !h_d2 || !h_kp1_xy || !h_pose_prior || !h_pose) return VSB_ERR_INVALID;
+    if ((h_n1 == nullptr) != (h_n2 == nullptr)) return VSB_ERR_INVALID;
+    if (count <= 0) return count < 0 ? VSB_ERR_INVALID : VSB_OK;
+    vsb_ctx* ctx = t->ctx;
+    const vsb_tracker_cfg_t& c = t->cfg;
+    const size_t fbytes = (size_t)c.w * c.h;
+    const size_t dstride = (size_t)c.n_feat_max * c.desc_bytes;
+    const size_t kstride = (size_t)c.n_feat_max * 2;
+    long long h2d = 0, d2h = 0;
+    int chunk_idx = 0;
+    int rc = VSB_OK;
+    for (int p0 = 0; p0 < count && rc == VSB_OK; chunk_idx++) {
+        const int pairs = count - p0 < c.max_pairs ? count - p0 : c.max_pairs;
+        Slot& s = t->slot[chunk_idx & 1];
+        cudaStream_t st = s.stream;
+        if (chunk_idx >= 2) VSB_CUDA(ctx, cudaEventSynchronize(s.done));   // slot buffers are free again
+        if (!s.desc2) VSB_CUDA(ctx, cudaMalloc((void**)&s.desc2, (size_t)c.max_pairs * dstride));
+        if (!s.n_feat2) VSB_CUDA(ctx, cudaMalloc((void**)&s.n_feat2, (size_t)c.max_pairs * sizeof(int32_t)));
+        uint8_t* pyr_prev = s.pyr;
+        uint8_t* pyr_cur = s.pyr + (size_t)c.max_pairs * t->lay.frame_stride;
+        VSB_CUDA(ctx, cudaMemcpy2DAsync(pyr_prev, (size_t)t->lay.frame_stride, h_prev + (size_t)p0 * fbytes, fbytes, fbytes, pairs,
+                                        cudaMemcpyHostToDevice, st));
+        VSB_CUDA(ctx, cudaMemcpy2DAsync(pyr_cur, (size_t)t->lay.frame_stride, h_cur + (size_t)p0 * fbytes, fbytes, fbytes, pairs,
+                                        cudaMemcpyHostToDevice, st));
+        VSB_CUDA(ctx, cudaMemcpyAsync(s.desc, h_d1 + (size_t)p0 * dstride, pairs * dstride, cudaMemcpyHostToDevice, st));
+        VSB_CUDA(ctx, cudaMemcpyAsync(s.desc2, h_d2 + (size_t)p0 * dstride, pairs * dstride, cudaMemcpyHostToDevice, st));
+        VSB_CUDA(ctx, cudaMemcpyAsync(s.kp, h_kp1_xy + (size_t)p0 * kstride, pairs * kstride * sizeof(float), cudaMemcpyHostToDevice, st));
+        VSB_CUDA(ctx, cudaMemcpyAsync(s.prior, h_pose_prior + (size_t)p0 * 7, (size_t)pairs * 28, cudaMemcpyHostToDevice, st));
+        if (h_n1) {
+            VSB_CUDA(ctx, cudaMemcpyAsync(s.n_feat, h_n1 + p0, pairs * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+            VSB_CUDA(ctx, cudaMemcpyAsync(s.n_feat2, h_n2 + p0, pairs * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+        }
+        h2d += (long long)pairs * (2 * fbytes + 2 * dstride + kstride * sizeof(float) + 28 + (h_n1 ? 8 : 0));
+        d2h += pairs * 28LL + (h_n_good ? pairs * 4LL : 0);
+        if ((rc = vsb_pyramid_build(ctx, nullptr, (int64_t)fbytes, c.w, pairs, &t->lay, pyr_prev, st))) break;
+        if ((rc = vsb_pyramid_build(ctx, nullptr, (int64_t)fbytes, c.w, pairs, &t->lay, pyr_cur, st))) break;
+        if (c.gn.grad_mode == 0 && (rc = vsb_gradient_build(ctx, pyr_prev, pairs, &t->lay, s.gx, s.gy, nullptr, st))) break;
+        if ((rc = run_pairs(t, s, pyr_prev, pyr_cur, s.gx, s.gy, s.desc, s.desc2, s.kp, h_n1 ? s.n_feat : nullptr,
+                            h_n1 ? s.n_feat2 : nullptr, s.prior, pairs, s.pose, nullptr, st)))
+            break;
+        VSB_CUDA(ctx, cudaMemcpyAsync(h_pose + (size_t)p0 * 7, s.pose, (size_t)pairs * 28, cudaMemcpyDeviceToHost, st));
+        if (h_n_good)
+            VSB_CUDA(ctx, cudaMemcpyAsync(h_n_good + p0, s.n_good, pairs * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+        VSB_CUDA(ctx, cudaEventRecord(s.done, st));
+        p0 += pairs;
+    }
+    for (int i = 0; i < 2; i++) cudaStreamSynchronize(t->slot[i].stream);      // also on the error path: copies may be in flight
+    if (rc) return rc;
     t->host_h2d_bytes = h2d; t->host_d2h_bytes = d2h; t->host_chunks = chunk_idx;
     return VSB_OK;
 }
