@@ -127,7 +127,7 @@ int ref_track_pair(const uint8_t* img_prev, const uint8_t* img_cur, int w, int h
         cv::Mat::oob_reads() = 0;
         sys.EstimatePoseFeatures(prev, cur);
         const long long oob = cv::Mat::oob_reads();
-        for (int i = 0; i < 7; i++) pose_out[i] = prev->rigid_transformation_.p[i];
+        for (int i = 0; i < 7; i++) pose_out[i] = prev->rigid_transformation_.data()[i];   // qx qy qz qw tx ty tz (se3.hpp data())
 
         // "lvl = <l>Error it <k> =<e>    Last Error it  =<le>"
         int nt = 0;
@@ -158,7 +158,7 @@ int ref_warp(const float* pts, int n, const float pose[7], int w, int h, const f
         cv::Mat p(n, 4, CV_32FC1);
         memcpy(p.data, pts, (size_t)n * 16);
         vi::SE3 T;
-        for (int i = 0; i < 7; i++) T.p[i] = pose[i];
+        for (int i = 0; i < 7; i++) T.data()[i] = pose[i];
         cv::Mat r = sys.WarpFunctionSE3(p, T, lvl);
         for (int i = 0; i < n; i++) memcpy(out + 4 * (size_t)i, r.ptr(i), 16);
         return 0;

@@ -171,6 +171,13 @@ void vso_rot_to_quat(const float m[9], float q[4]) {
     }
 }
 
+/* Sophus::SE3f(rotation matrix, translation) (se3.hpp:438-440 -> SO3(R), so3.hpp:422-427): the quaternion of R, t as given. */
+int vso_se3_from_rt(const float r[9], const float t[3], float pose[7]) {
+    vso_rot_to_quat(r, pose);
+    pose[4] = t[0]; pose[5] = t[1]; pose[6] = t[2];
+    return 0;
+}
+
 static void mat33_mul(const float a[9], const float b[9], float c[9]) {
     for (int i = 0; i < 3; i++)
         for (int j = 0; j < 3; j++)

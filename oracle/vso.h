@@ -107,6 +107,7 @@ void vso_se3_matrix(const float pose[7], float m[16]);          /* se3.hpp:253-2
 void vso_rpy_to_rot(const double rpy[3], float r[9]);           /* Plus.cpp:182-220 */
 void vso_rot_to_rpy(const float r[9], double rpy[3]);           /* Plus.cpp:56-83 */
 void vso_rot_to_quat(const float r[9], float q[4]);             /* Eigen Quaternion(Matrix3) */
+int vso_se3_from_rt(const float r[9], const float t[3], float pose[7]); /* SE3(R, t), se3.hpp:438-440; returns 0 */
 /* VISystem.cpp:1135-1168: pose0 = SE3(RPY2rot(-rot2RPY(imu2cam^T R_imu imu2cam)), -t_res) */
 void vso_initial_pose(const float imu2cam[9], const float r_imu_res[9], const float t_res[3], float pose[7]);
 
