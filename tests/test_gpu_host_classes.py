@@ -210,3 +210,43 @@ def test_visystem_gpu_from_raw_frames_vs_oracle(tmp_path, oracle):
                               n_cells=n_cells)
         assert int(ngood[k]) == len(r["good_q"]) > 10
         np.testing.assert_array_equal(poses[k], r["pose"])
+
+
+def test_reference_gpu_main_runs_from_files(tmp_path):
+    """The reproduced GPU executable of the reference (host/tests/main_vi_slamGPU_caller.cpp, built against the forwarding
+    headers) on an EuRoC-layout dataset on disk: DataReader -> VISystemGPU::InitializeSystemGPU (calibration XML) ->
+    AddFrameGPU per frame (IMU samples -> imuCore.estimate -> GN prior; ORB on the device -> match -> GN) -> CSV."""
+    import subprocess
+    from test_host_build import CAL_XML, PKG, _build
+    from vislam_b200 import synth
+    _build()
+    T = 18
+    seq = synth.make_sequence(T, n_feat=10, seed=2001)
+    img_dir = tmp_path / "cam0" / "data"
+    img_dir.mkdir(parents=True)
+    t0, cam_dt, imu_dt = 1403636579763555584, 50_000_000, 5_000_000
+    for k in range(T):
+        with open(img_dir / f"{t0 + k * cam_dt}.pgm", "wb") as f:
+            f.write(b"P5\n752 480\n255\n" + seq["frames"][k].tobytes())
+    rng = np.random.default_rng(3)
+    with open(tmp_path / "imu0.csv", "w") as f:
+        f.write("#timestamp [ns],w_x,w_y,w_z,a_x,a_y,a_z\n")
+        for k in range(T - 1):
+            for i in range(10):
+                w = seq["gyro"][k, i]
+                a = np.array([0, 0, 9.68]) + rng.normal(0, 2e-3, 3)
+                f.write(str(t0 + k * cam_dt + i * imu_dt) + "," + ",".join(repr(float(x)) for x in np.concatenate([w, a])) + "\n")
+    with open(tmp_path / "gt.csv", "w") as f:
+        f.write("#timestamp,p_x,p_y,p_z,q_w,q_x,q_y,q_z,v_x,v_y,v_z,bw_x,bw_y,bw_z,ba_x,ba_y,ba_z\n")
+        for k in range((T - 1) * 10):
+            f.write(str(t0 + k * imu_dt) + "," + ",".join(repr(float(x)) for x in [0.001 * k, 0, 1, 1, 0, 0, 0, 0.2, 0, 0] + [0] * 6) + "\n")
+    (tmp_path / "cal.xml").write_text(CAL_XML % "0 0 0 0")
+    out_csv = tmp_path / "out.csv"
+    r = subprocess.run([os.path.join(PKG, "ref_main_gpu"), str(img_dir) + "/", str(tmp_path / "imu0.csv"), str(tmp_path / "gt.csv"),
+                        str(tmp_path / "cal.xml"), str(out_csv), "1"], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    rows = np.loadtxt(out_csv, delimiter=",", ndmin=2)
+    assert rows.shape[0] >= T - 4 and rows.shape[1] == 14
+    assert np.isfinite(rows).all()
+    q = rows[:, 3:7]
+    np.testing.assert_allclose(np.linalg.norm(q, axis=1), 1.0, atol=1e-4)      # toQuaternion of the tracked orientation

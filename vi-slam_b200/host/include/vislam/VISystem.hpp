@@ -2,11 +2,12 @@
 // (include/VISystem.hpp:40-148, include/VISystemGPU.hpp:17-30): InitializePyramid, EstimatePoseFeatures,
 // WarpFunctionSE3, IdentityWeights, Track, AddFrame / AddFrameGPU and the public pose state.
 //
-// Out of this library's scope, and therefore absent here: calibration XML / undistortion
-// (InitializeSystem, Calibration, CameraModel), the ROS/Madgwick IMU filter (imuCore), RANSAC / triangulation
-// experiments (F2FRansac, Triangulate, ...), drawing.  Their outputs that the path consumes are plain public
-// fields the caller sets: K (through InitializePyramid), imu2camRotation, RotationResidualImu (the reference's
-// imuCore.residual_rotationMatrix), TranslationResidual (setGtRes).
+// VISystemGPU::InitializeSystemGPU (VISystemGPU.cpp:39-129) reads the reference's calibration XML (vi::CameraModel, without
+// undistortion) and sets up the pyramid, the initial pose state, imuCore and the camera; AddFrame / AddFrameGPU run
+// imuCore.setImuData + estimate() on the IMU samples they are given and feed residual_rotationMatrix into the GN prior
+// (VISystemGPU.cpp:148-149, VISystem.cpp:1135).  A caller that has no samples (empty vectors) sets RotationResidualImu
+// itself.  Out of scope: undistortion, RANSAC / triangulation experiments (F2FRansac, Triangulate, ...),
+// drawing.  TranslationResidual comes from setGtRes, as upstream.
 #ifndef VISLAM_VISYSTEM_HPP_
 #define VISLAM_VISYSTEM_HPP_
 
@@ -14,6 +15,8 @@
 #include <vector>
 
 #include "vislam/Camera.hpp"
+#include "vislam/CameraModel.hpp"
+#include "vislam/Imu.hpp"
 #include "vislam/Plus.hpp"
 #include "vislam/compat.hpp"
 #include "vislam/device.hpp"
@@ -42,6 +45,7 @@ public:
     cv::Mat TukeyFunctionWeights(cv::Mat _input);
     cv::Mat WarpFunctionSE3(cv::Mat _points2warp, SE3 _rigid_transformation, int _lvl);
     void setGtRes(cv::Mat TranslationResGT, cv::Mat RotationGT);
+    void Calibration(std::string _calibration_path);        // VISystem.cpp:208-221
 
     bool initialized, distortion_valid, depth_available;
     int num_keyframes;
@@ -62,6 +66,10 @@ public:
 
     cv::Matx33f imu2camRotation;
     cv::Point3d imu2camTranslation;
+    cv::Mat imu2camTransformation, world2imuTransformation;
+    cv::Matx33f world2imuRotation;
+    CameraModel* camera_model;
+    Imu imuCore;
 
     SE3 final_poseCam;
     SE3 final_poseImu;
@@ -104,8 +112,10 @@ public:
     std::vector<vsb_gn_trace_t> last_trace;   // per-iteration record of the last EstimatePoseFeatures (when keep_trace)
     bool keep_trace;
     bool verbose;
+    bool imu_ready;                     // imuCore has its initial orientation (first batch of samples seen)
 
 protected:
+    void update_imu_prior(std::vector<cv::Point3d>& w, std::vector<cv::Point3d>& a);
     void fill_intrinsics(vsb_intr_t out[VSB_MAX_LEVELS]) const;
     virtual Camera& active_camera() { return camera; }   // the camera whose frameList Track() reads
     DevBuf d_pose_, d_trace_, d_ntrace_, d_cand_, d_ncand_, d_pts_;
@@ -116,6 +126,8 @@ public:
     VISystemGPU();
     VISystemGPU(int argc, char* argv[]);
     ~VISystemGPU();
+    void InitializeSystemGPU(std::string _calPath, cv::Point3d _iniPosition, cv::Point3d _iniVelocity, cv::Point3d _iniRPY,
+                             cv::Mat image);
     void InitializeCameraGPU(int _detector, int _matcher, int _w_size, int _h_size, int _num_cells, int _length_path);
     void AddFrameGPU(cv::Mat _currentImage, std::vector<cv::Point3d> _imuAngularVelocity,
                      std::vector<cv::Point3d> _imuAcceleration);

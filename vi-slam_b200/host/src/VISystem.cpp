@@ -21,17 +21,44 @@ namespace vi {
 VISystem::VISystem()
     : initialized(false), distortion_valid(false), depth_available(false), num_keyframes(0), num_max_keyframes(10),
       min_features(0), start_index(0), h(0), w(0), h_input(0), w_input(0), fx(0), fy(0), cx(0), cy(0),
-      imu2camRotation(Matx33f::eye()), RotationResidual(Matx33f::eye()), RotationResCam(Matx33f::eye()),
+      imu2camRotation(Matx33f::eye()), world2imuRotation(Matx33f::eye()), camera_model(nullptr), RotationResidual(Matx33f::eye()), RotationResCam(Matx33f::eye()),
       init_rotationMatrix(Matx33f::eye()), final_rotationMatrix(Matx33f::eye()), nPointsLastKeyframe(0),
       nPointsCurrentImage(0), lastImageWasKeyframe(false), currentImageIsKeyframe(false),
-      RotationResidualImu(Matx33f::eye()), track_from_estimate(false), keep_trace(false), verbose(false) {
+      RotationResidualImu(Matx33f::eye()),
+      track_from_estimate(false), keep_trace(false), verbose(false), imu_ready(false) {
     vsb_gn_default_opts(&gn_options);
     TranslationResidual = Mat::zeros(3, 1, CV_32F);
 }
 
 VISystem::VISystem(int, char*[]) : VISystem() {}   // VISystem.cpp:36-46: the reference only starts a ROS node here
 
-VISystem::~VISystem() {}
+VISystem::~VISystem() { delete camera_model; }
+
+void VISystem::Calibration(std::string _calibration_path) {   // VISystem.cpp:208-221 (throws where the reference exit()s)
+    delete camera_model;
+    camera_model = new CameraModel();
+    camera_model->GetCameraModel(_calibration_path);
+    w = camera_model->GetOutputWidth();
+    h = camera_model->GetOutputHeight();
+    if (w % 2 != 0 || h % 2 != 0) throw std::invalid_argument("Output image dimensions must be multiples of 32");   // :216-220
+}
+
+// imuCore.setImuData + estimate() (VISystem.cpp:284-285, VISystemGPU.cpp:142-143): the residual rotation of the frame interval
+// becomes the rotation prior of the Gauss-Newton solve (VISystem.cpp:1135).  The first batch of samples also gives the
+// filter its initial orientation — Imu::initializate(yaw, velocity, w, a), which InitializeSystem calls upstream
+// (VISystem.cpp:143); VISystemGPU.cpp:119 names a one-argument overload that does not exist.  Empty vectors leave
+// RotationResidualImu as the caller set it.
+void VISystem::update_imu_prior(vector<Point3d>& w_meas, vector<Point3d>& a_meas) {
+    if (w_meas.empty() || a_meas.empty()) return;
+    if (imuCore.timeStep <= 0) imuCore.createPublisher(1.0 / 200.0);        // calibration default (imu_frecuency 200)
+    if (!imu_ready) {
+        imuCore.initializate(RPYOrientationImu.z, velocityImu, w_meas, a_meas);
+        imu_ready = true;
+    }
+    imuCore.setImuData(w_meas, a_meas);
+    imuCore.estimate();
+    RotationResidualImu = imuCore.residual_rotationMatrix;
+}
 
 void VISystem::InitializeCamera(int _detector, int _matcher, int _w_size, int _h_size, int _num_cells, int _length_path) {
     camera.initializate(_detector, _matcher, _w_size, _h_size, _num_cells, _length_path);   // VISystem.cpp:1637-1640
@@ -214,7 +241,7 @@ void VISystem::FreeLastFrame() {   // VISystem.cpp:407-412 (the reference runs t
 // keyframes picked from the keyboard).  The tracking loop the path is quoted on is VISystemGPU::AddFrameGPU
 // (VISystemGPU.cpp:144-169); AddFrame runs that same sequence on `camera`.
 bool VISystem::AddFrame(Mat _currentImage, vector<Point3d> _imuAngularVelocity, vector<Point3d> _imuAcceleration) {
-    (void)_imuAngularVelocity; (void)_imuAcceleration;   // the IMU filter is upstream of the path: RotationResidualImu is its output
+    update_imu_prior(_imuAngularVelocity, _imuAcceleration);
     prevImage = currentImage;
     currentImage = _currentImage.clone();
     camera.Update(_currentImage);
@@ -256,6 +283,61 @@ VISystemGPU::VISystemGPU() : VISystem() {}
 VISystemGPU::VISystemGPU(int argc, char* argv[]) : VISystem(argc, argv) {}
 VISystemGPU::~VISystemGPU() {}
 
+// VISystemGPU.cpp:39-129.  Differences, all forced by what is outside the library: no undistortion maps (CameraModel refuses
+// distorted calibrations), imuCore receives its initial orientation with the first batch of samples (update_imu_prior).
+void VISystemGPU::InitializeSystemGPU(std::string _calPath, Point3d _iniPosition, Point3d _iniVelocity, Point3d _iniRPY, Mat image) {
+    currentImage = image;
+    Calibration(_calPath);
+    imu2camTransformation = camera_model->imu2cam0Transformation;
+    const Mat r = transformationMatrix2rotationMatrix(imu2camTransformation);
+    for (int i = 0; i < 3; i++)
+        for (int j = 0; j < 3; j++) imu2camRotation(i, j) = r.at<float>(i, j);
+    imu2camTranslation = transformationMatrix2position(imu2camTransformation);
+    K = camera_model->GetK();
+    w_input = camera_model->GetInputWidth();
+    h_input = camera_model->GetInputHeight();
+    distortion_valid = camera_model->IsValid();          // always false: frames are taken as undistorted
+    w = w_input;
+    h = h_input;
+    InitializePyramid(w, h, K);
+    initialized = true;
+    positionImu = _iniPosition;                          // :97-104
+    velocityImu = _iniVelocity;
+    RPYOrientationImu = _iniRPY;
+    qOrientationImu = toQuaternion(_iniRPY.x, _iniRPY.y, _iniRPY.z);
+    world2imuTransformation = RPYAndPosition2transformationMatrix(RPYOrientationImu, positionImu);
+    const Mat wr = transformationMatrix2rotationMatrix(world2imuTransformation);
+    for (int i = 0; i < 3; i++)
+        for (int j = 0; j < 3; j++) world2imuRotation(i, j) = wr.at<float>(i, j);
+    final_poseImu = SE3((float)qOrientationImu.w, (float)qOrientationImu.x, (float)qOrientationImu.y, (float)qOrientationImu.z,
+                        0.f, 0.f, 0.f);
+    // camera pose: T_imu2cam [p 1]^T, R_imu2cam v, R_imu2cam R_world2imu (:108-114)
+    {
+        const Mat& T = imu2camTransformation;
+        const float p[4] = {(float)positionImu.x, (float)positionImu.y, (float)positionImu.z, 1.f};
+        double o[3];
+        for (int i = 0; i < 3; i++) {
+            double s = 0;
+            for (int k = 0; k < 4; k++) s += (double)T.at<float>(i, k) * p[k];       // cv::gemm: float in, double accumulate
+            o[i] = (float)s;
+        }
+        positionCam = Point3d(o[0], o[1], o[2]);
+        const cv::Point3f v = imu2camRotation * cv::Point3f((float)velocityImu.x, (float)velocityImu.y, (float)velocityImu.z);
+        velocityCam = Point3d(v.x, v.y, v.z);
+    }
+    RPYOrientationCam = rotationMatrix2RPY(imu2camRotation * world2imuRotation);
+    qOrientationCam = toQuaternion(RPYOrientationCam.x, RPYOrientationCam.y, RPYOrientationCam.z);
+    final_poseCam = SE3((float)qOrientationCam.w, (float)qOrientationCam.x, (float)qOrientationCam.y, (float)qOrientationCam.z,
+                        (float)-positionCam.x, (float)-positionCam.z, (float)-positionCam.y);
+    imuCore.createPublisher(1.0 / (camera_model->imu_frecuency));    // :117-119
+    imuCore.setImuInitialVelocity(_iniVelocity);
+    imu_ready = false;
+    num_max_keyframes = camera_model->min_features;                   // :122 (sic: the reference assigns min_features)
+    min_features = camera_model->min_features;
+    start_index = camera_model->start_index;
+    InitializeCameraGPU(camera_model->detector, camera_model->matcher, w, h, camera_model->num_cells, camera_model->length_patch);
+}
+
 void VISystemGPU::InitializeCameraGPU(int _detector, int _matcher, int _w_size, int _h_size, int _num_cells, int _length_path) {
     cameraGPU.initializateCameraGPU(_detector, _matcher, _w_size, _h_size, _num_cells, _length_path);   // VISystemGPU.cpp:136-139
 }
@@ -267,7 +349,7 @@ void VISystemGPU::FreeLastFrameGPU() {   // VISystemGPU.cpp:171-175
 }
 
 void VISystemGPU::AddFrameGPU(Mat _currentImage, vector<Point3d> _imuAngularVelocity, vector<Point3d> _imuAcceleration) {
-    (void)_imuAngularVelocity; (void)_imuAcceleration;   // VISystemGPU.cpp:144-169
+    update_imu_prior(_imuAngularVelocity, _imuAcceleration);   // VISystemGPU.cpp:142-143; the rest is :144-169
     prevImage = currentImage;
     currentImage = _currentImage.clone();
     cameraGPU.Update(_currentImage);

@@ -6,6 +6,7 @@
 #include <exception>
 #include <string>
 
+#include "vislam/CameraModel.hpp"
 #include "vislam/DataReader.hpp"
 #include "vislam/Imu.hpp"
 #include "vislam/Plus.hpp"
@@ -226,6 +227,26 @@ int vih_imu_run(double timestep, double gt_yaw, const double gt_vel[3], const do
             imu.estimate();
             dump(out + 60 * (s + 1));
         }
+        return 0;
+    } catch (const std::exception& e) { return fail(e); }
+}
+
+// vi::CameraModel::GetCameraModel (src/CameraModel.cpp:16-101) on a calibration XML: out[0..3] = fx fy cx cy, [4..7] = in / out
+// sizes, [8..9] = camera / imu rate, [10..18] = min_features num_max_keyframes start_index use_gt use_ros num_cells length_patch
+// detector matcher, [19..34] = imu2cam0Transformation row-major.  Returns -1 (message in vih_last_error) where the reference exits.
+int vih_camera_model(const char* path, double* out) {
+    try {
+        vi::CameraModel m;
+        m.GetCameraModel(path);
+        const cv::Mat& K = m.GetK();
+        out[0] = K.at<float>(0, 0); out[1] = K.at<float>(1, 1); out[2] = K.at<float>(0, 2); out[3] = K.at<float>(1, 2);
+        out[4] = m.GetInputWidth(); out[5] = m.GetInputHeight(); out[6] = m.GetOutputWidth(); out[7] = m.GetOutputHeight();
+        out[8] = m.camera_frecuency; out[9] = m.imu_frecuency;
+        const int v[9] = {m.min_features, m.num_max_keyframes, m.start_index, m.use_gt, m.use_ros, m.num_cells, m.length_patch,
+                          m.detector, m.matcher};
+        for (int i = 0; i < 9; i++) out[10 + i] = v[i];
+        for (int i = 0; i < 4; i++)
+            for (int j = 0; j < 4; j++) out[19 + 4 * i + j] = m.imu2cam0Transformation.at<float>(i, j);
         return 0;
     } catch (const std::exception& e) { return fail(e); }
 }
