@@ -19,9 +19,10 @@ def main():
     specs = sys.argv[2:] or ["1:0:1:8192", "1:0:0:8192", "1:0:1:0", "1:0:1:32768", "1:128:0:8192", "1:256:0:8192",
                              "1:512:0:8192", "0:0:0:0"]
     n_cells = int(os.environ.get("KB_CELLS", "49"))
-    seq = bench.make_data(n_frames, 2001, "cuda")
+    from vislam_b200 import workloads as wl
+    seq = wl.sequence(wl.CFG1, bench.product_initial_pose(vb), n_frames=n_frames, device="cuda")
     ctx = vb.Context(0)
-    tr = ctx.tracker(bench.W, bench.H, bench.N_FEAT, seq["K"], n_cells=n_cells, max_pairs=n_frames - 1)
+    tr = ctx.tracker(wl.CFG1["w"], wl.CFG1["h"], wl.CFG1["n_feat"], seq["K"], n_cells=n_cells, max_pairs=n_frames - 1)
     dev = lambda a: a.cuda() if torch.is_tensor(a) else torch.from_numpy(np.ascontiguousarray(a)).cuda()
     frames, desc, kp, prior = dev(seq["frames"]), dev(seq["desc"]), dev(seq["kp"]), dev(seq["prior"])
     ref = None

@@ -517,6 +517,11 @@ int orb_one_level(vsb_ctx_t* ctx, const OrbScratch& S, const uint8_t* in, int64_
 
 // ORB key points + descriptors of `count` frames, one pyramid level (cv::ORB::create(nfeatures, 1.2f, 1, 31, 0, 2,
 // HARRIS_SCORE, 31, fast_threshold)->detectAndCompute).  See include/vislam_b200.h.
+// Scratch budget of one chunk of frames.  Every stage is one launch per chunk and pyramid level, and the upper levels of
+// the scale pyramid are small, so few large chunks keep the machine filled where many small ones are launch-bound: 2000
+// 752x480 frames need 7.6 GB in one chunk (an HBM3e part has 180 GB), which the default budget allows.
+static size_t orb_scratch_budget(const vsb_ctx* ctx) { return (size_t)(ctx->orb_scratch_mb > 0 ? ctx->orb_scratch_mb : 8192) << 20; }
+
 extern "C" int vsb_orb_detect_compute(vsb_ctx_t* ctx, const uint8_t* img, int64_t img_stride, int pitch, int w, int h, int count,
                                       int nfeatures, int fast_threshold, int cap, int32_t* kp_xy, float* kp_resp,
                                       float* kp_angle, uint8_t* desc, int32_t* n_kp, void* stream) {
@@ -528,7 +533,7 @@ extern "C" int vsb_orb_detect_compute(vsb_ctx_t* ctx, const uint8_t* img, int64_
     // FAST corners per frame: 3x3 non-maximum suppression leaves at most one corner per 2x2 block, so w*h/4 can never
     // overflow (dense noise does reach a quarter of that); the batch is processed in chunks that keep the scratch bounded
     const size_t per_frame = orb_scratch_bytes(1, w, h, desc != nullptr);
-    const int chunk = (int)max((size_t)1, min((size_t)count, ((size_t)384 << 20) / per_frame));
+    const int chunk = (int)max((size_t)1, min((size_t)count, orb_scratch_budget(ctx) / per_frame));
     void* scratch = nullptr;
     int rc = vsb_scratch2_reserve(ctx, orb_scratch_bytes(chunk, w, h, desc != nullptr) + 256, &scratch);
     if (rc) return rc;
@@ -566,7 +571,7 @@ extern "C" int vsb_orb_detect_compute_pyr(vsb_ctx_t* ctx, const uint8_t* img, in
     const bool describe = desc != nullptr;
     const size_t tmp_frame = orb_al((size_t)cap * 8) + 2 * orb_al((size_t)cap * 4) + (describe ? orb_al((size_t)cap * 32) : 0);
     const size_t per_frame = orb_scratch_bytes(1, w, h, describe) + 2 * orb_al((size_t)w * h) + tmp_frame + 256;
-    const int chunk = (int)max((size_t)1, min((size_t)count, ((size_t)384 << 20) / per_frame));
+    const int chunk = (int)max((size_t)1, min((size_t)count, orb_scratch_budget(ctx) / per_frame));
     const size_t b_img = orb_al((size_t)chunk * w * h);
     void* scratch = nullptr;
     int rc = vsb_scratch2_reserve(ctx, orb_scratch_bytes(chunk, w, h, describe) + 2 * b_img + chunk * tmp_frame + orb_al((size_t)chunk * 4) +

@@ -3,6 +3,7 @@
 // Update (pyramid) -> computeGPUGoodMatches -> computeGradient -> ObtainPatchesPointsPreviousFrame ->
 // EstimatePoseFeatures — batched over independent frame pairs, with no host round trip between stages.
 // Pairs of a sequence are independent given their priors, so a sequence is one batch.
+#include <cmath>
 #include <cstdlib>
 #include "common.cuh"
 #include "knn_keys.cuh"
@@ -81,6 +82,7 @@ struct vsb_tracker {
     vsb_intr_t K[VSB_MAX_LEVELS];
     int lw[VSB_MAX_LEVELS], lh[VSB_MAX_LEVELS];
     int good_cap, cand_cap, feat_cap;
+    bool principal_point_ok;     // |cx|, |cy| >= 2^-10 at every level (gn_track.cu's division, see div3)
     Slot slot[2];
     int n_slots;
     unsigned long long* stats;   // device, 4 counters shared by both slots
@@ -147,17 +149,28 @@ void slot_free(Slot& s) {
     s = Slot();
 }
 
-// Threads per frame pair of gn_track.cu.  A pair is one block, so a batch that cannot fill the machine with 128-thread
-// blocks gets more threads per pair: the largest block size whose resident blocks (6 / 3 / 2 / 1 per SM for 128 / 256 / 512 /
-// 1024 threads) still hold the whole batch.  A large batch runs in waves of 6 x SMs blocks; the pairs of the last, partial
-// wave would leave most of the machine idle while they finish, so they go to a second launch with more threads each, on
-// a second stream: its blocks fill the SMs that the main launch drains.  Measured on configs[1] (1999 pairs; tools/
-// sweep_gn_tail.sh): 1.85 ms with the tail launch, 1.89 ms without; tail sizes 100..600 pairs and 256 / 512 threads all
-// land within 2 % of each other.
-void gn_plan(const vsb_ctx* ctx, int count, int* threads, int* n_tail, int* threads_tail) {
+// Threads per frame pair of gn_track.cu.  A pair is one block, so a batch that cannot fill the machine with small blocks
+// gets more threads per pair: the largest block size whose resident blocks still hold the whole batch.  Two regimes,
+// both measured (tools/kbench_gn.py, tools/leg_once.py):
+//   * num_cells 49 (<= 64 features, 8.6 KB of back-projection tables): 128-thread blocks, 6-7 per SM, are the fastest for
+//     a large batch (1999 pairs: 1.85 ms; 256 threads 1.96, 512 threads 2.09);
+//   * the 200-feature cap (35 KB of tables, four times the points per pair): shared memory leaves room for three
+//     128-thread blocks per SM only, and 512-thread blocks win (1024 pairs x 5000 features: 5.4 ms against 7.2 ms), 1024
+//     threads when the batch fits one block per SM (199 KITTI pairs: 1.63 against 1.85 ms).
+// A large batch runs in waves; the pairs of the last, partial wave would leave most of the machine idle while they finish,
+// so they go to a second launch with more threads each, on a second stream: its blocks fill the SMs the main launch
+// drains (1999 pairs: 1.85 ms with the tail launch, 1.89 ms without; tail sizes 100..600 pairs and 256 / 512 threads all
+// land within 2 % of each other, tools/sweep_gn_tail.sh).
+void gn_plan(const vsb_ctx* ctx, int count, int feat_cap, int* threads, int* n_tail, int* threads_tail) {
     const int sms = ctx->sm_count > 0 ? ctx->sm_count : 148;
-    auto fit = [&](int n) { return n <= sms ? 1024 : n <= 2 * sms ? 512 : n <= 3 * sms ? 256 : 128; };
-    *n_tail = 0; *threads_tail = 128;
+    const bool big = feat_cap > 64;
+    const int base = big ? 512 : 128;                       // block size of a large batch
+    const int per_sm = big ? 2 : 6;                         // resident blocks per SM the wave arithmetic assumes
+    auto fit = [&](int n) {
+        const int t = n <= (big ? 2 : 1) * sms ? 1024 : n <= 2 * sms ? 512 : n <= 3 * sms ? 256 : 128;
+        return t > base ? t : base;
+    };
+    *n_tail = 0; *threads_tail = base;
     if (ctx->gn_threads) { *threads = ctx->gn_threads < 128 ? 128 : ctx->gn_threads; return; }
     *threads = fit(count);
     if (const char* e = getenv("VSB_GN_TAIL_PAIRS")) {           // experiment knob: explicit tail size / threads
@@ -165,10 +178,10 @@ void gn_plan(const vsb_ctx* ctx, int count, int* threads, int* n_tail, int* thre
         *n_tail = atoi(e) < count ? atoi(e) : 0; *threads_tail = tt ? atoi(tt) : 512;
         return;
     }
-    if (ctx->gn_tail && count > 6 * sms) {
-        const int rem = count % (6 * sms);
+    if (ctx->gn_tail && count > per_sm * sms) {
+        const int rem = count % (per_sm * sms);
         const int tt = fit(rem);
-        if (rem > 0 && tt > 128) { *n_tail = rem; *threads_tail = tt; }
+        if (rem > 0 && tt > base) { *n_tail = rem; *threads_tail = tt; }
     }
 }
 
@@ -206,7 +219,7 @@ int run_pairs(vsb_tracker* t, Slot& s, const uint8_t* pyr_prev, const uint8_t* p
     // reference modes (identity weights, nearest-pixel lookup, FP64 Gram): gn_track.cu — 8-byte records that name their
     // slots in per-feature back-projection tables, nothing else per point
     const bool tables = fused && ctx->gn_impl == 1 && c.gn.weight_mode == 0 && c.gn.sample_mode == 0 &&
-                        t->feat_cap * 11 <= 4096;
+                        t->feat_cap * 11 <= 4096 && t->principal_point_ok;
     // ... otherwise gn_solve.cu; with identity weights the points are handed over already back-projected, as doubles,
     // in the candidate buffer itself (a double2 is as wide as the float4 row it replaces)
     const int unit = fused && !tables && c.gn.weight_mode == 0;
@@ -217,7 +230,7 @@ int run_pairs(vsb_tracker* t, Slot& s, const uint8_t* pyr_prev, const uint8_t* p
         return rc;
     if (tables) {
         int threads, n_tail, threads_tail;
-        gn_plan(ctx, count, &threads, &n_tail, &threads_tail);
+        gn_plan(ctx, count, t->feat_cap, &threads, &n_tail, &threads_tail);
         const int n_main = count - n_tail;
         ProfScope ps(ctx, VSB_K_GN_SOLVE, st);
         if (n_tail > 0) {
@@ -263,6 +276,9 @@ extern "C" int vsb_tracker_create(vsb_ctx_t* ctx, const vsb_tracker_cfg_t* cfg, 
     const int nf = t->good_cap < VSB_MAX_GN_FEATURES ? t->good_cap : VSB_MAX_GN_FEATURES;
     t->cand_cap = 121 * nf;
     t->feat_cap = nf;
+    t->principal_point_ok = true;
+    for (int l = 0; l < VSB_MAX_LEVELS; l++)
+        if (!(fabsf(t->K[l].cx) >= 9.765625e-4f && fabsf(t->K[l].cy) >= 9.765625e-4f)) t->principal_point_ok = false;
     t->n_slots = 2;
     t->stats = nullptr;
     t->host_h2d_bytes = t->host_d2h_bytes = t->host_chunks = 0;
