@@ -4,18 +4,16 @@
 # usage (from the repo root, on the GPU box):  bash tools/gpu_round_check.sh [outdir]
 OUT=${1:-gpurun_out/check}
 mkdir -p $OUT
-KREGEX='regex:pyramid|knn|mx_|gn_|match_filter|candidates|gather|unpack|gradient'
+KREGEX='regex:pyramid|knn|mx_|gn_|match_filter|candidates|gather|unpack|gradient|l2_'
 python -m pytest tests -m gpu -x -q > $OUT/pytest.log 2>&1; echo "pytest rc=$?" >> $OUT/pytest.log
 python bench.py > $OUT/bench.json 2> $OUT/bench.err; echo "bench rc=$?"
 python bench.py --impl reference --steps 3 --warmup 1 > $OUT/bench_ref.json 2> $OUT/bench_ref.err
-# profiled command = the bench on the full workload, one timed step, small CPU sample
-export VSB_CPU_SAMPLE_PAIRS=4
-export VSB_BENCH_RAW_FRAMES=0     # the profiled command is the headline workload only (no from-raw-frames leg)
-export VSB_BENCH_KNN_VARIANTS=0   # ... and no side-by-side matcher timing
-python bench.py --steps 1 --warmup 1 > $OUT/plain.log 2>&1 && \
-ncu --metrics gpu__time_duration.sum,launch__grid_size --clock-control none -k "$KREGEX" -c 200 --csv --log-file $OUT/launches.csv \
-    python bench.py --steps 1 --warmup 1 > $OUT/ncu_l.log 2>&1
-# steady-state launches of the three dominant kernels (skip the warm-up step's launches)
-ncu --set full --clock-control none --import-source on -k 'regex:gn_solve_kernel|knn2_hamming_mx_bulk_kernel|pyramid16_kernel' \
-    -s 3 -c 3 -o $OUT/prof_top -f python bench.py --steps 1 --warmup 1 > $OUT/ncu_f.log 2>&1
+# profiled command = the headline workload (configs[1]) through the tracker: one warm-up pass + timed passes
+python tools/leg_once.py 1 3 > $OUT/plain.log 2>&1 && \
+ncu --metrics gpu__time_duration.sum,launch__grid_size --clock-control none -k "$KREGEX" -s 7 -c 21 --csv --log-file $OUT/launches.csv \
+    python tools/leg_once.py 1 3 > $OUT/ncu_l.log 2>&1
+python tools/launch_table.py $OUT/launches.csv > $OUT/launches.txt
+# steady-state launches of every kernel of the step (skip the warm-up pass: 7 launches)
+ncu --set full --clock-control none --import-source on -k 'regex:gn_track|mx_bulk|candidates|pyramid16|mx_expand|match_filter' \
+    -s 7 -c 7 -o $OUT/prof_step -f python tools/leg_once.py 1 1 > $OUT/ncu_f.log 2>&1
 tail -3 $OUT/pytest.log

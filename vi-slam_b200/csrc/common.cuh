@@ -9,6 +9,9 @@
 
 #include <vector>
 
+// pixels of a pyramid level whose candidate points the fused candidate pass merges per distinct pixel (gn_track.cu)
+#define VSB_DEDUP_PIX 8192
+
 enum vsb_kernel_id {
     VSB_K_KNN_HAMMING = 0, VSB_K_KNN_UNPACK, VSB_K_MATCH_FILTER, VSB_K_GATHER, VSB_K_PYRAMID, VSB_K_GRADIENT,
     VSB_K_CANDIDATES, VSB_K_GN_SOLVE, VSB_K_KNN_L2, VSB_K_KNN_L2_PREP, VSB_K_GN_PREPARE,
@@ -53,6 +56,7 @@ struct vsb_ctx {
     int gn_variant;   // GN solver register/unroll variant (tuning experiments; 0 = default)
     int gn_impl;      // tracker GN kernel: 1 (default) = gn_track.cu (8-byte point records + back-projection tables, staged coarse levels) for the reference modes, 0 = always gn_solve.cu
     int gn_stage_bytes;   // gn_track.cu: shared-memory budget for the staged current-image level (0 = gather from global memory)
+    int gn_dedup;     // gn_track.cu: 1 (default) = candidate points of small levels are merged per distinct pixel (multiplicity)
     int gn_tail;      // gn_track.cu: 1 (default) = pairs of the last partial wave run with more threads each, 0 = one launch
     int orb_scratch_mb;   // ORB: scratch budget of one chunk of frames in MB (default 8192)
     int pyr_impl;     // pyramid: 0 = generic shared-memory tile kernel, 1 = register-blocked kernel when w, h are multiples of 16

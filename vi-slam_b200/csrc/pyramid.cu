@@ -255,11 +255,14 @@ struct CandParams {
     // points as doubles (VISystem.cpp:1519-1524 with z = 1; bx = backproj_offset(cx, invfx), see se3.cuh), which is all the
     // solver needs of a point
     double2* xy;
-    // ... or (gn_track.cu's form) nothing per point but the record, which then also names the point's slots in the
-    // per-feature back-projection tables: {gx | gy << 16, I_prev | (f * 11 + column) << 8 | (f * 11 + row) << 20}, and
-    // per feature the first column / row of its patch
-    short2* org;
-    int feat_cap;
+    // ... or (gn_track.cu's form, rec_abs) nothing per point but the record, which then also carries the point's column
+    // and row — the solver's back-projection tables are indexed by them: {gx | gy << 16, I_prev | column << 8 | row << 20}.
+    // Levels in dedup_mask (small images, where the patches of different features overlap heavily: level 3 of a 752x480
+    // frame is 94x60 pixels for up to 200 x 121 candidate points) get ONE record per distinct pixel with its multiplicity:
+    // {gx | gy << 16, I_prev | column << 8 | row << 16 | multiplicity << 24}.  n_pts = candidate points before merging.
+    int rec_abs;
+    uint32_t dedup_mask;
+    int32_t* n_pts;
     float bx[VSB_MAX_LEVELS], by[VSB_MAX_LEVELS], invfx[VSB_MAX_LEVELS], invfy[VSB_MAX_LEVELS];
 };
 
@@ -294,8 +297,6 @@ candidates_kernel(const float* __restrict__ good_xy, int good_cap, const int32_t
         const int ni = max(ib - ia + 1, 0), nj = max(jb - ja + 1, 0);
         cnt = ni * nj;
         s_ia[tid] = ia; s_ja[tid] = ja; s_nj[tid] = nj;
-        if (P.org != nullptr && lvl >= P.last_lvl && tid < P.feat_cap)
-            P.org[((size_t)prob * P.levels + lvl) * P.feat_cap + tid] = make_short2((short)ia, (short)ja);
     }
     s_cnt[tid] = cnt;
     // exclusive prefix of the per-feature counts (cnt is 0 from feature nf on): warp scans, then the eight warp totals
@@ -325,6 +326,68 @@ candidates_kernel(const float* __restrict__ good_xy, int good_cap, const int32_t
     const int cols = P.lay.w[lvl], rows = P.lay.h[lvl];
     // one warp per feature: lanes stride over the feature's points (i outer, j inner — reference row order)
     const int warp = tid >> 5, lane = tid & 31;
+    if (P.rec_abs && P.n_pts != nullptr && tid == 0) P.n_pts[(size_t)prob * P.levels + lvl] = total;
+    if (attrs && P.rec_abs && ((P.dedup_mask >> lvl) & 1u)) {
+        // ---- one record per distinct pixel, with its multiplicity -------------------------------------------------
+        __shared__ uint32_t s_mult[VSB_DEDUP_PIX / 4];                  // one byte per pixel (at most 200 features cover it)
+        const int npix = cols * rows, words = (npix + 3) >> 2;
+        for (int k = tid; k < words; k += 256) s_mult[k] = 0u;
+        __syncthreads();
+        for (int f = warp; f < nf; f += 8) {
+            const int c = s_cnt[f], njs = max(s_nj[f], 1), ia = s_ia[f], ja = s_ja[f];
+            for (int p = lane; p < c; p += 32) {
+                const int ii = p / njs, jj = p - ii * njs;
+                const int pix = (ja + jj) * cols + ia + ii;
+                atomicAdd(&s_mult[pix >> 2], 1u << ((pix & 3) * 8));
+            }
+        }
+        __syncthreads();
+        // every thread owns a contiguous span of words; records come out in pixel order
+        const int wspan = (words + 255) >> 8;
+        const int w0 = min(tid * wspan, words), w1 = min(w0 + wspan, words);
+        int mine = 0;
+        for (int w = w0; w < w1; w++) {
+            const uint32_t v = s_mult[w];
+            mine += ((v & 0xFFu) != 0u) + ((v & 0xFF00u) != 0u) + ((v & 0xFF0000u) != 0u) + ((v >> 24) != 0u);
+        }
+        int inc2 = mine;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const int v = __shfl_up_sync(0xFFFFFFFFu, inc2, d);
+            if (lane >= d) inc2 += v;
+        }
+        __syncthreads();                                                  // s_wsum is reused
+        if (lane == 31) s_wsum[warp] = inc2;
+        __syncthreads();
+        int o = inc2 - mine;
+#pragma unroll
+        for (int k = 0; k < 8; k++) o += k < warp ? s_wsum[k] : 0;
+        if (tid == 255) n_cand[(size_t)prob * P.levels + lvl] = o + mine;
+        for (int w = w0; w < w1; w++) {
+            const uint32_t v = s_mult[w];
+            if (v == 0u) continue;
+#pragma unroll
+            for (int b = 0; b < 4; b++) {
+                const uint32_t m = (v >> (8 * b)) & 0xFFu;
+                if (m == 0u) continue;
+                const int pix = 4 * w + b;
+                const int j = pix / cols, i = pix - j * cols;
+                // 0 < i < lw <= cols and 0 < j < lh <= rows: the centre is inside, the neighbours reflect (101) at the border
+                const int xm = i - 1, xp = reflect101(i + 1, cols), ym = j - 1, yp = reflect101(j + 1, rows);
+                const uint8_t* q0 = image1 + (size_t)ym * cols;
+                const uint8_t* q1 = image1 + (size_t)j * cols;
+                const uint8_t* q2 = image1 + (size_t)yp * cols;
+                const int a00 = __ldg(q0 + xm), a01 = __ldg(q0 + i), a02 = __ldg(q0 + xp);
+                const int a10 = __ldg(q1 + xm), a11 = __ldg(q1 + i), a12 = __ldg(q1 + xp);
+                const int a20 = __ldg(q2 + xm), a21 = __ldg(q2 + i), a22 = __ldg(q2 + xp);
+                const int gx = 3 * (3 * (a02 - a00) + 10 * (a12 - a10) + 3 * (a22 - a20));
+                const int gy = 3 * (3 * (a20 - a00) + 10 * (a21 - a01) + 3 * (a22 - a02));
+                pout[o++] = make_uint2(((uint32_t)gx & 0xFFFFu) | ((uint32_t)gy << 16),
+                                       (uint32_t)a11 | (uint32_t)i << 8 | (uint32_t)j << 16 | m << 24);
+            }
+        }
+        return;
+    }
     // the feature's patch plus its one-pixel Scharr apron (<= 13 x 13 bytes) is staged row by row (contiguous bytes per image
     // row) — the points themselves run down the columns, so reading the nine neighbours straight from the image would touch
     // a different row per lane
@@ -364,8 +427,8 @@ candidates_kernel(const float* __restrict__ good_xy, int good_cap, const int32_t
             // (float) of a small non-negative integer without the conversion pipe: 2^23 + n is exact, so is the subtraction
             const float xf = __fsub_rn(__int_as_float(0x4B000000 | (ia + ii)), 8388608.0f);
             const float yf = __fsub_rn(__int_as_float(0x4B000000 | (ja + jj)), 8388608.0f);
-            if (attrs && P.org) {
-                // no per-point coordinates at all: the record carries the table slots
+            if (attrs && P.rec_abs) {
+                // no per-point coordinates beside the record: it carries the column and the row
             } else if (attrs && P.xy) {
                 const float X = __fadd_rn(__fmul_rn(xf, P.invfx[lvl]), P.bx[lvl]);   // * z (= 1) is the identity
                 const float Y = __fadd_rn(__fmul_rn(yf, P.invfy[lvl]), P.by[lvl]);
@@ -385,7 +448,7 @@ candidates_kernel(const float* __restrict__ good_xy, int good_cap, const int32_t
                 const int gx = 3 * (3 * (a02 - a00) + 10 * (a12 - a10) + 3 * (a22 - a20));
                 const int gy = 3 * (3 * (a20 - a00) + 10 * (a21 - a01) + 3 * (a22 - a02));
                 uint32_t tag = (uint32_t)a11;
-                if (P.org) tag |= (uint32_t)(f * 11 + ii) << 8 | (uint32_t)(f * 11 + jj) << 20;
+                if (P.rec_abs) tag |= (uint32_t)(ia + ii) << 8 | (uint32_t)(ja + jj) << 20;
                 pout[off + p] = make_uint2(((uint32_t)gx & 0xFFFFu) | ((uint32_t)gy << 16), tag);
             }
             ii += di;
@@ -481,23 +544,29 @@ extern "C" int vsb_gradient_build(vsb_ctx_t* ctx, const uint8_t* pyr, int count,
 int vsb_candidates_prepare(vsb_ctx_t* ctx, const float* good_xy, int good_cap, const int32_t* n_good, int count, int levels,
                            const int* lw, const int* lh, float* cand, int cand_cap, int32_t* n_cand,
                            const uint8_t* prev_pyr, int64_t pair_stride, const vsb_pyr_layout_t* layout, int first_lvl,
-                           int last_lvl, void* patt, void* xy, const vsb_intr_t* K, void* org, int feat_cap, void* stream) {
-    if (!ctx || !good_xy || !n_good || (!cand && !org) || !n_cand || !lw || !lh) return VSB_ERR_INVALID;
-    if (org && (!prev_pyr || !layout || !patt || feat_cap < 1)) return VSB_ERR_INVALID;
+                           int last_lvl, void* patt, void* xy, const vsb_intr_t* K, int rec_abs, uint32_t dedup_mask,
+                           int32_t* n_pts, void* stream) {
+    if (!ctx || !good_xy || !n_good || (!cand && !rec_abs) || !n_cand || !lw || !lh) return VSB_ERR_INVALID;
+    if (rec_abs && (!prev_pyr || !layout || !patt)) return VSB_ERR_INVALID;
     if (levels < 1 || levels > VSB_MAX_LEVELS || count < 0 || cand_cap < 0) return VSB_ERR_INVALID;
     if (count == 0) return VSB_OK;
     CandParams P;
     P.levels = levels;
     for (int l = 0; l < levels; l++) { P.lw[l] = lw[l]; P.lh[l] = lh[l]; }
     P.prev_pyr = nullptr; P.pair_stride = 0; P.first_lvl = -1; P.last_lvl = 0; P.patt = nullptr; P.xy = nullptr;
-    P.org = nullptr; P.feat_cap = 0;
+    P.rec_abs = 0; P.dedup_mask = 0u; P.n_pts = nullptr;
     for (int l = 0; l < VSB_MAX_LEVELS; l++) { P.bx[l] = P.by[l] = 0.f; P.invfx[l] = P.invfy[l] = 0.f; }
     memset(&P.lay, 0, sizeof(P.lay));
     if (prev_pyr && layout && patt) {
         P.prev_pyr = prev_pyr; P.pair_stride = pair_stride; P.lay = *layout;
         P.first_lvl = first_lvl; P.last_lvl = last_lvl; P.patt = reinterpret_cast<uint2*>(patt);
-        if (org) {
-            P.org = reinterpret_cast<short2*>(org); P.feat_cap = feat_cap;
+        if (rec_abs) {
+            P.rec_abs = 1; P.n_pts = n_pts;
+            for (int l = 0; l < levels; l++)      // records hold 12-bit columns / rows; merged levels 8-bit ones and a byte map
+                if (layout->w[l] > 4095 || layout->h[l] > 4095) return VSB_ERR_UNSUPPORTED;
+            for (int l = 0; l < levels; l++)
+                if (((dedup_mask >> l) & 1u) && layout->w[l] <= 255 && layout->h[l] <= 255 && layout->w[l] * layout->h[l] <= VSB_DEDUP_PIX)
+                    P.dedup_mask |= 1u << l;
         } else if (xy && K) {
             P.xy = reinterpret_cast<double2*>(xy);
             for (int l = 0; l < VSB_MAX_LEVELS; l++) {
@@ -518,6 +587,6 @@ extern "C" int vsb_candidates_build(vsb_ctx_t* ctx, const float* good_xy, int go
                                     int count, int levels, const int* lw, const int* lh, float* cand, int cand_cap,
                                     int32_t* n_cand, void* stream) {
     return vsb_candidates_prepare(ctx, good_xy, good_cap, n_good, count, levels, lw, lh, cand, cand_cap, n_cand, nullptr, 0,
-                                  nullptr, 0, 0, nullptr, nullptr, nullptr, nullptr, 0, stream);
+                                  nullptr, 0, 0, nullptr, nullptr, nullptr, 0, 0u, nullptr, stream);
 }
 

@@ -23,9 +23,10 @@ int vsb_match_filter_keys(vsb_ctx_t* ctx, const void* keys12, const void* keys21
 int vsb_candidates_prepare(vsb_ctx_t* ctx, const float* good_xy, int good_cap, const int32_t* n_good, int count, int levels,
                            const int* lw, const int* lh, float* cand, int cand_cap, int32_t* n_cand,
                            const uint8_t* prev_pyr, int64_t pair_stride, const vsb_pyr_layout_t* layout, int first_lvl,
-                           int last_lvl, void* patt, void* xy, const vsb_intr_t* K, void* org, int feat_cap, void* stream);
+                           int last_lvl, void* patt, void* xy, const vsb_intr_t* K, int rec_abs, uint32_t dedup_mask,
+                           int32_t* n_pts, void* stream);
 int vsb_gn_track(vsb_ctx_t* ctx, const uint8_t* cur_pyr, int64_t pair_stride_pixels, const vsb_pyr_layout_t* layout,
-                 const void* patt, const void* org, const int32_t* n_cand, const int32_t* n_good, int cand_cap, int feat_cap,
+                 const void* patt, const int32_t* n_cand, const int32_t* n_pts, uint32_t dedup_mask, int cand_cap,
                  const vsb_intr_t K[VSB_MAX_LEVELS], const float* pose_in, const vsb_gn_opts_t* opts, int pair0, int count,
                  int threads, float* pose_out, vsb_gn_trace_t* trace, int32_t* n_trace, unsigned long long* stats,
                  void* stream);
@@ -59,7 +60,7 @@ struct Slot {
     float* cand = nullptr;
     uint2* patt = nullptr;        // per-point attributes of the solver, [max_pairs][levels][cand_cap]
     int32_t* n_cand = nullptr;
-    short2* org = nullptr;        // first column / row of every feature's patch, [max_pairs][levels][feat_cap] (gn_track.cu)
+    int32_t* n_pts = nullptr;     // candidate points per level before merging, [max_pairs][levels] (gn_track.cu)
     float* pose = nullptr;
     float* orb_resp = nullptr;    // [max_pairs + 1][n_feat] each, allocated on the first vsb_track_sequence_orb call
     float* orb_angle = nullptr;
@@ -127,7 +128,7 @@ int slot_alloc(vsb_tracker* t, Slot& s) {
     A(cand, P * VSB_MAX_LEVELS * (size_t)t->cand_cap * 4);
     A(patt, P * VSB_MAX_LEVELS * (size_t)t->cand_cap);
     A(n_cand, P * VSB_MAX_LEVELS);
-    A(org, P * VSB_MAX_LEVELS * (size_t)t->feat_cap);
+    A(n_pts, P * VSB_MAX_LEVELS);
     A(pose, P * 7);
 #undef A
     VSB_CUDA(ctx, cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
@@ -139,7 +140,7 @@ int slot_alloc(vsb_tracker* t, Slot& s) {
 }
 
 void slot_free(Slot& s) {
-    void* ptrs[] = {s.pyr, s.gx, s.gy, s.desc, s.kp, s.n_feat, s.prior, s.key12, s.key21, s.good_q, s.good_t, s.good_d, s.n_good, s.n_sym, s.good_xy, s.cand, s.patt, s.n_cand, s.org, s.pose, s.orb_resp, s.orb_angle, s.stage, s.desc2, s.n_feat2};
+    void* ptrs[] = {s.pyr, s.gx, s.gy, s.desc, s.kp, s.n_feat, s.prior, s.key12, s.key21, s.good_q, s.good_t, s.good_d, s.n_good, s.n_sym, s.good_xy, s.cand, s.patt, s.n_cand, s.n_pts, s.pose, s.orb_resp, s.orb_angle, s.stage, s.desc2, s.n_feat2};
     for (void* p : ptrs) if (p) cudaFree(p);
     if (s.stream) cudaStreamDestroy(s.stream);
     if (s.done) cudaEventDestroy(s.done);
@@ -219,14 +220,16 @@ int run_pairs(vsb_tracker* t, Slot& s, const uint8_t* pyr_prev, const uint8_t* p
     // reference modes (identity weights, nearest-pixel lookup, FP64 Gram): gn_track.cu — 8-byte records that name their
     // slots in per-feature back-projection tables, nothing else per point
     const bool tables = fused && ctx->gn_impl == 1 && c.gn.weight_mode == 0 && c.gn.sample_mode == 0 &&
-                        t->feat_cap * 11 <= 4096 && t->principal_point_ok;
+                        t->principal_point_ok && t->lay.w[0] <= 4095 && t->lay.h[0] <= 4095;
+    // levels whose candidate points are merged per distinct pixel: every level small enough for the candidate pass's byte map
+    const uint32_t dedup_mask = (tables && ctx->gn_dedup && ctx->gn_variant != 1) ? 0xFFFFFFFFu : 0u;
     // ... otherwise gn_solve.cu; with identity weights the points are handed over already back-projected, as doubles,
     // in the candidate buffer itself (a double2 is as wide as the float4 row it replaces)
     const int unit = fused && !tables && c.gn.weight_mode == 0;
     if ((rc = vsb_candidates_prepare(ctx, s.good_xy, t->good_cap, s.n_good, count, t->lay.levels, t->lw, t->lh, s.cand,
                                      t->cand_cap, s.n_cand, fused ? pyr_prev : nullptr, t->lay.frame_stride, &t->lay,
                                      c.gn.first_lvl, c.gn.last_lvl, fused ? s.patt : nullptr, unit ? (void*)s.cand : nullptr,
-                                     t->K, tables ? (void*)s.org : nullptr, t->feat_cap, st)))
+                                     t->K, tables ? 1 : 0, dedup_mask, s.n_pts, st)))
         return rc;
     if (tables) {
         int threads, n_tail, threads_tail;
@@ -237,12 +240,12 @@ int run_pairs(vsb_tracker* t, Slot& s, const uint8_t* pyr_prev, const uint8_t* p
             VSB_CUDA(ctx, cudaEventRecord(s.fork, st));
             VSB_CUDA(ctx, cudaStreamWaitEvent(s.aux, s.fork, 0));
         }
-        if ((rc = vsb_gn_track(ctx, pyr_cur, t->lay.frame_stride, &t->lay, s.patt, s.org, s.n_cand, s.n_good, t->cand_cap,
-                               t->feat_cap, t->K, prior, &c.gn, 0, n_main, threads, pose_out, t->trace, t->n_trace, t->stats, st)))
+        if ((rc = vsb_gn_track(ctx, pyr_cur, t->lay.frame_stride, &t->lay, s.patt, s.n_cand, s.n_pts, dedup_mask, t->cand_cap,
+                               t->K, prior, &c.gn, 0, n_main, threads, pose_out, t->trace, t->n_trace, t->stats, st)))
             return rc;
         if (n_tail > 0) {
-            if ((rc = vsb_gn_track(ctx, pyr_cur, t->lay.frame_stride, &t->lay, s.patt, s.org, s.n_cand, s.n_good, t->cand_cap,
-                                   t->feat_cap, t->K, prior, &c.gn, n_main, n_tail, threads_tail, pose_out, t->trace,
+            if ((rc = vsb_gn_track(ctx, pyr_cur, t->lay.frame_stride, &t->lay, s.patt, s.n_cand, s.n_pts, dedup_mask, t->cand_cap,
+                                   t->K, prior, &c.gn, n_main, n_tail, threads_tail, pose_out, t->trace,
                                    t->n_trace, t->stats, s.aux)))
                 return rc;
             VSB_CUDA(ctx, cudaEventRecord(s.join, s.aux));
