@@ -217,16 +217,19 @@ def ref_units_timing(seq, cfg, n_pairs):
         eye = np.eye(3, dtype=np.float32)
         t0 = time.perf_counter()
         poses = []
+        oob = 0
         for k in range(n_pairs):
             r = rv.track_pair(seq["frames"][k], seq["frames"][k + 1], K4, eye, seq["R_imu_res"][k], seq["t_res"][k],
                               kp_prev=seq["kp"][k], desc_prev=seq["desc"][k], kp_cur=seq["kp"][k + 1],
                               desc_cur=seq["desc"][k + 1], n_cells=cfg["n_cells"])
             poses.append(r["pose"].copy())
+            oob += int(r["oob_reads"] > 0)
         dt = time.perf_counter() - t0
         return {"value": n_pairs / dt, "unit": "frames/s", "cores": 1, "kind": "reference",
                 "sample": f"first {n_pairs} frame pairs of the same sequence ({dt:.1f}s): the reference's own src/*.cpp "
                           "(oracle/_ref/libref_visystem.so) against the OpenCV stand-in oracle/refshim — an upper bound on "
                           "its CPU time, see bench.py ref_units_timing",
+                "pairs_with_out_of_bounds_reads_upstream": oob,      # parity is defined for runs without them
                 "poses": np.stack(poses)}
     except Exception as e:      # informational
         return {"error": str(e), "kind": "reference"}

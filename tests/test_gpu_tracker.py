@@ -228,23 +228,34 @@ def test_tracker_solver_per_iteration(ctx, oracle, n_cells, threads, stage):
         ctx.option("gn_stage_bytes", 8192)
 
 
-def test_tracker_solver_matches_general_kernel(ctx):
-    """gn_track.cu and gn_solve.cu give the same bits for the same pairs (gn_impl 1 / 0)."""
+@pytest.mark.parametrize("n_cells", [49, 225])
+def test_tracker_solver_matches_general_kernel(ctx, n_cells):
+    """gn_track.cu (with and without merging coincident candidate points, with the Gram matrix on the FP64 tensor cores or
+    in registers) and gn_solve.cu give the same bits for the same pairs."""
     import torch
     from vislam_b200 import synth
-    pairs = [synth.make_pair(n_feat=400, seed=s) for s in (31, 32, 33, 34)]
+    pairs = [synth.make_pair(n_feat=600, seed=s) for s in (31, 32, 33, 34)]
     st = lambda k: torch.from_numpy(np.stack([p[k] for p in pairs])).cuda()
     out = []
-    for impl in (1, 0):
+    for impl, dedup, variant in ((1, 1, 0), (1, 0, 0), (1, 0, 1), (0, 0, 0)):
         ctx.option("gn_impl", impl)
+        ctx.option("gn_dedup", dedup)
+        ctx.option("gn_variant", variant)
         try:
-            tr = ctx.tracker(752, 480, 400, pairs[0]["K"], n_cells=49, max_pairs=4)
+            tr = ctx.tracker(752, 480, 600, pairs[0]["K"], n_cells=n_cells, max_pairs=4)
             pose, _ = tr.track_pairs(st("prev"), st("cur"), st("d1"), st("d2"), st("kp1"), st("pose_prior"))
             out.append(pose.cpu().numpy())
+            stats = tr.stats()
             tr.close()
         finally:
             ctx.option("gn_impl", 1)
-    np.testing.assert_array_equal(out[0], out[1])
+            ctx.option("gn_dedup", 1)
+            ctx.option("gn_variant", 0)
+        if len(out) > 1:
+            np.testing.assert_array_equal(out[0], out[-1])
+            assert stats == first_stats          # the work counters count candidate points before merging
+        else:
+            first_stats = stats
 
 
 def test_tracker_tail_launch_same_bits(ctx):
