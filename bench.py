@@ -286,8 +286,13 @@ def run_reference(args, rank, world):
     cfg = base_config(world)
     if n_frames != N_FRAMES:
         cfg["frames"], cfg["pairs_per_step"] = n_frames, n_pairs
+    try:        # what native code this process mapped: the oracle libraries only
+        maps = sorted({ln.split()[-1] for ln in open("/proc/self/maps") if ".so" in ln and ROOT in ln})
+        native = [os.path.relpath(m, ROOT) for m in maps]
+    except Exception:
+        native = None
     print(json.dumps({
-        "impl": "reference", "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": args.gpus,
+        "impl": "reference", "native_libraries_of_this_repo_loaded": native, "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": DTYPE, "data": "synthetic", "config": cfg,
         "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port", "sample": sample,
