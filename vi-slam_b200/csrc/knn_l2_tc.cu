@@ -64,6 +64,9 @@ __device__ __forceinline__ unsigned long long l2_key(double s, uint32_t idx) {
 
 // ---- stage 0 ---------------------------------------------------------------------------------------------
 // prep[desc] = {h1, h2, h3, |b|} with h1 + h2 + h3 = -|b|^2 / 2 (each piece exact in TF32); nmax[prob*2 + set] = max |b|.
+// Eight lanes per descriptor: a lane sums the squares of its float4 chunks (chunk c belongs to lane c % 8, so the eight
+// lanes of a descriptor read 128 contiguous bytes per step), the partial sums meet in an xor tree.  The norm only feeds the
+// candidate SELECTION and an upper bound — exactness comes from the re-check — so the summation order is free.
 __global__ void __launch_bounds__(256)
 l2_prep_kernel(const float* __restrict__ d1, int n1_max, const int32_t* __restrict__ n1_arr,
                const float* __restrict__ d2, int n2_max, const int32_t* __restrict__ n2_arr, int dim,
@@ -72,12 +75,20 @@ l2_prep_kernel(const float* __restrict__ d1, int n1_max, const int32_t* __restri
     const int n_max = set ? n2_max : n1_max;
     const int32_t* n_arr = set ? n2_arr : n1_arr;
     const int n = n_arr ? min(n_arr[prob], n_max) : n_max;
-    const int i = blockIdx.x * 256 + threadIdx.x;
+    const int i = blockIdx.x * 32 + (threadIdx.x >> 3), sub = threadIdx.x & 7;
     float norm = 0.f;
+    double s = 0.0;
     if (i < n) {
-        const float* v = (set ? d2 : d1) + ((size_t)prob * n_max + i) * dim;
-        double s = 0.0;
-        for (int k = 0; k < dim; k++) { const double x = (double)__ldg(v + k); s = __fma_rn(x, x, s); }
+        const float4* v = reinterpret_cast<const float4*>((set ? d2 : d1) + ((size_t)prob * n_max + i) * dim);
+        for (int c = sub; c < (dim >> 2); c += 8) {
+            const float4 x = __ldg(v + c);
+            s = __fma_rn((double)x.x, (double)x.x, s); s = __fma_rn((double)x.y, (double)x.y, s);
+            s = __fma_rn((double)x.z, (double)x.z, s); s = __fma_rn((double)x.w, (double)x.w, s);
+        }
+    }
+#pragma unroll
+    for (int off = 1; off < 8; off <<= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+    if (i < n && sub == 0) {
         const double h = -0.5 * s;
         const float h1 = tf32_trunc((float)h);
         const double r1 = h - (double)h1;
@@ -493,7 +504,7 @@ int vsb_knn2_l2_tc(vsb_ctx* ctx, const float* d1, int n1_max, const int32_t* n1,
         if (n2) Q.n2_arr += z0;
         {
             ProfScope ps(ctx, VSB_K_KNN_L2_PREP, st);
-            l2_prep_kernel<<<dim3(vsb_div_up(n_big, 256), 2, zc), 256, 0, st>>>(
+            l2_prep_kernel<<<dim3(vsb_div_up(n_big, 32), 2, zc), 256, 0, st>>>(
                 Q.d1, n1_max, Q.n1_arr, Q.d2, n2_max, Q.n2_arr, dim, const_cast<float4*>(Q.prep1),
                 const_cast<float4*>(Q.prep2), nmax + (size_t)z0 * 2);
             VSB_LAUNCHED(ctx);

@@ -38,23 +38,30 @@ pyramid_kernel(const uint8_t* __restrict__ img, long long img_stride, int pitch,
     const int tid = threadIdx.x;
     const int w0 = L.w[0], h0 = L.h[0];
 
-    // level 0: load the tile (16 bytes per thread when aligned), copy it out unless it is in place
+    // level 0: load the tile (16 bytes per thread when rows are 16-byte aligned; otherwise byte by byte with consecutive
+    // threads on consecutive bytes, so a warp's access is one contiguous run), copy it out unless it is in place
     {
-        const int ty = tid >> 2, tx = (tid & 3) * 16;
-        const int gy = y0 + ty, gx = x0 + tx;
         const bool vec_ok = ((in_pitch & 15) == 0) && ((w0 & 15) == 0) && ((((size_t)in) & 15) == 0);
-        if (gy < h0 && gx + 15 < w0 && vec_ok) {
-            uint4 v = __ldg(reinterpret_cast<const uint4*>(in + (size_t)gy * in_pitch + gx));
+        if (vec_ok) {
+            const int ty = tid >> 2, tx = (tid & 3) * 16;
+            const int gy = y0 + ty, gx = x0 + tx;
+            uint4 v = make_uint4(0u, 0u, 0u, 0u);
+            if (gy < h0 && gx + 15 < w0) {
+                v = __ldg(reinterpret_cast<const uint4*>(in + (size_t)gy * in_pitch + gx));
+                if (img) *reinterpret_cast<uint4*>(out + (size_t)gy * w0 + gx) = v;
+            }
             *reinterpret_cast<uint4*>(&s[0][ty * PT + tx]) = v;
-            if (img) *reinterpret_cast<uint4*>(out + (size_t)gy * w0 + gx) = v;
         } else {
-            for (int k = 0; k < 16; k++) {
+#pragma unroll 4
+            for (int i = tid; i < PT * PT; i += 256) {
+                const int ty = i >> 6, tx = i & 63;
+                const int gy = y0 + ty, gx = x0 + tx;
                 uint8_t v = 0;
-                if (gy < h0 && gx + k < w0) {
-                    v = __ldg(in + (size_t)gy * in_pitch + gx + k);
-                    if (img) out[(size_t)gy * w0 + gx + k] = v;
+                if (gy < h0 && gx < w0) {
+                    v = __ldg(in + (size_t)gy * in_pitch + gx);
+                    if (img) out[(size_t)gy * w0 + gx] = v;
                 }
-                s[0][ty * PT + tx + k] = v;
+                s[0][i] = v;
             }
         }
     }
