@@ -589,7 +589,7 @@ def leg_single_pair(g, steps):
            "gn_iterations": stats["iterations"] / max(1, stats["pairs"]), "gn_points": stats["point_visits"] / max(1, stats["pairs"]),
            "roofline": {"kernel": "gn_solve", "bound": "latency", "achieved": visit_b / (gn_us * 1e-6) / 1e9, "peak": g.hbm_peak,
                         "unit": "GB/s", "frac": visit_b / (gn_us * 1e-6) / 1e9 / g.hbm_peak, "peak_source": g.hbm_src, "traffic": None,
-                        "note": "a single pair is one thread block (1024 threads) running ~20 serial Gauss-Newton iterations: "
+                        "note": "a single pair is one cluster of 8 thread blocks (4096 threads, partial sums exchanged through distributed shared memory) running its serial Gauss-Newton iterations: "
                                 "latency-bound by construction (SURVEY 8d: report achieved bandwidth and wall time, claim a "
                                 "roofline fraction only for the batched configs)"},
            "cpu_baseline": {"value": best * 1e6, "unit": "us per frame pair", "cores": 1, "kind": "port",

@@ -49,6 +49,9 @@ int vsb_ctx_destroy(vsb_ctx_t* ctx);
  * with the packed 16x2 epilogue; "gn_threads" = threads per frame pair of the GN solver, 64 / 128 / 256 / 512 / 1024 ((0) = chosen from the
  * batch size); "gn_impl" = (1) the tracker solves reference-mode problems with gn_track.cu, 0 = always gn_solve.cu;
  * "gn_stage_bytes" = shared-memory budget for the staged current-image level of gn_track.cu ((8192); 0 = none);
+ * "gn_cluster" = (1) a batch of fewer frame pairs than 0.7 x the SMs gives each pair a thread-block cluster of 2 / 4 / 8
+ *   blocks that share the sweep and exchange partial sums through distributed shared memory; 0 = never, 2 / 4 / 8 = always
+ *   that size.  "gn_cluster_threads" = (0: by batch size) | 256 | 512 threads per block of that kernel.
  * "gn_tail" = (1) the pairs of the last partial wave of a large batch get more threads each, 0 = one launch.
  * Results are identical for every setting. */
 int vsb_ctx_option(vsb_ctx_t* ctx, const char* name, int value);
@@ -227,6 +230,9 @@ int vsb_gn_solve(vsb_ctx_t* ctx, const uint8_t* prev_pyr, const uint8_t* cur_pyr
 /* VISystem::WarpFunctionSE3 (VISystem.cpp:1495-1558) on its own: pts/out are n x 4 f32 rows (x, y, z, 1). */
 int vsb_warp_se3(vsb_ctx_t* ctx, const float* pts, int n, const float pose[7], const vsb_intr_t* K, float* out,
                  void* stream);
+/* The pose update of a GN iteration, batched on the device: out[i] = pose[i] * exp(delta[i]) (VISystem.cpp:1421;
+ * se3.hpp:723-742, 285-321).  pose / out: n x 7 f32 {qx,qy,qz,qw,tx,ty,tz}, delta: n x 6 f32 (upsilon, omega); device. */
+int vsb_se3_update_batch(vsb_ctx_t* ctx, const float* pose, const float* delta, int n, float* out, void* stream);
 /* Sophus SE3f::exp (se3.hpp:723-742) and SE3f::matrix (se3.hpp:253-268, row-major 4x4).  Host-side. */
 int vsb_se3_exp(const float delta[6], float pose[7]);
 /* Sophus SE3f(rotation matrix, translation) (so3.hpp:422-427 -> Eigen Quaternion(Matrix3)); r row-major. Host-side. */

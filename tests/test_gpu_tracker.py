@@ -228,6 +228,42 @@ def test_tracker_solver_per_iteration(ctx, oracle, n_cells, threads, stage):
         ctx.option("gn_stage_bytes", 8192)
 
 
+@pytest.mark.parametrize("n_cells,cluster,cthreads,stage", [(49, 1, 512, 8192), (49, 2, 256, 0), (49, 4, 512, 32768),
+                                                            (49, 8, 256, 8192), (225, 1, 512, 8192), (225, 8, 256, 0),
+                                                            (225, 2, 512, 32768), (225, 4, 256, 8192)])
+def test_tracker_solver_cluster_per_iteration(ctx, oracle, n_cells, cluster, cthreads, stage):
+    """Small batches: one frame pair per thread-block cluster (gn_track.cu, CLUSTER kernels — partial Gram matrices summed
+    out of the peers' shared memory, pose pushed back into it) against the oracle PER ITERATION, for every cluster size,
+    both block sizes, with / without the staged level; and the same bits as the one-block-per-pair kernel."""
+    import torch
+    from vislam_b200 import synth
+    pairs = [synth.make_pair(n_feat=400, seed=s) for s in (1001, 1777, 4242)]
+    st = lambda k: torch.from_numpy(np.stack([p[k] for p in pairs])).cuda()
+    ctx.option("gn_stage_bytes", stage)
+    try:
+        out = {}
+        for cl in (cluster, 0):
+            ctx.option("gn_cluster", cl)
+            ctx.option("gn_cluster_threads", cthreads)
+            tr = ctx.tracker(752, 480, 400, pairs[0]["K"], n_cells=n_cells, max_pairs=3)
+            tr.trace_on()
+            pose, n_good = tr.track_pairs(st("prev"), st("cur"), st("d1"), st("d2"), st("kp1"), st("pose_prior"))
+            out[cl] = (pose.cpu().numpy(), tr.traces(len(pairs)), tr.stats())
+            tr.close()
+        from test_gpu_gn import compare_traces
+        pose, traces, stats = out[cluster]
+        for b, p in enumerate(pairs):
+            ref = oracle.track_pair(p["prev"], p["cur"], p["d1"], p["d2"], p["kp1"], p["K"], p["pose_prior"], n_cells=n_cells)
+            compare_traces(traces[b], ref["trace"])
+            np.testing.assert_array_equal(pose[b], ref["pose"])
+        np.testing.assert_array_equal(pose, out[0][0])
+        assert stats == out[0][2]
+    finally:
+        ctx.option("gn_cluster", 1)
+        ctx.option("gn_cluster_threads", 0)
+        ctx.option("gn_stage_bytes", 8192)
+
+
 @pytest.mark.parametrize("n_cells", [49, 225])
 def test_tracker_solver_matches_general_kernel(ctx, n_cells):
     """gn_track.cu (with and without merging coincident candidate points, with the Gram matrix on the FP64 tensor cores or

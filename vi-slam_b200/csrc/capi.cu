@@ -54,6 +54,8 @@ extern "C" int vsb_ctx_create(int device, vsb_ctx_t** out) {
     c->gn_stage_bytes = 8192;
     c->gn_tail = 1;
     c->gn_dedup = 1;
+    c->gn_cluster = 1;
+    c->gn_cluster_threads = 0;
     c->orb_scratch_mb = 8192;
     c->knn_l2_impl = 1;
     if (const char* e = getenv("VSB_KNN_L2_IMPL")) c->knn_l2_impl = atoi(e) ? 1 : 0;
@@ -63,6 +65,8 @@ extern "C" int vsb_ctx_create(int device, vsb_ctx_t** out) {
     if (const char* e = getenv("VSB_GN_STAGE_BYTES")) vsb_ctx_option(c, "gn_stage_bytes", atoi(e));
     if (const char* e = getenv("VSB_GN_TAIL")) c->gn_tail = atoi(e) ? 1 : 0;
     if (const char* e = getenv("VSB_GN_DEDUP")) c->gn_dedup = atoi(e) ? 1 : 0;
+    if (const char* e = getenv("VSB_GN_CLUSTER")) vsb_ctx_option(c, "gn_cluster", atoi(e));
+    if (const char* e = getenv("VSB_GN_CLUSTER_THREADS")) vsb_ctx_option(c, "gn_cluster_threads", atoi(e));
     if (const char* e = getenv("VSB_ORB_SCRATCH_MB")) vsb_ctx_option(c, "orb_scratch_mb", atoi(e));
     if (const char* e = getenv("VSB_GN_THREADS")) vsb_ctx_option(c, "gn_threads", atoi(e));
     *out = c;
@@ -94,6 +98,16 @@ extern "C" int vsb_ctx_option(vsb_ctx_t* ctx, const char* name, int value) {
     if (!strcmp(name, "gn_dedup")) {
         if (value < 0 || value > 1) return VSB_ERR_INVALID;
         ctx->gn_dedup = value;
+        return VSB_OK;
+    }
+    if (!strcmp(name, "gn_cluster")) {
+        if (value != 0 && value != 1 && value != 2 && value != 4 && value != 8) return VSB_ERR_INVALID;
+        ctx->gn_cluster = value;
+        return VSB_OK;
+    }
+    if (!strcmp(name, "gn_cluster_threads")) {
+        if (value != 0 && value != 256 && value != 512) return VSB_ERR_INVALID;
+        ctx->gn_cluster_threads = value;
         return VSB_OK;
     }
     if (!strcmp(name, "gn_tail")) {

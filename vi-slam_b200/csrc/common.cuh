@@ -57,6 +57,8 @@ struct vsb_ctx {
     int gn_impl;      // tracker GN kernel: 1 (default) = gn_track.cu (8-byte point records + back-projection tables, staged coarse levels) for the reference modes, 0 = always gn_solve.cu
     int gn_stage_bytes;   // gn_track.cu: shared-memory budget for the staged current-image level (0 = gather from global memory)
     int gn_dedup;     // gn_track.cu: 1 (default) = candidate points of small levels are merged per distinct pixel (multiplicity)
+    int gn_cluster;   // gn_track.cu: 1 (default) = a batch of fewer pairs than 0.7 x the SMs gives each pair a cluster of 2 / 4 / 8 blocks (by batch size); 0 = never; 2 / 4 / 8 = that size always
+    int gn_cluster_threads;   // threads per block of the cluster kernel: 0 (default) = by batch size, 256, 512
     int gn_tail;      // gn_track.cu: 1 (default) = pairs of the last partial wave run with more threads each, 0 = one launch
     int orb_scratch_mb;   // ORB: scratch budget of one chunk of frames in MB (default 8192)
     int pyr_impl;     // pyramid: 0 = generic shared-memory tile kernel, 1 = register-blocked kernel when w, h are multiples of 16

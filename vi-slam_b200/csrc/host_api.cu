@@ -105,6 +105,31 @@ extern "C" int vsb_se3_matrix(const float pose[7], float m[16]) {
     return VSB_OK;
 }
 
+// ---- the pose update of a Gauss-Newton iteration as a batched device operation -----------------------------
+// out[i] = pose[i] * exp(delta[i])  (VISystem.cpp:1421; se3.hpp:723-742 exp, :285-321 operator*): the same device functions
+// the solver kernels call, exposed so that they can be checked by the million against the host helpers / the oracle.
+namespace {
+__global__ void __launch_bounds__(256) se3_update_kernel(const float* __restrict__ pose, const float* __restrict__ delta, int n,
+                                                          float* __restrict__ out) {
+    const int i = blockIdx.x * 256 + threadIdx.x;
+    if (i >= n) return;
+    float a[7], d[6], e[7], r[7];
+    for (int k = 0; k < 7; k++) a[k] = pose[(size_t)i * 7 + k];
+    for (int k = 0; k < 6; k++) d[k] = delta[(size_t)i * 6 + k];
+    vsb::se3_exp(d, e);
+    vsb::se3_mul(a, e, r);
+    for (int k = 0; k < 7; k++) out[(size_t)i * 7 + k] = r[k];
+}
+}  // namespace
+
+extern "C" int vsb_se3_update_batch(vsb_ctx_t* ctx, const float* pose, const float* delta, int n, float* out, void* stream) {
+    if (!ctx || n < 0 || (n && (!pose || !delta || !out))) return VSB_ERR_INVALID;
+    if (n == 0) return VSB_OK;
+    se3_update_kernel<<<vsb_div_up(n, 256), 256, 0, (cudaStream_t)stream>>>(pose, delta, n, out);
+    VSB_LAUNCHED(ctx);
+    return VSB_OK;
+}
+
 // ---- WarpFunctionSE3 as a stand-alone operation ------------------------------------------------------------
 namespace {
 struct WarpParams {

@@ -38,8 +38,45 @@ namespace vsb {
 
 constexpr float kSophusEps = 1e-5f;
 
+#if defined(__CUDA_ARCH__)
+// Device: for |x| <= 0.5 (every Gauss-Newton update is far inside) the double sine / cosine is a Taylor polynomial in Horner
+// form with fused multiply-adds — 10 dependent FP64 operations instead of libdevice's argument reduction + kernel (~5x the
+// latency, and the pose update is the serial part of every iteration).  Truncation error < 2e-23, evaluation error
+// 2.3e-16 relative; checked on the CPU (same operation sequence, fma()) for EVERY float in [0, 0.5] — 1 056 964 609 values —
+// against (float) sin((double) x) / (float) cos((double) x) of glibc: no result differs, so on this range the device
+// returns the host's bits by construction (tests/test_gpu_se3.py repeats the sweep on the device).  Odd / even symmetry of
+// the polynomials covers negative arguments exactly.  Larger arguments take libdevice's double functions as before.
+VSB_HD double sin_small(double x) {
+    const double z = __dmul_rn(x, x);
+    double p = -1.0 / 355687428096000.0;                 // -1/17!
+    p = __fma_rn(p, z, 1.0 / 1307674368000.0);           //  1/15!
+    p = __fma_rn(p, z, -1.0 / 6227020800.0);             // -1/13!
+    p = __fma_rn(p, z, 1.0 / 39916800.0);                //  1/11!
+    p = __fma_rn(p, z, -1.0 / 362880.0);                 // -1/9!
+    p = __fma_rn(p, z, 1.0 / 5040.0);
+    p = __fma_rn(p, z, -1.0 / 120.0);
+    p = __fma_rn(p, z, 1.0 / 6.0);
+    return __fma_rn(__dmul_rn(x, z), -p, x);
+}
+VSB_HD double cos_small(double x) {
+    const double z = __dmul_rn(x, x);
+    double p = 1.0 / 6402373705728000.0;                 //  1/18!
+    p = __fma_rn(p, z, -1.0 / 20922789888000.0);         // -1/16!
+    p = __fma_rn(p, z, 1.0 / 87178291200.0);             //  1/14!
+    p = __fma_rn(p, z, -1.0 / 479001600.0);              // -1/12!
+    p = __fma_rn(p, z, 1.0 / 3628800.0);                 //  1/10!
+    p = __fma_rn(p, z, -1.0 / 40320.0);
+    p = __fma_rn(p, z, 1.0 / 720.0);
+    p = __fma_rn(p, z, -1.0 / 24.0);
+    p = __fma_rn(p, z, 0.5);
+    return __fma_rn(-z, p, 1.0);
+}
+VSB_HD float sin_cr(float x) { return fabsf(x) <= 0.5f ? (float)sin_small((double)x) : (float)sin((double)x); }
+VSB_HD float cos_cr(float x) { return fabsf(x) <= 0.5f ? (float)cos_small((double)x) : (float)cos((double)x); }
+#else
 VSB_HD float sin_cr(float x) { return (float)sin((double)x); }
 VSB_HD float cos_cr(float x) { return (float)cos((double)x); }
+#endif
 
 // q = {x, y, z, w}
 VSB_HD void quat_to_rot(const float* q, float* R) {

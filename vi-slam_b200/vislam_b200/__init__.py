@@ -60,7 +60,7 @@ EXPORTS = [
     "vsb_malloc", "vsb_free", "vsb_host_alloc", "vsb_host_free", "vsb_upload", "vsb_upload_2d", "vsb_download",
     "vsb_copy", "vsb_memset", "vsb_stream_create", "vsb_stream_destroy", "vsb_stream_sync",
     "vsb_nn_filter", "vsb_sym_matches", "vsb_sort_keys", "vsb_grid_best", "vsb_warp_se3", "vsb_se3_exp",
-    "vsb_se3_matrix", "vsb_se3_from_rt", "vsb_ctx_option",
+    "vsb_se3_matrix", "vsb_se3_from_rt", "vsb_ctx_option", "vsb_se3_update_batch",
 ]
 
 _lib = None
@@ -107,6 +107,7 @@ def lib():
                                C.POINTER(GnOpts), i32, vp, vp, vp, vp]
     L.vsb_initial_pose.argtypes = [C.POINTER(f32), C.POINTER(f32), C.POINTER(f32), C.POINTER(f32)]
     L.vsb_se3_mul.argtypes = [C.POINTER(f32), C.POINTER(f32), C.POINTER(f32)]
+    L.vsb_se3_update_batch.argtypes = [vp, vp, vp, i32, vp, vp]
     L.vsb_tracker_create.argtypes = [vp, C.POINTER(TrackerCfg), C.POINTER(vp)]
     L.vsb_tracker_destroy.argtypes = [vp]
     L.vsb_track_sequence.argtypes = [vp, vp, vp, vp, vp, vp, i32, vp, vp, vp]
