@@ -4,6 +4,7 @@
 #include <cstdio>
 #include <cstdint>
 #include <cuda_fp16.h>
+#include <cuda_bf16.h>
 #include <cuda_runtime.h>
 
 template <int OP>
@@ -20,6 +21,16 @@ __global__ void __launch_bounds__(1024) k(uint32_t* out, uint32_t seed, int iter
             if (OP == 3) a[i] = max(a[i], x);
             if (OP == 4) a[i] = __float_as_uint(fmaxf(__uint_as_float(a[i]), __uint_as_float(x)));
             if (OP == 5) a[i] = __vminu2(a[i], x);
+            if (OP == 6) {      // half of the registers on VIMNMX.U16x2, half on HMNMX2: do the two pipes add up?
+                if (i & 1) a[i] = __vmaxu2(a[i], x);
+                else { __half2 h = __hmax2(*reinterpret_cast<__half2*>(&a[i]), *reinterpret_cast<__half2*>(&x)); a[i] = *reinterpret_cast<uint32_t*>(&h); }
+            }
+            if (OP == 7) { __nv_bfloat162 h = __hmax2(*reinterpret_cast<__nv_bfloat162*>(&a[i]), *reinterpret_cast<__nv_bfloat162*>(&x)); a[i] = *reinterpret_cast<uint32_t*>(&h); }
+            if (OP == 8) {      // VIMNMX.U16x2 + FMNMX
+                if (i & 1) a[i] = __vmaxu2(a[i], x);
+                else a[i] = __float_as_uint(fmaxf(__uint_as_float(a[i]), __uint_as_float(x)));
+            }
+            if (OP == 9) { __half2 h = __hmin2(*reinterpret_cast<__half2*>(&a[i]), *reinterpret_cast<__half2*>(&x)); a[i] = *reinterpret_cast<uint32_t*>(&h); }
         }
         x += 0x01010101u;
     }
@@ -59,5 +70,9 @@ int main() {
     run<2>("HMNMX2 (half2 max)");
     run<3>("IMNMX.U32");
     run<4>("FMNMX");
+    run<9>("HMNMX2 (half2 min)");
+    run<7>("HMNMX2.BF16 max");
+    run<6>("VIMNMX.U16x2 + HMNMX2");
+    run<8>("VIMNMX.U16x2 + FMNMX");
     return 0;
 }

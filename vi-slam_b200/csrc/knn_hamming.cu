@@ -185,7 +185,9 @@ int vsb_knn2_hamming_keys(vsb_ctx* ctx, const uint8_t* d1, int n1_max, const int
     if (n1_max > (int)KEY_IDX_MASK || n2_max > (int)KEY_IDX_MASK) return VSB_ERR_CAPACITY;
     if (count == 0) return VSB_OK;
     int impl = ctx->knn_impl;
-    if (impl == 6) impl = (n1_max > n2_max ? n1_max : n2_max) >= 768 ? 5 : 2;      // auto: the 4-bit persistent kernel pays from ~768 rows
+    const int n_big = n1_max > n2_max ? n1_max : n2_max;
+    if (impl == 6) impl = (n_big >= 768 && n_big <= 24576) ? 5 : 2;      // auto: the 4-bit persistent kernel pays from ~768 rows (its fold holds the tile index in a byte: <= 256 tiles of 96)
+    if (impl == 5 && n_big > 24576) return VSB_ERR_CAPACITY;
     if (impl >= 3) return vsb_knn2_hamming_mx(ctx, d1, n1_max, n1, d2, n2_max, n2, count, key12, key21, impl - 3, st);
     if (impl != 0)   // tensor-core path: every valid row is written by exactly one CTA, no memset, no atomics
         return vsb_knn2_hamming_tc(ctx, d1, n1_max, n1, d2, n2_max, n2, count, key12, key21, impl == 2,

@@ -101,6 +101,26 @@ __device__ __forceinline__ void top2max_merge_u16x2(uint32_t& a0, uint32_t& a1, 
     a1 = __vmaxu2(lo, hi2);
 }
 
+// 32-bit running pair, LARGEST first (the bulk kernel's G form, see its epilogue)
+__device__ __forceinline__ void top2max_insert(uint32_t& b0, uint32_t& b1, uint32_t k) {
+    const uint32_t lo = min(b0, k);
+    b0 = max(b0, k);
+    b1 = max(b1, lo);
+}
+__device__ __forceinline__ void top2max_merge(uint32_t& a0, uint32_t& a1, uint32_t o0, uint32_t o1) {
+    const uint32_t lo = min(a0, o0);
+    const uint32_t hi2 = max(a1, o1);
+    a0 = max(a0, o0);
+    a1 = max(lo, hi2);
+}
+// G = [257 - hamming : 9][7 bits, ignored][255 - tile : 8][x : 1][127 - c : 7]  ->  hamming << 23 | column;  no candidate (distance
+// field 0) -> KEY_INF
+__device__ __forceinline__ uint32_t g_to_key(uint32_t g) {
+    const uint32_t hp = g >> 23;
+    const uint32_t col = (255u - ((g >> 8) & 0xFFu)) * (uint32_t)TN + 127u - (g & 0x7Fu);
+    return hp == 0u ? KEY_INF : (((257u - hp) << KEY_SHIFT) | col);
+}
+
 // one 96-column accumulator tile: 64 + 32 columns of packed keys, pairwise top-2 on the 16x2 unit, fold into the global keys
 __device__ __forceinline__ void epilogue_tile(uint32_t taddr, uint32_t tempty_bar, int col0, uint32_t& gb0, uint32_t& gb1) {
     uint32_t pb0[2] = {0u, 0u}, pb1[2] = {0u, 0u};
@@ -118,14 +138,14 @@ __device__ __forceinline__ void epilogue_tile(uint32_t taddr, uint32_t tempty_ba
     const uint32_t k16[4] = {pb0[0] & 0xFFFFu, pb0[0] >> 16, pb1[0] & 0xFFFFu, pb1[0] >> 16};
 #pragma unroll
     for (int q = 0; q < 4; q++) {
-        const uint32_t t = k16[q] - 1u;                             // 128 * (256 - hamming) + (127 - c)
+        const uint32_t t = k16[q] - 128u;                           // 128 * (256 - hamming) + (127 - c)
         const uint32_t g = (k16[q] == 0u) ? KEY_INF
                                           : (((256u - (t >> 7)) << KEY_SHIFT) | (uint32_t)(col0 + 127 - (int)(t & 127u)));
         top2_insert(gb0, gb1, g);
     }
 }
 
-// bias operand rows (K slice 0 = bytes 0..31: the 2^14 x 513 term; K slice 1 = bytes 32..63: the 128 - c term)
+// bias operand rows (K slice 0 = bytes 0..31: the 2^14 x 513 term; K slice 1 = bytes 32..63: the 255 - c term)
 __device__ __forceinline__ uint32_t bias_byte(int which, int r, int b, int last_valid) {
     // which 0: row side (every row the same); 1: column side, full tile; 2: column side, last tile (columns >= last_valid are zero)
     if (r >= (which == 0 ? TM : TN)) return 0u;
@@ -135,7 +155,7 @@ __device__ __forceinline__ uint32_t bias_byte(int which, int r, int b, int last_
     }
     const int e0 = 2 * (b - 32), e1 = e0 + 1;                       // the two elements of this byte
     auto row_elem = [](int e) -> uint32_t { return e == 0 ? 0x2u : e == 1 ? 0x4u : e <= 18 ? 0x6u : 0u; };     // 1, 2, 4, 4, 4, ...
-    auto col_elem = [](int e, int v) -> uint32_t {                  // digits of v = 128 - c against the row constants
+    auto col_elem = [](int e, int v) -> uint32_t {                  // digits of v = 255 - c against the row constants
         if (e == 0) return (v & 1) ? 0x2u : 0u;                     // 1 x 1
         if (e == 1) return (v & 2) ? 0x2u : 0u;                     // 2 x 1
         if (e == 2) return (v & 4) ? 0x2u : 0u;                     // 4 x 1
@@ -147,7 +167,7 @@ __device__ __forceinline__ uint32_t bias_byte(int which, int r, int b, int last_
         return 0u;
     };
     if (which == 0) return row_elem(e0) | (row_elem(e1) << 4);
-    const int v = 128 - r;
+    const int v = 255 - r;      // 128 + (127 - c): the extra 128 makes every valid key's distance field >= 1 (0 = no candidate)
     return col_elem(e0, v) | (col_elem(e1, v) << 4);
 }
 
@@ -507,7 +527,7 @@ knn2_hamming_mx_bulk_kernel(const uint8_t* __restrict__ e1, int n1_max, const in
             if (!mx_item(it, row_tiles, n1_max, n1_arr, n2_max, n2_arr, w)) continue;
             const int last_valid = w.n_cols - (w.T - 1) * TN;
             const int row = w.row0 + wq * 32 + lane;
-            uint32_t gb0 = KEY_INF, gb1 = KEY_INF;
+            uint32_t gb0 = 0u, gb1 = 0u;                                  // running pair in G form, largest first (0 = none)
             for (int j = (int)((tc ^ (uint32_t)grp) & 1u); j < w.T; j += 2) {      // this group's tiles of the item
                 const uint32_t g = tc + (uint32_t)j;
                 const int t = grp;
@@ -522,15 +542,16 @@ knn2_hamming_mx_bulk_kernel(const uint8_t* __restrict__ e1, int n1_max, const in
                 umma::fence_before_sync();
                 umma::mbar_arrive(BAR(TEMPTY + t));                       // accumulator stage is free again
                 if (j == w.T - 1 && last_valid < TN) {                    // columns past the end of the set: key 0
+                    // register i holds columns 2 i and 2 i + 1: mask 0xFFFFFFFF >> 16 x (its columns past the end); shr clamps
+                    // amounts above 31, so a register entirely past the end is cleared
+                    int lv = last_valid;
+                    asm volatile("" : "+r"(lv));              // (opaque: keeps the 48 shift amounts from being hoisted out of the tile loop and spilled)
+                    const int sh0 = 32 - 16 * lv;
 #pragma unroll
-                    for (int i = 0; i < 32; i++) {
-                        const int c = 2 * i;
-                        v[i] = c + 1 < last_valid ? v[i] : (c < last_valid ? (v[i] & 0xFFFFu) : 0u);
-                    }
-#pragma unroll
-                    for (int i = 0; i < 16; i++) {
-                        const int c = 64 + 2 * i;
-                        u[i] = c + 1 < last_valid ? u[i] : (c < last_valid ? (u[i] & 0xFFFFu) : 0u);
+                    for (int i = 0; i < 48; i++) {
+                        uint32_t m;
+                        asm("shr.b32 %0, %1, %2;" : "=r"(m) : "r"(0xFFFFFFFFu), "r"(max(sh0 + 32 * i, 0)));
+                        if (i < 32) v[i] &= m; else u[i - 32] &= m;
                     }
                 }
 #pragma unroll
@@ -538,25 +559,29 @@ knn2_hamming_mx_bulk_kernel(const uint8_t* __restrict__ e1, int n1_max, const in
 #pragma unroll
                 for (int i = 0; i < 16; i += 2) top2max_insert2_u16x2(pb0[(i >> 1) & 1], pb1[(i >> 1) & 1], u[i], u[i + 1]);
                 top2max_merge_u16x2(pb0[0], pb1[0], pb0[1], pb1[1]);
-                const uint32_t k16[4] = {pb0[0] & 0xFFFFu, pb0[0] >> 16, pb1[0] & 0xFFFFu, pb1[0] >> 16};
-                const int col0 = j * TN;
-#pragma unroll
-                for (int q = 0; q < 4; q++) {
-                    const uint32_t tt = k16[q] - 1u;                    // 128 * (256 - hamming) + (127 - c)
-                    const uint32_t gk = (k16[q] == 0u) ? KEY_INF
-                                                       : (((256u - (tt >> 7)) << KEY_SHIFT) | (uint32_t)(col0 + 127 - (int)(tt & 127u)));
-                    top2_insert(gb0, gb1, gk);
-                }
+                // fold into the item's running pair without decoding: a 16-bit key k = [257 - hamming : 9][127 - c : 7] of
+                // tile j becomes G = [k : 16][255 - j : 8][low byte of k : 8] (one PRMT).  Inside a tile unsigned order of G is
+                // the order of k; the running pair gets its 7 column bits of the HIGH half forced to ones first, so a candidate
+                // of a later tile can only win on the distance field, an equal distance keeps the earlier tile (its tile byte
+                // is larger), and the true column bits survive in the low byte.
+                const uint32_t tsel = (uint32_t)(255 - j);
+                gb0 |= 0x007F0000u; gb1 |= 0x007F0000u;
+                top2max_insert(gb0, gb1, __byte_perm(pb0[0], tsel, 0x1040));
+                top2max_insert(gb0, gb1, __byte_perm(pb0[0], tsel, 0x3242));
+                top2max_insert(gb0, gb1, __byte_perm(pb1[0], tsel, 0x1040));
+                top2max_insert(gb0, gb1, __byte_perm(pb1[0], tsel, 0x3242));
             }
             tc += (uint32_t)w.T;
             // the two groups' partial results of this item (double-buffered by item parity: the barrier of item ic + 1 orders the
             // next write of a buffer after this read)
             uint2* part = s_part + (ic & 1) * 128;
+            gb0 |= 0x007F0000u; gb1 |= 0x007F0000u;                       // different tiles from here on: distance, tile, column
             if (grp == 1) part[wq * 32 + lane] = make_uint2(gb0, gb1);
             asm volatile("bar.sync 2, 256;" ::: "memory");                // the eight epilogue warps
             if (grp == 0) {
                 const uint2 o = part[wq * 32 + lane];
-                top2_merge(gb0, gb1, o.x, o.y);
+                top2max_merge(gb0, gb1, o.x, o.y);
+                gb0 = g_to_key(gb0); gb1 = g_to_key(gb1);
                 uint32_t* keys_out = w.dir ? key21 + (size_t)w.prob * n2_max * 2 : key12 + (size_t)w.prob * n1_max * 2;
                 if (row < w.n_rows) *reinterpret_cast<uint2*>(keys_out + (size_t)row * 2) = make_uint2(gb0, gb1);
             }
