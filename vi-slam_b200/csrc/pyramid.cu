@@ -5,6 +5,9 @@
 #include "common.cuh"
 #include "se3.cuh"
 
+int vsb_pyramid_build_levels(vsb_ctx_t* ctx, const uint8_t* img, int64_t img_stride, int pitch, int count,
+                             const vsb_pyr_layout_t* layout, uint8_t* pyr, int copy_l0, void* stream);
+
 namespace {
 
 // ---------------------------------------------------------------------------------------------- pyramid
@@ -16,6 +19,7 @@ constexpr int PT = 64;
 
 struct PyrParams {
     vsb_pyr_layout_t lay;
+    int copy_l0;          // 1 = Camera::Update's copy of the frame as level 0 is written; 0 = the readers take level 0 from the frames
 };
 
 __device__ __forceinline__ uint8_t mean_clipped(int sum, int count) {
@@ -48,7 +52,7 @@ pyramid_kernel(const uint8_t* __restrict__ img, long long img_stride, int pitch,
             uint4 v = make_uint4(0u, 0u, 0u, 0u);
             if (gy < h0 && gx + 15 < w0) {
                 v = __ldg(reinterpret_cast<const uint4*>(in + (size_t)gy * in_pitch + gx));
-                if (img) *reinterpret_cast<uint4*>(out + (size_t)gy * w0 + gx) = v;
+                if (img && P.copy_l0) *reinterpret_cast<uint4*>(out + (size_t)gy * w0 + gx) = v;
             }
             *reinterpret_cast<uint4*>(&s[0][ty * PT + tx]) = v;
         } else {
@@ -59,7 +63,7 @@ pyramid_kernel(const uint8_t* __restrict__ img, long long img_stride, int pitch,
                 uint8_t v = 0;
                 if (gy < h0 && gx < w0) {
                     v = __ldg(in + (size_t)gy * in_pitch + gx);
-                    if (img) out[(size_t)gy * w0 + gx] = v;
+                    if (img && P.copy_l0) out[(size_t)gy * w0 + gx] = v;
                 }
                 s[0][i] = v;
             }
@@ -137,7 +141,7 @@ pyramid16_kernel(const uint8_t* __restrict__ img, long long img_stride, int pitc
     const uint8_t* src = in + (size_t)(by * 16) * in_pitch + bx * 16;
 #pragma unroll
     for (int k = 0; k < 16; k++) r[k] = __ldcs(reinterpret_cast<const uint4*>(src + (size_t)k * in_pitch));
-    if (img) {                                                    // Camera::Update keeps a copy of the frame as level 0
+    if (img && P.copy_l0) {                                       // Camera::Update keeps a copy of the frame as level 0
         uint8_t* dst = out + (size_t)(by * 16) * w0 + bx * 16;
 #pragma unroll
         for (int k = 0; k < 16; k++) *reinterpret_cast<uint4*>(dst + (size_t)k * w0) = r[k];
@@ -255,6 +259,8 @@ struct CandParams {
     // {Scharr gx | gy << 16, I_prev} that gn_prepare_kernel would gather (grad_mode 1 arithmetic, bit-identical)
     const uint8_t* prev_pyr;
     long long pair_stride;
+    const uint8_t* prev_l0;       // level 0 of the previous frames outside the packed pyramid (frame p at prev_l0 + p * l0_stride), or NULL
+    long long l0_stride;
     vsb_pyr_layout_t lay;
     int first_lvl, last_lvl;
     uint2* patt;
@@ -329,7 +335,8 @@ candidates_kernel(const float* __restrict__ good_xy, int good_cap, const int32_t
     const int total = min(s_off[nf], cand_cap);
     const bool attrs = P.patt != nullptr && lvl <= P.first_lvl && lvl >= P.last_lvl;
     uint2* pout = attrs ? P.patt + ((size_t)prob * P.levels + lvl) * cand_cap : nullptr;
-    const uint8_t* image1 = attrs ? P.prev_pyr + (size_t)prob * P.pair_stride + P.lay.offset[lvl] : nullptr;
+    const uint8_t* image1 = !attrs ? nullptr : (lvl == 0 && P.prev_l0) ? P.prev_l0 + (size_t)prob * P.l0_stride
+                                                                       : P.prev_pyr + (size_t)prob * P.pair_stride + P.lay.offset[lvl];
     const int cols = P.lay.w[lvl], rows = P.lay.h[lvl];
     // one warp per feature: lanes stride over the feature's points (i outer, j inner — reference row order)
     const int warp = tid >> 5, lane = tid & 31;
@@ -490,10 +497,18 @@ extern "C" int vsb_pyr_layout(int w, int h, int levels, vsb_pyr_layout_t* out) {
 
 extern "C" int vsb_pyramid_build(vsb_ctx_t* ctx, const uint8_t* img, int64_t img_stride, int pitch, int count,
                                  const vsb_pyr_layout_t* layout, uint8_t* pyr, void* stream) {
+    return vsb_pyramid_build_levels(ctx, img, img_stride, pitch, count, layout, pyr, 1, stream);
+}
+
+// Internal form (tracker): copy_l0 = 0 leaves level 0 of the packed pyramid unwritten — the candidate pass and the solver then
+// read level 0 from the caller's frames (prev_l0 / cur_l0), which saves a write and later reads of w h bytes per frame.
+int vsb_pyramid_build_levels(vsb_ctx_t* ctx, const uint8_t* img, int64_t img_stride, int pitch, int count,
+                             const vsb_pyr_layout_t* layout, uint8_t* pyr, int copy_l0, void* stream) {
     if (!ctx || !layout || !pyr || count < 0) return VSB_ERR_INVALID;
     if (count == 0) return VSB_OK;
     PyrParams P;
     P.lay = *layout;
+    P.copy_l0 = copy_l0;
     // register-blocked fast path: exact halving at every level and 16-byte aligned rows
     const int in_pitch = img ? pitch : layout->w[0];
     const bool fast = ctx->pyr_impl != 0 && (layout->w[0] % 16 == 0) && (layout->h[0] % 16 == 0) &&
@@ -552,7 +567,7 @@ int vsb_candidates_prepare(vsb_ctx_t* ctx, const float* good_xy, int good_cap, c
                            const int* lw, const int* lh, float* cand, int cand_cap, int32_t* n_cand,
                            const uint8_t* prev_pyr, int64_t pair_stride, const vsb_pyr_layout_t* layout, int first_lvl,
                            int last_lvl, void* patt, void* xy, const vsb_intr_t* K, int rec_abs, uint32_t dedup_mask,
-                           int32_t* n_pts, void* stream) {
+                           int32_t* n_pts, const uint8_t* prev_l0, int64_t l0_stride, void* stream) {
     if (!ctx || !good_xy || !n_good || (!cand && !rec_abs) || !n_cand || !lw || !lh) return VSB_ERR_INVALID;
     if (rec_abs && (!prev_pyr || !layout || !patt)) return VSB_ERR_INVALID;
     if (levels < 1 || levels > VSB_MAX_LEVELS || count < 0 || cand_cap < 0) return VSB_ERR_INVALID;
@@ -561,11 +576,11 @@ int vsb_candidates_prepare(vsb_ctx_t* ctx, const float* good_xy, int good_cap, c
     P.levels = levels;
     for (int l = 0; l < levels; l++) { P.lw[l] = lw[l]; P.lh[l] = lh[l]; }
     P.prev_pyr = nullptr; P.pair_stride = 0; P.first_lvl = -1; P.last_lvl = 0; P.patt = nullptr; P.xy = nullptr;
-    P.rec_abs = 0; P.dedup_mask = 0u; P.n_pts = nullptr;
+    P.rec_abs = 0; P.dedup_mask = 0u; P.n_pts = nullptr; P.prev_l0 = nullptr; P.l0_stride = 0;
     for (int l = 0; l < VSB_MAX_LEVELS; l++) { P.bx[l] = P.by[l] = 0.f; P.invfx[l] = P.invfy[l] = 0.f; }
     memset(&P.lay, 0, sizeof(P.lay));
     if (prev_pyr && layout && patt) {
-        P.prev_pyr = prev_pyr; P.pair_stride = pair_stride; P.lay = *layout;
+        P.prev_pyr = prev_pyr; P.pair_stride = pair_stride; P.lay = *layout; P.prev_l0 = prev_l0; P.l0_stride = l0_stride;
         P.first_lvl = first_lvl; P.last_lvl = last_lvl; P.patt = reinterpret_cast<uint2*>(patt);
         if (rec_abs) {
             P.rec_abs = 1; P.n_pts = n_pts;
@@ -594,6 +609,6 @@ extern "C" int vsb_candidates_build(vsb_ctx_t* ctx, const float* good_xy, int go
                                     int count, int levels, const int* lw, const int* lh, float* cand, int cand_cap,
                                     int32_t* n_cand, void* stream) {
     return vsb_candidates_prepare(ctx, good_xy, good_cap, n_good, count, levels, lw, lh, cand, cand_cap, n_cand, nullptr, 0,
-                                  nullptr, 0, 0, nullptr, nullptr, nullptr, 0, 0u, nullptr, stream);
+                                  nullptr, 0, 0, nullptr, nullptr, nullptr, 0, 0u, nullptr, nullptr, 0, stream);
 }
 

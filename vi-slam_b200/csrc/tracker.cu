@@ -24,12 +24,14 @@ int vsb_candidates_prepare(vsb_ctx_t* ctx, const float* good_xy, int good_cap, c
                            const int* lw, const int* lh, float* cand, int cand_cap, int32_t* n_cand,
                            const uint8_t* prev_pyr, int64_t pair_stride, const vsb_pyr_layout_t* layout, int first_lvl,
                            int last_lvl, void* patt, void* xy, const vsb_intr_t* K, int rec_abs, uint32_t dedup_mask,
-                           int32_t* n_pts, void* stream);
+                           int32_t* n_pts, const uint8_t* prev_l0, int64_t l0_stride, void* stream);
+int vsb_pyramid_build_levels(vsb_ctx_t* ctx, const uint8_t* img, int64_t img_stride, int pitch, int count,
+                             const vsb_pyr_layout_t* layout, uint8_t* pyr, int copy_l0, void* stream);
 int vsb_gn_track(vsb_ctx_t* ctx, const uint8_t* cur_pyr, int64_t pair_stride_pixels, const vsb_pyr_layout_t* layout,
                  const void* patt, const int32_t* n_cand, const int32_t* n_pts, uint32_t dedup_mask, int cand_cap,
                  const vsb_intr_t K[VSB_MAX_LEVELS], const float* pose_in, const vsb_gn_opts_t* opts, int pair0, int count,
                  int threads, float* pose_out, vsb_gn_trace_t* trace, int32_t* n_trace, unsigned long long* stats,
-                 void* stream);
+                 const uint8_t* cur_l0, int64_t l0_stride, void* stream);
 int vsb_knn_unpack(vsb_ctx* ctx, const uint32_t* keys, int n_max, const int32_t* n, int count, int32_t* idx,
                    float* dist, cudaStream_t st);
 int vsb_knn2_l2_keys(vsb_ctx* ctx, const float* d1, int n1_max, const int32_t* n1, const float* d2, int n2_max,
@@ -188,9 +190,20 @@ void gn_plan(const vsb_ctx* ctx, int count, int feat_cap, int* threads, int* n_t
 
 // Stages after the pyramids exist: match -> filter -> candidates -> GN.  prev pyramid of pair c is
 // pyr_prev + c * frame_stride, current is pyr_cur + c * frame_stride.
+// The solver's reference-mode path (gn_track.cu behind the fused candidate pass): the only one that can take level 0 from
+// the caller's frames instead of a copy inside the packed pyramid.
+bool tables_path(const vsb_tracker* t) {
+    const vsb_tracker_cfg_t& c = t->cfg;
+    return c.gn.grad_mode == 1 && t->ctx->gn_impl == 1 && c.gn.weight_mode == 0 && c.gn.sample_mode == 0 &&
+           t->principal_point_ok && t->lay.w[0] <= 4095 && t->lay.h[0] <= 4095;
+}
+
+// prev_l0 / cur_l0 (optional, tables_path only): level 0 of pair c at prev_l0 / cur_l0 + c * w * h; the packed pyramids then
+// hold levels 1.. only.
 int run_pairs(vsb_tracker* t, Slot& s, const uint8_t* pyr_prev, const uint8_t* pyr_cur, const int16_t* gx_prev,
               const int16_t* gy_prev, const uint8_t* d1, const uint8_t* d2, const float* kp1, const int32_t* n1,
-              const int32_t* n2, const float* prior, int count, float* pose_out, int32_t* n_good_out, cudaStream_t st) {
+              const int32_t* n2, const float* prior, int count, float* pose_out, int32_t* n_good_out, cudaStream_t st,
+              const uint8_t* prev_l0 = nullptr, const uint8_t* cur_l0 = nullptr) {
     vsb_ctx* ctx = t->ctx;
     const vsb_tracker_cfg_t& c = t->cfg;
     const int N = c.n_feat_max;
@@ -219,8 +232,9 @@ int run_pairs(vsb_tracker* t, Slot& s, const uint8_t* pyr_prev, const uint8_t* p
     const int fused = c.gn.grad_mode == 1 ? 1 : 0;
     // reference modes (identity weights, nearest-pixel lookup, FP64 Gram): gn_track.cu — 8-byte records that name their
     // slots in per-feature back-projection tables, nothing else per point
-    const bool tables = fused && ctx->gn_impl == 1 && c.gn.weight_mode == 0 && c.gn.sample_mode == 0 &&
-                        t->principal_point_ok && t->lay.w[0] <= 4095 && t->lay.h[0] <= 4095;
+    const bool tables = tables_path(t);
+    if (!tables && (prev_l0 || cur_l0)) return VSB_ERR_INVALID;
+    const int64_t l0_stride = (int64_t)c.w * c.h;
     // levels whose candidate points are merged per distinct pixel: every level small enough for the candidate pass's byte map
     const uint32_t dedup_mask = (tables && ctx->gn_dedup && ctx->gn_variant != 1) ? 0xFFFFFFFFu : 0u;
     // ... otherwise gn_solve.cu; with identity weights the points are handed over already back-projected, as doubles,
@@ -229,7 +243,7 @@ int run_pairs(vsb_tracker* t, Slot& s, const uint8_t* pyr_prev, const uint8_t* p
     if ((rc = vsb_candidates_prepare(ctx, s.good_xy, t->good_cap, s.n_good, count, t->lay.levels, t->lw, t->lh, s.cand,
                                      t->cand_cap, s.n_cand, fused ? pyr_prev : nullptr, t->lay.frame_stride, &t->lay,
                                      c.gn.first_lvl, c.gn.last_lvl, fused ? s.patt : nullptr, unit ? (void*)s.cand : nullptr,
-                                     t->K, tables ? 1 : 0, dedup_mask, s.n_pts, st)))
+                                     t->K, tables ? 1 : 0, dedup_mask, s.n_pts, prev_l0, l0_stride, st)))
         return rc;
     if (tables) {
         int threads, n_tail, threads_tail;
@@ -241,12 +255,12 @@ int run_pairs(vsb_tracker* t, Slot& s, const uint8_t* pyr_prev, const uint8_t* p
             VSB_CUDA(ctx, cudaStreamWaitEvent(s.aux, s.fork, 0));
         }
         if ((rc = vsb_gn_track(ctx, pyr_cur, t->lay.frame_stride, &t->lay, s.patt, s.n_cand, s.n_pts, dedup_mask, t->cand_cap,
-                               t->K, prior, &c.gn, 0, n_main, threads, pose_out, t->trace, t->n_trace, t->stats, st)))
+                               t->K, prior, &c.gn, 0, n_main, threads, pose_out, t->trace, t->n_trace, t->stats, cur_l0, l0_stride, st)))
             return rc;
         if (n_tail > 0) {
             if ((rc = vsb_gn_track(ctx, pyr_cur, t->lay.frame_stride, &t->lay, s.patt, s.n_cand, s.n_pts, dedup_mask, t->cand_cap,
                                    t->K, prior, &c.gn, n_main, n_tail, threads_tail, pose_out, t->trace,
-                                   t->n_trace, t->stats, s.aux)))
+                                   t->n_trace, t->stats, cur_l0, l0_stride, s.aux)))
                 return rc;
             VSB_CUDA(ctx, cudaEventRecord(s.join, s.aux));
             VSB_CUDA(ctx, cudaStreamWaitEvent(st, s.join, 0));
@@ -317,15 +331,20 @@ static int track_sequence_slot(vsb_tracker* t, Slot& s, const uint8_t* frames, b
     const int pairs = n_frames - 1;
     if (pairs > c.max_pairs) return VSB_ERR_CAPACITY;
     int rc;
-    // Camera::Update for every frame (level 0 is copied unless it was uploaded straight into the pyramid)
-    if ((rc = vsb_pyramid_build(ctx, frames_in_place ? nullptr : frames, (int64_t)c.w * c.h, c.w, n_frames, &t->lay, s.pyr, st)))
+    // Camera::Update for every frame.  Level 0: already in place when the frames were uploaded straight into the pyramid;
+    // read from the caller's frames by the candidate pass and the solver on the reference-mode path (no copy at all);
+    // copied otherwise.
+    const bool ext_l0 = !frames_in_place && tables_path(t);
+    if ((rc = vsb_pyramid_build_levels(ctx, frames_in_place ? nullptr : frames, (int64_t)c.w * c.h, c.w, n_frames, &t->lay, s.pyr,
+                                       ext_l0 ? 0 : 1, st)))
         return rc;
     // Camera::computeGradient — only the previous frame of each pair is read by the solver
     if (c.gn.grad_mode == 0)
         if ((rc = vsb_gradient_build(ctx, s.pyr, pairs, &t->lay, s.gx, s.gy, nullptr, st))) return rc;
     const size_t dstride = (size_t)c.n_feat_max * c.desc_bytes;
     return run_pairs(t, s, s.pyr, s.pyr + t->lay.frame_stride, s.gx, s.gy, desc, desc + dstride, kp_xy, n_feat,
-                     n_feat ? n_feat + 1 : nullptr, prior, pairs, pose, n_good, st);
+                     n_feat ? n_feat + 1 : nullptr, prior, pairs, pose, n_good, st, ext_l0 ? frames : nullptr,
+                     ext_l0 ? frames + (size_t)c.w * c.h : nullptr);
 }
 
 extern "C" int vsb_track_sequence(vsb_tracker_t* t, const uint8_t* frames, const uint8_t* desc, const float* kp_xy,
@@ -385,11 +404,13 @@ extern "C" int vsb_track_pairs(vsb_tracker_t* t, const uint8_t* prev, const uint
     uint8_t* pyr_prev = s.pyr;
     uint8_t* pyr_cur = s.pyr + (size_t)c.max_pairs * t->lay.frame_stride;
     int rc;
-    if ((rc = vsb_pyramid_build(ctx, prev, (int64_t)c.w * c.h, c.w, count, &t->lay, pyr_prev, st))) return rc;
-    if ((rc = vsb_pyramid_build(ctx, cur, (int64_t)c.w * c.h, c.w, count, &t->lay, pyr_cur, st))) return rc;
+    const bool ext_l0 = tables_path(t);      // level 0 is read from prev / cur themselves
+    if ((rc = vsb_pyramid_build_levels(ctx, prev, (int64_t)c.w * c.h, c.w, count, &t->lay, pyr_prev, ext_l0 ? 0 : 1, st))) return rc;
+    if ((rc = vsb_pyramid_build_levels(ctx, cur, (int64_t)c.w * c.h, c.w, count, &t->lay, pyr_cur, ext_l0 ? 0 : 1, st))) return rc;
     if (c.gn.grad_mode == 0)
         if ((rc = vsb_gradient_build(ctx, pyr_prev, count, &t->lay, s.gx, s.gy, nullptr, st))) return rc;
-    return run_pairs(t, s, pyr_prev, pyr_cur, s.gx, s.gy, d1, d2, kp1_xy, n1, n2, pose_prior, count, pose, n_good, st);
+    return run_pairs(t, s, pyr_prev, pyr_cur, s.gx, s.gy, d1, d2, kp1_xy, n1, n2, pose_prior, count, pose, n_good, st,
+                     ext_l0 ? prev : nullptr, ext_l0 ? cur : nullptr);
 }
 
 extern "C" int vsb_track_sequence_host(vsb_tracker_t* t, const uint8_t* h_frames, const uint8_t* h_desc,
