@@ -168,7 +168,7 @@ void gn_plan(const vsb_ctx* ctx, int count, int feat_cap, int* threads, int* n_t
     const int sms = ctx->sm_count > 0 ? ctx->sm_count : 148;
     const bool big = feat_cap > 64;
     const int base = big ? 512 : 128;                       // block size of a large batch
-    const int per_sm = big ? 2 : 6;                         // resident blocks per SM the wave arithmetic assumes
+    const int per_sm = big ? 2 : (ctx->gn_variant == 0 ? 4 : 6);      // resident blocks per SM the wave arithmetic assumes (128 registers: 4)
     auto fit = [&](int n) {
         const int t = n <= (big ? 2 : 1) * sms ? 1024 : n <= 2 * sms ? 512 : n <= 3 * sms ? 256 : 128;
         return t > base ? t : base;
