@@ -434,7 +434,11 @@ extern "C" int vsb_track_sequence_host(vsb_tracker_t* t, const uint8_t* h_frames
     const size_t sz_desc = ((size_t)n_frames * dstride + al - 1) / al * al, sz_kp = ((size_t)n_frames * kstride * 4 + al - 1) / al * al;
     const size_t sz_nf = ((size_t)n_frames * 4 + al - 1) / al * al, sz_pr = ((size_t)total_pairs * 28 + al - 1) / al * al;
     const size_t side_total = sz_desc + sz_kp + sz_nf + sz_pr;
-    const bool upfront = !(upf && upf[0] == '0') && side_total <= ((size_t)1 << 30);
+    // ... when they are small next to the frames (1000 ORB descriptors: 40 KB against a 361 KB frame).  Large side inputs
+    // (5000 descriptors, float descriptors) would hold back the first chunk's kernels behind one long copy: they travel with
+    // their chunk instead (configs[2]: 6.74 -> 6.12 ms, configs[3]: 5.43 -> 5.14 ms; tools/sweep_cfg_host_chunk.py).
+    const bool side_small = (dstride + kstride * 4) * 4 <= fbytes;
+    const bool upfront = (upf ? upf[0] != '0' : side_small) && side_total <= ((size_t)1 << 30);
     uint8_t* a_desc = nullptr; float* a_kp = nullptr; int32_t* a_nf = nullptr; float* a_pr = nullptr;
     if (upfront) {
         if (t->seq_side_bytes < side_total) {
