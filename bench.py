@@ -330,7 +330,7 @@ class Gpu:
                          else "fallback 1.59 PFLOP/s dense bf16")
         self.traffic = {}
         try:
-            self.traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic_r2.json")))["per_step"]
+            self.traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic_r2b.json")))["per_step"]
         except Exception:
             pass
 
@@ -423,9 +423,9 @@ def kernel_table(g, cfg, prof, steps, stats, n_pairs_per_step, n_frames_per_step
                                           "the solver itself only moves the first term (8-byte records + the gathered byte), the "
                                           "second is paid by the pyramid and candidate kernels"},
                         "point_visits_per_s": stats["point_visits"] / sec,
-                        "note": "bound as SURVEY 8(d) defines it; ncu (profiles/r2_gn_track.txt) shows the kernel limited by the "
-                                "FP64 pipe it shares between DMMA (Gram matrix) and DADD/DFMA (warp, J = Jl Jw) and by instruction "
-                                "issue (57 % of issue slots), DRAM at 3 %"})
+                        "note": "bound as SURVEY 8(d) defines it; ncu (profiles/r2b_full_step.txt) shows the kernel limited by "
+                                "instruction issue (65 % of the issue slots busy with 16 warps per SM: 128 registers hold the 28 "
+                                "Gram accumulators), FP64 pipe 32 %, conversion pipe 30 %, DRAM at 3 %"})
         elif name == "knn2_hamming":
             if knn_impl_env == 0:
                 work, unit, peak, src, bound = 8.0 * N * N * pairs_total, "GPOPC/s", g.ctx.popc_peak() / 1e9, "measured by vsb_popc_peak on this GPU", "int"
