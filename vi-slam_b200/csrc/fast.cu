@@ -4,7 +4,7 @@
 // Semantics are cv::FAST(TYPE_9_16)'s, restated in oracle/fast.c and pinned there against cv2: corner test, score
 // (largest threshold that keeps the pixel a corner, minus one), strict 3x3 suppression, row-major output order.
 //
-//   fast_score_kernel   one 64x16 tile (+halo) per CTA in shared memory, four adjacent pixels per thread.  The flag pass is
+//   fast_score_kernel   one 64x32 tile (+halo) per CTA in shared memory, 4 adjacent pixels x 2 rows per thread.  The flag pass is
 //                       the NECESSARY condition only — two neighbouring compass points of the ring both brighter or both
 //                       darker, 8 comparisons on packed bytes (SWAR) — and the few percent of pixels that pass get the full
 //                       arc test from their score (sliding-window minima; corner iff score + 1 > threshold), one thread per
@@ -60,22 +60,24 @@ __device__ __forceinline__ uint32_t gt7(uint32_t a, uint32_t b) {
     return r;
 }
 
-// One 64x16 tile per CTA, FOUR horizontally adjacent pixels per thread, all ring comparisons on packed bytes.
-// Shared tile: 22 rows x 72 bytes (x0 - 4 .. x0 + 67), so a thread's centre word is aligned and the 16 ring positions of
-// its four pixels are funnel shifts of three aligned words per row (21 LDS.32 per thread instead of 17 byte loads per
-// pixel); rows are 48 words apart so that the two tile rows a warp touches fall into disjoint banks.  (Reading the 21
-// words straight through L1 instead was measured 13 % slower.)
-// Arc test on bit masks: T3_k = B_k & B_k+1 & B_k+2, T9_k = T3_k & T3_k+3 & T3_k+6 (one LOP3 each), any = OR_k T9_k.
-// Pixels that ARE corners (a percent or so) are queued in shared memory and scored densely, one thread per corner, after
-// the tile's flag pass — inside the flag pass the scalar score would run for whole warps whenever one lane has a corner.
-constexpr int FT_W = 64, FT_H = 16, FT_HALO = 3, FT_SH = FT_H + 2 * FT_HALO;
+// One 64x32 tile per CTA, FOUR horizontally adjacent pixels x TWO rows (ty, ty + 16) per thread, all ring comparisons on
+// packed bytes.  Shared tile: 38 rows x 72 bytes (x0 - 4 .. x0 + 67), so a thread's centre word is aligned and the ring
+// positions of its four pixels are funnel shifts of aligned words; rows are 48 words apart so that the two tile rows a warp
+// touches fall into disjoint banks.  The loader requests a thread's (up to three) words before it stores any of them, so
+// their latencies overlap; the tile's height halves the halo share (38 rows read for 32) and the per-thread set-up is spread
+// over eight pixels instead of four.
+// Pixels that pass the flag pass (a percent or so up to a fifth, by texture) are queued in shared memory and scored densely,
+// one thread per candidate, after the tile's flag pass — inside the flag pass the scalar score would run for whole warps
+// whenever one lane has a candidate.
+constexpr int FT_W = 64, FT_H = 32, FT_HALO = 3, FT_SH = FT_H + 2 * FT_HALO;
 constexpr int FT_WORDS = 18, FT_PITCH = 48;
+constexpr int FT_LOADS = (FT_SH * FT_WORDS + 255) / 256;              // words per thread of the loader (3)
 
 __global__ void __launch_bounds__(256, 4)
 fast_score_kernel(const uint8_t* __restrict__ img, long long img_stride, int pitch, int w, int h, int threshold,
                   uint8_t* __restrict__ score1, int sw) {
     __shared__ uint32_t s[FT_SH][FT_PITCH];
-    __shared__ uint16_t s_list[FT_W * FT_H];                            // tile-local (y << 6 | x) of the corners found
+    __shared__ uint16_t s_list[FT_W * FT_H];                            // tile-local (y << 6 | x) of the candidates found
     __shared__ int s_count;
     if (threadIdx.x == 0) s_count = 0;
     const int frame = blockIdx.z;
@@ -83,55 +85,67 @@ fast_score_kernel(const uint8_t* __restrict__ img, long long img_stride, int pit
     uint8_t* out = score1 + (size_t)frame * sw * h;      // score rows are sw = round_up(w, 4) bytes apart; the pad stays 0
     const int x0 = blockIdx.x * FT_W, y0 = blockIdx.y * FT_H;
     const bool aligned_in = ((reinterpret_cast<uintptr_t>(in) | (uintptr_t)pitch) & 3u) == 0;
-    for (int p = threadIdx.x; p < FT_SH * FT_WORDS; p += 256) {
-        const int py = p / FT_WORDS, pw = p - py * FT_WORDS;
-        const int gx = x0 - 4 + 4 * pw, gy = y0 + py - FT_HALO;
-        uint32_t v = 0u;
-        if (gy >= 0 && gy < h) {
-            const uint8_t* row = in + (size_t)gy * pitch;
-            if (aligned_in && gx >= 0 && gx + 3 < w) {
-                v = __ldg(reinterpret_cast<const uint32_t*>(row + gx));
-            } else {
+    {
+        uint32_t v[FT_LOADS];
+        int slot[FT_LOADS];
 #pragma unroll
-                for (int j = 0; j < 4; j++)
-                    if (gx + j >= 0 && gx + j < w) v |= (uint32_t)__ldg(row + gx + j) << (8 * j);
+        for (int q = 0; q < FT_LOADS; q++) {
+            const int p = threadIdx.x + 256 * q;
+            const int py = (p * 3641) >> 16, pw = p - py * FT_WORDS;   // p / 18 for p < 1024
+            const int gx = x0 - 4 + 4 * pw, gy = y0 + py - FT_HALO;
+            slot[q] = p < FT_SH * FT_WORDS ? py * FT_PITCH + pw : -1;
+            v[q] = 0u;
+            if (slot[q] >= 0 && gy >= 0 && gy < h) {
+                const uint8_t* row = in + (size_t)gy * pitch;
+                if (aligned_in && gx >= 0 && gx + 3 < w) {
+                    v[q] = __ldg(reinterpret_cast<const uint32_t*>(row + gx));
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 4; j++)
+                        if (gx + j >= 0 && gx + j < w) v[q] |= (uint32_t)__ldg(row + gx + j) << (8 * j);
+                }
             }
         }
-        s[py][pw] = v;
+#pragma unroll
+        for (int q = 0; q < FT_LOADS; q++)
+            if (slot[q] >= 0) (&s[0][0])[slot[q]] = v[q];
     }
     __syncthreads();
-    const int ty = threadIdx.x >> 4, wc = (threadIdx.x & 15) + 1;      // row in the tile, word column of the centre word
-    const int x = x0 + 4 * (wc - 1), y = y0 + ty;
-    const bool in_image = x < w && y < h;
+    const int ty0 = threadIdx.x >> 4, wc = (threadIdx.x & 15) + 1;     // first row in the tile, word column of the centre word
+    const int x = x0 + 4 * (wc - 1);
+    const uint32_t T4 = (uint32_t)threshold * 0x01010101u;
     // Flag pass = the necessary condition only.  Any 9 contiguous ring positions contain two NEIGHBOURING compass points
     // (ring positions 0, 4, 8, 12), so a corner needs two neighbouring compass pixels that are both brighter than centre + t or
-    // both darker than centre - t.  That test needs 4 of the 16 ring positions (rows y-3, y, y+3 only) and passes for a few
-    // percent of the pixels of a natural image; the pixels that pass are queued and get the full arc test from their score.
-    uint32_t corner = 0u;
-    if (in_image && y >= 3 && y < h - 3) {
-        const uint32_t C = s[ty + 3][wc];
-        const uint32_t T4 = (uint32_t)threshold * 0x01010101u;
-        const uint32_t hi = __vaddus4(C, T4), lo = __vsubus4(C, T4);   // saturating: a ring byte can never beat 255 / 0
-        const uint32_t up = s[ty + 6][wc], dn = s[ty][wc];            // ring positions 0 (0, +3) and 8 (0, -3)
-        const uint32_t rt = __funnelshift_r(s[ty + 3][wc], s[ty + 3][wc + 1], 24);      // position 4 (+3, 0)
-        const uint32_t lf = __funnelshift_r(s[ty + 3][wc - 1], s[ty + 3][wc], 8);       // position 12 (-3, 0)
-        const uint32_t b0 = gt7(up, hi), b4 = gt7(rt, hi), b8 = gt7(dn, hi), b12 = gt7(lf, hi);
-        const uint32_t d0 = gt7(lo, up), d4 = gt7(lo, rt), d8 = gt7(lo, dn), d12 = gt7(lo, lf);
-        const uint32_t bb = ((b0 | b8) & (b4 | b12));                  // (b0&b4)|(b4&b8)|(b8&b12)|(b12&b0)
-        const uint32_t dd = ((d0 | d8) & (d4 | d12));
-        corner = (bb | dd) & 0x80808080u;
-    }
-    // every pixel gets its byte now (0 = no corner); the candidates are queued for the arc test / score pass below
-    uint8_t* o = out + (size_t)y * sw + x;
-    if (in_image) *reinterpret_cast<uint32_t*>(o) = 0u;                 // x is a multiple of 4 and x + 3 < sw
-    if (corner) {
+    // both darker than centre - t.  That test needs 4 of the 16 ring positions (rows y-3, y, y+3 only); the pixels that pass are
+    // queued and get the full arc test from their score.
 #pragma unroll
-        for (int j = 0; j < 4; j++)
-            if (((corner >> (8 * j + 7)) & 1u) && x + j >= 3 && x + j < w - 3)      // the 3-pixel border is never a corner
-                s_list[atomicAdd(&s_count, 1)] = (uint16_t)((ty << 6) | (4 * (wc - 1) + j));
+    for (int half = 0; half < 2; half++) {
+        const int ty = ty0 + 16 * half, y = y0 + ty;
+        const bool in_image = x < w && y < h;
+        uint32_t corner = 0u;
+        if (in_image && y >= 3 && y < h - 3) {
+            const uint32_t C = s[ty + 3][wc];
+            const uint32_t hi = __vaddus4(C, T4), lo = __vsubus4(C, T4);   // saturating: a ring byte can never beat 255 / 0
+            const uint32_t up = s[ty + 6][wc], dn = s[ty][wc];            // ring positions 0 (0, +3) and 8 (0, -3)
+            const uint32_t rt = __funnelshift_r(C, s[ty + 3][wc + 1], 24);                  // position 4 (+3, 0)
+            const uint32_t lf = __funnelshift_r(s[ty + 3][wc - 1], C, 8);                   // position 12 (-3, 0)
+            const uint32_t b0 = gt7(up, hi), b4 = gt7(rt, hi), b8 = gt7(dn, hi), b12 = gt7(lf, hi);
+            const uint32_t d0 = gt7(lo, up), d4 = gt7(lo, rt), d8 = gt7(lo, dn), d12 = gt7(lo, lf);
+            const uint32_t bb = ((b0 | b8) & (b4 | b12));                  // (b0&b4)|(b4&b8)|(b8&b12)|(b12&b0)
+            const uint32_t dd = ((d0 | d8) & (d4 | d12));
+            corner = (bb | dd) & 0x80808080u;
+        }
+        // every pixel gets its byte now (0 = no corner); the candidates are queued for the arc test / score pass below
+        if (in_image) *reinterpret_cast<uint32_t*>(out + (size_t)y * sw + x) = 0u;      // x is a multiple of 4 and x + 3 < sw
+        if (corner) {
+#pragma unroll
+            for (int j = 0; j < 4; j++)
+                if (((corner >> (8 * j + 7)) & 1u) && x + j >= 3 && x + j < w - 3)      // the 3-pixel border is never a corner
+                    s_list[atomicAdd(&s_count, 1)] = (uint16_t)((ty << 6) | (4 * (wc - 1) + j));
+        }
     }
     __syncthreads();
-    // ---- score pass: one thread per queued corner (dense), ring bytes from the shared tile ---------------------------------
+    // ---- score pass: one thread per queued candidate (dense), ring bytes from the shared tile ------------------------------
     const uint8_t* sb = reinterpret_cast<const uint8_t*>(&s[0][0]);
     const int ring_x[16] = FAST_RING_X, ring_y[16] = FAST_RING_Y;
     for (int e = threadIdx.x; e < s_count; e += 256) {
