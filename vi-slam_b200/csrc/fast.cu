@@ -198,10 +198,9 @@ __device__ __forceinline__ uint32_t row_max3(uint32_t prev, uint32_t cur, uint32
     const uint32_t m = __vmaxu4(L, R);
     return centre ? __vmaxu4(m, cur) : m;
 }
-__device__ __forceinline__ uint32_t keep_mask4(const uint32_t* __restrict__ r0, const uint32_t* __restrict__ r1,
-                                               const uint32_t* __restrict__ r2, int k, int nonmax, uint32_t& cur) {
-    cur = __ldg(r1 + k);
-    if (cur == 0u) return 0u;                              // the common case: no corner among these 4 pixels
+// keep mask of the four pixels of word k whose score bytes are `cur` (already loaded, non-zero)
+__device__ __forceinline__ uint32_t keep_of4(const uint32_t* __restrict__ r0, const uint32_t* __restrict__ r1,
+                                             const uint32_t* __restrict__ r2, int k, int nonmax, uint32_t cur) {
     if (!nonmax) return __vcmpgtu4(cur, 0u);
     uint32_t n = row_max3(__ldg(r1 + k - 1), cur, __ldg(r1 + k + 1), false);
     n = __vmaxu4(n, row_max3(__ldg(r0 + k - 1), __ldg(r0 + k), __ldg(r0 + k + 1), true));
@@ -219,9 +218,19 @@ fast_count4_kernel(const uint8_t* __restrict__ score1, int w, int h, int nonmax,
         const uint32_t* r0 = reinterpret_cast<const uint32_t*>(sc + (size_t)(y - 1) * w);
         const uint32_t* r1 = reinterpret_cast<const uint32_t*>(sc + (size_t)y * w);
         const uint32_t* r2 = reinterpret_cast<const uint32_t*>(sc + (size_t)(y + 1) * w);
-        for (int k = lane; k < (w >> 2); k += 32) {
-            uint32_t cur;
-            n += __popc(keep_mask4(r0, r1, r2, k, nonmax, cur) & 0x01010101u);
+        // four words per lane and round, requested together (a row is a handful of dependent-free loads per lane); words
+        // without a corner — almost all — cost nothing more
+        const int words = w >> 2;
+        for (int k0 = 0; k0 < words; k0 += 128) {
+            uint32_t cur[4];
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                const int k = k0 + 32 * j + lane;
+                cur[j] = k < words ? __ldg(r1 + k) : 0u;
+            }
+#pragma unroll
+            for (int j = 0; j < 4; j++)
+                if (cur[j] != 0u) n += __popc(keep_of4(r0, r1, r2, k0 + 32 * j + lane, nonmax, cur[j]) & 0x01010101u);
         }
     }
 #pragma unroll
@@ -231,9 +240,10 @@ fast_count4_kernel(const uint8_t* __restrict__ score1, int w, int h, int nonmax,
 
 __global__ void __launch_bounds__(256)
 fast_write4_kernel(const uint8_t* __restrict__ score1, int w, int h, int nonmax, const int32_t* __restrict__ row_offset,
-                   int cap, int32_t* __restrict__ kp_xy, int32_t* __restrict__ kp_score) {
+                   const int32_t* __restrict__ row_count, int cap, int32_t* __restrict__ kp_xy, int32_t* __restrict__ kp_score) {
     const int y = blockIdx.x * 8 + (threadIdx.x >> 5), frame = blockIdx.y, lane = threadIdx.x & 31;
     if (y < 3 || y >= h - 3) return;
+    if (row_count[(size_t)frame * h + y] == 0) return;     // about half of the rows of a natural image hold no corner
     int base = row_offset[(size_t)frame * h + y];
     if (base >= cap) return;
     const uint8_t* sc = score1 + (size_t)frame * w * h;
@@ -246,7 +256,8 @@ fast_write4_kernel(const uint8_t* __restrict__ score1, int w, int h, int nonmax,
     for (int k0 = 0; k0 < words; k0 += 32) {
         const int k = k0 + lane;
         uint32_t cur = 0u, keep = 0u;
-        if (k < words) keep = keep_mask4(r0, r1, r2, k, nonmax, cur);
+        if (k < words) cur = __ldg(r1 + k);
+        if (cur != 0u) keep = keep_of4(r0, r1, r2, k, nonmax, cur);
         if (!__any_sync(0xffffffffu, keep != 0u)) continue;
         const int cnt = __popc(keep & 0x01010101u);
         int incl = cnt;                                    // inclusive warp scan of the per-lane counts
@@ -309,7 +320,8 @@ extern "C" int vsb_fast_detect(vsb_ctx_t* ctx, const uint8_t* img, int64_t img_s
         fast_scan_kernel<<<zc, 256, 0, st>>>(row_count + (size_t)z0 * h, h, row_offset + (size_t)z0 * h, n_kp + z0);
         VSB_LAUNCHED(ctx);
         if (cap > 0) {
-            fast_write4_kernel<<<dim3(vsb_div_up(h, 8), zc), 256, 0, st>>>(sc, sw, h, nonmax, row_offset + (size_t)z0 * h, cap,
+            fast_write4_kernel<<<dim3(vsb_div_up(h, 8), zc), 256, 0, st>>>(sc, sw, h, nonmax, row_offset + (size_t)z0 * h,
+                                                                           row_count + (size_t)z0 * h, cap,
                                                                            kp_xy + (size_t)z0 * cap * 2, kp_score + (size_t)z0 * cap);
             VSB_LAUNCHED(ctx);
         }
