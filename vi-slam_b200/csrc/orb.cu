@@ -255,7 +255,7 @@ __device__ __forceinline__ int refl101(int p, int n) {
     return p;
 }
 __global__ void __launch_bounds__(256)
-orb_blur_kernel(const uint8_t* __restrict__ img, long long img_stride, int pitch, int w, int h, uint8_t* __restrict__ out) {
+orb_blur_kernel(const uint8_t* __restrict__ img, long long img_stride, int pitch, int w, int h, uint8_t* __restrict__ out, int opitch) {
     __shared__ __align__(16) uint8_t s_in[BTH + 6][BTP];          // columns x0 - 4 .. x0 + 67
     __shared__ __align__(16) float s_row[BTH + 6][BTW];
     const int f = blockIdx.z, x0 = blockIdx.x * BTW, y0 = blockIdx.y * BTH, tid = threadIdx.x;
@@ -305,8 +305,8 @@ orb_blur_kernel(const uint8_t* __restrict__ img, long long img_stride, int pitch
     }
     __syncthreads();
     // column pass: BTH rows x 16 quads, one packed store per quad
-    uint8_t* dst = out + (size_t)f * w * h;
-    const bool store_words = (w & 3) == 0;
+    uint8_t* dst = out + (size_t)f * opitch * h;          // rows opitch bytes apart (a multiple of 4 wherever the caller can pad)
+    const bool store_words = (opitch & 3) == 0;
     for (int i = tid; i < BTH * (BTW / 4); i += 256) {
         const int cy = i / (BTW / 4), q = i - cy * (BTW / 4);
         const int x = x0 + 4 * q, y = y0 + cy;
@@ -324,8 +324,8 @@ orb_blur_kernel(const uint8_t* __restrict__ img, long long img_stride, int pitch
             const int v = min(max(__float2int_rn(acc), 0), 255);
             packed |= (uint32_t)v << (8 * j);
         }
-        uint8_t* o = dst + (size_t)y * w + x;
-        if (store_words && x + 3 < w) {
+        uint8_t* o = dst + (size_t)y * opitch + x;
+        if (store_words && x + 3 < opitch) {                 // (bytes past w land in the row's padding)
             *reinterpret_cast<uint32_t*>(o) = packed;
         } else {
 #pragma unroll
@@ -337,7 +337,7 @@ orb_blur_kernel(const uint8_t* __restrict__ img, long long img_stride, int pitch
 
 // ---- stage 6: steered rBRIEF (computeOrbDescriptors, WTA_K = 2): one warp per key point, one descriptor byte per lane -----
 __global__ void __launch_bounds__(256)
-orb_describe_kernel(const uint8_t* __restrict__ blurred, int w, int h, const int32_t* __restrict__ kp_xy,
+orb_describe_kernel(const uint8_t* __restrict__ blurred, int w, int h, int bpitch, const int32_t* __restrict__ kp_xy,
                     const float* __restrict__ kp_angle, const int32_t* __restrict__ n_kp, int cap, uint8_t* __restrict__ desc) {
     __shared__ signed char s_pat[1024];
     for (int i = threadIdx.x; i < 1024; i += 256) s_pat[i] = c_pattern[i];
@@ -352,7 +352,7 @@ orb_describe_kernel(const uint8_t* __restrict__ blurred, int w, int h, const int
     if (lane == 0) { a = (float)cos((double)angle); b = (float)sin((double)angle); }      // one double-precision pair per key point
     a = __shfl_sync(0xffffffffu, a, 0);
     b = __shfl_sync(0xffffffffu, b, 0);
-    const uint8_t* center = blurred + (size_t)f * w * h + (size_t)y0 * w + x0;
+    const uint8_t* center = blurred + (size_t)f * bpitch * h + (size_t)y0 * bpitch + x0;
     int val = 0;
 #pragma unroll
     for (int i = 0; i < 8; i++) {
@@ -363,7 +363,7 @@ orb_describe_kernel(const uint8_t* __restrict__ blurred, int w, int h, const int
             const float px = (float)t[2 * q], py = (float)t[2 * q + 1];
             const float x = __fsub_rn(__fmul_rn(px, a), __fmul_rn(py, b));
             const float y = __fadd_rn(__fmul_rn(px, b), __fmul_rn(py, a));
-            v[q] = __ldg(center + __float2int_rn(y) * w + __float2int_rn(x));
+            v[q] = __ldg(center + __float2int_rn(y) * bpitch + __float2int_rn(x));
         }
         val |= (v[0] < v[1]) << i;
     }
@@ -395,7 +395,7 @@ __global__ void orb_resize_coeff_kernel(int sw, int sh, int dw, int dh, int4* __
 }
 __global__ void __launch_bounds__(256)
 orb_resize_kernel(const uint8_t* __restrict__ src, long long src_stride, int spitch, int sw, int sh, uint8_t* __restrict__ dst,
-                  int dw, int dh, const int4* __restrict__ tab) {
+                  int dw, int dh, int dpitch, const int4* __restrict__ tab) {
     // four adjacent output pixels per thread, one packed store
     const int xq = (blockIdx.x * 32 + (threadIdx.x & 31)) * 4, y = blockIdx.y * 8 + (threadIdx.x >> 5), f = blockIdx.z;
     if (xq >= dw || y >= dh) return;
@@ -423,9 +423,9 @@ orb_resize_kernel(const uint8_t* __restrict__ src, long long src_stride, int spi
         v = (v + (1u << 15)) >> 16;
         packed |= min(v, 255u) << (8 * j);
     }
-    uint8_t* o = dst + ((size_t)f * dh + y) * dw + xq;
-    if ((dw & 3) == 0) {
-        *reinterpret_cast<uint32_t*>(o) = packed;                  // dw % 4 == 0: all four pixels exist and the address is aligned
+    uint8_t* o = dst + ((size_t)f * dh + y) * dpitch + xq;
+    if ((dpitch & 3) == 0) {
+        *reinterpret_cast<uint32_t*>(o) = packed;                  // rows padded to a multiple of 4: the address is aligned, bytes past dw are padding
     } else {
 #pragma unroll
         for (int j = 0; j < 4; j++)
@@ -491,7 +491,8 @@ inline OrbScratch orb_scratch_carve(uint8_t*& p, int chunk, int w, int h, bool d
 // the one-level pipeline on zc frames of w x h (fcap is taken from the scratch, sized for the largest level)
 int orb_one_level(vsb_ctx_t* ctx, const OrbScratch& S, const uint8_t* in, int64_t img_stride, int pitch, int w, int h, int zc,
                   int nfeatures, int fast_threshold, int cap, int32_t* kp_xy, float* kp_resp, float* kp_angle, uint8_t* desc,
-                  int32_t* n_kp, cudaStream_t st) {
+                  int32_t* n_kp, cudaStream_t st, int bpitch = 0) {
+    if (bpitch <= 0) bpitch = w;                 // row pitch of the blurred copy (the scratch holds w0 x h0 bytes per frame)
     const int fcap = S.fcap;
     int rc = vsb_fast_detect(ctx, in, img_stride, pitch, w, h, zc, fast_threshold, 1, fcap, S.fxy, S.fsc, S.nfast, (void*)st);
     if (rc) return rc;
@@ -505,9 +506,9 @@ int orb_one_level(vsb_ctx_t* ctx, const OrbScratch& S, const uint8_t* in, int64_
     orb_angle_kernel<<<dim3(min(vsb_div_up(cap, 8), max(4, vsb_div_up(nfeatures + 64, 8))), zc), 256, 0, st>>>(in, img_stride, pitch, kp_xy, n_kp, cap, kp_angle);
     VSB_LAUNCHED(ctx);
     if (desc) {
-        orb_blur_kernel<<<dim3(vsb_div_up(w, BTW), vsb_div_up(h, BTH), zc), 256, 0, st>>>(in, img_stride, pitch, w, h, S.blurred);
+        orb_blur_kernel<<<dim3(vsb_div_up(w, BTW), vsb_div_up(h, BTH), zc), 256, 0, st>>>(in, img_stride, pitch, w, h, S.blurred, bpitch);
         VSB_LAUNCHED(ctx);
-        orb_describe_kernel<<<dim3(min(vsb_div_up(cap, 8), max(4, vsb_div_up(nfeatures + 64, 8))), zc), 256, 0, st>>>(S.blurred, w, h, kp_xy, kp_angle, n_kp, cap, desc);
+        orb_describe_kernel<<<dim3(min(vsb_div_up(cap, 8), max(4, vsb_div_up(nfeatures + 64, 8))), zc), 256, 0, st>>>(S.blurred, w, h, bpitch, kp_xy, kp_angle, n_kp, cap, desc);
         VSB_LAUNCHED(ctx);
     }
     return VSB_OK;
@@ -605,11 +606,15 @@ extern "C" int vsb_orb_detect_compute_pyr(vsb_ctx_t* ctx, const uint8_t* img, in
                 ProfScope ps(ctx, VSB_K_ORB, st);
                 orb_resize_coeff_kernel<<<vsb_div_up(nw + nh, 256), 256, 0, st>>>(cw, ch, nw, nh, rz_tab);
                 VSB_LAUNCHED(ctx);
-                orb_resize_kernel<<<dim3(vsb_div_up(nw, 128), vsb_div_up(nh, 8), zc), 256, 0, st>>>(cur, cur_stride, cp, cw, ch, dst, nw, nh, rz_tab);
+                // level images get rows padded to 16 bytes (they fit: nw <= w / 1.2), so that every reader takes its aligned
+                // word path (FAST's loader, the blur, this kernel's packed stores) whatever nw is
+                const int np = (nw + 15) & ~15;
+                orb_resize_kernel<<<dim3(vsb_div_up(nw, 128), vsb_div_up(nh, 8), zc), 256, 0, st>>>(cur, cur_stride, cp, cw, ch, dst, nw, nh, np, rz_tab);
                 VSB_LAUNCHED(ctx);
-                cur = dst; cur_stride = (int64_t)nw * nh; cw = nw; ch = nh; cp = nw;
+                cur = dst; cur_stride = (int64_t)np * nh; cw = nw; ch = nh; cp = np;
             }
-            rc = orb_one_level(ctx, S, cur, cur_stride, cp, cw, ch, zc, budget[l], fast_threshold, cap, lxy, lresp, langle, ldesc, ln, st);
+            rc = orb_one_level(ctx, S, cur, cur_stride, cp, cw, ch, zc, budget[l], fast_threshold, cap, lxy, lresp, langle, ldesc, ln, st,
+                               l > 0 ? cp : 0);
             if (rc) return rc;
             ProfScope ps(ctx, VSB_K_ORB, st);
             orb_append_kernel<<<dim3(vsb_div_up(cap, 256), zc), 256, 0, st>>>(
