@@ -150,3 +150,28 @@ def test_orb_pyramid_batch_vs_oracle(ctx, oracle):
                 assert np.array_equal(xy, oxy[:m]) and np.array_equal(octv, ooct[:m])
                 assert np.array_equal(resp, oresp[:m]) and np.array_equal(ang, oang[:m])
                 assert np.array_equal(desc, odesc[:m])
+
+
+@pytest.mark.parametrize("w,h,sf,nl", [(752, 480, 1.2, 8), (1241, 376, 1.2, 8), (640, 480, 2.0, 3), (333, 201, 1.05, 6),
+                                       (501, 303, 1.7, 4), (752, 480, 2.5, 3)])
+def test_orb_pyramid_forms_agree(ctx, w, h, sf, nl):
+    """The word-based resize (four columns x eight rows per thread, folded border taps) and the per-warp trigonometry pre-pass
+    against the per-pixel / per-warp forms they replace ("orb_impl" bit mask), incl. unaligned level-0 rows (1241), scale
+    factors up to 2 and beyond (2.5: the generic kernel serves both settings) — every output array identical."""
+    rng = np.random.default_rng(w + h)
+    frames = []
+    for s in range(2):
+        f = (rng.random((h, w)) * 255).astype(np.float32)
+        f = (f + np.roll(f, 1, 0) + np.roll(f, 1, 1) + np.roll(f, (1, 1), (0, 1))) / 4
+        frames.append(f.astype(np.uint8))
+    imgs = np.stack(frames)
+    try:
+        ctx.option("orb_impl", 15)
+        old = run_pyr(ctx, imgs, 800, sf, nl, cap=1600)
+    finally:
+        ctx.option("orb_impl", 0)
+    new = run_pyr(ctx, imgs, 800, sf, nl, cap=1600)
+    for a, b in zip(old, new):
+        assert a[0] == b[0] and a[0] > 100
+        for x, y in zip(a[1:], b[1:]):
+            assert np.array_equal(x, y)

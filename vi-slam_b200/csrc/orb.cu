@@ -433,6 +433,88 @@ orb_resize_kernel(const uint8_t* __restrict__ src, long long src_stride, int spi
     }
 }
 
+// The same resize for the case every level of the scale pyramid is in: source rows on 4-byte boundaries and a scale of at most
+// 2.  One thread owns FOUR adjacent destination columns for RZ_ROWS destination rows.  Per source row it loads the (up to three)
+// aligned words that cover its taps, funnel-shifts them into an 8-byte window that starts at its first tap, picks every
+// column's two neighbouring bytes with one PRMT (selectors formed once per thread) and forms (256 - a) p0 + a p1 with one
+// two-way 16 x 8-bit dot product; the border cases are ordinary taps in the folded table (before the first sample: offset 0,
+// weight 0; past the last: offset size - 2, weight 256), so nothing branches per pixel.  A source row's horizontal pass is
+// kept for the next destination row when that one starts on it (scale 1.2: most of the time).  Rounded sums are below
+// 2^24 with the result in byte 2, so the four results are packed with three PRMTs.  ~12 instructions per output (the
+// per-pixel kernel above: ~55).
+constexpr int RZ_ROWS = 8;
+__global__ void orb_resize_coeff_folded_kernel(int sw, int sh, int dw, int dh, int2* __restrict__ tab) {
+    const int i = blockIdx.x * 256 + threadIdx.x;
+    if (i >= dw + dh) return;
+    int ofs, c1, edge;
+    const int ssize = i < dw ? sw : sh;
+    if (i < dw) lin_exact_coeff(i, sw, dw, ofs, c1, edge); else lin_exact_coeff(i - dw, sh, dh, ofs, c1, edge);
+    if (edge < 0) { ofs = 0; c1 = 0; }
+    else if (edge > 0) { ofs = ssize - 2; c1 = 256; }
+    tab[i] = make_int2(ofs, c1);
+}
+__device__ __forceinline__ void resize_row_taps(const uint32_t* __restrict__ rp, int wi0, int wi1, int wi2, uint32_t shift,
+                                                const uint32_t (&sel)[4], const uint32_t (&cf)[4], uint32_t (&hout)[4]) {
+    const uint32_t w0 = __ldg(rp + wi0), w1 = __ldg(rp + wi1), w2 = __ldg(rp + wi2);
+    const uint32_t a = __funnelshift_r(w0, w1, shift), b = __funnelshift_r(w1, w2, shift);
+#pragma unroll
+    for (int j = 0; j < 4; j++) hout[j] = __dp2a_lo(cf[j], __byte_perm(a, b, sel[j]), 0u);
+}
+__global__ void __launch_bounds__(256)
+orb_resize4_kernel(const uint8_t* __restrict__ src, long long src_stride, int spitch, uint8_t* __restrict__ dst, int dw, int dh,
+                   int dpitch, const int2* __restrict__ tab) {
+    const int lane = threadIdx.x & 31, wrp = threadIdx.x >> 5;
+    const int xq = (blockIdx.x * 32 + lane) * 4, yb = (blockIdx.y * 8 + wrp) * RZ_ROWS, f = blockIdx.z;
+    if (xq >= dw || yb >= dh) return;
+    // column constants: window start, byte selectors inside the window, packed weights, mask of the columns that exist
+    int ox[4];
+    uint32_t cf[4], sel[4], mask = 0u;
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        const int2 t = __ldg(tab + min(xq + j, dw - 1));
+        ox[j] = t.x;
+        cf[j] = (uint32_t)(256 - t.y) | ((uint32_t)t.y << 16);
+        if (xq + j < dw) mask |= 0xFFu << (8 * j);
+    }
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        const uint32_t d = (uint32_t)(ox[j] - ox[0]);                  // 0 .. 6 for a scale of at most 2
+        sel[j] = d | ((d + 1u) << 4);
+    }
+    const int last_word = (spitch >> 2) - 1;
+    const int wi0 = ox[0] >> 2, wi1 = min(wi0 + 1, last_word), wi2 = min(wi0 + 2, last_word);   // (a clamped word holds no tap)
+    const uint32_t shift = (uint32_t)(ox[0] & 3) * 8u;
+    const uint32_t* img = reinterpret_cast<const uint32_t*>(src + (size_t)f * src_stride);
+    const int wpitch = spitch >> 2;
+    uint8_t* out = dst + ((size_t)f * dh + yb) * dpitch + xq;
+    int have = -1;
+    uint32_t hp[4] = {0u, 0u, 0u, 0u};
+#pragma unroll 2
+    for (int k = 0; k < RZ_ROWS; k++) {
+        if (yb + k >= dh) break;
+        const int2 ty = __ldg(tab + dw + yb + k);
+        const int oy = ty.x;
+        const uint32_t ay = (uint32_t)ty.y;
+        uint32_t h0[4], h1[4];
+        if (oy == have) {                                            // (uniform over the warp: one destination row per warp)
+#pragma unroll
+            for (int j = 0; j < 4; j++) h0[j] = hp[j];
+        } else {
+            resize_row_taps(img + (size_t)oy * wpitch, wi0, wi1, wi2, shift, sel, cf, h0);
+        }
+        resize_row_taps(img + (size_t)(oy + 1) * wpitch, wi0, wi1, wi2, shift, sel, cf, h1);
+        uint32_t v[4];
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            v[j] = (256u - ay) * h0[j] + (ay * h1[j] + (1u << 15));   // < 2^24: the rounded result is byte 2
+            hp[j] = h1[j];
+        }
+        have = oy + 1;
+        const uint32_t lo = __byte_perm(v[0], v[1], 0x0062), hi = __byte_perm(v[2], v[3], 0x0062);
+        *reinterpret_cast<uint32_t*>(out + (size_t)k * dpitch) = __byte_perm(lo, hi, 0x5410) & mask;   // dpitch % 4 == 0: aligned, bytes past dw are padding
+    }
+}
+
 // appends one level's key points to the frame's list: pt = level coordinates * scale (float), octave = level
 __global__ void __launch_bounds__(256)
 orb_append_kernel(const int32_t* __restrict__ lxy, const float* __restrict__ lresp, const float* __restrict__ langle,
@@ -604,12 +686,21 @@ extern "C" int vsb_orb_detect_compute_pyr(vsb_ctx_t* ctx, const uint8_t* img, in
                 if (nw <= 2 * ORB_EDGE || nh <= 2 * ORB_EDGE) break;       // the border filter leaves nothing from here on
                 uint8_t* dst = lvl_img[l & 1];
                 ProfScope ps(ctx, VSB_K_ORB, st);
-                orb_resize_coeff_kernel<<<vsb_div_up(nw + nh, 256), 256, 0, st>>>(cw, ch, nw, nh, rz_tab);
-                VSB_LAUNCHED(ctx);
                 // level images get rows padded to 16 bytes (they fit: nw <= w / 1.2), so that every reader takes its aligned
                 // word path (FAST's loader, the blur, this kernel's packed stores) whatever nw is
                 const int np = (nw + 15) & ~15;
-                orb_resize_kernel<<<dim3(vsb_div_up(nw, 128), vsb_div_up(nh, 8), zc), 256, 0, st>>>(cur, cur_stride, cp, cw, ch, dst, nw, nh, np, rz_tab);
+                const bool words = ((reinterpret_cast<uintptr_t>(cur) | (uintptr_t)cur_stride | (uintptr_t)cp) & 3u) == 0 &&
+                                   cw >= 2 && ch >= 2 && 2 * nw >= cw && !(ctx->orb_impl & 1);
+                if (words) {
+                    orb_resize_coeff_folded_kernel<<<vsb_div_up(nw + nh, 256), 256, 0, st>>>(cw, ch, nw, nh, reinterpret_cast<int2*>(rz_tab));
+                    VSB_LAUNCHED(ctx);
+                    orb_resize4_kernel<<<dim3(vsb_div_up(nw, 128), vsb_div_up(nh, 8 * RZ_ROWS), zc), 256, 0, st>>>(
+                        cur, cur_stride, cp, dst, nw, nh, np, reinterpret_cast<const int2*>(rz_tab));
+                } else {
+                    orb_resize_coeff_kernel<<<vsb_div_up(nw + nh, 256), 256, 0, st>>>(cw, ch, nw, nh, rz_tab);
+                    VSB_LAUNCHED(ctx);
+                    orb_resize_kernel<<<dim3(vsb_div_up(nw, 128), vsb_div_up(nh, 8), zc), 256, 0, st>>>(cur, cur_stride, cp, cw, ch, dst, nw, nh, np, rz_tab);
+                }
                 VSB_LAUNCHED(ctx);
                 cur = dst; cur_stride = (int64_t)np * nh; cw = nw; ch = nh; cp = np;
             }
