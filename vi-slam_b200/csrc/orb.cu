@@ -15,8 +15,9 @@ namespace {
 
 constexpr int ORB_EDGE = 31;
 constexpr int ORB_HALF = 15;
+constexpr int ORB_KP_PER_WARP = 2;     // key points a warp of the angle / descriptor kernels is sized for (fewer, longer-lived blocks)
 
-__device__ const signed char c_pattern[256 * 4] = {
+__device__ __align__(16) const signed char c_pattern[256 * 4] = {
 #include "orb_pattern.inc"
 };
 // end of each row of the circular patch of radius 15 (orb.cpp: umax)
@@ -336,31 +337,52 @@ orb_blur_kernel(const uint8_t* __restrict__ img, long long img_stride, int pitch
 }
 
 // ---- stage 6: steered rBRIEF (computeOrbDescriptors, WTA_K = 2): one warp per key point, one descriptor byte per lane -----
+// cos / sin of every key point's angle, one THREAD per key point: inside the descriptor kernel the double-precision pair ran on
+// one lane of a warp while the other 31 waited (40 % of that kernel's issue slots, all of them latency-bound).
+__global__ void __launch_bounds__(256)
+orb_trig_kernel(const float* __restrict__ kp_angle, const int32_t* __restrict__ n_kp, int cap, int cs_stride, float2* __restrict__ cs) {
+    const int f = blockIdx.y, i = blockIdx.x * 256 + threadIdx.x;
+    if (i >= min(n_kp[f], cap)) return;
+    const float angle = __fmul_rn(kp_angle[(size_t)f * cap + i], (float)(3.14159265358979323846 / 180.f));
+    cs[(size_t)f * cs_stride + i] = make_float2((float)cos((double)angle), (float)sin((double)angle));
+}
+// A lane's eight tests (its descriptor byte) stay in eight registers for every key point the warp describes: four signed bytes
+// (x0, y0, x1, y1) per test, converted straight out of the register bytes.  (Kept in shared memory the pattern was read one
+// byte at a time at a 32-byte lane stride: eight-way bank conflicts, 55 % of the shared-memory pipe.)
 __global__ void __launch_bounds__(256)
 orb_describe_kernel(const uint8_t* __restrict__ blurred, int w, int h, int bpitch, const int32_t* __restrict__ kp_xy,
-                    const float* __restrict__ kp_angle, const int32_t* __restrict__ n_kp, int cap, uint8_t* __restrict__ desc) {
-    __shared__ signed char s_pat[1024];
-    for (int i = threadIdx.x; i < 1024; i += 256) s_pat[i] = c_pattern[i];
-    __syncthreads();
+                    const float* __restrict__ kp_angle, const float2* __restrict__ cs, int cs_stride,
+                    const int32_t* __restrict__ n_kp, int cap, uint8_t* __restrict__ desc) {
     const int f = blockIdx.y, lane = threadIdx.x & 31;
+    uint32_t pat[8];
+    {
+        const uint4* p4 = reinterpret_cast<const uint4*>(c_pattern) + 2 * lane;
+        const uint4 a = __ldg(p4), b = __ldg(p4 + 1);
+        pat[0] = a.x; pat[1] = a.y; pat[2] = a.z; pat[3] = a.w; pat[4] = b.x; pat[5] = b.y; pat[6] = b.z; pat[7] = b.w;
+    }
     const int nk = min(n_kp[f], cap);
     for (int k = blockIdx.x * 8 + (threadIdx.x >> 5); k < nk; k += gridDim.x * 8) {
     const int x0 = kp_xy[((size_t)f * cap + k) * 2], y0 = kp_xy[((size_t)f * cap + k) * 2 + 1];
-    float angle = kp_angle[(size_t)f * cap + k];
-    angle = __fmul_rn(angle, (float)(3.14159265358979323846 / 180.f));
-    float a = 0.f, b = 0.f;
-    if (lane == 0) { a = (float)cos((double)angle); b = (float)sin((double)angle); }      // one double-precision pair per key point
-    a = __shfl_sync(0xffffffffu, a, 0);
-    b = __shfl_sync(0xffffffffu, b, 0);
+    float a, b;
+    if (cs) {
+        const float2 t = __ldg(cs + (size_t)f * cs_stride + k);
+        a = t.x; b = t.y;
+    } else {
+        float angle = kp_angle[(size_t)f * cap + k];
+        angle = __fmul_rn(angle, (float)(3.14159265358979323846 / 180.f));
+        a = 0.f; b = 0.f;
+        if (lane == 0) { a = (float)cos((double)angle); b = (float)sin((double)angle); }      // one double-precision pair per key point
+        a = __shfl_sync(0xffffffffu, a, 0);
+        b = __shfl_sync(0xffffffffu, b, 0);
+    }
     const uint8_t* center = blurred + (size_t)f * bpitch * h + (size_t)y0 * bpitch + x0;
     int val = 0;
 #pragma unroll
     for (int i = 0; i < 8; i++) {
-        const signed char* t = s_pat + 4 * (8 * lane + i);
         int v[2];
 #pragma unroll
         for (int q = 0; q < 2; q++) {
-            const float px = (float)t[2 * q], py = (float)t[2 * q + 1];
+            const float px = (float)(signed char)(pat[i] >> (16 * q)), py = (float)(signed char)(pat[i] >> (16 * q + 8));
             const float x = __fsub_rn(__fmul_rn(px, a), __fmul_rn(py, b));
             const float y = __fadd_rn(__fmul_rn(px, b), __fmul_rn(py, a));
             v[q] = __ldg(center + __float2int_rn(y) * bpitch + __float2int_rn(x));
@@ -585,12 +607,19 @@ int orb_one_level(vsb_ctx_t* ctx, const OrbScratch& S, const uint8_t* in, int64_
     VSB_LAUNCHED(ctx);
     orb_select_harris_kernel<<<zc, 256, 0, st>>>(S.sel, S.resp, S.nsel, fcap, nfeatures, cap, kp_xy, kp_resp, n_kp);
     VSB_LAUNCHED(ctx);
-    orb_angle_kernel<<<dim3(min(vsb_div_up(cap, 8), max(4, vsb_div_up(nfeatures + 64, 8))), zc), 256, 0, st>>>(in, img_stride, pitch, kp_xy, n_kp, cap, kp_angle);
+    orb_angle_kernel<<<dim3(min(vsb_div_up(cap, 8), max(4, vsb_div_up(nfeatures + 64, 8 * ORB_KP_PER_WARP))), zc), 256, 0, st>>>(in, img_stride, pitch, kp_xy, n_kp, cap, kp_angle);
     VSB_LAUNCHED(ctx);
     if (desc) {
         orb_blur_kernel<<<dim3(vsb_div_up(w, BTW), vsb_div_up(h, BTH), zc), 256, 0, st>>>(in, img_stride, pitch, w, h, S.blurred, bpitch);
         VSB_LAUNCHED(ctx);
-        orb_describe_kernel<<<dim3(min(vsb_div_up(cap, 8), max(4, vsb_div_up(nfeatures + 64, 8))), zc), 256, 0, st>>>(S.blurred, w, h, bpitch, kp_xy, kp_angle, n_kp, cap, desc);
+        // (the selected-corner list is consumed by now: its space holds the key points' cos / sin, one pair per corner slot)
+        float2* cs = (ctx->orb_impl & 2) ? nullptr : reinterpret_cast<float2*>(S.sel);
+        if (cs) {
+            orb_trig_kernel<<<dim3(vsb_div_up(min(cap, fcap), 256), zc), 256, 0, st>>>(kp_angle, n_kp, cap, fcap, cs);
+            VSB_LAUNCHED(ctx);
+        }
+        orb_describe_kernel<<<dim3(min(vsb_div_up(cap, 8), max(4, vsb_div_up(nfeatures + 64, 8 * ORB_KP_PER_WARP))), zc), 256, 0, st>>>(
+            S.blurred, w, h, bpitch, kp_xy, kp_angle, cs, fcap, n_kp, cap, desc);
         VSB_LAUNCHED(ctx);
     }
     return VSB_OK;
