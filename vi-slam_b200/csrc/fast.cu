@@ -118,11 +118,15 @@ fast_score_kernel(const uint8_t* __restrict__ img, long long img_stride, int pit
     // (ring positions 0, 4, 8, 12), so a corner needs two neighbouring compass pixels that are both brighter than centre + t or
     // both darker than centre - t.  That test needs 4 of the 16 ring positions (rows y-3, y, y+3 only); the pixels that pass are
     // queued and get the full arc test from their score.
+    uint32_t inside = 0u;                                              // the 3-pixel border is never a corner
+#pragma unroll
+    for (int j = 0; j < 4; j++)
+        if (x + j >= 3 && x + j < w - 3) inside |= 0x80u << (8 * j);
+    uint32_t cand = 0u;                                                // bit 8 j + half: pixel j of row ty0 + 16 half passed
 #pragma unroll
     for (int half = 0; half < 2; half++) {
         const int ty = ty0 + 16 * half, y = y0 + ty;
         const bool in_image = x < w && y < h;
-        uint32_t corner = 0u;
         if (in_image && y >= 3 && y < h - 3) {
             const uint32_t C = s[ty + 3][wc];
             const uint32_t hi = __vaddus4(C, T4), lo = __vsubus4(C, T4);   // saturating: a ring byte can never beat 255 / 0
@@ -133,34 +137,63 @@ fast_score_kernel(const uint8_t* __restrict__ img, long long img_stride, int pit
             const uint32_t d0 = gt7(lo, up), d4 = gt7(lo, rt), d8 = gt7(lo, dn), d12 = gt7(lo, lf);
             const uint32_t bb = ((b0 | b8) & (b4 | b12));                  // (b0&b4)|(b4&b8)|(b8&b12)|(b12&b0)
             const uint32_t dd = ((d0 | d8) & (d4 | d12));
-            corner = (bb | dd) & 0x80808080u;
+            cand |= ((bb | dd) & inside) >> (7 - half);
         }
         // every pixel gets its byte now (0 = no corner); the candidates are queued for the arc test / score pass below
         if (in_image) *reinterpret_cast<uint32_t*>(out + (size_t)y * sw + x) = 0u;      // x is a multiple of 4 and x + 3 < sw
-        if (corner) {
+    }
+    // Queue the candidates: ONE shared-memory atomic per warp (inclusive scan of the per-thread counts), then every thread
+    // writes its own.  (One atomic per pixel position cost eight warp-aggregated atomics per thread as soon as one lane of the
+    // warp had a candidate there — with a tenth of the pixels passing, always.)  The order of the queue does not matter: every
+    // entry is scored on its own and written to its own pixel.
+    {
+        const int lane = threadIdx.x & 31;
+        const int n = __popc(cand);
+        int incl = n;
 #pragma unroll
-            for (int j = 0; j < 4; j++)
-                if (((corner >> (8 * j + 7)) & 1u) && x + j >= 3 && x + j < w - 3)      // the 3-pixel border is never a corner
-                    s_list[atomicAdd(&s_count, 1)] = (uint16_t)((ty << 6) | (4 * (wc - 1) + j));
+        for (int off = 1; off < 32; off <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, incl, off);
+            if (lane >= off) incl += t;
+        }
+        const int total = __shfl_sync(0xffffffffu, incl, 31);
+        if (total) {
+            int base = 0;
+            if (lane == 31) base = atomicAdd(&s_count, total);
+            base = __shfl_sync(0xffffffffu, base, 31) + incl - n;
+            while (cand) {
+                const int b = __ffs(cand) - 1;
+                cand &= cand - 1u;
+                s_list[base++] = (uint16_t)(((ty0 + 16 * (b & 1)) << 6) | (4 * (wc - 1) + (b >> 3)));
+            }
         }
     }
     __syncthreads();
     // ---- score pass: one thread per queued candidate (dense), ring bytes from the shared tile ------------------------------
+    // Both polarities at once in the two 16-bit lanes of a register, biased by 256 so that the lanes stay unsigned:
+    // low = 256 + centre - ring, high = 256 + ring - centre = kv + ring * 0xFFFF (the low lane stays >= 1, so no borrow crosses
+    // the lanes).  min over the 9 positions of an arc as min3(min3, min3, min3) of shared triples, max over the 16 arcs.
     const uint8_t* sb = reinterpret_cast<const uint8_t*>(&s[0][0]);
     const int ring_x[16] = FAST_RING_X, ring_y[16] = FAST_RING_Y;
     for (int e = threadIdx.x; e < s_count; e += 256) {
         const int ly = s_list[e] >> 6, lx = s_list[e] & 63;
         const uint8_t* c = sb + (size_t)(ly + FT_HALO) * (FT_PITCH * 4) + lx + 4;
-        const int v = c[0];
-        int d[16], neg[16];
+        const uint32_t v = c[0];
+        const uint32_t kv = (v + 256u) + ((256u - v) << 16);
+        uint32_t a[16], t3[16];
 #pragma unroll
-        for (int k = 0; k < 16; k++) {
-            d[k] = v - (int)c[ring_y[k] * (FT_PITCH * 4) + ring_x[k]];
-            neg[k] = -d[k];
+        for (int k = 0; k < 16; k++) a[k] = kv + (uint32_t)c[ring_y[k] * (FT_PITCH * 4) + ring_x[k]] * 0xFFFFu;
+#pragma unroll
+        for (int k = 0; k < 16; k++) t3[k] = __vminu2(__vminu2(a[k], a[(k + 1) & 15]), a[(k + 2) & 15]);
+        uint32_t best2 = 0u;
+#pragma unroll
+        for (int k = 0; k < 16; k += 2) {
+            const uint32_t arc0 = __vminu2(__vminu2(t3[k], t3[(k + 3) & 15]), t3[(k + 6) & 15]);
+            const uint32_t arc1 = __vminu2(__vminu2(t3[k + 1], t3[(k + 4) & 15]), t3[(k + 7) & 15]);
+            best2 = __vmaxu2(__vmaxu2(arc0, arc1), best2);
         }
         // largest threshold for which the pixel still has a 9-arc, plus one: the pixel is a corner iff that exceeds the
         // threshold (cv::FAST's corner test and cornerScore agree by construction); stored as score + 1, in 1..255
-        const int best = max(best_arc_min(d), best_arc_min(neg));
+        const int best = max((int)(best2 & 0xFFFFu), (int)(best2 >> 16)) - 256;
         if (best > threshold) out[(size_t)(y0 + ly) * sw + x0 + lx] = (uint8_t)best;
     }
 }
