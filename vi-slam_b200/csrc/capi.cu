@@ -58,6 +58,7 @@ extern "C" int vsb_ctx_create(int device, vsb_ctx_t** out) {
     c->gn_cluster_threads = 0;
     c->orb_scratch_mb = 8192;
     c->orb_impl = 0;
+    c->fast_impl = 0;
     c->knn_l2_impl = 1;
     if (const char* e = getenv("VSB_KNN_L2_IMPL")) c->knn_l2_impl = atoi(e) ? 1 : 0;
     if (const char* e = getenv("VSB_GN_VARIANT")) c->gn_variant = atoi(e);
@@ -70,6 +71,7 @@ extern "C" int vsb_ctx_create(int device, vsb_ctx_t** out) {
     if (const char* e = getenv("VSB_GN_CLUSTER_THREADS")) vsb_ctx_option(c, "gn_cluster_threads", atoi(e));
     if (const char* e = getenv("VSB_ORB_SCRATCH_MB")) vsb_ctx_option(c, "orb_scratch_mb", atoi(e));
     if (const char* e = getenv("VSB_ORB_IMPL")) vsb_ctx_option(c, "orb_impl", atoi(e));
+    if (const char* e = getenv("VSB_FAST_IMPL")) vsb_ctx_option(c, "fast_impl", atoi(e));
     if (const char* e = getenv("VSB_GN_THREADS")) vsb_ctx_option(c, "gn_threads", atoi(e));
     *out = c;
     return VSB_OK;
@@ -120,6 +122,11 @@ extern "C" int vsb_ctx_option(vsb_ctx_t* ctx, const char* name, int value) {
     if (!strcmp(name, "orb_scratch_mb")) {
         if (value < 16 || value > 65536) return VSB_ERR_INVALID;
         ctx->orb_scratch_mb = value;
+        return VSB_OK;
+    }
+    if (!strcmp(name, "fast_impl")) {
+        if (value < 0 || value > 1) return VSB_ERR_INVALID;
+        ctx->fast_impl = value;
         return VSB_OK;
     }
     if (!strcmp(name, "orb_impl")) {

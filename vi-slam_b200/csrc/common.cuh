@@ -61,6 +61,7 @@ struct vsb_ctx {
     int gn_cluster_threads;   // threads per block of the cluster kernel: 0 (default) = by batch size, 256, 512
     int gn_tail;      // gn_track.cu: 1 (default) = pairs of the last partial wave run with more threads each, 0 = one launch
     int orb_scratch_mb;   // ORB: scratch budget of one chunk of frames in MB (default 8192)
+    int fast_impl;    // FAST compaction: 0 (default) = 16 pixels per lane, suppression once (bit per pixel); 1 = 4 pixels per lane, suppression in both passes
     int orb_impl;     // ORB tuning switch, bit mask of the PREVIOUS forms kept for comparison (default 0): 1 = per-pixel resize, 2 = per-warp sin / cos in the descriptor kernel
     int pyr_impl;     // pyramid: 0 = generic shared-memory tile kernel, 1 = register-blocked kernel when w, h are multiples of 16
 };

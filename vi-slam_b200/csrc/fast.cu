@@ -82,7 +82,7 @@ fast_score_kernel(const uint8_t* __restrict__ img, long long img_stride, int pit
     if (threadIdx.x == 0) s_count = 0;
     const int frame = blockIdx.z;
     const uint8_t* in = img + (size_t)frame * img_stride;
-    uint8_t* out = score1 + (size_t)frame * sw * h;      // score rows are sw = round_up(w, 4) bytes apart; the pad stays 0
+    uint8_t* out = score1 + (size_t)frame * sw * h;      // score rows are sw = round_up(w, 16) bytes apart; the pad is 0
     const int x0 = blockIdx.x * FT_W, y0 = blockIdx.y * FT_H;
     const bool aligned_in = ((reinterpret_cast<uintptr_t>(in) | (uintptr_t)pitch) & 3u) == 0;
     {
@@ -140,7 +140,7 @@ fast_score_kernel(const uint8_t* __restrict__ img, long long img_stride, int pit
             cand |= ((bb | dd) & inside) >> (7 - half);
         }
         // every pixel gets its byte now (0 = no corner); the candidates are queued for the arc test / score pass below
-        if (in_image) *reinterpret_cast<uint32_t*>(out + (size_t)y * sw + x) = 0u;      // x is a multiple of 4 and x + 3 < sw
+        if (x < sw && y < h) *reinterpret_cast<uint32_t*>(out + (size_t)y * sw + x) = 0u;   // x is a multiple of 4 and x + 3 < sw; the row's padding is zeroed too
     }
     // Queue the candidates: ONE shared-memory atomic per warp (inclusive scan of the per-thread counts), then every thread
     // writes its own.  (One atomic per pixel position cost eight warp-aggregated atomics per thread as soon as one lane of the
@@ -314,6 +314,93 @@ fast_write4_kernel(const uint8_t* __restrict__ score1, int w, int h, int nonmax,
     }
 }
 
+// ---- compaction, 16 pixels per lane (score rows 16 bytes aligned) -------------------------------------------------------
+// The suppression runs ONCE: the count pass loads 16 score bytes per lane (almost always zero: nothing more to do), runs
+// keep_of4 on the non-zero words and leaves one bit per pixel (a uint16 per 16 pixels) next to the row's count; the write pass
+// reads the bits only, plus the score byte of every corner it writes.
+__global__ void __launch_bounds__(256)
+fast_count16_kernel(const uint8_t* __restrict__ score1, int sw, int h, int nonmax, int32_t* __restrict__ row_count,
+                    uint16_t* __restrict__ bits) {
+    const int y = blockIdx.x * 8 + (threadIdx.x >> 5), frame = blockIdx.y, lane = threadIdx.x & 31;
+    if (y >= h) return;
+    int n = 0;
+    if (y >= 3 && y < h - 3) {
+        const uint8_t* sc = score1 + (size_t)frame * sw * h;
+        const uint32_t* r0 = reinterpret_cast<const uint32_t*>(sc + (size_t)(y - 1) * sw);
+        const uint32_t* r1 = reinterpret_cast<const uint32_t*>(sc + (size_t)y * sw);
+        const uint32_t* r2 = reinterpret_cast<const uint32_t*>(sc + (size_t)(y + 1) * sw);
+        const uint4* v1 = reinterpret_cast<const uint4*>(r1);
+        const int vecs = sw >> 4;
+        uint16_t* brow = bits + ((size_t)frame * h + y) * vecs;
+        for (int q0 = 0; q0 < vecs; q0 += 64) {
+            uint4 c[2];
+#pragma unroll
+            for (int j = 0; j < 2; j++) {
+                const int q = q0 + 32 * j + lane;
+                c[j] = q < vecs ? __ldg(v1 + q) : make_uint4(0u, 0u, 0u, 0u);
+            }
+#pragma unroll
+            for (int j = 0; j < 2; j++) {
+                const int q = q0 + 32 * j + lane;
+                if (q >= vecs) continue;
+                const uint32_t cw[4] = {c[j].x, c[j].y, c[j].z, c[j].w};
+                uint32_t m = 0u;
+#pragma unroll
+                for (int t = 0; t < 4; t++)
+                    if (cw[t] != 0u) {
+                        const uint32_t keep = keep_of4(r0, r1, r2, 4 * q + t, nonmax, cw[t]);
+                        m |= (((keep & 0x08040201u) * 0x01010101u) >> 24) << (4 * t);      // one bit per byte, gathered
+                    }
+                brow[q] = (uint16_t)m;
+                n += __popc(m);
+            }
+        }
+    }
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) n += __shfl_down_sync(0xffffffffu, n, off);
+    if (lane == 0) row_count[(size_t)frame * h + y] = n;
+}
+
+__global__ void __launch_bounds__(256)
+fast_write16_kernel(const uint8_t* __restrict__ score1, int sw, int h, int nonmax, const int32_t* __restrict__ row_offset,
+                    const int32_t* __restrict__ row_count, const uint16_t* __restrict__ bits, int cap,
+                    int32_t* __restrict__ kp_xy, int32_t* __restrict__ kp_score) {
+    const int y = blockIdx.x * 8 + (threadIdx.x >> 5), frame = blockIdx.y, lane = threadIdx.x & 31;
+    if (y < 3 || y >= h - 3) return;
+    if (row_count[(size_t)frame * h + y] == 0) return;     // about half of the rows of a natural image hold no corner
+    int base = row_offset[(size_t)frame * h + y];
+    if (base >= cap) return;
+    const uint8_t* srow = score1 + ((size_t)frame * h + y) * sw;
+    const int vecs = sw >> 4;
+    const uint16_t* brow = bits + ((size_t)frame * h + y) * vecs;
+    int32_t* oxy = kp_xy + (size_t)frame * cap * 2;
+    int32_t* osc = kp_score + (size_t)frame * cap;
+    for (int q0 = 0; q0 < vecs; q0 += 32) {
+        const int q = q0 + lane;
+        uint32_t m = q < vecs ? (uint32_t)brow[q] : 0u;
+        if (!__any_sync(0xffffffffu, m != 0u)) continue;
+        const int cnt = __popc(m);
+        int incl = cnt;                                    // inclusive warp scan of the per-lane counts
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+            const int v = __shfl_up_sync(0xffffffffu, incl, off);
+            if (lane >= off) incl += v;
+        }
+        int slot = base + incl - cnt;
+        while (m) {
+            const int x = 16 * q + __ffs(m) - 1;
+            m &= m - 1u;
+            if (slot < cap) {
+                oxy[2 * slot] = x; oxy[2 * slot + 1] = y;
+                osc[slot] = nonmax ? (int)__ldg(srow + x) - 1 : 0;
+            }
+            slot++;
+        }
+        base += __shfl_sync(0xffffffffu, incl, 31);
+        if (base >= cap) return;
+    }
+}
+
 }  // namespace
 
 // FAST-9/16 corners of `count` frames (cv::FAST, TYPE_9_16).  img: frames of h rows x pitch bytes, img_stride bytes apart.
@@ -326,21 +413,25 @@ extern "C" int vsb_fast_detect(vsb_ctx_t* ctx, const uint8_t* img, int64_t img_s
     if (w <= 0 || h <= 0 || pitch < w || count < 0 || cap < 0 || threshold < 0 || threshold > 255) return VSB_ERR_INVALID;
     if (count == 0) return VSB_OK;
     cudaStream_t st = (cudaStream_t)stream;
-    // score rows are padded to a multiple of 4 bytes (zero pad = "no corner"), so the 4-pixels-per-lane compaction kernels
+    // score rows are padded to a multiple of 16 bytes (zero pad = "no corner"), so the 16-pixels-per-lane compaction kernels
     // serve every width; words that straddle a row end only ever see border / pad zeros
-    const int sw = (w + 3) & ~3;
+    const int sw = (w + 15) & ~15;
     const size_t img_bytes = ((size_t)count * sw * h + 255) & ~(size_t)255;
     const size_t rows_bytes = ((size_t)count * h * sizeof(int32_t) + 255) & ~(size_t)255;
+    const size_t bits_bytes = ((size_t)count * h * (sw >> 4) * sizeof(uint16_t) + 255) & ~(size_t)255;
     void* scratch = nullptr;
-    int rc = vsb_scratch_reserve(ctx, img_bytes + 2 * rows_bytes + 256, &scratch);
+    int rc = vsb_scratch_reserve(ctx, img_bytes + 2 * rows_bytes + bits_bytes + 256, &scratch);
     if (rc) return rc;
     uint8_t* score1 = static_cast<uint8_t*>(scratch);
     int32_t* row_count = reinterpret_cast<int32_t*>(score1 + img_bytes);
     int32_t* row_offset = reinterpret_cast<int32_t*>(score1 + img_bytes + rows_bytes);
+    uint16_t* bits = reinterpret_cast<uint16_t*>(score1 + img_bytes + 2 * rows_bytes);
+    const bool per_word = ctx->fast_impl == 1;               // the previous compaction (suppression in both passes), kept for comparison
     for (int z0 = 0; z0 < count; z0 += 65535) {
         const int zc = count - z0 < 65535 ? count - z0 : 65535;
         const uint8_t* in = img + (size_t)z0 * img_stride;
         uint8_t* sc = score1 + (size_t)z0 * sw * h;
+        uint16_t* bz = bits + (size_t)z0 * h * (sw >> 4);
         {
             ProfScope ps(ctx, VSB_K_FAST_SCORE, st);
             fast_score_kernel<<<dim3(vsb_div_up(w, FT_W), vsb_div_up(h, FT_H), zc), 256, 0, st>>>(in, img_stride, pitch, w, h,
@@ -348,14 +439,20 @@ extern "C" int vsb_fast_detect(vsb_ctx_t* ctx, const uint8_t* img, int64_t img_s
             VSB_LAUNCHED(ctx);
         }
         ProfScope ps(ctx, VSB_K_FAST_COMPACT, st);
-        fast_count4_kernel<<<dim3(vsb_div_up(h, 8), zc), 256, 0, st>>>(sc, sw, h, nonmax, row_count + (size_t)z0 * h);
+        if (per_word) fast_count4_kernel<<<dim3(vsb_div_up(h, 8), zc), 256, 0, st>>>(sc, sw, h, nonmax, row_count + (size_t)z0 * h);
+        else fast_count16_kernel<<<dim3(vsb_div_up(h, 8), zc), 256, 0, st>>>(sc, sw, h, nonmax, row_count + (size_t)z0 * h, bz);
         VSB_LAUNCHED(ctx);
         fast_scan_kernel<<<zc, 256, 0, st>>>(row_count + (size_t)z0 * h, h, row_offset + (size_t)z0 * h, n_kp + z0);
         VSB_LAUNCHED(ctx);
         if (cap > 0) {
-            fast_write4_kernel<<<dim3(vsb_div_up(h, 8), zc), 256, 0, st>>>(sc, sw, h, nonmax, row_offset + (size_t)z0 * h,
-                                                                           row_count + (size_t)z0 * h, cap,
-                                                                           kp_xy + (size_t)z0 * cap * 2, kp_score + (size_t)z0 * cap);
+            if (per_word)
+                fast_write4_kernel<<<dim3(vsb_div_up(h, 8), zc), 256, 0, st>>>(sc, sw, h, nonmax, row_offset + (size_t)z0 * h,
+                                                                               row_count + (size_t)z0 * h, cap,
+                                                                               kp_xy + (size_t)z0 * cap * 2, kp_score + (size_t)z0 * cap);
+            else
+                fast_write16_kernel<<<dim3(vsb_div_up(h, 8), zc), 256, 0, st>>>(sc, sw, h, nonmax, row_offset + (size_t)z0 * h,
+                                                                                row_count + (size_t)z0 * h, bz, cap,
+                                                                                kp_xy + (size_t)z0 * cap * 2, kp_score + (size_t)z0 * cap);
             VSB_LAUNCHED(ctx);
         }
     }

@@ -250,10 +250,11 @@ orb_angle_kernel(const uint8_t* __restrict__ img, long long img_stride, int pitc
 // pass four adjacent outputs packed into one 32-bit store.  Every output is the same sequence of rounded operations as the
 // oracle's: s = x0 k0, s = fma(x_i, k_i, s) along the row; s = r3 k3, s = fma(r[3+i] + r[3-i], k[3+i], s) down the column.
 constexpr int BTW = 64, BTH = 32, BTP = 72;
+// BORDER_REFLECT_101 index for positions at most n - 1 outside the range (the blur reaches 3 outside an image of more than 62
+// pixels), branch-free; positions further out — tile padding nobody reads — are clamped into the range.
 __device__ __forceinline__ int refl101(int p, int n) {
-    if (n == 1) return 0;
-    while (p < 0 || p >= n) { if (p < 0) p = -p; if (p >= n) p = 2 * n - 2 - p; }
-    return p;
+    const int a = abs(p);
+    return max(min(a, 2 * n - 2 - a), 0);
 }
 __global__ void __launch_bounds__(256)
 orb_blur_kernel(const uint8_t* __restrict__ img, long long img_stride, int pitch, int w, int h, uint8_t* __restrict__ out, int opitch) {
@@ -266,10 +267,10 @@ orb_blur_kernel(const uint8_t* __restrict__ img, long long img_stride, int pitch
         const int ry = i / (BTP / 4), wx = i - ry * (BTP / 4);
         const int gy = y0 + ry - 3, gx = x0 - 4 + 4 * wx;
         uint32_t v;
-        if (words_ok && gy >= 0 && gy < h && gx >= 0 && gx + 3 < w) {
-            v = __ldg(reinterpret_cast<const uint32_t*>(src + (size_t)gy * pitch + gx));
+        const uint8_t* row = src + (size_t)refl101(gy, h) * pitch;
+        if (words_ok && gx >= 0 && gx + 3 < w) {
+            v = __ldg(reinterpret_cast<const uint32_t*>(row + gx));
         } else {
-            const uint8_t* row = src + (size_t)refl101(gy, h) * pitch;
             v = 0u;
 #pragma unroll
             for (int j = 0; j < 4; j++) v |= (uint32_t)__ldg(row + refl101(gx + j, w)) << (8 * j);
