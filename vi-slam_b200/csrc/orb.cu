@@ -249,19 +249,42 @@ orb_angle_kernel(const uint8_t* __restrict__ img, long long img_stride, int pitc
 // loaded as aligned 32-bit words where the image allows it; the row pass produces four adjacent outputs per thread, the column
 // pass four adjacent outputs packed into one 32-bit store.  Every output is the same sequence of rounded operations as the
 // oracle's: s = x0 k0, s = fma(x_i, k_i, s) along the row; s = r3 k3, s = fma(r[3+i] + r[3-i], k[3+i], s) down the column.
-constexpr int BTW = 64, BTH = 32, BTP = 72;
+constexpr int BTW = 64, BTH = 32;
 // BORDER_REFLECT_101 index for positions at most n - 1 outside the range (the blur reaches 3 outside an image of more than 62
 // pixels), branch-free; positions further out — tile padding nobody reads — are clamped into the range.
 __device__ __forceinline__ int refl101(int p, int n) {
     const int a = abs(p);
     return max(min(a, 2 * n - 2 - a), 0);
 }
+// VEC: frames whose base, stride and pitch are multiples of 16 (every level image; 752- and 640-wide frames): the tile is loaded
+// as 16-byte vectors from x0 - 16 on (6 per row, one per thread, rows outside the image from their reflected row), and the
+// up to six columns outside the image are then copied from their reflections inside the tile.
+template <bool VEC>
 __global__ void __launch_bounds__(256)
 orb_blur_kernel(const uint8_t* __restrict__ img, long long img_stride, int pitch, int w, int h, uint8_t* __restrict__ out, int opitch) {
-    __shared__ __align__(16) uint8_t s_in[BTH + 6][BTP];          // columns x0 - 4 .. x0 + 67
+    constexpr int XOFF = VEC ? 16 : 4;                            // tile column of x0
+    constexpr int BTP = VEC ? 192 : 72;                           // row pitch of the tile in bytes
+    __shared__ __align__(16) uint8_t s_in[BTH + 6][BTP];          // columns x0 - XOFF ..
     __shared__ __align__(16) float s_row[BTH + 6][BTW];
     const int f = blockIdx.z, x0 = blockIdx.x * BTW, y0 = blockIdx.y * BTH, tid = threadIdx.x;
     const uint8_t* src = img + (size_t)f * img_stride;
+    if (VEC) {
+        if (tid < (BTH + 6) * 6) {
+            const int ry = tid / 6, pc = tid - 6 * ry;
+            const int gx = x0 - 16 + 16 * pc;
+            uint4 v = make_uint4(0u, 0u, 0u, 0u);
+            if (gx >= 0 && gx + 15 < pitch) v = __ldg(reinterpret_cast<const uint4*>(src + (size_t)refl101(y0 + ry - 3, h) * pitch + gx));
+            *reinterpret_cast<uint4*>(&s_in[ry][16 * pc]) = v;
+        }
+        if (x0 == 0 || x0 + BTW + 3 > w) {                       // (uniform) a tile that reaches past the left or right border
+            __syncthreads();
+            if (tid < (BTH + 6) * 6) {
+                const int ry = tid / 6, k = tid - 6 * ry;
+                const int x = k < 3 ? k - 3 : w + k - 3;          // -3 .. -1, w .. w + 2
+                if (x >= x0 - 3 && x < x0 + BTW + 3) s_in[ry][x - x0 + 16] = s_in[ry][refl101(x, w) - x0 + 16];
+            }
+        }
+    } else {
     const bool words_ok = ((reinterpret_cast<uintptr_t>(src) | (uintptr_t)pitch) & 3u) == 0;
     for (int i = tid; i < (BTH + 6) * (BTP / 4); i += 256) {
         const int ry = i / (BTP / 4), wx = i - ry * (BTP / 4);
@@ -277,6 +300,7 @@ orb_blur_kernel(const uint8_t* __restrict__ img, long long img_stride, int pitch
         }
         *reinterpret_cast<uint32_t*>(&s_in[ry][4 * wx]) = v;
     }
+    }
     __syncthreads();
     float k[7];
 #pragma unroll
@@ -285,7 +309,7 @@ orb_blur_kernel(const uint8_t* __restrict__ img, long long img_stride, int pitch
     for (int i = tid; i < (BTH + 6) * (BTW / 4); i += 256) {
         const int ry = i / (BTW / 4), q = i - ry * (BTW / 4);
         // outputs x0 + 4q .. +3 need inputs x0 + 4q - 3 .. x0 + 4q + 6 = tile bytes 4q + 1 .. 4q + 10: three aligned words
-        const uint32_t* wp = reinterpret_cast<const uint32_t*>(&s_in[ry][4 * q]);
+        const uint32_t* wp = reinterpret_cast<const uint32_t*>(&s_in[ry][4 * q + XOFF - 4]);
         const uint32_t w0 = wp[0], w1 = wp[1], w2 = wp[2];
         float px[12];
 #pragma unroll
@@ -611,7 +635,11 @@ int orb_one_level(vsb_ctx_t* ctx, const OrbScratch& S, const uint8_t* in, int64_
     orb_angle_kernel<<<dim3(min(vsb_div_up(cap, 8), max(4, vsb_div_up(nfeatures + 64, 8 * ORB_KP_PER_WARP))), zc), 256, 0, st>>>(in, img_stride, pitch, kp_xy, n_kp, cap, kp_angle);
     VSB_LAUNCHED(ctx);
     if (desc) {
-        orb_blur_kernel<<<dim3(vsb_div_up(w, BTW), vsb_div_up(h, BTH), zc), 256, 0, st>>>(in, img_stride, pitch, w, h, S.blurred, bpitch);
+        const dim3 bgrid(vsb_div_up(w, BTW), vsb_div_up(h, BTH), zc);
+        if ((((uintptr_t)in | (uintptr_t)img_stride | (uintptr_t)pitch) & 15u) == 0 && !(ctx->orb_impl & 4))
+            orb_blur_kernel<true><<<bgrid, 256, 0, st>>>(in, img_stride, pitch, w, h, S.blurred, bpitch);
+        else
+            orb_blur_kernel<false><<<bgrid, 256, 0, st>>>(in, img_stride, pitch, w, h, S.blurred, bpitch);
         VSB_LAUNCHED(ctx);
         // (the selected-corner list is consumed by now: its space holds the key points' cos / sin, one pair per corner slot)
         float2* cs = (ctx->orb_impl & 2) ? nullptr : reinterpret_cast<float2*>(S.sel);
