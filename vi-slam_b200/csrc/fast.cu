@@ -358,13 +358,32 @@ fast_count16_kernel(const uint8_t* __restrict__ score1, int sw, int h, int nonma
                 const int q = q0 + 32 * j + lane;
                 if (q >= vecs) continue;
                 const uint32_t cw[4] = {c[j].x, c[j].y, c[j].z, c[j].w};
-                uint32_t m = 0u;
+                uint32_t nz = 0u;                                  // one bit per non-zero score byte
 #pragma unroll
-                for (int t = 0; t < 4; t++)
-                    if (cw[t] != 0u) {
-                        const uint32_t keep = keep_of4(r0, r1, r2, 4 * q + t, nonmax, cw[t]);
-                        m |= (((keep & 0x08040201u) * 0x01010101u) >> 24) << (4 * t);      // one bit per byte, gathered
+                for (int t = 0; t < 4; t++) {
+                    const uint32_t b7 = (cw[t] | ((cw[t] & 0x7f7f7f7fu) + 0x7f7f7f7fu)) & 0x80808080u;
+                    nz |= ((((b7 >> 7) & 0x01010101u) * 0x01020408u) >> 24 & 0xFu) << (4 * t);
+                }
+                // corners are a few percent of the pixels: each one is tested on its own bytes (nine byte loads that hit L1)
+                // instead of running the packed 3x3 maximum on every word that holds one
+                uint32_t m = 0u;
+                const uint8_t* b0 = reinterpret_cast<const uint8_t*>(r0);
+                const uint8_t* b1 = reinterpret_cast<const uint8_t*>(r1);
+                const uint8_t* b2 = reinterpret_cast<const uint8_t*>(r2);
+                while (nz) {
+                    const int b = __ffs(nz) - 1;
+                    nz &= nz - 1u;
+                    const int x = 16 * q + b;
+                    bool keep = true;
+                    if (nonmax) {
+                        const int cur = __ldg(b1 + x);
+                        const int n0 = max(max((int)__ldg(b0 + x - 1), (int)__ldg(b0 + x)), (int)__ldg(b0 + x + 1));
+                        const int n1 = max((int)__ldg(b1 + x - 1), (int)__ldg(b1 + x + 1));
+                        const int n2 = max(max((int)__ldg(b2 + x - 1), (int)__ldg(b2 + x)), (int)__ldg(b2 + x + 1));
+                        keep = cur > max(max(n0, n1), max(n2, 1));
                     }
+                    if (keep) m |= 1u << b;
+                }
                 brow[q] = (uint16_t)m;
                 n += __popc(m);
             }
