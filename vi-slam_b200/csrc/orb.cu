@@ -215,7 +215,7 @@ __device__ __forceinline__ float fast_atan2_deg(float y, float x) {
     if (y < 0.f) a = __fsub_rn(360.f, a);
     return a;
 }
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 4)
 orb_angle_kernel(const uint8_t* __restrict__ img, long long img_stride, int pitch, const int32_t* __restrict__ kp_xy,
                  const int32_t* __restrict__ n_kp, int cap, float* __restrict__ kp_angle) {
     const int f = blockIdx.y, lane = threadIdx.x & 31;
@@ -374,7 +374,7 @@ orb_trig_kernel(const float* __restrict__ kp_angle, const int32_t* __restrict__ 
 // A lane's eight tests (its descriptor byte) stay in eight registers for every key point the warp describes: four signed bytes
 // (x0, y0, x1, y1) per test, converted straight out of the register bytes.  (Kept in shared memory the pattern was read one
 // byte at a time at a 32-byte lane stride: eight-way bank conflicts, 55 % of the shared-memory pipe.)
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 3)
 orb_describe_kernel(const uint8_t* __restrict__ blurred, int w, int h, int bpitch, const int32_t* __restrict__ kp_xy,
                     const float* __restrict__ kp_angle, const float2* __restrict__ cs, int cs_stride,
                     const int32_t* __restrict__ n_kp, int cap, uint8_t* __restrict__ desc) {
