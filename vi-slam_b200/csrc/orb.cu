@@ -96,7 +96,7 @@ orb_select_fast_kernel(const int32_t* __restrict__ fxy, const int32_t* __restric
 }
 
 // ---- stage 2: Harris response of every selected corner (HarrisResponses, blockSize 7, k 0.04) --------------------------
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, 8)
 orb_harris_kernel(const uint8_t* __restrict__ img, long long img_stride, int pitch, const int32_t* __restrict__ sel_xy,
                   const int32_t* __restrict__ n_sel, int fcap, float* __restrict__ resp) {
     const int f = blockIdx.y;
@@ -215,7 +215,7 @@ __device__ __forceinline__ float fast_atan2_deg(float y, float x) {
     if (y < 0.f) a = __fsub_rn(360.f, a);
     return a;
 }
-__global__ void __launch_bounds__(256, 4)
+__global__ void __launch_bounds__(256, 6)
 orb_angle_kernel(const uint8_t* __restrict__ img, long long img_stride, int pitch, const int32_t* __restrict__ kp_xy,
                  const int32_t* __restrict__ n_kp, int cap, float* __restrict__ kp_angle) {
     const int f = blockIdx.y, lane = threadIdx.x & 31;
@@ -374,7 +374,7 @@ orb_trig_kernel(const float* __restrict__ kp_angle, const int32_t* __restrict__ 
 // A lane's eight tests (its descriptor byte) stay in eight registers for every key point the warp describes: four signed bytes
 // (x0, y0, x1, y1) per test, converted straight out of the register bytes.  (Kept in shared memory the pattern was read one
 // byte at a time at a 32-byte lane stride: eight-way bank conflicts, 55 % of the shared-memory pipe.)
-__global__ void __launch_bounds__(256, 3)
+__global__ void __launch_bounds__(256, 4)
 orb_describe_kernel(const uint8_t* __restrict__ blurred, int w, int h, int bpitch, const int32_t* __restrict__ kp_xy,
                     const float* __restrict__ kp_angle, const float2* __restrict__ cs, int cs_stride,
                     const int32_t* __restrict__ n_kp, int cap, uint8_t* __restrict__ desc) {
