@@ -215,7 +215,7 @@ __device__ __forceinline__ float fast_atan2_deg(float y, float x) {
     if (y < 0.f) a = __fsub_rn(360.f, a);
     return a;
 }
-__global__ void __launch_bounds__(256, 6)
+__global__ void __launch_bounds__(256, 8)
 orb_angle_kernel(const uint8_t* __restrict__ img, long long img_stride, int pitch, const int32_t* __restrict__ kp_xy,
                  const int32_t* __restrict__ n_kp, int cap, float* __restrict__ kp_angle) {
     const int f = blockIdx.y, lane = threadIdx.x & 31;
@@ -347,8 +347,9 @@ orb_blur_kernel(const uint8_t* __restrict__ img, long long img_stride, int pitch
             float acc = __fmul_rn(c0[12], k[3]);
 #pragma unroll
             for (int t = 1; t <= 3; t++) acc = __fmaf_rn(__fadd_rn(c0[4 * (3 + t)], c0[4 * (3 - t)]), k[3 + t], acc);
-            const int v = min(max(__float2int_rn(acc), 0), 255);
-            packed |= (uint32_t)v << (8 * j);
+            uint32_t v;                                           // cv::saturate_cast<uchar>(cvRound(acc)): the conversion saturates by itself
+            asm("cvt.rni.u8.f32 %0, %1;" : "=r"(v) : "f"(acc));
+            packed |= v << (8 * j);
         }
         uint8_t* o = dst + (size_t)y * opitch + x;
         if (store_words && x + 3 < opitch) {                 // (bytes past w land in the row's padding)
