@@ -153,7 +153,7 @@ def test_orb_pyramid_batch_vs_oracle(ctx, oracle):
 
 
 @pytest.mark.parametrize("w,h,sf,nl", [(752, 480, 1.2, 8), (1241, 376, 1.2, 8), (640, 480, 2.0, 3), (333, 201, 1.05, 6),
-                                       (501, 303, 1.7, 4), (752, 480, 2.5, 3)])
+                                       (501, 303, 1.7, 4), (752, 480, 2.5, 3), (750, 470, 1.002, 3)])
 def test_orb_pyramid_forms_agree(ctx, w, h, sf, nl):
     """The word-based resize (four columns x eight rows per thread, folded border taps) and the per-warp trigonometry pre-pass
     against the per-pixel / per-warp forms they replace ("orb_impl" bit mask), incl. unaligned level-0 rows (1241), scale

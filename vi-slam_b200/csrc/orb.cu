@@ -601,7 +601,7 @@ inline size_t orb_al(size_t b) { return (b + 255) & ~(size_t)255; }
 inline size_t orb_scratch_bytes(int chunk, int w, int h, bool describe) {
     const size_t fcap = (size_t)w * h / 4 + 16;
     return 2 * orb_al(chunk * fcap * 8) + orb_al(chunk * fcap * 4) + orb_al(chunk * fcap * 4) + 2 * orb_al((size_t)chunk * 4) +
-           (describe ? orb_al((size_t)chunk * w * h) : 0);
+           (describe ? orb_al((size_t)chunk * ((w + 15) & ~15) * h) : 0);       // (rows of the level images are padded to 16 bytes)
 }
 inline OrbScratch orb_scratch_carve(uint8_t*& p, int chunk, int w, int h, bool describe) {
     OrbScratch s;
@@ -614,7 +614,7 @@ inline OrbScratch orb_scratch_carve(uint8_t*& p, int chunk, int w, int h, bool d
     s.nfast = reinterpret_cast<int32_t*>(p); p += orb_al((size_t)chunk * 4);
     s.nsel = reinterpret_cast<int32_t*>(p); p += orb_al((size_t)chunk * 4);
     s.blurred = describe ? p : nullptr;
-    if (describe) p += orb_al((size_t)chunk * w * h);
+    if (describe) p += orb_al((size_t)chunk * ((w + 15) & ~15) * h);
     return s;
 }
 
@@ -712,9 +712,10 @@ extern "C" int vsb_orb_detect_compute_pyr(vsb_ctx_t* ctx, const uint8_t* img, in
     }
     const bool describe = desc != nullptr;
     const size_t tmp_frame = orb_al((size_t)cap * 8) + 2 * orb_al((size_t)cap * 4) + (describe ? orb_al((size_t)cap * 32) : 0);
-    const size_t per_frame = orb_scratch_bytes(1, w, h, describe) + 2 * orb_al((size_t)w * h) + tmp_frame + 256;
+    const size_t wpad = (size_t)((w + 15) & ~15);            // level rows are padded to 16 bytes: a level can be up to wpad x h bytes (scale factors close to 1)
+    const size_t per_frame = orb_scratch_bytes(1, w, h, describe) + 2 * orb_al(wpad * h) + tmp_frame + 256;
     const int chunk = (int)max((size_t)1, min((size_t)count, orb_scratch_budget(ctx) / per_frame));
-    const size_t b_img = orb_al((size_t)chunk * w * h);
+    const size_t b_img = orb_al((size_t)chunk * wpad * h);
     void* scratch = nullptr;
     int rc = vsb_scratch2_reserve(ctx, orb_scratch_bytes(chunk, w, h, describe) + 2 * b_img + chunk * tmp_frame + orb_al((size_t)chunk * 4) +
                                        orb_al((size_t)(w + h) * sizeof(int4)) + 1024,
