@@ -797,6 +797,25 @@ def run_gpu(args, rank, world, local_rank):
                            "same match + GN path; frames resident in HBM; the rendered frames carry far fewer corners than the "
                            "%d random descriptors of configs[1]" % (cfg["n_feat"], cfg["n_feat"]),
                    "kernels_ms": r_prof}
+            # ... and end to end: frames in pinned host memory, ORB + match + GN on the device, poses back on the host
+            # (vsb_track_sequence_orb_host: the copy of chunk i + 1 overlaps the kernels of chunk i)
+            r_pose_d = tr.track_sequence_orb(d["frames"], d["prior"], nfeatures=cfg["n_feat"], stream=g.stream)[0]
+            torch.cuda.synchronize(dev)
+            h = leg["h"]
+            trh = ctx.tracker(cfg["w"], cfg["h"], cfg["n_feat"], cfg["K"], n_cells=cfg["n_cells"],
+                              max_pairs=min(n_pairs, int(os.environ.get("VSB_BENCH_RAW_CHUNK", "1000"))))
+            r_pose = torch.zeros((n_pairs, 7), dtype=torch.float32).pin_memory()
+            trh.track_sequence_orb_host(h["frames"], h["prior"], r_pose, nfeatures=cfg["n_feat"])          # warm-up (allocations)
+            t0 = time.perf_counter()
+            for _ in range(2):
+                trh.track_sequence_orb_host(h["frames"], h["prior"], r_pose, nfeatures=cfg["n_feat"])
+            rh_ms = (time.perf_counter() - t0) * 1e3 / 2
+            rt = trh.host_traffic()
+            raw["e2e"] = {"value": n_pairs / (rh_ms * 1e-3), "unit": "frames/s", "ms_per_step": rh_ms,
+                          "h2d_bytes_per_step": int(rt["h2d"]), "d2h_bytes_per_step": int(rt["d2h"]), "host_chunks": int(rt["chunks"]),
+                          "matches_device_path": bool(torch.equal(r_pose.to(dev), r_pose_d)),
+                          "what": "vsb_track_sequence_orb_host: frames and priors from pinned host memory, nothing else"}
+            trh.close()
             leg["step_device"]()          # restore d_pose for the parity check below
             torch.cuda.synchronize(dev)
         except Exception as e:      # informational leg: never fails the bench

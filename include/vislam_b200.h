@@ -337,6 +337,14 @@ int vsb_track_sequence_host(vsb_tracker_t* t, const uint8_t* h_frames, const uin
                             const float* h_kp_xy, const int32_t* h_n_feat, const float* h_pose_prior,
                             int n_frames, float* h_pose, int32_t* h_n_good);
 
+/* The loop from images alone with HOST buffers: frames and priors are copied host->device in chunks of cfg.max_pairs
+ * pairs on a copy stream while ORB (cv::ORB::create(nfeatures), 8 levels, factor 1.2), the matcher and the solver run on
+ * the previous chunk — what the reference's CameraGPU path does per frame (upload, cv::cuda::ORB, match;
+ * src/CameraGPU.cpp:71-117, src/VISystemGPU.cpp:144-169), for a whole sequence.  h_n_good [n_frames - 1] and h_n_feat
+ * [n_frames] (key points used per frame) are optional.  Synchronous: returns when h_pose is complete. */
+int vsb_track_sequence_orb_host(vsb_tracker_t* t, const uint8_t* h_frames, const float* h_pose_prior, int n_frames,
+                                int nfeatures, float* h_pose, int32_t* h_n_good, int32_t* h_n_feat);
+
 /* Tracks `count` independent frame pairs resident on the DEVICE (BASELINE config 5):
  *   prev/cur [count][h][w] u8, d1/d2 [count][n_feat_max][desc_bytes], kp1 [count][n_feat_max][2]. */
 int vsb_track_pairs(vsb_tracker_t* t, const uint8_t* prev, const uint8_t* cur, const uint8_t* d1,

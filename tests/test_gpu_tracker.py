@@ -200,6 +200,38 @@ def test_track_sequence_from_raw_frames(ctx, oracle, n_feat_max):
     tr.close()
 
 
+@pytest.mark.parametrize("max_pairs", [2, 3, 8])
+def test_track_sequence_orb_host_matches_device_entry(ctx, max_pairs):
+    """vsb_track_sequence_orb_host (frames in pinned HOST memory, chunks of max_pairs pairs: copies on one stream, ORB + match +
+    GN on the other) returns the bits of vsb_track_sequence_orb on the whole sequence resident on the device — 7 pairs in 4, 3
+    and 1 chunks (a chunk's last frame is described again as the next chunk's first)."""
+    import torch
+    import vislam_b200 as vb
+    from vislam_b200 import synth
+    T = 8
+    seq = synth.make_sequence(T, n_feat=10, seed=2002)
+    prior = np.stack([_prior(vb, seq["R_imu_res"][k], seq["t_res"][k]) for k in range(T - 1)])
+    dev = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()
+    tr = ctx.tracker(752, 480, 1200, seq["K"], n_cells=49, max_pairs=T - 1)
+    pose_d, ng_d, nf_d = tr.track_sequence_orb(dev(seq["frames"]), dev(prior), nfeatures=1000)
+    torch.cuda.synchronize()
+    tr.close()
+    tr = ctx.tracker(752, 480, 1200, seq["K"], n_cells=49, max_pairs=max_pairs)
+    pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
+    pose = torch.zeros((T - 1, 7), dtype=torch.float32).pin_memory()
+    ng = torch.zeros((T - 1,), dtype=torch.int32).pin_memory()
+    nf = torch.zeros((T,), dtype=torch.int32).pin_memory()
+    for _ in range(2):                                           # the second call reuses the slots' buffers
+        tr.track_sequence_orb_host(pin(seq["frames"]), pin(prior), pose, nfeatures=1000, n_good=ng, n_feat=nf)
+        np.testing.assert_array_equal(pose.numpy(), pose_d.cpu().numpy())
+        np.testing.assert_array_equal(ng.numpy(), ng_d.cpu().numpy())
+        np.testing.assert_array_equal(nf.numpy(), nf_d.cpu().numpy())
+    ht = tr.host_traffic()
+    assert ht["chunks"] == {2: 4, 3: 3, 8: 1}[max_pairs]
+    assert ht["h2d"] == (T - 1 + ht["chunks"]) * 752 * 480 + (T - 1) * 28
+    tr.close()
+
+
 @pytest.mark.parametrize("n_cells,threads,stage", [(49, 0, 8192), (49, 128, 0), (49, 256, 32768), (49, 512, 8192),
                                                    (225, 1024, 0), (225, 128, 32768), (225, 0, 8192)])
 def test_tracker_solver_per_iteration(ctx, oracle, n_cells, threads, stage):

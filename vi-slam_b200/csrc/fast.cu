@@ -436,13 +436,20 @@ fast_write16_kernel(const uint8_t* __restrict__ score1, int sw, int h, int nonma
 
 }  // namespace
 
-// FAST-9/16 corners of `count` frames (cv::FAST, TYPE_9_16).  img: frames of h rows x pitch bytes, img_stride bytes apart.
-// kp_xy [count][cap][2] int32 (x, y) and kp_score [count][cap] int32 in row-major order; n_kp [count] = corners FOUND
-// (may exceed cap; only the first cap are stored).  Scratch comes from the context.
-extern "C" int vsb_fast_detect(vsb_ctx_t* ctx, const uint8_t* img, int64_t img_stride, int pitch, int w, int h, int count,
-                               int threshold, int nonmax, int cap, int32_t* kp_xy, int32_t* kp_score, int32_t* n_kp,
-                               void* stream) {
-    if (!ctx || !img || !kp_xy || !kp_score || !n_kp) return VSB_ERR_INVALID;
+// Scratch of one vsb_fast_detect_ws call: the score image (rows padded to 16 bytes), two int32 per image row, one bit per pixel.
+size_t vsb_fast_scratch_bytes(int w, int h, int count) {
+    const int sw = (w + 15) & ~15;
+    const size_t img_bytes = ((size_t)count * sw * h + 255) & ~(size_t)255;
+    const size_t rows_bytes = ((size_t)count * h * sizeof(int32_t) + 255) & ~(size_t)255;
+    const size_t bits_bytes = ((size_t)count * h * (sw >> 4) * sizeof(uint16_t) + 255) & ~(size_t)255;
+    return img_bytes + 2 * rows_bytes + bits_bytes + 256;
+}
+
+// The detector on a caller-provided scratch block (at least vsb_fast_scratch_bytes, 256-byte aligned): what the tracker's
+// per-slot workspaces use, so that two chunks of a sequence can be in flight on two streams.
+int vsb_fast_detect_ws(vsb_ctx_t* ctx, const uint8_t* img, int64_t img_stride, int pitch, int w, int h, int count, int threshold,
+                       int nonmax, int cap, int32_t* kp_xy, int32_t* kp_score, int32_t* n_kp, void* scratch, void* stream) {
+    if (!ctx || !img || !kp_xy || !kp_score || !n_kp || !scratch) return VSB_ERR_INVALID;
     if (w <= 0 || h <= 0 || pitch < w || count < 0 || cap < 0 || threshold < 0 || threshold > 255) return VSB_ERR_INVALID;
     if (count == 0) return VSB_OK;
     cudaStream_t st = (cudaStream_t)stream;
@@ -451,10 +458,6 @@ extern "C" int vsb_fast_detect(vsb_ctx_t* ctx, const uint8_t* img, int64_t img_s
     const int sw = (w + 15) & ~15;
     const size_t img_bytes = ((size_t)count * sw * h + 255) & ~(size_t)255;
     const size_t rows_bytes = ((size_t)count * h * sizeof(int32_t) + 255) & ~(size_t)255;
-    const size_t bits_bytes = ((size_t)count * h * (sw >> 4) * sizeof(uint16_t) + 255) & ~(size_t)255;
-    void* scratch = nullptr;
-    int rc = vsb_scratch_reserve(ctx, img_bytes + 2 * rows_bytes + bits_bytes + 256, &scratch);
-    if (rc) return rc;
     uint8_t* score1 = static_cast<uint8_t*>(scratch);
     int32_t* row_count = reinterpret_cast<int32_t*>(score1 + img_bytes);
     int32_t* row_offset = reinterpret_cast<int32_t*>(score1 + img_bytes + rows_bytes);
@@ -492,4 +495,19 @@ extern "C" int vsb_fast_detect(vsb_ctx_t* ctx, const uint8_t* img, int64_t img_s
         }
     }
     return VSB_OK;
+}
+
+// FAST-9/16 corners of `count` frames (cv::FAST, TYPE_9_16).  img: frames of h rows x pitch bytes, img_stride bytes apart.
+// kp_xy [count][cap][2] int32 (x, y) and kp_score [count][cap] int32 in row-major order; n_kp [count] = corners FOUND
+// (may exceed cap; only the first cap are stored).  Scratch comes from the context.
+extern "C" int vsb_fast_detect(vsb_ctx_t* ctx, const uint8_t* img, int64_t img_stride, int pitch, int w, int h, int count,
+                               int threshold, int nonmax, int cap, int32_t* kp_xy, int32_t* kp_score, int32_t* n_kp,
+                               void* stream) {
+    if (!ctx || !img || !kp_xy || !kp_score || !n_kp) return VSB_ERR_INVALID;
+    if (w <= 0 || h <= 0 || pitch < w || count < 0 || cap < 0 || threshold < 0 || threshold > 255) return VSB_ERR_INVALID;
+    if (count == 0) return VSB_OK;
+    void* scratch = nullptr;
+    int rc = vsb_scratch_reserve(ctx, vsb_fast_scratch_bytes(w, h, count), &scratch);
+    if (rc) return rc;
+    return vsb_fast_detect_ws(ctx, img, img_stride, pitch, w, h, count, threshold, nonmax, cap, kp_xy, kp_score, n_kp, scratch, stream);
 }

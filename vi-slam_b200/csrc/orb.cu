@@ -11,6 +11,10 @@
 // float separable filter with the fused steps the oracle documents.
 #include "common.cuh"
 
+size_t vsb_fast_scratch_bytes(int w, int h, int count);
+int vsb_fast_detect_ws(vsb_ctx_t* ctx, const uint8_t* img, int64_t img_stride, int pitch, int w, int h, int count, int threshold,
+                       int nonmax, int cap, int32_t* kp_xy, int32_t* kp_score, int32_t* n_kp, void* scratch, void* stream);
+
 namespace {
 
 constexpr int ORB_EDGE = 31;
@@ -619,12 +623,12 @@ inline OrbScratch orb_scratch_carve(uint8_t*& p, int chunk, int w, int h, bool d
 }
 
 // the one-level pipeline on zc frames of w x h (fcap is taken from the scratch, sized for the largest level)
-int orb_one_level(vsb_ctx_t* ctx, const OrbScratch& S, const uint8_t* in, int64_t img_stride, int pitch, int w, int h, int zc,
+int orb_one_level(vsb_ctx_t* ctx, const OrbScratch& S, void* fast_scratch, const uint8_t* in, int64_t img_stride, int pitch, int w, int h, int zc,
                   int nfeatures, int fast_threshold, int cap, int32_t* kp_xy, float* kp_resp, float* kp_angle, uint8_t* desc,
                   int32_t* n_kp, cudaStream_t st, int bpitch = 0) {
     if (bpitch <= 0) bpitch = w;                 // row pitch of the blurred copy (the scratch holds w0 x h0 bytes per frame)
     const int fcap = S.fcap;
-    int rc = vsb_fast_detect(ctx, in, img_stride, pitch, w, h, zc, fast_threshold, 1, fcap, S.fxy, S.fsc, S.nfast, (void*)st);
+    int rc = vsb_fast_detect_ws(ctx, in, img_stride, pitch, w, h, zc, fast_threshold, 1, fcap, S.fxy, S.fsc, S.nfast, fast_scratch, (void*)st);
     if (rc) return rc;
     ProfScope ps(ctx, VSB_K_ORB, st);
     orb_select_fast_kernel<<<zc, 256, 0, st>>>(S.fxy, S.fsc, S.nfast, fcap, w, h, 2 * nfeatures, S.sel, S.nsel);
@@ -681,9 +685,11 @@ extern "C" int vsb_orb_detect_compute(vsb_ctx_t* ctx, const uint8_t* img, int64_
     if (rc) return rc;
     uint8_t* p = static_cast<uint8_t*>(scratch);
     const OrbScratch S = orb_scratch_carve(p, chunk, w, h, desc != nullptr);
+    void* fast_scratch = nullptr;
+    if ((rc = vsb_scratch_reserve(ctx, vsb_fast_scratch_bytes(w, h, chunk), &fast_scratch))) return rc;
     for (int z0 = 0; z0 < count; z0 += chunk) {
         const int zc = min(chunk, count - z0);
-        rc = orb_one_level(ctx, S, img + (size_t)z0 * img_stride, img_stride, pitch, w, h, zc, nfeatures, fast_threshold, cap,
+        rc = orb_one_level(ctx, S, fast_scratch, img + (size_t)z0 * img_stride, img_stride, pitch, w, h, zc, nfeatures, fast_threshold, cap,
                            kp_xy + (size_t)z0 * cap * 2, kp_resp + (size_t)z0 * cap, kp_angle + (size_t)z0 * cap,
                            desc ? desc + (size_t)z0 * cap * 32 : nullptr, n_kp + z0, st);
         if (rc) return rc;
@@ -692,10 +698,24 @@ extern "C" int vsb_orb_detect_compute(vsb_ctx_t* ctx, const uint8_t* img, int64_
 }
 
 // cv::ORB with its scale pyramid (the reference's ORB::create(n): nlevels 8, scale factor 1.2).  See include/vislam_b200.h.
-extern "C" int vsb_orb_detect_compute_pyr(vsb_ctx_t* ctx, const uint8_t* img, int64_t img_stride, int pitch, int w, int h,
-                                          int count, int nfeatures, float scale_factor, int nlevels, int fast_threshold, int cap,
-                                          float* kp_xy, int32_t* kp_octave, float* kp_resp, float* kp_angle, uint8_t* desc,
-                                          int32_t* n_kp, void* stream) {
+// Workspace bytes per frame of vsb_orb_detect_compute_pyr_ws (its own scratch, two level images, per-level key-point lists, the
+// FAST detector's scratch).
+static size_t orb_pyr_frame_bytes(int w, int h, int cap, bool describe) {
+    const size_t tmp_frame = orb_al((size_t)cap * 8) + 2 * orb_al((size_t)cap * 4) + (describe ? orb_al((size_t)cap * 32) : 0);
+    const size_t wpad = (size_t)((w + 15) & ~15);            // level rows are padded to 16 bytes: a level can be up to wpad x h bytes (scale factors close to 1)
+    return orb_scratch_bytes(1, w, h, describe) + 2 * orb_al(wpad * h) + tmp_frame + 256 + vsb_fast_scratch_bytes(w, h, 1);
+}
+size_t vsb_orb_pyr_ws_bytes(int w, int h, int frames, int cap, int describe) {
+    return (size_t)frames * orb_pyr_frame_bytes(w, h, cap, describe != 0) + orb_al((size_t)(w + h) * sizeof(int4)) + 4096;
+}
+
+// The detector on a caller-provided workspace `ws` of `ws_bytes` (256-byte aligned): the batch is processed in chunks of as
+// many frames as the workspace holds.  The tracker gives each of its two slots its own workspace, so that the chunks of a
+// sequence can run on two streams at once; the public entry below takes the workspace from the context.
+int vsb_orb_detect_compute_pyr_ws(vsb_ctx_t* ctx, const uint8_t* img, int64_t img_stride, int pitch, int w, int h,
+                                  int count, int nfeatures, float scale_factor, int nlevels, int fast_threshold, int cap,
+                                  float* kp_xy, int32_t* kp_octave, float* kp_resp, float* kp_angle, uint8_t* desc,
+                                  int32_t* n_kp, void* ws, size_t ws_bytes, void* stream) {
     if (!ctx || !img || !kp_xy || !kp_resp || !kp_angle || !n_kp) return VSB_ERR_INVALID;
     if (w <= 2 * ORB_EDGE || h <= 2 * ORB_EDGE || pitch < w || count < 0 || cap <= 0 || nfeatures < 0) return VSB_ERR_INVALID;
     if (fast_threshold < 0 || fast_threshold > 255 || nlevels < 1 || nlevels > 32 || !(scale_factor > 1.f)) return VSB_ERR_INVALID;
@@ -711,17 +731,14 @@ extern "C" int vsb_orb_detect_compute_pyr(vsb_ctx_t* ctx, const uint8_t* img, in
         budget[nlevels - 1] = nfeatures - sum > 0 ? nfeatures - sum : 0;
     }
     const bool describe = desc != nullptr;
-    const size_t tmp_frame = orb_al((size_t)cap * 8) + 2 * orb_al((size_t)cap * 4) + (describe ? orb_al((size_t)cap * 32) : 0);
-    const size_t wpad = (size_t)((w + 15) & ~15);            // level rows are padded to 16 bytes: a level can be up to wpad x h bytes (scale factors close to 1)
-    const size_t per_frame = orb_scratch_bytes(1, w, h, describe) + 2 * orb_al(wpad * h) + tmp_frame + 256;
-    const int chunk = (int)max((size_t)1, min((size_t)count, orb_scratch_budget(ctx) / per_frame));
+    if (!ws) return VSB_ERR_INVALID;
+    const size_t wpad = (size_t)((w + 15) & ~15);
+    const size_t fixed = orb_al((size_t)(w + h) * sizeof(int4)) + 4096;
+    if (ws_bytes < fixed + orb_pyr_frame_bytes(w, h, cap, describe)) return VSB_ERR_CAPACITY;
+    const int chunk = (int)min((size_t)count, (ws_bytes - fixed) / orb_pyr_frame_bytes(w, h, cap, describe));
     const size_t b_img = orb_al((size_t)chunk * wpad * h);
-    void* scratch = nullptr;
-    int rc = vsb_scratch2_reserve(ctx, orb_scratch_bytes(chunk, w, h, describe) + 2 * b_img + chunk * tmp_frame + orb_al((size_t)chunk * 4) +
-                                       orb_al((size_t)(w + h) * sizeof(int4)) + 1024,
-                                  &scratch);
-    if (rc) return rc;
-    uint8_t* p = static_cast<uint8_t*>(scratch);
+    int rc;
+    uint8_t* p = static_cast<uint8_t*>(ws);
     const OrbScratch S = orb_scratch_carve(p, chunk, w, h, describe);
     uint8_t* lvl_img[2];
     lvl_img[0] = p; p += b_img;
@@ -732,7 +749,8 @@ extern "C" int vsb_orb_detect_compute_pyr(vsb_ctx_t* ctx, const uint8_t* img, in
     uint8_t* ldesc = nullptr;
     if (describe) { ldesc = p; p += orb_al((size_t)chunk * cap * 32); }
     int32_t* ln = reinterpret_cast<int32_t*>(p); p += orb_al((size_t)chunk * 4);
-    int4* rz_tab = reinterpret_cast<int4*>(p);
+    int4* rz_tab = reinterpret_cast<int4*>(p); p += orb_al((size_t)(w + h) * sizeof(int4));
+    void* fast_scratch = p;                                  // vsb_fast_scratch_bytes(w, h, chunk) <= chunk x the per-frame figure
     for (int z0 = 0; z0 < count; z0 += chunk) {
         const int zc = min(chunk, count - z0);
         VSB_CUDA(ctx, cudaMemsetAsync(n_kp + z0, 0, (size_t)zc * sizeof(int32_t), st));
@@ -746,7 +764,7 @@ extern "C" int vsb_orb_detect_compute_pyr(vsb_ctx_t* ctx, const uint8_t* img, in
                 if (nw <= 2 * ORB_EDGE || nh <= 2 * ORB_EDGE) break;       // the border filter leaves nothing from here on
                 uint8_t* dst = lvl_img[l & 1];
                 ProfScope ps(ctx, VSB_K_ORB, st);
-                // level images get rows padded to 16 bytes (they fit: nw <= w / 1.2), so that every reader takes its aligned
+                // level images get rows padded to 16 bytes (the workspace is sized for padded rows), so that every reader takes its aligned
                 // word path (FAST's loader, the blur, this kernel's packed stores) whatever nw is
                 const int np = (nw + 15) & ~15;
                 const bool words = ((reinterpret_cast<uintptr_t>(cur) | (uintptr_t)cur_stride | (uintptr_t)cp) & 3u) == 0 &&
@@ -764,7 +782,7 @@ extern "C" int vsb_orb_detect_compute_pyr(vsb_ctx_t* ctx, const uint8_t* img, in
                 VSB_LAUNCHED(ctx);
                 cur = dst; cur_stride = (int64_t)np * nh; cw = nw; ch = nh; cp = np;
             }
-            rc = orb_one_level(ctx, S, cur, cur_stride, cp, cw, ch, zc, budget[l], fast_threshold, cap, lxy, lresp, langle, ldesc, ln, st,
+            rc = orb_one_level(ctx, S, fast_scratch, cur, cur_stride, cp, cw, ch, zc, budget[l], fast_threshold, cap, lxy, lresp, langle, ldesc, ln, st,
                                l > 0 ? cp : 0);
             if (rc) return rc;
             ProfScope ps(ctx, VSB_K_ORB, st);
@@ -777,4 +795,25 @@ extern "C" int vsb_orb_detect_compute_pyr(vsb_ctx_t* ctx, const uint8_t* img, in
         }
     }
     return VSB_OK;
+}
+
+extern "C" int vsb_orb_detect_compute_pyr(vsb_ctx_t* ctx, const uint8_t* img, int64_t img_stride, int pitch, int w, int h,
+                                          int count, int nfeatures, float scale_factor, int nlevels, int fast_threshold, int cap,
+                                          float* kp_xy, int32_t* kp_octave, float* kp_resp, float* kp_angle, uint8_t* desc,
+                                          int32_t* n_kp, void* stream) {
+    if (!ctx || !img || !kp_xy || !kp_resp || !kp_angle || !n_kp) return VSB_ERR_INVALID;
+    if (w <= 2 * ORB_EDGE || h <= 2 * ORB_EDGE || pitch < w || count < 0 || cap <= 0 || nfeatures < 0) return VSB_ERR_INVALID;
+    if (count == 0) return VSB_OK;
+    // Every stage is one launch per chunk of frames and pyramid level, and the upper levels are small, so few large chunks keep
+    // the machine filled where many small ones are launch-bound: the budget (orb_scratch_mb) allows 2000 752x480 frames at once.
+    const size_t one = vsb_orb_pyr_ws_bytes(w, h, 1, cap, desc != nullptr);
+    const size_t per_frame = orb_pyr_frame_bytes(w, h, cap, desc != nullptr);
+    size_t frames = (orb_scratch_budget(ctx) > one ? (orb_scratch_budget(ctx) - one) / per_frame : 0) + 1;
+    if (frames > (size_t)count) frames = (size_t)count;
+    const size_t bytes = vsb_orb_pyr_ws_bytes(w, h, (int)frames, cap, desc != nullptr);
+    void* ws = nullptr;
+    int rc = vsb_scratch2_reserve(ctx, bytes, &ws);
+    if (rc) return rc;
+    return vsb_orb_detect_compute_pyr_ws(ctx, img, img_stride, pitch, w, h, count, nfeatures, scale_factor, nlevels, fast_threshold,
+                                         cap, kp_xy, kp_octave, kp_resp, kp_angle, desc, n_kp, ws, bytes, stream);
 }

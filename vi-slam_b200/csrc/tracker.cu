@@ -32,6 +32,11 @@ int vsb_gn_track(vsb_ctx_t* ctx, const uint8_t* cur_pyr, int64_t pair_stride_pix
                  const vsb_intr_t K[VSB_MAX_LEVELS], const float* pose_in, const vsb_gn_opts_t* opts, int pair0, int count,
                  int threads, float* pose_out, vsb_gn_trace_t* trace, int32_t* n_trace, unsigned long long* stats,
                  const uint8_t* cur_l0, int64_t l0_stride, void* stream);
+size_t vsb_orb_pyr_ws_bytes(int w, int h, int frames, int cap, int describe);
+int vsb_orb_detect_compute_pyr_ws(vsb_ctx_t* ctx, const uint8_t* img, int64_t img_stride, int pitch, int w, int h,
+                                  int count, int nfeatures, float scale_factor, int nlevels, int fast_threshold, int cap,
+                                  float* kp_xy, int32_t* kp_octave, float* kp_resp, float* kp_angle, uint8_t* desc,
+                                  int32_t* n_kp, void* ws, size_t ws_bytes, void* stream);
 int vsb_knn_unpack(vsb_ctx* ctx, const uint32_t* keys, int n_max, const int32_t* n, int count, int32_t* idx,
                    float* dist, cudaStream_t st);
 int vsb_knn2_l2_keys(vsb_ctx* ctx, const float* d1, int n1_max, const int32_t* n1, const float* d2, int n2_max,
@@ -64,6 +69,8 @@ struct Slot {
     int32_t* n_cand = nullptr;
     int32_t* n_pts = nullptr;     // candidate points per level before merging, [max_pairs][levels] (gn_track.cu)
     float* pose = nullptr;
+    void* orb_ws = nullptr;       // the detector's workspace of this slot (vsb_orb_detect_compute_pyr_ws), allocated on first use
+    size_t orb_ws_bytes = 0;
     float* orb_resp = nullptr;    // [max_pairs + 1][n_feat] each, allocated on the first vsb_track_sequence_orb call
     float* orb_angle = nullptr;
     uint8_t* desc2 = nullptr;     // second descriptor set of the pairs host entry, [max_pairs][n_feat][desc_bytes], allocated on first use
@@ -74,6 +81,7 @@ struct Slot {
     // the solver's tail launch (pairs of the last partial wave, more threads each) runs beside the main one
     cudaStream_t aux = nullptr;
     cudaEvent_t fork = nullptr, join = nullptr;
+    cudaEvent_t ready = nullptr;  // vsb_track_sequence_orb_host: the slot's frames have arrived (recorded on the copy stream)
 };
 
 }  // namespace
@@ -138,6 +146,7 @@ int slot_alloc(vsb_tracker* t, Slot& s) {
     VSB_CUDA(ctx, cudaStreamCreateWithFlags(&s.aux, cudaStreamNonBlocking));
     VSB_CUDA(ctx, cudaEventCreateWithFlags(&s.fork, cudaEventDisableTiming));
     VSB_CUDA(ctx, cudaEventCreateWithFlags(&s.join, cudaEventDisableTiming));
+    VSB_CUDA(ctx, cudaEventCreateWithFlags(&s.ready, cudaEventDisableTiming));
     return VSB_OK;
 }
 
@@ -149,6 +158,8 @@ void slot_free(Slot& s) {
     if (s.aux) cudaStreamDestroy(s.aux);
     if (s.fork) cudaEventDestroy(s.fork);
     if (s.join) cudaEventDestroy(s.join);
+    if (s.ready) cudaEventDestroy(s.ready);
+    if (s.orb_ws) cudaFree(s.orb_ws);
     s = Slot();
 }
 
@@ -367,27 +378,84 @@ __global__ void clamp_counts_kernel(int32_t* n, int count, int cap) {
 // The loop from images alone: every frame goes through cv::ORB::create(nfeatures) on the device (orb.cu), the key points and
 // descriptors stay on the device and feed the matcher (Camera::detectAndComputeFeatures -> computeGoodMatches ->
 // EstimatePoseFeatures, VISystemGPU.cpp:144-169).  Frames with more key points than cfg.n_feat_max keep the first n_feat_max.
+static int track_sequence_orb_slot(vsb_tracker* t, Slot& s, const uint8_t* frames, const float* prior, int n_frames, int nfeatures,
+                                   float* pose, int32_t* n_good, int32_t* n_feat_out, cudaStream_t st) {
+    vsb_ctx* ctx = t->ctx;
+    const vsb_tracker_cfg_t& c = t->cfg;
+    int rc;
+    const size_t per = (size_t)(c.max_pairs + 1) * c.n_feat_max;
+    if (!s.orb_resp && (rc = dev_alloc(ctx, &s.orb_resp, per))) return rc;
+    if (!s.orb_angle && (rc = dev_alloc(ctx, &s.orb_angle, per))) return rc;
+    if (!s.orb_ws) {
+        // as many frames as the slot holds, inside the context's budget for the detector ("orb_scratch_mb")
+        const size_t budget = (size_t)(ctx->orb_scratch_mb > 0 ? ctx->orb_scratch_mb : 8192) << 20;
+        size_t bytes = vsb_orb_pyr_ws_bytes(c.w, c.h, c.max_pairs + 1, c.n_feat_max, 1);
+        const size_t floor_bytes = vsb_orb_pyr_ws_bytes(c.w, c.h, 1, c.n_feat_max, 1);
+        if (bytes > budget) bytes = budget > floor_bytes ? budget : floor_bytes;
+        VSB_CUDA(ctx, cudaMalloc(&s.orb_ws, bytes));
+        s.orb_ws_bytes = bytes;
+    }
+    if ((rc = vsb_orb_detect_compute_pyr_ws(ctx, frames, (int64_t)c.w * c.h, c.w, c.w, c.h, n_frames, nfeatures, 1.2f, 8, 20,
+                                            c.n_feat_max, s.kp, nullptr, s.orb_resp, s.orb_angle, s.desc, s.n_feat, s.orb_ws,
+                                            s.orb_ws_bytes, (void*)st)))
+        return rc;
+    clamp_counts_kernel<<<vsb_div_up(n_frames, 256), 256, 0, st>>>(s.n_feat, n_frames, c.n_feat_max);
+    VSB_LAUNCHED(ctx);
+    if (n_feat_out) VSB_CUDA(ctx, cudaMemcpyAsync(n_feat_out, s.n_feat, (size_t)n_frames * sizeof(int32_t), cudaMemcpyDefault, st));
+    return track_sequence_slot(t, s, frames, false, s.desc, s.kp, s.n_feat, prior, n_frames, pose, n_good, st);
+}
+
 extern "C" int vsb_track_sequence_orb(vsb_tracker_t* t, const uint8_t* frames, const float* pose_prior, int n_frames,
                                       int nfeatures, float* pose, int32_t* n_good, int32_t* n_feat_out, void* stream) {
     if (!t || !frames || !pose_prior || !pose || nfeatures < 0) return VSB_ERR_INVALID;
     if (t->cfg.norm != 1 || t->cfg.desc_bytes != 32) return VSB_ERR_INVALID;        // ORB descriptors: 32 bytes, Hamming
     if (n_frames < 2) return n_frames < 0 ? VSB_ERR_INVALID : VSB_OK;
     if (n_frames - 1 > t->cfg.max_pairs) return VSB_ERR_CAPACITY;
+    return track_sequence_orb_slot(t, t->slot[0], frames, pose_prior, n_frames, nfeatures, pose, n_good, n_feat_out,
+                                   (cudaStream_t)stream);
+}
+
+// The loop from images alone, from HOST buffers: what a caller of the reference's CameraGPU path has — frames in host memory,
+// key points and descriptors made on the device (VISystemGPU.cpp:144-169).  Chunks of cfg.max_pairs pairs alternate between the
+// two slots, each with its own stream, frame buffer and detector workspace: the frames of chunk i + 1 travel while chunk i is
+// tracked, and the launch-latency-bound parts of a chunk (a dozen launches per pyramid level, the solver's tail: ~1.3 ms per chunk
+// whatever its size) overlap the other chunk's kernels.  A chunk's last frame is the next chunk's first: it travels and is
+// described twice (1 / max_pairs of the work), which keeps the chunks independent.
+extern "C" int vsb_track_sequence_orb_host(vsb_tracker_t* t, const uint8_t* h_frames, const float* h_pose_prior, int n_frames,
+                                           int nfeatures, float* h_pose, int32_t* h_n_good, int32_t* h_n_feat) {
+    if (!t || !h_frames || !h_pose_prior || !h_pose || nfeatures < 0) return VSB_ERR_INVALID;
+    if (t->cfg.norm != 1 || t->cfg.desc_bytes != 32) return VSB_ERR_INVALID;
+    if (n_frames < 2) return n_frames < 0 ? VSB_ERR_INVALID : VSB_OK;
     vsb_ctx* ctx = t->ctx;
     const vsb_tracker_cfg_t& c = t->cfg;
-    Slot& s = t->slot[0];
-    cudaStream_t st = (cudaStream_t)stream;
-    int rc;
-    const size_t per = (size_t)(c.max_pairs + 1) * c.n_feat_max;
-    if (!s.orb_resp && (rc = dev_alloc(ctx, &s.orb_resp, per))) return rc;
-    if (!s.orb_angle && (rc = dev_alloc(ctx, &s.orb_angle, per))) return rc;
-    if ((rc = vsb_orb_detect_compute_pyr(ctx, frames, (int64_t)c.w * c.h, c.w, c.w, c.h, n_frames, nfeatures, 1.2f, 8, 20,
-                                         c.n_feat_max, s.kp, nullptr, s.orb_resp, s.orb_angle, s.desc, s.n_feat, stream)))
-        return rc;
-    clamp_counts_kernel<<<vsb_div_up(n_frames, 256), 256, 0, st>>>(s.n_feat, n_frames, c.n_feat_max);
-    VSB_LAUNCHED(ctx);
-    if (n_feat_out) VSB_CUDA(ctx, cudaMemcpyAsync(n_feat_out, s.n_feat, (size_t)n_frames * sizeof(int32_t), cudaMemcpyDeviceToDevice, st));
-    return track_sequence_slot(t, s, frames, false, s.desc, s.kp, s.n_feat, pose_prior, n_frames, pose, n_good, st);
+    const size_t fbytes = (size_t)c.w * c.h;
+    const int total_pairs = n_frames - 1;
+    long long h2d = 0, d2h = 0;
+    int chunk_idx = 0, rc = VSB_OK;
+    for (int p0 = 0; p0 < total_pairs && rc == VSB_OK; chunk_idx++) {
+        const int remaining = total_pairs - p0;
+        int pairs = remaining < c.max_pairs ? remaining : c.max_pairs;
+        // the first chunk is half a chunk when there is more than one: the kernels start after half the copy time
+        if (chunk_idx == 0 && remaining > c.max_pairs && c.max_pairs >= 64) pairs = c.max_pairs / 2;
+        const int nf = pairs + 1;
+        Slot& s = t->slot[chunk_idx & 1];
+        cudaStream_t st = s.stream;
+        if (!s.stage) { if (cudaMalloc((void**)&s.stage, (size_t)(c.max_pairs + 1) * fbytes) != cudaSuccess) { rc = VSB_ERR_CUDA; break; } }
+        // (stream order: the slot's previous chunk has been tracked before this copy overwrites its frames)
+        VSB_CUDA(ctx, cudaMemcpyAsync(s.stage, h_frames + (size_t)p0 * fbytes, (size_t)nf * fbytes, cudaMemcpyHostToDevice, st));
+        VSB_CUDA(ctx, cudaMemcpyAsync(s.prior, h_pose_prior + (size_t)p0 * 7, (size_t)pairs * 28, cudaMemcpyHostToDevice, st));
+        h2d += (long long)nf * fbytes + pairs * 28LL;
+        d2h += pairs * 28LL + (h_n_good ? pairs * 4LL : 0) + (h_n_feat ? nf * 4LL : 0);
+        if ((rc = track_sequence_orb_slot(t, s, s.stage, s.prior, nf, nfeatures, s.pose, nullptr, h_n_feat ? h_n_feat + p0 : nullptr, st)))
+            break;
+        VSB_CUDA(ctx, cudaMemcpyAsync(h_pose + (size_t)p0 * 7, s.pose, (size_t)pairs * 28, cudaMemcpyDeviceToHost, st));
+        if (h_n_good) VSB_CUDA(ctx, cudaMemcpyAsync(h_n_good + p0, s.n_good, pairs * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+        p0 += pairs;
+    }
+    for (int i = 0; i < 2; i++) cudaStreamSynchronize(t->slot[i].stream);      // also on the error path: copies may be in flight
+    if (rc) return rc;
+    t->host_h2d_bytes = h2d; t->host_d2h_bytes = d2h; t->host_chunks = chunk_idx;
+    return VSB_OK;
 }
 
 extern "C" int vsb_track_pairs(vsb_tracker_t* t, const uint8_t* prev, const uint8_t* cur, const uint8_t* d1,

@@ -55,7 +55,7 @@ EXPORTS = [
     "vsb_pyr_layout", "vsb_pyramid_build", "vsb_gradient_build", "vsb_candidates_build",
     "vsb_gather_keypoints", "vsb_init_pyramid", "vsb_gn_default_opts", "vsb_gn_solve", "vsb_initial_pose",
     "vsb_se3_mul", "vsb_tracker_create", "vsb_tracker_destroy", "vsb_track_sequence",
-    "vsb_track_sequence_host", "vsb_track_sequence_orb", "vsb_track_pairs", "vsb_track_pairs_host", "vsb_kernel_count", "vsb_kernel_name", "vsb_profile_enable",
+    "vsb_track_sequence_host", "vsb_track_sequence_orb", "vsb_track_sequence_orb_host", "vsb_track_pairs", "vsb_track_pairs_host", "vsb_kernel_count", "vsb_kernel_name", "vsb_profile_enable",
     "vsb_profile_reset", "vsb_profile_read", "vsb_popc_peak", "vsb_tracker_stats", "vsb_tracker_set_trace", "vsb_tracker_host_traffic", "vsb_fast_detect", "vsb_orb_detect_compute", "vsb_orb_detect_compute_pyr",
     "vsb_malloc", "vsb_free", "vsb_host_alloc", "vsb_host_free", "vsb_upload", "vsb_upload_2d", "vsb_download",
     "vsb_copy", "vsb_memset", "vsb_stream_create", "vsb_stream_destroy", "vsb_stream_sync",
@@ -113,6 +113,7 @@ def lib():
     L.vsb_track_sequence.argtypes = [vp, vp, vp, vp, vp, vp, i32, vp, vp, vp]
     L.vsb_track_sequence_orb.argtypes = [vp, vp, vp, i32, i32, vp, vp, vp, vp]
     L.vsb_track_sequence_host.argtypes = [vp, vp, vp, vp, vp, vp, i32, vp, vp]
+    L.vsb_track_sequence_orb_host.argtypes = [vp, vp, vp, i32, i32, vp, vp, vp]
     L.vsb_track_pairs.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, vp, vp, vp]
     L.vsb_track_pairs_host.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, vp, vp]
     L.vsb_kernel_count.restype = i32
@@ -494,6 +495,13 @@ class Tracker:
         check(lib().vsb_track_sequence_host(self.handle, _ptr(frames), _ptr(desc), _ptr(kp_xy), _ptr(n_feat),
                                             _ptr(prior), T, _ptr(pose), _ptr(n_good)), self.ctx.handle)
         return pose, n_good
+
+    def track_sequence_orb_host(self, frames, prior, pose, nfeatures=1000, n_good=None, n_feat=None):
+        """From images alone with HOST (pinned) tensors: frames [T,h,w] u8, prior [T-1,7] -> pose [T-1,7] (host); synchronous."""
+        T = frames.shape[0]
+        check(lib().vsb_track_sequence_orb_host(self.handle, _ptr(frames), _ptr(prior), T, int(nfeatures), _ptr(pose),
+                                                _ptr(n_good), _ptr(n_feat)), self.ctx.handle)
+        return pose, n_good, n_feat
 
     def track_pairs_host(self, prev, cur, d1, d2, kp1_xy, prior, pose, n_good=None, n1=None, n2=None):
         """HOST (pinned) tensors in, host tensors out; synchronous.  Independent pairs, chunked over two streams."""
