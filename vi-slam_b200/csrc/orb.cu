@@ -50,6 +50,19 @@ __device__ __forceinline__ int block_exclusive_scan(int v, int* s_warp, int& tot
     return base + inc - v;
 }
 
+// The bin a descending walk over a 256-bin histogram stops in: the largest b >= floor_bin with sum(hist[b..255]) >= want, and
+// the sum over the bins above it; floor_bin (with the sum over the bins above IT) when no bin reaches `want`.  All 256 threads
+// call it; the result lands in s_out[0..1].  (The walk itself, on one thread, was 256 dependent shared-memory loads per radix
+// pass: ~10 k cycles, most of these kernels' time and of the detector's fixed cost per call.)
+__device__ __forceinline__ void hist_select_desc(const int* s_hist, int want, int floor_bin, int* s_warp, int* s_out) {
+    const int b = 255 - (int)threadIdx.x;
+    const int v = b >= floor_bin ? s_hist[b] : 0;
+    int total;
+    const int excl = block_exclusive_scan(v, s_warp, total);       // over the bins above b
+    if (b > floor_bin ? (excl + v >= want && excl < want) : (b == floor_bin && excl < want)) { s_out[0] = b; s_out[1] = excl; }
+    __syncthreads();
+}
+
 // ---- stage 1: border filter + retainBest(2n) on the integer FAST score, order preserved --------------------------------
 // One block per frame.  Scores are integers 1..255, so the n-th best is found on a 256-bin histogram.
 __global__ void __launch_bounds__(256)
@@ -57,7 +70,7 @@ orb_select_fast_kernel(const int32_t* __restrict__ fxy, const int32_t* __restric
                        int fcap, int w, int h, int keep_n, int32_t* __restrict__ sel_xy, int32_t* __restrict__ n_sel) {
     __shared__ int s_hist[256];
     __shared__ int s_warp[8];
-    __shared__ int s_thr;
+    __shared__ int s_sel[2];
     const int f = blockIdx.x, tid = threadIdx.x;
     const int n = min(nfast[f], fcap);
     const int32_t* xy = fxy + (size_t)f * fcap * 2;
@@ -70,19 +83,11 @@ orb_select_fast_kernel(const int32_t* __restrict__ fxy, const int32_t* __restric
         if (x >= ORB_EDGE && x < w - ORB_EDGE && y >= ORB_EDGE && y < h - ORB_EDGE) atomicAdd(&s_hist[min(max(sc[i], 0), 255)], 1);
     }
     __syncthreads();
-    if (tid == 0) {
-        int total = 0;
-        for (int b = 0; b < 256; b++) total += s_hist[b];
-        int thr = 0;                                      // keep everything
-        if (keep_n >= 0 && total > keep_n) {
-            int acc = 0;
-            thr = 256;                                    // keep_n == 0: nothing
-            for (int b = 255; b >= 0 && keep_n > 0; b--) { acc += s_hist[b]; if (acc >= keep_n) { thr = b; break; } }
-        }
-        s_thr = thr;
-    }
-    __syncthreads();
-    const int thr = s_thr;
+    // threshold = the largest score s with at least keep_n corners of score >= s (everything when there are no more than keep_n)
+    hist_select_desc(s_hist, keep_n > 0 ? keep_n : 1, 0, s_warp, s_sel);
+    // (a bin >= 1 that reaches keep_n is the threshold whether or not there are more than keep_n corners in all — when there are
+    // not, nothing lies below it; bin 0 keeps everything)
+    const int thr = keep_n < 0 ? 0 : (keep_n == 0 ? 256 : s_sel[0]);
     int base = 0;
     for (int i0 = 0; i0 < n; i0 += 256) {
         const int i = i0 + tid;
@@ -150,6 +155,7 @@ orb_select_harris_kernel(const int32_t* __restrict__ sel_xy, const float* __rest
     __shared__ int s_warp[8];
     __shared__ uint32_t s_prefix;
     __shared__ int s_want;
+    __shared__ int s_sel[2];
     const int f = blockIdx.x, tid = threadIdx.x;
     const int n = n_sel[f];
     const int32_t* xy = sel_xy + (size_t)f * fcap * 2;
@@ -171,11 +177,10 @@ orb_select_harris_kernel(const int32_t* __restrict__ sel_xy, const float* __rest
                     if ((k & mask) == prefix) atomicAdd(&s_hist[(k >> shift) & 255], 1);
                 }
                 __syncthreads();
+                hist_select_desc(s_hist, s_want, 0, s_warp, s_sel);
                 if (tid == 0) {
-                    int want = s_want, acc = 0, b = 255;
-                    for (; b > 0; b--) { if (acc + s_hist[b] >= want) break; acc += s_hist[b]; }
-                    s_prefix = prefix | ((uint32_t)b << shift);
-                    s_want = want - acc;
+                    s_prefix = prefix | ((uint32_t)s_sel[0] << shift);
+                    s_want -= s_sel[1];
                 }
                 __syncthreads();
             }
