@@ -217,20 +217,27 @@ fast_scan_kernel(const int32_t* __restrict__ row_count, int h, int32_t* __restri
     const int frame = blockIdx.x;
     const int32_t* c = row_count + (size_t)frame * h;
     int32_t* o = row_offset + (size_t)frame * h;
-    __shared__ int s_sum[256];
+    __shared__ int s_warp[8];
     const int per = (h + 255) / 256;
     const int b = threadIdx.x * per, e = min(b + per, h);
     int t = 0;
     for (int i = b; i < e; i++) t += c[i];
-    s_sum[threadIdx.x] = t;
+    // exclusive scan of the 256 partial sums (warp scans; a walk by one thread was 256 dependent shared-memory accesses)
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int inc = t;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) { const int v = __shfl_up_sync(0xffffffffu, inc, off); if (lane >= off) inc += v; }
+    if (lane == 31) s_warp[warp] = inc;
     __syncthreads();
-    if (threadIdx.x == 0) {
-        int acc = 0;
-        for (int i = 0; i < 256; i++) { const int v = s_sum[i]; s_sum[i] = acc; acc += v; }
-        n_kp[frame] = acc;
+    if (warp == 0) {
+        int w8 = lane < 8 ? s_warp[lane] : 0;
+#pragma unroll
+        for (int off = 1; off < 8; off <<= 1) { const int v = __shfl_up_sync(0xffffffffu, w8, off); if (lane >= off) w8 += v; }
+        if (lane < 8) s_warp[lane] = w8;
     }
     __syncthreads();
-    int acc = s_sum[threadIdx.x];
+    if (threadIdx.x == 0) n_kp[frame] = s_warp[7];
+    int acc = (warp ? s_warp[warp - 1] : 0) + inc - t;
     for (int i = b; i < e; i++) { o[i] = acc; acc += c[i]; }
 }
 
