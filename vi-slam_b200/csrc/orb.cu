@@ -587,15 +587,21 @@ orb_resize_tile_kernel(const uint8_t* __restrict__ src, long long src_stride, in
     const int oy_first = __ldg(tab + dw + y0).x;
     const int nrows = min(__ldg(tab + dw + min(y0 + 8 * RZ_ROWS - 1, dh - 1)).x + 2 - oy_first, nrows_cap);
     const uint8_t* img = src + (size_t)f * src_stride;
-    // 16 x 16 threads over (vector column, row)
+    // 16 x 16 threads over (vector column, row); pointers advance by additions only
     for (int c = threadIdx.x & 15; c < nvec; c += 16) {
         const int gx = xs + 16 * c;
-        const uint8_t* col = img + (size_t)oy_first * spitch + gx;
+        const int r0 = threadIdx.x >> 4;
+        uint4* sp = s_tile + r0 * nvec + c;
+        if (gx < spitch) {
+            const uint8_t* gp = img + (size_t)(oy_first + r0) * spitch + gx;
+            const size_t gstep = (size_t)16 * spitch;
 #pragma unroll 4
-        for (int r = threadIdx.x >> 4; r < nrows; r += 16) {
-            uint4 v = make_uint4(0u, 0u, 0u, 0u);
-            if (gx < spitch) v = __ldg(reinterpret_cast<const uint4*>(col + (size_t)r * spitch));
-            s_tile[r * nvec + c] = v;
+            for (int r = r0; r < nrows; r += 16) {
+                *sp = __ldg(reinterpret_cast<const uint4*>(gp));
+                gp += gstep; sp += 16 * nvec;
+            }
+        } else {
+            for (int r = r0; r < nrows; r += 16) { *sp = make_uint4(0u, 0u, 0u, 0u); sp += 16 * nvec; }
         }
     }
     __syncthreads();
@@ -616,7 +622,7 @@ orb_resize_tile_kernel(const uint8_t* __restrict__ src, long long src_stride, in
         sel[j] = d | ((d + 1u) << 4);
     }
     const int wrow = nvec * 4;                                         // words per tile row
-    const int wi0 = (ox[0] - xs) >> 2, wi1 = min(wi0 + 1, wrow - 1), wi2 = min(wi0 + 2, wrow - 1);
+    const int wi0 = min((ox[0] - xs) >> 2, wrow - 3);                 // (the tile row is sized for the 12-byte window of its last thread)
     const uint32_t shift = (uint32_t)(ox[0] & 3) * 8u;                 // (xs is a multiple of 4)
     const uint32_t* tile = reinterpret_cast<const uint32_t*>(s_tile);
     uint8_t* out = dst + ((size_t)f * dh + yb) * dpitch + xq;
@@ -633,14 +639,14 @@ orb_resize_tile_kernel(const uint8_t* __restrict__ src, long long src_stride, in
 #pragma unroll
             for (int j = 0; j < 4; j++) h0[j] = hp[j];
         } else {
-            const uint32_t* rp = tile + (oy - oy_first) * wrow;
-            const uint32_t a = __funnelshift_r(rp[wi0], rp[wi1], shift), b = __funnelshift_r(rp[wi1], rp[wi2], shift);
+            const uint32_t* rp = tile + (oy - oy_first) * wrow + wi0;
+            const uint32_t a = __funnelshift_r(rp[0], rp[1], shift), b = __funnelshift_r(rp[1], rp[2], shift);
 #pragma unroll
             for (int j = 0; j < 4; j++) h0[j] = __dp2a_lo(cf[j], __byte_perm(a, b, sel[j]), 0u);
         }
         {
-            const uint32_t* rp = tile + (oy + 1 - oy_first) * wrow;
-            const uint32_t a = __funnelshift_r(rp[wi0], rp[wi1], shift), b = __funnelshift_r(rp[wi1], rp[wi2], shift);
+            const uint32_t* rp = tile + (oy + 1 - oy_first) * wrow + wi0;
+            const uint32_t a = __funnelshift_r(rp[0], rp[1], shift), b = __funnelshift_r(rp[1], rp[2], shift);
 #pragma unroll
             for (int j = 0; j < 4; j++) h1[j] = __dp2a_lo(cf[j], __byte_perm(a, b, sel[j]), 0u);
         }
