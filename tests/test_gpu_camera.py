@@ -39,10 +39,11 @@ def test_pyramid_and_gradient(ctx, oracle, w, h):
             np.testing.assert_array_equal(ggm[l], oracle.grad_mag(rx, ry))
 
 
-@pytest.mark.parametrize("w,h", [(752, 480), (640, 480), (64, 48), (16, 16), (2048, 1024)])
+@pytest.mark.parametrize("w,h", [(752, 480), (640, 480), (64, 48), (16, 16), (2048, 1024), (1241, 376), (1243, 379), (155, 47), (33, 31), (37, 21)])
 @pytest.mark.parametrize("levels", [5, 3, 1])
 def test_pyramid_register_blocked_kernel(ctx, oracle, w, h, levels):
-    """The register-blocked kernel (pyr_impl 1: one thread per 16x16 block) against the shared-memory tile kernel
+    """The register-blocked kernels (pyr_impl 1: one thread per 16x16 block; aligned multiples of 16, and the any-size form with
+    its edge fix-up for level sizes that cvRound rounds up: 155 -> 78, 47 -> 24) against the shared-memory tile kernel
     (pyr_impl 0) and the oracle, for every level count, with the frame copied in and with level 0 already in place."""
     import torch
     import vislam_b200 as vb

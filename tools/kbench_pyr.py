@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Micro-benchmark of the pyramid kernels (CUDA events): GB/s of algorithmic traffic (read w*h, write every level)
-for pyr_impl 0 (shared-memory tile kernel) and 1 (register-blocked).  Usage: python tools/kbench_pyr.py [frames]"""
+for pyr_impl 0 (shared-memory tile kernel) and 1 (register-blocked).  Usage: python tools/kbench_pyr.py [frames] [w h]"""
 import ctypes
 import os
 import sys
@@ -11,7 +11,7 @@ import torch
 import vislam_b200 as vb
 
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 2000
-w, h = 752, 480
+w, h = (int(sys.argv[2]), int(sys.argv[3])) if len(sys.argv) > 3 else (752, 480)
 ctx = vb.Context(0)
 lay = vb.pyr_layout(w, h)
 img = torch.randint(0, 256, (B, h, w), dtype=torch.uint8, device="cuda")

@@ -192,6 +192,159 @@ pyramid16_kernel(const uint8_t* __restrict__ img, long long img_stride, int pitc
     out[L.offset[4] + (size_t)by * L.w[4] + bx] = (uint8_t)((s4 + 2u) >> 2);
 }
 
+// The same register-blocked form for ANY frame size and alignment (KITTI's 1241x376: rows start on every byte alignment, the
+// levels are 620x188, 310x94, 155x47, 77x23).  Level l is (w >> l) x (h >> l) (Camera.cpp:44-47), so pixel (x, y) of level l
+// is still the rounded mean of the level-0 block [x 2^l, (x + 1) 2^l) x [y 2^l, (y + 1) 2^l), which lies inside the frame
+// whenever the pixel exists: a thread owns a 16x16 level-0 block as before, the blocks of the last column / row are partial.
+// A block row is read as five aligned words and funnel-shifted into place (bytes past the frame's width only reach pixels
+// that do not exist); stores take the widest unit the destination's alignment allows (level 1 of a 1241-wide frame is on
+// 4-byte boundaries, level 2 on 2-byte ones) and stop at the level's width.
+template <int NW>
+__device__ __forceinline__ void store_run(uint8_t* dst, const uint32_t (&wd)[NW], int nbytes) {
+    if (nbytes <= 0) return;
+    const unsigned a = (unsigned)(reinterpret_cast<uintptr_t>(dst) & 3u);
+    if (a == 0u) {
+#pragma unroll
+        for (int j = 0; j < NW; j++) {
+            if (4 * j + 3 < nbytes) *reinterpret_cast<uint32_t*>(dst + 4 * j) = wd[j];
+            else {
+#pragma unroll
+                for (int t = 0; t < 4; t++) if (4 * j + t < nbytes) dst[4 * j + t] = (uint8_t)(wd[j] >> (8 * t));
+            }
+        }
+    } else if (a == 2u) {
+#pragma unroll
+        for (int j = 0; j < 2 * NW; j++) {
+            const uint32_t hw = (wd[j >> 1] >> (16 * (j & 1))) & 0xFFFFu;
+            if (2 * j + 1 < nbytes) *reinterpret_cast<uint16_t*>(dst + 2 * j) = (uint16_t)hw;
+            else if (2 * j < nbytes) dst[2 * j] = (uint8_t)hw;
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < 4 * NW; i++) if (i < nbytes) dst[i] = (uint8_t)(wd[i >> 2] >> (8 * (i & 3)));
+    }
+}
+
+__global__ void __launch_bounds__(P16_THREADS)
+pyramid16u_kernel(const uint8_t* __restrict__ img, long long img_stride, int pitch, PyrParams P, uint8_t* __restrict__ pyr) {
+    const vsb_pyr_layout_t& L = P.lay;
+    const int w0 = L.w[0], h0 = L.h[0];
+    const int bw = (w0 + 15) >> 4, nb = bw * ((h0 + 15) >> 4);
+    const int b = blockIdx.x * P16_THREADS + threadIdx.x;
+    if (b >= nb) return;
+    const int by = b / bw, bx = b - by * bw;
+    const int frame = blockIdx.y;
+    uint8_t* out = pyr + (size_t)frame * L.frame_stride;
+    const uint8_t* in = img ? img + (size_t)frame * img_stride : out;
+    const int in_pitch = img ? pitch : w0;
+    const int nx0 = min(16, w0 - 16 * bx), ny0 = min(16, h0 - 16 * by);      // valid level-0 bytes / rows of this block
+
+    uint4 r[16];
+#pragma unroll
+    for (int k = 0; k < 16; k++) {
+        uint32_t wv[5] = {0u, 0u, 0u, 0u, 0u};
+        const uint8_t* a = in + (size_t)(by * 16 + k) * in_pitch + bx * 16;
+        const unsigned mis = (unsigned)(reinterpret_cast<uintptr_t>(a) & 3u);
+        if (k < ny0) {
+            const uint32_t* wp = reinterpret_cast<const uint32_t*>(a - mis);
+            const int need = (int)mis + nx0;                              // bytes from the aligned start to the last valid one
+#pragma unroll
+            for (int j = 0; j < 5; j++) if (4 * j < need) wv[j] = __ldg(wp + j);
+        }
+        const unsigned sh = 8u * mis;
+        r[k] = make_uint4(__funnelshift_r(wv[0], wv[1], sh), __funnelshift_r(wv[1], wv[2], sh),
+                          __funnelshift_r(wv[2], wv[3], sh), __funnelshift_r(wv[3], wv[4], sh));
+    }
+    if (img && P.copy_l0) {                                       // Camera::Update keeps a copy of the frame as level 0
+        uint8_t* dst = out + (size_t)(by * 16) * w0 + bx * 16;
+#pragma unroll
+        for (int k = 0; k < 16; k++)
+            if (k < ny0) { const uint32_t wd[4] = {r[k].x, r[k].y, r[k].z, r[k].w}; store_run<4>(dst + (size_t)k * w0, wd, nx0); }
+    }
+    if (L.levels < 2) return;
+    uint2 l1[8];
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+        const uint4 a = r[2 * k], c = r[2 * k + 1];
+        const uint32_t s0 = mean4(hsum2(a.x) + hsum2(c.x)), s1 = mean4(hsum2(a.y) + hsum2(c.y));
+        const uint32_t s2 = mean4(hsum2(a.z) + hsum2(c.z)), s3 = mean4(hsum2(a.w) + hsum2(c.w));
+        l1[k] = make_uint2(pack4(s0, s1), pack4(s2, s3));
+    }
+    {
+        const int w1 = L.w[1], nx = min(8, w1 - 8 * bx), ny = min(8, L.h[1] - 8 * by);
+        uint8_t* dst = out + L.offset[1] + (size_t)(by * 8) * w1 + bx * 8;
+#pragma unroll
+        for (int k = 0; k < 8; k++)
+            if (k < ny) { const uint32_t wd[2] = {l1[k].x, l1[k].y}; store_run<2>(dst + (size_t)k * w1, wd, nx); }
+    }
+    if (L.levels < 3) return;
+    uint32_t l2[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        const uint2 a = l1[2 * k], c = l1[2 * k + 1];
+        l2[k] = pack4(mean4(hsum2(a.x) + hsum2(c.x)), mean4(hsum2(a.y) + hsum2(c.y)));
+    }
+    {
+        const int w2 = L.w[2], nx = min(4, w2 - 4 * bx), ny = min(4, L.h[2] - 4 * by);
+        uint8_t* dst = out + L.offset[2] + (size_t)(by * 4) * w2 + bx * 4;
+#pragma unroll
+        for (int k = 0; k < 4; k++)
+            if (k < ny) { const uint32_t wd[1] = {l2[k]}; store_run<1>(dst + (size_t)k * w2, wd, nx); }
+    }
+    if (L.levels < 4) return;
+    uint32_t l3[2];
+#pragma unroll
+    for (int k = 0; k < 2; k++) {
+        const uint32_t s = mean4(hsum2(l2[2 * k]) + hsum2(l2[2 * k + 1]));
+        l3[k] = (s & 0xFFu) | ((s >> 8) & 0xFF00u);
+    }
+    {
+        const int w3 = L.w[3], nx = min(2, w3 - 2 * bx), ny = min(2, L.h[3] - 2 * by);
+        uint8_t* dst = out + L.offset[3] + (size_t)(by * 2) * w3 + bx * 2;
+#pragma unroll
+        for (int k = 0; k < 2; k++)
+            if (k < ny) { const uint32_t wd[1] = {l3[k]}; store_run<1>(dst + (size_t)k * w3, wd, nx); }
+    }
+    if (L.levels < 5) return;
+    if (bx < L.w[4] && by < L.h[4]) {
+        const uint32_t s4 = (l3[0] & 0xFFu) + (l3[0] >> 8) + (l3[1] & 0xFFu) + (l3[1] >> 8);
+        out[L.offset[4] + (size_t)by * L.w[4] + bx] = (uint8_t)((s4 + 2u) >> 2);
+    }
+}
+
+// Level sizes are cvRound(size / 2) (vsb_pyr_layout), which rounds an odd half UP when it is odd (155 -> 78, 47 -> 24): the
+// last column / row of such a level has only one source column / row (the clipped mean of pyramid_kernel: sum / count, rounded
+// to nearest even), and everything computed from it inherits that.  Whatever the block kernel does wrong therefore stays inside
+// the last two columns and rows of every level (pixel x of level l reads 2x and 2x + 1 of level l - 1), and this kernel — one
+// block per frame, level after level — recomputes exactly those from the level below with the generic kernel's arithmetic.
+__global__ void __launch_bounds__(256)
+pyramid_edge_fix_kernel(const uint8_t* __restrict__ img, long long img_stride, int pitch, PyrParams P, uint8_t* __restrict__ pyr) {
+    const vsb_pyr_layout_t& L = P.lay;
+    const int frame = blockIdx.x;
+    uint8_t* out = pyr + (size_t)frame * L.frame_stride;
+    for (int l = 1; l < L.levels; l++) {
+        const int sw = L.w[l - 1], sh = L.h[l - 1], dw = L.w[l], dh = L.h[l];
+        const uint8_t* src = (l == 1 && img) ? img + (size_t)frame * img_stride : out + L.offset[l - 1];
+        const int sp = (l == 1 && img) ? pitch : sw;
+        uint8_t* dst = out + L.offset[l];
+        const int ncol = 2 * dh, nrow = 2 * dw;                    // the last two columns, then the last two rows
+        for (int i = threadIdx.x; i < ncol + nrow; i += 256) {
+            int dx, dy;
+            if (i < ncol) { dy = i >> 1; dx = dw - 1 - (i & 1); }
+            else { const int j = i - ncol; dx = j >> 1; dy = dh - 1 - (j & 1); }
+            if (dx < 0 || dy < 0) continue;
+            int sum = 0, cnt = 0;
+#pragma unroll
+            for (int sy = 0; sy < 2; sy++)
+#pragma unroll
+                for (int sx = 0; sx < 2; sx++)
+                    if (2 * dy + sy < sh && 2 * dx + sx < sw) { sum += src[(size_t)(2 * dy + sy) * sp + 2 * dx + sx]; cnt++; }
+            dst[(size_t)dy * dw + dx] = mean_clipped(sum, cnt);
+        }
+        __syncthreads();                                            // the next level reads what this one wrote
+    }
+}
+
 // ---------------------------------------------------------------------------------------------- Scharr
 // cv::Scharr(src, dst, CV_16S, dx, dy, scale = 3, 0, BORDER_REFLECT_101): derivative [-1 0 1], smoothing
 // [3 10 3], times 3 (Camera.cpp:171-172; the literal 3 is `scale`).  One launch covers every
@@ -525,6 +678,42 @@ int vsb_pyramid_build_levels(vsb_ctx_t* ctx, const uint8_t* img, int64_t img_str
             VSB_LAUNCHED(ctx);
         }
         return VSB_OK;
+    }
+    // any other size / alignment: the same blocks read as aligned words and funnel-shifted (levels are floor halvings up to
+    // level 4, which is all a 16x16 block determines)
+    if (ctx->pyr_impl != 0 && layout->levels <= 5) {
+        // level sizes a 16x16 block hierarchy covers: floor or ceil of half the level below (cvRound(size / 2) is one of them)
+        bool halvings = true, exact = true;
+        for (int l = 1; l < layout->levels; l++) {
+            const int pw = layout->w[l - 1], ph = layout->h[l - 1];
+            if ((layout->w[l] != pw / 2 && layout->w[l] != (pw + 1) / 2) || (layout->h[l] != ph / 2 && layout->h[l] != (ph + 1) / 2)) halvings = false;
+            if (layout->w[l] != pw / 2 || layout->h[l] != ph / 2) exact = false;
+        }
+        if (halvings) {
+            const int nb = ((layout->w[0] + 15) / 16) * ((layout->h[0] + 15) / 16);
+            // Camera::Update's copy of the frame as level 0: rows of any alignment are best left to the copy engine's
+            // arithmetic (one strided device-to-device copy for the batch) rather than byte stores in the kernel
+            if (img && copy_l0 && pitch == layout->w[0]) {
+                ProfScope ps(ctx, VSB_K_PYRAMID, (cudaStream_t)stream);
+                VSB_CUDA(ctx, cudaMemcpy2DAsync(pyr, (size_t)layout->frame_stride, img, (size_t)img_stride, (size_t)layout->w[0] * layout->h[0],
+                                                (size_t)count, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+                P.copy_l0 = 0;
+            }
+            for (int z0 = 0; z0 < count; z0 += 65535) {
+                int zc = count - z0 < 65535 ? count - z0 : 65535;
+                dim3 grid(vsb_div_up(nb, P16_THREADS), zc);
+                ProfScope ps(ctx, VSB_K_PYRAMID, (cudaStream_t)stream);
+                pyramid16u_kernel<<<grid, P16_THREADS, 0, (cudaStream_t)stream>>>(
+                    img ? img + (size_t)z0 * img_stride : nullptr, img_stride, pitch, P, pyr + (size_t)z0 * layout->frame_stride);
+                VSB_LAUNCHED(ctx);
+                if (!exact) {
+                    pyramid_edge_fix_kernel<<<zc, 256, 0, (cudaStream_t)stream>>>(
+                        img ? img + (size_t)z0 * img_stride : nullptr, img_stride, pitch, P, pyr + (size_t)z0 * layout->frame_stride);
+                    VSB_LAUNCHED(ctx);
+                }
+            }
+            return VSB_OK;
+        }
     }
     for (int z0 = 0; z0 < count; z0 += 65535) {
         int zc = count - z0 < 65535 ? count - z0 : 65535;
