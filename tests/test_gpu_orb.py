@@ -175,3 +175,26 @@ def test_orb_pyramid_forms_agree(ctx, w, h, sf, nl):
         assert a[0] == b[0] and a[0] > 100
         for x, y in zip(a[1:], b[1:]):
             assert np.array_equal(x, y)
+
+
+def test_orb_levels_on_separate_streams(ctx):
+    """Small batches run the pyramid levels on separate streams ("orb_lp" 1, the default: one block of scratch per level, key
+    points appended in level order at the end); the one-stream form (0) must give the same arrays, call after call."""
+    rng = np.random.default_rng(77)
+    frames = []
+    for s in range(3):
+        f = (rng.random((480, 752)) * 255).astype(np.float32)
+        f = (f + np.roll(f, 1, 0) + np.roll(f, 1, 1) + np.roll(f, (1, 1), (0, 1))) / 4
+        frames.append(f.astype(np.uint8))
+    imgs = np.stack(frames)
+    try:
+        ctx.option("orb_lp", 0)
+        one = run_pyr(ctx, imgs, 1000, cap=2000)
+    finally:
+        ctx.option("orb_lp", 1)
+    for _ in range(3):
+        lp = run_pyr(ctx, imgs, 1000, cap=2000)
+        for a, b in zip(one, lp):
+            assert a[0] == b[0] and a[0] > 500
+            for x, y in zip(a[1:], b[1:]):
+                assert np.array_equal(x, y)

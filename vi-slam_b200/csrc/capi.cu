@@ -58,6 +58,8 @@ extern "C" int vsb_ctx_create(int device, vsb_ctx_t** out) {
     c->gn_cluster_threads = 0;
     c->orb_scratch_mb = 8192;
     c->orb_impl = 0;
+    c->orb_lp = 1;
+    c->orb_lp_ready = 0;
     c->fast_impl = 0;
     c->knn_l2_impl = 1;
     if (const char* e = getenv("VSB_KNN_L2_IMPL")) c->knn_l2_impl = atoi(e) ? 1 : 0;
@@ -71,6 +73,7 @@ extern "C" int vsb_ctx_create(int device, vsb_ctx_t** out) {
     if (const char* e = getenv("VSB_GN_CLUSTER_THREADS")) vsb_ctx_option(c, "gn_cluster_threads", atoi(e));
     if (const char* e = getenv("VSB_ORB_SCRATCH_MB")) vsb_ctx_option(c, "orb_scratch_mb", atoi(e));
     if (const char* e = getenv("VSB_ORB_IMPL")) vsb_ctx_option(c, "orb_impl", atoi(e));
+    if (const char* e = getenv("VSB_ORB_LP")) vsb_ctx_option(c, "orb_lp", atoi(e));
     if (const char* e = getenv("VSB_FAST_IMPL")) vsb_ctx_option(c, "fast_impl", atoi(e));
     if (const char* e = getenv("VSB_GN_THREADS")) vsb_ctx_option(c, "gn_threads", atoi(e));
     *out = c;
@@ -129,6 +132,11 @@ extern "C" int vsb_ctx_option(vsb_ctx_t* ctx, const char* name, int value) {
         ctx->fast_impl = value;
         return VSB_OK;
     }
+    if (!strcmp(name, "orb_lp")) {
+        if (value < 0 || value > 1) return VSB_ERR_INVALID;
+        ctx->orb_lp = value;
+        return VSB_OK;
+    }
     if (!strcmp(name, "orb_impl")) {
         if (value < 0 || value > 15) return VSB_ERR_INVALID;
         ctx->orb_impl = value;
@@ -157,6 +165,8 @@ extern "C" int vsb_ctx_destroy(vsb_ctx_t* ctx) {
     if (ctx->scratch) cudaFree(ctx->scratch);
     if (ctx->scratch2) cudaFree(ctx->scratch2);
     for (int i = 0; i < ctx->ws_n; i++) if (ctx->ws_ptr[i]) cudaFree(ctx->ws_ptr[i]);
+    if (ctx->orb_lp_ready)
+        for (int i = 0; i < 8; i++) { cudaStreamDestroy(ctx->orb_stream[i]); cudaEventDestroy(ctx->orb_ev_ready[i]); cudaEventDestroy(ctx->orb_ev_done[i]); }
     for (auto& r : ctx->prof_pending) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
     for (auto e : ctx->prof_free) cudaEventDestroy(e);
     delete ctx;
@@ -166,6 +176,17 @@ extern "C" int vsb_ctx_destroy(vsb_ctx_t* ctx) {
 extern "C" const char* vsb_last_cuda_error(vsb_ctx_t* ctx) { return ctx ? ctx->last_error : ""; }
 extern "C" int vsb_sm_count(vsb_ctx_t* ctx) { return ctx ? ctx->sm_count : 0; }
 extern "C" long long vsb_launch_count(vsb_ctx_t* ctx) { return ctx ? ctx->launches : 0; }
+
+int vsb_orb_lp_streams(vsb_ctx* ctx) {
+    if (ctx->orb_lp_ready) return VSB_OK;
+    for (int i = 0; i < 8; i++) {
+        VSB_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->orb_stream[i], cudaStreamNonBlocking));
+        VSB_CUDA(ctx, cudaEventCreateWithFlags(&ctx->orb_ev_ready[i], cudaEventDisableTiming));
+        VSB_CUDA(ctx, cudaEventCreateWithFlags(&ctx->orb_ev_done[i], cudaEventDisableTiming));
+    }
+    ctx->orb_lp_ready = 1;
+    return VSB_OK;
+}
 
 int vsb_scratch_reserve(vsb_ctx* ctx, size_t bytes, void** out) {
     if (bytes > ctx->scratch_bytes) {

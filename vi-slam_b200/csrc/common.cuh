@@ -62,6 +62,10 @@ struct vsb_ctx {
     int gn_tail;      // gn_track.cu: 1 (default) = pairs of the last partial wave run with more threads each, 0 = one launch
     int orb_scratch_mb;   // ORB: scratch budget of one chunk of frames in MB (default 8192)
     int fast_impl;    // FAST compaction: 0 (default) = 16 pixels per lane, suppression once (bit per pixel); 1 = 4 pixels per lane, suppression in both passes
+    int orb_lp;       // ORB: 1 (default) = small batches run the pyramid levels on separate streams, 0 = one stream always
+    cudaStream_t orb_stream[8];   // per-level streams / events of that form, created on first use
+    cudaEvent_t orb_ev_ready[8], orb_ev_done[8];
+    int orb_lp_ready;
     int orb_impl;     // ORB tuning switch, bit mask of the PREVIOUS forms kept for comparison (default 0): 1 = per-pixel resize, 2 = per-warp sin / cos in the descriptor kernel
     int pyr_impl;     // pyramid: 0 = generic shared-memory tile kernel, 1 = register-blocked kernel when w, h are multiples of 16
 };

@@ -12,6 +12,7 @@
 #include "common.cuh"
 
 size_t vsb_fast_scratch_bytes(int w, int h, int count);
+int vsb_orb_lp_streams(vsb_ctx_t* ctx);            // capi.cu: creates the context's per-level streams and events on first use
 int vsb_fast_detect_ws(vsb_ctx_t* ctx, const uint8_t* img, int64_t img_stride, int pitch, int w, int h, int count, int threshold,
                        int nonmax, int cap, int32_t* kp_xy, int32_t* kp_score, int32_t* n_kp, void* scratch, void* stream);
 
@@ -800,13 +801,94 @@ static size_t orb_pyr_frame_bytes(int w, int h, int cap, bool describe) {
     const size_t wpad = (size_t)((w + 15) & ~15);            // level rows are padded to 16 bytes: a level can be up to wpad x h bytes (scale factors close to 1)
     return orb_scratch_bytes(1, w, h, describe) + 2 * orb_al(wpad * h) + tmp_frame + 256 + vsb_fast_scratch_bytes(w, h, 1);
 }
-size_t vsb_orb_pyr_ws_bytes(int w, int h, int frames, int cap, int describe) {
-    return (size_t)frames * orb_pyr_frame_bytes(w, h, cap, describe != 0) + orb_al((size_t)(w + h) * sizeof(int4)) + 4096;
+constexpr int ORB_LP_LEVELS = 8;
+// the levels cv::ORB builds: (int)lrintf(size / scale_l), until the 31-pixel border filter leaves nothing
+static int orb_level_dims(int w, int h, float scale_factor, int nlevels, int* lw, int* lh) {
+    int nl = 0;
+    for (int l = 0; l < nlevels && l < 32; l++, nl++) {
+        const float scale = (float)pow((double)scale_factor, (double)l);
+        lw[l] = l ? (int)lrintf((float)w / scale) : w;
+        lh[l] = l ? (int)lrintf((float)h / scale) : h;
+        if (l > 0 && (lw[l] <= 2 * ORB_EDGE || lh[l] <= 2 * ORB_EDGE)) break;
+    }
+    return nl;
 }
+// workspace of the levels-in-parallel form: one block of scratch per level, sized for that level
+static size_t orb_pyr_lp_frame_bytes(int w, int h, int cap, bool describe, float scale_factor, int nlevels) {
+    int lw[32], lh[32];
+    const int nl = orb_level_dims(w, h, scale_factor, nlevels, lw, lh);
+    size_t sum = 0;
+    for (int l = 0; l < nl; l++) sum += orb_pyr_frame_bytes(l ? (lw[l] + 15) & ~15 : w, lh[l], cap, describe);
+    return sum;
+}
+// Workspace for `frames` frames at once: the levels-in-parallel form when it fits `budget` bytes (small and medium batches are
+// bound by the chain of dependent launches, see below), else one block that the levels share.
+size_t vsb_orb_pyr_ws_bytes(int w, int h, int frames, int cap, int describe, float scale_factor, int nlevels, size_t budget) {
+    const size_t fixed = orb_al((size_t)(w + h) * sizeof(int4)) + 4096;
+    const size_t lp = fixed + (size_t)frames * orb_pyr_lp_frame_bytes(w, h, cap, describe != 0, scale_factor, nlevels);
+    if (nlevels > 1 && nlevels <= ORB_LP_LEVELS && lp <= budget) return lp;
+    return fixed + (size_t)frames * orb_pyr_frame_bytes(w, h, cap, describe != 0);
+}
+
+namespace {
+struct OrbBlock {                     // everything one run of the one-level pipeline needs besides the input image
+    OrbScratch S;
+    uint8_t* img[2];                  // level images (ping-pong in the one-block form)
+    int32_t* lxy; float* lresp; float* langle; uint8_t* ldesc; int32_t* ln;
+    void* fast_scratch;
+};
+OrbBlock orb_block_carve(uint8_t*& p, int chunk, int w, int h, int cap, bool describe) {
+    OrbBlock b;
+    const size_t wpad = (size_t)((w + 15) & ~15);
+    const size_t b_img = orb_al((size_t)chunk * wpad * h);
+    b.S = orb_scratch_carve(p, chunk, w, h, describe);
+    b.img[0] = p; p += b_img;
+    b.img[1] = p; p += b_img;
+    b.lxy = reinterpret_cast<int32_t*>(p); p += orb_al((size_t)chunk * cap * 8);
+    b.lresp = reinterpret_cast<float*>(p); p += orb_al((size_t)chunk * cap * 4);
+    b.langle = reinterpret_cast<float*>(p); p += orb_al((size_t)chunk * cap * 4);
+    b.ldesc = nullptr;
+    if (describe) { b.ldesc = p; p += orb_al((size_t)chunk * cap * 32); }
+    b.ln = reinterpret_cast<int32_t*>(p); p += orb_al((size_t)chunk * 4);
+    b.fast_scratch = p; p += (vsb_fast_scratch_bytes(w, h, chunk) + 255) & ~(size_t)255;
+    return b;
+}
+// one level image from the one below it (cv::resize, INTER_LINEAR_EXACT), rows padded to 16 bytes
+int orb_resize_level(vsb_ctx_t* ctx, const uint8_t* cur, int64_t cur_stride, int cp, int cw, int ch, uint8_t* dst, int nw, int nh,
+                      int np, int zc, int4* rz_tab, cudaStream_t st) {
+    const bool words = ((reinterpret_cast<uintptr_t>(cur) | (uintptr_t)cur_stride | (uintptr_t)cp) & 3u) == 0 &&
+                       cw >= 2 && ch >= 2 && 2 * nw >= cw && !(ctx->orb_impl & 1);
+    if (words) {
+        orb_resize_coeff_folded_kernel<<<vsb_div_up(nw + nh, 256), 256, 0, st>>>(cw, ch, nw, nh, reinterpret_cast<int2*>(rz_tab));
+        VSB_LAUNCHED(ctx);
+        // tile form: a tile row spans ceil(127 s) + 2 taps, up to 15 bytes of alignment and the 12-byte window
+        const int nvec = ((127 * cw + nw - 1) / nw + 2 + 15 + 12 + 15) / 16;
+        const int nrows_cap = ((8 * RZ_ROWS - 1) * ch + nh - 1) / nh + 3;
+        const size_t tile_bytes = (size_t)nvec * 16 * nrows_cap;
+        const bool tiles = ((reinterpret_cast<uintptr_t>(cur) | (uintptr_t)cur_stride | (uintptr_t)cp) & 15u) == 0 &&
+                           tile_bytes <= 48 * 1024 && !(ctx->orb_impl & 8);
+        const dim3 rgrid(vsb_div_up(nw, 128), vsb_div_up(nh, 8 * RZ_ROWS), zc);
+        if (tiles)
+            orb_resize_tile_kernel<<<rgrid, 256, tile_bytes, st>>>(cur, cur_stride, cp, dst, nw, nh, np,
+                                                                   reinterpret_cast<const int2*>(rz_tab), nvec, nrows_cap);
+        else
+            orb_resize4_kernel<<<rgrid, 256, 0, st>>>(cur, cur_stride, cp, dst, nw, nh, np, reinterpret_cast<const int2*>(rz_tab));
+    } else {
+        orb_resize_coeff_kernel<<<vsb_div_up(nw + nh, 256), 256, 0, st>>>(cw, ch, nw, nh, rz_tab);
+        VSB_LAUNCHED(ctx);
+        orb_resize_kernel<<<dim3(vsb_div_up(nw, 128), vsb_div_up(nh, 8), zc), 256, 0, st>>>(cur, cur_stride, cp, cw, ch, dst, nw, nh, np, rz_tab);
+    }
+    VSB_LAUNCHED(ctx);
+    return VSB_OK;
+}
+}  // namespace
 
 // The detector on a caller-provided workspace `ws` of `ws_bytes` (256-byte aligned): the batch is processed in chunks of as
 // many frames as the workspace holds.  The tracker gives each of its two slots its own workspace, so that the chunks of a
 // sequence can run on two streams at once; the public entry below takes the workspace from the context.
+// A batch whose per-level scratch fits the workspace (a few hundred frames under the default budget) is bound by the chain of ~14 dependent launches per level:
+// there the scale pyramid is built first, then every level's pipeline runs on its own stream with its own block of scratch,
+// and the levels' key points are appended in order at the end — the chain is 7 + 14 launches deep instead of 8 x 15.
 int vsb_orb_detect_compute_pyr_ws(vsb_ctx_t* ctx, const uint8_t* img, int64_t img_stride, int pitch, int w, int h,
                                   int count, int nfeatures, float scale_factor, int nlevels, int fast_threshold, int cap,
                                   float* kp_xy, int32_t* kp_octave, float* kp_resp, float* kp_angle, uint8_t* desc,
@@ -827,76 +909,78 @@ int vsb_orb_detect_compute_pyr_ws(vsb_ctx_t* ctx, const uint8_t* img, int64_t im
     }
     const bool describe = desc != nullptr;
     if (!ws) return VSB_ERR_INVALID;
-    const size_t wpad = (size_t)((w + 15) & ~15);
     const size_t fixed = orb_al((size_t)(w + h) * sizeof(int4)) + 4096;
-    if (ws_bytes < fixed + orb_pyr_frame_bytes(w, h, cap, describe)) return VSB_ERR_CAPACITY;
-    const int chunk = (int)min((size_t)count, (ws_bytes - fixed) / orb_pyr_frame_bytes(w, h, cap, describe));
-    const size_t b_img = orb_al((size_t)chunk * wpad * h);
+    const size_t per = orb_pyr_frame_bytes(w, h, cap, describe);
+    if (ws_bytes < fixed + per) return VSB_ERR_CAPACITY;
+    // levels in parallel: the whole batch at once, one block per level (sized for that level)
+    int lvw[32], lvh[32];
+    const int nlv = orb_level_dims(w, h, scale_factor, nlevels, lvw, lvh);
+    const bool lp = ctx->orb_lp && nlevels > 1 && nlevels <= ORB_LP_LEVELS &&
+                    ws_bytes >= fixed + (size_t)count * orb_pyr_lp_frame_bytes(w, h, cap, describe, scale_factor, nlevels);
+    const int chunk = lp ? count : (int)min((size_t)count, (ws_bytes - fixed) / per);
     int rc;
     uint8_t* p = static_cast<uint8_t*>(ws);
-    const OrbScratch S = orb_scratch_carve(p, chunk, w, h, describe);
-    uint8_t* lvl_img[2];
-    lvl_img[0] = p; p += b_img;
-    lvl_img[1] = p; p += b_img;
-    int32_t* lxy = reinterpret_cast<int32_t*>(p); p += orb_al((size_t)chunk * cap * 8);
-    float* lresp = reinterpret_cast<float*>(p); p += orb_al((size_t)chunk * cap * 4);
-    float* langle = reinterpret_cast<float*>(p); p += orb_al((size_t)chunk * cap * 4);
-    uint8_t* ldesc = nullptr;
-    if (describe) { ldesc = p; p += orb_al((size_t)chunk * cap * 32); }
-    int32_t* ln = reinterpret_cast<int32_t*>(p); p += orb_al((size_t)chunk * 4);
     int4* rz_tab = reinterpret_cast<int4*>(p); p += orb_al((size_t)(w + h) * sizeof(int4));
-    void* fast_scratch = p;                                  // vsb_fast_scratch_bytes(w, h, chunk) <= chunk x the per-frame figure
+    OrbBlock blk[ORB_LP_LEVELS];
+    if (lp) for (int l = 0; l < nlv; l++) blk[l] = orb_block_carve(p, chunk, l ? (lvw[l] + 15) & ~15 : w, lvh[l], cap, describe);
+    else blk[0] = orb_block_carve(p, chunk, w, h, cap, describe);
+    if (lp && (rc = vsb_orb_lp_streams(ctx))) return rc;
     for (int z0 = 0; z0 < count; z0 += chunk) {
         const int zc = min(chunk, count - z0);
         VSB_CUDA(ctx, cudaMemsetAsync(n_kp + z0, 0, (size_t)zc * sizeof(int32_t), st));
         const uint8_t* cur = img + (size_t)z0 * img_stride;
         int64_t cur_stride = img_stride;
         int cw = w, ch = h, cp = pitch;
-        for (int l = 0; l < nlevels; l++) {
+        int nl = 0;                                               // levels that exist (the border filter empties the small ones)
+        float scales[32];
+        for (int l = 0; l < nlevels; l++, nl++) {
             const float scale = (float)pow((double)scale_factor, (double)l);
+            scales[l] = scale;
+            OrbBlock& B = blk[lp ? l : 0];
             if (l > 0) {
                 const int nw = (int)lrintf((float)w / scale), nh = (int)lrintf((float)h / scale);
                 if (nw <= 2 * ORB_EDGE || nh <= 2 * ORB_EDGE) break;       // the border filter leaves nothing from here on
-                uint8_t* dst = lvl_img[l & 1];
+                uint8_t* dst = B.img[lp ? 0 : (l & 1)];
                 ProfScope ps(ctx, VSB_K_ORB, st);
                 // level images get rows padded to 16 bytes (the workspace is sized for padded rows), so that every reader takes its aligned
-                // word path (FAST's loader, the blur, this kernel's packed stores) whatever nw is
+                // word path (FAST's loader, the blur, the resize's packed stores) whatever nw is
                 const int np = (nw + 15) & ~15;
-                const bool words = ((reinterpret_cast<uintptr_t>(cur) | (uintptr_t)cur_stride | (uintptr_t)cp) & 3u) == 0 &&
-                                   cw >= 2 && ch >= 2 && 2 * nw >= cw && !(ctx->orb_impl & 1);
-                if (words) {
-                    orb_resize_coeff_folded_kernel<<<vsb_div_up(nw + nh, 256), 256, 0, st>>>(cw, ch, nw, nh, reinterpret_cast<int2*>(rz_tab));
-                    VSB_LAUNCHED(ctx);
-                    // tile form: a tile row spans ceil(127 s) + 2 taps, up to 15 bytes of alignment and the 12-byte window
-                    const int nvec = ((127 * cw + nw - 1) / nw + 2 + 15 + 12 + 15) / 16;
-                    const int nrows_cap = ((8 * RZ_ROWS - 1) * ch + nh - 1) / nh + 3;
-                    const size_t tile_bytes = (size_t)nvec * 16 * nrows_cap;
-                    const bool tiles = ((reinterpret_cast<uintptr_t>(cur) | (uintptr_t)cur_stride | (uintptr_t)cp) & 15u) == 0 &&
-                                       tile_bytes <= 48 * 1024 && !(ctx->orb_impl & 8);
-                    const dim3 rgrid(vsb_div_up(nw, 128), vsb_div_up(nh, 8 * RZ_ROWS), zc);
-                    if (tiles)
-                        orb_resize_tile_kernel<<<rgrid, 256, tile_bytes, st>>>(cur, cur_stride, cp, dst, nw, nh, np,
-                                                                               reinterpret_cast<const int2*>(rz_tab), nvec, nrows_cap);
-                    else
-                        orb_resize4_kernel<<<rgrid, 256, 0, st>>>(cur, cur_stride, cp, dst, nw, nh, np, reinterpret_cast<const int2*>(rz_tab));
-                } else {
-                    orb_resize_coeff_kernel<<<vsb_div_up(nw + nh, 256), 256, 0, st>>>(cw, ch, nw, nh, rz_tab);
-                    VSB_LAUNCHED(ctx);
-                    orb_resize_kernel<<<dim3(vsb_div_up(nw, 128), vsb_div_up(nh, 8), zc), 256, 0, st>>>(cur, cur_stride, cp, cw, ch, dst, nw, nh, np, rz_tab);
-                }
-                VSB_LAUNCHED(ctx);
+                if ((rc = orb_resize_level(ctx, cur, cur_stride, cp, cw, ch, dst, nw, nh, np, zc, rz_tab, st))) return rc;
                 cur = dst; cur_stride = (int64_t)np * nh; cw = nw; ch = nh; cp = np;
             }
-            rc = orb_one_level(ctx, S, fast_scratch, cur, cur_stride, cp, cw, ch, zc, budget[l], fast_threshold, cap, lxy, lresp, langle, ldesc, ln, st,
-                               l > 0 ? cp : 0);
+            cudaStream_t sl = st;
+            if (lp) {                                             // this level's image is ready: its pipeline forks off
+                sl = ctx->orb_stream[l];
+                VSB_CUDA(ctx, cudaEventRecord(ctx->orb_ev_ready[l], st));
+                VSB_CUDA(ctx, cudaStreamWaitEvent(sl, ctx->orb_ev_ready[l], 0));
+            }
+            rc = orb_one_level(ctx, B.S, B.fast_scratch, cur, cur_stride, cp, cw, ch, zc, budget[l], fast_threshold, cap, B.lxy, B.lresp,
+                               B.langle, B.ldesc, B.ln, sl, l > 0 ? cp : 0);
             if (rc) return rc;
+            if (lp) {
+                VSB_CUDA(ctx, cudaEventRecord(ctx->orb_ev_done[l], sl));
+                continue;                                         // appended below, in level order
+            }
             ProfScope ps(ctx, VSB_K_ORB, st);
             orb_append_kernel<<<dim3(vsb_div_up(cap, 256), zc), 256, 0, st>>>(
-                lxy, lresp, langle, ldesc, ln, cap, scale, l, kp_xy + (size_t)z0 * cap * 2, kp_octave ? kp_octave + (size_t)z0 * cap : nullptr,
+                B.lxy, B.lresp, B.langle, B.ldesc, B.ln, cap, scale, l, kp_xy + (size_t)z0 * cap * 2, kp_octave ? kp_octave + (size_t)z0 * cap : nullptr,
                 kp_resp + (size_t)z0 * cap, kp_angle + (size_t)z0 * cap, desc ? desc + (size_t)z0 * cap * 32 : nullptr, n_kp + z0);
             VSB_LAUNCHED(ctx);
-            orb_advance_kernel<<<vsb_div_up(zc, 256), 256, 0, st>>>(n_kp + z0, ln, zc);
+            orb_advance_kernel<<<vsb_div_up(zc, 256), 256, 0, st>>>(n_kp + z0, B.ln, zc);
             VSB_LAUNCHED(ctx);
+        }
+        if (lp) {
+            for (int l = 0; l < nl; l++) {
+                OrbBlock& B = blk[l];
+                VSB_CUDA(ctx, cudaStreamWaitEvent(st, ctx->orb_ev_done[l], 0));
+                ProfScope ps(ctx, VSB_K_ORB, st);
+                orb_append_kernel<<<dim3(vsb_div_up(cap, 256), zc), 256, 0, st>>>(
+                    B.lxy, B.lresp, B.langle, B.ldesc, B.ln, cap, scales[l], l, kp_xy + (size_t)z0 * cap * 2, kp_octave ? kp_octave + (size_t)z0 * cap : nullptr,
+                    kp_resp + (size_t)z0 * cap, kp_angle + (size_t)z0 * cap, desc ? desc + (size_t)z0 * cap * 32 : nullptr, n_kp + z0);
+                VSB_LAUNCHED(ctx);
+                orb_advance_kernel<<<vsb_div_up(zc, 256), 256, 0, st>>>(n_kp + z0, B.ln, zc);
+                VSB_LAUNCHED(ctx);
+            }
         }
     }
     return VSB_OK;
@@ -911,11 +995,15 @@ extern "C" int vsb_orb_detect_compute_pyr(vsb_ctx_t* ctx, const uint8_t* img, in
     if (count == 0) return VSB_OK;
     // Every stage is one launch per chunk of frames and pyramid level, and the upper levels are small, so few large chunks keep
     // the machine filled where many small ones are launch-bound: the budget (orb_scratch_mb) allows 2000 752x480 frames at once.
-    const size_t one = vsb_orb_pyr_ws_bytes(w, h, 1, cap, desc != nullptr);
-    const size_t per_frame = orb_pyr_frame_bytes(w, h, cap, desc != nullptr);
-    size_t frames = (orb_scratch_budget(ctx) > one ? (orb_scratch_budget(ctx) - one) / per_frame : 0) + 1;
-    if (frames > (size_t)count) frames = (size_t)count;
-    const size_t bytes = vsb_orb_pyr_ws_bytes(w, h, (int)frames, cap, desc != nullptr);
+    if (nlevels < 1 || nlevels > 32 || !(scale_factor > 1.f)) return VSB_ERR_INVALID;
+    const size_t budget = orb_scratch_budget(ctx);
+    size_t bytes = vsb_orb_pyr_ws_bytes(w, h, count, cap, desc != nullptr, scale_factor, nlevels, budget);
+    if (bytes > budget) {                                         // as many frames as the budget holds (at least one)
+        const size_t one = vsb_orb_pyr_ws_bytes(w, h, 1, cap, desc != nullptr, scale_factor, nlevels, 0);
+        const size_t per_frame = orb_pyr_frame_bytes(w, h, cap, desc != nullptr);
+        const size_t frames = (budget > one ? (budget - one) / per_frame : 0) + 1;
+        bytes = vsb_orb_pyr_ws_bytes(w, h, (int)min(frames, (size_t)count), cap, desc != nullptr, scale_factor, nlevels, 0);
+    }
     void* ws = nullptr;
     int rc = vsb_scratch2_reserve(ctx, bytes, &ws);
     if (rc) return rc;

@@ -32,7 +32,7 @@ int vsb_gn_track(vsb_ctx_t* ctx, const uint8_t* cur_pyr, int64_t pair_stride_pix
                  const vsb_intr_t K[VSB_MAX_LEVELS], const float* pose_in, const vsb_gn_opts_t* opts, int pair0, int count,
                  int threads, float* pose_out, vsb_gn_trace_t* trace, int32_t* n_trace, unsigned long long* stats,
                  const uint8_t* cur_l0, int64_t l0_stride, void* stream);
-size_t vsb_orb_pyr_ws_bytes(int w, int h, int frames, int cap, int describe);
+size_t vsb_orb_pyr_ws_bytes(int w, int h, int frames, int cap, int describe, float scale_factor, int nlevels, size_t budget);
 int vsb_orb_detect_compute_pyr_ws(vsb_ctx_t* ctx, const uint8_t* img, int64_t img_stride, int pitch, int w, int h,
                                   int count, int nfeatures, float scale_factor, int nlevels, int fast_threshold, int cap,
                                   float* kp_xy, int32_t* kp_octave, float* kp_resp, float* kp_angle, uint8_t* desc,
@@ -389,8 +389,8 @@ static int track_sequence_orb_slot(vsb_tracker* t, Slot& s, const uint8_t* frame
     if (!s.orb_ws) {
         // as many frames as the slot holds, inside the context's budget for the detector ("orb_scratch_mb")
         const size_t budget = (size_t)(ctx->orb_scratch_mb > 0 ? ctx->orb_scratch_mb : 8192) << 20;
-        size_t bytes = vsb_orb_pyr_ws_bytes(c.w, c.h, c.max_pairs + 1, c.n_feat_max, 1);
-        const size_t floor_bytes = vsb_orb_pyr_ws_bytes(c.w, c.h, 1, c.n_feat_max, 1);
+        size_t bytes = vsb_orb_pyr_ws_bytes(c.w, c.h, c.max_pairs + 1, c.n_feat_max, 1, 1.2f, 8, budget);    // (one block per level if that fits)
+        const size_t floor_bytes = vsb_orb_pyr_ws_bytes(c.w, c.h, 1, c.n_feat_max, 1, 1.2f, 8, 0);
         if (bytes > budget) bytes = budget > floor_bytes ? budget : floor_bytes;
         VSB_CUDA(ctx, cudaMalloc(&s.orb_ws, bytes));
         s.orb_ws_bytes = bytes;
