@@ -14,6 +14,7 @@
 #define VISLAM_CAMERA_HPP_
 
 #include <functional>
+#include <memory>
 #include <vector>
 
 #include "vislam/Matcher.hpp"
@@ -139,6 +140,7 @@ public:
 protected:
     void match_with(Matcher& m, bool gpu_entry);
     void stats_accumulate();
+    std::shared_ptr<struct CameraOrbBuffers> orb_bufs;   // device outputs of detectOrbOnDevice, kept between frames (six allocations per frame otherwise)
 };
 
 // include/CameraGPU.hpp:18-40

@@ -104,6 +104,8 @@ void Camera::setFeatures(const vector<KeyPoint>& keypoints, const Mat& descripto
 // cv::ORB::create(orb_nfeatures)->detect / detectAndCompute on the device (vsb_orb_detect_compute_pyr): the level-0 image is
 // already in the frame's packed pyramid; results come back as cv::KeyPoint (pt, size = 31 * scale, angle, response, octave)
 // and a CV_8U n x 32 descriptor matrix, level by level in row-major order
+struct CameraOrbBuffers { vi::DevBuf xy, oct, resp, ang, desc, n; };
+
 int Camera::detectOrbOnDevice(bool describe) {
     Frame* f = currentFrame;
     if (!f || !f->pyr_on_device) throw std::logic_error("Camera::detectOrbOnDevice: call Update first");
@@ -114,7 +116,9 @@ int Camera::detectOrbOnDevice(bool describe) {
     f->descriptors = Mat();
     if (w <= 62 || h <= 62 || orb_nfeatures <= 0) return 0;        // the 31-pixel border filter leaves nothing
     const int cap = 2 * orb_nfeatures + 256;                         // ties at the selection thresholds can exceed n
-    vi::DevBuf d_xy, d_oct, d_resp, d_ang, d_desc, d_n;
+    if (!orb_bufs) orb_bufs = std::make_shared<CameraOrbBuffers>();
+    vi::DevBuf &d_xy = orb_bufs->xy, &d_oct = orb_bufs->oct, &d_resp = orb_bufs->resp, &d_ang = orb_bufs->ang, &d_desc = orb_bufs->desc,
+               &d_n = orb_bufs->n;
     float* xy = static_cast<float*>(d_xy.reserve((size_t)cap * 8));
     int32_t* oct = static_cast<int32_t*>(d_oct.reserve((size_t)cap * 4));
     float* resp = static_cast<float*>(d_resp.reserve((size_t)cap * 4));
