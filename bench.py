@@ -595,6 +595,15 @@ def leg_single_pair(g, steps):
            "cpu_baseline": {"value": best * 1e6, "unit": "us per frame pair", "cores": 1, "kind": "port",
                             "sample": "the same pair, oracle port, best of 3",
                             "max_abs_pose_diff_vs_gpu": float(np.abs(poses[0] - d_pose[0].cpu().numpy()).max())}}
+    # the same pair from IMAGES alone (informational): cv::ORB::create(1000) on the device for both frames (pyramid levels on
+    # separate streams for a batch this small), then match + GN
+    try:
+        frames2 = torch.stack([d["prev"][0], d["cur"][0]]).contiguous()
+        tr.track_sequence_orb(frames2, d["pose_prior"], nfeatures=cfg["n_feat"], stream=g.stream)
+        raw_ms = timed(g, lambda: tr.track_sequence_orb(frames2, d["pose_prior"], nfeatures=cfg["n_feat"], stream=g.stream), reps, 3)
+        out["from_raw_frames"] = {"value": raw_ms * 1e3, "unit": "us per frame pair (two frames through ORB on the device, then match + GN)"}
+    except Exception as e:      # informational
+        out["from_raw_frames"] = {"error": repr(e)}
     tr.close()
     return out
 
