@@ -147,8 +147,19 @@ fast_score_kernel(const uint8_t* __restrict__ img, long long img_stride, int pit
             const uint32_t up = s[ty + 6][wc], dn = s[ty][wc];            // ring positions 0 (0, +3) and 8 (0, -3)
             const uint32_t rt = __funnelshift_r(C, s[ty + 3][wc + 1], 24);                  // position 4 (+3, 0)
             const uint32_t lf = __funnelshift_r(s[ty + 3][wc - 1], C, 8);                   // position 12 (-3, 0)
-            const uint32_t b0 = gt7(up, hi), b4 = gt7(rt, hi), b8 = gt7(dn, hi), b12 = gt7(lf, hi);
-            const uint32_t d0 = gt7(lo, up), d4 = gt7(lo, rt), d8 = gt7(lo, dn), d12 = gt7(lo, lf);
+            // gt7 with the parts that depend on the centre only formed once: five instructions per ring position for both tests
+            const uint32_t nh = ~hi & 0x7f7f7f7fu, lm = (lo & 0x7f7f7f7fu) + 0x7f7f7f7fu;
+            uint32_t bq[4], dq[4];
+            const uint32_t ring4[4] = {up, rt, dn, lf};
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                const uint32_t m = ring4[q] & 0x7f7f7f7fu;
+                const uint32_t tb = m + nh, td = lm - m;               // (ring & 0x7f) + (~hi & 0x7f);  (lo & 0x7f) + (~ring & 0x7f)
+                asm("lop3.b32 %0, %1, %2, %3, 0xb2;" : "=r"(bq[q]) : "r"(ring4[q]), "r"(hi), "r"(tb));
+                asm("lop3.b32 %0, %1, %2, %3, 0xb2;" : "=r"(dq[q]) : "r"(lo), "r"(ring4[q]), "r"(td));
+            }
+            const uint32_t b0 = bq[0], b4 = bq[1], b8 = bq[2], b12 = bq[3];
+            const uint32_t d0 = dq[0], d4 = dq[1], d8 = dq[2], d12 = dq[3];
             const uint32_t bb = ((b0 | b8) & (b4 | b12));                  // (b0&b4)|(b4&b8)|(b8&b12)|(b12&b0)
             const uint32_t dd = ((d0 | d8) & (d4 | d12));
             cand |= ((bb | dd) & inside) >> (7 - half);
