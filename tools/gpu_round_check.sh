@@ -17,3 +17,10 @@ python tools/launch_table.py $OUT/launches.csv > $OUT/launches.txt
 ncu --set full --clock-control none --import-source on -k 'regex:gn_track|mx_bulk|candidates|pyramid16|mx_expand|match_filter' \
     -s 7 -c 7 -o $OUT/prof_step -f python tools/leg_once.py 1 1 > $OUT/ncu_f.log 2>&1
 tail -3 $OUT/pytest.log
+# the ORB front end (from raw frames): per-kernel table over two 500-frame calls, and one --set full capture of its main kernels
+python tools/orb_once.py > $OUT/orb_plain.log 2>&1 && \
+ncu --metrics gpu__time_duration.sum,smsp__inst_executed.sum,smsp__issue_active.avg.pct_of_peak_sustained_active,sm__warps_active.avg.pct_of_peak_sustained_active \
+    --clock-control none -k 'regex:orb_|fast_' --csv --log-file $OUT/orb_metrics.csv python tools/orb_once.py > $OUT/ncu_orb.log 2>&1
+python tools/orb_kernel_table.py $OUT/orb_metrics.csv > $OUT/orb_kernels.txt
+ncu --set full --clock-control none --import-source on -k 'regex:fast_score_kernel|orb_blur_kernel|orb_resize_tile_kernel|fast_count16_kernel|orb_describe_kernel' \
+    -s 5 -c 5 -o $OUT/orb_full -f python tools/orb_once.py > $OUT/ncu_orb_f.log 2>&1

@@ -1,3 +1,6 @@
+#!/usr/bin/env python
+"""Per-kernel table (time, share, warp instructions, issue-slot and warp occupancy) from an ncu --csv log of the ORB front end.
+usage: python tools/orb_kernel_table.py <orb_metrics.csv>"""
 import csv,collections,sys
 rows=list(csv.reader(open(sys.argv[1])))
 for i,r in enumerate(rows):
