@@ -812,7 +812,7 @@ def run_gpu(args, rank, world, local_rank):
             torch.cuda.synchronize(dev)
             h = leg["h"]
             trh = ctx.tracker(cfg["w"], cfg["h"], cfg["n_feat"], cfg["K"], n_cells=cfg["n_cells"],
-                              max_pairs=min(n_pairs, int(os.environ.get("VSB_BENCH_RAW_CHUNK", "600"))))
+                              max_pairs=min(n_pairs, int(os.environ.get("VSB_BENCH_RAW_CHUNK", "1000"))))
             r_pose = torch.zeros((n_pairs, 7), dtype=torch.float32).pin_memory()
             trh.track_sequence_orb_host(h["frames"], h["prior"], r_pose, nfeatures=cfg["n_feat"])          # warm-up (allocations)
             t0 = time.perf_counter()

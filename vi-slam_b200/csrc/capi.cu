@@ -56,7 +56,7 @@ extern "C" int vsb_ctx_create(int device, vsb_ctx_t** out) {
     c->gn_dedup = 1;
     c->gn_cluster = 1;
     c->gn_cluster_threads = 0;
-    c->orb_scratch_mb = 8192;
+    c->orb_scratch_mb = 32768;
     c->orb_impl = 0;
     c->orb_lp = 1;
     c->orb_lp_ready = 0;

@@ -60,7 +60,7 @@ struct vsb_ctx {
     int gn_cluster;   // gn_track.cu: 1 (default) = a batch of fewer pairs than 0.7 x the SMs gives each pair a cluster of 2 / 4 / 8 blocks (by batch size); 0 = never; 2 / 4 / 8 = that size always
     int gn_cluster_threads;   // threads per block of the cluster kernel: 0 (default) = by batch size, 256, 512
     int gn_tail;      // gn_track.cu: 1 (default) = pairs of the last partial wave run with more threads each, 0 = one launch
-    int orb_scratch_mb;   // ORB: scratch budget of one chunk of frames in MB (default 8192)
+    int orb_scratch_mb;   // ORB: scratch budget of one workspace in MB (default 32768: 2000 752x480 frames with one block of scratch per pyramid level)
     int fast_impl;    // FAST compaction: 0 (default) = 16 pixels per lane, suppression once (bit per pixel); 1 = 4 pixels per lane, suppression in both passes
     int orb_lp;       // ORB: 1 (default) = small batches run the pyramid levels on separate streams, 0 = one stream always
     cudaStream_t orb_stream[8];   // per-level streams / events of that form, created on first use

@@ -762,7 +762,7 @@ int orb_one_level(vsb_ctx_t* ctx, const OrbScratch& S, void* fast_scratch, const
 // Scratch budget of one chunk of frames.  Every stage is one launch per chunk and pyramid level, and the upper levels of
 // the scale pyramid are small, so few large chunks keep the machine filled where many small ones are launch-bound: 2000
 // 752x480 frames need 7.6 GB in one chunk (an HBM3e part has 180 GB), which the default budget allows.
-static size_t orb_scratch_budget(const vsb_ctx* ctx) { return (size_t)(ctx->orb_scratch_mb > 0 ? ctx->orb_scratch_mb : 8192) << 20; }
+static size_t orb_scratch_budget(const vsb_ctx* ctx) { return (size_t)(ctx->orb_scratch_mb > 0 ? ctx->orb_scratch_mb : 32768) << 20; }
 
 extern "C" int vsb_orb_detect_compute(vsb_ctx_t* ctx, const uint8_t* img, int64_t img_stride, int pitch, int w, int h, int count,
                                       int nfeatures, int fast_threshold, int cap, int32_t* kp_xy, float* kp_resp,

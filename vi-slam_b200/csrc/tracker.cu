@@ -388,7 +388,7 @@ static int track_sequence_orb_slot(vsb_tracker* t, Slot& s, const uint8_t* frame
     if (!s.orb_angle && (rc = dev_alloc(ctx, &s.orb_angle, per))) return rc;
     if (!s.orb_ws) {
         // as many frames as the slot holds, inside the context's budget for the detector ("orb_scratch_mb")
-        const size_t budget = (size_t)(ctx->orb_scratch_mb > 0 ? ctx->orb_scratch_mb : 8192) << 20;
+        const size_t budget = (size_t)(ctx->orb_scratch_mb > 0 ? ctx->orb_scratch_mb : 32768) << 20;
         size_t bytes = vsb_orb_pyr_ws_bytes(c.w, c.h, c.max_pairs + 1, c.n_feat_max, 1, 1.2f, 8, budget);    // (one block per level if that fits)
         const size_t floor_bytes = vsb_orb_pyr_ws_bytes(c.w, c.h, 1, c.n_feat_max, 1, 1.2f, 8, 0);
         if (bytes > budget) bytes = budget > floor_bytes ? budget : floor_bytes;
