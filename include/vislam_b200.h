@@ -53,6 +53,11 @@ int vsb_ctx_destroy(vsb_ctx_t* ctx);
  *   blocks that share the sweep and exchange partial sums through distributed shared memory; 0 = never, 2 / 4 / 8 = always
  *   that size.  "gn_cluster_threads" = (0: by batch size) | 256 | 512 threads per block of that kernel.
  * "gn_tail" = (1) the pairs of the last partial wave of a large batch get more threads each, 0 = one launch.
+ * ORB front end: "orb_scratch_mb" = budget of one detector workspace in MB ((32768): 2000 752x480 frames with one block of
+ *   scratch per pyramid level); "orb_lp" = (1) the pyramid levels of a batch run on separate streams when one block of scratch
+ *   per level fits the workspace, 0 = one stream; "orb_impl" / "fast_impl" = (0) bit masks that switch the PREVIOUS form of a
+ *   kernel back on for comparison (orb_impl 1 per-pixel resize, 2 per-warp sin / cos, 4 word-wise blur loader, 8 register
+ *   resize; fast_impl 1 per-word compaction and tile loader).
  * Results are identical for every setting. */
 int vsb_ctx_option(vsb_ctx_t* ctx, const char* name, int value);
 const char* vsb_last_cuda_error(vsb_ctx_t* ctx);
