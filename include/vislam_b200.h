@@ -45,14 +45,18 @@ const char* vsb_error_string(int status);
 int vsb_ctx_create(int device, vsb_ctx_t** ctx);
 int vsb_ctx_destroy(vsb_ctx_t* ctx);
 /* Tuning knobs (defaults in parentheses; the environment variables VSB_KNN_IMPL / VSB_GN_THREADS set the same at
- * context creation): "knn_impl" = 0 POPC kernel on the INT pipe, 1 tcgen05 tensor-core kernel, (2) tensor-core kernel
- * with the packed 16x2 epilogue; "gn_threads" = threads per frame pair of the GN solver, 64 / 128 / 256 / 512 / 1024 ((0) = chosen from the
+ * context creation): "knn_impl" = 0 POPC kernel on the INT pipe, 1 / 2 tcgen05 int8 kernels (2: packed 16x2 epilogue),
+ * 3 / 4 / 5 4-bit (mxf4) kernels (5: persistent, bulk-copied tiles), (6) chosen by the set size: 5 from 768 descriptors up, else 2; "gn_threads" = threads per frame pair of the GN solver, 64 / 128 / 256 / 512 / 1024 ((0) = chosen from the
  * batch size); "gn_impl" = (1) the tracker solves reference-mode problems with gn_track.cu, 0 = always gn_solve.cu;
  * "gn_stage_bytes" = shared-memory budget for the staged current-image level of gn_track.cu ((8192); 0 = none);
  * "gn_cluster" = (1) a batch of fewer frame pairs than 0.7 x the SMs gives each pair a thread-block cluster of 2 / 4 / 8
  *   blocks that share the sweep and exchange partial sums through distributed shared memory; 0 = never, 2 / 4 / 8 = always
  *   that size.  "gn_cluster_threads" = (0: by batch size) | 256 | 512 threads per block of that kernel.
  * "gn_tail" = (1) the pairs of the last partial wave of a large batch get more threads each, 0 = one launch.
+ * "gn_dedup" = (1) candidate points of the small levels are merged per distinct pixel with a multiplicity, 0 = one record per
+ *   point; "gn_variant" = (0) | 1 | 2 | 3 earlier forms of the tracker's solver kept for comparison;
+ *   "knn_l2_impl" = (1) float kNN as tensor-core distance GEMM + exact re-check, 0 = exact FP64 kernel; "pyr_impl" = (1)
+ *   register-blocked pyramid kernels, 0 = shared-memory tile kernel.
  * ORB front end: "orb_scratch_mb" = budget of one detector workspace in MB ((32768): 2000 752x480 frames with one block of
  *   scratch per pyramid level); "orb_lp" = (1) the pyramid levels of a batch run on separate streams when one block of scratch
  *   per level fits the workspace, 0 = one stream; "orb_impl" / "fast_impl" = (0) bit masks that switch the PREVIOUS form of a

@@ -110,3 +110,15 @@ def test_default_opts_are_the_reference_literals(vb):
     assert (o.first_lvl, o.last_lvl, o.max_iterations) == (3, 0, 10)              # VISystem.cpp:1117-1120
     assert o.epsilon == np.float32(0.001) and o.z_factor == np.float32(0.002)     # :1115, :1121
     assert o.weight_mode == 0 and o.sample_mode == 0                              # identity weights, round()
+
+
+def test_every_context_option_is_documented_in_the_header():
+    """vsb_ctx_option's names (csrc/capi.cu) all appear in the header's description of the tuning knobs."""
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    src = open(os.path.join(root, "vi-slam_b200", "csrc", "capi.cu")).read()
+    hdr = open(os.path.join(root, "include", "vislam_b200.h")).read()
+    names = sorted(set(re.findall(r'!strcmp\(name, "([a-z0-9_]+)"\)', src)))
+    assert len(names) >= 10
+    missing = [n for n in names if '"' + n + '"' not in hdr]
+    assert not missing, missing
