@@ -4,16 +4,17 @@
 // Semantics are cv::FAST(TYPE_9_16)'s, restated in oracle/fast.c and pinned there against cv2: corner test, score
 // (largest threshold that keeps the pixel a corner, minus one), strict 3x3 suppression, row-major output order.
 //
-//   fast_score_kernel   one 64x32 tile (+halo) per CTA in shared memory, 4 adjacent pixels x 2 rows per thread.  The flag pass is
-//                       the NECESSARY condition only — two neighbouring compass points of the ring both brighter or both
-//                       darker, 8 comparisons on packed bytes (SWAR) — and the few percent of pixels that pass get the full
-//                       arc test from their score (sliding-window minima; corner iff score + 1 > threshold), one thread per
-//                       candidate.  Writes score + 1 per pixel (0 = no corner): one byte read, one written.
-//   fast_count4_kernel  one warp per image row, 4 pixels per lane: 3x3 suppression on packed bytes, the row's corner count
-//                       (score rows are padded to a multiple of 4 bytes, so every width takes this path).
-//   fast_scan_kernel    exclusive scan of the row counts of each frame (row-major order needs the offsets).
-//   fast_write4_kernel  suppression again (cheaper than a flag image), warp scan, ordered write of (x, y, score) while the
-//                       slot is below the caller's capacity.
+//   fast_score_kernel    one 64x32 tile (+halo) per CTA in shared memory (one 16-byte vector per thread where the frame allows
+//                        it), 4 adjacent pixels x 2 rows per thread.  The flag pass is the NECESSARY condition only — two
+//                        neighbouring compass points of the ring both brighter or both darker, 8 comparisons on packed bytes
+//                        (SWAR) — and the pixels that pass (a few percent up to a fifth, by texture) are queued with one
+//                        shared-memory atomic per warp and get the full arc test from their score, one thread per candidate,
+//                        both polarities in the two 16-bit lanes of a register.  Writes score + 1 per pixel (0 = no corner).
+//   fast_count16_kernel  one warp per image row, 16 pixels per lane: the 3x3 suppression runs on the (few) corners only and leaves
+//                        one bit per pixel next to the row's corner count (score rows are padded to 16 bytes).
+//   fast_scan_kernel     exclusive scan of the row counts of each frame (row-major order needs the offsets).
+//   fast_write16_kernel  reads the bits, warp scan, ordered write of (x, y, score) while the slot is below the caller's capacity.
+//   fast_count4_kernel / fast_write4_kernel: the previous compaction (4 pixels per lane, suppression in both passes; fast_impl 1).
 #include "common.cuh"
 
 namespace {

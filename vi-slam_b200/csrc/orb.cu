@@ -9,6 +9,8 @@
 // key points come out in row-major (y, x) order (OpenCV's own order is whatever std::nth_element leaves).
 // All float arithmetic that OpenCV evaluates without fused multiply-add uses explicitly rounded intrinsics; the blur is the
 // float separable filter with the fused steps the oracle documents.
+// vsb_orb_detect_compute_pyr adds the scale pyramid (cv::ORB::create(n): 8 levels, factor 1.2; INTER_LINEAR_EXACT resize in 8.8
+// fixed point); when one block of scratch per level fits the workspace the levels run on separate streams.
 #include "common.cuh"
 
 size_t vsb_fast_scratch_bytes(int w, int h, int count);
